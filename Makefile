@@ -1,0 +1,21 @@
+# Builds the C-ABI CUDA library (sm_100a only) and nothing else.
+NVCC ?= nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall
+CSRC := torch_semantic_segmentation_b200/csrc
+SRCS := $(wildcard $(CSRC)/*.cu)
+OBJS := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
+LIB := torch_semantic_segmentation_b200/libtss_b200.so
+
+all: $(LIB)
+
+build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/tss_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
+
+clean:
+	rm -rf build $(LIB)
+.PHONY: all clean

@@ -1,0 +1,212 @@
+/* libtss_b200 -- C ABI of the B200 (sm_100a) kernels behind the Fast-SCNN / ContextNet
+ * hot path of torch_semantic_segmentation.
+ *
+ * The reference (bernardomig/torch_semantic_segmentation) is pure Python: it has no FFI
+ * of its own.  Each entry point below replaces the stock torch op that a reference
+ * call site dispatches to; the call site is cited on every declaration (paths relative
+ * to the reference root).  INTEGRATION.md shows the ctypes / torch.library binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions:
+ *  - plain pointers and sizes only; every buffer is device memory owned by the caller
+ *    (PyTorch's caching allocator); the library never allocates, frees or keeps them.
+ *  - activations are dense NHWC ("channels_last"): x[n][h][w][c]; `dtype` selects the
+ *    activation storage type (TSS_F32 or TSS_BF16); parameters, statistics and weight
+ *    gradients are always fp32; accumulation is always fp32.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *    synchronises, is re-entrant and thread-safe (autograd calls from its own thread).
+ *  - return value 0 = success; otherwise an error code, and tss_last_error() returns a
+ *    thread-local message.  Unsupported shapes are hard errors: there is no fallback.
+ *  - vector paths need C % 8 == 0 and 16-byte aligned base pointers; the 3-channel
+ *    input and the 19-class logits have their own entry points.
+ */
+#ifndef TSS_B200_H_
+#define TSS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSS_VERSION 100
+
+#define TSS_OK 0
+#define TSS_ERR_ARG 1
+#define TSS_ERR_CUDA 2
+
+#define TSS_F32 0
+#define TSS_BF16 1
+
+/* epilogue flags shared by the conv entry points */
+#define TSS_EPI_RELU 1      /* max(.,0) after affine (+residual) */
+
+int tss_version(void);
+const char* tss_last_error(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+uint64_t tss_launch_count(void);
+
+/* ---- depthwise 3x3 convolution, padding == dilation ("same" for stride 1) --------------
+ * replaces nn.Conv2d(C, C, 3, stride, padding=dilation, dilation, groups=C, bias=False)
+ * at fastscnn.py:179-180,191-192 and contextnet.py:157-160.
+ * x[N][Hi][Wi][C], w[C][3][3] fp32 (= the (C,1,3,3) parameter), y[N][Ho][Wo][C],
+ * Ho = (Hi-1)/stride+1.
+ * Epilogue: if scale/shift != NULL: y = y*scale[c]+shift[c] (folded eval-mode BatchNorm,
+ * fastscnn.py:181), then ReLU if flags&TSS_EPI_RELU.  If stats != NULL (training):
+ * stats[c] += sum(y), stats[C+c] += sum(y*y) over all pixels of the raw conv output
+ * (BatchNorm batch statistics, fp32 atomics). */
+int tss_dwconv3x3_fwd(const void* x, const float* w, void* y, int N, int Hi, int Wi, int C,
+                      int stride, int dilation, const float* scale, const float* shift,
+                      int flags, float* stats, int dtype, void* stream);
+/* grad wrt input: dx[N][Hi][Wi][C] from dy[N][Ho][Wo][C] (autograd of the above). */
+int tss_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int N, int Hi, int Wi, int C,
+                        int stride, int dilation, int dtype, void* stream);
+/* grad wrt weight: dw[C][3][3] (fp32) += sum_{n,ho,wo} x * dy  (warp-shuffle + block
+ * reduction, fp32 atomics).  dw must be zeroed (or hold a gradient to accumulate into). */
+int tss_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi, int C,
+                        int stride, int dilation, int dtype, void* stream);
+
+/* ---- pointwise (1x1) convolution = GEMM  y[M][Nc] = x[M][K] . w[Nc][K]^T -----------------
+ * replaces nn.Conv2d(K, Nc, 1[, bias]) at fastscnn.py:167-168,194,97,109-110,115 and
+ * contextnet.py:172-175,86.  x has row pitch ldx elements (>= K), y row pitch ldy.
+ * w is the fp32 (Nc,K,1,1) parameter.  Epilogue as for the depthwise conv, plus an
+ * optional residual res[M][Nc] (pitch ldr) added before the ReLU (fastscnn.py:158-161).
+ * `shift` alone (scale == NULL) is a bias (fastscnn.py:97).
+ * impl: 0 = SIMT fp32-accumulate reference-precision kernel (any dtype);
+ *       1 = tcgen05/TMEM/TMA tensor-core kernel (bf16 only, needs wp = bf16 packed weights
+ *           from tss_pack_weights_bf16). */
+int tss_pwconv_fwd(const void* x, const float* w, const void* wp, void* y, int64_t M, int K, int Nc,
+                   int64_t ldx, int64_t ldy, const float* scale, const float* shift,
+                   const void* res, int64_t ldr, int flags, float* stats, int impl,
+                   int dtype, void* stream);
+/* dx[M][K] = dy[M][Nc] . w[Nc][K]   (wpT = bf16 packed transpose for impl 1) */
+int tss_pwconv_dgrad(const void* dy, const float* w, const void* wpT, void* dx, int64_t M, int K,
+                     int Nc, int64_t lddy, int64_t lddx, int impl, int dtype, void* stream);
+/* dw[Nc][K] (fp32) += dy^T . x ; db[Nc] (fp32, may be NULL) += column sums of dy */
+int tss_pwconv_wgrad(const void* x, const void* dy, float* dw, float* db, int64_t M, int K, int Nc,
+                     int64_t ldx, int64_t lddy, int impl, int dtype, void* stream);
+/* bf16 copies of a (Nc,K) fp32 weight: wp[Nc][K] and wpT[K][Nc] (either may be NULL) */
+int tss_pack_weights_bf16(const float* w, void* wp, void* wpT, int Nc, int K, void* stream);
+
+/* ---- dense 3x3 convolution ---------------------------------------------------------------
+ * Stem: replaces nn.Conv2d(3, 32, 3, stride=2, padding=1, bias=False) at fastscnn.py:30 /
+ * contextnet.py:38,48.  x is the user's NCHW fp32 image batch (N,3,H,W) read in place
+ * (no layout/precision pre-pass); y[N][H/2][W/2][Cout] NHWC in `dtype`; w (Cout,3,3,3).
+ * Epilogue as above. */
+int tss_stem3x3s2_fwd(const float* x, const float* w, void* y, int N, int H, int W, int Cout,
+                      const float* scale, const float* shift, int flags, float* stats,
+                      int dtype, void* stream);
+int tss_stem3x3s2_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout,
+                        int dtype, void* stream);
+/* ---- BatchNorm (training) -----------------------------------------------------------------
+ * replaces nn.BatchNorm2d (+ nn.ReLU / F.relu / residual add) at fastscnn.py:169-172,
+ * 181-184,193-198,158-161,89.
+ * finalize: from stats[2C] (sum, sum of squares over `count` values per channel) compute
+ * mean[c], rstd[c] = 1/sqrt(var_biased+eps), scale = gamma*rstd, shift = beta-mean*scale and
+ * update running_mean/var (momentum, unbiased var) and num_batches_tracked (int64, may be NULL). */
+int tss_bn_finalize(const float* stats, int64_t count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                    float momentum, float eps, float* scale, float* shift, float* mean,
+                    float* rstd, int C, void* stream);
+/* eval mode: scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale */
+int tss_bn_fold(const float* gamma, const float* beta, const float* running_mean,
+                const float* running_var, float eps, float* scale, float* shift, int C,
+                void* stream);
+/* z = act( y*scale+shift [+ y2*scale2+shift2] [+ res] ), rows of C channels, pitches in elements */
+int tss_bn_apply(const void* y, const float* scale, const float* shift, const void* y2,
+                 const float* scale2, const float* shift2, const void* res, void* z, int64_t M,
+                 int C, int64_t ldy, int64_t ldy2, int64_t ldr, int64_t ldz, int flags, int dtype,
+                 void* stream);
+/* backward, pass 1: g = dz * (z > 0 if relu); sums[c] += sum g ; sums[C+c] += sum g*xhat,
+ * xhat = (y-mean)*rstd.  z may be NULL when there was no ReLU. */
+int tss_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean,
+                      const float* rstd, float* sums, int64_t M, int C, int64_t lddz, int64_t ldz,
+                      int64_t ldy, int flags, int dtype, void* stream);
+/* backward, pass 2: dy = gamma*rstd*(g - sums[c]/M - xhat*sums[C+c]/M); optional dres = g.
+ * dgamma[c] += sums[C+c], dbeta[c] += sums[c] (done by block 0; may be NULL). */
+int tss_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean,
+                     const float* rstd, const float* gamma, const float* sums, void* dy, void* dres,
+                     float* dgamma, float* dbeta, int64_t M, int C, int64_t lddz, int64_t ldz,
+                     int64_t ldy, int64_t lddy, int64_t lddres, int flags, int dtype, void* stream);
+/* g = dz * (z > 0): ReLU backward alone (fusion add, eval-free paths) */
+int tss_relu_bwd(const void* dz, const void* z, void* g, int64_t M, int C, int64_t lddz, int64_t ldz,
+                 int64_t ldg, int dtype, void* stream);
+/* out = a + b (residual gradient accumulation), rows of C channels */
+int tss_add(const void* a, const void* b, void* out, int64_t M, int C, int64_t lda, int64_t ldb,
+            int64_t ldo, int dtype, void* stream);
+/* strided row copy: dst[m][0..C) = src[m][0..C) */
+int tss_copy_rows(const void* src, void* dst, int64_t M, int C, int64_t lds, int64_t ldd, int dtype,
+                  void* stream);
+
+/* ---- pyramid pooling ------------------------------------------------------------------------
+ * replaces the four nn.AdaptiveAvgPool2d(bin) of fastscnn.py:108 in ONE pass: windows
+ * [floor(i*H/b), ceil((i+1)*H/b)).  out is the concatenation over bins of [N][b*b][C]
+ * blocks (bin i starts at element N*C*sum_{j<i} b_j^2), so each bin is a plain row matrix
+ * for the 1x1 convolution that follows (fastscnn.py:109-110). */
+int tss_adaptive_pool_fwd(const void* x, void* out, int N, int H, int W, int C, const int* bins,
+                          int nbins, int dtype, void* stream);
+int tss_adaptive_pool_bwd(const void* dout, void* dx, int N, int H, int W, int C, const int* bins,
+                          int nbins, int accumulate, int dtype, void* stream);
+
+/* ---- bilinear resize, align_corners=True -------------------------------------------------------
+ * replaces F.interpolate(..., mode='bilinear', align_corners=True) / nn.UpsamplingBilinear2d at
+ * fastscnn.py:74,119-120 and contextnet.py:119-121.  NHWC, C % 8 == 0, channel pitches ldx/ldy
+ * so that the result can be written straight into the concat buffer of fastscnn.py:122. */
+int tss_bilinear_fwd(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                     int64_t ldx, int64_t ldy, int dtype, void* stream);
+int tss_bilinear_bwd(const void* dy, void* dx, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                     int64_t lddy, int64_t lddx, int dtype, void* stream);
+/* Final x8 up-sampling of the class scores (fastscnn.py:63-64, contextnet.py:74-76):
+ * in NHWC x[N][Hi][Wi][ldx] (C = 19 classes in a pitch of ldx >= C, any C <= 64) -> out NCHW
+ * y[N][C][Ho][Wo] (the layout the reference returns), Wo % 8 == 0. */
+int tss_upsample_logits_fwd(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                            int64_t ldx, int dtype, void* stream);
+/* backward: dx32[N][Hi][Wi][lddx] (fp32, zeroed by the caller) += U^T dy (dy NCHW) */
+int tss_upsample_logits_bwd(const void* dy, float* dx32, int N, int Hi, int Wi, int Ho, int Wo,
+                            int C, int64_t lddx, int dtype, void* stream);
+/* ContextNet input shrink (contextnet.py:65-67): NCHW fp32 (N,3,H,W) -> NCHW fp32 (N,3,Ho,Wo) */
+int tss_bilinear_nchw_f32(const float* x, float* y, int NC, int Hi, int Wi, int Ho, int Wo,
+                          void* stream);
+/* dst (dtype) = src (fp32), n elements (n % 8 == 0) */
+int tss_cast_from_f32(const float* src, void* dst, int64_t n, int dtype, void* stream);
+
+/* ---- softmax cross-entropy with ignore_index ------------------------------------------------------
+ * replaces nn.CrossEntropyLoss(ignore_index=255) (scripts/train_fastscnn.py:132) and the
+ * F.cross_entropy(reduction='none') inside losses/ohem_loss.py:11-12.
+ * logits NCHW [N][C][HW] (C <= 32, HW % 4 == 0), target int64 [N][HW].
+ * count_valid: nvalid[0] = #(target != ignore_index).
+ * fwd: ONE pass computes per-pixel loss, the loss sum (loss_sum[0] += , fp64) and, if
+ * dlogits != NULL, the gradient of the MEAN loss: (softmax - onehot)/nvalid[0] (0 at ignored
+ * pixels).  pixel_loss (fp32 [N][HW], may be NULL) receives the reduction='none' values. */
+int tss_ce_count_valid(const int64_t* target, int64_t n, int64_t ignore_index, int64_t* nvalid,
+                       void* stream);
+int tss_ce_fwd(const void* logits, const int64_t* target, int N, int C, int64_t HW,
+               int64_t ignore_index, const int64_t* nvalid, double* loss_sum, float* pixel_loss,
+               void* dlogits, int dtype, void* stream);
+/* loss[0] = loss_sum[0] / nvalid[0]  (NaN if no valid pixel, like the reference) */
+int tss_ce_finalize(const double* loss_sum, const int64_t* nvalid, float* loss, void* stream);
+/* x *= s[0] (device scalar), n elements: non-unit upstream gradient of the loss */
+int tss_scale_inplace(void* x, const float* s, int64_t n, int dtype, void* stream);
+
+/* ---- confusion matrix --------------------------------------------------------------------------
+ * replaces ignite ConfusionMatrix.update x4 (engine.py:65-72): cm[t][p] += 1 for 0<=t<C.
+ * cm is int64 [C][C].  Warp-aggregated shared-memory atomics, one global atomic per bin per CTA. */
+int tss_confusion_from_labels(const int64_t* pred, const int64_t* target, int64_t n, int C,
+                              int64_t* cm, void* stream);
+/* same, with the argmax over the class planes of NCHW logits fused (ties -> lowest index,
+ * NaN = max, like torch.argmax).  If pred_out != NULL the int64 argmax map is written too. */
+int tss_confusion_from_logits(const void* logits, const int64_t* target, int N, int C, int64_t HW,
+                              int64_t* cm, int64_t* pred_out, int dtype, void* stream);
+
+/* ---- optimizer ---------------------------------------------------------------------------------
+ * torch.optim.AdamW (scripts/train_fastscnn.py:125-129) over ONE flat fp32 parameter arena.
+ * hyper (device, fp32[8]): lr, beta1, beta2, eps, weight_decay, step (incremented by the call),
+ * bias_correction1, bias_correction2 (written by the call). */
+int tss_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float* hyper,
+                   float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSS_B200_H_ */

@@ -1,0 +1,281 @@
+"""CPU emulation of the C ABI for HOST-LOGIC tests only (tests/ infrastructure).
+
+The product has no CPU path.  This object is installed with ``_lib.set_backend`` by the
+``fake_backend`` fixture so that the Python side (layout/pitch bookkeeping, autograd
+formulas, module wiring, engine, optimizer arena, data-parallel plumbing) can be exercised
+on a box without a GPU.  Each entry point is emulated with stock torch CPU ops on the very
+tensors (views) the real backend would turn into pointers, with the same in-place /
+accumulate semantics as the kernels documented in ``include/tss_b200.h``.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch.nn import grad as nngrad
+
+RELU = 1
+
+
+def _epilogue(y, scale, shift, res, flags):
+    if shift is not None:
+        s = scale.view(1, -1, 1, 1) if scale is not None else 1.0
+        y = y * s + shift.view(1, -1, 1, 1)
+    if res is not None:
+        y = y + res.float()
+    if flags & RELU:
+        y = y.clamp_min(0)
+    return y
+
+
+def _stats(stats, y):
+    if stats is not None:
+        C = y.shape[1]
+        stats[:C] += y.sum(dim=(0, 2, 3))
+        stats[C:] += (y * y).sum(dim=(0, 2, 3))
+
+
+class FakeBackend:
+    def __init__(self):
+        self.launches = 0
+
+    def call(self, name, k):
+        self.launches += 1
+        return getattr(self, name)(**k)
+
+    # ---------------------------------------------------------------- depthwise
+    def tss_dwconv3x3_fwd(self, x, w, y, N, Hi, Wi, C, stride, dilation, scale, shift, flags, stats, dtype):
+        assert x.shape == (N, C, Hi, Wi)
+        raw = F.conv2d(x.float(), w.view(C, 1, 3, 3), None, stride, dilation, dilation, C)
+        _stats(stats, raw)
+        y.copy_(_epilogue(raw, scale, shift, None, flags))
+        return 0
+
+    def tss_dwconv3x3_dgrad(self, dy, w, dx, N, Hi, Wi, C, stride, dilation, dtype):
+        dx.copy_(nngrad.conv2d_input((N, C, Hi, Wi), w.view(C, 1, 3, 3), dy.float(), stride, dilation, dilation, C))
+        return 0
+
+    def tss_dwconv3x3_wgrad(self, x, dy, dw, N, Hi, Wi, C, stride, dilation, dtype):
+        dw += nngrad.conv2d_weight(x.float(), (C, 1, 3, 3), dy.float(), stride, dilation, dilation, C).view_as(dw)
+        return 0
+
+    # ---------------------------------------------------------------- pointwise
+    def tss_pwconv_fwd(self, x, w, wp, y, M, K, Nc, ldx, ldy, scale, shift, res, ldr, flags, stats, impl, dtype):
+        assert x.shape[1] == K and y.shape[1] == Nc and x.shape[0] * x.shape[2] * x.shape[3] == M
+        assert x.stride(3) == ldx or x.shape[3] == 1
+        raw = F.conv2d(x.float(), w.view(Nc, K, 1, 1).float())
+        _stats(stats, raw)
+        y.copy_(_epilogue(raw, scale, shift, res, flags))
+        return 0
+
+    def tss_pwconv_dgrad(self, dy, w, wpT, dx, M, K, Nc, lddy, lddx, impl, dtype):
+        dx.copy_(F.conv2d(dy.float(), w.view(Nc, K).t().reshape(K, Nc, 1, 1)))
+        return 0
+
+    def tss_pwconv_wgrad(self, x, dy, dw, db, M, K, Nc, ldx, lddy, impl, dtype):
+        g = dy.float().permute(1, 0, 2, 3).reshape(Nc, -1)
+        a = x.float().permute(1, 0, 2, 3).reshape(K, -1)
+        dw += (g @ a.t()).view_as(dw)
+        if db is not None:
+            db += g.sum(1)
+        return 0
+
+    def tss_pack_weights_bf16(self, w, wp, wpT, Nc, K):
+        if wp is not None:
+            wp.copy_(w.view(Nc, K))
+        if wpT is not None:
+            wpT.copy_(w.view(Nc, K).t())
+        return 0
+
+    # ---------------------------------------------------------------- stem
+    def tss_stem3x3s2_fwd(self, x, w, y, N, H, W, Cout, scale, shift, flags, stats, dtype):
+        raw = F.conv2d(x, w, None, 2, 1)
+        _stats(stats, raw)
+        y.copy_(_epilogue(raw, scale, shift, None, flags))
+        return 0
+
+    def tss_stem3x3s2_wgrad(self, x, dy, dw, N, H, W, Cout, dtype):
+        dw += nngrad.conv2d_weight(x, dw.shape, dy.float(), 2, 1)
+        return 0
+
+    # ---------------------------------------------------------------- batch norm
+    def tss_bn_finalize(self, stats, count, gamma, beta, running_mean, running_var, num_batches_tracked,
+                        momentum, eps, scale, shift, mean, rstd, C):
+        if count <= 1:
+            raise RuntimeError('tss_bn_finalize failed (1): Expected more than 1 value per channel when training')
+        m = stats[:C].double() / count
+        var = (stats[C:].double() / count - m * m).clamp_min(0)
+        r = 1.0 / torch.sqrt(var + eps)
+        mean.copy_(m)
+        rstd.copy_(r)
+        scale.copy_(gamma.detach() * rstd)
+        shift.copy_(beta.detach() - mean * scale)
+        if running_mean is not None:
+            running_mean.mul_(1 - momentum).add_(momentum * m.float())
+            running_var.mul_(1 - momentum).add_(momentum * (var * count / (count - 1)).float())
+        if num_batches_tracked is not None:
+            num_batches_tracked += 1
+        return 0
+
+    def tss_bn_fold(self, gamma, beta, running_mean, running_var, eps, scale, shift, C):
+        scale.copy_(gamma.detach() / torch.sqrt(running_var + eps))
+        shift.copy_(beta.detach() - running_mean * scale)
+        return 0
+
+    def tss_bn_apply(self, y, scale, shift, y2, scale2, shift2, res, z, M, C, ldy, ldy2, ldr, ldz, flags, dtype):
+        v = y.float() * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+        if y2 is not None:
+            v = v + y2.float() * scale2.view(1, -1, 1, 1) + shift2.view(1, -1, 1, 1)
+        if res is not None:
+            v = v + res.float()
+        if flags & RELU:
+            v = v.clamp_min(0)
+        z.copy_(v)
+        return 0
+
+    @staticmethod
+    def _g(dz, z, flags):
+        g = dz.float()
+        if flags & RELU:
+            g = g * (z.float() > 0)
+        return g
+
+    def tss_bn_bwd_reduce(self, dz, z, y, mean, rstd, sums, M, C, lddz, ldz, ldy, flags, dtype):
+        g = self._g(dz, z, flags)
+        xh = (y.float() - mean.view(1, -1, 1, 1)) * rstd.view(1, -1, 1, 1)
+        sums[:C] += g.sum(dim=(0, 2, 3))
+        sums[C:] += (g * xh).sum(dim=(0, 2, 3))
+        return 0
+
+    def tss_bn_bwd_apply(self, dz, z, y, mean, rstd, gamma, sums, dy, dres, dgamma, dbeta, M, C, lddz, ldz,
+                         ldy, lddy, lddres, flags, dtype):
+        g = self._g(dz, z, flags)
+        v = lambda t: t.detach().view(1, -1, 1, 1)
+        xh = (y.float() - v(mean)) * v(rstd)
+        dy.copy_(v(gamma) * v(rstd) * (g - v(sums[:C]) / M - xh * v(sums[C:]) / M))
+        if dres is not None:
+            dres.copy_(g)
+        if dbeta is not None:
+            dbeta += sums[:C]
+        if dgamma is not None:
+            dgamma += sums[C:]
+        return 0
+
+    def tss_relu_bwd(self, dz, z, g, M, C, lddz, ldz, ldg, dtype):
+        g.copy_(dz.float() * (z.float() > 0))
+        return 0
+
+    def tss_add(self, a, b, out, M, C, lda, ldb, ldo, dtype):
+        out.copy_(a.float() + b.float())
+        return 0
+
+    def tss_copy_rows(self, src, dst, M, C, lds, ldd, dtype):
+        dst.copy_(src)
+        return 0
+
+    def tss_cast_from_f32(self, src, dst, n, dtype):
+        dst.copy_(src)
+        return 0
+
+    def tss_scale_inplace(self, x, s, n, dtype):
+        x.copy_(x.float() * s)
+        return 0
+
+    # ---------------------------------------------------------------- pooling / resize
+    def tss_adaptive_pool_fwd(self, x, out, N, H, W, C, bins, nbins, dtype):
+        off = 0
+        for b in bins.values:
+            p = F.adaptive_avg_pool2d(x.float(), b).permute(0, 2, 3, 1).reshape(N * b * b, C)
+            out[off:off + N * b * b].copy_(p)
+            off += N * b * b
+        return 0
+
+    def tss_adaptive_pool_bwd(self, dout, dx, N, H, W, C, bins, nbins, accumulate, dtype):
+        acc = dx.float().clone() if accumulate else torch.zeros(dx.shape)
+        off = 0
+        for b in bins.values:
+            g = dout[off:off + N * b * b].float().view(N, b, b, C).permute(0, 3, 1, 2)
+            xx = torch.zeros(N, C, H, W, requires_grad=True)
+            with torch.enable_grad():
+                F.adaptive_avg_pool2d(xx, b).backward(g)
+            acc = acc + xx.grad
+            off += N * b * b
+        dx.copy_(acc)
+        return 0
+
+    def tss_bilinear_fwd(self, x, y, N, Hi, Wi, Ho, Wo, C, ldx, ldy, dtype):
+        y.copy_(F.interpolate(x.float(), size=(Ho, Wo), mode='bilinear', align_corners=True))
+        return 0
+
+    def tss_bilinear_bwd(self, dy, dx, N, Hi, Wi, Ho, Wo, C, lddy, lddx, dtype):
+        xx = torch.zeros(N, C, Hi, Wi, requires_grad=True)
+        with torch.enable_grad():
+            F.interpolate(xx, size=(Ho, Wo), mode='bilinear', align_corners=True).backward(dy.float())
+        dx.copy_(xx.grad)
+        return 0
+
+    def tss_upsample_logits_fwd(self, x, y, N, Hi, Wi, Ho, Wo, C, ldx, dtype):
+        y.copy_(F.interpolate(x.float(), size=(Ho, Wo), mode='bilinear', align_corners=True))
+        return 0
+
+    def tss_upsample_logits_bwd(self, dy, dx32, N, Hi, Wi, Ho, Wo, C, lddx, dtype):
+        xx = torch.zeros(N, C, Hi, Wi, requires_grad=True)
+        with torch.enable_grad():
+            F.interpolate(xx, size=(Ho, Wo), mode='bilinear', align_corners=True).backward(dy.float())
+        dx32[..., :C] += xx.grad.permute(0, 2, 3, 1)
+        return 0
+
+    def tss_bilinear_nchw_f32(self, x, y, NC, Hi, Wi, Ho, Wo):
+        y.copy_(F.interpolate(x, size=(Ho, Wo), mode='bilinear', align_corners=True))
+        return 0
+
+    # ---------------------------------------------------------------- loss / metrics
+    def tss_ce_count_valid(self, target, n, ignore_index, nvalid):
+        nvalid.fill_(int((target != ignore_index).sum()))
+        return 0
+
+    def tss_ce_fwd(self, logits, target, N, C, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, dtype):
+        x = logits.float()
+        logp = x.log_softmax(1)
+        valid = target != ignore_index
+        t = torch.where(valid, target, torch.zeros_like(target))
+        nll = -logp.gather(1, t.unsqueeze(1)).squeeze(1) * valid
+        if loss_sum is not None:
+            loss_sum += nll.double().sum()
+        if pixel_loss is not None:
+            pixel_loss.copy_(nll)
+        if dlogits is not None:
+            p = logp.exp()
+            p.scatter_add_(1, t.unsqueeze(1), -torch.ones_like(p[:, :1]))
+            nv = float(nvalid.item())
+            dlogits.copy_(p * valid.unsqueeze(1) / nv if nv > 0 else torch.zeros_like(p))
+        return 0
+
+    def tss_ce_finalize(self, loss_sum, nvalid, loss):
+        nv = float(nvalid.item())
+        loss.fill_(float(loss_sum.item()) / nv if nv > 0 else float('nan'))
+        return 0
+
+    def tss_confusion_from_labels(self, pred, target, n, C, cm):
+        m = (target >= 0) & (target < C) & (pred >= 0) & (pred < C)
+        cm += torch.bincount(C * target[m] + pred[m], minlength=C * C).view(C, C)
+        return 0
+
+    def tss_confusion_from_logits(self, logits, target, N, C, HW, cm, pred_out, dtype):
+        x = logits.float()
+        pred = torch.where(torch.isnan(x), torch.full_like(x, math.inf), x).argmax(1)
+        if pred_out is not None:
+            pred_out.copy_(pred)
+        return self.tss_confusion_from_labels(pred.reshape(-1), target.reshape(-1), pred.numel(), C, cm)
+
+    def tss_adamw_step(self, p, g, m, v, n, hyper, grad_scale):
+        lr, b1, b2, eps, wd = [float(hyper[i]) for i in range(5)]
+        step = float(hyper[5]) + 1
+        hyper[5] = step
+        bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+        hyper[6], hyper[7] = 1 / bc1, math.sqrt(bc2)
+        gr = g * grad_scale
+        p.mul_(1 - lr * wd)
+        m.lerp_(gr, 1 - b1)
+        v.mul_(b2).addcmul_(gr, gr, value=1 - b2)
+        p.addcdiv_(m, v.sqrt() / math.sqrt(bc2) + eps, value=-lr / bc1)
+        return 0

@@ -1,0 +1,132 @@
+"""Host-side logic (layout bookkeeping, autograd formulas, module tree, engine) exercised on
+CPU through tests/fake_backend.py.  The kernels themselves are tested on the GPU (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import confusion as o_cm
+from oracle.golden_inputs import eval_input, train_batch
+from oracle.init_state import init_state
+from oracle.train_step import AdamW as OracleAdamW, loss_and_grads, model_forward, split_state, train_step
+from torch_semantic_segmentation_b200 import ops
+from torch_semantic_segmentation_b200.engine import (create_segmentation_evaluator,
+                                                     create_segmentation_trainer)
+from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+from torch_semantic_segmentation_b200.models import fastscnn
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def _no_dropout(model):
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    return model
+
+
+def test_geom_and_pitch():
+    t = ops.empty_nhwc(2, 19, 4, 6, torch.float32, 'cpu', pitch=32)
+    assert ops.geom(t) == (2, 19, 4, 6, 32)
+    assert ops.geom(torch.zeros(2, 8, 4, 6)) is None                    # NCHW-contiguous is not NHWC
+    assert ops.geom(ops.as_nhwc(torch.zeros(2, 8, 4, 6))) == (2, 8, 4, 6, 8)
+    assert ops.geom(ops.empty_nhwc(3, 16, 1, 1, torch.float32, 'cpu')) == (3, 16, 1, 1, 16)
+    cat = ops.empty_nhwc(2, 256, 3, 5, torch.float32, 'cpu')
+    assert ops.geom(cat[:, 128:160]) == (2, 32, 3, 5, 256)
+
+
+def test_state_dict_is_the_reference_layout(fake_backend):
+    torch.manual_seed(0)
+    model = fastscnn(3, 19)
+    want = init_state('fastscnn', 0)
+    got = model.state_dict()
+    assert list(got.keys()) == list(want.keys())
+    for k in want:
+        assert got[k].shape == want[k].shape and torch.equal(got[k], want[k]), k
+    model.load_state_dict(want, strict=True)
+
+
+def test_eval_forward_matches_oracle(fake_backend):
+    torch.manual_seed(0)
+    model = fastscnn(3, 19).eval()
+    x = eval_input('fastscnn')
+    with torch.no_grad():
+        out = model(x)
+    assert out.shape == (1, 19, 160, 224) and out.is_contiguous()
+    ref = model_forward('fastscnn', init_state('fastscnn', 0), x, False)
+    assert rel(out, ref) < 1e-5
+
+
+def test_forward_hooks_fire_on_downsample_and_features(fake_backend):
+    torch.manual_seed(0)
+    model = fastscnn(3, 19).eval()
+    seen = {}
+    model.downsample.register_forward_hook(lambda m, i, o: seen.__setitem__('d', o.shape))
+    model.features.register_forward_hook(lambda m, i, o: seen.__setitem__('f', o.shape))
+    with torch.no_grad():
+        model(torch.randn(1, 3, 64, 96))
+    assert seen == {'d': (1, 64, 8, 12), 'f': (1, 128, 2, 3)}
+
+
+def test_train_step_matches_oracle(fake_backend):
+    torch.manual_seed(0)
+    model = _no_dropout(fastscnn(3, 19)).train()
+    x, y = train_batch('fastscnn')
+    out = model(x)
+    loss = CrossEntropyLoss(ignore_index=255)(out, y)
+    loss.backward()
+    sd = split_state(init_state('fastscnn', 0))
+    ref_loss, ref_logits, ref_grads = loss_and_grads('fastscnn', sd, x, y, dropout_mask=1.0)
+    assert abs(float(loss) - float(ref_loss)) < 1e-5
+    assert rel(out, ref_logits) < 1e-4
+    params = dict(model.named_parameters())
+    # the head is well conditioned; deep layers suffer ReLU-mask flips (the fp32 reference itself is
+    # ~1e-2 away from an fp64 run there), so they get a looser bound
+    for k in ('classifier.3.weight', 'classifier.3.bias', 'classifier.1.3.weight'):
+        assert rel(params[k].grad, ref_grads[k]) < 1e-4, k
+    for k, p in params.items():
+        if k.endswith('.0.weight') or k.endswith('.2.weight'):
+            assert rel(p.grad, ref_grads[k]) < 3e-2, k
+    msd = model.state_dict()
+    for k in sd:
+        if 'running' in k:
+            assert (msd[k] - sd[k]).abs().max() < 1e-5, k
+        if 'num_batches' in k:
+            assert int(msd[k]) == 1
+
+
+def test_batch_of_one_is_rejected_in_training_like_the_reference(fake_backend):
+    model = fastscnn(3, 19).train()
+    with pytest.raises(RuntimeError, match='more than 1 value per channel'):
+        model(torch.randn(1, 3, 32, 32))
+
+
+def test_trainer_and_evaluator(fake_backend):
+    torch.manual_seed(0)
+    model = _no_dropout(fastscnn(3, 19))
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    trainer = create_segmentation_trainer(model, opt, CrossEntropyLoss(ignore_index=255), 'cpu', logging=False)
+    x, y = train_batch('fastscnn')
+    state = trainer.run([(x, y)] * 2, max_epochs=1)
+    assert state.iteration == 2 and np.isfinite(state.output) and 'loss' in state.metrics and state.metrics['lr'] == 1e-3
+
+    sd = split_state(init_state('fastscnn', 0))
+    oopt = OracleAdamW(sd, lr=1e-3, weight_decay=1e-5)
+    l1 = train_step('fastscnn', sd, oopt, x, y, dropout_mask=1.0)
+    l2 = train_step('fastscnn', sd, oopt, x, y, dropout_mask=1.0)
+    assert abs(state.output - l2) < 2e-3 * abs(l2), (state.output, l1, l2)
+
+    evaluator = create_segmentation_evaluator(model, 'cpu', num_classes=19, loss_fn=CrossEntropyLoss(ignore_index=255))
+    es = evaluator.run([(x, y)])
+    with torch.no_grad():
+        logits = model.eval()(x)
+    want = o_cm.confusion_matrix(o_cm.argmax_classes(logits.numpy()), y.numpy(), 19)
+    assert (es.metrics['confusion_matrix'].numpy() == want).all()
+    met = o_cm.metrics(want)
+    assert float(es.metrics['miou']) == met['miou']
+    np.testing.assert_array_equal(es.metrics['iou'].numpy(), met['iou'])
+    assert float(es.metrics['accuracy']) == met['accuracy']
+    np.testing.assert_array_equal(es.metrics['dice'].numpy(), met['dice'])
+    assert np.isfinite(es.metrics['loss'])

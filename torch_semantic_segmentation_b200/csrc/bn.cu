@@ -1,0 +1,400 @@
+// BatchNorm (training statistics / apply / backward) and the small NHWC elementwise
+// kernels around it.  All of them are pure HBM streaming: 8 channels per thread
+// (128-bit bf16 accesses), grid-stride over (row, channel-group) items, rows may be
+// pitched (ld*) so that slices of a concat buffer can be read and written in place.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int stream_grid(int64_t items, int per_sm = 8) {
+    int64_t want = ceil_div64(items, kThreads);
+    int64_t cap = (int64_t)tss_num_sms() * per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+__device__ __forceinline__ void ldg8f(const float* __restrict__ p, float (&v)[8]) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// ------------------------------------------------------------------ finalize / fold --
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, double inv_count, double unbias,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   int64_t* __restrict__ nbt, float momentum, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt != nullptr) *nbt += 1;
+    if (c >= C) return;
+    const double mean = (double)stats[c] * inv_count;
+    double var = (double)stats[C + c] * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma != nullptr ? gamma[c] : 1.f;
+    const float b = beta != nullptr ? beta[c] : 0.f;
+    const float sc = g * rstd;
+    scale[c] = sc;
+    shift[c] = b - (float)mean * sc;
+    mean_out[c] = (float)mean;
+    rstd_out[c] = rstd;
+    if (running_mean != nullptr) {
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * unbias);
+    }
+}
+
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sc = (gamma != nullptr ? gamma[c] : 1.f) / sqrtf(rv[c] + eps);
+    scale[c] = sc;
+    shift[c] = (beta != nullptr ? beta[c] : 0.f) - rm[c] * sc;
+}
+
+// ------------------------------------------------------------------ apply -------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                const T* __restrict__ y2, const float* __restrict__ scale2, const float* __restrict__ shift2,
+                const T* __restrict__ res, T* __restrict__ z, int64_t M, int C,
+                int64_t ldy, int64_t ldy2, int64_t ldr, int64_t ldz, int relu) {
+    const int CG = C >> 3;
+    const int64_t total = M * CG;
+    for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
+         item += (int64_t)gridDim.x * kThreads) {
+        const int64_t m = item / CG;
+        const int c0 = (int)(item - m * CG) * 8;
+        float v[8], sc[8], sh[8];
+        load8(y + m * ldy + c0, v);
+        ldg8f(scale + c0, sc);
+        ldg8f(shift + c0, sh);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
+        if (y2 != nullptr) {
+            float u[8];
+            load8(y2 + m * ldy2 + c0, u);
+            ldg8f(scale2 + c0, sc);
+            ldg8f(shift2 + c0, sh);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += fmaf(u[e], sc[e], sh[e]);
+        }
+        if (res != nullptr) {
+            float u[8];
+            load8(res + m * ldr + c0, u);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += u[e];
+        }
+        if (relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+        }
+        store8(z + m * ldz + c0, v);
+    }
+}
+
+// ------------------------------------------------------------------ backward ----------
+// pass 1: per-channel sums of g and g*xhat.  Block = CG channel groups x PL row lanes.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     float* __restrict__ sums, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy,
+                     int relu, int PL) {
+    extern __shared__ float s_sum[];   // [2*C]
+    const int CG = C >> 3;
+    const int cg = threadIdx.x % CG;
+    const int pl = threadIdx.x / CG;
+    const int c0 = cg * 8;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_sum[i] = 0.f;
+    __syncthreads();
+    float s1[8], s2[8], mu[8], rs[8];
+    zero8(s1); zero8(s2);
+    ldg8f(mean + c0, mu);
+    ldg8f(rstd + c0, rs);
+    if (pl < PL) {
+        for (int64_t m = (int64_t)blockIdx.x * PL + pl; m < M; m += (int64_t)gridDim.x * PL) {
+            float g[8], yy[8];
+            load8(dz + m * lddz + c0, g);
+            load8(y + m * ldy + c0, yy);
+            if (relu) {
+                float zz[8];
+                load8(z + m * ldz + c0, zz);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                s1[e] += g[e];
+                s2[e] = fmaf(g[e], (yy[e] - mu[e]) * rs[e], s2[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            atomicAdd(&s_sum[c0 + e], s1[e]);
+            atomicAdd(&s_sum[C + c0 + e], s2[e]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, s_sum[i]);
+}
+
+// pass 2: dy = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)); optional dres = g
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y,
+                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ gamma, const float* __restrict__ sums,
+                    T* __restrict__ dy, T* __restrict__ dres, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy,
+                    int64_t lddy, int64_t lddres, int relu, float inv_m) {
+    const int CG = C >> 3;
+    const int64_t total = M * CG;
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += kThreads) {
+            if (dbeta != nullptr) dbeta[c] += sums[c];
+            if (dgamma != nullptr) dgamma[c] += sums[C + c];
+        }
+    }
+    for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
+         item += (int64_t)gridDim.x * kThreads) {
+        const int64_t m = item / CG;
+        const int c0 = (int)(item - m * CG) * 8;
+        float g[8], yy[8], mu[8], rs[8], ga[8], a1[8], a2[8];
+        load8(dz + m * lddz + c0, g);
+        load8(y + m * ldy + c0, yy);
+        ldg8f(mean + c0, mu);
+        ldg8f(rstd + c0, rs);
+        if (gamma != nullptr) ldg8f(gamma + c0, ga);
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ga[e] = 1.f;
+        }
+        ldg8f(sums + c0, a1);
+        ldg8f(sums + C + c0, a2);
+        if (relu) {
+            float zz[8];
+            load8(z + m * ldz + c0, zz);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
+        }
+        if (dres != nullptr) store8(dres + m * lddres + c0, g);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float xh = (yy[e] - mu[e]) * rs[e];
+            o[e] = ga[e] * rs[e] * (g[e] - a1[e] * inv_m - xh * a2[e] * inv_m);
+        }
+        store8(dy + m * lddy + c0, o);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+relu_bwd_kernel(const T* __restrict__ dz, const T* __restrict__ z, T* __restrict__ g, int64_t M, int C,
+                int64_t lddz, int64_t ldz, int64_t ldg) {
+    const int CG = C >> 3;
+    const int64_t total = M * CG;
+    for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
+         item += (int64_t)gridDim.x * kThreads) {
+        const int64_t m = item / CG;
+        const int c0 = (int)(item - m * CG) * 8;
+        float a[8], b[8];
+        load8(dz + m * lddz + c0, a);
+        load8(z + m * ldz + c0, b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] = b[e] > 0.f ? a[e] : 0.f;
+        store8(g + m * ldg + c0, a);
+    }
+}
+
+// out = a + b (b may be nullptr: plain strided copy)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t M, int C,
+           int64_t lda, int64_t ldb, int64_t ldo) {
+    const int CG = C >> 3;
+    const int64_t total = M * CG;
+    for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
+         item += (int64_t)gridDim.x * kThreads) {
+        const int64_t m = item / CG;
+        const int c0 = (int)(item - m * CG) * 8;
+        float u[8];
+        load8(a + m * lda + c0, u);
+        if (b != nullptr) {
+            float v[8];
+            load8(b + m * ldb + c0, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) u[e] += v[e];
+        }
+        store8(out + m * ldo + c0, u);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+cast_from_f32_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n8) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n8; i += (int64_t)gridDim.x * kThreads) {
+        float v[8];
+        load8(src + i * 8, v);
+        store8(dst + i * 8, v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+scale_inplace_kernel(T* __restrict__ x, const float* __restrict__ s, int64_t n8) {
+    const float k = __ldg(s);
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n8; i += (int64_t)gridDim.x * kThreads) {
+        float v[8];
+        load8(x + i * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= k;
+        store8(x + i * 8, v);
+    }
+}
+
+int check_rows(const char* name, int64_t M, int C) {
+    TSS_REQUIRE(M > 0, "%s: empty tensor (M=%lld)", name, (long long)M);
+    TSS_REQUIRE(C > 0 && C % 8 == 0 && C <= 2048, "%s: C=%d must be a multiple of 8 (<= 2048)", name, C);
+    return TSS_OK;
+}
+
+}  // namespace
+
+extern "C" int tss_bn_finalize(const float* stats, int64_t count, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                               float momentum, float eps, float* scale, float* shift, float* mean,
+                               float* rstd, int C, void* stream) {
+    TSS_REQUIRE(C > 0, "bn_finalize: C=%d", C);
+    // nn.BatchNorm2d raises "Expected more than 1 value per channel when training"
+    TSS_REQUIRE(count > 1, "bn_finalize: Expected more than 1 value per channel when training, got %lld",
+                (long long)count);
+    TSS_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats mismatch");
+    const double unbias = (double)count / (double)(count - 1);
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        stats, 1.0 / (double)count, unbias, gamma, beta, running_mean, running_var, num_batches_tracked,
+        momentum, eps, scale, shift, mean, rstd, C);
+    TSS_LAUNCH_CHECK("bn_finalize");
+    return TSS_OK;
+}
+
+extern "C" int tss_bn_fold(const float* gamma, const float* beta, const float* running_mean,
+                           const float* running_var, float eps, float* scale, float* shift, int C,
+                           void* stream) {
+    TSS_REQUIRE(C > 0, "bn_fold: C=%d", C);
+    bn_fold_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var,
+                                                                     eps, scale, shift, C);
+    TSS_LAUNCH_CHECK("bn_fold");
+    return TSS_OK;
+}
+
+extern "C" int tss_bn_apply(const void* y, const float* scale, const float* shift, const void* y2,
+                            const float* scale2, const float* shift2, const void* res, void* z, int64_t M,
+                            int C, int64_t ldy, int64_t ldy2, int64_t ldr, int64_t ldz, int flags, int dtype,
+                            void* stream) {
+    if (int e = check_rows("bn_apply", M, C)) return e;
+    TSS_REQUIRE(y2 == nullptr || (scale2 != nullptr && shift2 != nullptr), "bn_apply: y2 without scale2/shift2");
+    TSS_DISPATCH_DTYPE(dtype, "bn_apply", {
+        bn_apply_kernel<T><<<stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+            (const T*)y, scale, shift, (const T*)y2, scale2, shift2, (const T*)res, (T*)z, M, C, ldy, ldy2,
+            ldr, ldz, flags & TSS_EPI_RELU);
+        TSS_LAUNCH_CHECK("bn_apply");
+        return TSS_OK;
+    });
+}
+
+extern "C" int tss_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean,
+                                 const float* rstd, float* sums, int64_t M, int C, int64_t lddz, int64_t ldz,
+                                 int64_t ldy, int flags, int dtype, void* stream) {
+    if (int e = check_rows("bn_bwd_reduce", M, C)) return e;
+    const int relu = flags & TSS_EPI_RELU;
+    TSS_REQUIRE(!relu || z != nullptr, "bn_bwd_reduce: ReLU mask needs z");
+    const int CG = C / 8;
+    TSS_REQUIRE(CG <= kThreads, "bn_bwd_reduce: C=%d too large", C);
+    const int PL = kThreads / CG;
+    const int threads = PL * CG;
+    int64_t want = ceil_div64(M, (int64_t)PL * 4);
+    int64_t cap = (int64_t)tss_num_sms() * 4;
+    const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+    TSS_DISPATCH_DTYPE(dtype, "bn_bwd_reduce", {
+        bn_bwd_reduce_kernel<T><<<grid, threads, (size_t)2 * C * sizeof(float), (cudaStream_t)stream>>>(
+            (const T*)dz, (const T*)z, (const T*)y, mean, rstd, sums, M, C, lddz, ldz, ldy, relu, PL);
+        TSS_LAUNCH_CHECK("bn_bwd_reduce");
+        return TSS_OK;
+    });
+}
+
+extern "C" int tss_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean,
+                                const float* rstd, const float* gamma, const float* sums, void* dy,
+                                void* dres, float* dgamma, float* dbeta, int64_t M, int C, int64_t lddz,
+                                int64_t ldz, int64_t ldy, int64_t lddy, int64_t lddres, int flags, int dtype,
+                                void* stream) {
+    if (int e = check_rows("bn_bwd_apply", M, C)) return e;
+    const int relu = flags & TSS_EPI_RELU;
+    TSS_REQUIRE(!relu || z != nullptr, "bn_bwd_apply: ReLU mask needs z");
+    TSS_DISPATCH_DTYPE(dtype, "bn_bwd_apply", {
+        bn_bwd_apply_kernel<T><<<stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+            (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, sums, (T*)dy, (T*)dres, dgamma, dbeta,
+            M, C, lddz, ldz, ldy, lddy, lddres, relu, (float)(1.0 / (double)M));
+        TSS_LAUNCH_CHECK("bn_bwd_apply");
+        return TSS_OK;
+    });
+}
+
+extern "C" int tss_relu_bwd(const void* dz, const void* z, void* g, int64_t M, int C, int64_t lddz,
+                            int64_t ldz, int64_t ldg, int dtype, void* stream) {
+    if (int e = check_rows("relu_bwd", M, C)) return e;
+    TSS_DISPATCH_DTYPE(dtype, "relu_bwd", {
+        relu_bwd_kernel<T><<<stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+            (const T*)dz, (const T*)z, (T*)g, M, C, lddz, ldz, ldg);
+        TSS_LAUNCH_CHECK("relu_bwd");
+        return TSS_OK;
+    });
+}
+
+extern "C" int tss_add(const void* a, const void* b, void* out, int64_t M, int C, int64_t lda, int64_t ldb,
+                       int64_t ldo, int dtype, void* stream) {
+    if (int e = check_rows("add", M, C)) return e;
+    TSS_DISPATCH_DTYPE(dtype, "add", {
+        add_kernel<T><<<stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+            (const T*)a, (const T*)b, (T*)out, M, C, lda, ldb, ldo);
+        TSS_LAUNCH_CHECK("add");
+        return TSS_OK;
+    });
+}
+
+extern "C" int tss_copy_rows(const void* src, void* dst, int64_t M, int C, int64_t lds, int64_t ldd, int dtype,
+                             void* stream) {
+    if (int e = check_rows("copy_rows", M, C)) return e;
+    TSS_DISPATCH_DTYPE(dtype, "copy_rows", {
+        add_kernel<T><<<stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+            (const T*)src, (const T*)nullptr, (T*)dst, M, C, lds, 0, ldd);
+        TSS_LAUNCH_CHECK("copy_rows");
+        return TSS_OK;
+    });
+}
+
+extern "C" int tss_cast_from_f32(const float* src, void* dst, int64_t n, int dtype, void* stream) {
+    TSS_REQUIRE(n > 0 && n % 8 == 0, "cast_from_f32: n=%lld must be a positive multiple of 8", (long long)n);
+    TSS_DISPATCH_DTYPE(dtype, "cast_from_f32", {
+        cast_from_f32_kernel<T><<<stream_grid(n / 8), kThreads, 0, (cudaStream_t)stream>>>(src, (T*)dst, n / 8);
+        TSS_LAUNCH_CHECK("cast_from_f32");
+        return TSS_OK;
+    });
+}
+
+extern "C" int tss_scale_inplace(void* x, const float* s, int64_t n, int dtype, void* stream) {
+    TSS_REQUIRE(n > 0 && n % 8 == 0, "scale_inplace: n=%lld must be a positive multiple of 8", (long long)n);
+    TSS_DISPATCH_DTYPE(dtype, "scale_inplace", {
+        scale_inplace_kernel<T><<<stream_grid(n / 8), kThreads, 0, (cudaStream_t)stream>>>((T*)x, s, n / 8);
+        TSS_LAUNCH_CHECK("scale_inplace");
+        return TSS_OK;
+    });
+}

@@ -1,0 +1,144 @@
+// Shared device/host helpers for libtss_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tss_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- errors ------------
+void tss_set_error(const char* fmt, ...);
+void tss_count_launch(int n);
+
+#define TSS_REQUIRE(cond, ...)                                                        \
+    do {                                                                              \
+        if (!(cond)) {                                                                \
+            tss_set_error(__VA_ARGS__);                                               \
+            return TSS_ERR_ARG;                                                       \
+        }                                                                             \
+    } while (0)
+
+#define TSS_LAUNCH_CHECK(name)                                                        \
+    do {                                                                              \
+        cudaError_t e_ = cudaGetLastError();                                          \
+        if (e_ != cudaSuccess) {                                                      \
+            tss_set_error("%s: launch failed: %s", name, cudaGetErrorString(e_));     \
+            return TSS_ERR_CUDA;                                                      \
+        }                                                                             \
+        tss_count_launch(1);                                                          \
+    } while (0)
+
+#define TSS_CUDA(call)                                                                \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            tss_set_error("%s failed: %s", #call, cudaGetErrorString(e_));            \
+            return TSS_ERR_CUDA;                                                      \
+        }                                                                             \
+    } while (0)
+
+// Dispatch a launcher body on the activation dtype. `T` is float or bf16 inside BODY.
+#define TSS_DISPATCH_DTYPE(dtype, name, ...)                                          \
+    do {                                                                              \
+        if ((dtype) == TSS_F32) { typedef float T; __VA_ARGS__ }                      \
+        else if ((dtype) == TSS_BF16) { typedef bf16 T; __VA_ARGS__ }                 \
+        else { tss_set_error("%s: unsupported dtype %d", name, (int)(dtype)); return TSS_ERR_ARG; } \
+    } while (0)
+
+static inline int tss_num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- scalar conversion --
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---------------------------------------------------------------- 8-wide vectors -----
+// All NHWC activation kernels move 8 channels per thread: one 128-bit access for bf16,
+// two for fp32.  Pointers must be 16-byte aligned (C % 8 == 0 and 16B-aligned base).
+__device__ __forceinline__ void load8(const float* __restrict__ p, float (&v)[8]) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+    v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+    v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+    v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xffff0000u);
+    v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+__device__ __forceinline__ void load8(const bf16* __restrict__ p, float (&v)[8]) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    unpack8(u, v);
+}
+__device__ __forceinline__ void zero8(float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void store8(float* __restrict__ p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* __restrict__ p, const float (&v)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+// value as it will be read back after the store (rounding to the storage type)
+__device__ __forceinline__ float round_as(float v, const float*) { return v; }
+__device__ __forceinline__ float round_as(float v, const bf16*) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// ---------------------------------------------------------------- reductions ---------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// lane l ends with sum over the 32 lanes of v[l]  (31 shuffles instead of 160)
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int step = 16, n = 32; step >= 1; step >>= 1, n >>= 1) {
+        const bool upper = (lane & step) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            float send = upper ? v[i] : v[i + n / 2];
+            float keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
+    }
+    return v[0];
+}
+
+// bilinear align_corners=True source index, same float arithmetic as ATen
+// (area_pixel_compute_scale / compute_source_index): scale = (in-1)/(out-1) in fp32.
+__host__ __device__ __forceinline__ float ac_scale(int in, int out) {
+    return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+}
+__device__ __forceinline__ void ac_source(float scale, int dst, int in_size, int& i0, int& i1, float& lam) {
+    float s = scale * (float)dst;
+    i0 = (int)s;
+    if (i0 > in_size - 1) i0 = in_size - 1;   // guards fp rounding at the last pixel
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    lam = fminf(fmaxf(s - (float)i0, 0.f), 1.f);
+}

@@ -1,0 +1,159 @@
+// Confusion matrix (integer exact).  cm[t][p] += 1 for every pixel with 0 <= t < C.
+// Per-CTA histogram in shared memory; lanes of a warp that hit the same bin are merged with
+// __match_any_sync so that one shared atomic carries the whole group (semantic maps are
+// piecewise constant, so whole warps usually collapse to one or two atomics); one global
+// 64-bit atomic per non-empty bin per CTA at the end.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxC = 32;
+
+__device__ __forceinline__ void warp_agg_inc(unsigned int* s_hist, int bin, bool active) {
+    // every lane of the warp must call this (convergent); inactive lanes use a private key
+    const unsigned lane = threadIdx.x & 31;
+    const int key = active ? bin : (-1 - (int)lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (active && (unsigned)(__ffs(peers) - 1) == lane) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
+}
+
+__device__ __forceinline__ void flush_hist(const unsigned int* s_hist, int bins, unsigned long long* cm) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += kThreads) {
+        const unsigned v = s_hist[i];
+        if (v) atomicAdd(cm + i, (unsigned long long)v);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+cm_labels_kernel(const int64_t* __restrict__ pred, const int64_t* __restrict__ target, int64_t n, int C,
+                 unsigned long long* __restrict__ cm) {
+    __shared__ unsigned int s_hist[kMaxC * kMaxC];
+    for (int i = threadIdx.x; i < C * C; i += kThreads) s_hist[i] = 0;
+    __syncthreads();
+    const int64_t n2 = n >> 1;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    // trip count is made warp-uniform so that __match_any_sync stays convergent
+    const int64_t iters = (n2 + stride - 1) / stride;
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    for (int64_t it = 0; it < iters; ++it, i += stride) {
+        const bool in = i < n2;
+        longlong2 p = make_longlong2(0, -1), t = make_longlong2(-1, -1);
+        if (in) {
+            p = __ldg(reinterpret_cast<const longlong2*>(pred) + i);
+            t = __ldg(reinterpret_cast<const longlong2*>(target) + i);
+        }
+        const bool a0 = in && t.x >= 0 && t.x < C && p.x >= 0 && p.x < C;
+        const bool a1 = in && t.y >= 0 && t.y < C && p.y >= 0 && p.y < C;
+        warp_agg_inc(s_hist, a0 ? (int)(t.x * C + p.x) : 0, a0);
+        warp_agg_inc(s_hist, a1 ? (int)(t.y * C + p.y) : 0, a1);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t t = target[n - 1], p = pred[n - 1];
+        if (t >= 0 && t < C && p >= 0 && p < C) atomicAdd(&s_hist[t * C + p], 1u);
+    }
+    flush_hist(s_hist, C * C, cm);
+}
+
+template <typename T> struct Quad4;
+template <> struct Quad4<float> {
+    __device__ static void ld(const float* p, float (&v)[4]) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+template <> struct Quad4<bf16> {
+    __device__ static void ld(const bf16* p, float (&v)[4]) {
+        uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+        v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+        v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+    }
+};
+
+// argmax over the C class planes fused in.  torch.argmax: first maximal index, NaN is maximal.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+cm_logits_kernel(const T* __restrict__ logits, const int64_t* __restrict__ target, int N, int C, int64_t HW,
+                 unsigned long long* __restrict__ cm, int64_t* __restrict__ pred_out) {
+    __shared__ unsigned int s_hist[kMaxC * kMaxC];
+    for (int i = threadIdx.x; i < C * C; i += kThreads) s_hist[i] = 0;
+    __syncthreads();
+    const int64_t qpi = HW >> 2;
+    const int64_t total = (int64_t)N * qpi;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    const int64_t iters = (total + stride - 1) / stride;
+    int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    for (int64_t it = 0; it < iters; ++it, q += stride) {
+        const bool in = q < total;
+        int best[4] = {0, 0, 0, 0};
+        int64_t tg[4] = {-1, -1, -1, -1};
+        if (in) {
+            const int64_t n = q / qpi;
+            const int64_t hw = (q - n * qpi) << 2;
+            const T* lp = logits + n * C * HW + hw;
+            float bv[4];
+            bool bnan[4];
+            Quad4<T>::ld(lp, bv);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) bnan[p] = bv[p] != bv[p];
+            for (int c = 1; c < C; ++c) {
+                float v[4];
+                Quad4<T>::ld(lp + (int64_t)c * HW, v);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const bool vn = v[p] != v[p];
+                    if (!bnan[p] && (vn || v[p] > bv[p])) { bv[p] = v[p]; best[p] = c; bnan[p] = vn; }
+                }
+            }
+            const longlong2 ta = __ldg(reinterpret_cast<const longlong2*>(target + n * HW + hw));
+            const longlong2 tb = __ldg(reinterpret_cast<const longlong2*>(target + n * HW + hw) + 1);
+            tg[0] = ta.x; tg[1] = ta.y; tg[2] = tb.x; tg[3] = tb.y;
+            if (pred_out != nullptr) {
+                longlong2* po = reinterpret_cast<longlong2*>(pred_out + n * HW + hw);
+                po[0] = make_longlong2(best[0], best[1]);
+                po[1] = make_longlong2(best[2], best[3]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const bool a = in && tg[p] >= 0 && tg[p] < C;
+            warp_agg_inc(s_hist, a ? (int)(tg[p] * C + best[p]) : 0, a);
+        }
+    }
+    flush_hist(s_hist, C * C, cm);
+}
+
+inline int cm_grid(int64_t items) {
+    int64_t want = ceil_div64(items, kThreads * 4);
+    int64_t cap = (int64_t)tss_num_sms() * 8;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace
+
+extern "C" int tss_confusion_from_labels(const int64_t* pred, const int64_t* target, int64_t n, int C,
+                                         int64_t* cm, void* stream) {
+    TSS_REQUIRE(n >= 0, "confusion_from_labels: n=%lld", (long long)n);
+    TSS_REQUIRE(C > 0 && C <= kMaxC, "confusion_from_labels: C=%d (max %d)", C, kMaxC);
+    if (n == 0) return TSS_OK;
+    TSS_REQUIRE((((uintptr_t)pred | (uintptr_t)target) & 15) == 0, "confusion_from_labels: maps must be 16-byte aligned");
+    cm_labels_kernel<<<cm_grid(n / 2 + 1), kThreads, 0, (cudaStream_t)stream>>>(pred, target, n, C,
+                                                                               (unsigned long long*)cm);
+    TSS_LAUNCH_CHECK("confusion_from_labels");
+    return TSS_OK;
+}
+
+extern "C" int tss_confusion_from_logits(const void* logits, const int64_t* target, int N, int C, int64_t HW,
+                                         int64_t* cm, int64_t* pred_out, int dtype, void* stream) {
+    TSS_REQUIRE(N > 0 && HW > 0, "confusion_from_logits: empty input");
+    TSS_REQUIRE(C > 0 && C <= kMaxC, "confusion_from_logits: C=%d (max %d)", C, kMaxC);
+    TSS_REQUIRE(HW % 4 == 0, "confusion_from_logits: H*W=%lld must be a multiple of 4", (long long)HW);
+    TSS_DISPATCH_DTYPE(dtype, "confusion_from_logits", {
+        cm_logits_kernel<T><<<cm_grid((int64_t)N * (HW / 4)), kThreads, 0, (cudaStream_t)stream>>>(
+            (const T*)logits, target, N, C, HW, (unsigned long long*)cm, pred_out);
+        TSS_LAUNCH_CHECK("confusion_from_logits");
+        return TSS_OK;
+    });
+}

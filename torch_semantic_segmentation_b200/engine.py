@@ -1,0 +1,212 @@
+"""Train / eval loop, drop-in for ``torch_semantic_segmentation.engine`` (reference: engine.py).
+
+``create_segmentation_trainer`` and ``create_segmentation_evaluator`` keep the reference's
+signatures and step semantics (engine.py:22-39, 59-82).  The reference builds them on
+pytorch-ignite and NVIDIA apex, neither of which this path needs:
+
+* the small :class:`Engine` / :class:`Events` below provide the part of the ignite API the
+  reference scripts use (``run``, ``state``, ``on`` / ``add_event_handler``, ``every=``
+  filters, metric dict);
+* ``use_f16=True`` selects the bf16 kernels (fp32 master weights, fp32 BatchNorm statistics;
+  bf16 has fp32's exponent range, so apex's loss scaling, engine.py:32-34, has no counterpart);
+* the evaluator feeds ONE device-side confusion matrix (the reference keeps four identical
+  ones, engine.py:65-72) and derives ``iou`` / ``miou`` / ``accuracy`` / ``dice`` from it.
+"""
+import torch
+
+from . import metrics as M
+from .functional import unit_loss_grad
+
+__all__ = ['create_segmentation_trainer', 'create_segmentation_evaluator', 'Engine', 'Events', 'State']
+
+
+# ------------------------------------------------------------------ minimal ignite surface --
+class _Event:
+    def __init__(self, name, every=None, once=None):
+        self.name, self.every, self.once = name, every, once
+
+    def __call__(self, every=None, once=None):
+        return _Event(self.name, every, once)
+
+    def __eq__(self, other):
+        return isinstance(other, _Event) and other.name == self.name
+
+    def __hash__(self):
+        return hash(self.name)
+
+    def __repr__(self):
+        return 'Events.%s' % self.name
+
+
+class Events:
+    STARTED = _Event('STARTED')
+    EPOCH_STARTED = _Event('EPOCH_STARTED')
+    ITERATION_STARTED = _Event('ITERATION_STARTED')
+    ITERATION_COMPLETED = _Event('ITERATION_COMPLETED')
+    EPOCH_COMPLETED = _Event('EPOCH_COMPLETED')
+    COMPLETED = _Event('COMPLETED')
+
+
+class State:
+    def __init__(self):
+        self.iteration = 0
+        self.epoch = 0
+        self.max_epochs = None
+        self.output = None
+        self.batch = None
+        self.metrics = {}
+
+
+class Engine:
+    """``Engine(process_function)``; ``process_function(engine, batch) -> output``."""
+
+    def __init__(self, process_function):
+        self._process_function = process_function
+        self._handlers = {}
+        self.state = State()
+        self.should_terminate = False
+
+    def add_event_handler(self, event, handler, *args, **kwargs):
+        self._handlers.setdefault(event.name, []).append((event, handler, args, kwargs))
+
+    def on(self, event, *args, **kwargs):
+        def decorator(fn):
+            self.add_event_handler(event, fn, *args, **kwargs)
+            return fn
+        return decorator
+
+    def terminate(self):
+        self.should_terminate = True
+
+    def _fire(self, event):
+        count = self.state.epoch if 'EPOCH' in event.name else self.state.iteration
+        for ev, handler, args, kwargs in self._handlers.get(event.name, ()):
+            if ev.every is not None and (count == 0 or count % ev.every != 0):
+                continue
+            if ev.once is not None and count != ev.once:
+                continue
+            handler(self, *args, **kwargs)
+
+    def run(self, data, max_epochs=1):
+        self.state = State()
+        self.state.max_epochs = max_epochs
+        self.should_terminate = False
+        self._fire(Events.STARTED)
+        for _ in range(max_epochs):
+            if self.should_terminate:
+                break
+            self.state.epoch += 1
+            self._fire(Events.EPOCH_STARTED)
+            for batch in data:
+                self.state.iteration += 1
+                self.state.batch = batch
+                self._fire(Events.ITERATION_STARTED)
+                self.state.output = self._process_function(self, batch)
+                self._fire(Events.ITERATION_COMPLETED)
+                if self.should_terminate:
+                    break
+            self._fire(Events.EPOCH_COMPLETED)
+        self._fire(Events.COMPLETED)
+        return self.state
+
+
+class RunningAverage:
+    """Exponential moving average of the step output (ignite default alpha = 0.98)."""
+
+    def __init__(self, output_transform=lambda x: x, alpha=0.98):
+        self.transform, self.alpha, self.value = output_transform, alpha, None
+
+    def attach(self, engine, name):
+        def started(_engine):
+            self.value = None
+
+        def update(e):
+            v = float(self.transform(e.state.output))
+            self.value = v if self.value is None else self.value * self.alpha + (1.0 - self.alpha) * v
+            e.state.metrics[name] = self.value
+        engine.add_event_handler(Events.EPOCH_STARTED, started)
+        engine.add_event_handler(Events.ITERATION_COMPLETED, update)
+
+
+def _prepare_batch(batch, device=None, non_blocking=False):
+    """ignite's ``_prepare_batch`` (engine.py:27): move (x, y) to the device."""
+    x, y = batch
+    return (x.to(device=device, non_blocking=non_blocking),
+            y.to(device=device, non_blocking=non_blocking))
+
+
+# ------------------------------------------------------------------ the two factories -------
+def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False, logging=True,
+                                non_blocking=True):
+    """reference: engine.py:22-56."""
+    if use_f16 and hasattr(model, 'set_compute_dtype'):
+        model.set_compute_dtype(torch.bfloat16)
+
+    def update_fn(_trainer, batch):
+        model.train()
+        optimizer.zero_grad()
+        x, y = _prepare_batch(batch, device=device, non_blocking=non_blocking)
+
+        y_pred = model(x)
+        loss = loss_fn(y_pred, y)
+
+        with unit_loss_grad():      # backward() seeds d(loss)/d(loss) = 1: no rescale pass needed
+            loss.backward()
+
+        optimizer.step()
+        return loss.item()
+
+    trainer = Engine(update_fn)
+    RunningAverage(output_transform=lambda x: x).attach(trainer, 'loss')
+
+    @trainer.on(Events.ITERATION_COMPLETED)
+    def log_optimizer_params(engine):
+        param_groups = optimizer.param_groups[0]
+        for h in ['lr', 'momentum', 'weight_decay']:
+            if h in param_groups.keys():
+                engine.state.metrics[h] = param_groups[h]
+
+    if logging:
+        @trainer.on(Events.EPOCH_COMPLETED)
+        def _log(engine):
+            print('epoch %d iteration %d loss %.4f lr %s' % (
+                engine.state.epoch, engine.state.iteration, engine.state.metrics.get('loss', float('nan')),
+                engine.state.metrics.get('lr')))
+
+    return trainer
+
+
+def create_segmentation_evaluator(model, device, num_classes=19, loss_fn=None, non_blocking=True):
+    """reference: engine.py:59-82.  ``state.metrics`` gets 'iou', 'miou', 'accuracy', 'dice'
+    (float64 tensors / scalars, ignite formulas) and, with ``loss_fn``, 'loss'."""
+    cm = M.ConfusionMatrix(num_classes)
+    loss_acc = {'sum': None, 'n': 0}
+
+    def eval_fn(_evaluator, batch):
+        model.eval()
+        with torch.no_grad():
+            x, y = _prepare_batch(batch, device=device, non_blocking=non_blocking)
+            y_pred = model(x)
+            cm.update((y_pred, y))
+            if loss_fn is not None:
+                l = loss_fn(y_pred, y).detach().double() * y.shape[0]
+                loss_acc['sum'] = l if loss_acc['sum'] is None else loss_acc['sum'] + l
+                loss_acc['n'] += y.shape[0]
+            return y_pred, y
+
+    evaluator = Engine(eval_fn)
+
+    @evaluator.on(Events.EPOCH_STARTED)
+    def _reset(engine):
+        cm.reset()
+        loss_acc['sum'], loss_acc['n'] = None, 0
+
+    @evaluator.on(Events.EPOCH_COMPLETED)
+    def _compute(engine):
+        engine.state.metrics.update(M.metrics_from_cm(cm.compute()))
+        engine.state.metrics['confusion_matrix'] = cm.compute(sync=False)
+        if loss_fn is not None and loss_acc['n'] > 0:
+            engine.state.metrics['loss'] = float(loss_acc['sum']) / loss_acc['n']
+
+    evaluator.confusion_matrix = cm
+    return evaluator

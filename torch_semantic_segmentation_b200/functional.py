@@ -1,0 +1,249 @@
+"""Autograd formulas of the hot path, expressed with the C-ABI kernels only.
+
+One ``torch.autograd.Function`` per reference building block:
+
+* :class:`ConvBNAct`   -- Conv2d(bias=False) -> BatchNorm2d -> [+residual] -> [ReLU]
+  (``Conv2dBlock``/``DWConv2dBlock`` fastscnn.py:164-185, the tail of ``BottleneckBlock``
+  fastscnn.py:158-161 and of ``FeatureFusionModule`` fastscnn.py:89), in training mode:
+  conv kernel (+BatchNorm statistics in its epilogue) -> finalize -> apply.
+* :class:`ConvBias`    -- the classifier's Conv2d(128, classes, 1) with bias (fastscnn.py:97).
+* :class:`AdaptivePool`, :class:`PPMConcat` -- ``PyramidPoolingModule`` fastscnn.py:108,119-122.
+* :class:`Bilinear`, :class:`UpsampleLogits` -- ``align_corners=True`` resizes
+  (fastscnn.py:74, 63-64).
+* :class:`CrossEntropy` -- ``nn.CrossEntropyLoss(ignore_index=255)`` (train_fastscnn.py:132),
+  forward and gradient fused in one pass.
+
+Backward runs on autograd's worker thread; every kernel launch goes to that thread's
+current stream (``_lib.call``), which autograd sets to the forward stream.
+"""
+import threading
+
+import torch
+
+from . import ops
+
+_tls = threading.local()
+
+
+class unit_loss_grad:
+    """Context manager: promise that ``loss.backward()`` is called with the implicit
+    gradient 1.0, so that :class:`CrossEntropy` can hand its fused gradient on without
+    a rescaling pass over the logits-sized tensor."""
+
+    def __enter__(self):
+        self.prev = getattr(_tls, 'unit', False)
+        _tls.unit = True
+
+    def __exit__(self, *exc):
+        _tls.unit = self.prev
+
+
+def _unit_grad():
+    return getattr(_tls, 'unit', False)
+
+
+class ConvSpec:
+    """Static description of one conv+BN block (built once per module)."""
+
+    __slots__ = ('kind', 'stride', 'dilation', 'relu', 'bn', 'dtype', 'impl')
+
+    def __init__(self, kind, stride, dilation, relu, bn, dtype, impl=0):
+        self.kind, self.stride, self.dilation = kind, stride, dilation
+        self.relu, self.bn, self.dtype, self.impl = relu, bn, dtype, impl
+
+
+def conv_forward(spec, x, weight, scale=None, shift=None, res=None, relu=False, stats=None, packed=None):
+    """The raw convolution of a block with an optional fused epilogue."""
+    if spec.kind == 'pw':
+        wp = packed[0] if packed is not None else None
+        return ops.pwconv_fwd(x, weight, scale=scale, shift=shift, res=res, relu=relu, stats=stats,
+                              wp=wp, impl=spec.impl if wp is not None else 0)
+    if res is not None:
+        raise RuntimeError('residual epilogue is only available on pointwise convolutions')
+    if spec.kind == 'dw':
+        return ops.dwconv_fwd(x, weight, spec.stride, spec.dilation, scale=scale, shift=shift,
+                              relu=relu, stats=stats)
+    if spec.kind == 'stem':
+        return ops.stem_fwd(x, weight, spec.dtype, scale=scale, shift=shift, relu=relu, stats=stats)
+    raise RuntimeError('unknown conv kind %r' % spec.kind)
+
+
+class ConvBNAct(torch.autograd.Function):
+    """z = act(BN_train(conv(x, w)) [+ res])."""
+
+    @staticmethod
+    def forward(ctx, x, res, weight, gamma, beta, spec, packed):
+        bn = spec.bn
+        C = weight.shape[0]
+        if bn.momentum is None:
+            raise RuntimeError('BatchNorm2d(momentum=None) (cumulative average) is not supported')
+        stats = ops.zeros_f32(2 * C, weight.device)
+        y = conv_forward(spec, x, weight, stats=stats, packed=packed)
+        N, _, H, W = y.shape
+        scale, shift, mean, rstd = ops.bn_finalize(stats, N * H * W, bn, float(bn.momentum), float(bn.eps),
+                                                   update_running=bn.track_running_stats)
+        z = ops.bn_apply(y, scale, shift, res=res, relu=spec.relu)
+        ctx.spec, ctx.packed = spec, packed
+        ctx.has_res = res is not None
+        ctx.in_hw = (x.shape[2], x.shape[3])
+        ctx.save_for_backward(x, weight, gamma, y, z if spec.relu else None, mean, rstd)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        spec = ctx.spec
+        x, weight, gamma, y, z, mean, rstd = ctx.saved_tensors
+        dz = ops.as_nhwc(dz)
+        C = weight.shape[0]
+        dgb = ops.zeros_f32(2 * C, weight.device)
+        want_dres = ctx.has_res and ctx.needs_input_grad[1]
+        dy, dres = ops.bn_backward(dz, z, y, mean, rstd, gamma, spec.relu, want_dres=want_dres,
+                                   dgamma=dgb[:C], dbeta=dgb[C:])
+        dx = None
+        dw = torch.zeros_like(weight)
+        if spec.kind == 'pw':
+            wpT = ctx.packed[1] if ctx.packed is not None else None
+            impl = spec.impl if wpT is not None else 0
+            if ctx.needs_input_grad[0]:
+                dx = ops.pwconv_dgrad(dy, weight, wpT=wpT, impl=impl)
+            ops.pwconv_wgrad(x, dy, dw, impl=impl)
+        elif spec.kind == 'dw':
+            if ctx.needs_input_grad[0]:
+                dx = ops.dwconv_dgrad(dy, weight, ctx.in_hw[0], ctx.in_hw[1], spec.stride, spec.dilation)
+            ops.dwconv_wgrad(x, dy, dw, spec.stride, spec.dilation)
+        else:  # stem: the image needs no gradient
+            if ctx.needs_input_grad[0]:
+                raise RuntimeError('gradient w.r.t. the input image is not implemented')
+            ops.stem_wgrad(x, dy, dw)
+        return dx, dres, dw, dgb[:C], dgb[C:], None, None
+
+
+class ConvBias(torch.autograd.Function):
+    """y = conv1x1(x, w) + b  (class scores; Nc = 19 lives in a padded channel pitch)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        y = ops.pwconv_fwd(x, weight, shift=bias)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        Nc = weight.shape[0]
+        g = ops.geom(dy)
+        if g is None or g[4] % 8 != 0 or g[4] < (Nc + 7) // 8 * 8:
+            # re-pitch: gradient rows must be 16-byte aligned with zeroed pad columns
+            pitch = (Nc + 7) // 8 * 8 + 8
+            buf = torch.zeros((dy.shape[0], dy.shape[2], dy.shape[3], pitch), dtype=dy.dtype, device=dy.device)
+            view = buf[..., :Nc].permute(0, 3, 1, 2)
+            view.copy_(dy)
+            dy = view
+        dx = ops.pwconv_dgrad(dy, weight) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(weight)
+        db = torch.zeros(Nc, dtype=torch.float32, device=weight.device) if ctx.has_bias else None
+        ops.pwconv_wgrad(x, dy, dw, db)
+        return dx, dw, db
+
+
+class AdaptivePool(torch.autograd.Function):
+    """All pyramid bins in one pass; outputs one (N,C,b,b) tensor per bin."""
+
+    @staticmethod
+    def forward(ctx, x, bins):
+        ctx.bins, ctx.shape = tuple(bins), x.shape
+        ctx.dtype, ctx.device = x.dtype, x.device
+        _, outs = ops.adaptive_pool_fwd(x, ctx.bins)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        N, C, H, W = ctx.shape
+        dev = ctx.device
+        cells = sum(b * b for b in ctx.bins)
+        dbuf = torch.zeros((cells * N, C), dtype=ctx.dtype, device=dev)
+        for view, g in zip(ops.split_pool_buffer(dbuf, N, C, ctx.bins), grads):
+            if g is not None:
+                ops.copy_rows(ops.as_nhwc(g), view)
+        dx = ops.empty_nhwc(N, C, H, W, ctx.dtype, dev)
+        ops.adaptive_pool_bwd(dbuf, dx, ctx.bins, accumulate=False)
+        return dx, None
+
+
+class PPMConcat(torch.autograd.Function):
+    """cat([x, up(z_1), ..., up(z_k)], dim=1) with the bilinear up-samplings written
+    straight into their channel slices of the concat buffer (fastscnn.py:119-122)."""
+
+    @staticmethod
+    def forward(ctx, x, *zs):
+        N, C, H, W = x.shape
+        total = C + sum(z.shape[1] for z in zs)
+        cat = ops.empty_nhwc(N, total, H, W, x.dtype, x.device)
+        ops.copy_rows(x, cat[:, :C])
+        off = C
+        for z in zs:
+            ops.bilinear_fwd(z, H, W, out=cat[:, off:off + z.shape[1]])
+            off += z.shape[1]
+        ctx.c_in = C
+        ctx.z_shapes = [z.shape for z in zs]
+        return cat
+
+    @staticmethod
+    def backward(ctx, dcat):
+        dcat = ops.as_nhwc(dcat)
+        C = ctx.c_in
+        N, _, H, W = dcat.shape
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.copy_rows(dcat[:, :C], ops.empty_nhwc(N, C, H, W, dcat.dtype, dcat.device))
+        dzs, off = [], C
+        for shp in ctx.z_shapes:
+            dzs.append(ops.bilinear_bwd(dcat[:, off:off + shp[1]], shp[2], shp[3]))
+            off += shp[1]
+        return (dx, *dzs)
+
+
+class Bilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Ho, Wo):
+        ctx.in_hw = (x.shape[2], x.shape[3])
+        return ops.bilinear_fwd(x, Ho, Wo)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.bilinear_bwd(ops.as_nhwc(dy), ctx.in_hw[0], ctx.in_hw[1]), None, None
+
+
+class UpsampleLogits(torch.autograd.Function):
+    """NHWC class scores -> NCHW-contiguous full-resolution logits (the reference's output layout)."""
+
+    @staticmethod
+    def forward(ctx, x, Ho, Wo):
+        g = ops.geom(x)
+        ctx.in_hw, ctx.pitch = (x.shape[2], x.shape[3]), max(g[4], (x.shape[1] + 7) // 8 * 8)
+        return ops.upsample_logits_fwd(x, Ho, Wo)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.upsample_logits_bwd(dy, ctx.in_hw[0], ctx.in_hw[1], ctx.pitch), None, None
+
+
+class CrossEntropy(torch.autograd.Function):
+    """mean softmax cross-entropy over non-ignored pixels; gradient computed in the forward pass."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        want = ctx.needs_input_grad[0]
+        loss, dlogits, _, _ = ops.ce_forward(logits, target, ignore_index, want_grad=want)
+        ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dlogits,) = ctx.saved_tensors
+        if dlogits is None:
+            return None, None, None
+        if not _unit_grad():
+            dlogits = ops.scale_inplace(dlogits, grad_out.to(torch.float32).reshape(1))
+        return dlogits, None, None

@@ -1,0 +1,130 @@
+"""Fast-SCNN on hand-written sm_100a kernels, drop-in for
+``torch_semantic_segmentation.models.fastscnn`` (reference: models/fastscnn.py).
+
+Same constructor signature, same child names (``downsample``, ``features``, ``fusion``,
+``classifier``), same ``state_dict`` keys/shapes and the same random init under the same
+seed, so reference checkpoints load with ``strict=True`` and forward hooks on
+``model.downsample`` / ``model.features`` (``DeepSupervisionWrapper``) keep working.
+Input: NCHW float32 ``(N, 3, H, W)``, H and W multiples of 32; output: NCHW-contiguous
+``(N, out_channels, H, W)`` in the compute dtype.
+"""
+import torch
+from torch import nn
+
+from .. import ops
+from .. import functional as Fn
+from ..nn.blocks import (Conv2dBlock, DWConv2dBlock, DSConv2dBlock, BottleneckBlock, ClassScores,
+                         set_compute_dtype)
+
+__all__ = ['FastSCNN', 'fastscnn', 'Classifier']
+
+
+def fastscnn(in_channels, out_channels):
+    return FastSCNN(in_channels, out_channels)
+
+
+class FastSCNN(nn.Module):
+    """reference: models/fastscnn.py:15-64."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.downsample = nn.Sequential(
+            Conv2dBlock(in_channels, 32, kernel_size=3, padding=1, stride=2),
+            DSConv2dBlock(32, 48, kernel_size=3, padding=1, stride=2),
+            DSConv2dBlock(48, 64, kernel_size=3, padding=1, stride=2),
+        )
+        self.features = nn.Sequential(
+            BottleneckModule(64, 64, expansion=6, repeats=3, stride=2),
+            BottleneckModule(64, 96, expansion=6, repeats=3, stride=2),
+            BottleneckModule(96, 128, expansion=6, repeats=3, stride=1),
+            PyramidPoolingModule(128, 128),
+        )
+        self.fusion = FeatureFusionModule((128, 64), 128, scale_factor=4)
+        self.classifier = Classifier(128, out_channels)
+
+    def set_compute_dtype(self, dtype, pw_impl=None):
+        """float32 (verification mode, default) or bfloat16 (the B200 production path)."""
+        set_compute_dtype(self, dtype, pw_impl)
+        return self
+
+    def forward(self, input):
+        if input.dim() != 4 or input.shape[2] % 32 or input.shape[3] % 32:
+            raise RuntimeError('FastSCNN expects (N, C, H, W) input with H and W multiples of 32, got %s'
+                               % (tuple(input.shape),))
+        if input.dtype != torch.float32 or not input.is_contiguous():
+            input = input.float().contiguous()
+        downsample = self.downsample(input)
+        features = self.features(downsample)
+        fusion = self.fusion(features, downsample)
+        classes = self.classifier(fusion)
+        return Fn.UpsampleLogits.apply(ops.as_nhwc(classes), classes.shape[2] * 8, classes.shape[3] * 8)
+
+
+class FeatureFusionModule(nn.Module):
+    """reference: models/fastscnn.py:67-89.  ``lowres[0]`` stays an ``nn.UpsamplingBilinear2d``
+    child (index parity of the state_dict keys ``lowres.1.*`` / ``lowres.2.*``)."""
+
+    def __init__(self, in_channels, out_channels, scale_factor):
+        super().__init__()
+        lowres_channels, highres_channels = in_channels
+        self.scale_factor = scale_factor
+        self.lowres = nn.Sequential(
+            nn.UpsamplingBilinear2d(scale_factor=scale_factor),
+            DWConv2dBlock(lowres_channels, lowres_channels, kernel_size=3,
+                          padding=scale_factor, dilation=scale_factor),
+            Conv2dBlock(lowres_channels, out_channels, kernel_size=1, use_activation=False),
+        )
+        self.highres = nn.Sequential(
+            Conv2dBlock(highres_channels, out_channels, kernel_size=1, use_activation=False)
+        )
+
+    def forward(self, lowres, highres):
+        lowres = ops.as_nhwc(lowres)
+        s = self.scale_factor
+        x = Fn.Bilinear.apply(lowres, lowres.shape[2] * s, lowres.shape[3] * s)
+        x = self.lowres[1](x)
+        high = self.highres[0](highres)
+        # relu(lowres + highres): add and ReLU fused into the low-res branch's BatchNorm apply
+        return self.lowres[2](x, residual=high, relu=True)
+
+
+def Classifier(in_channels, out_channels):
+    """reference: models/fastscnn.py:92-98 (also imported by scripts/train_fastscnn.py:28)."""
+    return nn.Sequential(
+        DSConv2dBlock(in_channels, in_channels, kernel_size=3, padding=1),
+        DSConv2dBlock(in_channels, in_channels, kernel_size=3, padding=1),
+        nn.Dropout(0.1),
+        ClassScores(in_channels, out_channels),
+    )
+
+
+class PyramidPoolingModule(nn.Module):
+    """reference: models/fastscnn.py:101-123.  One pooling pass for all bins; the bilinear
+    up-samplings write straight into the concat buffer."""
+
+    def __init__(self, in_channels, out_channels, pyramids=(1, 2, 3, 6)):
+        super().__init__()
+        self.bins = tuple(pyramids)
+        self.pyramids = nn.ModuleList([
+            nn.Sequential(
+                nn.AdaptiveAvgPool2d(bin),
+                Conv2dBlock(in_channels, in_channels // len(pyramids), kernel_size=1),
+            )
+            for bin in pyramids
+        ])
+        self.conv = Conv2dBlock(in_channels * 2, out_channels, kernel_size=1)
+
+    def forward(self, input):
+        x = ops.as_nhwc(input)
+        pooled = Fn.AdaptivePool.apply(x, self.bins)
+        zs = [pyramid[1](p) for pyramid, p in zip(self.pyramids, pooled)]
+        cat = Fn.PPMConcat.apply(x, *zs)
+        return self.conv(cat)
+
+
+def BottleneckModule(in_channels, out_channels, expansion, repeats=1, stride=1):
+    """reference: models/fastscnn.py:126-135."""
+    layers = [BottleneckBlock(in_channels, out_channels, expansion=expansion, stride=stride)]
+    for _ in range(1, repeats):
+        layers.append(BottleneckBlock(out_channels, out_channels, expansion=expansion))
+    return nn.Sequential(*layers)

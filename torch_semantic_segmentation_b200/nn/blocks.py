@@ -1,0 +1,204 @@
+"""B200 building blocks with the reference's module tree.
+
+The reference builds its blocks as plain ``nn.Sequential(Conv2d, BatchNorm2d[, ReLU])``
+(``Conv2dBlock`` fastscnn.py:164-173, ``DWConv2dBlock`` :176-185, ``DSConv2dBlock`` :188-199;
+``ConvBlock``/``DWConvBlock`` contextnet.py:150-177).  The classes below ARE such
+``nn.Sequential``s -- same children, same indices, same parameter shapes and the same
+construction order (identical ``state_dict`` keys and identical random init under the same
+seed) -- but their ``forward`` runs the fused sm_100a kernels instead of the children's
+forwards.  The child modules only hold parameters and buffers.
+"""
+import torch
+from torch import nn
+
+from .. import ops
+from .. import functional as Fn
+
+
+def _versions(*tensors):
+    return tuple(t._version for t in tensors) + tuple(t.data_ptr() for t in tensors)
+
+
+class _FusedConvBN:
+    """Mixin state/logic shared by all conv+BN pairs (conv at index ``ci``, BN at ``ci+1``)."""
+
+    def _init_fused(self):
+        self._specs = {}
+        self._fold_cache = {}
+        self._pack_cache = {}
+        self.compute_dtype = torch.float32
+        self.pw_impl = 0
+
+    def _kind(self, conv):
+        if conv.kernel_size == (1, 1) and conv.groups == 1:
+            return 'pw'
+        if conv.kernel_size == (3, 3) and conv.groups == conv.in_channels and conv.in_channels == conv.out_channels \
+                and conv.padding == conv.dilation and conv.dilation[0] == conv.dilation[1]:
+            return 'dw'
+        if conv.kernel_size == (3, 3) and conv.groups == 1 and conv.in_channels == 3 and conv.stride == (2, 2) \
+                and conv.padding == (1, 1):
+            return 'stem'
+        raise RuntimeError('no sm_100a kernel for %r' % (conv,))
+
+    def _spec(self, ci, relu):
+        key = (ci, relu, self.compute_dtype, self.pw_impl)
+        spec = self._specs.get(key)
+        if spec is None:
+            conv, bn = self[ci], self[ci + 1]
+            spec = Fn.ConvSpec(self._kind(conv), conv.stride[0], conv.dilation[0], relu, bn,
+                               self.compute_dtype, self.pw_impl)
+            self._specs[key] = spec
+        return spec
+
+    def _folded(self, ci):
+        """Eval-mode BatchNorm as per-channel scale/shift, cached on the tensors' versions."""
+        bn = self[ci + 1]
+        key = _versions(bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        hit = self._fold_cache.get(ci)
+        if hit is None or hit[0] != key:
+            hit = (key, ops.bn_fold(bn))
+            self._fold_cache[ci] = hit
+        return hit[1]
+
+    def _packed(self, ci):
+        """bf16 (W, W^T) copies for the tensor-core path, cached on the weight's version."""
+        if self.pw_impl == 0 or self.compute_dtype != torch.bfloat16:
+            return None
+        w = self[ci].weight
+        if self._kind(self[ci]) != 'pw' or w.shape[0] % 8 != 0:
+            return None
+        key = _versions(w)
+        hit = self._pack_cache.get(ci)
+        if hit is None or hit[0] != key:
+            hit = (key, ops.pack_weights_bf16(w))
+            self._pack_cache[ci] = hit
+        return hit[1]
+
+    def _conv_bn(self, ci, x, relu, res=None):
+        conv, bn = self[ci], self[ci + 1]
+        spec = self._spec(ci, relu)
+        if spec.kind != 'stem':
+            x = ops.as_nhwc(x)
+            if x.dtype != self.compute_dtype:
+                x = x.to(self.compute_dtype)
+        if res is not None:
+            res = ops.as_nhwc(res)
+        packed = self._packed(ci)
+        use_batch_stats = self.training or not bn.track_running_stats
+        if use_batch_stats:
+            return Fn.ConvBNAct.apply(x, res, conv.weight, bn.weight, bn.bias, spec, packed)
+        if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
+            raise RuntimeError('eval-mode BatchNorm with autograd is not implemented; '
+                               'wrap inference in torch.no_grad()')
+        scale, shift = self._folded(ci)
+        return Fn.conv_forward(spec, x, conv.weight, scale=scale, shift=shift, res=res, relu=relu,
+                               packed=packed)
+
+
+class ConvBNBlock(nn.Sequential, _FusedConvBN):
+    """``Conv2dBlock`` / ``DWConv2dBlock`` (fastscnn.py:164-185), ``ConvBlock`` / ``DWConvBlock``
+    (contextnet.py:150-177): Conv2d(bias=False) -> BatchNorm2d -> optional ReLU(inplace)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 groups=1, use_activation=True):
+        layers = [
+            nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
+                      dilation=dilation, groups=groups, bias=False),
+            nn.BatchNorm2d(out_channels),
+        ]
+        if use_activation:
+            layers.append(nn.ReLU(inplace=True))
+        super().__init__(*layers)
+        self.use_activation = use_activation
+        self._init_fused()
+
+    def forward(self, input, residual=None, relu=None):
+        """``residual``/``relu`` let the enclosing block fuse its ``+input`` and trailing
+        ``F.relu`` (fastscnn.py:158-161, 89) into this block's BatchNorm apply."""
+        return self._conv_bn(0, input, self.use_activation if relu is None else relu, residual)
+
+
+class DSConvBNBlock(nn.Sequential, _FusedConvBN):
+    """``DSConv2dBlock`` fastscnn.py:188-199: dw3x3 -> BN (no ReLU) -> 1x1 -> BN -> optional ReLU."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 use_activation=True):
+        layers = [
+            nn.Conv2d(in_channels, in_channels, kernel_size, stride=stride, padding=padding,
+                      dilation=dilation, groups=in_channels, bias=False),
+            nn.BatchNorm2d(in_channels),
+            nn.Conv2d(in_channels, out_channels, kernel_size=1, bias=False),
+            nn.BatchNorm2d(out_channels),
+        ]
+        if use_activation:
+            layers.append(nn.ReLU(inplace=True))
+        super().__init__(*layers)
+        self.use_activation = use_activation
+        self._init_fused()
+
+    def forward(self, input):
+        x = self._conv_bn(0, input, False)
+        return self._conv_bn(2, x, self.use_activation)
+
+
+def Conv2dBlock(in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                use_activation=True):
+    return ConvBNBlock(in_channels, out_channels, kernel_size, stride, padding, dilation, 1, use_activation)
+
+
+def DWConv2dBlock(in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                  use_activation=True):
+    if in_channels != out_channels:
+        raise ValueError("input and output channels must be the same in depthwise convolution")
+    return ConvBNBlock(in_channels, out_channels, kernel_size, stride, padding, dilation, in_channels,
+                       use_activation)
+
+
+def DSConv2dBlock(in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                  use_activation=True):
+    return DSConvBNBlock(in_channels, out_channels, kernel_size, stride, padding, dilation, use_activation)
+
+
+class BottleneckBlock(nn.Module):
+    """``BottleneckBlock`` fastscnn.py:138-161 / contextnet.py:129-147.  The residual add and the
+    unconditional trailing ReLU are fused into conv3's BatchNorm apply."""
+
+    def __init__(self, in_channels, out_channels, stride=1, expansion=6):
+        super().__init__()
+        expansion_channels = expansion * in_channels
+        self.conv1 = Conv2dBlock(in_channels, expansion_channels, kernel_size=1)
+        self.conv2 = DWConv2dBlock(expansion_channels, expansion_channels, kernel_size=3, padding=1,
+                                   stride=stride)
+        self.conv3 = Conv2dBlock(expansion_channels, out_channels, kernel_size=1, use_activation=False)
+        self.has_residual = stride == 1 and in_channels == out_channels   # "x.shape == input.shape"
+
+    def forward(self, input):
+        x = self.conv1(input)
+        x = self.conv2(x)
+        return self.conv3(x, residual=input if self.has_residual else None, relu=True)
+
+
+class ClassScores(nn.Conv2d):
+    """``nn.Conv2d(in_channels, classes, 1)`` with bias (fastscnn.py:97, contextnet.py:86)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__(in_channels, out_channels, kernel_size=1)
+        self.compute_dtype = torch.float32
+
+    def forward(self, input):
+        x = ops.as_nhwc(input)
+        if x.dtype != self.compute_dtype:
+            x = x.to(self.compute_dtype)
+        return Fn.ConvBias.apply(x, self.weight, self.bias)
+
+
+def set_compute_dtype(module, dtype, pw_impl=None):
+    """Select the activation storage type (fp32 verification mode / bf16) of every fused block."""
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError('compute dtype must be float32 or bfloat16')
+    for m in module.modules():
+        if hasattr(m, 'compute_dtype'):
+            m.compute_dtype = dtype
+        if pw_impl is not None and hasattr(m, 'pw_impl'):
+            m.pw_impl = pw_impl
+    return module

@@ -1,0 +1,376 @@
+"""Tensor-level wrappers of the C-ABI kernels (``include/tss_b200.h``).
+
+Activations are 4-D tensors with *logical* shape (N, C, H, W) and *physical* dense NHWC
+layout (``torch.channels_last``), optionally with a channel pitch ``ld >= C`` (a channel
+slice of a wider NHWC buffer).  Wrappers allocate outputs through PyTorch's caching
+allocator, derive sizes/pitches from the tensors and call the library on the current
+stream.  Nothing here computes on the host and nothing falls back to torch ops.
+"""
+import torch
+
+from . import _lib
+from ._lib import EPI_RELU, dtype_code
+
+PYRAMID_BINS = (1, 2, 3, 6)
+
+
+# ------------------------------------------------------------------ layout helpers -----
+def empty_nhwc(N, C, H, W, dtype, device, pitch=None):
+    """Logical (N,C,H,W) tensor over a dense NHWC buffer (channel pitch ``pitch``)."""
+    ld = C if pitch is None else pitch
+    buf = torch.empty((N, H, W, ld), dtype=dtype, device=device)
+    return buf[..., :C].permute(0, 3, 1, 2)
+
+
+def geom(t):
+    """-> (N, C, H, W, ld) of an NHWC(-pitched) activation, or None if it is not one."""
+    if t.dim() != 4:
+        return None
+    N, C, H, W = t.shape
+    sN, sC, sH, sW = t.stride()
+    if W > 1:
+        ld = sW
+    elif H > 1:
+        ld = sH
+    elif N > 1:
+        ld = sN
+    else:
+        ld = C
+    ok = (C == 1 or sC == 1) and ld >= C and (W == 1 or sW == ld) and \
+        (H == 1 or sH == W * ld) and (N == 1 or sN == H * W * ld)
+    return (N, C, H, W, ld) if ok else None
+
+
+def as_nhwc(t):
+    """Return ``t`` if it already is NHWC(-pitched), else a dense NHWC copy (API boundary only)."""
+    if geom(t) is not None:
+        return t
+    return t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+def _g(t, name):
+    g = geom(t)
+    if g is None:
+        raise RuntimeError('%s: tensor of shape %s / strides %s is not NHWC' % (name, tuple(t.shape), t.stride()))
+    return g
+
+
+def _flags(relu):
+    return EPI_RELU if relu else 0
+
+
+def zeros_f32(n, device):
+    return torch.zeros(n, dtype=torch.float32, device=device)
+
+
+# ------------------------------------------------------------------ depthwise 3x3 ------
+def dwconv_fwd(x, w, stride, dilation, scale=None, shift=None, relu=False, stats=None):
+    N, C, Hi, Wi, ld = _g(x, 'dwconv_fwd')
+    if ld != C:
+        raise RuntimeError('dwconv_fwd: pitched input not supported')
+    Ho, Wo = (Hi - 1) // stride + 1, (Wi - 1) // stride + 1
+    y = empty_nhwc(N, C, Ho, Wo, x.dtype, x.device)
+    _lib.call('tss_dwconv3x3_fwd', x=x, w=w, y=y, N=N, Hi=Hi, Wi=Wi, C=C, stride=stride,
+              dilation=dilation, scale=scale, shift=shift, flags=_flags(relu), stats=stats,
+              dtype=dtype_code(x.dtype))
+    return y
+
+
+def dwconv_dgrad(dy, w, Hi, Wi, stride, dilation):
+    N, C, Ho, Wo, ld = _g(dy, 'dwconv_dgrad')
+    if ld != C:
+        raise RuntimeError('dwconv_dgrad: pitched input not supported')
+    dx = empty_nhwc(N, C, Hi, Wi, dy.dtype, dy.device)
+    _lib.call('tss_dwconv3x3_dgrad', dy=dy, w=w, dx=dx, N=N, Hi=Hi, Wi=Wi, C=C, stride=stride,
+              dilation=dilation, dtype=dtype_code(dy.dtype))
+    return dx
+
+
+def dwconv_wgrad(x, dy, dw, stride, dilation):
+    """dw (fp32, shape (C,1,3,3)) += wgrad."""
+    N, C, Hi, Wi, ld = _g(x, 'dwconv_wgrad')
+    if ld != C or _g(dy, 'dwconv_wgrad')[4] != C:
+        raise RuntimeError('dwconv_wgrad: pitched input not supported')
+    _lib.call('tss_dwconv3x3_wgrad', x=x, dy=dy, dw=dw, N=N, Hi=Hi, Wi=Wi, C=C, stride=stride,
+              dilation=dilation, dtype=dtype_code(x.dtype))
+
+
+# ------------------------------------------------------------------ pointwise 1x1 ------
+def _pad8(c):
+    return (c + 7) // 8 * 8
+
+
+def pwconv_fwd(x, w, scale=None, shift=None, res=None, relu=False, stats=None, out=None,
+               wp=None, impl=0):
+    """y = x . w^T (+epilogue).  ``w`` fp32 (Nc, K, 1, 1).  Nc % 8 != 0 gets a padded pitch."""
+    N, K, H, W, ldx = _g(x, 'pwconv_fwd')
+    Nc = w.shape[0]
+    if out is None:
+        out = empty_nhwc(N, Nc, H, W, x.dtype, x.device, pitch=None if Nc % 8 == 0 else _pad8(Nc) + 8)
+    ldy = _g(out, 'pwconv_fwd')[4]
+    ldr = _g(res, 'pwconv_fwd')[4] if res is not None else 0
+    _lib.call('tss_pwconv_fwd', x=x, w=w, wp=wp, y=out, M=N * H * W, K=K, Nc=Nc, ldx=ldx, ldy=ldy,
+              scale=scale, shift=shift, res=res, ldr=ldr, flags=_flags(relu), stats=stats,
+              impl=impl, dtype=dtype_code(x.dtype))
+    return out
+
+
+def pwconv_dgrad(dy, w, wpT=None, impl=0):
+    N, Nc, H, W, lddy = _g(dy, 'pwconv_dgrad')
+    K = w.shape[1]
+    dx = empty_nhwc(N, K, H, W, dy.dtype, dy.device)
+    _lib.call('tss_pwconv_dgrad', dy=dy, w=w, wpT=wpT, dx=dx, M=N * H * W, K=K, Nc=Nc, lddy=lddy,
+              lddx=K, impl=impl, dtype=dtype_code(dy.dtype))
+    return dx
+
+
+def pwconv_wgrad(x, dy, dw, db=None, impl=0):
+    """dw (fp32 (Nc,K,1,1)) += dy^T x ; db (fp32 (Nc,)) += colsum(dy)."""
+    N, K, H, W, ldx = _g(x, 'pwconv_wgrad')
+    Nc, lddy = dy.shape[1], _g(dy, 'pwconv_wgrad')[4]
+    _lib.call('tss_pwconv_wgrad', x=x, dy=dy, dw=dw, db=db, M=N * H * W, K=K, Nc=Nc, ldx=ldx,
+              lddy=lddy, impl=impl, dtype=dtype_code(x.dtype))
+
+
+def pack_weights_bf16(w):
+    Nc, K = w.shape[0], w.shape[1]
+    wp = torch.empty((Nc, K), dtype=torch.bfloat16, device=w.device)
+    wpT = torch.empty((K, Nc), dtype=torch.bfloat16, device=w.device)
+    _lib.call('tss_pack_weights_bf16', w=w, wp=wp, wpT=wpT, Nc=Nc, K=K)
+    return wp, wpT
+
+
+# ------------------------------------------------------------------ stem ---------------
+def stem_fwd(x, w, dtype, scale=None, shift=None, relu=False, stats=None):
+    """x: NCHW fp32 contiguous (N,3,H,W) image batch, read in place."""
+    N, Cin, H, W = x.shape
+    if Cin != 3 or x.dtype != torch.float32 or not x.is_contiguous():
+        raise RuntimeError('stem_fwd: expects a contiguous float32 (N,3,H,W) batch')
+    Cout = w.shape[0]
+    y = empty_nhwc(N, Cout, (H - 1) // 2 + 1, (W - 1) // 2 + 1, dtype, x.device)
+    _lib.call('tss_stem3x3s2_fwd', x=x, w=w, y=y, N=N, H=H, W=W, Cout=Cout, scale=scale,
+              shift=shift, flags=_flags(relu), stats=stats, dtype=dtype_code(dtype))
+    return y
+
+
+def stem_wgrad(x, dy, dw):
+    N, _, H, W = x.shape
+    _lib.call('tss_stem3x3s2_wgrad', x=x, dy=dy, dw=dw, N=N, H=H, W=W, Cout=dy.shape[1],
+              dtype=dtype_code(dy.dtype))
+
+
+# ------------------------------------------------------------------ batch norm ---------
+def bn_finalize(stats, count, bn, momentum, eps, update_running=True):
+    """-> scale, shift, mean, rstd (fp32 (C,)); updates bn's running stats in place."""
+    C = stats.numel() // 2
+    out = torch.empty((4, C), dtype=torch.float32, device=stats.device)
+    track = update_running and bn.running_mean is not None
+    _lib.call('tss_bn_finalize', stats=stats, count=count, gamma=bn.weight, beta=bn.bias,
+              running_mean=bn.running_mean if track else None,
+              running_var=bn.running_var if track else None,
+              num_batches_tracked=bn.num_batches_tracked if track else None,
+              momentum=momentum, eps=eps, scale=out[0], shift=out[1], mean=out[2], rstd=out[3], C=C)
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_fold(bn):
+    C = bn.num_features
+    out = torch.empty((2, C), dtype=torch.float32, device=bn.running_mean.device)
+    _lib.call('tss_bn_fold', gamma=bn.weight, beta=bn.bias, running_mean=bn.running_mean,
+              running_var=bn.running_var, eps=bn.eps, scale=out[0], shift=out[1], C=C)
+    return out[0], out[1]
+
+
+def bn_apply(y, scale, shift, y2=None, scale2=None, shift2=None, res=None, relu=False, out=None):
+    N, C, H, W, ldy = _g(y, 'bn_apply')
+    if out is None:
+        out = empty_nhwc(N, C, H, W, y.dtype, y.device)
+    _lib.call('tss_bn_apply', y=y, scale=scale, shift=shift, y2=y2, scale2=scale2, shift2=shift2,
+              res=res, z=out, M=N * H * W, C=C, ldy=ldy,
+              ldy2=_g(y2, 'bn_apply')[4] if y2 is not None else 0,
+              ldr=_g(res, 'bn_apply')[4] if res is not None else 0,
+              ldz=_g(out, 'bn_apply')[4], flags=_flags(relu), dtype=dtype_code(y.dtype))
+    return out
+
+
+def bn_backward(dz, z, y, mean, rstd, gamma, relu, want_dres=False, dgamma=None, dbeta=None):
+    """-> dy, dres (or None).  dgamma/dbeta (fp32 (C,)) are accumulated into."""
+    N, C, H, W, lddz = _g(dz, 'bn_backward')
+    M = N * H * W
+    sums = zeros_f32(2 * C, dz.device)
+    fl = _flags(relu)
+    code = dtype_code(dz.dtype)
+    ldz = _g(z, 'bn_backward')[4] if z is not None else 0
+    ldy = _g(y, 'bn_backward')[4]
+    _lib.call('tss_bn_bwd_reduce', dz=dz, z=z if relu else None, y=y, mean=mean, rstd=rstd, sums=sums,
+              M=M, C=C, lddz=lddz, ldz=ldz, ldy=ldy, flags=fl, dtype=code)
+    dy = empty_nhwc(N, C, H, W, dz.dtype, dz.device)
+    dres = empty_nhwc(N, C, H, W, dz.dtype, dz.device) if want_dres else None
+    _lib.call('tss_bn_bwd_apply', dz=dz, z=z if relu else None, y=y, mean=mean, rstd=rstd, gamma=gamma,
+              sums=sums, dy=dy, dres=dres, dgamma=dgamma, dbeta=dbeta, M=M, C=C, lddz=lddz, ldz=ldz,
+              ldy=ldy, lddy=C, lddres=C, flags=fl, dtype=code)
+    return dy, dres
+
+
+def relu_bwd(dz, z):
+    N, C, H, W, lddz = _g(dz, 'relu_bwd')
+    g = empty_nhwc(N, C, H, W, dz.dtype, dz.device)
+    _lib.call('tss_relu_bwd', dz=dz, z=z, g=g, M=N * H * W, C=C, lddz=lddz, ldz=_g(z, 'relu_bwd')[4],
+              ldg=C, dtype=dtype_code(dz.dtype))
+    return g
+
+
+def add(a, b):
+    N, C, H, W, lda = _g(a, 'add')
+    out = empty_nhwc(N, C, H, W, a.dtype, a.device)
+    _lib.call('tss_add', a=a, b=b, out=out, M=N * H * W, C=C, lda=lda, ldb=_g(b, 'add')[4], ldo=C,
+              dtype=dtype_code(a.dtype))
+    return out
+
+
+def copy_rows(src, dst):
+    N, C, H, W, lds = _g(src, 'copy_rows')
+    _lib.call('tss_copy_rows', src=src, dst=dst, M=N * H * W, C=C, lds=lds, ldd=_g(dst, 'copy_rows')[4],
+              dtype=dtype_code(src.dtype))
+    return dst
+
+
+def cast_from_f32(src, dtype):
+    dst = torch.empty(src.shape, dtype=dtype, device=src.device)
+    _lib.call('tss_cast_from_f32', src=src, dst=dst, n=src.numel(), dtype=dtype_code(dtype))
+    return dst
+
+
+def scale_inplace(x, s):
+    _lib.call('tss_scale_inplace', x=x, s=s, n=x.numel(), dtype=dtype_code(x.dtype))
+    return x
+
+
+# ------------------------------------------------------------------ pooling / resize ---
+def adaptive_pool_fwd(x, bins=PYRAMID_BINS):
+    """-> list of (N, C, b, b) NHWC tensors (views into one buffer), one per bin."""
+    N, C, H, W, ld = _g(x, 'adaptive_pool_fwd')
+    if ld != C:
+        raise RuntimeError('adaptive_pool_fwd: pitched input not supported')
+    cells = sum(b * b for b in bins)
+    buf = torch.empty((cells * N, C), dtype=x.dtype, device=x.device)
+    _lib.call('tss_adaptive_pool_fwd', x=x, out=buf, N=N, H=H, W=W, C=C, bins=_HostInts(bins),
+              nbins=len(bins), dtype=dtype_code(x.dtype))
+    return buf, split_pool_buffer(buf, N, C, bins)
+
+
+def split_pool_buffer(buf, N, C, bins):
+    outs, off = [], 0
+    for b in bins:
+        outs.append(buf[off:off + N * b * b].view(N, b, b, C).permute(0, 3, 1, 2))
+        off += N * b * b
+    return outs
+
+
+def adaptive_pool_bwd(dbuf, dx, bins=PYRAMID_BINS, accumulate=False):
+    N, C, H, W, ld = _g(dx, 'adaptive_pool_bwd')
+    if ld != C:
+        raise RuntimeError('adaptive_pool_bwd: pitched gradient not supported')
+    _lib.call('tss_adaptive_pool_bwd', dout=dbuf, dx=dx, N=N, H=H, W=W, C=C, bins=_HostInts(bins),
+              nbins=len(bins), accumulate=int(accumulate), dtype=dtype_code(dx.dtype))
+    return dx
+
+
+class _HostInts:
+    """A small host int array argument (``const int*`` read by the launcher, not a kernel)."""
+
+    def __init__(self, values):
+        import ctypes
+        self.values = tuple(int(v) for v in values)
+        self.array = (ctypes.c_int * len(self.values))(*self.values)
+
+
+def bilinear_fwd(x, Ho, Wo, out=None):
+    N, C, Hi, Wi, ldx = _g(x, 'bilinear_fwd')
+    if out is None:
+        out = empty_nhwc(N, C, Ho, Wo, x.dtype, x.device)
+    _lib.call('tss_bilinear_fwd', x=x, y=out, N=N, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, C=C, ldx=ldx,
+              ldy=_g(out, 'bilinear_fwd')[4], dtype=dtype_code(x.dtype))
+    return out
+
+
+def bilinear_bwd(dy, Hi, Wi):
+    N, C, Ho, Wo, lddy = _g(dy, 'bilinear_bwd')
+    dx = empty_nhwc(N, C, Hi, Wi, dy.dtype, dy.device)
+    _lib.call('tss_bilinear_bwd', dy=dy, dx=dx, N=N, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, C=C, lddy=lddy,
+              lddx=C, dtype=dtype_code(dy.dtype))
+    return dx
+
+
+def upsample_logits_fwd(x, Ho, Wo):
+    """NHWC (pitched) class scores -> NCHW-contiguous (N, C, Ho, Wo)."""
+    N, C, Hi, Wi, ldx = _g(x, 'upsample_logits_fwd')
+    y = torch.empty((N, C, Ho, Wo), dtype=x.dtype, device=x.device)
+    _lib.call('tss_upsample_logits_fwd', x=x, y=y, N=N, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, C=C, ldx=ldx,
+              dtype=dtype_code(x.dtype))
+    return y
+
+
+def upsample_logits_bwd(dy, Hi, Wi, pitch):
+    """NCHW-contiguous gradient -> NHWC gradient (N, C, Hi, Wi) with channel pitch ``pitch``."""
+    N, C, Ho, Wo = dy.shape
+    if not dy.is_contiguous():
+        dy = dy.contiguous()
+    acc = torch.zeros((N, Hi, Wi, pitch), dtype=torch.float32, device=dy.device)
+    _lib.call('tss_upsample_logits_bwd', dy=dy, dx32=acc, N=N, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, C=C,
+              lddx=pitch, dtype=dtype_code(dy.dtype))
+    if dy.dtype != torch.float32:
+        acc = cast_from_f32(acc, dy.dtype)
+    return acc[..., :C].permute(0, 3, 1, 2)
+
+
+def bilinear_nchw_f32(x, Ho, Wo):
+    N, C, Hi, Wi = x.shape
+    y = torch.empty((N, C, Ho, Wo), dtype=torch.float32, device=x.device)
+    _lib.call('tss_bilinear_nchw_f32', x=x, y=y, NC=N * C, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo)
+    return y
+
+
+# ------------------------------------------------------------------ loss / metrics -----
+def ce_forward(logits, target, ignore_index, want_grad, want_pixel_loss=False):
+    """-> loss (fp32 scalar tensor), dlogits (or None), pixel_loss (or None), nvalid (int64 (1,))."""
+    N, C, H, W = logits.shape
+    if not logits.is_contiguous():
+        logits = logits.contiguous()
+    if target.dtype != torch.int64 or not target.is_contiguous():
+        target = target.long().contiguous()
+    dev = logits.device
+    nvalid = torch.empty(1, dtype=torch.int64, device=dev)
+    _lib.call('tss_ce_count_valid', target=target, n=target.numel(), ignore_index=ignore_index, nvalid=nvalid)
+    loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+    dlogits = torch.empty_like(logits) if want_grad else None
+    pixel = torch.empty((N, H, W), dtype=torch.float32, device=dev) if want_pixel_loss else None
+    _lib.call('tss_ce_fwd', logits=logits, target=target, N=N, C=C, HW=H * W, ignore_index=ignore_index,
+              nvalid=nvalid, loss_sum=loss_sum, pixel_loss=pixel, dlogits=dlogits,
+              dtype=dtype_code(logits.dtype))
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    _lib.call('tss_ce_finalize', loss_sum=loss_sum, nvalid=nvalid, loss=loss)
+    return loss, dlogits, pixel, nvalid
+
+
+def confusion_from_labels(pred, target, num_classes, cm):
+    """cm (int64 (C,C), device) += histogram of (target, pred)."""
+    pred = pred.long().contiguous().view(-1)
+    target = target.long().contiguous().view(-1)
+    _lib.call('tss_confusion_from_labels', pred=pred, target=target, n=pred.numel(), C=num_classes, cm=cm)
+    return cm
+
+
+def confusion_from_logits(logits, target, cm, want_pred=False):
+    N, C, H, W = logits.shape
+    if not logits.is_contiguous():
+        logits = logits.contiguous()
+    target = target.long().contiguous()
+    pred = torch.empty((N, H, W), dtype=torch.int64, device=logits.device) if want_pred else None
+    _lib.call('tss_confusion_from_logits', logits=logits, target=target, N=N, C=C, HW=H * W, cm=cm,
+              pred_out=pred, dtype=dtype_code(logits.dtype))
+    return pred
+
+
+def adamw_step(p, g, m, v, hyper, grad_scale=1.0):
+    _lib.call('tss_adamw_step', p=p, g=g, m=m, v=v, n=p.numel(), hyper=hyper, grad_scale=float(grad_scale))
