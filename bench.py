@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Fast-SCNN training, bf16, 12 crops of 768x768 per GPU, softmax-CE
+with ignore_index=255, data-parallel over N B200s (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` = images/s of the whole job with the batch resident in
+HBM; `e2e` = the same metric through the public engine API (create_segmentation_trainer) with the
+batch in pinned HOST memory (H2D copy + loss read-back inside the timed region); `roofline` =
+the dominant kernel of the step timed alone with CUDA events; `cpu_baseline` = the CPU oracle
+(a restatement of the reference's own stock-PyTorch path) on this box's host cores.
+`--impl reference` times that CPU path alone, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'fastscnn_train_images_per_sec'
+UNIT = 'img/s'
+BATCH, CROP, CLASSES = 12, 768, 19
+CPU_SAMPLE_BATCH = 2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of a CUDA graph')
+    ap.add_argument('--kernels', action='store_true', help='also dump the per-kernel table to stderr')
+    return ap.parse_args()
+
+
+def synthetic_batch(n, size, seed, device):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    x = torch.randn(n, 3, size, size, generator=g, device=device)
+    y = torch.randint(0, CLASSES, (n, size, size), generator=g, device=device)
+    y[torch.rand(n, size, size, generator=g, device=device) < 0.1] = 255
+    return x, y
+
+
+# ------------------------------------------------------------------ CPU arm -----------------
+def cpu_train_throughput(steps, warmup, batch=CPU_SAMPLE_BATCH):
+    """The reference's path (stock PyTorch fp32 on the host cores) restated by the oracle:
+    forward (train mode) + CE(ignore 255) + backward + AdamW on `batch` crops of 768x768."""
+    from oracle.init_state import init_state
+    from oracle.train_step import AdamW, split_state, train_step
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = split_state(init_state('fastscnn', 0))
+    opt = AdamW(sd, lr=1e-3, weight_decay=1e-5)
+    x, y = synthetic_batch(batch, CROP, 1234, 'cpu')
+    for _ in range(warmup):
+        train_step('fastscnn', sd, opt, x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        train_step('fastscnn', sd, opt, x, y)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
+    value, spt, cores = cpu_train_throughput(steps, warmup)
+    sample = ('%d steps of %d crops %dx%d (of the %d-crop step), fp32, %d torch threads'
+              % (steps, CPU_SAMPLE_BATCH, CROP, CROP, BATCH, cores))
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warmup, 'ms_per_step': spt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'Fast-SCNN train step (fwd+CE ignore255+bwd+AdamW), 19 classes, 768x768 crops',
+                   'per_gpu_batch': BATCH, 'sample_batch': CPU_SAMPLE_BATCH},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+# ------------------------------------------------------------------ clocks ------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------ roofline ----------------
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs'
+    except Exception:
+        return 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
+
+
+def time_kernel(fn, iters=20, flush=None):
+    """Average device time of `fn()` in ms: CUDA events on the launching stream, L2 flushed
+    (a 256 MB write) before every timed launch."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        total += a.elapsed_time(b)
+    return total / iters
+
+
+def kernel_table(device):
+    """Per-launch time and algorithmic bytes (SURVEY.md section 8d formulas) of the kernels of one
+    training step at the TRN shapes, each timed alone.  Returns rows sorted by share of the step."""
+    from torch_semantic_segmentation_b200 import ops
+    bf = torch.bfloat16
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    N = BATCH
+    rows = []
+
+    def act(C, div):
+        return ops.empty_nhwc(N, C, CROP // div, CROP // div, bf, device).normal_()
+
+    def add(name, count, nbytes, fn):
+        ms = time_kernel(fn, 10, flush)
+        rows.append({'kernel': name, 'launches_per_step': count, 'ms': ms, 'bytes': nbytes,
+                     'gbs': nbytes / ms / 1e6, 'share_ms': ms * count})
+
+    px = lambda div: N * (CROP // div) ** 2
+    # final x8 up-sampling of the class scores + fused CE + its backward (the 269 MB logits tensor)
+    small = ops.empty_nhwc(N, CLASSES, CROP // 8, CROP // 8, bf, device, pitch=32).normal_()
+    logits = torch.empty(N, CLASSES, CROP, CROP, dtype=bf, device=device).normal_()
+    target = torch.randint(0, CLASSES, (N, CROP, CROP), device=device)
+    add('upsample_logits_fwd', 1, 2 * CLASSES * (px(8) + px(1)), lambda: ops.upsample_logits_fwd(small, CROP, CROP))
+    add('ce_fwd(+grad)', 1, px(1) * (2 * CLASSES * 2 + 8), lambda: ops.ce_forward(logits, target, 255, True))
+    add('upsample_logits_bwd', 1, 2 * CLASSES * px(1) + 4 * 32 * px(8), lambda: ops.upsample_logits_bwd(logits, CROP // 8, CROP // 8, 32))
+    # stem
+    x = torch.randn(N, 3, CROP, CROP, device=device)
+    w = torch.randn(32, 3, 3, 3, device=device)
+    st = torch.zeros(64, device=device)
+    y2 = act(32, 2)
+    add('stem3x3s2_fwd', 1, 4 * 3 * px(1) + 2 * 32 * px(2), lambda: ops.stem_fwd(x, w, bf, stats=st))
+    add('stem3x3s2_wgrad', 1, 4 * 3 * px(1) + 2 * 32 * px(2), lambda: ops.stem_wgrad(x, y2, torch.zeros_like(w)))
+    # BatchNorm apply / backward on the largest activation (32 ch @ 1/2)
+    sc = torch.ones(32, device=device)
+    add('bn_apply 32ch@1/2', 1, 2 * 2 * 32 * px(2), lambda: ops.bn_apply(y2, sc, sc, relu=True))
+    add('bn_backward 32ch@1/2 (2 kernels)', 1, 2 * 32 * px(2) * (3 + 4), lambda: ops.bn_backward(y2, y2, y2, sc, sc, sc, True))
+    # depthwise: the biggest (32 ch, s2, 1/2 -> 1/4) and the classifier / fusion size (128 ch @ 1/8)
+    for C, div, s, d, cnt in [(32, 2, 2, 1, 1), (128, 8, 1, 1, 2), (128, 8, 1, 4, 1), (384, 8, 2, 1, 1), (384, 16, 1, 1, 2)]:
+        xi = act(C, div)
+        wd = torch.randn(C, 1, 3, 3, device=device)
+        sd = torch.zeros(2 * C, device=device)
+        yo = ops.dwconv_fwd(xi, wd, s, d)
+        io = 2 * C * (px(div) + px(div * s))
+        add('dwconv_fwd C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_fwd(xi, wd, s, d, stats=sd))
+        add('dwconv_dgrad C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_dgrad(yo, wd, xi.shape[2], xi.shape[3], s, d))
+        add('dwconv_wgrad C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_wgrad(xi, yo, torch.zeros_like(wd), s, d))
+    # pointwise GEMMs (impl 0 until the tcgen05 kernel lands)
+    for K, Nc, div, cnt in [(32, 48, 4, 1), (64, 384, 8, 1), (128, 128, 8, 3), (64, 128, 8, 1), (384, 64, 16, 3), (64, 384, 16, 3)]:
+        xi = act(K, div)
+        wp = torch.randn(Nc, K, 1, 1, device=device) * 0.05
+        yo = act(Nc, div)
+        sp = torch.zeros(2 * Nc, device=device)
+        io = 2 * px(div) * (K + Nc)
+        add('pwconv_fwd %d->%d @1/%d' % (K, Nc, div), cnt, io, lambda: ops.pwconv_fwd(xi, wp, stats=sp))
+        add('pwconv_dgrad %d->%d @1/%d' % (K, Nc, div), cnt, io, lambda: ops.pwconv_dgrad(yo, wp))
+        add('pwconv_wgrad %d->%d @1/%d' % (K, Nc, div), cnt, io, lambda: ops.pwconv_wgrad(xi, yo, torch.zeros_like(wp)))
+    rows.sort(key=lambda r: -r['share_ms'])
+    return rows
+
+
+# ------------------------------------------------------------------ our arm -----------------
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product has no CPU path')
+    import torch.distributed as dist
+    from torch_semantic_segmentation_b200 import _lib
+    from torch_semantic_segmentation_b200.distributed import GradientAllReducer, broadcast_parameters
+    from torch_semantic_segmentation_b200.engine import create_segmentation_trainer
+    from torch_semantic_segmentation_b200.functional import unit_loss_grad
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', init_method='env://', device_id=device)
+    torch.manual_seed(0)
+    model = fastscnn(3, CLASSES).to(device).set_compute_dtype(torch.bfloat16)
+    broadcast_parameters(model)
+    opt = FlatAdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    reducer = GradientAllReducer(opt, num_buckets=4).install()
+    loss_fn = CrossEntropyLoss(ignore_index=255)
+    x, y = synthetic_batch(BATCH, CROP, 1234 + rank, device)
+    model.train()
+
+    def step():
+        opt.zero_grad()
+        out = model(x)
+        loss = loss_fn(out, y)
+        with unit_loss_grad():
+            loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = _lib.launch_count() - launches0
+    ms_total = float(ms)
+    value = world * BATCH * args.steps / (ms_total / 1e3)
+
+    # ---- end to end: the public engine API, batch in pinned host memory -------------------
+    xh, yh = x.cpu().pin_memory(), y.cpu().pin_memory()
+    trainer = create_segmentation_trainer(model, opt, loss_fn, device, use_f16=True, logging=False)
+    trainer.run([(xh, yh)] * 2)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    trainer.run([(xh, yh)] * args.steps)
+    t1.record()
+    barrier()
+    ems = torch.tensor([t0.elapsed_time(t1)], device=device)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = world * BATCH * args.steps / (float(ems) / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (timed alone, L2 flushed) -------------------------
+    peak, peak_src = measured_peak()
+    rows = kernel_table(device)
+    if args.kernels:
+        for r in rows:
+            print('%-44s x%d  %8.3f ms  %8.1f MB  %7.0f GB/s  share %7.3f ms' % (
+                r['kernel'], r['launches_per_step'], r['ms'], r['bytes'] / 1e6, r['gbs'], r['share_ms']), file=sys.stderr)
+    top = rows[0]
+    roofline = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['gbs'], 'peak': peak, 'unit': 'GB/s',
+                'frac': top['gbs'] / peak, 'traffic': None, 'peak_source': peak_src,
+                'launch_ms': top['ms'], 'algorithmic_bytes': top['bytes']}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v, spt, cores = cpu_train_throughput(3, 1)
+        cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': '3 steps of %d crops %dx%d (of the %d-crop step), fp32 oracle, %d torch threads'
+                         % (CPU_SAMPLE_BATCH, CROP, CROP, BATCH, cores)}
+
+    print(json.dumps({
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': 'Fast-SCNN training step (fwd + CE ignore_index=255 + bwd + grad all-reduce + AdamW), '
+                               '19 classes, 12 crops of 768x768 per GPU, random-init weights',
+                   'global_batch': world * BATCH, 'parallelism': 'dp%d' % world,
+                   'l2': 'per-step working set (>3 GB of activations) far exceeds the 126 MB L2',
+                   'launch_mode': 'eager'},
+        'loss': float(loss),
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': xh.numel() * 4 + yh.numel() * 8,
+                'd2h_bytes_per_step': 4, 'ms_per_step': float(ems) / args.steps},
+        'gpu_launches': launches,
+        'clocks': clocks,
+        'roofline': roofline,
+        'cpu_baseline': cpu,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -130,3 +130,26 @@ def test_trainer_and_evaluator(fake_backend):
     assert float(es.metrics['accuracy']) == met['accuracy']
     np.testing.assert_array_equal(es.metrics['dice'].numpy(), met['dice'])
     assert np.isfinite(es.metrics['loss'])
+
+
+def test_flat_adamw_matches_oracle_adamw(fake_backend):
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    torch.manual_seed(0)
+    model = _no_dropout(fastscnn(3, 19))
+    opt = FlatAdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    # parameters now live in one arena and gradients accumulate in place
+    p0 = next(model.parameters())
+    assert p0.data_ptr() == opt.param_arena.data_ptr() and p0.grad.data_ptr() == opt.grad_arena.data_ptr()
+    trainer = create_segmentation_trainer(model, opt, CrossEntropyLoss(ignore_index=255), 'cpu', logging=False)
+    x, y = train_batch('fastscnn')
+    state = trainer.run([(x, y)] * 3, max_epochs=1)
+    sd = split_state(init_state('fastscnn', 0))
+    oopt = OracleAdamW(sd, lr=1e-3, weight_decay=1e-5)
+    ref = [train_step('fastscnn', sd, oopt, x, y, dropout_mask=1.0) for _ in range(3)]
+    assert abs(state.output - ref[-1]) < 5e-3 * abs(ref[-1]), (state.output, ref)
+    assert opt.step_count == 3
+    # eval after training must see the updated weights and running statistics (cache invalidation)
+    with torch.no_grad():
+        out = model.eval()(x)
+        want = model_forward('fastscnn', {k: v.detach() for k, v in sd.items()}, x, False)
+    assert rel(out, want) < 5e-2

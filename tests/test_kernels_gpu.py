@@ -1,0 +1,415 @@
+"""Kernel parity on the GPU: every C-ABI entry point is called with CUDA tensors and compared
+with stock torch fp32 ops on the CPU (tests/fake_backend.py doubles as the per-kernel
+reference), on identical seeded inputs, at the Fast-SCNN / ContextNet shapes (SURVEY.md
+Appendix E, spatially reduced) plus ragged / odd shapes.
+
+Tolerances: fp32 activations 1e-4 relative (L2) -- observed ~1e-6; bf16 2e-2 relative with the
+inputs rounded to bf16 on both sides (so only accumulation order and the final rounding differ);
+integer results (confusion matrix, argmax, counts) bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import confusion as o_cm
+from tests.fake_backend import FakeBackend
+from torch_semantic_segmentation_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.bfloat16]
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def gen(seed):
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return g
+
+
+def pair(N, C, H, W, dtype, g, pitch=None, scale=1.0):
+    """(cpu, cuda) logical-NCHW / physical-NHWC tensors with identical contents and layout."""
+    ld = C if pitch is None else pitch
+    base = (torch.randn(N, H, W, ld, generator=g) * scale).to(dtype)
+    gb = base.cuda()
+    return base[..., :C].permute(0, 3, 1, 2), gb[..., :C].permute(0, 3, 1, 2)
+
+
+def both(name, kc, kg):
+    """Run entry point `name` on the CPU emulation (kc) and on the GPU through the C ABI (kg)."""
+    FakeBackend().call(name, kc)
+    _lib.backend().call(name, kg)
+    torch.cuda.synchronize()
+
+
+def dev(t):
+    return None if t is None else t.cuda()
+
+
+# ------------------------------------------------------------------ depthwise 3x3 ------
+DW_CASES = [  # C, stride, dilation, N, H, W
+    (32, 2, 1, 2, 40, 56), (48, 2, 1, 2, 20, 28), (384, 2, 1, 2, 16, 24), (384, 1, 1, 2, 12, 16),
+    (576, 1, 1, 2, 6, 8), (768, 1, 1, 2, 6, 8), (128, 1, 4, 2, 24, 40), (128, 1, 1, 2, 24, 40),
+    (192, 1, 1, 1, 9, 13), (288, 2, 1, 1, 9, 13), (64, 2, 1, 3, 7, 5), (8, 1, 1, 1, 1, 1), (40, 1, 1, 1, 5, 3),
+]
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('C,s,d,N,H,W', DW_CASES)
+def test_dwconv(C, s, d, N, H, W, dtype):
+    g = gen(C + H)
+    xc, xg = pair(N, C, H, W, dtype, g)
+    w = torch.randn(C, 1, 3, 3, generator=g) * 0.3
+    Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+    code = _lib.dtype_code(dtype)
+    # training form: raw output + BatchNorm statistics
+    yc, yg = pair(N, C, Ho, Wo, dtype, g)
+    sc, sg = torch.zeros(2 * C), torch.zeros(2 * C).cuda()
+    common = dict(N=N, Hi=H, Wi=W, C=C, stride=s, dilation=d, dtype=code)
+    both('tss_dwconv3x3_fwd', dict(x=xc, w=w, y=yc, scale=None, shift=None, flags=0, stats=sc, **common),
+         dict(x=xg, w=w.cuda(), y=yg, scale=None, shift=None, flags=0, stats=sg, **common))
+    assert rel(yg, yc) < TOL[dtype]
+    assert rel(sg, sc) < 1e-4
+    # inference form: folded BatchNorm + ReLU in the epilogue
+    scale, shift = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    both('tss_dwconv3x3_fwd', dict(x=xc, w=w, y=yc, scale=scale, shift=shift, flags=1, stats=None, **common),
+         dict(x=xg, w=w.cuda(), y=yg, scale=scale.cuda(), shift=shift.cuda(), flags=1, stats=None, **common))
+    assert rel(yg, yc) < TOL[dtype]
+    # dgrad / wgrad
+    dyc, dyg = pair(N, C, Ho, Wo, dtype, g)
+    dxc, dxg = pair(N, C, H, W, dtype, g)
+    both('tss_dwconv3x3_dgrad', dict(dy=dyc, w=w, dx=dxc, **common), dict(dy=dyg, w=w.cuda(), dx=dxg, **common))
+    assert rel(dxg, dxc) < TOL[dtype]
+    dwc = torch.randn(C, 1, 3, 3, generator=g)         # accumulate semantics
+    dwg = dwc.clone().cuda()
+    both('tss_dwconv3x3_wgrad', dict(x=xc, dy=dyc, dw=dwc, **common), dict(x=xg, dy=dyg, dw=dwg, **common))
+    assert rel(dwg, dwc) < 1e-4
+
+
+# ------------------------------------------------------------------ pointwise 1x1 ------
+PW_CASES = [  # K, Nc, N, H, W
+    (32, 48, 2, 20, 28), (48, 64, 2, 10, 14), (64, 384, 2, 10, 14), (384, 64, 2, 5, 7), (384, 96, 2, 3, 4),
+    (96, 576, 2, 3, 4), (576, 128, 2, 3, 4), (128, 768, 2, 3, 4), (768, 128, 2, 3, 4), (128, 32, 2, 1, 1),
+    (256, 128, 2, 3, 4), (128, 128, 2, 12, 20), (64, 128, 1, 12, 20), (128, 19, 2, 12, 20), (192, 32, 1, 9, 7),
+    (288, 48, 1, 9, 7), (32, 32, 1, 17, 3),
+]
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('K,Nc,N,H,W', PW_CASES)
+def test_pwconv_simt(K, Nc, N, H, W, dtype):
+    g = gen(K * 7 + Nc)
+    code = _lib.dtype_code(dtype)
+    M = N * H * W
+    xc, xg = pair(N, K, H, W, dtype, g)
+    w = torch.randn(Nc, K, 1, 1, generator=g) / math.sqrt(K)
+    ldy = Nc if Nc % 8 == 0 else (Nc + 7) // 8 * 8 + 8
+    yc, yg = pair(N, Nc, H, W, dtype, g, pitch=ldy)
+    sc, sg = torch.zeros(2 * Nc), torch.zeros(2 * Nc).cuda()
+    base = dict(M=M, K=K, Nc=Nc, ldx=K, ldy=ldy, ldr=0, impl=0, dtype=code, wp=None)
+    both('tss_pwconv_fwd', dict(x=xc, w=w, y=yc, scale=None, shift=None, res=None, flags=0, stats=sc, **base),
+         dict(x=xg, w=w.cuda(), y=yg, scale=None, shift=None, res=None, flags=0, stats=sg, **base))
+    assert rel(yg, yc) < TOL[dtype]
+    assert rel(sg, sc) < 1e-4
+    if Nc % 8 == 0:
+        rc, rg = pair(N, Nc, H, W, dtype, g)
+        scale, shift = torch.rand(Nc, generator=g) + 0.5, torch.randn(Nc, generator=g)
+        base['ldr'] = Nc
+        both('tss_pwconv_fwd', dict(x=xc, w=w, y=yc, scale=scale, shift=shift, res=rc, flags=1, stats=None, **base),
+             dict(x=xg, w=w.cuda(), y=yg, scale=scale.cuda(), shift=shift.cuda(), res=rg, flags=1, stats=None, **base))
+        assert rel(yg, yc) < TOL[dtype]
+    else:
+        bias = torch.randn(Nc, generator=g)
+        both('tss_pwconv_fwd', dict(x=xc, w=w, y=yc, scale=None, shift=bias, res=None, flags=0, stats=None, **base),
+             dict(x=xg, w=w.cuda(), y=yg, scale=None, shift=bias.cuda(), res=None, flags=0, stats=None, **base))
+        assert rel(yg, yc) < TOL[dtype]
+        pad = yg.permute(0, 2, 3, 1)      # pad columns written by the kernel must be zero
+        full = torch.as_strided(pad, (N, H, W, ldy), (H * W * ldy, W * ldy, ldy, 1))
+        assert float(full[..., Nc:(Nc + 7) // 8 * 8].abs().max()) == 0.0
+    # backward: gradient buffers with zeroed pad columns
+    dbase_c = torch.zeros(N, H, W, ldy, dtype=dtype)
+    dbase_c[..., :Nc] = torch.randn(N, H, W, Nc, generator=g).to(dtype)
+    dyc, dyg = dbase_c[..., :Nc].permute(0, 3, 1, 2), dbase_c.cuda()[..., :Nc].permute(0, 3, 1, 2)
+    dxc, dxg = pair(N, K, H, W, dtype, g)
+    both('tss_pwconv_dgrad', dict(dy=dyc, w=w, wpT=None, dx=dxc, M=M, K=K, Nc=Nc, lddy=ldy, lddx=K, impl=0, dtype=code),
+         dict(dy=dyg, w=w.cuda(), wpT=None, dx=dxg, M=M, K=K, Nc=Nc, lddy=ldy, lddx=K, impl=0, dtype=code))
+    assert rel(dxg, dxc) < TOL[dtype]
+    dwc = torch.randn(Nc, K, 1, 1, generator=g)
+    dbc = torch.randn(Nc, generator=g)
+    dwg, dbg = dwc.clone().cuda(), dbc.clone().cuda()
+    both('tss_pwconv_wgrad', dict(x=xc, dy=dyc, dw=dwc, db=dbc, M=M, K=K, Nc=Nc, ldx=K, lddy=ldy, impl=0, dtype=code),
+         dict(x=xg, dy=dyg, dw=dwg, db=dbg, M=M, K=K, Nc=Nc, ldx=K, lddy=ldy, impl=0, dtype=code))
+    assert rel(dwg, dwc) < 1e-4 and rel(dbg, dbc) < 1e-4
+
+
+def test_pwconv_pitched_input_from_concat_buffer():
+    g = gen(5)
+    catc, catg = pair(2, 256, 3, 5, torch.float32, g)
+    w = torch.randn(32, 128, 1, 1, generator=g) * 0.1
+    yc, yg = pair(2, 32, 3, 5, torch.float32, g)
+    kw = dict(M=30, K=128, Nc=32, ldx=256, ldy=32, ldr=0, impl=0, dtype=0, wp=None, scale=None, shift=None, res=None, flags=0, stats=None)
+    both('tss_pwconv_fwd', dict(x=catc[:, 128:], w=w, y=yc, **kw), dict(x=catg[:, 128:], w=w.cuda(), y=yg, **kw))
+    assert rel(yg, yc) < 1e-5
+
+
+# ------------------------------------------------------------------ stem ---------------
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('N,H,W', [(2, 64, 96), (1, 32, 32), (3, 34, 70)])
+def test_stem(N, H, W, dtype):
+    g = gen(H)
+    code = _lib.dtype_code(dtype)
+    x = torch.randn(N, 3, H, W, generator=g)
+    w = torch.randn(32, 3, 3, 3, generator=g) * 0.2
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    yc, yg = pair(N, 32, Ho, Wo, dtype, g)
+    sc, sg = torch.zeros(64), torch.zeros(64).cuda()
+    kw = dict(N=N, H=H, W=W, Cout=32, dtype=code)
+    both('tss_stem3x3s2_fwd', dict(x=x, w=w, y=yc, scale=None, shift=None, flags=0, stats=sc, **kw),
+         dict(x=x.cuda(), w=w.cuda(), y=yg, scale=None, shift=None, flags=0, stats=sg, **kw))
+    assert rel(yg, yc) < TOL[dtype] and rel(sg, sc) < 1e-4
+    scale, shift = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g)
+    both('tss_stem3x3s2_fwd', dict(x=x, w=w, y=yc, scale=scale, shift=shift, flags=1, stats=None, **kw),
+         dict(x=x.cuda(), w=w.cuda(), y=yg, scale=scale.cuda(), shift=shift.cuda(), flags=1, stats=None, **kw))
+    assert rel(yg, yc) < TOL[dtype]
+    dyc, dyg = pair(N, 32, Ho, Wo, dtype, g)
+    dwc = torch.randn(32, 3, 3, 3, generator=g)
+    dwg = dwc.clone().cuda()
+    both('tss_stem3x3s2_wgrad', dict(x=x, dy=dyc, dw=dwc, **kw), dict(x=x.cuda(), dy=dyg, dw=dwg, **kw))
+    assert rel(dwg, dwc) < 1e-4
+
+
+# ------------------------------------------------------------------ batch norm ---------
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('C,N,H,W', [(32, 2, 20, 28), (384, 2, 5, 7), (48, 3, 9, 5), (768, 2, 3, 4), (128, 4, 1, 1)])
+def test_batchnorm_family(C, N, H, W, dtype):
+    g = gen(C + N)
+    code = _lib.dtype_code(dtype)
+    M = N * H * W
+    yc, yg = pair(N, C, H, W, dtype, g)
+    # finalize
+    stats = torch.stack([yc.float().sum((0, 2, 3)), (yc.float() ** 2).sum((0, 2, 3))]).reshape(-1)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    outs_c = [torch.empty(C) for _ in range(4)]
+    outs_g = [torch.empty(C).cuda() for _ in range(4)]
+    rm, rv, nbt = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5, torch.tensor(3)
+    rmg, rvg, nbtg = rm.clone().cuda(), rv.clone().cuda(), nbt.clone().cuda()
+    names = ('scale', 'shift', 'mean', 'rstd')
+    both('tss_bn_finalize', dict(stats=stats, count=M, gamma=gamma, beta=beta, running_mean=rm, running_var=rv,
+                                 num_batches_tracked=nbt, momentum=0.1, eps=1e-5, C=C, **dict(zip(names, outs_c))),
+         dict(stats=stats.cuda(), count=M, gamma=gamma.cuda(), beta=beta.cuda(), running_mean=rmg, running_var=rvg,
+              num_batches_tracked=nbtg, momentum=0.1, eps=1e-5, C=C, **dict(zip(names, outs_g))))
+    for a, b in zip(outs_g, outs_c):
+        assert rel(a, b) < 1e-5
+    assert rel(rmg, rm) < 1e-6 and rel(rvg, rv) < 1e-6 and int(nbtg) == 4
+    # against nn.functional.batch_norm's own statistics
+    want_var = yc.float().var((0, 2, 3), unbiased=False)
+    assert rel(outs_g[3], 1 / torch.sqrt(want_var + 1e-5)) < 1e-4
+    fc, fg = [torch.empty(C), torch.empty(C)], [torch.empty(C).cuda(), torch.empty(C).cuda()]
+    both('tss_bn_fold', dict(gamma=gamma, beta=beta, running_mean=rm, running_var=rv, eps=1e-5, scale=fc[0], shift=fc[1], C=C),
+         dict(gamma=gamma.cuda(), beta=beta.cuda(), running_mean=rmg, running_var=rvg, eps=1e-5, scale=fg[0], shift=fg[1], C=C))
+    assert rel(fg[0], fc[0]) < 1e-6 and rel(fg[1], fc[1]) < 1e-6
+    # apply (+ second branch, + residual, + relu)
+    scale, shift, mean, rstd = outs_c
+    y2c, y2g = pair(N, C, H, W, dtype, g)
+    rc, rg = pair(N, C, H, W, dtype, g)
+    zc, zg = pair(N, C, H, W, dtype, g)
+    kw = dict(M=M, C=C, ldy=C, ldy2=C, ldr=C, ldz=C, dtype=code)
+    for use2, user, relu in [(False, False, 0), (False, True, 1), (True, False, 1), (False, False, 1)]:
+        both('tss_bn_apply', dict(y=yc, scale=scale, shift=shift, y2=y2c if use2 else None, scale2=gamma if use2 else None,
+                                  shift2=beta if use2 else None, res=rc if user else None, z=zc, flags=relu, **kw),
+             dict(y=yg, scale=scale.cuda(), shift=shift.cuda(), y2=y2g if use2 else None, scale2=gamma.cuda() if use2 else None,
+                  shift2=beta.cuda() if use2 else None, res=rg if user else None, z=zg, flags=relu, **kw))
+        assert rel(zg, zc) < TOL[dtype]
+    # backward (z from the last apply: relu, no residual)
+    dzc, dzg = pair(N, C, H, W, dtype, g)
+    for relu in (1, 0):
+        sums_c, sums_g = torch.zeros(2 * C), torch.zeros(2 * C).cuda()
+        kb = dict(M=M, C=C, lddz=C, ldz=C, ldy=C, flags=relu, dtype=code)
+        both('tss_bn_bwd_reduce', dict(dz=dzc, z=zc if relu else None, y=yc, mean=mean, rstd=rstd, sums=sums_c, **kb),
+             dict(dz=dzg, z=zg if relu else None, y=yg, mean=mean.cuda(), rstd=rstd.cuda(), sums=sums_g, **kb))
+        assert rel(sums_g, sums_c) < 1e-4
+        dyc, dyg = pair(N, C, H, W, dtype, g)
+        drc, drg = pair(N, C, H, W, dtype, g)
+        dgc, dbc = torch.randn(C, generator=g), torch.randn(C, generator=g)
+        dgg, dbg = dgc.clone().cuda(), dbc.clone().cuda()
+        both('tss_bn_bwd_apply', dict(dz=dzc, z=zc if relu else None, y=yc, mean=mean, rstd=rstd, gamma=gamma, sums=sums_c,
+                                      dy=dyc, dres=drc, dgamma=dgc, dbeta=dbc, lddy=C, lddres=C, **kb),
+             dict(dz=dzg, z=zg if relu else None, y=yg, mean=mean.cuda(), rstd=rstd.cuda(), gamma=gamma.cuda(), sums=sums_c.cuda(),
+                  dy=dyg, dres=drg, dgamma=dgg, dbeta=dbg, lddy=C, lddres=C, **kb))
+        assert rel(dyg, dyc) < TOL[dtype] and rel(drg, drc) < TOL[dtype]
+        assert rel(dgg, dgc) < 1e-5 and rel(dbg, dbc) < 1e-5
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_elementwise_helpers(dtype):
+    g = gen(2)
+    code = _lib.dtype_code(dtype)
+    ac, ag = pair(2, 64, 5, 7, dtype, g, pitch=96)
+    bc, bg = pair(2, 64, 5, 7, dtype, g)
+    oc, og = pair(2, 64, 5, 7, dtype, g)
+    kw = dict(M=70, C=64, dtype=code)
+    both('tss_add', dict(a=ac, b=bc, out=oc, lda=96, ldb=64, ldo=64, **kw), dict(a=ag, b=bg, out=og, lda=96, ldb=64, ldo=64, **kw))
+    assert rel(og, oc) < TOL[dtype]
+    both('tss_relu_bwd', dict(dz=ac, z=bc, g=oc, lddz=96, ldz=64, ldg=64, **kw), dict(dz=ag, z=bg, g=og, lddz=96, ldz=64, ldg=64, **kw))
+    assert rel(og, oc) == 0.0
+    both('tss_copy_rows', dict(src=bc, dst=ac, lds=64, ldd=96, **kw), dict(src=bg, dst=ag, lds=64, ldd=96, **kw))
+    assert rel(ag, ac) == 0.0
+    src = torch.randn(4096, generator=g)
+    dc, dg = torch.empty(4096, dtype=dtype), torch.empty(4096, dtype=dtype).cuda()
+    both('tss_cast_from_f32', dict(src=src, dst=dc, n=4096, dtype=code), dict(src=src.cuda(), dst=dg, n=4096, dtype=code))
+    assert rel(dg, dc) == 0.0
+    s = torch.tensor([0.4])
+    both('tss_scale_inplace', dict(x=dc, s=s, n=4096, dtype=code), dict(x=dg, s=s.cuda(), n=4096, dtype=code))
+    assert rel(dg, dc) < TOL[dtype]
+
+
+# ------------------------------------------------------------------ pooling / resize ---
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('N,H,W', [(2, 24, 24), (1, 32, 64), (2, 5, 7), (3, 1, 2)])
+def test_adaptive_pool(N, H, W, dtype):
+    g = gen(H * W)
+    C, bins = 128, (1, 2, 3, 6)
+    code = _lib.dtype_code(dtype)
+    xc, xg = pair(N, C, H, W, dtype, g)
+    cells = sum(b * b for b in bins)
+    oc, og = torch.empty(cells * N, C, dtype=dtype), torch.empty(cells * N, C, dtype=dtype).cuda()
+    hb = ops._HostInts(bins)
+    kw = dict(N=N, H=H, W=W, C=C, bins=hb, nbins=4, dtype=code)
+    both('tss_adaptive_pool_fwd', dict(x=xc, out=oc, **kw), dict(x=xg, out=og, **kw))
+    assert rel(og, oc) < TOL[dtype]
+    dc = torch.randn(cells * N, C, generator=g).to(dtype)
+    dxc, dxg = pair(N, C, H, W, dtype, g)
+    for acc in (0, 1):
+        both('tss_adaptive_pool_bwd', dict(dout=dc, dx=dxc, accumulate=acc, **kw), dict(dout=dc.cuda(), dx=dxg, accumulate=acc, **kw))
+        assert rel(dxg, dxc) < TOL[dtype]
+
+
+RESIZE = [(2, 32, 6, 6, 24, 24), (2, 32, 1, 1, 24, 24), (1, 32, 3, 3, 32, 64), (2, 128, 6, 8, 24, 32), (1, 128, 5, 7, 20, 28),
+          (1, 16, 2, 2, 5, 7), (1, 8, 7, 9, 7, 9), (1, 8, 12, 16, 5, 6)]
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('N,C,Hi,Wi,Ho,Wo', RESIZE)
+def test_bilinear_nhwc(N, C, Hi, Wi, Ho, Wo, dtype):
+    g = gen(Hi * Wo)
+    code = _lib.dtype_code(dtype)
+    xc, xg = pair(N, C, Hi, Wi, dtype, g)
+    yc, yg = pair(N, C, Ho, Wo, dtype, g, pitch=C + 32)       # e.g. a slice of the concat buffer
+    kw = dict(N=N, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, C=C, dtype=code)
+    both('tss_bilinear_fwd', dict(x=xc, y=yc, ldx=C, ldy=C + 32, **kw), dict(x=xg, y=yg, ldx=C, ldy=C + 32, **kw))
+    assert rel(yg, yc) < TOL[dtype]
+    dxc, dxg = pair(N, C, Hi, Wi, dtype, g)
+    both('tss_bilinear_bwd', dict(dy=yc, dx=dxc, lddy=C + 32, lddx=C, **kw), dict(dy=yg, dx=dxg, lddy=C + 32, lddx=C, **kw))
+    assert rel(dxg, dxc) < TOL[dtype]
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('N,C,Hi,Wi,s', [(2, 19, 12, 20, 8), (1, 19, 4, 4, 8), (2, 19, 3, 5, 8), (1, 11, 6, 7, 8), (1, 19, 1, 1, 8)])
+def test_upsample_logits(N, C, Hi, Wi, s, dtype):
+    g = gen(Hi + Wi)
+    code = _lib.dtype_code(dtype)
+    Ho, Wo = Hi * s, Wi * s
+    xc, xg = pair(N, C, Hi, Wi, dtype, g, pitch=32)
+    yc = torch.empty(N, C, Ho, Wo, dtype=dtype)
+    yg = torch.empty(N, C, Ho, Wo, dtype=dtype).cuda()
+    kw = dict(N=N, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, C=C, dtype=code)
+    both('tss_upsample_logits_fwd', dict(x=xc, y=yc, ldx=32, **kw), dict(x=xg, y=yg, ldx=32, **kw))
+    assert rel(yg, yc) < TOL[dtype]
+    dy = torch.randn(N, C, Ho, Wo, generator=g).to(dtype)
+    ac, ag = torch.zeros(N, Hi, Wi, 32), torch.zeros(N, Hi, Wi, 32).cuda()
+    both('tss_upsample_logits_bwd', dict(dy=dy, dx32=ac, lddx=32, **kw), dict(dy=dy.cuda(), dx32=ag, lddx=32, **kw))
+    assert rel(ag, ac) < 1e-4
+    assert float(ag[..., C:].abs().max()) == 0.0
+
+
+def test_bilinear_nchw_shrink():
+    g = gen(9)
+    x = torch.randn(2, 3, 64, 96, generator=g)
+    for Ho, Wo in [(16, 24), (32, 48), (8, 12)]:
+        yc, yg = torch.empty(2, 3, Ho, Wo), torch.empty(2, 3, Ho, Wo).cuda()
+        kw = dict(NC=6, Hi=64, Wi=96, Ho=Ho, Wo=Wo)
+        both('tss_bilinear_nchw_f32', dict(x=x, y=yc, **kw), dict(x=x.cuda(), y=yg, **kw))
+        assert rel(yg, yc) < 1e-6
+
+
+# ------------------------------------------------------------------ loss ---------------
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('N,H,W,frac', [(2, 24, 32, 0.1), (1, 8, 4, 0.0), (3, 5, 12, 0.5), (1, 16, 16, 1.0)])
+def test_cross_entropy(N, H, W, frac, dtype):
+    g = gen(H + W)
+    logits = (torch.randn(N, 19, H, W, generator=g) * 3).to(dtype)
+    target = torch.randint(0, 19, (N, H, W), generator=g)
+    target[torch.rand(N, H, W, generator=g) < frac] = 255
+    lg = logits.cuda().requires_grad_(True)
+    loss, dlogits, pixel, nvalid = ops.ce_forward(lg, target.cuda(), 255, want_grad=True, want_pixel_loss=True)
+    torch.cuda.synchronize()
+    ref_in = logits.float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_in, target, ignore_index=255)
+    assert int(nvalid) == int((target != 255).sum())
+    if frac == 1.0:
+        assert math.isnan(float(loss)) and float(dlogits.float().abs().max()) == 0.0
+        return
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    assert rel(dlogits, ref_in.grad) < (1e-5 if dtype == torch.float32 else 1e-2)
+    ref_px = torch.nn.functional.cross_entropy(logits.float(), target, ignore_index=255, reduction='none')
+    assert rel(pixel, ref_px) < 1e-5
+
+
+# ------------------------------------------------------------------ confusion matrix ---
+@pytest.mark.parametrize('n', [0, 1, 7, 4096, 1024 * 2048 + 3])
+def test_confusion_from_labels_bit_exact(n):
+    rng = np.random.RandomState(n % 1000)
+    pred = rng.randint(0, 19, size=n)
+    target = rng.randint(0, 19, size=n)
+    target[rng.rand(n) < 0.1] = 255
+    if n > 8:
+        target[3] = -1
+        pred[5:64] = 7
+        target[5:64] = 7                 # a homogeneous run: exercises the warp aggregation
+    cm = torch.zeros(19, 19, dtype=torch.int64).cuda()
+    # odd offsets break 16-byte alignment of a view: the wrapper passes a fresh contiguous copy
+    ops.confusion_from_labels(torch.from_numpy(pred).cuda(), torch.from_numpy(target).cuda(), 19, cm)
+    ops.confusion_from_labels(torch.from_numpy(pred).cuda(), torch.from_numpy(target).cuda(), 19, cm)   # accumulates
+    want = o_cm.confusion_matrix(pred, target, 19)
+    assert (cm.cpu().numpy() == 2 * want).all()
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_confusion_from_logits_bit_exact(dtype):
+    g = gen(21)
+    logits = torch.randn(2, 19, 32, 64, generator=g).to(dtype)
+    logits[0, 3, 0, 0] = float('nan')
+    logits[0, :, 0, 1] = 1.0                       # all tied -> class 0
+    logits[1, 5, 2, 3] = logits[1, 9, 2, 3] = 50.0  # tie -> lowest index
+    target = torch.randint(0, 19, (2, 32, 64), generator=g)
+    target[torch.rand(2, 32, 64, generator=g) < 0.1] = 255
+    cm = torch.zeros(19, 19, dtype=torch.int64).cuda()
+    pred = ops.confusion_from_logits(logits.cuda(), target.cuda(), cm, want_pred=True)
+    want_pred = logits.float().argmax(1)
+    assert torch.equal(pred.cpu(), want_pred)
+    assert (o_cm.argmax_classes(logits.float().numpy()) == want_pred.numpy()).all()
+    assert (cm.cpu().numpy() == o_cm.confusion_matrix(want_pred.numpy(), target.numpy(), 19)).all()
+
+
+def test_adamw_flat_arena():
+    g = gen(33)
+    n = 10007
+    p = torch.randn(n, generator=g)
+    p_ref = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([p_ref], lr=1e-3, weight_decay=1e-5)
+    pg, m, v = p.clone().cuda(), torch.zeros(n).cuda(), torch.zeros(n).cuda()
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 1e-5, 0, 0, 0], dtype=torch.float32).cuda()
+    for step in range(3):
+        grad = torch.randn(n, generator=g)
+        p_ref.grad = grad.clone()
+        opt.step()
+        ops.adamw_step(pg, (grad * 2).cuda(), m, v, hyper, grad_scale=0.5)
+    assert rel(pg, p_ref) < 1e-6 and float(hyper[5]) == 3.0

@@ -42,6 +42,24 @@ def _unit_grad():
     return getattr(_tls, 'unit', False)
 
 
+_grad_ready_hook = None
+
+
+def set_grad_ready_hook(fn):
+    """``fn(param)`` is called from backward right after the kernels that produce ``param``'s
+    gradient have been enqueued (used by ``distributed.GradientAllReducer`` to launch bucket
+    all-reduces while the rest of backward is still running)."""
+    global _grad_ready_hook
+    _grad_ready_hook = fn
+
+
+def grad_ready(*params):
+    if _grad_ready_hook is not None:
+        for p in params:
+            if p is not None:
+                _grad_ready_hook(p)
+
+
 class ConvSpec:
     """Static description of one conv+BN block (built once per module)."""
 
@@ -84,6 +102,9 @@ class ConvBNAct(torch.autograd.Function):
                                                    update_running=bn.track_running_stats)
         z = ops.bn_apply(y, scale, shift, res=res, relu=spec.relu)
         ctx.spec, ctx.packed = spec, packed
+        ctx.params = (weight, gamma, beta)
+        ctx.arena = (getattr(weight, '_tss_grad', None), getattr(gamma, '_tss_grad', None),
+                     getattr(beta, '_tss_grad', None))
         ctx.has_res = res is not None
         ctx.in_hw = (x.shape[2], x.shape[3])
         ctx.save_for_backward(x, weight, gamma, y, z if spec.relu else None, mean, rstd)
@@ -95,12 +116,17 @@ class ConvBNAct(torch.autograd.Function):
         x, weight, gamma, y, z, mean, rstd = ctx.saved_tensors
         dz = ops.as_nhwc(dz)
         C = weight.shape[0]
-        dgb = ops.zeros_f32(2 * C, weight.device)
+        gw, gg, gb = ctx.arena       # FlatAdamW gradient-arena views: accumulate in place
+        if gg is None or gb is None:
+            dgb = ops.zeros_f32(2 * C, weight.device)
+            gg_out, gb_out = dgb[:C], dgb[C:]
+        else:
+            gg_out, gb_out = gg, gb
         want_dres = ctx.has_res and ctx.needs_input_grad[1]
         dy, dres = ops.bn_backward(dz, z, y, mean, rstd, gamma, spec.relu, want_dres=want_dres,
-                                   dgamma=dgb[:C], dbeta=dgb[C:])
+                                   dgamma=gg_out, dbeta=gb_out)
         dx = None
-        dw = torch.zeros_like(weight)
+        dw = gw if gw is not None else torch.zeros_like(weight)
         if spec.kind == 'pw':
             wpT = ctx.packed[1] if ctx.packed is not None else None
             impl = spec.impl if wpT is not None else 0
@@ -115,7 +141,9 @@ class ConvBNAct(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 raise RuntimeError('gradient w.r.t. the input image is not implemented')
             ops.stem_wgrad(x, dy, dw)
-        return dx, dres, dw, dgb[:C], dgb[C:], None, None
+        grad_ready(*ctx.params)
+        return (dx, dres, None if gw is not None else dw, None if gg is not None else gg_out,
+                None if gb is not None else gb_out, None, None)
 
 
 class ConvBias(torch.autograd.Function):
@@ -124,13 +152,17 @@ class ConvBias(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         y = ops.pwconv_fwd(x, weight, shift=bias)
-        ctx.save_for_backward(x, weight)
+        ctx.save_for_backward(x, weight, bias)
+        ctx.params = (weight, bias)
+        ctx.arena = (getattr(weight, '_tss_grad', None),
+                     getattr(bias, '_tss_grad', None) if bias is not None else None)
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, weight, bias = ctx.saved_tensors
+        gw, gbias = ctx.arena
         Nc = weight.shape[0]
         g = ops.geom(dy)
         if g is None or g[4] % 8 != 0 or g[4] < (Nc + 7) // 8 * 8:
@@ -141,10 +173,13 @@ class ConvBias(torch.autograd.Function):
             view.copy_(dy)
             dy = view
         dx = ops.pwconv_dgrad(dy, weight) if ctx.needs_input_grad[0] else None
-        dw = torch.zeros_like(weight)
-        db = torch.zeros(Nc, dtype=torch.float32, device=weight.device) if ctx.has_bias else None
+        dw = gw if gw is not None else torch.zeros_like(weight)
+        db = None
+        if ctx.has_bias:
+            db = gbias if gbias is not None else torch.zeros(Nc, dtype=torch.float32, device=weight.device)
         ops.pwconv_wgrad(x, dy, dw, db)
-        return dx, dw, db
+        grad_ready(*ctx.params)
+        return dx, None if gw is not None else dw, None if gbias is not None else db
 
 
 class AdaptivePool(torch.autograd.Function):

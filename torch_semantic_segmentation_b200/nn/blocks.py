@@ -16,7 +16,7 @@ from .. import functional as Fn
 
 
 def _versions(*tensors):
-    return tuple(t._version for t in tensors) + tuple(t.data_ptr() for t in tensors)
+    return (ops.WEIGHTS_EPOCH[0],) + tuple(t._version for t in tensors) + tuple(t.data_ptr() for t in tensors)
 
 
 class _FusedConvBN:

@@ -13,6 +13,10 @@ from ._lib import EPI_RELU, dtype_code
 
 PYRAMID_BINS = (1, 2, 3, 6)
 
+# Bumped whenever a kernel rewrites parameters or BatchNorm buffers behind autograd's back
+# (raw-pointer writes do not touch tensor._version); derived caches key on it.
+WEIGHTS_EPOCH = [0]
+
 
 # ------------------------------------------------------------------ layout helpers -----
 def empty_nhwc(N, C, H, W, dtype, device, pitch=None):
@@ -170,6 +174,8 @@ def bn_finalize(stats, count, bn, momentum, eps, update_running=True):
               running_var=bn.running_var if track else None,
               num_batches_tracked=bn.num_batches_tracked if track else None,
               momentum=momentum, eps=eps, scale=out[0], shift=out[1], mean=out[2], rstd=out[3], C=C)
+    if track:
+        WEIGHTS_EPOCH[0] += 1
     return out[0], out[1], out[2], out[3]
 
 
@@ -374,3 +380,4 @@ def confusion_from_logits(logits, target, cm, want_pred=False):
 
 def adamw_step(p, g, m, v, hyper, grad_scale=1.0):
     _lib.call('tss_adamw_step', p=p, g=g, m=m, v=v, n=p.numel(), hyper=hyper, grad_scale=float(grad_scale))
+    WEIGHTS_EPOCH[0] += 1

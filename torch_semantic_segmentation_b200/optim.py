@@ -1,0 +1,90 @@
+"""``FlatAdamW``: torch.optim.AdamW semantics (scripts/train_fastscnn.py:125-129) over ONE flat
+fp32 arena.
+
+On construction every parameter is re-homed into a contiguous fp32 arena (``p.data`` becomes a
+view) and gets a persistent gradient view into a second arena (``p.grad``).  Consequences:
+
+* ``zero_grad()`` is one memset, ``step()`` is one streaming kernel (``tss_adamw_step``);
+* the weight-gradient kernels accumulate straight into the arena (``p._tss_grad``), so
+  autograd launches no per-parameter accumulation kernels;
+* data-parallel training all-reduces contiguous slices of the gradient arena (buckets)
+  without flatten / unflatten copies (``distributed.GradientAllReducer``).
+
+Hyper-parameters live in a small device tensor refreshed from pinned host memory each step,
+so a captured CUDA graph of the step can be replayed under a learning-rate schedule.
+"""
+import torch
+
+from . import ops
+
+__all__ = ['FlatAdamW']
+
+
+class FlatAdamW(torch.optim.Optimizer):
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        if len(self.param_groups) != 1:
+            raise ValueError('FlatAdamW supports a single parameter group')
+        ps = [p for p in self.param_groups[0]['params'] if p.requires_grad]
+        if not ps:
+            raise ValueError('no trainable parameters')
+        dev = ps[0].device
+        if any(p.device != dev or p.dtype != torch.float32 for p in ps):
+            raise ValueError('FlatAdamW needs fp32 parameters on one device')
+        # 16-byte aligned slots so that every view is vector-load friendly
+        offsets, n = [], 0
+        for p in ps:
+            offsets.append(n)
+            n += (p.numel() + 3) // 4 * 4
+        self.numel = n
+        self.param_arena = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad_arena = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.slots = []
+        with torch.no_grad():
+            for p, off in zip(ps, offsets):
+                view = self.param_arena[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+                g = self.grad_arena[off:off + p.numel()].view_as(p)
+                p.grad = g
+                p._tss_grad = g          # kernels accumulate here directly (functional.py)
+                self.slots.append((p, off, p.numel()))
+        g0 = self.param_groups[0]
+        self.hyper = torch.tensor([g0['lr'], g0['betas'][0], g0['betas'][1], g0['eps'], g0['weight_decay'],
+                                   0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
+        self._host = torch.empty(5, dtype=torch.float32)
+        if dev.type == 'cuda':
+            self._host = self._host.pin_memory()
+        self.grad_scale = 1.0          # e.g. 1/world_size after a SUM all-reduce
+
+    def zero_grad(self, set_to_none=False):
+        """One memset; the gradient views stay attached (``set_to_none`` is ignored)."""
+        self.grad_arena.zero_()
+
+    def _refresh_hyper(self):
+        g = self.param_groups[0]
+        self._host[0], self._host[1], self._host[2] = g['lr'], g['betas'][0], g['betas'][1]
+        self._host[3], self._host[4] = g['eps'], g['weight_decay']
+        self.hyper[:5].copy_(self._host, non_blocking=True)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        reducer = getattr(self, '_reducer', None)
+        if reducer is not None:
+            reducer.finish()         # gradient all-reduce buckets launched during backward
+        self._refresh_hyper()
+        ops.adamw_step(self.param_arena, self.grad_arena, self.exp_avg, self.exp_avg_sq, self.hyper,
+                       self.grad_scale)
+        return loss
+
+    @property
+    def step_count(self):
+        return int(self.hyper[5].item())
