@@ -8,7 +8,7 @@ make -j8 > gpurun_out/make.log 2>&1 || { echo "BUILD FAILED"; tail -20 gpurun_ou
 status=0
 for group in "$@"; do
   name=$(echo "$group" | tr '/:[] ' '_____')
-  timeout 600 python -m pytest "$group" -q -m gpu -x --no-header -p no:cacheprovider > "gpurun_out/test_${name}.log" 2>&1
+  timeout 600 python -m pytest "$group" -q -m gpu --tb=short --no-header -p no:cacheprovider > "gpurun_out/test_${name}.log" 2>&1
   rc=$?
   echo "== $group -> rc=$rc : $(tail -1 gpurun_out/test_${name}.log)"
   if [ $rc -ne 0 ]; then status=1; grep -E "^(FAILED|ERROR)|Error|error:|assert " "gpurun_out/test_${name}.log" | head -12; fi
