@@ -99,7 +99,7 @@ constexpr int PH = 2 * TH + 1, PW = 2 * TW + 1; // input patch 17 x 65
 constexpr int PWP = PW + 2;                    // pitch
 constexpr int kSplits = 10;
 constexpr int kWgThreads = 24 * kSplits;       // (8 co-quads x 3 ci) x 10 pixel splits
-constexpr int kPatch = 3 * PH * PWP;           // floats
+constexpr int kPatch = (3 * PH * PWP + 3) & ~3; // floats, rounded so that dy_s stays 16-byte aligned
 constexpr int kDyTile = TH * TW * CO;          // floats
 static_assert(kPatch + kDyTile >= kSplits * 864, "scratch reuse");
 
