@@ -413,3 +413,45 @@ def test_adamw_flat_arena():
         opt.step()
         ops.adamw_step(pg, (grad * 2).cuda(), m, v, hyper, grad_scale=0.5)
     assert rel(pg, p_ref) < 1e-6 and float(hyper[5]) == 3.0
+
+
+# ------------------------------------------------------------------ tcgen05 pointwise ---
+TC_CASES = [  # K, Nc, M (rows = N*H*W with N=1, H=1)
+    (64, 64, 128), (64, 64, 4096), (32, 48, 1000), (48, 64, 777), (64, 384, 2304), (384, 64, 2304), (384, 96, 576),
+    (96, 576, 576), (576, 96, 576), (576, 128, 576), (128, 768, 576), (768, 128, 576), (256, 128, 576), (128, 128, 9216),
+    (64, 128, 9216), (128, 32, 12), (192, 32, 300), (288, 48, 300), (48, 288, 300), (32, 32, 129), (128, 128, 1),
+]
+
+
+@pytest.mark.parametrize('K,Nc,M', TC_CASES)
+def test_pwconv_tcgen05(K, Nc, M):
+    """impl 1 (TMA + tcgen05.mma + TMEM) against fp32 torch on bf16-rounded operands."""
+    g = gen(K + Nc + M)
+    dtype, code = torch.bfloat16, 1
+    xc, xg = pair(1, K, 1, M, dtype, g)
+    w = (torch.randn(Nc, K, 1, 1, generator=g) / math.sqrt(K)).to(dtype).float()     # exactly representable
+    wp, wpT = ops.pack_weights_bf16(w.cuda())
+    assert torch.equal(wp.float().cpu(), w.view(Nc, K)) and torch.equal(wpT.float().cpu(), w.view(Nc, K).t())
+    yc, yg = pair(1, Nc, 1, M, dtype, g)
+    sc, sg = torch.zeros(2 * Nc), torch.zeros(2 * Nc).cuda()
+    base = dict(M=M, K=K, Nc=Nc, ldx=K, ldy=Nc, ldr=0, dtype=code)
+    FakeBackend().call('tss_pwconv_fwd', dict(x=xc, w=w, wp=None, y=yc, scale=None, shift=None, res=None, flags=0, stats=sc, impl=0, **base))
+    _lib.backend().call('tss_pwconv_fwd', dict(x=xg, w=w.cuda(), wp=wp, y=yg, scale=None, shift=None, res=None, flags=0, stats=sg, impl=1, **base))
+    torch.cuda.synchronize()
+    assert rel(yg, yc) < 5e-3, rel(yg, yc)          # same operands, fp32 accumulate: only the final rounding differs
+    assert rel(sg, sc) < 1e-4
+    rc, rg = pair(1, Nc, 1, M, dtype, g)
+    scale, shift = torch.rand(Nc, generator=g) + 0.5, torch.randn(Nc, generator=g)
+    base['ldr'] = Nc
+    FakeBackend().call('tss_pwconv_fwd', dict(x=xc, w=w, wp=None, y=yc, scale=scale, shift=shift, res=rc, flags=1, stats=None, impl=0, **base))
+    _lib.backend().call('tss_pwconv_fwd', dict(x=xg, w=w.cuda(), wp=wp, y=yg, scale=scale.cuda(), shift=shift.cuda(), res=rg, flags=1, stats=None, impl=1, **base))
+    torch.cuda.synchronize()
+    assert rel(yg, yc) < 5e-3
+    # dgrad = the same kernel on the transposed pack
+    dyc, dyg = pair(1, Nc, 1, M, dtype, g)
+    dxc, dxg = pair(1, K, 1, M, dtype, g)
+    kw = dict(M=M, K=K, Nc=Nc, lddy=Nc, lddx=K, dtype=code)
+    FakeBackend().call('tss_pwconv_dgrad', dict(dy=dyc, w=w, wpT=None, dx=dxc, impl=0, **kw))
+    _lib.backend().call('tss_pwconv_dgrad', dict(dy=dyg, w=w.cuda(), wpT=wpT, dx=dxg, impl=1, **kw))
+    torch.cuda.synchronize()
+    assert rel(dxg, dxc) < 5e-3

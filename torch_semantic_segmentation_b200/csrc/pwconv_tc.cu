@@ -1,10 +1,310 @@
-// Pointwise convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
-// Placeholder until the kernel lands: the entry point refuses loudly (no fallback).
+// Pointwise (1x1) convolution on the 5th-generation tensor cores (sm_100a only).
+//
+//   Y[M][Nc] = X[M][K] . W[Nc][K]^T  (+ BatchNorm statistics | affine + residual + ReLU), bf16 in,
+//   fp32 accumulate in TMEM, bf16 out.   dgrad is the same kernel with the transposed weight pack.
+//
+// One CTA per 128-row x BLOCK_N tile (BLOCK_N = largest multiple-of-16 divisor of Nc <= 256):
+//   warp 0 (one lane): TMA producer  -- cp.async.bulk.tensor.2d boxes of 128 x 64 (A) and
+//                      BLOCK_N x 64 (B) bf16, 128-byte swizzle, mbarrier complete_tx;
+//                      K tails and the M tail are zero-filled by TMA.
+//   warp 1 (one lane): MMA issuer    -- tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N,
+//                      K=16 per instruction, SS operands through shared-memory descriptors;
+//                      tcgen05.commit releases smem stages / publishes the accumulator.
+//                      (the whole warp allocates / frees the TMEM columns)
+//   warps 2-5:         epilogue      -- tcgen05.ld 32x32b (one output row per thread), fused
+//                      BatchNorm statistics (warp-transposed shuffle sums -> smem -> one global
+//                      atomic per column per CTA) or scale/shift/residual/ReLU, bf16 stores.
+// These GEMMs are HBM-bound (arithmetic intensity 19..110 flop/B vs a ridge of ~246): several
+// CTAs stay resident per SM (smem = stages x (16 KB + BLOCK_N x 128 B), TMEM = BLOCK_N columns)
+// so that loads, MMAs and stores of different tiles overlap.
+#include <cuda.h>
+
 #include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;          // rows per tile = UMMA M
+constexpr int BK = 64;           // bf16 elements per k-block = 128 bytes = one swizzle row
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = BM * BK * 2;
+
+// ------------------------------------------------------------------ PTX wrappers ------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+
+// lanes 2j / 2j+1 end with the sum over the 32 lanes of v[j], j = lane >> 1
+__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int step = 16, n = 16; step >= 2; step >>= 1, n >>= 1) {
+        const bool upper = (lane & step) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = upper ? v[i] : v[i + n / 2];
+            const float keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// ------------------------------------------------------------------ the kernel ---------
+__global__ void __launch_bounds__(kThreads)
+pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             bf16* __restrict__ Y, int64_t M, int K, int64_t ldy, int block_n, int stages, uint32_t tmem_cols,
+             const float* __restrict__ scale, const float* __restrict__ shift, const bf16* __restrict__ res,
+             int64_t ldr, int relu, float* __restrict__ stats, int stats_stride) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SW128 needs 1024-B alignment
+    const uint32_t b_bytes = (uint32_t)block_n * BK * 2;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)stages * kABytes;
+    uint64_t* bars = (uint64_t*)(sB + (size_t)stages * b_bytes);     // full[stages], empty[stages], tmem_full
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * stages + 1);
+    float* s_stat = (float*)(tmem_slot + 2);                          // [2][block_n]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * block_n;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(bars + s), 1);
+            mbar_init(smem_u32(bars + stages + s), 1);
+        }
+        mbar_init(smem_u32(bars + 2 * stages), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (stats != nullptr)
+        for (int i = threadIdx.x; i < 2 * block_n; i += kThreads) s_stat[i] = 0.f;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ---------------- TMA producer
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % stages;
+                const uint32_t phase = (kb / stages) & 1;
+                mbar_wait(smem_u32(bars + stages + s), phase ^ 1);
+                const uint32_t full = smem_u32(bars + s);
+                mbar_expect_tx(full, kABytes + b_bytes);
+                tma_load_2d(smem_u32(sA + (size_t)s * kABytes), &tmA, full, kb * BK, (int)m0);
+                tma_load_2d(smem_u32(sB + (size_t)s * b_bytes), &tmB, full, kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ---------------- MMA issuer
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=block_n, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % stages;
+                const uint32_t phase = (kb / stages) & 1;
+                mbar_wait(smem_u32(bars + s), phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t adesc = make_desc_k_sw128(smem_u32(sA + (size_t)s * kABytes));
+                const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + (size_t)s * b_bytes));
+                int rem = K - kb * BK;
+                const int k16 = rem >= BK ? BK / 16 : (rem + 15) / 16;     // skip all-zero K slices of the tail
+                for (int k = 0; k < k16; ++k)                                // +32 bytes (= 2 x 16 B) per K=16 slice
+                    umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)(kb > 0 || k > 0));
+                umma_commit(smem_u32(bars + stages + s));                    // smem stage free once these MMAs retire
+            }
+            umma_commit(smem_u32(bars + 2 * stages));                        // accumulator complete
+        }
+    } else {                                               // ---------------- epilogue warps 2..5
+        const int q = warp & 3;                            // TMEM lane quarter this warp may access
+        const int row_in_tile = q * 32 + lane;
+        const int64_t row = m0 + row_in_tile;
+        const bool row_ok = row < M;
+        mbar_wait(smem_u32(bars + 2 * stages), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c = 0; c < block_n; c += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (stats != nullptr) {                        // rows >= M are exact zeros (TMA zero fill)
+                float sq[16], sm[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { sm[i] = v[i]; sq[i] = v[i] * v[i]; }
+                const float s1 = warp_transpose_sum16(sm, lane);
+                const float s2 = warp_transpose_sum16(sq, lane);
+                if ((lane & 1) == 0) {
+                    atomicAdd(&s_stat[c + (lane >> 1)], s1);
+                    atomicAdd(&s_stat[block_n + c + (lane >> 1)], s2);
+                }
+            }
+            if (row_ok) {
+                const int col = n0 + c;
+                if (shift != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        v[i] = fmaf(v[i], scale != nullptr ? __ldg(scale + col + i) : 1.f, __ldg(shift + col + i));
+                }
+                if (res != nullptr) {
+                    float r0[8], r1[8];
+                    load8(res + row * ldr + col, r0);
+                    load8(res + row * ldr + col + 8, r1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { v[i] += r0[i]; v[8 + i] += r1[i]; }
+                }
+                if (relu) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                float lo[8], hi[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
+                store8(Y + row * ldy + col, lo);
+                store8(Y + row * ldy + col + 8, hi);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (stats != nullptr) {
+        for (int i = threadIdx.x; i < block_n; i += kThreads) {
+            atomicAdd(stats + n0 + i, s_stat[i]);
+            atomicAdd(stats + stats_stride + n0 + i, s_stat[block_n + i]);
+        }
+    }
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host side ----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// 2-D bf16 row-major [rows][cols] with row pitch ld (elements); box = box_rows x 64 columns, 128-B swizzle
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode_tiled();
+    TSS_REQUIRE(enc != nullptr, "pwconv_tc: cuTensorMapEncodeTiled is not available from the driver");
+    TSS_REQUIRE(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0, "pwconv_tc: TMA needs 16-byte aligned base and pitch");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TSS_REQUIRE(r == CUDA_SUCCESS, "pwconv_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d ld=%lld box_rows=%d",
+                (int)r, (long long)rows, cols, (long long)ld, box_rows);
+    return TSS_OK;
+}
+
+int pick_block_n(int Nc) {
+    for (int bn = 256; bn >= 16; bn -= 16)
+        if (Nc % bn == 0) return bn;
+    return 0;
+}
+
+}  // namespace
 
 int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, int Nc, int64_t ldx,
                       int64_t ldy, const float* scale, const float* shift, const void* res, int64_t ldr,
                       int flags, float* stats, cudaStream_t st) {
-    tss_set_error("pwconv impl 1 (tcgen05) is not built yet");
-    return TSS_ERR_ARG;
+    TSS_REQUIRE(Nc % 16 == 0 && K % 8 == 0, "pwconv_tc: needs Nc %% 16 == 0 and K %% 8 == 0 (Nc=%d K=%d)", Nc, K);
+    TSS_REQUIRE(ldy % 8 == 0 && (res == nullptr || ldr % 8 == 0), "pwconv_tc: output / residual pitch must be a multiple of 8");
+    TSS_REQUIRE(((uintptr_t)y & 15) == 0 && ((uintptr_t)res & 15) == 0, "pwconv_tc: output / residual must be 16-byte aligned");
+    TSS_REQUIRE(scale == nullptr || shift != nullptr, "pwconv_tc: scale without shift");
+    const int bn = pick_block_n(Nc);
+    TSS_REQUIRE(bn >= 16, "pwconv_tc: no tile width for Nc=%d", Nc);
+    CUtensorMap tmA, tmB;
+    if (int e = make_map(&tmA, x, M, K, ldx, BM)) return e;
+    if (int e = make_map(&tmB, wp, Nc, K, K, bn)) return e;
+    const int num_kb = (K + BK - 1) / BK;
+    const int stages = num_kb < 4 ? num_kb : 4;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < bn) tmem_cols <<= 1;
+    const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 1) * 8 + 8 + 2 * bn * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        TSS_CUDA(cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)ceil_div64(M, BM), (unsigned)(Nc / bn));
+    pw_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, (bf16*)y, M, K, ldy, bn, stages, tmem_cols, scale, shift,
+                                               (const bf16*)res, ldr, flags & TSS_EPI_RELU, stats, Nc);
+    TSS_LAUNCH_CHECK("pwconv_fwd_tc");
+    return TSS_OK;
 }

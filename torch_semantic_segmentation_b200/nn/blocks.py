@@ -65,7 +65,7 @@ class _FusedConvBN:
         if self.pw_impl == 0 or self.compute_dtype != torch.bfloat16:
             return None
         w = self[ci].weight
-        if self._kind(self[ci]) != 'pw' or w.shape[0] % 8 != 0:
+        if self._kind(self[ci]) != 'pw' or w.shape[0] % 16 != 0 or w.shape[1] % 16 != 0:
             return None
         key = _versions(w)
         hit = self._pack_cache.get(ci)
