@@ -236,7 +236,7 @@ def main():
     import torch.distributed as dist
     from torch_semantic_segmentation_b200 import _lib
     from torch_semantic_segmentation_b200.distributed import GradientAllReducer, broadcast_parameters
-    from torch_semantic_segmentation_b200.engine import create_segmentation_trainer
+    from torch_semantic_segmentation_b200.engine import GraphedTrainStep, create_segmentation_trainer
     from torch_semantic_segmentation_b200.functional import unit_loss_grad
     from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
     from torch_semantic_segmentation_b200.models import fastscnn
@@ -255,14 +255,26 @@ def main():
     x, y = synthetic_batch(BATCH, CROP, 1234 + rank, device)
     model.train()
 
-    def step():
+    use_graph = not args.no_graph
+    graphed = None
+
+    def eager_step():
         opt.zero_grad()
         out = model(x)
         loss = loss_fn(out, y)
         with unit_loss_grad():
             loss.backward()
         opt.step()
-        return loss
+        return loss.detach()
+
+    if use_graph:
+        graphed = GraphedTrainStep(model, opt, loss_fn, x, y)      # static inputs = the resident batch
+
+        def step():
+            graphed.graph.replay()
+            return graphed.loss
+    else:
+        step = eager_step
 
     def barrier():
         if world > 1:
@@ -287,12 +299,15 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = _lib.launch_count() - launches0
+    if use_graph:
+        launches = graphed.kernels_per_step * args.steps
     ms_total = float(ms)
     value = world * BATCH * args.steps / (ms_total / 1e3)
 
     # ---- end to end: the public engine API, batch in pinned host memory -------------------
     xh, yh = x.cpu().pin_memory(), y.cpu().pin_memory()
-    trainer = create_segmentation_trainer(model, opt, loss_fn, device, use_f16=True, logging=False)
+    trainer = create_segmentation_trainer(model, opt, loss_fn, device, use_f16=True, logging=False,
+                                          cuda_graph=use_graph)
     trainer.run([(xh, yh)] * 2)
     barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -338,7 +353,7 @@ def main():
                                '19 classes, 12 crops of 768x768 per GPU, random-init weights',
                    'global_batch': world * BATCH, 'parallelism': 'dp%d' % world,
                    'l2': 'per-step working set (>3 GB of activations) far exceeds the 126 MB L2',
-                   'launch_mode': 'eager'},
+                   'launch_mode': 'cuda_graph' if use_graph else 'eager'},
         'loss': float(loss),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': xh.numel() * 4 + yh.numel() * 8,
                 'd2h_bytes_per_step': 4, 'ms_per_step': float(ems) / args.steps},

@@ -135,15 +135,76 @@ def _prepare_batch(batch, device=None, non_blocking=False):
             y.to(device=device, non_blocking=non_blocking))
 
 
+class GraphedTrainStep:
+    """The whole optimisation step (zero_grad, forward, loss, backward, gradient all-reduce,
+    optimizer) captured ONCE as a CUDA graph and replayed per batch: ~350 kernel launches become
+    one graph launch, which is what a 1.1 M-parameter net needs to stay GPU-bound.  The batch is
+    copied straight from (pinned) host memory into the graph's static input buffers."""
+
+    def __init__(self, model, optimizer, loss_fn, x, y, warmup=3):
+        dev = x.device
+        self.x = torch.empty_like(x)
+        self.y = torch.empty_like(y)
+        self.x.copy_(x)
+        self.y.copy_(y)
+        self.key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype)
+
+        def body():
+            optimizer.zero_grad()
+            loss = loss_fn(model(self.x), self.y)
+            with unit_loss_grad():
+                loss.backward()
+            optimizer.step()
+            return loss.detach()
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):          # allocator / cuBLAS-free warm-up on a side stream
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import _lib
+        self.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = body()
+        self.kernels_per_step = _lib.launch_count() - before   # libtss_b200 kernel nodes in the graph
+        self.warmup_steps = warmup + 1        # steps the optimizer already took on the example batch
+
+    def matches(self, x, y):
+        return (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype) == self.key
+
+    def __call__(self, x, y, non_blocking=True):
+        self.x.copy_(x, non_blocking=non_blocking)
+        self.y.copy_(y, non_blocking=non_blocking)
+        self.graph.replay()
+        return self.loss
+
+
 # ------------------------------------------------------------------ the two factories -------
 def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False, logging=True,
-                                non_blocking=True):
-    """reference: engine.py:22-56."""
+                                non_blocking=True, cuda_graph=False):
+    """reference: engine.py:22-56.  ``cuda_graph=True`` (an addition) replays the step as one
+    CUDA graph; it needs fixed batch shapes and a capturable optimizer (``optim.FlatAdamW`` or
+    ``torch.optim.AdamW(capturable=True)``).  The first batch is used for warm-up and capture
+    (its optimisation steps are real steps)."""
     if use_f16 and hasattr(model, 'set_compute_dtype'):
         model.set_compute_dtype(torch.bfloat16)
+    graphed = {}
 
     def update_fn(_trainer, batch):
         model.train()
+        if cuda_graph:
+            x, y = batch
+            g = graphed.get('step')
+            if g is None:
+                xd, yd = _prepare_batch(batch, device=device, non_blocking=non_blocking)
+                graphed['step'] = g = GraphedTrainStep(model, optimizer, loss_fn, xd, yd)
+                return g.loss.item()
+            if not g.matches(x, y):
+                raise RuntimeError('cuda_graph=True needs a fixed batch shape; got %s' % (tuple(x.shape),))
+            return g(x, y, non_blocking).item()
         optimizer.zero_grad()
         x, y = _prepare_batch(batch, device=device, non_blocking=non_blocking)
 

@@ -30,16 +30,19 @@ class unit_loss_grad:
     gradient 1.0, so that :class:`CrossEntropy` can hand its fused gradient on without
     a rescaling pass over the logits-sized tensor."""
 
+    # process-wide on purpose: backward runs on autograd's per-device worker thread while the
+    # thread that called backward() is blocked inside this context manager
+    depth = 0
+
     def __enter__(self):
-        self.prev = getattr(_tls, 'unit', False)
-        _tls.unit = True
+        unit_loss_grad.depth += 1
 
     def __exit__(self, *exc):
-        _tls.unit = self.prev
+        unit_loss_grad.depth -= 1
 
 
 def _unit_grad():
-    return getattr(_tls, 'unit', False)
+    return unit_loss_grad.depth > 0
 
 
 _grad_ready_hook = None
