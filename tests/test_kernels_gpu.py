@@ -455,3 +455,11 @@ def test_pwconv_tcgen05(K, Nc, M):
     _lib.backend().call('tss_pwconv_dgrad', dict(dy=dyg, w=w.cuda(), wpT=wpT, dx=dxg, impl=1, **kw))
     torch.cuda.synchronize()
     assert rel(dxg, dxc) < 5e-3
+    # wgrad on the tensor cores (MN-major operands straight from the activations), accumulate semantics
+    dwc = torch.randn(Nc, K, 1, 1, generator=g)
+    dwg = dwc.clone().cuda()
+    kw = dict(M=M, K=K, Nc=Nc, ldx=K, lddy=Nc, dtype=code, db=None)
+    FakeBackend().call('tss_pwconv_wgrad', dict(x=xc, dy=dyc, dw=dwc, impl=0, **kw))
+    _lib.backend().call('tss_pwconv_wgrad', dict(x=xg, dy=dyg, dw=dwg, impl=1, **kw))
+    torch.cuda.synchronize()
+    assert rel(dwg, dwc) < 1e-4, rel(dwg, dwc)

@@ -231,6 +231,9 @@ int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, 
                       int64_t ldy, const float* scale, const float* shift, const void* res, int64_t ldr,
                       int flags, float* stats, cudaStream_t st);
 
+int tss_pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int K, int Nc, int64_t ldx,
+                        int64_t lddy, cudaStream_t st);
+
 static int check_gemm(const char* name, int64_t M, int K, int Nc, int64_t lda, int64_t ldc, int red, int out) {
     TSS_REQUIRE(M > 0 && K > 0 && Nc > 0, "%s: empty problem M=%lld K=%d Nc=%d", name, (long long)M, K, Nc);
     TSS_REQUIRE(K % 8 == 0, "%s: K=%d must be a multiple of 8", name, K);
@@ -290,6 +293,10 @@ extern "C" int tss_pwconv_wgrad(const void* x, const void* dy, float* dw, float*
     TSS_REQUIRE(lddy % 8 == 0 && lddy >= round_up8(Nc), "pwconv_wgrad: lddy=%lld Nc=%d", (long long)lddy, Nc);
     TSS_REQUIRE(impl == 0 || impl == 1, "pwconv_wgrad: unknown impl %d", impl);
     cudaStream_t st = (cudaStream_t)stream;
+    if (impl == 1) {
+        TSS_REQUIRE(dtype == TSS_BF16 && db == nullptr, "pwconv_wgrad: impl 1 needs bf16 activations and no bias gradient");
+        return tss_pwconv_wgrad_tc(x, dy, dw, M, K, Nc, ldx, lddy, st);
+    }
     const int gx = (Nc + WT - 1) / WT, gy = (K + WT - 1) / WT;
     int64_t target = (int64_t)tss_num_sms() * 4;
     int64_t nsplit = target / ((int64_t)gx * gy);

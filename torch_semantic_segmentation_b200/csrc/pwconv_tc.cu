@@ -238,6 +238,125 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
 }
 
+// ------------------------------------------------------------------ wgrad --------------
+// dW[Nc][K] += dY[M][Nc]^T . X[M][K].  The reduction runs over pixels (M), so both operands are
+// "MN-major" as they sit in HBM: a TMA box of 64 pixels x 64 channels (128-byte swizzle) IS the
+// canonical MN-major UMMA atom stack (8 pixel rows x 128 B per atom, atoms 1024 B apart, the
+// next 64-channel group one box further = leading byte offset).  One CTA owns a 128 (n) x
+// BLOCK_K (k <= 256) tile of dW and a contiguous range of pixels; the fp32 accumulator lives
+// in TMEM for the whole range and is added to global memory once, with 128-bit vector reductions.
+constexpr int WM = 64;                           // pixels per stage
+constexpr uint32_t kBoxBytes = WM * 64 * 2;      // one 64-pixel x 64-channel box
+
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(kBoxBytes >> 4) << 16;       // leading byte offset: next 64-channel group
+    d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset: next 8-pixel atom
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
+                float* __restrict__ dW, int64_t M, int K, int Nc, int block_k, int n_groups, int k_groups,
+                int64_t rows_per, int stages, uint32_t tmem_cols) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = (uint32_t)n_groups * kBoxBytes, b_bytes = (uint32_t)k_groups * kBoxBytes;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)stages * a_bytes;
+    uint64_t* bars = (uint64_t*)(sB + (size_t)stages * b_bytes);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * stages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * 128, k0 = blockIdx.y * block_k;
+    const int64_t mb = (int64_t)blockIdx.z * rows_per;
+    const int64_t me = mb + rows_per < M ? mb + rows_per : M;
+    const int num_it = (int)((me - mb + WM - 1) / WM);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(bars + s), 1);
+            mbar_init(smem_u32(bars + stages + s), 1);
+        }
+        mbar_init(smem_u32(bars + 2 * stages), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < num_it; ++it) {
+                const int s = it % stages;
+                const uint32_t phase = (it / stages) & 1;
+                mbar_wait(smem_u32(bars + stages + s), phase ^ 1);
+                const uint32_t full = smem_u32(bars + s);
+                mbar_expect_tx(full, a_bytes + b_bytes);
+                const int m = (int)(mb + (int64_t)it * WM);
+                for (int g = 0; g < n_groups; ++g)
+                    tma_load_2d(smem_u32(sA + (size_t)s * a_bytes + (size_t)g * kBoxBytes), &tmG, full, n0 + g * 64, m);
+                for (int g = 0; g < k_groups; ++g)
+                    tma_load_2d(smem_u32(sB + (size_t)s * b_bytes + (size_t)g * kBoxBytes), &tmX, full, k0 + g * 64, m);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D=f32, A=B=bf16, both MN-major (bits 15, 16), N=block_k, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(block_k >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int it = 0; it < num_it; ++it) {
+                const int s = it % stages;
+                const uint32_t phase = (it / stages) & 1;
+                mbar_wait(smem_u32(bars + s), phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t adesc = make_desc_mn_sw128(smem_u32(sA + (size_t)s * a_bytes));
+                const uint64_t bdesc = make_desc_mn_sw128(smem_u32(sB + (size_t)s * b_bytes));
+                int64_t left = me - (mb + (int64_t)it * WM);
+                const int k16 = left >= WM ? WM / 16 : (int)((left + 15) / 16);
+                for (int k = 0; k < k16; ++k)                 // 16 pixels = 2 atoms = 2048 B per slice
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (uint32_t)(it > 0 || k > 0));
+                umma_commit(smem_u32(bars + stages + s));
+            }
+            umma_commit(smem_u32(bars + 2 * stages));
+        }
+    } else {
+        const int q = warp & 3;
+        const int n = n0 + q * 32 + lane;
+        mbar_wait(smem_u32(bars + 2 * stages), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c = 0; c < block_k; c += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (n < Nc && num_it > 0) {
+                float* dst = dW + (int64_t)n * K + k0 + c;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    if (k0 + c + j < K) red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------ host side ----------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -279,6 +398,38 @@ int pick_block_n(int Nc) {
 }
 
 }  // namespace
+
+int tss_pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int K, int Nc, int64_t ldx,
+                        int64_t lddy, cudaStream_t st) {
+    TSS_REQUIRE(Nc % 16 == 0 && K % 16 == 0, "pwconv_wgrad_tc: needs Nc %% 16 == 0 and K %% 16 == 0 (Nc=%d K=%d)", Nc, K);
+    TSS_REQUIRE(((uintptr_t)dw & 15) == 0, "pwconv_wgrad_tc: dw must be 16-byte aligned");
+    const int bk = pick_block_n(K);
+    TSS_REQUIRE(bk >= 16, "pwconv_wgrad_tc: no tile width for K=%d", K);
+    CUtensorMap tmG, tmX;
+    if (int e = make_map(&tmG, dy, M, Nc, lddy, WM)) return e;
+    if (int e = make_map(&tmX, x, M, K, ldx, WM)) return e;
+    const int gx = (Nc + 127) / 128, gy = K / bk;
+    const int n_groups = 2, k_groups = (bk + 63) / 64;
+    int64_t nsplit = ((int64_t)tss_num_sms() * 2) / ((int64_t)gx * gy);
+    const int64_t max_split = ceil_div64(M, 512);
+    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit < 1) nsplit = 1;
+    const int64_t rows_per = ceil_div64(ceil_div64(M, nsplit), WM) * WM;
+    nsplit = ceil_div64(M, rows_per);
+    const int stages = 4;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < bk) tmem_cols <<= 1;
+    const size_t smem = 1024 + (size_t)stages * (n_groups + k_groups) * kBoxBytes + (2 * stages + 1) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TSS_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(gx, gy, (unsigned)nsplit);
+    wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tmG, tmX, dw, M, K, Nc, bk, n_groups, k_groups, rows_per, stages, tmem_cols);
+    TSS_LAUNCH_CHECK("pwconv_wgrad_tc");
+    return TSS_OK;
+}
 
 int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, int Nc, int64_t ldx,
                       int64_t ldy, const float* scale, const float* shift, const void* res, int64_t ldr,

@@ -43,7 +43,10 @@ class FastSCNN(nn.Module):
         self.classifier = Classifier(128, out_channels)
 
     def set_compute_dtype(self, dtype, pw_impl=None):
-        """float32 (verification mode, default) or bfloat16 (the B200 production path)."""
+        """float32 (verification mode, default) or bfloat16 (the B200 production path: pointwise
+        convolutions on tcgen05 tensor cores unless ``pw_impl=0`` asks for the SIMT kernels)."""
+        if pw_impl is None:
+            pw_impl = 1 if dtype == torch.bfloat16 else 0
         set_compute_dtype(self, dtype, pw_impl)
         return self
 
