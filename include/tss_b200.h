@@ -155,8 +155,10 @@ int tss_adaptive_pool_bwd(const void* dout, void* dx, int N, int H, int W, int C
  * so that the result can be written straight into the concat buffer of fastscnn.py:122. */
 int tss_bilinear_fwd(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C,
                      int64_t ldx, int64_t ldy, int dtype, void* stream);
-int tss_bilinear_bwd(const void* dy, void* dx, int N, int Hi, int Wi, int Ho, int Wo, int C,
-                     int64_t lddy, int64_t lddx, int dtype, void* stream);
+/* backward (transpose).  workspace: fp32 [N*Hi*Wo*C] scratch for the separable two-pass form
+ * (rows, then columns); NULL selects a single gather pass (small maps only). */
+int tss_bilinear_bwd(const void* dy, void* dx, float* workspace, int N, int Hi, int Wi, int Ho, int Wo,
+                     int C, int64_t lddy, int64_t lddx, int dtype, void* stream);
 /* Final x8 up-sampling of the class scores (fastscnn.py:63-64, contextnet.py:74-76):
  * in NHWC x[N][Hi][Wi][ldx] (C = 19 classes in a pitch of ldx >= C, any C <= 64) -> out NCHW
  * y[N][C][Ho][Wo] (the layout the reference returns), Wo % 8 == 0. */

@@ -206,7 +206,7 @@ class FakeBackend:
         y.copy_(F.interpolate(x.float(), size=(Ho, Wo), mode='bilinear', align_corners=True))
         return 0
 
-    def tss_bilinear_bwd(self, dy, dx, N, Hi, Wi, Ho, Wo, C, lddy, lddx, dtype):
+    def tss_bilinear_bwd(self, dy, dx, workspace, N, Hi, Wi, Ho, Wo, C, lddy, lddx, dtype):
         xx = torch.zeros(N, C, Hi, Wi, requires_grad=True)
         with torch.enable_grad():
             F.interpolate(xx, size=(Ho, Wo), mode='bilinear', align_corners=True).backward(dy.float())

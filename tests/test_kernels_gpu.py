@@ -306,8 +306,10 @@ def test_bilinear_nhwc(N, C, Hi, Wi, Ho, Wo, dtype):
     both('tss_bilinear_fwd', dict(x=xc, y=yc, ldx=C, ldy=C + 32, **kw), dict(x=xg, y=yg, ldx=C, ldy=C + 32, **kw))
     assert rel(yg, yc) < TOL[dtype]
     dxc, dxg = pair(N, C, Hi, Wi, dtype, g)
-    both('tss_bilinear_bwd', dict(dy=yc, dx=dxc, lddy=C + 32, lddx=C, **kw), dict(dy=yg, dx=dxg, lddy=C + 32, lddx=C, **kw))
-    assert rel(dxg, dxc) < TOL[dtype]
+    for ws in (None, torch.empty(N * Hi * Wo * C).cuda()):       # single gather pass / separable two-pass
+        both('tss_bilinear_bwd', dict(dy=yc, dx=dxc, workspace=None, lddy=C + 32, lddx=C, **kw),
+             dict(dy=yg, dx=dxg, workspace=ws, lddy=C + 32, lddx=C, **kw))
+        assert rel(dxg, dxc) < TOL[dtype]
 
 
 @pytest.mark.parametrize('dtype', DTYPES)

@@ -86,6 +86,17 @@ __device__ __forceinline__ void load8(const bf16* __restrict__ p, float (&v)[8])
     uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
     unpack8(u, v);
 }
+// same, from shared memory (plain loads: the read-only/LDG path is for global memory)
+__device__ __forceinline__ void load8_smem(const float* p, float (&v)[8]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0];
+    const float4 b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8_smem(const bf16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    unpack8(u, v);
+}
 __device__ __forceinline__ void zero8(float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;

@@ -8,6 +8,11 @@
 // flushed once per CTA.
 #include "common.cuh"
 
+// dwconv_tma.cu: TMA-staged forward / stride-1 dgrad; returns -1 when the shape is not covered
+int tss_dwconv3x3_tma(const void* x, const float* w, void* y, int N, int Hi, int Wi, int C, int stride, int dilation,
+                      bool flip, const float* scale, const float* shift, int flags, float* stats, int dtype,
+                      cudaStream_t st);
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -299,6 +304,11 @@ extern "C" int tss_dwconv3x3_fwd(const void* x, const float* w, void* y, int N, 
     TSS_REQUIRE(scale == nullptr || shift != nullptr, "dwconv3x3_fwd: scale without shift");
     cudaStream_t st = (cudaStream_t)stream;
     const int Ho = (Hi - 1) / stride + 1, Wo = (Wi - 1) / stride + 1;
+    {   // TMA-staged halo-tile kernel for every shape it covers; the register kernel below is the
+        // general path (channel counts without a 32/48/64/96 block, dilation 2)
+        const int r = tss_dwconv3x3_tma(x, w, y, N, Hi, Wi, C, stride, dilation, false, scale, shift, flags, stats, dtype, st);
+        if (r >= 0) return r;
+    }
     TSS_DISPATCH_DTYPE(dtype, "dwconv3x3_fwd", {
         if (stride == 1 && dilation == 1) return launch_fwd<T, 1, 1, 4, false>(x, w, y, N, Hi, Wi, Ho, Wo, C, scale, shift, flags, stats, st);
         if (stride == 2 && dilation == 1) return launch_fwd<T, 2, 1, 4, false>(x, w, y, N, Hi, Wi, Ho, Wo, C, scale, shift, flags, stats, st);
@@ -312,6 +322,10 @@ extern "C" int tss_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int
     if (int e = check_common("dwconv3x3_dgrad", N, Hi, Wi, C, stride, dilation)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int Ho = (Hi - 1) / stride + 1, Wo = (Wi - 1) / stride + 1;
+    if (stride == 1) {
+        const int r = tss_dwconv3x3_tma(dy, w, dx, N, Hi, Wi, C, 1, dilation, true, nullptr, nullptr, 0, nullptr, dtype, st);
+        if (r >= 0) return r;
+    }
     TSS_DISPATCH_DTYPE(dtype, "dwconv3x3_dgrad", {
         // stride 1: dx = conv(dy, flipped taps), same padding
         if (stride == 1 && dilation == 1) return launch_fwd<T, 1, 1, 4, true>(dy, w, dx, N, Hi, Wi, Hi, Wi, C, nullptr, nullptr, 0, nullptr, st);

@@ -1,0 +1,202 @@
+// Depthwise 3x3 forward (and stride-1 dgrad) with TMA-staged halo tiles.
+//
+// One CTA = TH x TW output pixels x CB channels.  A single elected thread issues ONE 4-D
+// cp.async.bulk.tensor box load {CB, IW, IH, 1} of the input halo tile into shared memory;
+// the box may start at negative coordinates / run past the edge -- TMA zero-fills, which IS
+// the convolution's zero padding.  While the copy is in flight every thread loads its 72
+// weights; then thread = (8-channel group, output column) slides a 3-row register window
+// down the TH rows reading 128-bit vectors from shared memory (conflict-free: consecutive
+// lanes read consecutive 16 B), and stores 128-bit results.  No register staging of global
+// loads, so HBM latency is covered by the other CTAs resident on the SM (3-4 per SM).
+// Algorithmic traffic: 2*C*(in + out pixels) bytes in bf16; halo re-reads hit L2.
+#include "tma.cuh"
+
+namespace {
+
+template <int S, int D, int TH>
+struct Geo {
+    static constexpr int IH = (TH - 1) * S + 2 * D + 1;
+};
+
+template <typename T, int S, int D, int TH, bool FLIP>
+__global__ void __launch_bounds__(192, 2)
+dw_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w, T* __restrict__ y,
+              int Ho, int Wo, int C, int CB, int TW, int tiles_w, int tiles_h,
+              const float* __restrict__ scale, const float* __restrict__ shift, int flags,
+              float* __restrict__ stats) {
+    constexpr int IH = Geo<S, D, TH>::IH;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    const int IW = (TW - 1) * S + 2 * D + 1;
+    const uint32_t tile_bytes = (uint32_t)IH * IW * CB * sizeof(T);
+    T* tile = (T*)smem;
+    uint64_t* bar = (uint64_t*)(smem + ((tile_bytes + 15) & ~15u));
+    float* s_stat = (float*)(bar + 1);                       // [2][CB]
+
+    int t = blockIdx.x;
+    const int tw = t % tiles_w; t /= tiles_w;
+    const int th = t % tiles_h;
+    const int n = t / tiles_h;
+    const int cb0 = blockIdx.y * CB;
+    const int ho0 = th * TH, wo0 = tw * TW;
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(bar), 1);
+        mbar_fence_init();
+    }
+    if (stats != nullptr)
+        for (int i = threadIdx.x; i < 2 * CB; i += blockDim.x) s_stat[i] = 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(smem_u32(bar), tile_bytes);
+        tma_load_4d(smem_u32(tile), &tmX, smem_u32(bar), cb0, wo0 * S - D, ho0 * S - D, n);
+    }
+
+    const int CGB = CB >> 3;
+    const int cg = threadIdx.x % CGB, col = threadIdx.x / CGB;     // col < TW by construction
+    const int c0 = cb0 + cg * 8;
+    float wr[9][8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) wr[k][e] = __ldg(w + (c0 + e) * 9 + (FLIP ? 8 - k : k));
+
+    mbar_wait(smem_u32(bar), 0);
+
+    float acc[TH][8];
+#pragma unroll
+    for (int r = 0; r < TH; ++r) zero8(acc[r]);
+    const T* tp = tile + ((size_t)col * S) * CB + cg * 8;
+#pragma unroll
+    for (int j = 0; j < IH; ++j) {
+        bool used = false;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int tt = j - ky * D;
+            if (tt >= 0 && tt % S == 0 && tt / S < TH) used = true;
+        }
+        if (!used) continue;
+        float v[3][8];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) load8_smem(tp + ((size_t)j * IW + kx * D) * CB, v[kx]);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int tt = j - ky * D;
+            if (tt >= 0 && tt % S == 0 && tt / S < TH) {
+                const int r = tt / S;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[r][e] = fmaf(v[kx][e], wr[ky * 3 + kx][e], acc[r][e]);
+            }
+        }
+    }
+
+    const int wo = wo0 + col;
+    const bool relu = (flags & TSS_EPI_RELU) != 0;
+    float s1[8], s2[8];
+    zero8(s1); zero8(s2);
+    if (wo < Wo) {
+        T* yp = y + (((int64_t)n * Ho + ho0) * Wo + wo) * C + c0;
+#pragma unroll
+        for (int r = 0; r < TH; ++r) {
+            if (ho0 + r < Ho) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { s1[e] += acc[r][e]; s2[e] = fmaf(acc[r][e], acc[r][e], s2[e]); }
+                if (shift != nullptr) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        acc[r][e] = fmaf(acc[r][e], scale != nullptr ? __ldg(scale + c0 + e) : 1.f, __ldg(shift + c0 + e));
+                }
+                if (relu) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[r][e] = fmaxf(acc[r][e], 0.f);
+                }
+                store8(yp + (int64_t)r * Wo * C, acc[r]);
+            }
+        }
+    }
+    if (stats != nullptr) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            atomicAdd(&s_stat[cg * 8 + e], s1[e]);
+            atomicAdd(&s_stat[CB + cg * 8 + e], s2[e]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < CB; i += blockDim.x) {
+            atomicAdd(stats + cb0 + i, s_stat[i]);
+            atomicAdd(stats + C + cb0 + i, s_stat[CB + i]);
+        }
+    }
+}
+
+template <typename T> struct TmaType;
+template <> struct TmaType<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
+template <> struct TmaType<bf16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
+
+template <typename T, int S, int D, int TH, bool FLIP>
+int launch(const void* x, const float* w, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int CB, int TW,
+           const float* scale, const float* shift, int flags, float* stats, cudaStream_t st) {
+    TssEncodeTiledFn enc = tss_encode_tiled();
+    TSS_REQUIRE(enc != nullptr, "dwconv_tma: cuTensorMapEncodeTiled is not available from the driver");
+    constexpr int IH = Geo<S, D, TH>::IH;
+    const int IW = (TW - 1) * S + 2 * D + 1;
+    CUtensorMap map;
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * sizeof(T), (cuuint64_t)Wi * C * sizeof(T), (cuuint64_t)Hi * Wi * C * sizeof(T)};
+    cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)IW, (cuuint32_t)IH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&map, TmaType<T>::v, 4, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TSS_REQUIRE(r == CUDA_SUCCESS, "dwconv_tma: cuTensorMapEncodeTiled failed (%d) C=%d W=%d H=%d N=%d box=%dx%dx%d",
+                (int)r, C, Wi, Hi, N, CB, IW, IH);
+    const int tiles_w = (Wo + TW - 1) / TW, tiles_h = (Ho + TH - 1) / TH;
+    const int threads = (CB / 8) * TW;
+    const size_t tile_bytes = (size_t)IH * IW * CB * sizeof(T);
+    const size_t smem = 128 + ((tile_bytes + 15) & ~(size_t)15) + 8 + 2 * CB * sizeof(float);
+    auto kern = dw_tma_kernel<T, S, D, TH, FLIP>;
+    static bool attr_set = false;          // per template instance; idempotent, benign race
+    if (!attr_set) {
+        TSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((int64_t)N * tiles_h * tiles_w), (unsigned)(C / CB));
+    kern<<<grid, threads, smem, st>>>(map, w, (T*)y, Ho, Wo, C, CB, TW, tiles_w, tiles_h, scale, shift, flags, stats);
+    TSS_LAUNCH_CHECK("dwconv3x3(tma)");
+    return TSS_OK;
+}
+
+}  // namespace
+
+// Channel block / tile width for the TMA path, or false if C has no suitable block.
+bool tss_dw_tma_config(int C, int* CB, int* TW) {
+    if (C % 64 == 0) { *CB = 64; *TW = 16; return true; }
+    if (C % 96 == 0) { *CB = 96; *TW = 16; return true; }
+    if (C % 48 == 0) { *CB = 48; *TW = 32; return true; }
+    if (C % 32 == 0) { *CB = 32; *TW = 32; return true; }
+    return false;
+}
+
+// flip = stride-1 dgrad (correlation with flipped taps).  Returns -1 if this shape is not covered.
+int tss_dwconv3x3_tma(const void* x, const float* w, void* y, int N, int Hi, int Wi, int C, int stride, int dilation,
+                      bool flip, const float* scale, const float* shift, int flags, float* stats, int dtype,
+                      cudaStream_t st) {
+    int CB, TW;
+    if (!tss_dw_tma_config(C, &CB, &TW)) return -1;
+    if (((uintptr_t)x & 15) != 0) return -1;
+    const int Ho = (Hi - 1) / stride + 1, Wo = (Wi - 1) / stride + 1;
+    TSS_DISPATCH_DTYPE(dtype, "dwconv3x3(tma)", {
+        if (sizeof(T) == 4 && TW == 32) TW = 16;      // keep fp32 tiles under the smem budget
+        if (stride == 1 && dilation == 1) {
+            if (flip) return launch<T, 1, 1, 8, true>(x, w, y, N, Hi, Wi, Ho, Wo, C, CB, TW, scale, shift, flags, stats, st);
+            return launch<T, 1, 1, 8, false>(x, w, y, N, Hi, Wi, Ho, Wo, C, CB, TW, scale, shift, flags, stats, st);
+        }
+        if (stride == 2 && dilation == 1 && !flip)
+            return launch<T, 2, 1, 4, false>(x, w, y, N, Hi, Wi, Ho, Wo, C, CB, TW, scale, shift, flags, stats, st);
+        if (stride == 1 && dilation == 4) {
+            if (flip) return launch<T, 1, 4, 8, true>(x, w, y, N, Hi, Wi, Ho, Wo, C, CB, TW, scale, shift, flags, stats, st);
+            return launch<T, 1, 4, 8, false>(x, w, y, N, Hi, Wi, Ho, Wo, C, CB, TW, scale, shift, flags, stats, st);
+        }
+        return -1;
+    });
+}

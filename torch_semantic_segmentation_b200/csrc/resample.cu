@@ -183,6 +183,40 @@ bilinear_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int Hi,
     }
 }
 
+// transpose of a 1-D align_corners resize along one axis: the tensor is [outer][S][inner][C]
+// (C pitched); every thread sums the <= 2*ceil(So/Si)+3 source rows that read its row.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(kThreads)
+resize_bwd_axis_kernel(const Tin* __restrict__ dy, Tout* __restrict__ dx, int64_t outer, int So, int Si,
+                       int inner, int C, int64_t ld_in, int64_t ld_out, float scale) {
+    const int CG = C >> 3;
+    const int64_t total = outer * Si * inner * CG;
+    for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
+         item += (int64_t)gridDim.x * kThreads) {
+        int64_t t = item / CG;
+        const int c0 = (int)(item - t * CG) * 8;
+        const int p = (int)(t % inner); t /= inner;
+        const int si = (int)(t % Si);
+        const int64_t o = t / Si;
+        const int a = first_candidate(scale, si, So), b = last_candidate(scale, si, So);
+        float acc[8];
+        zero8(acc);
+        for (int so = a; so <= b; ++so) {
+            int i0, i1; float lam;
+            ac_source(scale, so, Si, i0, i1, lam);
+            float w = 0.f;
+            if (i0 == si) w += 1.f - lam;
+            if (i1 == si) w += lam;
+            if (w == 0.f) continue;
+            float v[8];
+            load8(dy + ((o * So + so) * inner + p) * ld_in + c0, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], w, acc[e]);
+        }
+        store8(dx + ((o * Si + si) * inner + p) * ld_out + c0, acc);
+    }
+}
+
 // ------------------------------------------------------------ final logits x8 ----------
 // out NCHW y[n][c][ho][wo].  One CTA per (n, ho): the two source rows are blended
 // vertically into shared memory (fp32 [Wi][C]) with coalesced reads, then every thread
@@ -348,14 +382,25 @@ extern "C" int tss_bilinear_fwd(const void* x, void* y, int N, int Hi, int Wi, i
     });
 }
 
-extern "C" int tss_bilinear_bwd(const void* dy, void* dx, int N, int Hi, int Wi, int Ho, int Wo, int C,
-                                int64_t lddy, int64_t lddx, int dtype, void* stream) {
+extern "C" int tss_bilinear_bwd(const void* dy, void* dx, float* workspace, int N, int Hi, int Wi, int Ho,
+                                int Wo, int C, int64_t lddy, int64_t lddx, int dtype, void* stream) {
     TSS_REQUIRE(N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bilinear_bwd: empty tensor");
     TSS_REQUIRE(C > 0 && C % 8 == 0 && lddx % 8 == 0 && lddy % 8 == 0 && lddx >= C && lddy >= C, "bilinear_bwd: C=%d", C);
+    cudaStream_t st = (cudaStream_t)stream;
     TSS_DISPATCH_DTYPE(dtype, "bilinear_bwd", {
-        bilinear_bwd_kernel<T><<<stream_grid((int64_t)N * Hi * Wi * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
-            (const T*)dy, (T*)dx, N, Hi, Wi, Ho, Wo, C, lddy, lddx, ac_scale(Hi, Ho), ac_scale(Wi, Wo));
-        TSS_LAUNCH_CHECK("bilinear_bwd");
+        if (workspace == nullptr) {      // single gather pass (fine for small maps)
+            bilinear_bwd_kernel<T><<<stream_grid((int64_t)N * Hi * Wi * (C / 8)), kThreads, 0, st>>>(
+                (const T*)dy, (T*)dx, N, Hi, Wi, Ho, Wo, C, lddy, lddx, ac_scale(Hi, Ho), ac_scale(Wi, Wo));
+            TSS_LAUNCH_CHECK("bilinear_bwd");
+            return TSS_OK;
+        }
+        // separable: rows first (Ho -> Hi) into the fp32 workspace [N][Hi][Wo][C], then columns
+        resize_bwd_axis_kernel<T, float><<<stream_grid((int64_t)N * Hi * Wo * (C / 8)), kThreads, 0, st>>>(
+            (const T*)dy, workspace, N, Ho, Hi, Wo, C, lddy, C, ac_scale(Hi, Ho));
+        TSS_LAUNCH_CHECK("bilinear_bwd(rows)");
+        resize_bwd_axis_kernel<float, T><<<stream_grid((int64_t)N * Hi * Wi * (C / 8)), kThreads, 0, st>>>(
+            workspace, (T*)dx, (int64_t)N * Hi, Wo, Wi, 1, C, C, lddx, ac_scale(Wi, Wo));
+        TSS_LAUNCH_CHECK("bilinear_bwd(cols)");
         return TSS_OK;
     });
 }

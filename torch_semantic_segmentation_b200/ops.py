@@ -303,8 +303,13 @@ def bilinear_fwd(x, Ho, Wo, out=None):
 def bilinear_bwd(dy, Hi, Wi):
     N, C, Ho, Wo, lddy = _g(dy, 'bilinear_bwd')
     dx = empty_nhwc(N, C, Hi, Wi, dy.dtype, dy.device)
-    _lib.call('tss_bilinear_bwd', dy=dy, dx=dx, N=N, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, C=C, lddy=lddy,
-              lddx=C, dtype=dtype_code(dy.dtype))
+    # separable rows-then-columns transpose through an fp32 scratch (Ho/Hi + Wo/Wi taps instead
+    # of their product); tiny maps take the single gather pass
+    ws = None
+    if N * Ho * Wo * C >= (1 << 16):
+        ws = torch.empty(N * Hi * Wo * C, dtype=torch.float32, device=dy.device)
+    _lib.call('tss_bilinear_bwd', dy=dy, dx=dx, workspace=ws, N=N, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, C=C,
+              lddy=lddy, lddx=C, dtype=dtype_code(dy.dtype))
     return dx
 
 
