@@ -117,15 +117,22 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
         }
     }
     if (stats != nullptr) {
+        // two-stage reduction without shared atomics: the input tile is dead, so every thread
+        // parks its 16 partial sums there ([2][col][CB]); then one thread per channel sums the
+        // TW columns and issues the CTA's single global atomic for that channel
+        __syncthreads();
+        float* part = (float*)tile;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            atomicAdd(&s_stat[cg * 8 + e], s1[e]);
-            atomicAdd(&s_stat[CB + cg * 8 + e], s2[e]);
+            part[(size_t)col * CB + cg * 8 + e] = s1[e];
+            part[(size_t)(TW + col) * CB + cg * 8 + e] = s2[e];
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < CB; i += blockDim.x) {
-            atomicAdd(stats + cb0 + i, s_stat[i]);
-            atomicAdd(stats + C + cb0 + i, s_stat[CB + i]);
+        for (int i = threadIdx.x; i < 2 * CB; i += blockDim.x) {
+            const int which = i / CB, ch = i - which * CB;
+            float s = 0.f;
+            for (int cidx = 0; cidx < TW; ++cidx) s += part[(size_t)(which * TW + cidx) * CB + ch];
+            atomicAdd(stats + which * C + cb0 + ch, s);
         }
     }
 }
