@@ -62,8 +62,10 @@ def kernels():
 
 def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    once = '--once' in sys.argv   # under ncu: a single launch per kernel keeps the report small
     for fn in kernels():
-        fn()                      # warm-up launch
+        if not once:
+            fn()                  # warm-up launch
         torch.cuda.synchronize()
         flush.zero_()
         fn()                      # the launch to look at
