@@ -208,16 +208,18 @@ def kernel_table(device):
         add('dwconv_fwd C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_fwd(xi, wd, s, d, stats=sd))
         add('dwconv_dgrad C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_dgrad(yo, wd, xi.shape[2], xi.shape[3], s, d))
         add('dwconv_wgrad C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_wgrad(xi, yo, torch.zeros_like(wd), s, d))
-    # pointwise GEMMs (impl 0 until the tcgen05 kernel lands)
+    # pointwise GEMMs: the tcgen05/TMEM/TMA kernels the bf16 model runs (impl 1)
     for K, Nc, div, cnt in [(32, 48, 4, 1), (64, 384, 8, 1), (128, 128, 8, 3), (64, 128, 8, 1), (384, 64, 16, 3), (64, 384, 16, 3)]:
         xi = act(K, div)
         wp = torch.randn(Nc, K, 1, 1, device=device) * 0.05
         yo = act(Nc, div)
         sp = torch.zeros(2 * Nc, device=device)
+        pk = ops.pack_weights_bf16(wp)
+        dwp = torch.zeros_like(wp)
         io = 2 * px(div) * (K + Nc)
-        add('pwconv_fwd %d->%d @1/%d' % (K, Nc, div), cnt, io, lambda: ops.pwconv_fwd(xi, wp, stats=sp))
-        add('pwconv_dgrad %d->%d @1/%d' % (K, Nc, div), cnt, io, lambda: ops.pwconv_dgrad(yo, wp))
-        add('pwconv_wgrad %d->%d @1/%d' % (K, Nc, div), cnt, io, lambda: ops.pwconv_wgrad(xi, yo, torch.zeros_like(wp)))
+        add('pwconv_fwd %d->%d @1/%d' % (K, Nc, div), cnt, io + 2 * K * Nc, lambda: ops.pwconv_fwd(xi, wp, stats=sp, wp=pk[0], impl=1))
+        add('pwconv_dgrad %d->%d @1/%d' % (K, Nc, div), cnt, io + 2 * K * Nc, lambda: ops.pwconv_dgrad(yo, wp, wpT=pk[1], impl=1))
+        add('pwconv_wgrad %d->%d @1/%d' % (K, Nc, div), cnt, io + 4 * K * Nc, lambda: ops.pwconv_wgrad(xi, yo, dwp, impl=1))
     rows.sort(key=lambda r: -r['share_ms'])
     return rows
 

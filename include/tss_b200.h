@@ -99,6 +99,18 @@ int tss_stem3x3s2_fwd(const float* x, const float* w, void* y, int N, int H, int
                       int dtype, void* stream);
 int tss_stem3x3s2_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout,
                         int dtype, void* stream);
+/* Dense 3x3, stride 1, padding 1, C -> Cout between equal-sized NHWC maps: replaces
+ * nn.Conv2d(128, 128, 3, padding=1, bias=False) at contextnet.py:55.  It runs as the pointwise
+ * GEMM above over a tap-major patch matrix:
+ *   col[N*H*W][9*C], col[m][tap*C + c] = x[n][h+ky-1][w+kx-1][c] (0 outside), tap = ky*3+kx
+ *   wk[Cout][9*C],   wk[co][tap*C + c] = w[co][c][ky][kx]
+ * im2col3x3 builds col; col2im3x3 is its transpose (dx from the GEMM dgrad's dcol);
+ * permute_weights3x3 converts the (Cout,C,3,3) parameter to wk (backward = 0) or accumulates a
+ * tap-major gradient dwk into the (Cout,C,3,3) gradient (backward = 1: dst += permuted src). */
+int tss_im2col3x3(const void* x, void* col, int N, int H, int W, int C, int dtype, void* stream);
+int tss_col2im3x3(const void* dcol, void* dx, int N, int H, int W, int C, int dtype, void* stream);
+int tss_permute_weights3x3(const float* src, float* dst, int Cout, int Cin, int backward, void* stream);
+
 /* ---- BatchNorm (training) -----------------------------------------------------------------
  * replaces nn.BatchNorm2d (+ nn.ReLU / F.relu / residual add) at fastscnn.py:169-172,
  * 181-184,193-198,158-161,89.

@@ -86,6 +86,28 @@ class FakeBackend:
             wpT.copy_(w.view(Nc, K).t())
         return 0
 
+    # ---------------------------------------------------------------- dense 3x3 as a patch GEMM
+    def tss_im2col3x3(self, x, col, N, H, W, C, dtype):
+        xp = F.pad(x, (1, 1, 1, 1))
+        taps = [xp[:, :, ky:ky + H, kx:kx + W] for ky in range(3) for kx in range(3)]
+        col.copy_(torch.cat(taps, dim=1))
+        return 0
+
+    def tss_col2im3x3(self, dcol, dx, N, H, W, C, dtype):
+        acc = torch.zeros(N, C, H + 2, W + 2)
+        for tap in range(9):
+            ky, kx = divmod(tap, 3)
+            acc[:, :, ky:ky + H, kx:kx + W] += dcol[:, tap * C:(tap + 1) * C].float()
+        dx.copy_(acc[:, :, 1:H + 1, 1:W + 1])
+        return 0
+
+    def tss_permute_weights3x3(self, src, dst, Cout, Cin, backward):
+        if backward:
+            dst += src.detach().view(Cout, 9, Cin).permute(0, 2, 1).reshape(Cout, Cin, 3, 3)
+        else:
+            dst.copy_(src.detach().reshape(Cout, Cin, 9).permute(0, 2, 1).reshape(Cout, 9 * Cin, 1, 1))
+        return 0
+
     # ---------------------------------------------------------------- stem
     def tss_stem3x3s2_fwd(self, x, w, y, N, H, W, Cout, scale, shift, flags, stats, dtype):
         raw = F.conv2d(x, w, None, 2, 1)

@@ -153,3 +153,54 @@ def test_flat_adamw_matches_oracle_adamw(fake_backend):
         out = model.eval()(x)
         want = model_forward('fastscnn', {k: v.detach() for k, v in sd.items()}, x, False)
     assert rel(out, want) < 5e-2
+
+
+# ------------------------------------------------------------------ ContextNet (config 3) ----
+def test_contextnet_state_dict_is_the_reference_layout(fake_backend):
+    from torch_semantic_segmentation_b200.models.contextnet import contextnet14
+    torch.manual_seed(0)
+    model = contextnet14(3, 19)
+    want = init_state('contextnet14', 0)
+    got = model.state_dict()
+    assert list(got.keys()) == list(want.keys())
+    for k in want:
+        assert got[k].shape == want[k].shape and torch.equal(got[k], want[k]), k
+    model.load_state_dict(want, strict=True)
+
+
+@pytest.mark.parametrize('shape', [(1, 3, 160, 224), (1, 3, 72, 104)])
+def test_contextnet_eval_forward_matches_oracle(fake_backend, shape):
+    from torch_semantic_segmentation_b200.models.contextnet import contextnet14
+    torch.manual_seed(0)
+    model = contextnet14(3, 19).eval()
+    x = eval_input('contextnet14') if shape == (1, 3, 160, 224) else torch.randn(*shape, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        out = model(x)
+    ref = model_forward('contextnet14', init_state('contextnet14', 0), x, False)
+    assert out.shape == ref.shape and out.is_contiguous()
+    assert rel(out, ref) < 1e-5
+
+
+def test_contextnet_train_step_matches_oracle(fake_backend):
+    from torch_semantic_segmentation_b200.models.contextnet import contextnet14
+    torch.manual_seed(0)
+    model = _no_dropout(contextnet14(3, 19)).train()
+    x, y = train_batch('contextnet14')
+    out = model(x)
+    loss = CrossEntropyLoss(ignore_index=255)(out, y)
+    loss.backward()
+    sd = split_state(init_state('contextnet14', 0))
+    ref_loss, ref_logits, ref_grads = loss_and_grads('contextnet14', sd, x, y, dropout_mask=1.0)
+    assert abs(float(loss) - float(ref_loss)) < 1e-5
+    assert rel(out, ref_logits) < 1e-4
+    params = dict(model.named_parameters())
+    for k in ('classifier.5.weight', 'classifier.5.bias', 'classifier.3.1.weight'):
+        assert rel(params[k].grad, ref_grads[k]) < 1e-4, k
+    # conv weights in front of a BatchNorm (their gradient is a near-cancellation; the fp32 reference
+    # itself is ~1e-2 from an fp64 run), incl. the dense 3x3 = patch GEMM + tap-major permutation
+    for k in ('classifier.3.0.weight', 'context.7.0.weight', 'context.6.1.conv3.0.weight', 'context.0.0.weight', 'spatial.0.0.weight'):
+        assert rel(params[k].grad, ref_grads[k]) < 3e-2, k
+    msd = model.state_dict()
+    for k in sd:
+        if 'running' in k:
+            assert (msd[k] - sd[k]).abs().max() < 1e-5, k

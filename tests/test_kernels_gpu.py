@@ -417,11 +417,44 @@ def test_adamw_flat_arena():
     assert rel(pg, p_ref) < 1e-6 and float(hyper[5]) == 3.0
 
 
+# ------------------------------------------------------------------ dense 3x3 as a patch GEMM
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('N,C,H,W', [(2, 128, 6, 9), (1, 16, 1, 1), (3, 8, 5, 2), (1, 128, 32, 64)])
+def test_dense3x3_patch_matrix(N, C, H, W, dtype):
+    g = gen(N * C + H)
+    code = _lib.dtype_code(dtype)
+    xc, xg = pair(N, C, H, W, dtype, g)
+    cc, cg = pair(N, 9 * C, H, W, dtype, g)
+    both('tss_im2col3x3', dict(x=xc, col=cc, N=N, H=H, W=W, C=C, dtype=code), dict(x=xg, col=cg, N=N, H=H, W=W, C=C, dtype=code))
+    assert torch.equal(cg.cpu(), cc)                                  # a pure copy: bit-exact
+    # the patch GEMM equals the dense convolution
+    w = torch.randn(16, C, 3, 3, generator=g)
+    wk_c, wk_g = torch.empty(16, 9 * C, 1, 1), torch.empty(16, 9 * C, 1, 1).cuda()
+    both('tss_permute_weights3x3', dict(src=w, dst=wk_c, Cout=16, Cin=C, backward=0),
+         dict(src=w.cuda(), dst=wk_g, Cout=16, Cin=C, backward=0))
+    assert torch.equal(wk_g.cpu(), wk_c)
+    ref = torch.nn.functional.conv2d(xc.float(), w, padding=1)
+    got = torch.nn.functional.conv2d(cg.cpu().float(), wk_g.cpu())
+    assert rel(got, ref) < 1e-5
+    # transposes
+    dcc, dcg = pair(N, 9 * C, H, W, dtype, g)
+    dxc, dxg = pair(N, C, H, W, dtype, g)
+    both('tss_col2im3x3', dict(dcol=dcc, dx=dxc, N=N, H=H, W=W, C=C, dtype=code), dict(dcol=dcg, dx=dxg, N=N, H=H, W=W, C=C, dtype=code))
+    assert rel(dxg, dxc) < TOL[dtype]
+    dwk = torch.randn(16, 9 * C, 1, 1, generator=g)
+    dwc = torch.randn(16, C, 3, 3, generator=g)
+    dwg = dwc.clone().cuda()
+    both('tss_permute_weights3x3', dict(src=dwk, dst=dwc, Cout=16, Cin=C, backward=1),
+         dict(src=dwk.cuda(), dst=dwg, Cout=16, Cin=C, backward=1))
+    assert torch.equal(dwg.cpu(), dwc)
+
+
 # ------------------------------------------------------------------ tcgen05 pointwise ---
 TC_CASES = [  # K, Nc, M (rows = N*H*W with N=1, H=1)
     (64, 64, 128), (64, 64, 4096), (32, 48, 1000), (48, 64, 777), (64, 384, 2304), (384, 64, 2304), (384, 96, 576),
     (96, 576, 576), (576, 96, 576), (576, 128, 576), (128, 768, 576), (768, 128, 576), (256, 128, 576), (128, 128, 9216),
     (64, 128, 9216), (128, 32, 12), (192, 32, 300), (288, 48, 300), (48, 288, 300), (32, 32, 129), (128, 128, 1),
+    (32, 192, 500), (192, 48, 500), (288, 64, 300), (1152, 128, 2048), (32, 64, 700),
 ]
 
 

@@ -166,3 +166,66 @@ def test_evaluator_metrics_match_oracle():
     assert float(st.metrics['miou']) == met['miou']
     ref_loss = F.cross_entropy(logits, y, ignore_index=255)
     assert abs(st.metrics['loss'] - float(ref_loss)) < 1e-4 * float(ref_loss)
+
+
+# ------------------------------------------------------------------ ContextNet-14 (config 3) --
+def make_contextnet(dtype=torch.float32):
+    from torch_semantic_segmentation_b200.models.contextnet import contextnet14
+    torch.manual_seed(0)
+    model = contextnet14(3, 19).cuda().set_compute_dtype(dtype)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    return model
+
+
+def test_contextnet_eval_forward_matches_golden_and_oracle():
+    model = make_contextnet().eval()
+    x = eval_input('contextnet14')
+    with torch.no_grad():
+        out = model(x.cuda())
+    ref = model_forward('contextnet14', init_state('contextnet14', 0), x, False)
+    assert out.shape == ref.shape and out.is_contiguous()
+    assert rel(out, ref) < 1e-4
+    g = np.load(os.path.join(GOLDEN_DIR, 'contextnet14_eval.npz'))
+    sy, sx = SUBSAMPLE
+    np.testing.assert_allclose(out[:, :, ::sy, ::sx].cpu().numpy(), g['sub'], rtol=1e-3, atol=1e-5)
+    # any input size (the reference's fusion module resizes; contextnet.py:119-121)
+    x2 = torch.randn(2, 3, 72, 104, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        out2 = model(x2.cuda())
+    ref2 = model_forward('contextnet14', init_state('contextnet14', 0), x2, False)
+    assert out2.shape == ref2.shape and rel(out2, ref2) < 1e-4
+    # bf16 inference
+    with torch.no_grad():
+        low = make_contextnet(torch.bfloat16).eval()(x.cuda())
+    assert low.dtype == torch.bfloat16 and rel(low, ref) < 2e-2
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_contextnet_train_forward_backward(dtype):
+    model = make_contextnet(dtype).train()
+    x, y = train_batch('contextnet14')
+    out = model(x.cuda())
+    loss = CrossEntropyLoss(ignore_index=255)(out, y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    sd = split_state(init_state('contextnet14', 0))
+    ref_loss, ref_logits, ref_grads = loss_and_grads('contextnet14', sd, x, y, dropout_mask=1.0)
+    params = dict(model.named_parameters())
+    msd = model.state_dict()
+    if dtype == torch.float32:
+        assert rel(out, ref_logits) < 1e-4
+        assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+        for k in ('classifier.5.weight', 'classifier.5.bias'):
+            assert rel(params[k].grad, ref_grads[k]) < 1e-4, k
+        worst = max(rel(p.grad, ref_grads[k]) for k, p in params.items() if k.endswith('.0.weight'))
+        assert worst < 5e-2, worst
+        for k in sd:
+            if 'running' in k:
+                torch.testing.assert_close(msd[k].cpu(), sd[k], rtol=1e-3, atol=1e-5, msg=k)
+    else:
+        assert abs(float(loss) - float(ref_loss)) < 3e-2 * abs(float(ref_loss))
+        for k in ('spatial.0.1.running_mean', 'spatial.0.1.running_var', 'context.0.1.running_var'):
+            assert rel(msd[k], sd[k]) < 2e-2, k
+        assert all(torch.isfinite(p.grad).all() for p in params.values())

@@ -149,6 +149,39 @@ class ConvBNAct(torch.autograd.Function):
                 None if gb is not None else gb_out, None, None)
 
 
+class Im2Col3x3(torch.autograd.Function):
+    """Patch matrix of a dense 3x3 / stride 1 / padding 1 convolution (contextnet.py:55)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.im2col3x3(x)
+
+    @staticmethod
+    def backward(ctx, dcol):
+        return ops.col2im3x3(ops.as_nhwc(dcol))
+
+
+class TapMajorWeight(torch.autograd.Function):
+    """(Cout, Cin, 3, 3) parameter -> the (Cout, 9*Cin, 1, 1) matrix the patch GEMM multiplies with;
+    backward accumulates straight into the optimizer's gradient arena when there is one."""
+
+    @staticmethod
+    def forward(ctx, w):
+        ctx.param = w
+        ctx.arena = getattr(w, '_tss_grad', None)
+        ctx.shape = w.shape
+        return ops.permute_weights3x3(w)
+
+    @staticmethod
+    def backward(ctx, dwk):
+        if ctx.arena is not None:
+            ops.permute_weights3x3_bwd(dwk.contiguous(), ctx.arena)
+            grad_ready(ctx.param)
+            return None
+        dw = torch.zeros(ctx.shape, dtype=torch.float32, device=dwk.device)
+        return ops.permute_weights3x3_bwd(dwk.contiguous(), dw)
+
+
 class ConvBias(torch.autograd.Function):
     """y = conv1x1(x, w) + b  (class scores; Nc = 19 lives in a padded channel pitch)."""
 

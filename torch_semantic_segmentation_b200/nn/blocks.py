@@ -38,6 +38,9 @@ class _FusedConvBN:
         if conv.kernel_size == (3, 3) and conv.groups == 1 and conv.in_channels == 3 and conv.stride == (2, 2) \
                 and conv.padding == (1, 1):
             return 'stem'
+        if conv.kernel_size == (3, 3) and conv.groups == 1 and conv.in_channels % 8 == 0 and conv.stride == (1, 1) \
+                and conv.padding == (1, 1) and conv.dilation == (1, 1):
+            return 'dense3'
         raise RuntimeError('no sm_100a kernel for %r' % (conv,))
 
     def _spec(self, ci, relu):
@@ -45,7 +48,9 @@ class _FusedConvBN:
         spec = self._specs.get(key)
         if spec is None:
             conv, bn = self[ci], self[ci + 1]
-            spec = Fn.ConvSpec(self._kind(conv), conv.stride[0], conv.dilation[0], relu, bn,
+            kind = self._kind(conv)
+            # a dense 3x3 runs as the pointwise GEMM over its patch matrix (csrc/conv3x3.cu)
+            spec = Fn.ConvSpec('pw' if kind == 'dense3' else kind, conv.stride[0], conv.dilation[0], relu, bn,
                                self.compute_dtype, self.pw_impl)
             self._specs[key] = spec
         return spec
@@ -83,15 +88,24 @@ class _FusedConvBN:
                 x = x.to(self.compute_dtype)
         if res is not None:
             res = ops.as_nhwc(res)
-        packed = self._packed(ci)
+        weight = conv.weight
+        if self._kind(conv) == 'dense3':
+            x = Fn.Im2Col3x3.apply(x)
+            weight = Fn.TapMajorWeight.apply(weight)
+            packed = None
+            if self.pw_impl != 0 and self.compute_dtype == torch.bfloat16 and weight.shape[0] % 16 == 0 \
+                    and weight.shape[1] % 16 == 0:
+                packed = ops.pack_weights_bf16(weight.detach())
+        else:
+            packed = self._packed(ci)
         use_batch_stats = self.training or not bn.track_running_stats
         if use_batch_stats:
-            return Fn.ConvBNAct.apply(x, res, conv.weight, bn.weight, bn.bias, spec, packed)
+            return Fn.ConvBNAct.apply(x, res, weight, bn.weight, bn.bias, spec, packed)
         if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
             raise RuntimeError('eval-mode BatchNorm with autograd is not implemented; '
                                'wrap inference in torch.no_grad()')
         scale, shift = self._folded(ci)
-        return Fn.conv_forward(spec, x, conv.weight, scale=scale, shift=shift, res=res, relu=relu,
+        return Fn.conv_forward(spec, x, weight, scale=scale, shift=shift, res=res, relu=relu,
                                packed=packed)
 
 

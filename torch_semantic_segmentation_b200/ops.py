@@ -163,6 +163,41 @@ def stem_wgrad(x, dy, dw):
               dtype=dtype_code(dy.dtype))
 
 
+# ------------------------------------------------------------------ dense 3x3 ----------
+def im2col3x3(x):
+    """(N, C, H, W) NHWC -> tap-major patch matrix as an NHWC tensor of logical shape (N, 9C, H, W)."""
+    N, C, H, W, ld = _g(x, 'im2col3x3')
+    if ld != C:
+        raise RuntimeError('im2col3x3: pitched input not supported')
+    col = empty_nhwc(N, 9 * C, H, W, x.dtype, x.device)
+    _lib.call('tss_im2col3x3', x=x, col=col, N=N, H=H, W=W, C=C, dtype=dtype_code(x.dtype))
+    return col
+
+
+def col2im3x3(dcol):
+    N, C9, H, W, ld = _g(dcol, 'col2im3x3')
+    if ld != C9 or C9 % 9:
+        raise RuntimeError('col2im3x3: expects a dense (N, 9C, H, W) NHWC gradient')
+    dx = empty_nhwc(N, C9 // 9, H, W, dcol.dtype, dcol.device)
+    _lib.call('tss_col2im3x3', dcol=dcol, dx=dx, N=N, H=H, W=W, C=C9 // 9, dtype=dtype_code(dcol.dtype))
+    return dx
+
+
+def permute_weights3x3(w):
+    """(Cout, Cin, 3, 3) fp32 -> tap-major (Cout, 9*Cin, 1, 1) fp32."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    wk = torch.empty((Cout, 9 * Cin, 1, 1), dtype=torch.float32, device=w.device)
+    _lib.call('tss_permute_weights3x3', src=w, dst=wk, Cout=Cout, Cin=Cin, backward=0)
+    return wk
+
+
+def permute_weights3x3_bwd(dwk, dw):
+    """dw (Cout, Cin, 3, 3) += tap-major gradient dwk (Cout, 9*Cin, 1, 1)."""
+    Cout, Cin = dw.shape[0], dw.shape[1]
+    _lib.call('tss_permute_weights3x3', src=dwk, dst=dw, Cout=Cout, Cin=Cin, backward=1)
+    return dw
+
+
 # ------------------------------------------------------------------ batch norm ---------
 def bn_finalize(stats, count, bn, momentum, eps, update_running=True):
     """-> scale, shift, mean, rstd (fp32 (C,)); updates bn's running stats in place."""
