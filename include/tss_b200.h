@@ -116,11 +116,14 @@ int tss_permute_weights3x3(const float* src, float* dst, int Cout, int Cin, int 
  * 181-184,193-198,158-161,89.
  * finalize: from stats[2C] (sum, sum of squares over `count` values per channel) compute
  * mean[c], rstd[c] = 1/sqrt(var_biased+eps), scale = gamma*rstd, shift = beta-mean*scale and
- * update running_mean/var (momentum, unbiased var) and num_batches_tracked (int64, may be NULL). */
-int tss_bn_finalize(const float* stats, int64_t count, const float* gamma, const float* beta,
+ * update running_mean/var (momentum, unbiased var) and num_batches_tracked (int64, may be NULL).
+ * clear_n > 0: "consume and clear" -- stats[0..clear_n) is zeroed after it has been read, so a
+ * per-layer scratch [stats 2C | backward sums 2C] is zero again for the next conv epilogue /
+ * bn_bwd_reduce without a memset launch per layer. */
+int tss_bn_finalize(float* stats, int64_t count, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, int64_t* num_batches_tracked,
                     float momentum, float eps, float* scale, float* shift, float* mean,
-                    float* rstd, int C, void* stream);
+                    float* rstd, int C, int64_t clear_n, void* stream);
 /* eval mode: scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale */
 int tss_bn_fold(const float* gamma, const float* beta, const float* running_mean,
                 const float* running_var, float eps, float* scale, float* shift, int C,
@@ -131,14 +134,16 @@ int tss_bn_apply(const void* y, const float* scale, const float* shift, const vo
                  int C, int64_t ldy, int64_t ldy2, int64_t ldr, int64_t ldz, int flags, int dtype,
                  void* stream);
 /* backward, pass 1: g = dz * (z > 0 if relu); sums[c] += sum g ; sums[C+c] += sum g*xhat,
- * xhat = (y-mean)*rstd.  z may be NULL when there was no ReLU. */
+ * xhat = (y-mean)*rstd.  z == NULL with TSS_EPI_RELU: the mask is recomputed from y as
+ * fma(y, gamma*rstd, beta - mean*gamma*rstd) > 0 -- the forward's own arithmetic, so the mask is
+ * identical and z need not be read (valid when no residual was added before the ReLU). */
 int tss_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean,
-                      const float* rstd, float* sums, int64_t M, int C, int64_t lddz, int64_t ldz,
-                      int64_t ldy, int flags, int dtype, void* stream);
+                      const float* rstd, const float* gamma, const float* beta, float* sums, int64_t M,
+                      int C, int64_t lddz, int64_t ldz, int64_t ldy, int flags, int dtype, void* stream);
 /* backward, pass 2: dy = gamma*rstd*(g - sums[c]/M - xhat*sums[C+c]/M); optional dres = g.
  * dgamma[c] += sums[C+c], dbeta[c] += sums[c] (done by block 0; may be NULL). */
 int tss_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean,
-                     const float* rstd, const float* gamma, const float* sums, void* dy, void* dres,
+                     const float* rstd, const float* gamma, const float* beta, const float* sums, void* dy, void* dres,
                      float* dgamma, float* dbeta, int64_t M, int C, int64_t lddz, int64_t ldz,
                      int64_t ldy, int64_t lddy, int64_t lddres, int flags, int dtype, void* stream);
 /* g = dz * (z > 0): ReLU backward alone (fusion add, eval-free paths) */

@@ -31,7 +31,7 @@ def _stats(stats, y):
     if stats is not None:
         C = y.shape[1]
         stats[:C] += y.sum(dim=(0, 2, 3))
-        stats[C:] += (y * y).sum(dim=(0, 2, 3))
+        stats[C:2 * C] += (y * y).sum(dim=(0, 2, 3))
 
 
 class FakeBackend:
@@ -121,11 +121,11 @@ class FakeBackend:
 
     # ---------------------------------------------------------------- batch norm
     def tss_bn_finalize(self, stats, count, gamma, beta, running_mean, running_var, num_batches_tracked,
-                        momentum, eps, scale, shift, mean, rstd, C):
+                        momentum, eps, scale, shift, mean, rstd, C, clear_n=0):
         if count <= 1:
             raise RuntimeError('tss_bn_finalize failed (1): Expected more than 1 value per channel when training')
         m = stats[:C].double() / count
-        var = (stats[C:].double() / count - m * m).clamp_min(0)
+        var = (stats[C:2 * C].double() / count - m * m).clamp_min(0)
         r = 1.0 / torch.sqrt(var + eps)
         mean.copy_(m)
         rstd.copy_(r)
@@ -136,6 +136,8 @@ class FakeBackend:
             running_var.mul_(1 - momentum).add_(momentum * (var * count / (count - 1)).float())
         if num_batches_tracked is not None:
             num_batches_tracked += 1
+        if clear_n:
+            stats[:clear_n].zero_()
         return 0
 
     def tss_bn_fold(self, gamma, beta, running_mean, running_var, eps, scale, shift, C):
@@ -155,22 +157,26 @@ class FakeBackend:
         return 0
 
     @staticmethod
-    def _g(dz, z, flags):
+    def _g(dz, z, flags, y=None, mean=None, rstd=None, gamma=None, beta=None):
         g = dz.float()
         if flags & RELU:
+            if z is None:      # mask recomputed from y with the forward's arithmetic
+                v = lambda t: t.detach().view(1, -1, 1, 1)
+                sc = v(gamma) * v(rstd)
+                z = torch.addcmul(v(beta) - v(mean) * sc, y.float(), sc)
             g = g * (z.float() > 0)
         return g
 
-    def tss_bn_bwd_reduce(self, dz, z, y, mean, rstd, sums, M, C, lddz, ldz, ldy, flags, dtype):
-        g = self._g(dz, z, flags)
+    def tss_bn_bwd_reduce(self, dz, z, y, mean, rstd, gamma, beta, sums, M, C, lddz, ldz, ldy, flags, dtype):
+        g = self._g(dz, z, flags, y, mean, rstd, gamma, beta)
         xh = (y.float() - mean.view(1, -1, 1, 1)) * rstd.view(1, -1, 1, 1)
         sums[:C] += g.sum(dim=(0, 2, 3))
         sums[C:] += (g * xh).sum(dim=(0, 2, 3))
         return 0
 
-    def tss_bn_bwd_apply(self, dz, z, y, mean, rstd, gamma, sums, dy, dres, dgamma, dbeta, M, C, lddz, ldz,
+    def tss_bn_bwd_apply(self, dz, z, y, mean, rstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C, lddz, ldz,
                          ldy, lddy, lddres, flags, dtype):
-        g = self._g(dz, z, flags)
+        g = self._g(dz, z, flags, y, mean, rstd, gamma, beta)
         v = lambda t: t.detach().view(1, -1, 1, 1)
         xh = (y.float() - v(mean)) * v(rstd)
         dy.copy_(v(gamma) * v(rstd) * (g - v(sums[:C]) / M - xh * v(sums[C:]) / M))

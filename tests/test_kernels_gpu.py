@@ -194,7 +194,9 @@ def test_batchnorm_family(C, N, H, W, dtype):
     M = N * H * W
     yc, yg = pair(N, C, H, W, dtype, g)
     # finalize
-    stats = torch.stack([yc.float().sum((0, 2, 3)), (yc.float() ** 2).sum((0, 2, 3))]).reshape(-1)
+    stats = torch.cat([torch.stack([yc.float().sum((0, 2, 3)), (yc.float() ** 2).sum((0, 2, 3))]).reshape(-1),
+                       torch.ones(2 * C)])          # [statistics | a backward-sums half that must get cleared]
+    stats_g = stats.cuda()
     gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
     outs_c = [torch.empty(C) for _ in range(4)]
     outs_g = [torch.empty(C).cuda() for _ in range(4)]
@@ -202,11 +204,12 @@ def test_batchnorm_family(C, N, H, W, dtype):
     rmg, rvg, nbtg = rm.clone().cuda(), rv.clone().cuda(), nbt.clone().cuda()
     names = ('scale', 'shift', 'mean', 'rstd')
     both('tss_bn_finalize', dict(stats=stats, count=M, gamma=gamma, beta=beta, running_mean=rm, running_var=rv,
-                                 num_batches_tracked=nbt, momentum=0.1, eps=1e-5, C=C, **dict(zip(names, outs_c))),
-         dict(stats=stats.cuda(), count=M, gamma=gamma.cuda(), beta=beta.cuda(), running_mean=rmg, running_var=rvg,
+                                 num_batches_tracked=nbt, momentum=0.1, eps=1e-5, C=C, clear_n=4 * C, **dict(zip(names, outs_c))),
+         dict(stats=stats_g, clear_n=4 * C, count=M, gamma=gamma.cuda(), beta=beta.cuda(), running_mean=rmg, running_var=rvg,
               num_batches_tracked=nbtg, momentum=0.1, eps=1e-5, C=C, **dict(zip(names, outs_g))))
     for a, b in zip(outs_g, outs_c):
         assert rel(a, b) < 1e-5
+    assert not stats_g.any() and not stats.any()        # consume-and-clear
     assert rel(rmg, rm) < 1e-6 and rel(rvg, rv) < 1e-6 and int(nbtg) == 4
     # against nn.functional.batch_norm's own statistics
     want_var = yc.float().var((0, 2, 3), unbiased=False)
@@ -229,19 +232,24 @@ def test_batchnorm_family(C, N, H, W, dtype):
         assert rel(zg, zc) < TOL[dtype]
     # backward (z from the last apply: relu, no residual)
     dzc, dzg = pair(N, C, H, W, dtype, g)
-    for relu in (1, 0):
+    ref_sums = None
+    for relu, use_z in ((1, True), (1, False), (0, False)):      # use_z False + relu: mask recomputed from y
         sums_c, sums_g = torch.zeros(2 * C), torch.zeros(2 * C).cuda()
         kb = dict(M=M, C=C, lddz=C, ldz=C, ldy=C, flags=relu, dtype=code)
-        both('tss_bn_bwd_reduce', dict(dz=dzc, z=zc if relu else None, y=yc, mean=mean, rstd=rstd, sums=sums_c, **kb),
-             dict(dz=dzg, z=zg if relu else None, y=yg, mean=mean.cuda(), rstd=rstd.cuda(), sums=sums_g, **kb))
+        both('tss_bn_bwd_reduce', dict(dz=dzc, z=zc if use_z else None, y=yc, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums_c, **kb),
+             dict(dz=dzg, z=zg if use_z else None, y=yg, mean=mean.cuda(), rstd=rstd.cuda(), gamma=gamma.cuda(), beta=beta.cuda(), sums=sums_g, **kb))
         assert rel(sums_g, sums_c) < 1e-4
+        if relu and use_z:
+            ref_sums = sums_g.clone()
+        elif relu:
+            assert torch.equal(sums_g.cpu() != 0, ref_sums.cpu() != 0) and rel(sums_g, ref_sums) < 1e-5   # same mask
         dyc, dyg = pair(N, C, H, W, dtype, g)
         drc, drg = pair(N, C, H, W, dtype, g)
         dgc, dbc = torch.randn(C, generator=g), torch.randn(C, generator=g)
         dgg, dbg = dgc.clone().cuda(), dbc.clone().cuda()
-        both('tss_bn_bwd_apply', dict(dz=dzc, z=zc if relu else None, y=yc, mean=mean, rstd=rstd, gamma=gamma, sums=sums_c,
+        both('tss_bn_bwd_apply', dict(dz=dzc, z=zc if use_z else None, y=yc, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums_c,
                                       dy=dyc, dres=drc, dgamma=dgc, dbeta=dbc, lddy=C, lddres=C, **kb),
-             dict(dz=dzg, z=zg if relu else None, y=yg, mean=mean.cuda(), rstd=rstd.cuda(), gamma=gamma.cuda(), sums=sums_c.cuda(),
+             dict(dz=dzg, z=zg if use_z else None, y=yg, mean=mean.cuda(), rstd=rstd.cuda(), gamma=gamma.cuda(), beta=beta.cuda(), sums=sums_c.cuda(),
                   dy=dyg, dres=drg, dgamma=dgg, dbeta=dbg, lddy=C, lddres=C, **kb))
         assert rel(dyg, dyc) < TOL[dtype] and rel(drg, drc) < TOL[dtype]
         assert rel(dgg, dgc) < 1e-5 and rel(dbg, dbc) < 1e-5

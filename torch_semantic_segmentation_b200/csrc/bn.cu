@@ -22,17 +22,22 @@ __device__ __forceinline__ void ldg8f(const float* __restrict__ p, float (&v)[8]
 }
 
 // ------------------------------------------------------------------ finalize / fold --
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, double inv_count, double unbias,
+__global__ void bn_finalize_kernel(float* __restrict__ stats, double inv_count, double unbias,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    int64_t* __restrict__ nbt, float momentum, float eps,
                                    float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int C) {
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int C,
+                                   int clear_n) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && nbt != nullptr) *nbt += 1;
     if (c >= C) return;
-    const double mean = (double)stats[c] * inv_count;
-    double var = (double)stats[C + c] * inv_count - mean * mean;
+    const float st1 = stats[c], st2 = stats[C + c];
+    // "consume and clear": thread c only ever touches indices == c (mod C), so nobody clears what
+    // another thread still has to read; the scratch is zero again for its next use
+    for (int i = c; i < clear_n; i += C) stats[i] = 0.f;
+    const double mean = (double)st1 * inv_count;
+    double var = (double)st2 * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
     const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     const float g = gamma != nullptr ? gamma[c] : 1.f;
@@ -105,6 +110,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
                      float* __restrict__ sums, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy,
                      int relu, int PL) {
     extern __shared__ float s_sum[];   // [2*C]
@@ -118,16 +124,31 @@ bn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T*
     zero8(s1); zero8(s2);
     ldg8f(mean + c0, mu);
     ldg8f(rstd + c0, rs);
+    // z == nullptr with ReLU: the mask is recomputed from y with the forward's own arithmetic
+    // (scale = gamma*rstd, shift = beta - mean*scale, fma) -- one tensor less to read
+    float sc[8], sh[8];
+    if (relu && z == nullptr) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            sc[e] = (gamma != nullptr ? __ldg(gamma + c0 + e) : 1.f) * rs[e];
+            sh[e] = (beta != nullptr ? __ldg(beta + c0 + e) : 0.f) - mu[e] * sc[e];
+        }
+    }
     if (pl < PL) {
         for (int64_t m = (int64_t)blockIdx.x * PL + pl; m < M; m += (int64_t)gridDim.x * PL) {
             float g[8], yy[8];
             load8(dz + m * lddz + c0, g);
             load8(y + m * ldy + c0, yy);
             if (relu) {
-                float zz[8];
-                load8(z + m * ldz + c0, zz);
+                if (z != nullptr) {
+                    float zz[8];
+                    load8(z + m * ldz + c0, zz);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
+                    for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) g[e] = fmaf(yy[e], sc[e], sh[e]) > 0.f ? g[e] : 0.f;
+                }
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -150,7 +171,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y,
                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const float* __restrict__ gamma, const float* __restrict__ sums,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ sums,
                     T* __restrict__ dy, T* __restrict__ dres, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy,
                     int64_t lddy, int64_t lddres, int relu, float inv_m) {
@@ -179,10 +201,19 @@ bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* 
         ldg8f(sums + c0, a1);
         ldg8f(sums + C + c0, a2);
         if (relu) {
-            float zz[8];
-            load8(z + m * ldz + c0, zz);
+            if (z != nullptr) {
+                float zz[8];
+                load8(z + m * ldz + c0, zz);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
+                for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float sc = ga[e] * rs[e];
+                    const float sh = (beta != nullptr ? __ldg(beta + c0 + e) : 0.f) - mu[e] * sc;
+                    g[e] = fmaf(yy[e], sc, sh) > 0.f ? g[e] : 0.f;
+                }
+            }
         }
         if (dres != nullptr) store8(dres + m * lddres + c0, g);
         float o[8];
@@ -268,11 +299,12 @@ int check_rows(const char* name, int64_t M, int C) {
 
 }  // namespace
 
-extern "C" int tss_bn_finalize(const float* stats, int64_t count, const float* gamma, const float* beta,
+extern "C" int tss_bn_finalize(float* stats, int64_t count, const float* gamma, const float* beta,
                                float* running_mean, float* running_var, int64_t* num_batches_tracked,
                                float momentum, float eps, float* scale, float* shift, float* mean,
-                               float* rstd, int C, void* stream) {
+                               float* rstd, int C, int64_t clear_n, void* stream) {
     TSS_REQUIRE(C > 0, "bn_finalize: C=%d", C);
+    TSS_REQUIRE(clear_n >= 0 && clear_n <= 64 * (int64_t)C, "bn_finalize: clear_n=%lld out of range", (long long)clear_n);
     // nn.BatchNorm2d raises "Expected more than 1 value per channel when training"
     TSS_REQUIRE(count > 1, "bn_finalize: Expected more than 1 value per channel when training, got %lld",
                 (long long)count);
@@ -280,7 +312,7 @@ extern "C" int tss_bn_finalize(const float* stats, int64_t count, const float* g
     const double unbias = (double)count / (double)(count - 1);
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         stats, 1.0 / (double)count, unbias, gamma, beta, running_mean, running_var, num_batches_tracked,
-        momentum, eps, scale, shift, mean, rstd, C);
+        momentum, eps, scale, shift, mean, rstd, C, (int)clear_n);
     TSS_LAUNCH_CHECK("bn_finalize");
     return TSS_OK;
 }
@@ -311,11 +343,11 @@ extern "C" int tss_bn_apply(const void* y, const float* scale, const float* shif
 }
 
 extern "C" int tss_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean,
-                                 const float* rstd, float* sums, int64_t M, int C, int64_t lddz, int64_t ldz,
+                                 const float* rstd, const float* gamma, const float* beta, float* sums,
+                                 int64_t M, int C, int64_t lddz, int64_t ldz,
                                  int64_t ldy, int flags, int dtype, void* stream) {
     if (int e = check_rows("bn_bwd_reduce", M, C)) return e;
     const int relu = flags & TSS_EPI_RELU;
-    TSS_REQUIRE(!relu || z != nullptr, "bn_bwd_reduce: ReLU mask needs z");
     const int CG = C / 8;
     TSS_REQUIRE(CG <= kThreads, "bn_bwd_reduce: C=%d too large", C);
     const int PL = kThreads / CG;
@@ -325,23 +357,22 @@ extern "C" int tss_bn_bwd_reduce(const void* dz, const void* z, const void* y, c
     const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
     TSS_DISPATCH_DTYPE(dtype, "bn_bwd_reduce", {
         bn_bwd_reduce_kernel<T><<<grid, threads, (size_t)2 * C * sizeof(float), (cudaStream_t)stream>>>(
-            (const T*)dz, (const T*)z, (const T*)y, mean, rstd, sums, M, C, lddz, ldz, ldy, relu, PL);
+            (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, beta, sums, M, C, lddz, ldz, ldy, relu, PL);
         TSS_LAUNCH_CHECK("bn_bwd_reduce");
         return TSS_OK;
     });
 }
 
 extern "C" int tss_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean,
-                                const float* rstd, const float* gamma, const float* sums, void* dy,
-                                void* dres, float* dgamma, float* dbeta, int64_t M, int C, int64_t lddz,
+                                const float* rstd, const float* gamma, const float* beta, const float* sums,
+                                void* dy, void* dres, float* dgamma, float* dbeta, int64_t M, int C, int64_t lddz,
                                 int64_t ldz, int64_t ldy, int64_t lddy, int64_t lddres, int flags, int dtype,
                                 void* stream) {
     if (int e = check_rows("bn_bwd_apply", M, C)) return e;
     const int relu = flags & TSS_EPI_RELU;
-    TSS_REQUIRE(!relu || z != nullptr, "bn_bwd_apply: ReLU mask needs z");
     TSS_DISPATCH_DTYPE(dtype, "bn_bwd_apply", {
         bn_bwd_apply_kernel<T><<<stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
-            (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, sums, (T*)dy, (T*)dres, dgamma, dbeta,
+            (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, beta, sums, (T*)dy, (T*)dres, dgamma, dbeta,
             M, C, lddz, ldz, ldy, lddy, lddres, relu, (float)(1.0 / (double)M));
         TSS_LAUNCH_CHECK("bn_bwd_apply");
         return TSS_OK;

@@ -13,6 +13,9 @@ int tss_dwconv3x3_tma(const void* x, const float* w, void* y, int N, int Hi, int
                       bool flip, const float* scale, const float* shift, int flags, float* stats, int dtype,
                       cudaStream_t st);
 
+int tss_dwconv3x3_wgrad_tma(const void* x, const void* dy, float* dw, int N, int Hi, int Wi, int C, int stride,
+                            int dilation, int dtype, cudaStream_t st);
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -135,17 +138,21 @@ dw_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restric
     }
 }
 
-// ---------------------------------------------------------------- dgrad, stride 2 ----
-// dx[hi][wi] = sum_{ky,kx} dy[(hi+D-ky*D)/S][(wi+D-kx*D)/S] * w[ky][kx] where divisible.
-template <typename T, int S, int D>
+// ---------------------------------------------------------------- dgrad, stride 2, quads ----
+// Stride 2 / dilation 1: the four input pixels (2p+a, 2q+b) of a quad see disjoint tap subsets of
+// the 2x2 output neighbourhood g[p..p+1][q..q+1] (9 FMAs per quad per channel, no divisibility
+// tests, no divergence).  A thread owns 8 channels and a vertical strip of R quads, sliding the
+// two gradient rows down the strip; horizontal neighbours share their loads through L1.
+template <typename T, int R>
 __global__ void __launch_bounds__(kThreads)
-dw_dgrad_strided_kernel(const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx,
+dw_dgrad_s2_quad_kernel(const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx,
                         int N, int Hi, int Wi, int Ho, int Wo, int C) {
     const int CG = C >> 3;
-    const int64_t total = (int64_t)N * Hi * Wi * CG;
+    const int nstrips = (Ho + R - 1) / R;
+    const int64_t total = (int64_t)N * nstrips * Wo * CG;
     const int64_t gstride = (int64_t)gridDim.x * kThreads;
     int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const int c0 = (int)(item % CG) * 8;
+    const int c0 = (int)(item % CG) * 8;          // loop-invariant: gstride % CG == 0
     float wr[9][8];
 #pragma unroll
     for (int k = 0; k < 9; ++k)
@@ -154,31 +161,50 @@ dw_dgrad_strided_kernel(const T* __restrict__ dy, const float* __restrict__ w, T
 
     for (; item < total; item += gstride) {
         int64_t t = item / CG;
-        const int wi = (int)(t % Wi); t /= Wi;
-        const int hi = (int)(t % Hi);
-        const int n = (int)(t / Hi);
+        const int q = (int)(t % Wo); t /= Wo;
+        const int strip = (int)(t % nstrips);
+        const int n = (int)(t / nstrips);
+        const int p0 = strip * R;
         const T* dyn = dy + (int64_t)n * Ho * Wo * C + c0;
-        float acc[8];
-        zero8(acc);
+        T* dxn = dx + (int64_t)n * Hi * Wi * C + c0;
+        const bool q1 = q + 1 < Wo;
+        const bool col1 = 2 * q + 1 < Wi;
+        float g0[2][8], g1[2][8];                  // rows p and p+1, columns q and q+1
+        load8(dyn + ((int64_t)p0 * Wo + q) * C, g0[0]);
+        if (q1) load8(dyn + ((int64_t)p0 * Wo + q + 1) * C, g0[1]); else zero8(g0[1]);
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int th = hi + D - ky * D;
-            if (th < 0 || (th % S) != 0) continue;
-            const int ho = th / S;
-            if (ho >= Ho) continue;
+        for (int r = 0; r < R; ++r) {
+            const int p = p0 + r;
+            if (p >= Ho) break;
+            if (p + 1 < Ho) {
+                load8(dyn + ((int64_t)(p + 1) * Wo + q) * C, g1[0]);
+                if (q1) load8(dyn + ((int64_t)(p + 1) * Wo + q + 1) * C, g1[1]); else zero8(g1[1]);
+            } else { zero8(g1[0]); zero8(g1[1]); }
+            float o[8];
+            T* row0 = dxn + ((int64_t)(2 * p) * Wi + 2 * q) * C;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int tw = wi + D - kx * D;
-                if (tw < 0 || (tw % S) != 0) continue;
-                const int wo = tw / S;
-                if (wo >= Wo) continue;
-                float v[8];
-                load8(dyn + ((int64_t)ho * Wo + wo) * C, v);
+            for (int e = 0; e < 8; ++e) o[e] = g0[0][e] * wr[4][e];
+            store8(row0, o);
+            if (col1) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], wr[ky * 3 + kx][e], acc[e]);
+                for (int e = 0; e < 8; ++e) o[e] = fmaf(g0[1][e], wr[3][e], g0[0][e] * wr[5][e]);
+                store8(row0 + C, o);
             }
+            if (2 * p + 1 < Hi) {
+                T* row1 = row0 + (int64_t)Wi * C;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fmaf(g1[0][e], wr[1][e], g0[0][e] * wr[7][e]);
+                store8(row1, o);
+                if (col1) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        o[e] = fmaf(g1[1][e], wr[0][e], fmaf(g1[0][e], wr[2][e], fmaf(g0[1][e], wr[6][e], g0[0][e] * wr[8][e])));
+                    store8(row1 + C, o);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { g0[0][e] = g1[0][e]; g0[1][e] = g1[1][e]; }
         }
-        store8(dx + (((int64_t)n * Hi + hi) * Wi + wi) * C + c0, acc);
     }
 }
 
@@ -331,9 +357,10 @@ extern "C" int tss_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int
         if (stride == 1 && dilation == 1) return launch_fwd<T, 1, 1, 4, true>(dy, w, dx, N, Hi, Wi, Hi, Wi, C, nullptr, nullptr, 0, nullptr, st);
         if (stride == 1 && dilation == 2) return launch_fwd<T, 1, 2, 4, true>(dy, w, dx, N, Hi, Wi, Hi, Wi, C, nullptr, nullptr, 0, nullptr, st);
         if (stride == 1 && dilation == 4) return launch_fwd<T, 1, 4, 4, true>(dy, w, dx, N, Hi, Wi, Hi, Wi, C, nullptr, nullptr, 0, nullptr, st);
-        const int64_t total = (int64_t)N * Hi * Wi * (C / 8);
+        constexpr int R = 4;
+        const int64_t total = (int64_t)N * ((Ho + R - 1) / R) * Wo * (C / 8);
         const int grid = persistent_grid(ceil_div64(total, kThreads), 6, C / 8);
-        dw_dgrad_strided_kernel<T, 2, 1><<<grid, kThreads, 0, st>>>((const T*)dy, w, (T*)dx, N, Hi, Wi, Ho, Wo, C);
+        dw_dgrad_s2_quad_kernel<T, R><<<grid, kThreads, 0, st>>>((const T*)dy, w, (T*)dx, N, Hi, Wi, Ho, Wo, C);
         TSS_LAUNCH_CHECK("dwconv3x3_dgrad");
         return TSS_OK;
     });
@@ -344,6 +371,10 @@ extern "C" int tss_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int
     if (int e = check_common("dwconv3x3_wgrad", N, Hi, Wi, C, stride, dilation)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int Ho = (Hi - 1) / stride + 1, Wo = (Wi - 1) / stride + 1;
+    {   // persistent TMA-pipelined kernel for every shape it covers
+        const int r = tss_dwconv3x3_wgrad_tma(x, dy, dw, N, Hi, Wi, C, stride, dilation, dtype, st);
+        if (r >= 0) return r;
+    }
     const int CG = C / 8;
     TSS_REQUIRE(CG <= kThreads, "dwconv3x3_wgrad: C=%d too large", C);
     const int PL = kThreads / CG;

@@ -137,6 +137,112 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: dw[c][ky][kx] += sum_{n,ho,wo} x[n][ho*S-D+ky*D][wo*S-D+kx*D][c] * dy[n][ho][wo][c]
+//
+// Persistent CTAs (grid.y = channel block, grid.x strides over the spatial tiles) with a 2-stage
+// TMA pipeline: while the threads consume stage s, one elected thread has already issued the box
+// loads of the next tile -- the x halo tile {CB, IW, IH} and the dy tile {CB, TW, TH}; both are
+// zero-filled outside the maps, which is the padding for x and "no contribution" for dy.
+// thread = (8-channel group, tile column): its 72 partial sums (9 taps x 8 channels) live in
+// registers across ALL tiles of the CTA; they are reduced over the TW columns through shared
+// memory once, and one fp32 atomic per (channel, tap) per CTA goes to global memory.
+template <typename T, int S, int D, int TH>
+__global__ void __launch_bounds__(192, 2)
+dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                    float* __restrict__ dw, int CB, int TW, int tiles_w, int tiles_h, int ntiles, uint32_t stage_bytes) {
+    constexpr int IH = Geo<S, D, TH>::IH;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    const int IW = (TW - 1) * S + 2 * D + 1;
+    const uint32_t x_bytes = (uint32_t)IH * IW * CB * sizeof(T);
+    const uint32_t x_pad = (x_bytes + 127) & ~127u;
+    const uint32_t g_bytes = (uint32_t)TH * TW * CB * sizeof(T);
+    uint64_t* bars = (uint64_t*)(smem + 2 * (size_t)stage_bytes);
+
+    const int cb0 = blockIdx.y * CB;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(bars), 1);
+        mbar_init(smem_u32(bars + 1), 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int stage) {
+        int t = tile;
+        const int tw = t % tiles_w; t /= tiles_w;
+        const int th = t % tiles_h;
+        const int n = t / tiles_h;
+        uint8_t* base = smem + (size_t)stage * stage_bytes;
+        const uint32_t bar = smem_u32(bars + stage);
+        mbar_expect_tx(bar, x_bytes + g_bytes);
+        tma_load_4d(smem_u32(base), &tmX, bar, cb0, tw * TW * S - D, th * TH * S - D, n);
+        tma_load_4d(smem_u32(base + x_pad), &tmG, bar, cb0, tw * TW, th * TH, n);
+    };
+
+    int tile = blockIdx.x;
+    if (threadIdx.x == 0 && tile < ntiles) issue(tile, 0);
+
+    const int CGB = CB >> 3;
+    const int cg = threadIdx.x % CGB, col = threadIdx.x / CGB;     // col < TW by construction
+    float acc[9][8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) zero8(acc[k]);
+
+    for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+        const int stage = it & 1;
+        const int next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < ntiles) issue(next, stage ^ 1);    // that stage was released by the
+                                                                          // __syncthreads of iteration it-1
+        mbar_wait(smem_u32(bars + stage), (uint32_t)(it >> 1) & 1);
+        const T* sx = (const T*)(smem + (size_t)stage * stage_bytes) + ((size_t)col * S) * CB + cg * 8;
+        const T* sg = (const T*)(smem + (size_t)stage * stage_bytes + x_pad) + (size_t)col * CB + cg * 8;
+        float g[TH][8];
+#pragma unroll
+        for (int r = 0; r < TH; ++r) load8_smem(sg + (size_t)r * TW * CB, g[r]);
+#pragma unroll
+        for (int j = 0; j < IH; ++j) {
+            bool used = false;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int tt = j - ky * D;
+                if (tt >= 0 && tt % S == 0 && tt / S < TH) used = true;
+            }
+            if (!used) continue;
+            float v[3][8];
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) load8_smem(sx + ((size_t)j * IW + kx * D) * CB, v[kx]);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int tt = j - ky * D;
+                if (tt >= 0 && tt % S == 0 && tt / S < TH) {
+                    const int r = tt / S;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[ky * 3 + kx][e] = fmaf(v[kx][e], g[r][e], acc[ky * 3 + kx][e]);
+                }
+            }
+        }
+        __syncthreads();                       // everyone is done with this stage: it may be refilled
+    }
+
+    // reduce the TW column partials: part[col][k][CB] in the (now idle) stage buffers
+    float* part = (float*)smem;
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) part[((size_t)col * 9 + k) * CB + cg * 8 + e] = acc[k][e];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * CB; i += blockDim.x) {
+        const int k = i / CB, ch = i - k * CB;
+        float s = 0.f;
+        for (int c = 0; c < TW; ++c) s += part[((size_t)c * 9 + k) * CB + ch];
+        atomicAdd(dw + (size_t)(cb0 + ch) * 9 + k, s);
+    }
+}
+
 template <typename T> struct TmaType;
 template <> struct TmaType<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
 template <> struct TmaType<bf16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
@@ -173,6 +279,62 @@ int launch(const void* x, const float* w, void* y, int N, int Hi, int Wi, int Ho
     return TSS_OK;
 }
 
+
+template <typename T>
+int make_map4(CUtensorMap* map, const void* base, int C, int W, int H, int N, int bc, int bw, int bh) {
+    TssEncodeTiledFn enc = tss_encode_tiled();
+    TSS_REQUIRE(enc != nullptr, "dwconv_tma: cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * sizeof(T), (cuuint64_t)W * C * sizeof(T), (cuuint64_t)H * W * C * sizeof(T)};
+    cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, TmaType<T>::v, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TSS_REQUIRE(r == CUDA_SUCCESS, "dwconv_tma: cuTensorMapEncodeTiled failed (%d) C=%d W=%d H=%d N=%d box=%dx%dx%d",
+                (int)r, C, W, H, N, bc, bw, bh);
+    return TSS_OK;
+}
+
+template <typename T, int S, int D, int TH>
+int launch_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi, int Ho, int Wo, int C, int CB, int TW,
+                 cudaStream_t st) {
+    constexpr int IH = Geo<S, D, TH>::IH;
+    int IW = (TW - 1) * S + 2 * D + 1;
+    auto stage_size = [&](int tw) {
+        const int iw = (tw - 1) * S + 2 * D + 1;
+        const size_t xb = ((size_t)IH * iw * CB * sizeof(T) + 127) & ~(size_t)127;
+        const size_t gb = ((size_t)TH * tw * CB * sizeof(T) + 127) & ~(size_t)127;
+        return xb + gb;
+    };
+    while (2 * stage_size(TW) > 200 * 1024 && TW > 8) TW >>= 1;
+    if (2 * stage_size(TW) > 200 * 1024 || IW > 256) return -1;
+    IW = (TW - 1) * S + 2 * D + 1;
+    size_t stage = stage_size(TW);
+    const size_t part = (size_t)TW * 9 * CB * sizeof(float);
+    if (2 * stage < part) stage = (part / 2 + 127) & ~(size_t)127;
+    CUtensorMap mx, mg;
+    if (int e = make_map4<T>(&mx, x, C, Wi, Hi, N, CB, IW, IH)) return e;
+    if (int e = make_map4<T>(&mg, dy, C, Wo, Ho, N, CB, TW, TH)) return e;
+    const int tiles_w = (Wo + TW - 1) / TW, tiles_h = (Ho + TH - 1) / TH;
+    const int ntiles = N * tiles_h * tiles_w;
+    const int cblocks = C / CB;
+    int gx = (2 * tss_num_sms() + cblocks - 1) / cblocks;
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    const int threads = (CB / 8) * TW;
+    const size_t smem = 128 + 2 * stage + 16;
+    auto kern = dw_wgrad_tma_kernel<T, S, D, TH>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    kern<<<dim3((unsigned)gx, (unsigned)cblocks), threads, smem, st>>>(mx, mg, dw, CB, TW, tiles_w, tiles_h, ntiles,
+                                                                      (uint32_t)stage);
+    TSS_LAUNCH_CHECK("dwconv3x3_wgrad(tma)");
+    return TSS_OK;
+}
+
 }  // namespace
 
 // Channel block / tile width for the TMA path, or false if C has no suitable block.
@@ -204,6 +366,22 @@ int tss_dwconv3x3_tma(const void* x, const float* w, void* y, int N, int Hi, int
             if (flip) return launch<T, 1, 4, 8, true>(x, w, y, N, Hi, Wi, Ho, Wo, C, CB, TW, scale, shift, flags, stats, st);
             return launch<T, 1, 4, 8, false>(x, w, y, N, Hi, Wi, Ho, Wo, C, CB, TW, scale, shift, flags, stats, st);
         }
+        return -1;
+    });
+}
+
+// Returns -1 if this shape is not covered by the TMA wgrad kernel.
+int tss_dwconv3x3_wgrad_tma(const void* x, const void* dy, float* dw, int N, int Hi, int Wi, int C, int stride,
+                            int dilation, int dtype, cudaStream_t st) {
+    int CB, TW;
+    if (!tss_dw_tma_config(C, &CB, &TW)) return -1;
+    if (((uintptr_t)x & 15) != 0 || ((uintptr_t)dy & 15) != 0) return -1;
+    const int Ho = (Hi - 1) / stride + 1, Wo = (Wi - 1) / stride + 1;
+    TSS_DISPATCH_DTYPE(dtype, "dwconv3x3_wgrad(tma)", {
+        if (sizeof(T) == 4 && TW == 32) TW = 16;
+        if (stride == 1 && dilation == 1) return launch_wgrad<T, 1, 1, 8>(x, dy, dw, N, Hi, Wi, Ho, Wo, C, CB, TW, st);
+        if (stride == 2 && dilation == 1) return launch_wgrad<T, 2, 1, 4>(x, dy, dw, N, Hi, Wi, Ho, Wo, C, CB, TW, st);
+        if (stride == 1 && dilation == 4) return launch_wgrad<T, 1, 4, 8>(x, dy, dw, N, Hi, Wi, Ho, Wo, C, CB, TW, st);
         return -1;
     });
 }

@@ -98,11 +98,14 @@ class ConvBNAct(torch.autograd.Function):
         C = weight.shape[0]
         if bn.momentum is None:
             raise RuntimeError('BatchNorm2d(momentum=None) (cumulative average) is not supported')
-        stats = ops.zeros_f32(2 * C, weight.device)
-        y = conv_forward(spec, x, weight, stats=stats, packed=packed)
+        # per-layer scratch [statistics 2C | backward sums 2C]: finalize re-zeroes all of it
+        scratch = ops.layer_scratch(bn, weight.device)
+        y = conv_forward(spec, x, weight, stats=scratch, packed=packed)
         N, _, H, W = y.shape
-        scale, shift, mean, rstd = ops.bn_finalize(stats, N * H * W, bn, float(bn.momentum), float(bn.eps),
-                                                   update_running=bn.track_running_stats)
+        scale, shift, mean, rstd = ops.bn_finalize(scratch, N * H * W, bn, float(bn.momentum), float(bn.eps),
+                                                   update_running=bn.track_running_stats, clear_n=4 * C, C=C)
+        bn._tss_dirty = False
+        ctx.scratch = scratch
         z = ops.bn_apply(y, scale, shift, res=res, relu=spec.relu)
         ctx.spec, ctx.packed = spec, packed
         ctx.params = (weight, gamma, beta)
@@ -110,13 +113,14 @@ class ConvBNAct(torch.autograd.Function):
                      getattr(beta, '_tss_grad', None))
         ctx.has_res = res is not None
         ctx.in_hw = (x.shape[2], x.shape[3])
-        ctx.save_for_backward(x, weight, gamma, y, z if spec.relu else None, mean, rstd)
+        # the ReLU mask is recomputed from y in backward unless a residual was added before the ReLU
+        ctx.save_for_backward(x, weight, gamma, beta, y, z if (spec.relu and res is not None) else None, mean, rstd)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         spec = ctx.spec
-        x, weight, gamma, y, z, mean, rstd = ctx.saved_tensors
+        x, weight, gamma, beta, y, z, mean, rstd = ctx.saved_tensors
         dz = ops.as_nhwc(dz)
         C = weight.shape[0]
         gw, gg, gb = ctx.arena       # FlatAdamW gradient-arena views: accumulate in place
@@ -126,8 +130,12 @@ class ConvBNAct(torch.autograd.Function):
         else:
             gg_out, gb_out = gg, gb
         want_dres = ctx.has_res and ctx.needs_input_grad[1]
+        sums = ctx.scratch[2 * C:]
+        if spec.bn._tss_dirty or ctx.scratch is not getattr(spec.bn, '_tss_scratch', None):
+            sums = None      # a second backward without a forward in between: fresh zeros
+        spec.bn._tss_dirty = True
         dy, dres = ops.bn_backward(dz, z, y, mean, rstd, gamma, spec.relu, want_dres=want_dres,
-                                   dgamma=gg_out, dbeta=gb_out)
+                                   dgamma=gg_out, dbeta=gb_out, beta=beta, sums=sums)
         dx = None
         dw = gw if gw is not None else torch.zeros_like(weight)
         if spec.kind == 'pw':

@@ -199,16 +199,29 @@ def permute_weights3x3_bwd(dwk, dw):
 
 
 # ------------------------------------------------------------------ batch norm ---------
-def bn_finalize(stats, count, bn, momentum, eps, update_running=True):
+def layer_scratch(bn, device):
+    """Per-layer fp32 scratch [conv-epilogue statistics 2C | BatchNorm-backward sums 2C], allocated
+    once and kept zero by ``tss_bn_finalize``'s consume-and-clear (no memset launch per layer and
+    step).  ``bn._tss_dirty`` tracks whether the backward half was used since it was last cleared."""
+    s = getattr(bn, '_tss_scratch', None)
+    if s is None or s.device != device or s.numel() != 4 * bn.num_features:
+        s = torch.zeros(4 * bn.num_features, dtype=torch.float32, device=device)
+        bn._tss_scratch = s
+        bn._tss_dirty = False
+    return s
+
+
+def bn_finalize(stats, count, bn, momentum, eps, update_running=True, clear_n=0, C=None):
     """-> scale, shift, mean, rstd (fp32 (C,)); updates bn's running stats in place."""
-    C = stats.numel() // 2
+    C = stats.numel() // 2 if C is None else C
     out = torch.empty((4, C), dtype=torch.float32, device=stats.device)
     track = update_running and bn.running_mean is not None
     _lib.call('tss_bn_finalize', stats=stats, count=count, gamma=bn.weight, beta=bn.bias,
               running_mean=bn.running_mean if track else None,
               running_var=bn.running_var if track else None,
               num_batches_tracked=bn.num_batches_tracked if track else None,
-              momentum=momentum, eps=eps, scale=out[0], shift=out[1], mean=out[2], rstd=out[3], C=C)
+              momentum=momentum, eps=eps, scale=out[0], shift=out[1], mean=out[2], rstd=out[3], C=C,
+              clear_n=clear_n)
     if track:
         WEIGHTS_EPOCH[0] += 1
     return out[0], out[1], out[2], out[3]
@@ -234,20 +247,24 @@ def bn_apply(y, scale, shift, y2=None, scale2=None, shift2=None, res=None, relu=
     return out
 
 
-def bn_backward(dz, z, y, mean, rstd, gamma, relu, want_dres=False, dgamma=None, dbeta=None):
-    """-> dy, dres (or None).  dgamma/dbeta (fp32 (C,)) are accumulated into."""
+def bn_backward(dz, z, y, mean, rstd, gamma, relu, want_dres=False, dgamma=None, dbeta=None, beta=None,
+                sums=None):
+    """-> dy, dres (or None).  dgamma/dbeta (fp32 (C,)) are accumulated into.  ``z=None`` with
+    ``relu``: the ReLU mask is recomputed from ``y`` (needs ``beta``; no residual before the ReLU)."""
     N, C, H, W, lddz = _g(dz, 'bn_backward')
     M = N * H * W
-    sums = zeros_f32(2 * C, dz.device)
+    if sums is None:
+        sums = zeros_f32(2 * C, dz.device)
     fl = _flags(relu)
     code = dtype_code(dz.dtype)
     ldz = _g(z, 'bn_backward')[4] if z is not None else 0
     ldy = _g(y, 'bn_backward')[4]
-    _lib.call('tss_bn_bwd_reduce', dz=dz, z=z if relu else None, y=y, mean=mean, rstd=rstd, sums=sums,
+    _lib.call('tss_bn_bwd_reduce', dz=dz, z=z if relu else None, y=y, mean=mean, rstd=rstd, gamma=gamma,
+              beta=beta, sums=sums,
               M=M, C=C, lddz=lddz, ldz=ldz, ldy=ldy, flags=fl, dtype=code)
     dy = empty_nhwc(N, C, H, W, dz.dtype, dz.device)
     dres = empty_nhwc(N, C, H, W, dz.dtype, dz.device) if want_dres else None
-    _lib.call('tss_bn_bwd_apply', dz=dz, z=z if relu else None, y=y, mean=mean, rstd=rstd, gamma=gamma,
+    _lib.call('tss_bn_bwd_apply', dz=dz, z=z if relu else None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta,
               sums=sums, dy=dy, dres=dres, dgamma=dgamma, dbeta=dbeta, M=M, C=C, lddz=lddz, ldz=ldz,
               ldy=ldy, lddy=C, lddres=C, flags=fl, dtype=code)
     return dy, dres
