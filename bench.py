@@ -182,11 +182,12 @@ def kernel_table(device):
     px = lambda div: N * (CROP // div) ** 2
     # final x8 up-sampling of the class scores + fused CE + its backward (the 269 MB logits tensor)
     small = ops.empty_nhwc(N, CLASSES, CROP // 8, CROP // 8, bf, device, pitch=32).normal_()
-    logits = torch.empty(N, CLASSES, CROP, CROP, dtype=bf, device=device).normal_()
     target = torch.randint(0, CLASSES, (N, CROP, CROP), device=device)
     add('upsample_logits_fwd', 1, 2 * CLASSES * (px(8) + px(1)), lambda: ops.upsample_logits_fwd(small, CROP, CROP))
-    add('ce_fwd(+grad)', 1, px(1) * (2 * CLASSES * 2 + 8), lambda: ops.ce_forward(logits, target, 255, True))
-    add('upsample_logits_bwd', 1, 2 * CLASSES * px(1) + 4 * 32 * px(8), lambda: ops.upsample_logits_bwd(logits, CROP // 8, CROP // 8, 32))
+    # fused head (x8 interpolation + CE + gradient w.r.t. the 1/8 scores): reads the int64 labels and the
+    # small scores, writes the small fp32 gradient accumulator + its bf16 copy
+    add('upsample_ce (fused head, 3 launches)', 1, 8 * px(1) + (2 * 32 + 4 * 24 * 2 + 2 * 24) * px(8),
+        lambda: ops.upsample_ce_forward(small, target, CROP, CROP, 255, True))
     # stem
     x = torch.randn(N, 3, CROP, CROP, device=device)
     w = torch.randn(32, 3, 3, 3, device=device)

@@ -208,6 +208,21 @@ int tss_ce_finalize(const double* loss_sum, const int64_t* nvalid, float* loss, 
 /* x *= s[0] (device scalar), n elements: non-unit upstream gradient of the loss */
 int tss_scale_inplace(void* x, const float* s, int64_t n, int dtype, void* stream);
 
+/* Fused head: the final x8 up-sampling (fastscnn.py:63-64) + the cross-entropy above + the gradient
+ * w.r.t. the LOW-resolution class scores, without reading the full-resolution logits and without
+ * ever forming their gradient.  x: NHWC scores [N][Hi][Wi][ldx] (C classes), target int64
+ * [N][Ho][Wo].  Accumulates (+=) loss_sum[0] (fp64), nvalid[0] (non-ignored pixels) and, if
+ * dx32 != NULL, the UNSCALED gradient sum_{pixels} U^T (softmax - onehot) into the fp32 buffer
+ * dx32 [N][Hi][Wi][lddx]; all three must be zeroed by the caller.  pixel_loss (fp32 [N][Ho][Wo],
+ * may be NULL) receives the reduction='none' values (losses/ohem_loss.py:11-12).
+ * finalize: loss[0] = loss_sum/nvalid (NaN if no valid pixel, like the reference) and
+ * dx[i] = dx32[i] / nvalid in the activation dtype (n = N*Hi*Wi*lddx elements, n % 8 == 0). */
+int tss_upsample_ce_fwd(const void* x, const int64_t* target, int N, int C, int Hi, int Wi, int Ho, int Wo,
+                        int64_t ldx, int64_t ignore_index, double* loss_sum, int64_t* nvalid,
+                        float* pixel_loss, float* dx32, int64_t lddx, int dtype, void* stream);
+int tss_upsample_ce_finalize(const double* loss_sum, const int64_t* nvalid, float* loss, const float* dx32,
+                             void* dx, int64_t n, int dtype, void* stream);
+
 /* ---- confusion matrix --------------------------------------------------------------------------
  * replaces ignite ConfusionMatrix.update x4 (engine.py:65-72): cm[t][p] += 1 for 0<=t<C.
  * cm is int64 [C][C].  Warp-aggregated shared-memory atomics, one global atomic per bin per CTA. */

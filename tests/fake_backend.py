@@ -278,6 +278,33 @@ class FakeBackend:
             dlogits.copy_(p * valid.unsqueeze(1) / nv if nv > 0 else torch.zeros_like(p))
         return 0
 
+    def tss_upsample_ce_fwd(self, x, target, N, C, Hi, Wi, Ho, Wo, ldx, ignore_index, loss_sum, nvalid, pixel_loss,
+                            dx32, lddx, dtype):
+        xs = x.detach().float().clone().requires_grad_(True)
+        with torch.enable_grad():
+            logits = F.interpolate(xs, size=(Ho, Wo), mode='bilinear', align_corners=True)
+            valid = (target != ignore_index) & (target >= 0) & (target < C)
+            t = torch.where(valid, target, torch.zeros_like(target))
+            nll = -logits.log_softmax(1).gather(1, t.unsqueeze(1)).squeeze(1) * valid
+            total = nll.double().sum()
+        if loss_sum is not None:
+            loss_sum += total.detach()
+        nvalid += int(valid.sum())
+        if pixel_loss is not None:
+            pixel_loss.copy_(nll.detach())
+        if dx32 is not None:
+            (g,) = torch.autograd.grad(total, xs)
+            dx32[..., :C] += g.permute(0, 2, 3, 1).float()
+        return 0
+
+    def tss_upsample_ce_finalize(self, loss_sum, nvalid, loss, dx32, dx, n, dtype):
+        nv = float(nvalid.item())
+        if loss is not None:
+            loss.fill_(float(loss_sum.item()) / nv if nv > 0 else float('nan'))
+        if dx is not None:
+            dx.copy_(dx32 / nv if nv > 0 else dx32 * float('nan'))
+        return 0
+
     def tss_ce_finalize(self, loss_sum, nvalid, loss):
         nv = float(nvalid.item())
         loss.fill_(float(loss_sum.item()) / nv if nv > 0 else float('nan'))

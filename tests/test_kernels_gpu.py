@@ -374,6 +374,48 @@ def test_cross_entropy(N, H, W, frac, dtype):
 
 
 # ------------------------------------------------------------------ confusion matrix ---
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('N,C,Hi,Wi,frac', [(2, 19, 12, 20, 0.1), (1, 19, 4, 4, 0.0), (2, 19, 3, 5, 0.5), (1, 11, 6, 7, 0.1),
+                                             (1, 19, 1, 1, 0.0), (1, 19, 5, 40, 0.1), (2, 19, 24, 24, 1.0)])
+def test_fused_head_upsample_cross_entropy(N, C, Hi, Wi, frac, dtype):
+    """x8 up-sampling + CE + gradient w.r.t. the low-resolution scores in one kernel, against
+    F.interpolate + log_softmax + autograd on the CPU (through the fake backend's formula) and against
+    the two-kernel path (tss_upsample_logits_fwd + tss_ce_fwd) on the GPU."""
+    g = gen(N * 100 + Hi * 10 + Wi)
+    code = _lib.dtype_code(dtype)
+    Ho, Wo = 8 * Hi, 8 * Wi
+    pitch = 32 if C > 16 else 16
+    xc, xg = pair(N, C, Hi, Wi, dtype, g, pitch=pitch, scale=2.0)
+    t = torch.randint(0, C, (N, Ho, Wo), generator=g)
+    t[torch.rand(N, Ho, Wo, generator=g) < frac] = 255
+    lp = (C + 7) // 8 * 8
+
+    def bufs(device):
+        return dict(loss_sum=torch.zeros(1, dtype=torch.float64, device=device), nvalid=torch.zeros(1, dtype=torch.int64, device=device),
+                    pixel_loss=torch.empty(N, Ho, Wo, device=device), dx32=torch.zeros(N, Hi, Wi, lp, device=device))
+    bc, bg = bufs('cpu'), bufs('cuda')
+    kw = dict(N=N, C=C, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, ldx=pitch, ignore_index=255, lddx=lp, dtype=code)
+    both('tss_upsample_ce_fwd', dict(x=xc, target=t, **bc, **kw), dict(x=xg, target=t.cuda(), **bg, **kw))
+    assert int(bg['nvalid']) == int(bc['nvalid']) == int((t != 255).sum())            # integer: exact
+    assert abs(float(bg['loss_sum']) - float(bc['loss_sum'])) <= 1e-5 * max(1.0, abs(float(bc['loss_sum'])))
+    assert (bg['pixel_loss'].cpu() - bc['pixel_loss']).abs().max() < 1e-4
+    assert rel(bg['dx32'], bc['dx32']) < 1e-4 or float(bc['dx32'].abs().max()) == 0.0
+    assert not bg['dx32'][..., C:].any()
+    lc, lg = torch.empty(()), torch.empty((), device='cuda')
+    dxc, dxg = torch.empty(N, Hi, Wi, lp, dtype=dtype), torch.empty(N, Hi, Wi, lp, dtype=dtype, device='cuda')
+    both('tss_upsample_ce_finalize', dict(loss_sum=bc['loss_sum'], nvalid=bc['nvalid'], loss=lc, dx32=bc['dx32'], dx=dxc, n=dxc.numel(), dtype=code),
+         dict(loss_sum=bg['loss_sum'], nvalid=bg['nvalid'], loss=lg, dx32=bg['dx32'], dx=dxg, n=dxg.numel(), dtype=code))
+    if frac < 1.0:
+        assert abs(float(lg) - float(lc)) < 1e-5 * abs(float(lc))
+        assert rel(dxg, dxc) < TOL[dtype]
+        # same loss as the materialised path (which rounds the logits to the activation dtype first)
+        logits = ops.upsample_logits_fwd(xg, Ho, Wo)
+        loss2 = ops.ce_forward(logits, t.cuda(), 255, want_grad=False)[0]
+        assert abs(float(lg) - float(loss2)) < (1e-5 if dtype == torch.float32 else 5e-3) * abs(float(loss2))
+    else:
+        assert math.isnan(float(lg)) and math.isnan(float(lc))                          # no valid pixel: NaN like the reference
+
+
 @pytest.mark.parametrize('n', [0, 1, 7, 4096, 1024 * 2048 + 3])
 def test_confusion_from_labels_bit_exact(n):
     rng = np.random.RandomState(n % 1000)

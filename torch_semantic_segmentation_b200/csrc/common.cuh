@@ -153,3 +153,16 @@ __device__ __forceinline__ void ac_source(float scale, int dst, int in_size, int
     i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
     lam = fminf(fmaxf(s - (float)i0, 0.f), 1.f);
 }
+
+// first output index whose source index floor can be >= i (conservative), given scale
+__device__ __forceinline__ int first_candidate(float scale, int i, int out_size) {
+    if (scale <= 0.f) return 0;
+    int o = (int)floorf((float)(i - 1) / scale) - 1;
+    return o < 0 ? 0 : (o > out_size - 1 ? out_size - 1 : o);
+}
+__device__ __forceinline__ int last_candidate(float scale, int i, int out_size) {
+    if (scale <= 0.f) return out_size - 1;
+    int o = (int)ceilf((float)(i + 1) / scale) + 1;
+    return o > out_size - 1 ? out_size - 1 : o;
+}
+

@@ -145,6 +145,193 @@ int launch_ce(const void* logits, const int64_t* target, int N, int64_t HW, int6
     return TSS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused head: x8 bilinear up-sampling (align_corners=True) + softmax cross-entropy + the
+// gradient w.r.t. the LOW-resolution class scores, in one pass that reads only the labels.
+// The full-resolution logits are recomputed on the fly from the 1/8-resolution NHWC scores and the
+// full-resolution gradient never exists: (softmax - onehot) is folded straight through the
+// transpose of the interpolation.
+//   CTA = (image n, source row interval hi, chunk of kCols output columns); thread = output column.
+//   The thread interpolates horizontally once (a[c], b[c] for source rows hi / hi+1), then walks the
+//   8-9 output rows whose source row is hi: vertical blend -> softmax -> loss -> g; g is blended
+//   back vertically into t0[c] (row hi) / t1[c] (row hi+1) in registers.  The column partials go to
+//   shared memory and (source column, class) threads gather their ~17 output columns: two fp32
+//   atomics per (source pixel, class) per CTA.  Gradients are accumulated UNSCALED; the valid
+//   count is produced by the same pass and applied by tss_upsample_ce_finalize.
+constexpr int kHeadCols = 256;
+
+template <typename T, int C>
+__global__ void __launch_bounds__(kHeadCols)
+upsample_ce_kernel(const T* __restrict__ x, const int64_t* __restrict__ target, float* __restrict__ dx32,
+                   double* __restrict__ loss_sum, unsigned long long* __restrict__ nvalid,
+                   float* __restrict__ pixel_loss, int Hi, int Wi, int Ho, int Wo, int64_t ldx, int64_t lddx,
+                   int64_t ignore_index, float sh, float sw, int chunks) {
+    extern __shared__ float s_mem[];
+    int b = blockIdx.x;
+    const int chunk = b % chunks; b /= chunks;
+    const int hi = b % Hi;
+    const int n = b / Hi;
+    const int wo_lo = chunk * kHeadCols;
+    const int wo_hi = min(wo_lo + kHeadCols, Wo) - 1;             // inclusive
+    // source column range touched by this chunk
+    int wl0, wl1, wh0, wh1; float tmp;
+    ac_source(sw, wo_lo, Wi, wl0, wl1, tmp);
+    ac_source(sw, wo_hi, Wi, wh0, wh1, tmp);
+    const int wi_lo = wl0, ncols = wh1 - wl0 + 1;
+    float* s_src = s_mem;                                         // [2][ncols][C]
+    float* s_t = s_mem + 2 * ncols * C;                           // [kHeadCols][2*C + 1]
+    constexpr int TP = 2 * C + 1;
+    const int h1src = hi + (hi < Hi - 1 ? 1 : 0);
+    for (int i = threadIdx.x; i < 2 * ncols * C; i += kHeadCols) {
+        const int r = i / (ncols * C), rem = i - r * ncols * C;
+        const int w = rem / C, c = rem - w * C;
+        s_src[i] = to_f32(x[(((int64_t)n * Hi + (r ? h1src : hi)) * Wi + wi_lo + w) * ldx + c]);
+    }
+    __syncthreads();
+
+    const int wo = wo_lo + threadIdx.x;
+    const bool col_ok = wo <= wo_hi;
+    float t0[C], t1[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { t0[c] = 0.f; t1[c] = 0.f; }
+    float lsum = 0.f;
+    unsigned int cnt = 0;
+    if (col_ok) {
+        int w0, w1; float lw;
+        ac_source(sw, wo, Wi, w0, w1, lw);
+        float a[C], bb[C];
+        const float* p00 = s_src + (w0 - wi_lo) * C;
+        const float* p01 = s_src + (w1 - wi_lo) * C;
+        const float* p10 = p00 + ncols * C;
+        const float* p11 = p01 + ncols * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            a[c] = (1.f - lw) * p00[c] + lw * p01[c];
+            bb[c] = (1.f - lw) * p10[c] + lw * p11[c];
+        }
+        const int ho_a = first_candidate(sh, hi, Ho), ho_b = last_candidate(sh, hi, Ho);
+        for (int ho = ho_a; ho <= ho_b; ++ho) {
+            int h0, h1; float lh;
+            ac_source(sh, ho, Hi, h0, h1, lh);
+            if (h0 != hi) continue;
+            const int64_t pix = ((int64_t)n * Ho + ho) * Wo + wo;
+            const int64_t tg = __ldg(target + pix);
+            const bool valid = tg != ignore_index && tg >= 0 && tg < C;
+            float v[C];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                v[c] = (1.f - lh) * a[c] + lh * bb[c];
+                mx = fmaxf(mx, v[c]);
+            }
+            float se = 0.f, xt = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                if ((int64_t)c == tg) xt = v[c];
+                v[c] = __expf(v[c] - mx);
+                se += v[c];
+            }
+            const float pl = valid ? (__logf(se) + mx - xt) : 0.f;
+            if (pixel_loss != nullptr) pixel_loss[pix] = pl;
+            if (valid) {
+                lsum += pl;
+                ++cnt;
+                const float inv = 1.f / se;
+                const float k0 = (h1 == hi) ? 1.f : 1.f - lh;        // clamped last row: both weights land on hi
+                const float k1 = (h1 == hi) ? 0.f : lh;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float g = v[c] * inv - ((int64_t)c == tg ? 1.f : 0.f);
+                    t0[c] = fmaf(g, k0, t0[c]);
+                    t1[c] = fmaf(g, k1, t1[c]);
+                }
+            }
+        }
+    }
+    if (dx32 != nullptr) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            s_t[threadIdx.x * TP + c] = t0[c];
+            s_t[threadIdx.x * TP + C + c] = t1[c];
+        }
+        __syncthreads();
+        const bool has_next = hi < Hi - 1;
+        for (int i = threadIdx.x; i < ncols * C; i += kHeadCols) {
+            const int w = i / C, c = i - w * C;
+            const int wi = wi_lo + w;
+            int ca = first_candidate(sw, wi, Wo), cb = last_candidate(sw, wi, Wo);
+            ca = max(ca, wo_lo); cb = min(cb, wo_hi);
+            float a0 = 0.f, a1 = 0.f;
+            for (int o = ca; o <= cb; ++o) {
+                int w0, w1; float lw;
+                ac_source(sw, o, Wi, w0, w1, lw);
+                float ww = 0.f;
+                if (w0 == wi) ww += 1.f - lw;
+                if (w1 == wi) ww += lw;
+                if (ww == 0.f) continue;
+                a0 = fmaf(s_t[(o - wo_lo) * TP + c], ww, a0);
+                a1 = fmaf(s_t[(o - wo_lo) * TP + C + c], ww, a1);
+            }
+            if (a0 != 0.f) atomicAdd(dx32 + (((int64_t)n * Hi + hi) * Wi + wi) * lddx + c, a0);
+            if (has_next && a1 != 0.f) atomicAdd(dx32 + (((int64_t)n * Hi + hi + 1) * Wi + wi) * lddx + c, a1);
+        }
+    }
+    lsum = warp_sum(lsum);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    __shared__ float s_part[kHeadCols / 32];
+    __shared__ unsigned int s_cnt[kHeadCols / 32];
+    if ((threadIdx.x & 31) == 0) { s_part[threadIdx.x >> 5] = lsum; s_cnt[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        unsigned int k = 0;
+#pragma unroll
+        for (int w = 0; w < kHeadCols / 32; ++w) { s += (double)s_part[w]; k += s_cnt[w]; }
+        if (loss_sum != nullptr) atomicAdd(loss_sum, s);
+        if (k) atomicAdd(nvalid, (unsigned long long)k);
+    }
+}
+
+// loss = loss_sum / nvalid; dx (activation dtype) = dx32 / nvalid * upstream  (n % 8 == 0 elements)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+upsample_ce_finalize_kernel(const double* __restrict__ loss_sum, const int64_t* __restrict__ nvalid,
+                            float* __restrict__ loss, const float* __restrict__ dx32, T* __restrict__ dx, int64_t n8) {
+    const double nv = (double)(*nvalid);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && loss != nullptr) *loss = (float)(*loss_sum / nv);
+    if (dx == nullptr) return;
+    const float k = (float)(1.0 / nv);
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n8; i += (int64_t)gridDim.x * kThreads) {
+        float v[8];
+        load8(dx32 + i * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= k;
+        store8(dx + i * 8, v);
+    }
+}
+
+template <typename T, int C>
+int launch_head(const void* x, const int64_t* target, float* dx32, double* loss_sum, int64_t* nvalid, float* pixel_loss,
+                int N, int Hi, int Wi, int Ho, int Wo, int64_t ldx, int64_t lddx, int64_t ignore_index, cudaStream_t st) {
+    const int chunks = (Wo + kHeadCols - 1) / kHeadCols;
+    const float sw = ac_scale(Wi, Wo);
+    int ncols_max = (int)((float)kHeadCols * sw) + 4;
+    if (ncols_max > Wi) ncols_max = Wi;
+    const size_t smem = ((size_t)2 * ncols_max * C + (size_t)kHeadCols * (2 * C + 1)) * sizeof(float);
+    TSS_REQUIRE(smem <= 200 * 1024, "upsample_ce: tile does not fit in shared memory (Wi=%d Wo=%d)", Wi, Wo);
+    auto kern = upsample_ce_kernel<T, C>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    kern<<<N * Hi * chunks, kHeadCols, smem, st>>>((const T*)x, target, dx32, loss_sum, (unsigned long long*)nvalid,
+                                                   pixel_loss, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index,
+                                                   ac_scale(Hi, Ho), sw, chunks);
+    TSS_LAUNCH_CHECK("upsample_ce_fwd");
+    return TSS_OK;
+}
+
 }  // namespace
 
 extern "C" int tss_ce_count_valid(const int64_t* target, int64_t n, int64_t ignore_index, int64_t* nvalid,
@@ -188,4 +375,37 @@ extern "C" int tss_ce_finalize(const double* loss_sum, const int64_t* nvalid, fl
     ce_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(loss_sum, nvalid, loss);
     TSS_LAUNCH_CHECK("ce_finalize");
     return TSS_OK;
+}
+
+extern "C" int tss_upsample_ce_fwd(const void* x, const int64_t* target, int N, int C, int Hi, int Wi, int Ho, int Wo,
+                                   int64_t ldx, int64_t ignore_index, double* loss_sum, int64_t* nvalid,
+                                   float* pixel_loss, float* dx32, int64_t lddx, int dtype, void* stream) {
+    TSS_REQUIRE(N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "upsample_ce_fwd: empty input");
+    TSS_REQUIRE(ldx >= C && (dx32 == nullptr || lddx >= C), "upsample_ce_fwd: pitch smaller than C=%d", C);
+    TSS_REQUIRE(nvalid != nullptr, "upsample_ce_fwd: nvalid is required");
+    cudaStream_t st = (cudaStream_t)stream;
+    TSS_DISPATCH_DTYPE(dtype, "upsample_ce_fwd", {
+        switch (C) {
+            case 19: return launch_head<T, 19>(x, target, dx32, loss_sum, nvalid, pixel_loss, N, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index, st);
+            case 11: return launch_head<T, 11>(x, target, dx32, loss_sum, nvalid, pixel_loss, N, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index, st);
+            case 12: return launch_head<T, 12>(x, target, dx32, loss_sum, nvalid, pixel_loss, N, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index, st);
+            case 21: return launch_head<T, 21>(x, target, dx32, loss_sum, nvalid, pixel_loss, N, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index, st);
+            default:
+                tss_set_error("upsample_ce_fwd: C=%d not instantiated (19 Cityscapes/BDD, 11/12 CamVid, 21 VOC)", C);
+                return TSS_ERR_ARG;
+        }
+    });
+}
+
+extern "C" int tss_upsample_ce_finalize(const double* loss_sum, const int64_t* nvalid, float* loss, const float* dx32,
+                                        void* dx, int64_t n, int dtype, void* stream) {
+    TSS_REQUIRE(dx == nullptr || (dx32 != nullptr && n > 0 && n % 8 == 0), "upsample_ce_finalize: n=%lld must be a positive multiple of 8", (long long)n);
+    TSS_DISPATCH_DTYPE(dtype, "upsample_ce_finalize", {
+        int64_t want = dx != nullptr ? ceil_div64(n / 8, kThreads) : 1;
+        const int64_t cap = (int64_t)tss_num_sms() * 8;
+        const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+        upsample_ce_finalize_kernel<T><<<grid, kThreads, 0, (cudaStream_t)stream>>>(loss_sum, nvalid, loss, dx32, (T*)dx, n / 8);
+        TSS_LAUNCH_CHECK("upsample_ce_finalize");
+        return TSS_OK;
+    });
 }

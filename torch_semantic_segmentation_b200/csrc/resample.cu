@@ -126,18 +126,6 @@ bilinear_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int Hi, i
     }
 }
 
-// first output index whose source index floor can be >= i (conservative), given scale
-__device__ __forceinline__ int first_candidate(float scale, int i, int out_size) {
-    if (scale <= 0.f) return 0;
-    int o = (int)floorf((float)(i - 1) / scale) - 1;
-    return o < 0 ? 0 : (o > out_size - 1 ? out_size - 1 : o);
-}
-__device__ __forceinline__ int last_candidate(float scale, int i, int out_size) {
-    if (scale <= 0.f) return out_size - 1;
-    int o = (int)ceilf((float)(i + 1) / scale) + 1;
-    return o > out_size - 1 ? out_size - 1 : o;
-}
-
 // gather form of the transpose: each input pixel sums the output pixels that read it
 template <typename T>
 __global__ void __launch_bounds__(kThreads)

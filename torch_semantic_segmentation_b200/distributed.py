@@ -91,6 +91,7 @@ class GradientAllReducer:
         b[4] = True
         chunk = self.opt.grad_arena[lo:hi]
         if self.cuda:
+            Fn.wgrad_lane.join(chunk.device)     # the bucket's wgrads run on the wgrad side stream
             self.side.wait_stream(torch.cuda.current_stream(chunk.device))
             with torch.cuda.stream(self.side):
                 self.handles.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))

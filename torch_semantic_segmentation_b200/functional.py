@@ -63,6 +63,58 @@ def grad_ready(*params):
                 _grad_ready_hook(p)
 
 
+class _WgradLane:
+    """Weight-gradient kernels run on a side stream: in backward nothing on the critical chain
+    (BatchNorm backward -> dgrad -> next layer) depends on a wgrad, so the ~45 wgrad launches of a
+    step overlap with it instead of lengthening it.  Only used when the gradients are accumulated
+    in place into the optimizer's arena (``FlatAdamW``), whose ``step()`` / all-reduce joins the lane.
+    Operand tensors are kept referenced until the join so that the caching allocator cannot hand
+    their memory to a main-stream kernel while a side-stream wgrad still reads it."""
+
+    def __init__(self):
+        self.enabled = True
+        self.streams = {}
+        self.keep = []
+        self.dirty = set()
+        self.queued = False
+
+    def stream(self, device):
+        st = self.streams.get(device)
+        if st is None:
+            st = self.streams[device] = torch.cuda.Stream(device)
+        return st
+
+    def run(self, device, fn, *tensors):
+        if not (self.enabled and device.type == 'cuda'):
+            fn()
+            return
+        side = self.stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            fn()
+        self.keep.append(tensors)
+        self.dirty.add(device)
+        if not self.queued:       # join when this backward pass ends, so that p.grad is complete for
+            self.queued = True    # whatever the caller does next on its stream (clipping, step, ...)
+            torch.autograd.Variable._execution_engine.queue_callback(self._end_of_backward)
+
+    def _end_of_backward(self):
+        self.queued = False
+        self.join()
+
+    def join(self, device=None):
+        """Make the current stream wait for every wgrad launched so far."""
+        for dev in list(self.dirty):
+            if device is None or dev == device:
+                torch.cuda.current_stream(dev).wait_stream(self.streams[dev])
+                self.dirty.discard(dev)
+        if not self.dirty:
+            self.keep.clear()
+
+
+wgrad_lane = _WgradLane()
+
+
 class ConvSpec:
     """Static description of one conv+BN block (built once per module)."""
 
@@ -138,20 +190,22 @@ class ConvBNAct(torch.autograd.Function):
                                    dgamma=gg_out, dbeta=gb_out, beta=beta, sums=sums)
         dx = None
         dw = gw if gw is not None else torch.zeros_like(weight)
+        # wgrad off the critical chain when it accumulates in place into the optimizer's arena
+        lane = (lambda fn: wgrad_lane.run(dy.device, fn, x, dy)) if gw is not None else (lambda fn: fn())
         if spec.kind == 'pw':
             wpT = ctx.packed[1] if ctx.packed is not None else None
             impl = spec.impl if wpT is not None else 0
+            lane(lambda: ops.pwconv_wgrad(x, dy, dw, impl=impl))
             if ctx.needs_input_grad[0]:
                 dx = ops.pwconv_dgrad(dy, weight, wpT=wpT, impl=impl)
-            ops.pwconv_wgrad(x, dy, dw, impl=impl)
         elif spec.kind == 'dw':
+            lane(lambda: ops.dwconv_wgrad(x, dy, dw, spec.stride, spec.dilation))
             if ctx.needs_input_grad[0]:
                 dx = ops.dwconv_dgrad(dy, weight, ctx.in_hw[0], ctx.in_hw[1], spec.stride, spec.dilation)
-            ops.dwconv_wgrad(x, dy, dw, spec.stride, spec.dilation)
         else:  # stem: the image needs no gradient
             if ctx.needs_input_grad[0]:
                 raise RuntimeError('gradient w.r.t. the input image is not implemented')
-            ops.stem_wgrad(x, dy, dw)
+            lane(lambda: ops.stem_wgrad(x, dy, dw))
         grad_ready(*ctx.params)
         return (dx, dres, None if gw is not None else dw, None if gg is not None else gg_out,
                 None if gb is not None else gb_out, None, None)
@@ -306,6 +360,43 @@ class UpsampleLogits(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         return ops.upsample_logits_bwd(dy, ctx.in_hw[0], ctx.in_hw[1], ctx.pitch), None, None
+
+
+class UpsampleCrossEntropy(torch.autograd.Function):
+    """mean CE of the x8-upsampled class scores, computed from the 1/8-resolution scores: the logits
+    are interpolated on the fly and the gradient is folded through the interpolation's transpose in
+    the same pass (fastscnn.py:63-64 + train_fastscnn.py:132 as ONE kernel)."""
+
+    @staticmethod
+    def forward(ctx, scores, target, ignore_index, Ho, Wo):
+        want = ctx.needs_input_grad[0]
+        loss, dx, _ = ops.upsample_ce_forward(scores, target, Ho, Wo, ignore_index, want_grad=want)
+        ctx.save_for_backward(dx)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dx,) = ctx.saved_tensors
+        if dx is None:
+            return None, None, None, None, None
+        if not _unit_grad():
+            dx = dx * grad_out.to(dx.dtype)       # 1/64 of the logits' size: not worth a kernel
+        return dx, None, None, None, None
+
+
+def attach_head(logits, scores):
+    """Remember on the model's output which low-resolution scores it was interpolated from, so that
+    ``losses.cross_entropy`` can take the fused head instead of re-reading the logits."""
+    logits._tss_head = (scores, logits._version)
+    return logits
+
+
+def fused_head_source(logits):
+    """-> the NHWC scores ``logits`` was up-sampled from, if it is still the untouched model output."""
+    head = getattr(logits, '_tss_head', None)
+    if head is None or head[1] != logits._version:
+        return None
+    return head[0]
 
 
 class CrossEntropy(torch.autograd.Function):

@@ -131,4 +131,6 @@ class ContextNet(nn.Module):
         context = self.context(context)
         fusion = self.feature_fusion(context, spatial)
         classes = self.classifier(fusion)
-        return Fn.UpsampleLogits.apply(ops.as_nhwc(classes), classes.shape[2] * 8, classes.shape[3] * 8)
+        classes = ops.as_nhwc(classes)
+        logits = Fn.UpsampleLogits.apply(classes, classes.shape[2] * 8, classes.shape[3] * 8)
+        return Fn.attach_head(logits, classes)

@@ -60,7 +60,9 @@ class FastSCNN(nn.Module):
         features = self.features(downsample)
         fusion = self.fusion(features, downsample)
         classes = self.classifier(fusion)
-        return Fn.UpsampleLogits.apply(ops.as_nhwc(classes), classes.shape[2] * 8, classes.shape[3] * 8)
+        classes = ops.as_nhwc(classes)
+        logits = Fn.UpsampleLogits.apply(classes, classes.shape[2] * 8, classes.shape[3] * 8)
+        return Fn.attach_head(logits, classes)
 
 
 class FeatureFusionModule(nn.Module):

@@ -416,6 +416,34 @@ def ce_forward(logits, target, ignore_index, want_grad, want_pixel_loss=False):
     return loss, dlogits, pixel, nvalid
 
 
+def upsample_ce_forward(scores, target, Ho, Wo, ignore_index, want_grad, want_pixel_loss=False):
+    """Fused head on the 1/8-resolution NHWC class scores: -> loss (fp32 scalar tensor), gradient
+    w.r.t. ``scores`` (same logical shape, channel pitch padded to 8; or None), per-pixel loss (or None)."""
+    N, C, Hi, Wi, ldx = _g(scores, 'upsample_ce_forward')
+    if target.dtype != torch.int64 or not target.is_contiguous():
+        target = target.long().contiguous()
+    if tuple(target.shape) != (N, Ho, Wo):
+        raise ValueError('upsample_ce_forward: target shape %s does not match (%d, %d, %d)' % (tuple(target.shape), N, Ho, Wo))
+    dev = scores.device
+    pitch = _pad8(C)
+    acc = torch.zeros((N, Hi, Wi, pitch), dtype=torch.float32, device=dev) if want_grad else None
+    # [loss_sum (fp64) | nvalid (int64 bits)] zeroed by one fill
+    red = torch.zeros(2, dtype=torch.float64, device=dev)
+    nvalid = red[1:].view(torch.int64)
+    pixel = torch.empty((N, Ho, Wo), dtype=torch.float32, device=dev) if want_pixel_loss else None
+    code = dtype_code(scores.dtype)
+    _lib.call('tss_upsample_ce_fwd', x=scores, target=target, N=N, C=C, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, ldx=ldx,
+              ignore_index=ignore_index, loss_sum=red[:1], nvalid=nvalid, pixel_loss=pixel, dx32=acc, lddx=pitch,
+              dtype=code)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dx = torch.empty((N, Hi, Wi, pitch), dtype=scores.dtype, device=dev) if want_grad else None
+    _lib.call('tss_upsample_ce_finalize', loss_sum=red[:1], nvalid=nvalid, loss=loss, dx32=acc, dx=dx,
+              n=N * Hi * Wi * pitch if want_grad else 0, dtype=code)
+    if dx is not None:
+        dx = dx[..., :C].permute(0, 3, 1, 2)
+    return loss, dx, pixel
+
+
 def confusion_from_labels(pred, target, num_classes, cm):
     """cm (int64 (C,C), device) += histogram of (target, pred)."""
     pred = pred.long().contiguous().view(-1)

@@ -63,6 +63,8 @@ class FlatAdamW(torch.optim.Optimizer):
 
     def zero_grad(self, set_to_none=False):
         """One memset; the gradient views stay attached (``set_to_none`` is ignored)."""
+        from .functional import wgrad_lane
+        wgrad_lane.join(self.grad_arena.device if self.grad_arena.is_cuda else None)
         self.grad_arena.zero_()
 
     def _refresh_hyper(self):
@@ -77,6 +79,8 @@ class FlatAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        from .functional import wgrad_lane
+        wgrad_lane.join(self.grad_arena.device if self.grad_arena.is_cuda else None)   # side-stream wgrads
         reducer = getattr(self, '_reducer', None)
         if reducer is not None:
             reducer.finish()         # gradient all-reduce buckets launched during backward
