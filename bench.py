@@ -324,9 +324,21 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * BATCH * args.steps / (float(ems) / 1e3)
 
-    if rank != 0:
+    def finish():
+        # every rank meets here (rank 0 after the single-rank roofline / CPU legs), tears the group
+        # down together, and a stuck teardown can never outlive the printed result
+        sys.stdout.flush()
         if world > 1:
+            import signal
+            signal.signal(signal.SIGALRM, lambda *_: os._exit(0))
+            signal.alarm(300)
+            dist.barrier()
+            signal.alarm(30)
             dist.destroy_process_group()
+            signal.alarm(0)
+
+    if rank != 0:
+        finish()
         return
 
     # ---- roofline of the dominant kernel (timed alone, L2 flushed) -------------------------
@@ -365,8 +377,7 @@ def main():
         'roofline': roofline,
         'cpu_baseline': cpu,
     }))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == '__main__':

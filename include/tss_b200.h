@@ -46,6 +46,9 @@ int tss_version(void);
 const char* tss_last_error(void);
 /* number of kernels launched by this library in this process (bench.py's gpu_launches) */
 uint64_t tss_launch_count(void);
+/* Programmatic dependent launch between consecutive kernels of a stream / graph (on by default;
+ * env TSS_PDL=0 or tss_set_pdl(0) selects plain serialized launches).  Process-wide. */
+int tss_set_pdl(int enabled);
 
 /* ---- depthwise 3x3 convolution, padding == dilation ("same" for stride 1) --------------
  * replaces nn.Conv2d(C, C, 3, stride, padding=dilation, dilation, groups=C, bias=False)

@@ -166,8 +166,14 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', init_method='env://', device_id=device)
     {3: config3, 4: config4, 5: config5}[args.config](args, rank, world, device)
+    sys.stdout.flush()
     if world > 1:
+        import signal
+        signal.signal(signal.SIGALRM, lambda *_: os._exit(0))
+        signal.alarm(120)
+        dist.barrier()
         dist.destroy_process_group()
+        signal.alarm(0)
 
 
 if __name__ == '__main__':

@@ -1,12 +1,28 @@
 // Library-wide state: version, thread-local error string, launch counter.
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_pdl{-1};
+
+bool tss_pdl_enabled() {
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("TSS_PDL");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+        g_pdl.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
+extern "C" int tss_set_pdl(int enabled) {
+    g_pdl.store(enabled ? 1 : 0, std::memory_order_relaxed);
+    return TSS_OK;
+}
 
 void tss_set_error(const char* fmt, ...) {
     va_list ap;

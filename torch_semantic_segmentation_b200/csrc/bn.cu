@@ -29,6 +29,7 @@ __global__ void bn_finalize_kernel(float* __restrict__ stats, double inv_count, 
                                    float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out, int C,
                                    int clear_n) {
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && nbt != nullptr) *nbt += 1;
     if (c >= C) return;
@@ -56,6 +57,7 @@ __global__ void bn_finalize_kernel(float* __restrict__ stats, double inv_count, 
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ rm, const float* __restrict__ rv, float eps,
                                float* __restrict__ scale, float* __restrict__ shift, int C) {
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float sc = (gamma != nullptr ? gamma[c] : 1.f) / sqrtf(rv[c] + eps);
@@ -70,6 +72,7 @@ bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const 
                 const T* __restrict__ y2, const float* __restrict__ scale2, const float* __restrict__ shift2,
                 const T* __restrict__ res, T* __restrict__ z, int64_t M, int C,
                 int64_t ldy, int64_t ldy2, int64_t ldr, int64_t ldz, int relu) {
+    pdl_wait();
     const int CG = C >> 3;
     const int64_t total = M * CG;
     for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
@@ -113,6 +116,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T*
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      float* __restrict__ sums, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy,
                      int relu, int PL) {
+    pdl_wait();
     extern __shared__ float s_sum[];   // [2*C]
     const int CG = C >> 3;
     const int cg = threadIdx.x % CG;
@@ -176,6 +180,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* 
                     T* __restrict__ dy, T* __restrict__ dres, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy,
                     int64_t lddy, int64_t lddres, int relu, float inv_m) {
+    pdl_wait();
     const int CG = C >> 3;
     const int64_t total = M * CG;
     if (blockIdx.x == 0) {
@@ -230,6 +235,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 relu_bwd_kernel(const T* __restrict__ dz, const T* __restrict__ z, T* __restrict__ g, int64_t M, int C,
                 int64_t lddz, int64_t ldz, int64_t ldg) {
+    pdl_wait();
     const int CG = C >> 3;
     const int64_t total = M * CG;
     for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
@@ -250,6 +256,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t M, int C,
            int64_t lda, int64_t ldb, int64_t ldo) {
+    pdl_wait();
     const int CG = C >> 3;
     const int64_t total = M * CG;
     for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
@@ -271,6 +278,7 @@ add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 cast_from_f32_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n8) {
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n8; i += (int64_t)gridDim.x * kThreads) {
         float v[8];
         load8(src + i * 8, v);
@@ -281,6 +289,7 @@ cast_from_f32_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 scale_inplace_kernel(T* __restrict__ x, const float* __restrict__ s, int64_t n8) {
+    pdl_wait();
     const float k = __ldg(s);
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n8; i += (int64_t)gridDim.x * kThreads) {
         float v[8];
@@ -310,7 +319,7 @@ extern "C" int tss_bn_finalize(float* stats, int64_t count, const float* gamma, 
                 (long long)count);
     TSS_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats mismatch");
     const double unbias = (double)count / (double)(count - 1);
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    tss_launch(bn_finalize_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, 
         stats, 1.0 / (double)count, unbias, gamma, beta, running_mean, running_var, num_batches_tracked,
         momentum, eps, scale, shift, mean, rstd, C, (int)clear_n);
     TSS_LAUNCH_CHECK("bn_finalize");
@@ -321,7 +330,7 @@ extern "C" int tss_bn_fold(const float* gamma, const float* beta, const float* r
                            const float* running_var, float eps, float* scale, float* shift, int C,
                            void* stream) {
     TSS_REQUIRE(C > 0, "bn_fold: C=%d", C);
-    bn_fold_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var,
+    tss_launch(bn_fold_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, gamma, beta, running_mean, running_var,
                                                                      eps, scale, shift, C);
     TSS_LAUNCH_CHECK("bn_fold");
     return TSS_OK;
@@ -334,7 +343,7 @@ extern "C" int tss_bn_apply(const void* y, const float* scale, const float* shif
     if (int e = check_rows("bn_apply", M, C)) return e;
     TSS_REQUIRE(y2 == nullptr || (scale2 != nullptr && shift2 != nullptr), "bn_apply: y2 without scale2/shift2");
     TSS_DISPATCH_DTYPE(dtype, "bn_apply", {
-        bn_apply_kernel<T><<<stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+        tss_launch(bn_apply_kernel<T>, stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream, 
             (const T*)y, scale, shift, (const T*)y2, scale2, shift2, (const T*)res, (T*)z, M, C, ldy, ldy2,
             ldr, ldz, flags & TSS_EPI_RELU);
         TSS_LAUNCH_CHECK("bn_apply");
@@ -356,7 +365,7 @@ extern "C" int tss_bn_bwd_reduce(const void* dz, const void* z, const void* y, c
     int64_t cap = (int64_t)tss_num_sms() * 4;
     const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
     TSS_DISPATCH_DTYPE(dtype, "bn_bwd_reduce", {
-        bn_bwd_reduce_kernel<T><<<grid, threads, (size_t)2 * C * sizeof(float), (cudaStream_t)stream>>>(
+        tss_launch(bn_bwd_reduce_kernel<T>, grid, threads, (size_t)2 * C * sizeof(float), (cudaStream_t)stream, 
             (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, beta, sums, M, C, lddz, ldz, ldy, relu, PL);
         TSS_LAUNCH_CHECK("bn_bwd_reduce");
         return TSS_OK;
@@ -371,7 +380,7 @@ extern "C" int tss_bn_bwd_apply(const void* dz, const void* z, const void* y, co
     if (int e = check_rows("bn_bwd_apply", M, C)) return e;
     const int relu = flags & TSS_EPI_RELU;
     TSS_DISPATCH_DTYPE(dtype, "bn_bwd_apply", {
-        bn_bwd_apply_kernel<T><<<stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+        tss_launch(bn_bwd_apply_kernel<T>, stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream, 
             (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, beta, sums, (T*)dy, (T*)dres, dgamma, dbeta,
             M, C, lddz, ldz, ldy, lddy, lddres, relu, (float)(1.0 / (double)M));
         TSS_LAUNCH_CHECK("bn_bwd_apply");
@@ -383,7 +392,7 @@ extern "C" int tss_relu_bwd(const void* dz, const void* z, void* g, int64_t M, i
                             int64_t ldz, int64_t ldg, int dtype, void* stream) {
     if (int e = check_rows("relu_bwd", M, C)) return e;
     TSS_DISPATCH_DTYPE(dtype, "relu_bwd", {
-        relu_bwd_kernel<T><<<stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+        tss_launch(relu_bwd_kernel<T>, stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream, 
             (const T*)dz, (const T*)z, (T*)g, M, C, lddz, ldz, ldg);
         TSS_LAUNCH_CHECK("relu_bwd");
         return TSS_OK;
@@ -394,7 +403,7 @@ extern "C" int tss_add(const void* a, const void* b, void* out, int64_t M, int C
                        int64_t ldo, int dtype, void* stream) {
     if (int e = check_rows("add", M, C)) return e;
     TSS_DISPATCH_DTYPE(dtype, "add", {
-        add_kernel<T><<<stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+        tss_launch(add_kernel<T>, stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream, 
             (const T*)a, (const T*)b, (T*)out, M, C, lda, ldb, ldo);
         TSS_LAUNCH_CHECK("add");
         return TSS_OK;
@@ -405,7 +414,7 @@ extern "C" int tss_copy_rows(const void* src, void* dst, int64_t M, int C, int64
                              void* stream) {
     if (int e = check_rows("copy_rows", M, C)) return e;
     TSS_DISPATCH_DTYPE(dtype, "copy_rows", {
-        add_kernel<T><<<stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+        tss_launch(add_kernel<T>, stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream, 
             (const T*)src, (const T*)nullptr, (T*)dst, M, C, lds, 0, ldd);
         TSS_LAUNCH_CHECK("copy_rows");
         return TSS_OK;
@@ -415,7 +424,7 @@ extern "C" int tss_copy_rows(const void* src, void* dst, int64_t M, int C, int64
 extern "C" int tss_cast_from_f32(const float* src, void* dst, int64_t n, int dtype, void* stream) {
     TSS_REQUIRE(n > 0 && n % 8 == 0, "cast_from_f32: n=%lld must be a positive multiple of 8", (long long)n);
     TSS_DISPATCH_DTYPE(dtype, "cast_from_f32", {
-        cast_from_f32_kernel<T><<<stream_grid(n / 8), kThreads, 0, (cudaStream_t)stream>>>(src, (T*)dst, n / 8);
+        tss_launch(cast_from_f32_kernel<T>, stream_grid(n / 8), kThreads, 0, (cudaStream_t)stream, src, (T*)dst, n / 8);
         TSS_LAUNCH_CHECK("cast_from_f32");
         return TSS_OK;
     });
@@ -424,7 +433,7 @@ extern "C" int tss_cast_from_f32(const float* src, void* dst, int64_t n, int dty
 extern "C" int tss_scale_inplace(void* x, const float* s, int64_t n, int dtype, void* stream) {
     TSS_REQUIRE(n > 0 && n % 8 == 0, "scale_inplace: n=%lld must be a positive multiple of 8", (long long)n);
     TSS_DISPATCH_DTYPE(dtype, "scale_inplace", {
-        scale_inplace_kernel<T><<<stream_grid(n / 8), kThreads, 0, (cudaStream_t)stream>>>((T*)x, s, n / 8);
+        tss_launch(scale_inplace_kernel<T>, stream_grid(n / 8), kThreads, 0, (cudaStream_t)stream, (T*)x, s, n / 8);
         TSS_LAUNCH_CHECK("scale_inplace");
         return TSS_OK;
     });

@@ -48,6 +48,34 @@ void tss_count_launch(int n);
         else { tss_set_error("%s: unsupported dtype %d", name, (int)(dtype)); return TSS_ERR_ARG; } \
     } while (0)
 
+// ---------------------------------------------------------------- launches ----------
+// Every kernel of the library is launched with programmatic stream serialization (PDL): the next
+// kernel of the stream (or graph) may be scheduled while the previous one drains, and each
+// kernel executes griddepcontrol.wait (pdl_wait) before it touches global memory, which returns
+// once the preceding grid has completed and its writes are visible.  On-chip setup (barrier
+// init, TMEM allocation, shared-memory zeroing) sits in front of the wait and overlaps with the
+// predecessor's tail.  A step is ~370 dependent launches of 5..50 us each, so the per-edge
+// latency is a first-order term.  tss_set_pdl(0) falls back to plain serialized launches.
+bool tss_pdl_enabled();
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t tss_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = tss_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int tss_num_sms() {
     static int sms = 0;
     if (sms == 0) {

@@ -24,6 +24,7 @@ inline int stream_grid(int64_t items) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W, int C) {
+    pdl_wait();
     const int CG = C >> 3;
     const int64_t total = (int64_t)N * H * W * 9 * CG;
     for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
@@ -51,6 +52,7 @@ im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 col2im3x3_kernel(const T* __restrict__ dcol, T* __restrict__ dx, int N, int H, int W, int C) {
+    pdl_wait();
     const int CG = C >> 3;
     const int64_t total = (int64_t)N * H * W * CG;
     for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
@@ -78,6 +80,7 @@ col2im3x3_kernel(const T* __restrict__ dcol, T* __restrict__ dx, int N, int H, i
 // forward: wk[co][tap][c] = w[co][c][tap];  backward (accumulate): dw[co][c][tap] += dwk[co][tap][c]
 __global__ void permute_w3x3_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin,
                                     int backward) {
+    pdl_wait();
     const int64_t total = (int64_t)Cout * Cin * 9;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int tap = (int)(i % 9);
@@ -96,7 +99,7 @@ extern "C" int tss_im2col3x3(const void* x, void* col, int N, int H, int W, int 
     TSS_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)col & 15) == 0, "im2col3x3: buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     TSS_DISPATCH_DTYPE(dtype, "im2col3x3", {
-        im2col3x3_kernel<T><<<stream_grid((int64_t)N * H * W * 9 * (C / 8)), kThreads, 0, st>>>((const T*)x, (T*)col, N, H, W, C);
+        tss_launch(im2col3x3_kernel<T>, stream_grid((int64_t)N * H * W * 9 * (C / 8)), kThreads, 0, st, (const T*)x, (T*)col, N, H, W, C);
         TSS_LAUNCH_CHECK("im2col3x3");
         return TSS_OK;
     });
@@ -107,7 +110,7 @@ extern "C" int tss_col2im3x3(const void* dcol, void* dx, int N, int H, int W, in
     TSS_REQUIRE(((uintptr_t)dx & 15) == 0 && ((uintptr_t)dcol & 15) == 0, "col2im3x3: buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     TSS_DISPATCH_DTYPE(dtype, "col2im3x3", {
-        col2im3x3_kernel<T><<<stream_grid((int64_t)N * H * W * (C / 8)), kThreads, 0, st>>>((const T*)dcol, (T*)dx, N, H, W, C);
+        tss_launch(col2im3x3_kernel<T>, stream_grid((int64_t)N * H * W * (C / 8)), kThreads, 0, st, (const T*)dcol, (T*)dx, N, H, W, C);
         TSS_LAUNCH_CHECK("col2im3x3");
         return TSS_OK;
     });
@@ -118,7 +121,7 @@ extern "C" int tss_permute_weights3x3(const float* src, float* dst, int Cout, in
     const int64_t total = (int64_t)Cout * Cin * 9;
     int64_t grid = ceil_div64(total, 256);
     if (grid > 1184) grid = 1184;
-    permute_w3x3_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(src, dst, Cout, Cin, backward);
+    tss_launch(permute_w3x3_kernel, (int)grid, 256, 0, (cudaStream_t)stream, src, dst, Cout, Cin, backward);
     TSS_LAUNCH_CHECK("permute_weights3x3");
     return TSS_OK;
 }

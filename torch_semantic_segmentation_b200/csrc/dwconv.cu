@@ -33,6 +33,7 @@ dw_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restric
               int N, int Hi, int Wi, int Ho, int Wo, int C,
               const float* __restrict__ scale, const float* __restrict__ shift, int flags,
               float* __restrict__ stats) {
+    pdl_wait();
     extern __shared__ float s_stats[];   // [2*C] when stats != nullptr
     const int CG = C >> 3;
     const int nstrips = (Ho + R - 1) / R;
@@ -147,6 +148,7 @@ template <typename T, int R>
 __global__ void __launch_bounds__(kThreads)
 dw_dgrad_s2_quad_kernel(const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx,
                         int N, int Hi, int Wi, int Ho, int Wo, int C) {
+    pdl_wait();
     const int CG = C >> 3;
     const int nstrips = (Ho + R - 1) / R;
     const int64_t total = (int64_t)N * nstrips * Wo * CG;
@@ -217,6 +219,7 @@ template <typename T, int S, int D>
 __global__ void __launch_bounds__(kThreads)
 dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw,
                 int N, int Hi, int Wi, int Ho, int Wo, int C, int PL) {
+    pdl_wait();
     extern __shared__ float s_red[];   // [PL][C]
     const int CG = C >> 3;
     const int cg = threadIdx.x % CG;
@@ -307,7 +310,7 @@ int launch_fwd(const void* x, const float* w, void* y, int N, int Hi, int Wi, in
     const int64_t total = (int64_t)N * nstrips * Wo * (C / 8);
     const int grid = persistent_grid(ceil_div64(total, kThreads), 4, C / 8);
     const size_t smem = stats ? (size_t)2 * C * sizeof(float) : 0;
-    dw_fwd_kernel<T, S, D, R, FLIP><<<grid, kThreads, smem, st>>>(
+    tss_launch(dw_fwd_kernel<T, S, D, R, FLIP>, grid, kThreads, smem, st, 
         (const T*)x, w, (T*)y, N, Hi, Wi, Ho, Wo, C, scale, shift, flags, stats);
     TSS_LAUNCH_CHECK("dwconv3x3_fwd");
     return TSS_OK;
@@ -360,7 +363,7 @@ extern "C" int tss_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int
         constexpr int R = 4;
         const int64_t total = (int64_t)N * ((Ho + R - 1) / R) * Wo * (C / 8);
         const int grid = persistent_grid(ceil_div64(total, kThreads), 6, C / 8);
-        dw_dgrad_s2_quad_kernel<T, R><<<grid, kThreads, 0, st>>>((const T*)dy, w, (T*)dx, N, Hi, Wi, Ho, Wo, C);
+        tss_launch(dw_dgrad_s2_quad_kernel<T, R>, grid, kThreads, 0, st, (const T*)dy, w, (T*)dx, N, Hi, Wi, Ho, Wo, C);
         TSS_LAUNCH_CHECK("dwconv3x3_dgrad");
         return TSS_OK;
     });
@@ -386,10 +389,10 @@ extern "C" int tss_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int
     const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
     const size_t smem = (size_t)PL * C * sizeof(float);
     TSS_DISPATCH_DTYPE(dtype, "dwconv3x3_wgrad", {
-        if (stride == 1 && dilation == 1) dw_wgrad_kernel<T, 1, 1><<<grid, threads, smem, st>>>((const T*)x, (const T*)dy, dw, N, Hi, Wi, Ho, Wo, C, PL);
-        else if (stride == 2) dw_wgrad_kernel<T, 2, 1><<<grid, threads, smem, st>>>((const T*)x, (const T*)dy, dw, N, Hi, Wi, Ho, Wo, C, PL);
-        else if (dilation == 2) dw_wgrad_kernel<T, 1, 2><<<grid, threads, smem, st>>>((const T*)x, (const T*)dy, dw, N, Hi, Wi, Ho, Wo, C, PL);
-        else dw_wgrad_kernel<T, 1, 4><<<grid, threads, smem, st>>>((const T*)x, (const T*)dy, dw, N, Hi, Wi, Ho, Wo, C, PL);
+        if (stride == 1 && dilation == 1) tss_launch(dw_wgrad_kernel<T, 1, 1>, grid, threads, smem, st, (const T*)x, (const T*)dy, dw, N, Hi, Wi, Ho, Wo, C, PL);
+        else if (stride == 2) tss_launch(dw_wgrad_kernel<T, 2, 1>, grid, threads, smem, st, (const T*)x, (const T*)dy, dw, N, Hi, Wi, Ho, Wo, C, PL);
+        else if (dilation == 2) tss_launch(dw_wgrad_kernel<T, 1, 2>, grid, threads, smem, st, (const T*)x, (const T*)dy, dw, N, Hi, Wi, Ho, Wo, C, PL);
+        else tss_launch(dw_wgrad_kernel<T, 1, 4>, grid, threads, smem, st, (const T*)x, (const T*)dy, dw, N, Hi, Wi, Ho, Wo, C, PL);
         TSS_LAUNCH_CHECK("dwconv3x3_wgrad");
         return TSS_OK;
     });

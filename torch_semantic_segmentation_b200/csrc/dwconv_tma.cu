@@ -47,6 +47,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
     if (stats != nullptr)
         for (int i = threadIdx.x; i < 2 * CB; i += blockDim.x) s_stat[i] = 0.f;
     __syncthreads();
+    pdl_wait();              // barrier init / smem zeroing above overlap the previous kernel's tail
     if (threadIdx.x == 0) {
         mbar_expect_tx(smem_u32(bar), tile_bytes);
         tma_load_4d(smem_u32(tile), &tmX, smem_u32(bar), cb0, wo0 * S - D, ho0 * S - D, n);
@@ -168,6 +169,7 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         mbar_fence_init();
     }
     __syncthreads();
+    pdl_wait();
 
     auto issue = [&](int tile, int stage) {
         int t = tile;
@@ -274,7 +276,7 @@ int launch(const void* x, const float* w, void* y, int N, int Hi, int Wi, int Ho
         attr_set = true;
     }
     dim3 grid((unsigned)((int64_t)N * tiles_h * tiles_w), (unsigned)(C / CB));
-    kern<<<grid, threads, smem, st>>>(map, w, (T*)y, Ho, Wo, C, CB, TW, tiles_w, tiles_h, scale, shift, flags, stats);
+    tss_launch(kern, grid, threads, smem, st, map, w, (T*)y, Ho, Wo, C, CB, TW, tiles_w, tiles_h, scale, shift, flags, stats);
     TSS_LAUNCH_CHECK("dwconv3x3(tma)");
     return TSS_OK;
 }
@@ -329,7 +331,7 @@ int launch_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi
         TSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    kern<<<dim3((unsigned)gx, (unsigned)cblocks), threads, smem, st>>>(mx, mg, dw, CB, TW, tiles_w, tiles_h, ntiles,
+    tss_launch(kern, dim3((unsigned)gx, (unsigned)cblocks), threads, smem, st, mx, mg, dw, CB, TW, tiles_w, tiles_h, ntiles,
                                                                       (uint32_t)stage);
     TSS_LAUNCH_CHECK("dwconv3x3_wgrad(tma)");
     return TSS_OK;

@@ -9,7 +9,6 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxC = 32;
 
 template <typename T> struct Quad;
 template <> struct Quad<float> {
@@ -36,6 +35,7 @@ template <> struct Quad<bf16> {
 __global__ void __launch_bounds__(kThreads)
 count_valid_kernel(const int64_t* __restrict__ target, int64_t n, int64_t ignore_index,
                    unsigned long long* __restrict__ nvalid) {
+    pdl_wait();
     unsigned int cnt = 0;
     const int64_t n2 = n >> 1;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kThreads) {
@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kThreads)
 ce_fwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ target, int N, int64_t HW,
               int64_t ignore_index, const int64_t* __restrict__ nvalid, double* __restrict__ loss_sum,
               float* __restrict__ pixel_loss, T* __restrict__ dlogits) {
+    pdl_wait();
     const int64_t quads_per_img = HW >> 2;
     const int64_t total = (int64_t)N * quads_per_img;
     const float inv_n = dlogits != nullptr ? 1.f / (float)(*nvalid) : 0.f;   // inf when no valid pixel; masked below
@@ -129,6 +130,7 @@ ce_fwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ target, 
 
 __global__ void ce_finalize_kernel(const double* __restrict__ loss_sum, const int64_t* __restrict__ nvalid,
                                    float* __restrict__ loss) {
+    pdl_wait();
     *loss = (float)(*loss_sum / (double)(*nvalid));   // 0/0 -> NaN like the reference
 }
 
@@ -139,7 +141,7 @@ int launch_ce(const void* logits, const int64_t* target, int N, int64_t HW, int6
     int64_t want = ceil_div64(total, kThreads);
     int64_t cap = (int64_t)tss_num_sms() * 8;
     const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
-    ce_fwd_kernel<T, C><<<grid, kThreads, 0, st>>>((const T*)logits, target, N, HW, ignore_index, nvalid,
+    tss_launch(ce_fwd_kernel<T, C>, grid, kThreads, 0, st, (const T*)logits, target, N, HW, ignore_index, nvalid,
                                                    loss_sum, pixel_loss, (T*)dlogits);
     TSS_LAUNCH_CHECK("ce_fwd");
     return TSS_OK;
@@ -166,6 +168,7 @@ upsample_ce_kernel(const T* __restrict__ x, const int64_t* __restrict__ target, 
                    double* __restrict__ loss_sum, unsigned long long* __restrict__ nvalid,
                    float* __restrict__ pixel_loss, int Hi, int Wi, int Ho, int Wo, int64_t ldx, int64_t lddx,
                    int64_t ignore_index, float sh, float sw, int chunks) {
+    pdl_wait();
     extern __shared__ float s_mem[];
     int b = blockIdx.x;
     const int chunk = b % chunks; b /= chunks;
@@ -297,6 +300,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 upsample_ce_finalize_kernel(const double* __restrict__ loss_sum, const int64_t* __restrict__ nvalid,
                             float* __restrict__ loss, const float* __restrict__ dx32, T* __restrict__ dx, int64_t n8) {
+    pdl_wait();
     const double nv = (double)(*nvalid);
     if (blockIdx.x == 0 && threadIdx.x == 0 && loss != nullptr) *loss = (float)(*loss_sum / nv);
     if (dx == nullptr) return;
@@ -325,7 +329,7 @@ int launch_head(const void* x, const int64_t* target, float* dx32, double* loss_
         TSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    kern<<<N * Hi * chunks, kHeadCols, smem, st>>>((const T*)x, target, dx32, loss_sum, (unsigned long long*)nvalid,
+    tss_launch(kern, N * Hi * chunks, kHeadCols, smem, st, (const T*)x, target, dx32, loss_sum, (unsigned long long*)nvalid,
                                                    pixel_loss, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index,
                                                    ac_scale(Hi, Ho), sw, chunks);
     TSS_LAUNCH_CHECK("upsample_ce_fwd");
@@ -343,7 +347,7 @@ extern "C" int tss_ce_count_valid(const int64_t* target, int64_t n, int64_t igno
     int64_t want = ceil_div64(n / 2 + 1, kThreads * 4);
     int64_t cap = (int64_t)tss_num_sms() * 8;
     const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
-    count_valid_kernel<<<grid, kThreads, 0, st>>>(target, n, ignore_index, (unsigned long long*)nvalid);
+    tss_launch(count_valid_kernel, grid, kThreads, 0, st, target, n, ignore_index, (unsigned long long*)nvalid);
     TSS_LAUNCH_CHECK("ce_count_valid");
     return TSS_OK;
 }
@@ -372,7 +376,7 @@ extern "C" int tss_ce_fwd(const void* logits, const int64_t* target, int N, int 
 }
 
 extern "C" int tss_ce_finalize(const double* loss_sum, const int64_t* nvalid, float* loss, void* stream) {
-    ce_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(loss_sum, nvalid, loss);
+    tss_launch(ce_finalize_kernel, 1, 1, 0, (cudaStream_t)stream, loss_sum, nvalid, loss);
     TSS_LAUNCH_CHECK("ce_finalize");
     return TSS_OK;
 }
@@ -404,7 +408,7 @@ extern "C" int tss_upsample_ce_finalize(const double* loss_sum, const int64_t* n
         int64_t want = dx != nullptr ? ceil_div64(n / 8, kThreads) : 1;
         const int64_t cap = (int64_t)tss_num_sms() * 8;
         const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
-        upsample_ce_finalize_kernel<T><<<grid, kThreads, 0, (cudaStream_t)stream>>>(loss_sum, nvalid, loss, dx32, (T*)dx, n / 8);
+        tss_launch(upsample_ce_finalize_kernel<T>, grid, kThreads, 0, (cudaStream_t)stream, loss_sum, nvalid, loss, dx32, (T*)dx, n / 8);
         TSS_LAUNCH_CHECK("upsample_ce_finalize");
         return TSS_OK;
     });

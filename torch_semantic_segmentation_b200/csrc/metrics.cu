@@ -29,6 +29,7 @@ __device__ __forceinline__ void flush_hist(const unsigned int* s_hist, int bins,
 __global__ void __launch_bounds__(kThreads)
 cm_labels_kernel(const int64_t* __restrict__ pred, const int64_t* __restrict__ target, int64_t n, int C,
                  unsigned long long* __restrict__ cm) {
+    pdl_wait();
     __shared__ unsigned int s_hist[kMaxC * kMaxC];
     for (int i = threadIdx.x; i < C * C; i += kThreads) s_hist[i] = 0;
     __syncthreads();
@@ -76,6 +77,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 cm_logits_kernel(const T* __restrict__ logits, const int64_t* __restrict__ target, int N, int C, int64_t HW,
                  unsigned long long* __restrict__ cm, int64_t* __restrict__ pred_out) {
+    pdl_wait();
     __shared__ unsigned int s_hist[kMaxC * kMaxC];
     for (int i = threadIdx.x; i < C * C; i += kThreads) s_hist[i] = 0;
     __syncthreads();
@@ -139,7 +141,7 @@ extern "C" int tss_confusion_from_labels(const int64_t* pred, const int64_t* tar
     TSS_REQUIRE(C > 0 && C <= kMaxC, "confusion_from_labels: C=%d (max %d)", C, kMaxC);
     if (n == 0) return TSS_OK;
     TSS_REQUIRE((((uintptr_t)pred | (uintptr_t)target) & 15) == 0, "confusion_from_labels: maps must be 16-byte aligned");
-    cm_labels_kernel<<<cm_grid(n / 2 + 1), kThreads, 0, (cudaStream_t)stream>>>(pred, target, n, C,
+    tss_launch(cm_labels_kernel, cm_grid(n / 2 + 1), kThreads, 0, (cudaStream_t)stream, pred, target, n, C,
                                                                                (unsigned long long*)cm);
     TSS_LAUNCH_CHECK("confusion_from_labels");
     return TSS_OK;
@@ -151,7 +153,7 @@ extern "C" int tss_confusion_from_logits(const void* logits, const int64_t* targ
     TSS_REQUIRE(C > 0 && C <= kMaxC, "confusion_from_logits: C=%d (max %d)", C, kMaxC);
     TSS_REQUIRE(HW % 4 == 0, "confusion_from_logits: H*W=%lld must be a multiple of 4", (long long)HW);
     TSS_DISPATCH_DTYPE(dtype, "confusion_from_logits", {
-        cm_logits_kernel<T><<<cm_grid((int64_t)N * (HW / 4)), kThreads, 0, (cudaStream_t)stream>>>(
+        tss_launch(cm_logits_kernel<T>, cm_grid((int64_t)N * (HW / 4)), kThreads, 0, (cudaStream_t)stream, 
             (const T*)logits, target, N, C, HW, (unsigned long long*)cm, pred_out);
         TSS_LAUNCH_CHECK("confusion_from_logits");
         return TSS_OK;

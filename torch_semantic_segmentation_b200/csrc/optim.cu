@@ -9,6 +9,7 @@ namespace {
 // hyper: [0] lr [1] beta1 [2] beta2 [3] eps [4] weight_decay [5] step [6] 1/bias_correction1
 //        [7] sqrt(bias_correction2)
 __global__ void adamw_prepare_kernel(float* __restrict__ hyper) {
+    pdl_wait();
     const double step = (double)hyper[5] + 1.0;
     hyper[5] = (float)step;
     hyper[6] = (float)(1.0 / (1.0 - pow((double)hyper[1], step)));
@@ -18,6 +19,7 @@ __global__ void adamw_prepare_kernel(float* __restrict__ hyper) {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              int64_t n4, int64_t n, const float* __restrict__ hyper, float grad_scale) {
+    pdl_wait();
     const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
     const float step_size = lr * hyper[6], bc2s = hyper[7];
     const float decay = 1.f - lr * wd;
@@ -59,12 +61,12 @@ extern "C" int tss_adamw_step(float* p, const float* g, float* m, float* v, int6
     TSS_REQUIRE(n > 0, "adamw_step: n=%lld", (long long)n);
     TSS_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw_step: arenas must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    adamw_prepare_kernel<<<1, 1, 0, st>>>(hyper);
+    tss_launch(adamw_prepare_kernel, 1, 1, 0, st, hyper);
     TSS_LAUNCH_CHECK("adamw_prepare");
     const int64_t n4 = n / 4;
     int64_t want = ceil_div64(n4 > 0 ? n4 : 1, 256);
     int64_t cap = (int64_t)tss_num_sms() * 8;
-    adamw_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(p, g, m, v, n4, n, hyper, grad_scale);
+    tss_launch(adamw_kernel, (int)(want < cap ? want : cap), 256, 0, st, p, g, m, v, n4, n, hyper, grad_scale);
     TSS_LAUNCH_CHECK("adamw_step");
     return TSS_OK;
 }

@@ -45,6 +45,7 @@ gemm_simt_kernel(const T* __restrict__ A, const float* __restrict__ W, T* __rest
                  int64_t M, int Kred, int Nout, int64_t lda, int ldw, int64_t ldc, int Nstore,
                  const float* __restrict__ scale, const float* __restrict__ shift,
                  const T* __restrict__ res, int64_t ldr, int relu, float* __restrict__ stats) {
+    pdl_wait();
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
     __shared__ float s_col[2][BN];
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(kThreads)
 wgrad_simt_kernel(const T* __restrict__ X, const T* __restrict__ dY, float* __restrict__ dW,
                   float* __restrict__ db, int64_t M, int K, int Nc, int64_t ldx, int64_t lddy,
                   int64_t rows_per) {
+    pdl_wait();
     __shared__ __align__(16) float Gs[WK][WT];   // dY rows
     __shared__ __align__(16) float Xs[WK][WT];   // X rows
     const int tid = threadIdx.x;
@@ -216,6 +218,7 @@ wgrad_simt_kernel(const T* __restrict__ X, const T* __restrict__ dY, float* __re
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ wp, bf16* __restrict__ wpT,
                                     int Nc, int K) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Nc * K) return;
     const int n = i / K, k = i - n * K;
@@ -258,7 +261,7 @@ extern "C" int tss_pwconv_fwd(const void* x, const float* w, const void* wp, voi
     const int Nstore = (Nc % 4 == 0) ? Nc : (int)(ldy < round_up8(Nc) ? ldy : round_up8(Nc));
     dim3 grid((unsigned)ceil_div64(M, BM), (unsigned)((Nstore + BN - 1) / BN));
     TSS_DISPATCH_DTYPE(dtype, "pwconv_fwd", {
-        gemm_simt_kernel<T, false><<<grid, kThreads, 0, st>>>(
+        tss_launch(gemm_simt_kernel<T, false>, grid, kThreads, 0, st, 
             (const T*)x, w, (T*)y, M, K, Nc, ldx, K, ldy, Nstore, scale, shift, (const T*)res, ldr,
             flags & TSS_EPI_RELU, stats);
         TSS_LAUNCH_CHECK("pwconv_fwd");
@@ -279,7 +282,7 @@ extern "C" int tss_pwconv_dgrad(const void* dy, const float* w, const void* wpT,
     TSS_REQUIRE(impl == 0, "pwconv_dgrad: unknown impl %d", impl);
     dim3 grid((unsigned)ceil_div64(M, BM), (unsigned)((K + BN - 1) / BN));
     TSS_DISPATCH_DTYPE(dtype, "pwconv_dgrad", {
-        gemm_simt_kernel<T, true><<<grid, kThreads, 0, st>>>(
+        tss_launch(gemm_simt_kernel<T, true>, grid, kThreads, 0, st, 
             (const T*)dy, w, (T*)dx, M, Nc, K, lddy, K, lddx, K, nullptr, nullptr, (const T*)nullptr, 0, 0, nullptr);
         TSS_LAUNCH_CHECK("pwconv_dgrad");
         return TSS_OK;
@@ -306,7 +309,7 @@ extern "C" int tss_pwconv_wgrad(const void* x, const void* dy, float* dw, float*
     nsplit = ceil_div64(M, rows_per);
     dim3 grid(gx, gy, (unsigned)nsplit);
     TSS_DISPATCH_DTYPE(dtype, "pwconv_wgrad", {
-        wgrad_simt_kernel<T><<<grid, kThreads, 0, st>>>((const T*)x, (const T*)dy, dw, db, M, K, Nc, ldx, lddy, rows_per);
+        tss_launch(wgrad_simt_kernel<T>, grid, kThreads, 0, st, (const T*)x, (const T*)dy, dw, db, M, K, Nc, ldx, lddy, rows_per);
         TSS_LAUNCH_CHECK("pwconv_wgrad");
         return TSS_OK;
     });
@@ -314,7 +317,7 @@ extern "C" int tss_pwconv_wgrad(const void* x, const void* dy, float* dw, float*
 
 extern "C" int tss_pack_weights_bf16(const float* w, void* wp, void* wpT, int Nc, int K, void* stream) {
     TSS_REQUIRE(Nc > 0 && K > 0, "pack_weights_bf16: Nc=%d K=%d", Nc, K);
-    pack_weights_kernel<<<(Nc * K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)wp, (bf16*)wpT, Nc, K);
+    tss_launch(pack_weights_kernel, (Nc * K + 255) / 256, 256, 0, (cudaStream_t)stream, w, (bf16*)wp, (bf16*)wpT, Nc, K);
     TSS_LAUNCH_CHECK("pack_weights_bf16");
     return TSS_OK;
 }

@@ -144,6 +144,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // everything above is on-chip setup; global memory is touched from here on
 
     if (warp == 0) {
         if (lane == 0) {                                   // ---------------- TMA producer
@@ -296,6 +297,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // everything above is on-chip setup; global memory is touched from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -426,7 +428,7 @@ int tss_pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int
         attr_set = true;
     }
     dim3 grid(gx, gy, (unsigned)nsplit);
-    wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tmG, tmX, dw, M, K, Nc, bk, n_groups, k_groups, rows_per, stages, tmem_cols);
+    tss_launch(wgrad_tc_kernel, grid, kThreads, smem, st, tmG, tmX, dw, M, K, Nc, bk, n_groups, k_groups, rows_per, stages, tmem_cols);
     TSS_LAUNCH_CHECK("pwconv_wgrad_tc");
     return TSS_OK;
 }
@@ -454,7 +456,7 @@ int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, 
         attr_set = true;
     }
     dim3 grid((unsigned)ceil_div64(M, BM), (unsigned)(Nc / bn));
-    pw_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, (bf16*)y, M, K, ldy, bn, stages, tmem_cols, scale, shift,
+    tss_launch(pw_tc_kernel, grid, kThreads, smem, st, tmA, tmB, (bf16*)y, M, K, ldy, bn, stages, tmem_cols, scale, shift,
                                                (const bf16*)res, ldr, flags & TSS_EPI_RELU, stats, Nc);
     TSS_LAUNCH_CHECK("pwconv_fwd_tc");
     return TSS_OK;

@@ -21,6 +21,7 @@ __device__ __forceinline__ int win_end(int i, int in, int b) { return ((i + 1) *
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, int N, int H, int W, int C, Bins bins, int PL) {
+    pdl_wait();
     extern __shared__ float s_acc[];   // [C]
     const int cells = bins.off[bins.n];
     const int n = blockIdx.x / cells;
@@ -61,6 +62,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pool_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dx, int N, int H, int W, int C, Bins bins,
                 int accumulate) {
+    pdl_wait();
     const int CG = C >> 3;
     const int64_t total = (int64_t)N * H * W * CG;
     for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
@@ -98,6 +100,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 bilinear_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int Hi, int Wi, int Ho, int Wo, int C,
                     int64_t ldx, int64_t ldy, float sh, float sw) {
+    pdl_wait();
     const int CG = C >> 3;
     const int64_t total = (int64_t)N * Ho * Wo * CG;
     for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
@@ -131,6 +134,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 bilinear_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int Hi, int Wi, int Ho, int Wo,
                     int C, int64_t lddy, int64_t lddx, float sh, float sw) {
+    pdl_wait();
     const int CG = C >> 3;
     const int64_t total = (int64_t)N * Hi * Wi * CG;
     for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
@@ -177,6 +181,7 @@ template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(kThreads)
 resize_bwd_axis_kernel(const Tin* __restrict__ dy, Tout* __restrict__ dx, int64_t outer, int So, int Si,
                        int inner, int C, int64_t ld_in, int64_t ld_out, float scale) {
+    pdl_wait();
     const int CG = C >> 3;
     const int64_t total = outer * Si * inner * CG;
     for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
@@ -213,6 +218,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 upsample_logits_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int Hi, int Wi, int Ho, int Wo, int C,
                            int64_t ldx, float sh, float sw) {
+    pdl_wait();
     extern __shared__ float s_row[];   // [Wi][C]
     const int n = blockIdx.x / Ho, ho = blockIdx.x - n * Ho;
     int h0, h1; float lh;
@@ -246,6 +252,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 upsample_logits_bwd_kernel(const T* __restrict__ dy, float* __restrict__ dx, int Hi, int Wi, int Ho, int Wo,
                            int C, int64_t lddx, float sh, float sw) {
+    pdl_wait();
     extern __shared__ float s_t[];     // [2][Wo]
     const int hi = blockIdx.x % Hi;
     const int c = (blockIdx.x / Hi) % C;
@@ -294,6 +301,7 @@ upsample_logits_bwd_kernel(const T* __restrict__ dy, float* __restrict__ dx, int
 __global__ void __launch_bounds__(kThreads)
 bilinear_nchw_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int NC, int Hi, int Wi, int Ho,
                          int Wo, float sh, float sw) {
+    pdl_wait();
     const int64_t total = (int64_t)NC * Ho * Wo;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
         int64_t t = i;
@@ -338,7 +346,7 @@ extern "C" int tss_adaptive_pool_fwd(const void* x, void* out, int N, int H, int
     TSS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && C / 8 <= kThreads, "adaptive_pool_fwd: bad shape");
     const int CG = C / 8, PL = kThreads / CG;
     TSS_DISPATCH_DTYPE(dtype, "adaptive_pool_fwd", {
-        pool_fwd_kernel<T><<<N * b.off[b.n], PL * CG, (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
+        tss_launch(pool_fwd_kernel<T>, N * b.off[b.n], PL * CG, (size_t)C * sizeof(float), (cudaStream_t)stream, 
             (const T*)x, (T*)out, N, H, W, C, b, PL);
         TSS_LAUNCH_CHECK("adaptive_pool_fwd");
         return TSS_OK;
@@ -351,7 +359,7 @@ extern "C" int tss_adaptive_pool_bwd(const void* dout, void* dx, int N, int H, i
     if (int e = make_bins("adaptive_pool_bwd", bins, nbins, b)) return e;
     TSS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "adaptive_pool_bwd: bad shape");
     TSS_DISPATCH_DTYPE(dtype, "adaptive_pool_bwd", {
-        pool_bwd_kernel<T><<<stream_grid((int64_t)N * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+        tss_launch(pool_bwd_kernel<T>, stream_grid((int64_t)N * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream, 
             (const T*)dout, (T*)dx, N, H, W, C, b, accumulate);
         TSS_LAUNCH_CHECK("adaptive_pool_bwd");
         return TSS_OK;
@@ -363,7 +371,7 @@ extern "C" int tss_bilinear_fwd(const void* x, void* y, int N, int Hi, int Wi, i
     TSS_REQUIRE(N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bilinear_fwd: empty tensor");
     TSS_REQUIRE(C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C, "bilinear_fwd: C=%d ldx=%lld ldy=%lld", C, (long long)ldx, (long long)ldy);
     TSS_DISPATCH_DTYPE(dtype, "bilinear_fwd", {
-        bilinear_fwd_kernel<T><<<stream_grid((int64_t)N * Ho * Wo * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+        tss_launch(bilinear_fwd_kernel<T>, stream_grid((int64_t)N * Ho * Wo * (C / 8)), kThreads, 0, (cudaStream_t)stream, 
             (const T*)x, (T*)y, N, Hi, Wi, Ho, Wo, C, ldx, ldy, ac_scale(Hi, Ho), ac_scale(Wi, Wo));
         TSS_LAUNCH_CHECK("bilinear_fwd");
         return TSS_OK;
@@ -377,16 +385,16 @@ extern "C" int tss_bilinear_bwd(const void* dy, void* dx, float* workspace, int 
     cudaStream_t st = (cudaStream_t)stream;
     TSS_DISPATCH_DTYPE(dtype, "bilinear_bwd", {
         if (workspace == nullptr) {      // single gather pass (fine for small maps)
-            bilinear_bwd_kernel<T><<<stream_grid((int64_t)N * Hi * Wi * (C / 8)), kThreads, 0, st>>>(
+            tss_launch(bilinear_bwd_kernel<T>, stream_grid((int64_t)N * Hi * Wi * (C / 8)), kThreads, 0, st, 
                 (const T*)dy, (T*)dx, N, Hi, Wi, Ho, Wo, C, lddy, lddx, ac_scale(Hi, Ho), ac_scale(Wi, Wo));
             TSS_LAUNCH_CHECK("bilinear_bwd");
             return TSS_OK;
         }
         // separable: rows first (Ho -> Hi) into the fp32 workspace [N][Hi][Wo][C], then columns
-        resize_bwd_axis_kernel<T, float><<<stream_grid((int64_t)N * Hi * Wo * (C / 8)), kThreads, 0, st>>>(
+        tss_launch(resize_bwd_axis_kernel<T, float>, stream_grid((int64_t)N * Hi * Wo * (C / 8)), kThreads, 0, st, 
             (const T*)dy, workspace, N, Ho, Hi, Wo, C, lddy, C, ac_scale(Hi, Ho));
         TSS_LAUNCH_CHECK("bilinear_bwd(rows)");
-        resize_bwd_axis_kernel<float, T><<<stream_grid((int64_t)N * Hi * Wi * (C / 8)), kThreads, 0, st>>>(
+        tss_launch(resize_bwd_axis_kernel<float, T>, stream_grid((int64_t)N * Hi * Wi * (C / 8)), kThreads, 0, st, 
             workspace, (T*)dx, (int64_t)N * Hi, Wo, Wi, 1, C, C, lddx, ac_scale(Wi, Wo));
         TSS_LAUNCH_CHECK("bilinear_bwd(cols)");
         return TSS_OK;
@@ -401,7 +409,7 @@ extern "C" int tss_upsample_logits_fwd(const void* x, void* y, int N, int Hi, in
     const size_t smem = (size_t)Wi * C * sizeof(float);
     TSS_REQUIRE(smem <= 48 * 1024, "upsample_logits_fwd: Wi*C=%d too large", Wi * C);
     TSS_DISPATCH_DTYPE(dtype, "upsample_logits_fwd", {
-        upsample_logits_fwd_kernel<T><<<N * Ho, kThreads, smem, (cudaStream_t)stream>>>(
+        tss_launch(upsample_logits_fwd_kernel<T>, N * Ho, kThreads, smem, (cudaStream_t)stream, 
             (const T*)x, (T*)y, Hi, Wi, Ho, Wo, C, ldx, ac_scale(Hi, Ho), ac_scale(Wi, Wo));
         TSS_LAUNCH_CHECK("upsample_logits_fwd");
         return TSS_OK;
@@ -416,7 +424,7 @@ extern "C" int tss_upsample_logits_bwd(const void* dy, float* dx32, int N, int H
     const size_t smem = (size_t)2 * Wo * sizeof(float);
     TSS_REQUIRE(smem <= 48 * 1024, "upsample_logits_bwd: Wo=%d too large", Wo);
     TSS_DISPATCH_DTYPE(dtype, "upsample_logits_bwd", {
-        upsample_logits_bwd_kernel<T><<<N * C * Hi, kThreads, smem, (cudaStream_t)stream>>>(
+        tss_launch(upsample_logits_bwd_kernel<T>, N * C * Hi, kThreads, smem, (cudaStream_t)stream, 
             (const T*)dy, dx32, Hi, Wi, Ho, Wo, C, lddx, ac_scale(Hi, Ho), ac_scale(Wi, Wo));
         TSS_LAUNCH_CHECK("upsample_logits_bwd");
         return TSS_OK;
@@ -426,7 +434,7 @@ extern "C" int tss_upsample_logits_bwd(const void* dy, float* dx32, int N, int H
 extern "C" int tss_bilinear_nchw_f32(const float* x, float* y, int NC, int Hi, int Wi, int Ho, int Wo,
                                      void* stream) {
     TSS_REQUIRE(NC > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bilinear_nchw_f32: empty tensor");
-    bilinear_nchw_f32_kernel<<<stream_grid((int64_t)NC * Ho * Wo), kThreads, 0, (cudaStream_t)stream>>>(
+    tss_launch(bilinear_nchw_f32_kernel, stream_grid((int64_t)NC * Ho * Wo), kThreads, 0, (cudaStream_t)stream, 
         x, y, NC, Hi, Wi, Ho, Wo, ac_scale(Hi, Ho), ac_scale(Wi, Wo));
     TSS_LAUNCH_CHECK("bilinear_nchw_f32");
     return TSS_OK;

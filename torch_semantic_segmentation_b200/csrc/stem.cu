@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(kFwdThreads)
 stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
                 int N, int H, int W, int Ho, int Wo, const float* __restrict__ scale,
                 const float* __restrict__ shift, int relu, float* __restrict__ stats) {
+    pdl_wait();
     __shared__ __align__(16) float ws[27][CO];
     __shared__ float s_stat[2 * CO];
     for (int i = threadIdx.x; i < 27 * CO; i += kFwdThreads) {
@@ -107,6 +108,7 @@ template <typename T>
 __global__ void __launch_bounds__(kWgThreads)
 stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw,
                   int N, int H, int W, int Ho, int Wo, int tiles_h, int tiles_w) {
+    pdl_wait();
     extern __shared__ __align__(16) float smem[];
     float* in_s = smem;                 // [3][PH][PWP]
     float* dy_s = smem + kPatch;        // [TH*TW][CO]
@@ -192,7 +194,7 @@ extern "C" int tss_stem3x3s2_fwd(const float* x, const float* w, void* y, int N,
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const int64_t total = (int64_t)N * Ho * Wo;
     TSS_DISPATCH_DTYPE(dtype, "stem3x3s2_fwd", {
-        stem_fwd_kernel<T><<<(unsigned)ceil_div64(total, kFwdThreads), kFwdThreads, 0, (cudaStream_t)stream>>>(
+        tss_launch(stem_fwd_kernel<T>, (unsigned)ceil_div64(total, kFwdThreads), kFwdThreads, 0, (cudaStream_t)stream, 
             x, w, (T*)y, N, H, W, Ho, Wo, scale, shift, flags & TSS_EPI_RELU, stats);
         TSS_LAUNCH_CHECK("stem3x3s2_fwd");
         return TSS_OK;
@@ -215,7 +217,7 @@ extern "C" int tss_stem3x3s2_wgrad(const float* x, const void* dy, float* dw, in
             TSS_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
-        stem_wgrad_kernel<T><<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(
+        tss_launch(stem_wgrad_kernel<T>, grid, kWgThreads, smem, (cudaStream_t)stream, 
             x, (const T*)dy, dw, N, H, W, Ho, Wo, tiles_h, tiles_w);
         TSS_LAUNCH_CHECK("stem3x3s2_wgrad");
         return TSS_OK;
