@@ -191,7 +191,7 @@ def kernel_table(device):
     # stem
     x = torch.randn(N, 3, CROP, CROP, device=device)
     w = torch.randn(32, 3, 3, 3, device=device)
-    st = torch.zeros(64, device=device)
+    st = torch.zeros(64, dtype=torch.float64, device=device)
     y2 = act(32, 2)
     add('stem3x3s2_fwd', 1, 4 * 3 * px(1) + 2 * 32 * px(2), lambda: ops.stem_fwd(x, w, bf, stats=st))
     add('stem3x3s2_wgrad', 1, 4 * 3 * px(1) + 2 * 32 * px(2), lambda: ops.stem_wgrad(x, y2, torch.zeros_like(w)))
@@ -203,7 +203,7 @@ def kernel_table(device):
     for C, div, s, d, cnt in [(32, 2, 2, 1, 1), (128, 8, 1, 1, 2), (128, 8, 1, 4, 1), (384, 8, 2, 1, 1), (384, 16, 1, 1, 2)]:
         xi = act(C, div)
         wd = torch.randn(C, 1, 3, 3, device=device)
-        sd = torch.zeros(2 * C, device=device)
+        sd = torch.zeros(2 * C, dtype=torch.float64, device=device)
         yo = ops.dwconv_fwd(xi, wd, s, d)
         io = 2 * C * (px(div) + px(div * s))
         add('dwconv_fwd C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_fwd(xi, wd, s, d, stats=sd))
@@ -214,7 +214,7 @@ def kernel_table(device):
         xi = act(K, div)
         wp = torch.randn(Nc, K, 1, 1, device=device) * 0.05
         yo = act(Nc, div)
-        sp = torch.zeros(2 * Nc, device=device)
+        sp = torch.zeros(2 * Nc, dtype=torch.float64, device=device)
         pk = ops.pack_weights_bf16(wp)
         dwp = torch.zeros_like(wp)
         io = 2 * px(div) * (K + Nc)

@@ -58,10 +58,11 @@ int tss_set_pdl(int enabled);
  * Epilogue: if scale/shift != NULL: y = y*scale[c]+shift[c] (folded eval-mode BatchNorm,
  * fastscnn.py:181), then ReLU if flags&TSS_EPI_RELU.  If stats != NULL (training):
  * stats[c] += sum(y), stats[C+c] += sum(y*y) over all pixels of the raw conv output
- * (BatchNorm batch statistics, fp32 atomics). */
+ * (BatchNorm batch statistics: fp32 partial sums per CTA, accumulated across CTAs with fp64
+ * atomics so that E[y^2] - mean^2 keeps fp32-reference accuracy). */
 int tss_dwconv3x3_fwd(const void* x, const float* w, void* y, int N, int Hi, int Wi, int C,
                       int stride, int dilation, const float* scale, const float* shift,
-                      int flags, float* stats, int dtype, void* stream);
+                      int flags, double* stats, int dtype, void* stream);
 /* grad wrt input: dx[N][Hi][Wi][C] from dy[N][Ho][Wo][C] (autograd of the above). */
 int tss_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int N, int Hi, int Wi, int C,
                         int stride, int dilation, int dtype, void* stream);
@@ -81,7 +82,7 @@ int tss_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int Hi,
  *           from tss_pack_weights_bf16). */
 int tss_pwconv_fwd(const void* x, const float* w, const void* wp, void* y, int64_t M, int K, int Nc,
                    int64_t ldx, int64_t ldy, const float* scale, const float* shift,
-                   const void* res, int64_t ldr, int flags, float* stats, int impl,
+                   const void* res, int64_t ldr, int flags, double* stats, int impl,
                    int dtype, void* stream);
 /* dx[M][K] = dy[M][Nc] . w[Nc][K]   (wpT = bf16 packed transpose for impl 1) */
 int tss_pwconv_dgrad(const void* dy, const float* w, const void* wpT, void* dx, int64_t M, int K,
@@ -98,7 +99,7 @@ int tss_pack_weights_bf16(const float* w, void* wp, void* wpT, int Nc, int K, vo
  * (no layout/precision pre-pass); y[N][H/2][W/2][Cout] NHWC in `dtype`; w (Cout,3,3,3).
  * Epilogue as above. */
 int tss_stem3x3s2_fwd(const float* x, const float* w, void* y, int N, int H, int W, int Cout,
-                      const float* scale, const float* shift, int flags, float* stats,
+                      const float* scale, const float* shift, int flags, double* stats,
                       int dtype, void* stream);
 int tss_stem3x3s2_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout,
                         int dtype, void* stream);
@@ -120,10 +121,10 @@ int tss_permute_weights3x3(const float* src, float* dst, int Cout, int Cin, int 
  * finalize: from stats[2C] (sum, sum of squares over `count` values per channel) compute
  * mean[c], rstd[c] = 1/sqrt(var_biased+eps), scale = gamma*rstd, shift = beta-mean*scale and
  * update running_mean/var (momentum, unbiased var) and num_batches_tracked (int64, may be NULL).
- * clear_n > 0: "consume and clear" -- stats[0..clear_n) is zeroed after it has been read, so a
- * per-layer scratch [stats 2C | backward sums 2C] is zero again for the next conv epilogue /
- * bn_bwd_reduce without a memset launch per layer. */
-int tss_bn_finalize(float* stats, int64_t count, const float* gamma, const float* beta,
+ * clear_n > 0: "consume and clear" -- stats[0..clear_n) (doubles) is zeroed after it has been read,
+ * so a per-layer scratch [stats: 2C doubles | backward sums: 2C floats = C doubles] is zero again
+ * for the next conv epilogue / bn_bwd_reduce without a memset launch per layer. */
+int tss_bn_finalize(double* stats, int64_t count, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, int64_t* num_batches_tracked,
                     float momentum, float eps, float* scale, float* shift, float* mean,
                     float* rstd, int C, int64_t clear_n, void* stream);

@@ -71,7 +71,7 @@ def test_dwconv(C, s, d, N, H, W, dtype):
     code = _lib.dtype_code(dtype)
     # training form: raw output + BatchNorm statistics
     yc, yg = pair(N, C, Ho, Wo, dtype, g)
-    sc, sg = torch.zeros(2 * C), torch.zeros(2 * C).cuda()
+    sc, sg = torch.zeros(2 * C, dtype=torch.float64), torch.zeros(2 * C, dtype=torch.float64).cuda()
     common = dict(N=N, Hi=H, Wi=W, C=C, stride=s, dilation=d, dtype=code)
     both('tss_dwconv3x3_fwd', dict(x=xc, w=w, y=yc, scale=None, shift=None, flags=0, stats=sc, **common),
          dict(x=xg, w=w.cuda(), y=yg, scale=None, shift=None, flags=0, stats=sg, **common))
@@ -112,7 +112,7 @@ def test_pwconv_simt(K, Nc, N, H, W, dtype):
     w = torch.randn(Nc, K, 1, 1, generator=g) / math.sqrt(K)
     ldy = Nc if Nc % 8 == 0 else (Nc + 7) // 8 * 8 + 8
     yc, yg = pair(N, Nc, H, W, dtype, g, pitch=ldy)
-    sc, sg = torch.zeros(2 * Nc), torch.zeros(2 * Nc).cuda()
+    sc, sg = torch.zeros(2 * Nc, dtype=torch.float64), torch.zeros(2 * Nc, dtype=torch.float64).cuda()
     base = dict(M=M, K=K, Nc=Nc, ldx=K, ldy=ldy, ldr=0, impl=0, dtype=code, wp=None)
     both('tss_pwconv_fwd', dict(x=xc, w=w, y=yc, scale=None, shift=None, res=None, flags=0, stats=sc, **base),
          dict(x=xg, w=w.cuda(), y=yg, scale=None, shift=None, res=None, flags=0, stats=sg, **base))
@@ -169,7 +169,7 @@ def test_stem(N, H, W, dtype):
     w = torch.randn(32, 3, 3, 3, generator=g) * 0.2
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     yc, yg = pair(N, 32, Ho, Wo, dtype, g)
-    sc, sg = torch.zeros(64), torch.zeros(64).cuda()
+    sc, sg = torch.zeros(64, dtype=torch.float64), torch.zeros(64, dtype=torch.float64).cuda()
     kw = dict(N=N, H=H, W=W, Cout=32, dtype=code)
     both('tss_stem3x3s2_fwd', dict(x=x, w=w, y=yc, scale=None, shift=None, flags=0, stats=sc, **kw),
          dict(x=x.cuda(), w=w.cuda(), y=yg, scale=None, shift=None, flags=0, stats=sg, **kw))
@@ -194,8 +194,8 @@ def test_batchnorm_family(C, N, H, W, dtype):
     M = N * H * W
     yc, yg = pair(N, C, H, W, dtype, g)
     # finalize
-    stats = torch.cat([torch.stack([yc.float().sum((0, 2, 3)), (yc.float() ** 2).sum((0, 2, 3))]).reshape(-1),
-                       torch.ones(2 * C)])          # [statistics | a backward-sums half that must get cleared]
+    stats = torch.cat([torch.stack([yc.double().sum((0, 2, 3)), (yc.double() ** 2).sum((0, 2, 3))]).reshape(-1),
+                       torch.ones(C, dtype=torch.float64)])   # [statistics | the backward-sums part that must get cleared]
     stats_g = stats.cuda()
     gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
     outs_c = [torch.empty(C) for _ in range(4)]
@@ -204,8 +204,8 @@ def test_batchnorm_family(C, N, H, W, dtype):
     rmg, rvg, nbtg = rm.clone().cuda(), rv.clone().cuda(), nbt.clone().cuda()
     names = ('scale', 'shift', 'mean', 'rstd')
     both('tss_bn_finalize', dict(stats=stats, count=M, gamma=gamma, beta=beta, running_mean=rm, running_var=rv,
-                                 num_batches_tracked=nbt, momentum=0.1, eps=1e-5, C=C, clear_n=4 * C, **dict(zip(names, outs_c))),
-         dict(stats=stats_g, clear_n=4 * C, count=M, gamma=gamma.cuda(), beta=beta.cuda(), running_mean=rmg, running_var=rvg,
+                                 num_batches_tracked=nbt, momentum=0.1, eps=1e-5, C=C, clear_n=3 * C, **dict(zip(names, outs_c))),
+         dict(stats=stats_g, clear_n=3 * C, count=M, gamma=gamma.cuda(), beta=beta.cuda(), running_mean=rmg, running_var=rvg,
               num_batches_tracked=nbtg, momentum=0.1, eps=1e-5, C=C, **dict(zip(names, outs_g))))
     for a, b in zip(outs_g, outs_c):
         assert rel(a, b) < 1e-5
@@ -518,7 +518,7 @@ def test_pwconv_tcgen05(K, Nc, M):
     wp, wpT = ops.pack_weights_bf16(w.cuda())
     assert torch.equal(wp.float().cpu(), w.view(Nc, K)) and torch.equal(wpT.float().cpu(), w.view(Nc, K).t())
     yc, yg = pair(1, Nc, 1, M, dtype, g)
-    sc, sg = torch.zeros(2 * Nc), torch.zeros(2 * Nc).cuda()
+    sc, sg = torch.zeros(2 * Nc, dtype=torch.float64), torch.zeros(2 * Nc, dtype=torch.float64).cuda()
     base = dict(M=M, K=K, Nc=Nc, ldx=K, ldy=Nc, ldr=0, dtype=code)
     FakeBackend().call('tss_pwconv_fwd', dict(x=xc, w=w, wp=None, y=yc, scale=None, shift=None, res=None, flags=0, stats=sc, impl=0, **base))
     _lib.backend().call('tss_pwconv_fwd', dict(x=xg, w=w.cuda(), wp=wp, y=yg, scale=None, shift=None, res=None, flags=0, stats=sg, impl=1, **base))

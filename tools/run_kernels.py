@@ -3,7 +3,7 @@
 benchmark shapes (12 x 768 x 768, bf16), so that `ncu --set full -k regex:...` can capture them:
 
     python tools/run_kernels.py                      # plain run (must exit 0 before profiling)
-    ncu --set full --clock-control none --import-source on -k regex:'dw_|pw_tc|wgrad_tc|bn_|upsample|ce_fwd|stem' \
+    ncu --set full --clock-control none --import-source on -k regex:'dw_|pw_tc|wgrad_tc|bn_|upsample|stem' \
         -s 60 -c 60 -o gpurun_out/prof python tools/run_kernels.py
 """
 import os
@@ -25,24 +25,23 @@ def act(C, div):
 
 def kernels():
     small = ops.empty_nhwc(N, CLASSES, CROP // 8, CROP // 8, bf, dev, pitch=32).normal_()
-    logits = torch.empty(N, CLASSES, CROP, CROP, dtype=bf, device=dev).normal_()
     target = torch.randint(0, CLASSES, (N, CROP, CROP), device=dev)
+    target[torch.rand(N, CROP, CROP, device=dev) < 0.1] = 255
     yield lambda: ops.upsample_logits_fwd(small, CROP, CROP)
-    yield lambda: ops.ce_forward(logits, target, 255, True)
-    yield lambda: ops.upsample_logits_bwd(logits, CROP // 8, CROP // 8, 32)
+    yield lambda: ops.upsample_ce_forward(small, target, CROP, CROP, 255, True)
     x = torch.randn(N, 3, CROP, CROP, device=dev)
     w = torch.randn(32, 3, 3, 3, device=dev)
-    st = torch.zeros(64, device=dev)
+    st = torch.zeros(64, dtype=torch.float64, device=dev)
     y2 = act(32, 2)
     sc = torch.ones(32, device=dev)
     yield lambda: ops.stem_fwd(x, w, bf, stats=st)
     yield lambda: ops.stem_wgrad(x, y2, torch.zeros_like(w))
     yield lambda: ops.bn_apply(y2, sc, sc, relu=True)
-    yield lambda: ops.bn_backward(y2, y2, y2, sc, sc, sc, True)
+    yield lambda: ops.bn_backward(y2, None, y2, sc, sc, sc, True, beta=sc)
     for C, div, s, d in [(32, 2, 2, 1), (128, 8, 1, 1), (128, 8, 1, 4), (384, 8, 2, 1), (384, 16, 1, 1)]:
         xi = act(C, div)
         wd = torch.randn(C, 1, 3, 3, device=dev)
-        sd = torch.zeros(2 * C, device=dev)
+        sd = torch.zeros(2 * C, dtype=torch.float64, device=dev)
         yo = ops.dwconv_fwd(xi, wd, s, d)
         yield lambda: ops.dwconv_fwd(xi, wd, s, d, stats=sd)
         yield lambda: ops.dwconv_dgrad(yo, wd, xi.shape[2], xi.shape[3], s, d)
@@ -52,7 +51,7 @@ def kernels():
         wp = torch.randn(Nc, K, 1, 1, device=dev) * 0.05
         packed = ops.pack_weights_bf16(wp)
         yo = act(Nc, div)
-        sp = torch.zeros(2 * Nc, device=dev)
+        sp = torch.zeros(2 * Nc, dtype=torch.float64, device=dev)
         yield lambda: ops.pwconv_fwd(xi, wp, stats=sp, wp=packed[0], impl=1)
         yield lambda: ops.pwconv_dgrad(yo, wp, wpT=packed[1], impl=1)
         yield lambda: ops.pwconv_wgrad(xi, yo, torch.zeros_like(wp), impl=1)

@@ -22,7 +22,7 @@ __device__ __forceinline__ void ldg8f(const float* __restrict__ p, float (&v)[8]
 }
 
 // ------------------------------------------------------------------ finalize / fold --
-__global__ void bn_finalize_kernel(float* __restrict__ stats, double inv_count, double unbias,
+__global__ void bn_finalize_kernel(double* __restrict__ stats, double inv_count, double unbias,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    int64_t* __restrict__ nbt, float momentum, float eps,
@@ -33,12 +33,12 @@ __global__ void bn_finalize_kernel(float* __restrict__ stats, double inv_count, 
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && nbt != nullptr) *nbt += 1;
     if (c >= C) return;
-    const float st1 = stats[c], st2 = stats[C + c];
+    const double st1 = stats[c], st2 = stats[C + c];
     // "consume and clear": thread c only ever touches indices == c (mod C), so nobody clears what
     // another thread still has to read; the scratch is zero again for its next use
-    for (int i = c; i < clear_n; i += C) stats[i] = 0.f;
-    const double mean = (double)st1 * inv_count;
-    double var = (double)st2 * inv_count - mean * mean;
+    for (int i = c; i < clear_n; i += C) stats[i] = 0.0;
+    const double mean = st1 * inv_count;
+    double var = st2 * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
     const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     const float g = gamma != nullptr ? gamma[c] : 1.f;
@@ -110,7 +110,7 @@ bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const 
 // ------------------------------------------------------------------ backward ----------
 // pass 1: per-channel sums of g and g*xhat.  Block = CG channel groups x PL row lanes.
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -139,25 +139,44 @@ bn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T*
         }
     }
     if (pl < PL) {
-        for (int64_t m = (int64_t)blockIdx.x * PL + pl; m < M; m += (int64_t)gridDim.x * PL) {
-            float g[8], yy[8];
-            load8(dz + m * lddz + c0, g);
-            load8(y + m * ldy + c0, yy);
-            if (relu) {
-                if (z != nullptr) {
-                    float zz[8];
-                    load8(z + m * ldz + c0, zz);
+        // U rows per iteration, loaded raw and unpacked late: 2U-3U independent 128-bit loads in
+        // flight per thread at a register cost of 4 per load
+        constexpr int U = 3;
+        const int64_t step = (int64_t)gridDim.x * PL;
+        for (int64_t m0 = (int64_t)blockIdx.x * PL + pl; m0 < M; m0 += U * step) {
+            Raw8<T> rg[U], ry[U], rz[U];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
+            for (int u = 0; u < U; ++u) {
+                const int64_t m = m0 + u * step;
+                if (m < M) {
+                    rg[u].ld(dz + m * lddz + c0);
+                    ry[u].ld(y + m * ldy + c0);
+                    if (relu && z != nullptr) rz[u].ld(z + m * ldz + c0);
                 } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) g[e] = fmaf(yy[e], sc[e], sh[e]) > 0.f ? g[e] : 0.f;
+                    rg[u].zero(); ry[u].zero(); rz[u].zero();
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                s1[e] += g[e];
-                s2[e] = fmaf(g[e], (yy[e] - mu[e]) * rs[e], s2[e]);
+            for (int u = 0; u < U; ++u) {
+                float g[8], yy[8];
+                rg[u].get(g);
+                ry[u].get(yy);
+                if (relu) {
+                    if (z != nullptr) {
+                        float zz[8];
+                        rz[u].get(zz);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) g[e] = fmaf(yy[e], sc[e], sh[e]) > 0.f ? g[e] : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    s1[e] += g[e];
+                    s2[e] = fmaf(g[e], (yy[e] - mu[e]) * rs[e], s2[e]);
+                }
             }
         }
 #pragma unroll
@@ -308,7 +327,7 @@ int check_rows(const char* name, int64_t M, int C) {
 
 }  // namespace
 
-extern "C" int tss_bn_finalize(float* stats, int64_t count, const float* gamma, const float* beta,
+extern "C" int tss_bn_finalize(double* stats, int64_t count, const float* gamma, const float* beta,
                                float* running_mean, float* running_var, int64_t* num_batches_tracked,
                                float momentum, float eps, float* scale, float* shift, float* mean,
                                float* rstd, int C, int64_t clear_n, void* stream) {
@@ -361,8 +380,8 @@ extern "C" int tss_bn_bwd_reduce(const void* dz, const void* z, const void* y, c
     TSS_REQUIRE(CG <= kThreads, "bn_bwd_reduce: C=%d too large", C);
     const int PL = kThreads / CG;
     const int threads = PL * CG;
-    int64_t want = ceil_div64(M, (int64_t)PL * 4);
-    int64_t cap = (int64_t)tss_num_sms() * 4;
+    int64_t want = ceil_div64(M, (int64_t)PL * 6);           // >= 2 iterations of 3 rows per pixel lane
+    int64_t cap = (int64_t)tss_num_sms() * 2;                 // 2 resident CTAs per SM (121 registers)
     const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
     TSS_DISPATCH_DTYPE(dtype, "bn_bwd_reduce", {
         tss_launch(bn_bwd_reduce_kernel<T>, grid, threads, (size_t)2 * C * sizeof(float), (cudaStream_t)stream, 

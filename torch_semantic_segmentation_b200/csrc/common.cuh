@@ -58,7 +58,15 @@ void tss_count_launch(int n);
 // latency is a first-order term.  tss_set_pdl(0) falls back to plain serialized launches.
 bool tss_pdl_enabled();
 
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// wait for the preceding grid, then let the NEXT grid's CTAs become resident as soon as every CTA
+// of this grid has started (its last wave is running): they fill the SM slots this grid's tail
+// frees, parked in their own griddepcontrol.wait, and never starve this grid's own CTAs.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifndef TSS_NO_PDL_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t tss_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -125,6 +133,64 @@ __device__ __forceinline__ void load8_smem(const bf16* p, float (&v)[8]) {
     const uint4 u = *reinterpret_cast<const uint4*>(p);
     unpack8(u, v);
 }
+// ---------------------------------------------------------------- packed fp32x2 ------
+// Blackwell issues two fp32 FMAs per lane with one FFMA2 (fma.rn.f32x2): the depthwise kernels are
+// bound by instruction issue (9 FMAs per output element against ~5 bytes of traffic), so their
+// inner loops run on float2 pairs.  Same IEEE result as two scalar fmaf.
+struct f2x4 { float2 p[4]; };
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ void load8p_smem(const bf16* p, float2 (&v)[4]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    v[0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+    v[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+    v[2] = make_float2(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u));
+    v[3] = make_float2(__uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
+}
+__device__ __forceinline__ void load8p_smem(const float* p, float2 (&v)[4]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0];
+    const float4 b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+    v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+}
+__device__ __forceinline__ void zero8p(float2 (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = make_float2(0.f, 0.f);
+}
+__device__ __forceinline__ void store8p(float* __restrict__ p, const float2 (&v)[4]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+}
+__device__ __forceinline__ void store8p(bf16* __restrict__ p, const float2 (&v)[4]) {
+    uint4 u;
+    __nv_bfloat162 h;
+    h = __float22bfloat162_rn(v[0]); u.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __float22bfloat162_rn(v[1]); u.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __float22bfloat162_rn(v[2]); u.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __float22bfloat162_rn(v[3]); u.w = *reinterpret_cast<uint32_t*>(&h);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// raw 8-element vectors (loads issued early, unpacked late: keeps many loads in flight per thread
+// without holding their fp32 expansions in registers)
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+    uint4 a;
+    __device__ __forceinline__ void ld(const bf16* p) { a = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void zero() { a = make_uint4(0, 0, 0, 0); }
+    __device__ __forceinline__ void get(float (&v)[8]) const { unpack8(a, v); }
+};
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void ld(const float* p) {
+        a = __ldg(reinterpret_cast<const float4*>(p));
+        b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    }
+    __device__ __forceinline__ void zero() { a = make_float4(0, 0, 0, 0); b = a; }
+    __device__ __forceinline__ void get(float (&v)[8]) const {
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+
 __device__ __forceinline__ void zero8(float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;

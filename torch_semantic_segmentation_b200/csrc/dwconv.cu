@@ -10,7 +10,7 @@
 
 // dwconv_tma.cu: TMA-staged forward / stride-1 dgrad; returns -1 when the shape is not covered
 int tss_dwconv3x3_tma(const void* x, const float* w, void* y, int N, int Hi, int Wi, int C, int stride, int dilation,
-                      bool flip, const float* scale, const float* shift, int flags, float* stats, int dtype,
+                      bool flip, const float* scale, const float* shift, int flags, double* stats, int dtype,
                       cudaStream_t st);
 
 int tss_dwconv3x3_wgrad_tma(const void* x, const void* dy, float* dw, int N, int Hi, int Wi, int C, int stride,
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(kThreads)
 dw_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
               int N, int Hi, int Wi, int Ho, int Wo, int C,
               const float* __restrict__ scale, const float* __restrict__ shift, int flags,
-              float* __restrict__ stats) {
+              double* __restrict__ stats) {
     pdl_wait();
     extern __shared__ float s_stats[];   // [2*C] when stats != nullptr
     const int CG = C >> 3;
@@ -134,7 +134,7 @@ dw_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restric
         __syncthreads();
         for (int i = threadIdx.x; i < 2 * C; i += kThreads) {
             const float v = s_stats[i];
-            if (v != 0.f) atomicAdd(stats + i, v);
+            if (v != 0.f) atomicAdd(stats + i, (double)v);
         }
     }
 }
@@ -145,7 +145,7 @@ dw_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restric
 // tests, no divergence).  A thread owns 8 channels and a vertical strip of R quads, sliding the
 // two gradient rows down the strip; horizontal neighbours share their loads through L1.
 template <typename T, int R>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 dw_dgrad_s2_quad_kernel(const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx,
                         int N, int Hi, int Wi, int Ho, int Wo, int C) {
     pdl_wait();
@@ -305,7 +305,7 @@ int persistent_grid(int64_t needed_ctas, int per_sm, int CG) {
 
 template <typename T, int S, int D, int R, bool FLIP>
 int launch_fwd(const void* x, const float* w, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C,
-               const float* scale, const float* shift, int flags, float* stats, cudaStream_t st) {
+               const float* scale, const float* shift, int flags, double* stats, cudaStream_t st) {
     const int nstrips = (Ho + R - 1) / R;
     const int64_t total = (int64_t)N * nstrips * Wo * (C / 8);
     const int grid = persistent_grid(ceil_div64(total, kThreads), 4, C / 8);
@@ -328,7 +328,7 @@ int check_common(const char* name, int N, int Hi, int Wi, int C, int stride, int
 
 extern "C" int tss_dwconv3x3_fwd(const void* x, const float* w, void* y, int N, int Hi, int Wi, int C,
                                  int stride, int dilation, const float* scale, const float* shift,
-                                 int flags, float* stats, int dtype, void* stream) {
+                                 int flags, double* stats, int dtype, void* stream) {
     if (int e = check_common("dwconv3x3_fwd", N, Hi, Wi, C, stride, dilation)) return e;
     TSS_REQUIRE(scale == nullptr || shift != nullptr, "dwconv3x3_fwd: scale without shift");
     cudaStream_t st = (cudaStream_t)stream;

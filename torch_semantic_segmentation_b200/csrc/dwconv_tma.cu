@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(192, 2)
 dw_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w, T* __restrict__ y,
               int Ho, int Wo, int C, int CB, int TW, int tiles_w, int tiles_h,
               const float* __restrict__ scale, const float* __restrict__ shift, int flags,
-              float* __restrict__ stats) {
+              double* __restrict__ stats) {
     constexpr int IH = Geo<S, D, TH>::IH;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -56,17 +56,18 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
     const int CGB = CB >> 3;
     const int cg = threadIdx.x % CGB, col = threadIdx.x / CGB;     // col < TW by construction
     const int c0 = cb0 + cg * 8;
-    float wr[9][8];
+    float2 wr[9][4];
 #pragma unroll
     for (int k = 0; k < 9; ++k)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) wr[k][e] = __ldg(w + (c0 + e) * 9 + (FLIP ? 8 - k : k));
+        for (int e = 0; e < 4; ++e)
+            wr[k][e] = make_float2(__ldg(w + (c0 + 2 * e) * 9 + (FLIP ? 8 - k : k)), __ldg(w + (c0 + 2 * e + 1) * 9 + (FLIP ? 8 - k : k)));
 
     mbar_wait(smem_u32(bar), 0);
 
-    float acc[TH][8];
+    float2 acc[TH][4];
 #pragma unroll
-    for (int r = 0; r < TH; ++r) zero8(acc[r]);
+    for (int r = 0; r < TH; ++r) zero8p(acc[r]);
     const T* tp = tile + ((size_t)col * S) * CB + cg * 8;
 #pragma unroll
     for (int j = 0; j < IH; ++j) {
@@ -77,9 +78,9 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
             if (tt >= 0 && tt % S == 0 && tt / S < TH) used = true;
         }
         if (!used) continue;
-        float v[3][8];
+        float2 v[3][4];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) load8_smem(tp + ((size_t)j * IW + kx * D) * CB, v[kx]);
+        for (int kx = 0; kx < 3; ++kx) load8p_smem(tp + ((size_t)j * IW + kx * D) * CB, v[kx]);
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int tt = j - ky * D;
@@ -88,32 +89,42 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[r][e] = fmaf(v[kx][e], wr[ky * 3 + kx][e], acc[r][e]);
+                    for (int e = 0; e < 4; ++e) acc[r][e] = ffma2(v[kx][e], wr[ky * 3 + kx][e], acc[r][e]);
             }
         }
     }
 
     const int wo = wo0 + col;
     const bool relu = (flags & TSS_EPI_RELU) != 0;
-    float s1[8], s2[8];
-    zero8(s1); zero8(s2);
+    float2 s1[4], s2[4];
+    zero8p(s1); zero8p(s2);
     if (wo < Wo) {
         T* yp = y + (((int64_t)n * Ho + ho0) * Wo + wo) * C + c0;
+        float2 sc[4], sh[4];
+        if (shift != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                sc[e] = scale != nullptr ? make_float2(__ldg(scale + c0 + 2 * e), __ldg(scale + c0 + 2 * e + 1)) : make_float2(1.f, 1.f);
+                sh[e] = make_float2(__ldg(shift + c0 + 2 * e), __ldg(shift + c0 + 2 * e + 1));
+            }
+        }
 #pragma unroll
         for (int r = 0; r < TH; ++r) {
             if (ho0 + r < Ho) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { s1[e] += acc[r][e]; s2[e] = fmaf(acc[r][e], acc[r][e], s2[e]); }
+                for (int e = 0; e < 4; ++e) {
+                    s1[e].x += acc[r][e].x; s1[e].y += acc[r][e].y;
+                    s2[e] = ffma2(acc[r][e], acc[r][e], s2[e]);
+                }
                 if (shift != nullptr) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        acc[r][e] = fmaf(acc[r][e], scale != nullptr ? __ldg(scale + c0 + e) : 1.f, __ldg(shift + c0 + e));
+                    for (int e = 0; e < 4; ++e) acc[r][e] = ffma2(acc[r][e], sc[e], sh[e]);
                 }
                 if (relu) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[r][e] = fmaxf(acc[r][e], 0.f);
+                    for (int e = 0; e < 4; ++e) acc[r][e] = make_float2(fmaxf(acc[r][e].x, 0.f), fmaxf(acc[r][e].y, 0.f));
                 }
-                store8(yp + (int64_t)r * Wo * C, acc[r]);
+                store8p(yp + (int64_t)r * Wo * C, acc[r]);
             }
         }
     }
@@ -124,16 +135,18 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
         __syncthreads();
         float* part = (float*)tile;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            part[(size_t)col * CB + cg * 8 + e] = s1[e];
-            part[(size_t)(TW + col) * CB + cg * 8 + e] = s2[e];
+        for (int e = 0; e < 4; ++e) {
+            part[(size_t)col * CB + cg * 8 + 2 * e] = s1[e].x;
+            part[(size_t)col * CB + cg * 8 + 2 * e + 1] = s1[e].y;
+            part[(size_t)(TW + col) * CB + cg * 8 + 2 * e] = s2[e].x;
+            part[(size_t)(TW + col) * CB + cg * 8 + 2 * e + 1] = s2[e].y;
         }
         __syncthreads();
         for (int i = threadIdx.x; i < 2 * CB; i += blockDim.x) {
             const int which = i / CB, ch = i - which * CB;
             float s = 0.f;
             for (int cidx = 0; cidx < TW; ++cidx) s += part[(size_t)(which * TW + cidx) * CB + ch];
-            atomicAdd(stats + which * C + cb0 + ch, s);
+            atomicAdd(stats + which * C + cb0 + ch, (double)s);
         }
     }
 }
@@ -188,9 +201,9 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
     const int CGB = CB >> 3;
     const int cg = threadIdx.x % CGB, col = threadIdx.x / CGB;     // col < TW by construction
-    float acc[9][8];
+    float2 acc[9][4];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) zero8(acc[k]);
+    for (int k = 0; k < 9; ++k) zero8p(acc[k]);
 
     for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
         const int stage = it & 1;
@@ -200,9 +213,9 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         mbar_wait(smem_u32(bars + stage), (uint32_t)(it >> 1) & 1);
         const T* sx = (const T*)(smem + (size_t)stage * stage_bytes) + ((size_t)col * S) * CB + cg * 8;
         const T* sg = (const T*)(smem + (size_t)stage * stage_bytes + x_pad) + (size_t)col * CB + cg * 8;
-        float g[TH][8];
+        float2 g[TH][4];
 #pragma unroll
-        for (int r = 0; r < TH; ++r) load8_smem(sg + (size_t)r * TW * CB, g[r]);
+        for (int r = 0; r < TH; ++r) load8p_smem(sg + (size_t)r * TW * CB, g[r]);
 #pragma unroll
         for (int j = 0; j < IH; ++j) {
             bool used = false;
@@ -212,9 +225,9 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 if (tt >= 0 && tt % S == 0 && tt / S < TH) used = true;
             }
             if (!used) continue;
-            float v[3][8];
+            float2 v[3][4];
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) load8_smem(sx + ((size_t)j * IW + kx * D) * CB, v[kx]);
+            for (int kx = 0; kx < 3; ++kx) load8p_smem(sx + ((size_t)j * IW + kx * D) * CB, v[kx]);
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
                 const int tt = j - ky * D;
@@ -223,7 +236,7 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[ky * 3 + kx][e] = fmaf(v[kx][e], g[r][e], acc[ky * 3 + kx][e]);
+                        for (int e = 0; e < 4; ++e) acc[ky * 3 + kx][e] = ffma2(v[kx][e], g[r][e], acc[ky * 3 + kx][e]);
                 }
             }
         }
@@ -235,7 +248,10 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
     for (int k = 0; k < 9; ++k)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) part[((size_t)col * 9 + k) * CB + cg * 8 + e] = acc[k][e];
+        for (int e = 0; e < 4; ++e) {
+            part[((size_t)col * 9 + k) * CB + cg * 8 + 2 * e] = acc[k][e].x;
+            part[((size_t)col * 9 + k) * CB + cg * 8 + 2 * e + 1] = acc[k][e].y;
+        }
     __syncthreads();
     for (int i = threadIdx.x; i < 9 * CB; i += blockDim.x) {
         const int k = i / CB, ch = i - k * CB;
@@ -251,7 +267,7 @@ template <> struct TmaType<bf16> { static constexpr CUtensorMapDataType v = CU_T
 
 template <typename T, int S, int D, int TH, bool FLIP>
 int launch(const void* x, const float* w, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int CB, int TW,
-           const float* scale, const float* shift, int flags, float* stats, cudaStream_t st) {
+           const float* scale, const float* shift, int flags, double* stats, cudaStream_t st) {
     TssEncodeTiledFn enc = tss_encode_tiled();
     TSS_REQUIRE(enc != nullptr, "dwconv_tma: cuTensorMapEncodeTiled is not available from the driver");
     constexpr int IH = Geo<S, D, TH>::IH;
@@ -350,7 +366,7 @@ bool tss_dw_tma_config(int C, int* CB, int* TW) {
 
 // flip = stride-1 dgrad (correlation with flipped taps).  Returns -1 if this shape is not covered.
 int tss_dwconv3x3_tma(const void* x, const float* w, void* y, int N, int Hi, int Wi, int C, int stride, int dilation,
-                      bool flip, const float* scale, const float* shift, int flags, float* stats, int dtype,
+                      bool flip, const float* scale, const float* shift, int flags, double* stats, int dtype,
                       cudaStream_t st) {
     int CB, TW;
     if (!tss_dw_tma_config(C, &CB, &TW)) return -1;

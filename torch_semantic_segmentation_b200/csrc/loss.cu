@@ -163,7 +163,7 @@ int launch_ce(const void* logits, const int64_t* target, int N, int64_t HW, int6
 constexpr int kHeadCols = 256;
 
 template <typename T, int C>
-__global__ void __launch_bounds__(kHeadCols)
+__global__ void __launch_bounds__(kHeadCols, 2)
 upsample_ce_kernel(const T* __restrict__ x, const int64_t* __restrict__ target, float* __restrict__ dx32,
                    double* __restrict__ loss_sum, unsigned long long* __restrict__ nvalid,
                    float* __restrict__ pixel_loss, int Hi, int Wi, int Ho, int Wo, int64_t ldx, int64_t lddx,

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kThreads)
 gemm_simt_kernel(const T* __restrict__ A, const float* __restrict__ W, T* __restrict__ Cout,
                  int64_t M, int Kred, int Nout, int64_t lda, int ldw, int64_t ldc, int Nstore,
                  const float* __restrict__ scale, const float* __restrict__ shift,
-                 const T* __restrict__ res, int64_t ldr, int relu, float* __restrict__ stats) {
+                 const T* __restrict__ res, int64_t ldr, int relu, double* __restrict__ stats) {
     pdl_wait();
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -114,8 +114,8 @@ gemm_simt_kernel(const T* __restrict__ A, const float* __restrict__ W, T* __rest
         }
         __syncthreads();
         if (tid < BN && n0 + tid < Nout) {
-            atomicAdd(stats + n0 + tid, s_col[0][tid]);
-            atomicAdd(stats + Nout + n0 + tid, s_col[1][tid]);
+            atomicAdd(stats + n0 + tid, (double)s_col[0][tid]);
+            atomicAdd(stats + Nout + n0 + tid, (double)s_col[1][tid]);
         }
     }
 
@@ -232,7 +232,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
 // implemented in pwconv_tc.cu
 int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, int Nc, int64_t ldx,
                       int64_t ldy, const float* scale, const float* shift, const void* res, int64_t ldr,
-                      int flags, float* stats, cudaStream_t st);
+                      int flags, double* stats, cudaStream_t st);
 
 int tss_pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int K, int Nc, int64_t ldx,
                         int64_t lddy, cudaStream_t st);
@@ -249,7 +249,7 @@ static int check_gemm(const char* name, int64_t M, int K, int Nc, int64_t lda, i
 
 extern "C" int tss_pwconv_fwd(const void* x, const float* w, const void* wp, void* y, int64_t M, int K, int Nc,
                               int64_t ldx, int64_t ldy, const float* scale, const float* shift,
-                              const void* res, int64_t ldr, int flags, float* stats, int impl,
+                              const void* res, int64_t ldr, int flags, double* stats, int impl,
                               int dtype, void* stream) {
     if (int e = check_gemm("pwconv_fwd", M, K, Nc, ldx, ldy, K, Nc)) return e;
     cudaStream_t st = (cudaStream_t)stream;

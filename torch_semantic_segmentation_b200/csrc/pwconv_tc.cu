@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kThreads)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              bf16* __restrict__ Y, int64_t M, int K, int64_t ldy, int block_n, int stages, uint32_t tmem_cols,
              const float* __restrict__ scale, const float* __restrict__ shift, const bf16* __restrict__ res,
-             int64_t ldr, int relu, float* __restrict__ stats, int stats_stride) {
+             int64_t ldr, int relu, double* __restrict__ stats, int stats_stride) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SW128 needs 1024-B alignment
     const uint32_t b_bytes = (uint32_t)block_n * BK * 2;
@@ -228,8 +228,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     __syncthreads();
     if (stats != nullptr) {
         for (int i = threadIdx.x; i < block_n; i += kThreads) {
-            atomicAdd(stats + n0 + i, s_stat[i]);
-            atomicAdd(stats + stats_stride + n0 + i, s_stat[block_n + i]);
+            atomicAdd(stats + n0 + i, (double)s_stat[i]);
+            atomicAdd(stats + stats_stride + n0 + i, (double)s_stat[block_n + i]);
         }
     }
     if (warp == 1) {
@@ -435,7 +435,7 @@ int tss_pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int
 
 int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, int Nc, int64_t ldx,
                       int64_t ldy, const float* scale, const float* shift, const void* res, int64_t ldr,
-                      int flags, float* stats, cudaStream_t st) {
+                      int flags, double* stats, cudaStream_t st) {
     TSS_REQUIRE(Nc % 16 == 0 && K % 8 == 0, "pwconv_tc: needs Nc %% 16 == 0 and K %% 8 == 0 (Nc=%d K=%d)", Nc, K);
     TSS_REQUIRE(ldy % 8 == 0 && (res == nullptr || ldr % 8 == 0), "pwconv_tc: output / residual pitch must be a multiple of 8");
     TSS_REQUIRE(((uintptr_t)y & 15) == 0 && ((uintptr_t)res & 15) == 0, "pwconv_tc: output / residual must be 16-byte aligned");

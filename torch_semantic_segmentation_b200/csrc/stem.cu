@@ -18,7 +18,7 @@ template <typename T>
 __global__ void __launch_bounds__(kFwdThreads)
 stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
                 int N, int H, int W, int Ho, int Wo, const float* __restrict__ scale,
-                const float* __restrict__ shift, int relu, float* __restrict__ stats) {
+                const float* __restrict__ shift, int relu, double* __restrict__ stats) {
     pdl_wait();
     __shared__ __align__(16) float ws[27][CO];
     __shared__ float s_stat[2 * CO];
@@ -90,7 +90,7 @@ stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __r
         atomicAdd(&s_stat[lane], s1);
         atomicAdd(&s_stat[CO + lane], s2);
         __syncthreads();
-        if (threadIdx.x < 2 * CO) atomicAdd(stats + threadIdx.x, s_stat[threadIdx.x]);
+        if (threadIdx.x < 2 * CO) atomicAdd(stats + threadIdx.x, (double)s_stat[threadIdx.x]);
     }
 }
 
@@ -186,7 +186,7 @@ stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* 
 }  // namespace
 
 extern "C" int tss_stem3x3s2_fwd(const float* x, const float* w, void* y, int N, int H, int W, int Cout,
-                                 const float* scale, const float* shift, int flags, float* stats,
+                                 const float* scale, const float* shift, int flags, double* stats,
                                  int dtype, void* stream) {
     TSS_REQUIRE(N > 0 && H > 0 && W > 0, "stem3x3s2_fwd: empty input");
     TSS_REQUIRE(Cout == CO, "stem3x3s2_fwd: Cout=%d unsupported (only %d)", Cout, CO);

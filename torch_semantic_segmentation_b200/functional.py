@@ -16,6 +16,7 @@ One ``torch.autograd.Function`` per reference building block:
 Backward runs on autograd's worker thread; every kernel launch goes to that thread's
 current stream (``_lib.call``), which autograd sets to the forward stream.
 """
+import os
 import threading
 
 import torch
@@ -72,7 +73,7 @@ class _WgradLane:
     their memory to a main-stream kernel while a side-stream wgrad still reads it."""
 
     def __init__(self):
-        self.enabled = True
+        self.enabled = os.environ.get('TSS_WGRAD_LANE', '1') != '0'
         self.streams = {}
         self.keep = []
         self.dirty = set()
@@ -150,12 +151,12 @@ class ConvBNAct(torch.autograd.Function):
         C = weight.shape[0]
         if bn.momentum is None:
             raise RuntimeError('BatchNorm2d(momentum=None) (cumulative average) is not supported')
-        # per-layer scratch [statistics 2C | backward sums 2C]: finalize re-zeroes all of it
+        # per-layer scratch [statistics 2C fp64 | backward sums 2C fp32]: finalize re-zeroes all of it
         scratch = ops.layer_scratch(bn, weight.device)
         y = conv_forward(spec, x, weight, stats=scratch, packed=packed)
         N, _, H, W = y.shape
         scale, shift, mean, rstd = ops.bn_finalize(scratch, N * H * W, bn, float(bn.momentum), float(bn.eps),
-                                                   update_running=bn.track_running_stats, clear_n=4 * C, C=C)
+                                                   update_running=bn.track_running_stats, clear_n=3 * C, C=C)
         bn._tss_dirty = False
         ctx.scratch = scratch
         z = ops.bn_apply(y, scale, shift, res=res, relu=spec.relu)
@@ -182,7 +183,7 @@ class ConvBNAct(torch.autograd.Function):
         else:
             gg_out, gb_out = gg, gb
         want_dres = ctx.has_res and ctx.needs_input_grad[1]
-        sums = ctx.scratch[2 * C:]
+        sums = ctx.scratch[2 * C:].view(torch.float32)
         if spec.bn._tss_dirty or ctx.scratch is not getattr(spec.bn, '_tss_scratch', None):
             sums = None      # a second backward without a forward in between: fresh zeros
         spec.bn._tss_dirty = True

@@ -67,6 +67,10 @@ def zeros_f32(n, device):
     return torch.zeros(n, dtype=torch.float32, device=device)
 
 
+def zeros_f64(n, device):
+    return torch.zeros(n, dtype=torch.float64, device=device)
+
+
 # ------------------------------------------------------------------ depthwise 3x3 ------
 def dwconv_fwd(x, w, stride, dilation, scale=None, shift=None, relu=False, stats=None):
     N, C, Hi, Wi, ld = _g(x, 'dwconv_fwd')
@@ -200,12 +204,13 @@ def permute_weights3x3_bwd(dwk, dw):
 
 # ------------------------------------------------------------------ batch norm ---------
 def layer_scratch(bn, device):
-    """Per-layer fp32 scratch [conv-epilogue statistics 2C | BatchNorm-backward sums 2C], allocated
-    once and kept zero by ``tss_bn_finalize``'s consume-and-clear (no memset launch per layer and
-    step).  ``bn._tss_dirty`` tracks whether the backward half was used since it was last cleared."""
+    """Per-layer scratch of 3C doubles: [conv-epilogue statistics, 2C fp64 | BatchNorm-backward sums,
+    2C fp32 in the last C doubles], allocated once and kept zero by ``tss_bn_finalize``'s
+    consume-and-clear (no memset launch per layer and step).  ``bn._tss_dirty`` tracks whether the
+    backward part was used since it was last cleared."""
     s = getattr(bn, '_tss_scratch', None)
-    if s is None or s.device != device or s.numel() != 4 * bn.num_features:
-        s = torch.zeros(4 * bn.num_features, dtype=torch.float32, device=device)
+    if s is None or s.device != device or s.numel() != 3 * bn.num_features:
+        s = torch.zeros(3 * bn.num_features, dtype=torch.float64, device=device)
         bn._tss_scratch = s
         bn._tss_dirty = False
     return s
