@@ -144,22 +144,33 @@ def measured_peak():
 
 
 def time_kernel(fn, iters=20, flush=None):
-    """Average device time of `fn()` in ms: CUDA events on the launching stream, L2 flushed
-    (a 256 MB write) before every timed launch."""
-    for _ in range(3):
+    """Average DEVICE time of `fn()` in ms.  `fn` (one or a few launches + their allocations) is
+    captured into a CUDA graph together with an L2 flush (a 256 MB write) in front of it and the
+    graph is replayed `iters` times between two CUDA events; the time of a flush-only graph,
+    measured the same way, is subtracted.  Host launch overhead is therefore outside the number."""
+    for _ in range(2):
         fn()
     torch.cuda.synchronize()
-    total = 0.0
-    for _ in range(iters):
-        if flush is not None:
-            flush.zero_()
+
+    def graph_ms(body):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        g.replay()
+        torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(iters):
+            g.replay()
         b.record()
         b.synchronize()
-        total += a.elapsed_time(b)
-    return total / iters
+        return a.elapsed_time(b) / iters
+
+    if flush is None:
+        return graph_ms(fn)
+    both = graph_ms(lambda: (flush.zero_(), fn()))
+    only = graph_ms(lambda: flush.zero_())
+    return max(both - only, 1e-6)
 
 
 def kernel_table(device):

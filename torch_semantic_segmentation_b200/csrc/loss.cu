@@ -161,6 +161,13 @@ int launch_ce(const void* logits, const int64_t* target, int N, int64_t HW, int6
 //   atomics per (source pixel, class) per CTA.  Gradients are accumulated UNSCALED; the valid
 //   count is produced by the same pass and applied by tss_upsample_ce_finalize.
 constexpr int kHeadCols = 256;
+constexpr int kHeadMaxRows = 32;      // output rows per source-row interval (ceil(1/scale) + 1 <= 32 for x2..x16)
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <typename T, int C>
 __global__ void __launch_bounds__(kHeadCols, 2)
@@ -170,92 +177,123 @@ upsample_ce_kernel(const T* __restrict__ x, const int64_t* __restrict__ target, 
                    int64_t ignore_index, float sh, float sw, int chunks) {
     pdl_wait();
     extern __shared__ float s_mem[];
+    constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+    constexpr int TP = 2 * C + 1;
+    __shared__ int s_nrows;
+    __shared__ int s_row_ho[kHeadMaxRows];
+    __shared__ float s_row_k0[kHeadMaxRows], s_row_k1[kHeadMaxRows], s_row_lh[kHeadMaxRows];
+    __shared__ int s_w0[kHeadCols];
+    __shared__ float s_lw[kHeadCols];
     int b = blockIdx.x;
     const int chunk = b % chunks; b /= chunks;
     const int hi = b % Hi;
     const int n = b / Hi;
     const int wo_lo = chunk * kHeadCols;
     const int wo_hi = min(wo_lo + kHeadCols, Wo) - 1;             // inclusive
-    // source column range touched by this chunk
     int wl0, wl1, wh0, wh1; float tmp;
     ac_source(sw, wo_lo, Wi, wl0, wl1, tmp);
     ac_source(sw, wo_hi, Wi, wh0, wh1, tmp);
-    const int wi_lo = wl0, ncols = wh1 - wl0 + 1;
-    float* s_src = s_mem;                                         // [2][ncols][C]
-    float* s_t = s_mem + 2 * ncols * C;                           // [kHeadCols][2*C + 1]
-    constexpr int TP = 2 * C + 1;
+    const int wi_lo = wl0, ncols = wh1 - wl0 + 1;                 // source columns touched by this chunk
+    float* s_src = s_mem;                                         // [2][ncols][C], pre-scaled by log2(e)
+    float* s_t = s_mem + 2 * ncols * C;                           // [kHeadCols][TP]: t0 | t1 per output column
     const int h1src = hi + (hi < Hi - 1 ? 1 : 0);
     for (int i = threadIdx.x; i < 2 * ncols * C; i += kHeadCols) {
         const int r = i / (ncols * C), rem = i - r * ncols * C;
         const int w = rem / C, c = rem - w * C;
-        s_src[i] = to_f32(x[(((int64_t)n * Hi + (r ? h1src : hi)) * Wi + wi_lo + w) * ldx + c]);
+        s_src[i] = kLog2e * to_f32(x[(((int64_t)n * Hi + (r ? h1src : hi)) * Wi + wi_lo + w) * ldx + c]);
     }
-    __syncthreads();
-
+    if (threadIdx.x == 0) {                                       // the output rows whose upper source row is hi
+        int cnt = 0;
+        const int ho_a = first_candidate(sh, hi, Ho), ho_b = last_candidate(sh, hi, Ho);
+        for (int ho = ho_a; ho <= ho_b && cnt < kHeadMaxRows; ++ho) {
+            int h0, h1; float lh;
+            ac_source(sh, ho, Hi, h0, h1, lh);
+            if (h0 != hi) continue;
+            s_row_ho[cnt] = ho;
+            s_row_lh[cnt] = lh;
+            s_row_k0[cnt] = (h1 == hi) ? 1.f : 1.f - lh;          // clamped last row: both weights land on hi
+            s_row_k1[cnt] = (h1 == hi) ? 0.f : lh;
+            ++cnt;
+        }
+        s_nrows = cnt;
+    }
     const int wo = wo_lo + threadIdx.x;
     const bool col_ok = wo <= wo_hi;
+    int w0 = 0, w1 = 0; float lw = 0.f;
+    if (col_ok) ac_source(sw, wo, Wi, w0, w1, lw);
+    s_w0[threadIdx.x] = col_ok ? w0 : -4;
+    s_lw[threadIdx.x] = lw;
+    float* my_t = s_t + threadIdx.x * TP;
+#pragma unroll
+    for (int c = 0; c < 2 * C; ++c) my_t[c] = 0.f;                // the -onehot part is accumulated here
+    __syncthreads();
+
     float t0[C], t1[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) { t0[c] = 0.f; t1[c] = 0.f; }
     float lsum = 0.f;
     unsigned int cnt = 0;
     if (col_ok) {
-        int w0, w1; float lw;
-        ac_source(sw, wo, Wi, w0, w1, lw);
-        float a[C], bb[C];
+        float a[C], d[C];                                         // row hi, and (row hi+1) - (row hi), in log2 units
         const float* p00 = s_src + (w0 - wi_lo) * C;
         const float* p01 = s_src + (w1 - wi_lo) * C;
         const float* p10 = p00 + ncols * C;
         const float* p11 = p01 + ncols * C;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            a[c] = (1.f - lw) * p00[c] + lw * p01[c];
-            bb[c] = (1.f - lw) * p10[c] + lw * p11[c];
+            a[c] = fmaf(lw, p01[c] - p00[c], p00[c]);
+            d[c] = fmaf(lw, p11[c] - p10[c], p10[c]) - a[c];
         }
-        const int ho_a = first_candidate(sh, hi, Ho), ho_b = last_candidate(sh, hi, Ho);
-        for (int ho = ho_a; ho <= ho_b; ++ho) {
-            int h0, h1; float lh;
-            ac_source(sh, ho, Hi, h0, h1, lh);
-            if (h0 != hi) continue;
+        const int nrows = s_nrows;
+        for (int r = 0; r < nrows; ++r) {
+            const int ho = s_row_ho[r];
+            const float lh = s_row_lh[r];
             const int64_t pix = ((int64_t)n * Ho + ho) * Wo + wo;
-            const int64_t tg = __ldg(target + pix);
-            const bool valid = tg != ignore_index && tg >= 0 && tg < C;
+            const int64_t tg64 = __ldg(target + pix);
+            const bool valid = tg64 != ignore_index && tg64 >= 0 && tg64 < C;
+            const int tg = valid ? (int)tg64 : 0;
             float v[C];
             float mx = -INFINITY;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                v[c] = (1.f - lh) * a[c] + lh * bb[c];
+                v[c] = fmaf(lh, d[c], a[c]);
                 mx = fmaxf(mx, v[c]);
             }
-            float se = 0.f, xt = 0.f;
+            float se = 0.f;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                if ((int64_t)c == tg) xt = v[c];
-                v[c] = __expf(v[c] - mx);
+                v[c] = ex2_approx(v[c] - mx);
                 se += v[c];
             }
-            const float pl = valid ? (__logf(se) + mx - xt) : 0.f;
-            if (pixel_loss != nullptr) pixel_loss[pix] = pl;
-            if (valid) {
+            if (valid || pixel_loss != nullptr) {
+                // the target class' logit again, from the staged source (dynamic index: shared memory)
+                const float xa = fmaf(lw, p01[tg] - p00[tg], p00[tg]);
+                const float xb = fmaf(lw, p11[tg] - p10[tg], p10[tg]);
+                const float xt = fmaf(lh, xb - xa, xa);
+                const float pl = valid ? kLn2 * (__log2f(se) + mx - xt) : 0.f;
+                if (pixel_loss != nullptr) pixel_loss[pix] = pl;
                 lsum += pl;
+            }
+            if (valid) {
                 ++cnt;
                 const float inv = 1.f / se;
-                const float k0 = (h1 == hi) ? 1.f : 1.f - lh;        // clamped last row: both weights land on hi
-                const float k1 = (h1 == hi) ? 0.f : lh;
+                const float k0 = s_row_k0[r], k1 = s_row_k1[r];
+                const float ik0 = inv * k0, ik1 = inv * k1;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const float g = v[c] * inv - ((int64_t)c == tg ? 1.f : 0.f);
-                    t0[c] = fmaf(g, k0, t0[c]);
-                    t1[c] = fmaf(g, k1, t1[c]);
+                    t0[c] = fmaf(v[c], ik0, t0[c]);
+                    t1[c] = fmaf(v[c], ik1, t1[c]);
                 }
+                my_t[tg] -= k0;
+                my_t[C + tg] -= k1;
             }
         }
     }
     if (dx32 != nullptr) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            s_t[threadIdx.x * TP + c] = t0[c];
-            s_t[threadIdx.x * TP + C + c] = t1[c];
+            my_t[c] += t0[c];
+            my_t[C + c] += t1[c];
         }
         __syncthreads();
         const bool has_next = hi < Hi - 1;
@@ -263,17 +301,16 @@ upsample_ce_kernel(const T* __restrict__ x, const int64_t* __restrict__ target, 
             const int w = i / C, c = i - w * C;
             const int wi = wi_lo + w;
             int ca = first_candidate(sw, wi, Wo), cb = last_candidate(sw, wi, Wo);
-            ca = max(ca, wo_lo); cb = min(cb, wo_hi);
+            ca = max(ca, wo_lo) - wo_lo; cb = min(cb, wo_hi) - wo_lo;
             float a0 = 0.f, a1 = 0.f;
             for (int o = ca; o <= cb; ++o) {
-                int w0, w1; float lw;
-                ac_source(sw, o, Wi, w0, w1, lw);
-                float ww = 0.f;
-                if (w0 == wi) ww += 1.f - lw;
-                if (w1 == wi) ww += lw;
-                if (ww == 0.f) continue;
-                a0 = fmaf(s_t[(o - wo_lo) * TP + c], ww, a0);
-                a1 = fmaf(s_t[(o - wo_lo) * TP + C + c], ww, a1);
+                const int ow0 = s_w0[o];
+                const float olw = s_lw[o];
+                // weight of output column o on source column wi (w1 == w0 at the clamped right edge)
+                const int ow1 = ow0 + (ow0 < Wi - 1 ? 1 : 0);
+                const float ww = (ow0 == wi ? 1.f - olw : 0.f) + (ow1 == wi ? olw : 0.f);
+                a0 = fmaf(s_t[o * TP + c], ww, a0);
+                a1 = fmaf(s_t[o * TP + C + c], ww, a1);
             }
             if (a0 != 0.f) atomicAdd(dx32 + (((int64_t)n * Hi + hi) * Wi + wi) * lddx + c, a0);
             if (has_next && a1 != 0.f) atomicAdd(dx32 + (((int64_t)n * Hi + hi + 1) * Wi + wi) * lddx + c, a1);
