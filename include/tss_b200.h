@@ -201,12 +201,14 @@ int tss_cast_from_f32(const float* src, void* dst, int64_t n, int dtype, void* s
  * count_valid: nvalid[0] = #(target != ignore_index).
  * fwd: ONE pass computes per-pixel loss, the loss sum (loss_sum[0] += , fp64) and, if
  * dlogits != NULL, the gradient of the MEAN loss: (softmax - onehot)/nvalid[0] (0 at ignored
- * pixels).  pixel_loss (fp32 [N][HW], may be NULL) receives the reduction='none' values. */
+ * pixels).  pixel_loss (fp32 [N][HW], may be NULL) receives the reduction='none' values.
+ * ohem != NULL (device float[4] = {cut, w_above, tie, w_tie} from tss_ohem_select): the gradient of
+ * pixel i is weighted by (loss_i > cut ? w_above : loss_i == tie ? w_tie : 0) instead of 1/nvalid. */
 int tss_ce_count_valid(const int64_t* target, int64_t n, int64_t ignore_index, int64_t* nvalid,
                        void* stream);
 int tss_ce_fwd(const void* logits, const int64_t* target, int N, int C, int64_t HW,
                int64_t ignore_index, const int64_t* nvalid, double* loss_sum, float* pixel_loss,
-               void* dlogits, int dtype, void* stream);
+               void* dlogits, const float* ohem, int dtype, void* stream);
 /* loss[0] = loss_sum[0] / nvalid[0]  (NaN if no valid pixel, like the reference) */
 int tss_ce_finalize(const double* loss_sum, const int64_t* nvalid, float* loss, void* stream);
 /* x *= s[0] (device scalar), n elements: non-unit upstream gradient of the loss */
@@ -219,11 +221,25 @@ int tss_scale_inplace(void* x, const float* s, int64_t n, int dtype, void* strea
  * dx32 != NULL, the UNSCALED gradient sum_{pixels} U^T (softmax - onehot) into the fp32 buffer
  * dx32 [N][Hi][Wi][lddx]; all three must be zeroed by the caller.  pixel_loss (fp32 [N][Ho][Wo],
  * may be NULL) receives the reduction='none' values (losses/ohem_loss.py:11-12).
+ * With ohem != NULL the gradient of each pixel carries its OHEM weight (see tss_ce_fwd) and the
+ * caller passes nvalid[0] = 1 to finalize.
  * finalize: loss[0] = loss_sum/nvalid (NaN if no valid pixel, like the reference) and
  * dx[i] = dx32[i] / nvalid in the activation dtype (n = N*Hi*Wi*lddx elements, n % 8 == 0). */
 int tss_upsample_ce_fwd(const void* x, const int64_t* target, int N, int C, int Hi, int Wi, int Ho, int Wo,
                         int64_t ldx, int64_t ignore_index, double* loss_sum, int64_t* nvalid,
-                        float* pixel_loss, float* dx32, int64_t lddx, int dtype, void* stream);
+                        float* pixel_loss, float* dx32, int64_t lddx, const float* ohem, int dtype, void* stream);
+
+/* ---- online hard example mining (losses/ohem_loss.py:10-21) -----------------------------------------
+ * pixel_loss: the n reduction='none' cross-entropy values (0 at ignored pixels, which still count in
+ * n, as in the reference).  n_keep = int(n * numel_frac).  v = the (n_keep+1)-th largest value, by a
+ * 3-pass radix select (no sort, no host synchronisation).  loss[0] = mean of the values > thresh if
+ * v > thresh, else the mean of the n_keep largest.  weights (device float[4]) receives the per-pixel
+ * gradient weights rule {cut, w_above, tie, w_tie} for the `ohem` argument of the CE kernels (values
+ * equal to the n_keep-th largest share the remaining slots evenly).  workspace:
+ * tss_ohem_workspace_bytes() bytes, ZERO on first use (the call leaves it reusable). */
+int64_t tss_ohem_workspace_bytes(void);
+int tss_ohem_select(const float* pixel_loss, int64_t n, int64_t n_keep, float thresh, void* workspace,
+                    float* loss, float* weights, void* stream);
 int tss_upsample_ce_finalize(const double* loss_sum, const int64_t* nvalid, float* loss, const float* dx32,
                              void* dx, int64_t n, int dtype, void* stream);
 

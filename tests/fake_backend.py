@@ -261,7 +261,29 @@ class FakeBackend:
         nvalid.fill_(int((target != ignore_index).sum()))
         return 0
 
-    def tss_ce_fwd(self, logits, target, N, C, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, dtype):
+    @staticmethod
+    def _ohem_weights(nll, ohem):
+        cut, above, tie, wtie = [float(v) for v in ohem]
+        return torch.where(nll > cut, torch.full_like(nll, above), torch.where(nll == tie, torch.full_like(nll, wtie), torch.zeros_like(nll)))
+
+    def tss_ohem_workspace_bytes(self):
+        return 16384
+
+    def tss_ohem_select(self, pixel_loss, n, n_keep, thresh, workspace, loss, weights):
+        v = pixel_loss.reshape(-1).float()
+        srt, _ = torch.sort(v, descending=True)
+        vk = srt[n_keep]
+        if float(vk) > thresh:
+            sel = v[v > thresh]
+            loss.fill_(float(sel.mean()))
+            weights.copy_(torch.tensor([thresh, 1.0 / sel.numel(), -1.0, 0.0]))
+        else:
+            loss.fill_(float(srt[:n_keep].mean()) if n_keep > 0 else float('nan'))
+            gt, eq = int((v > vk).sum()), int((v == vk).sum())
+            weights.copy_(torch.tensor([float(vk), 1.0 / max(n_keep, 1), float(vk), (n_keep - gt) / (eq * max(n_keep, 1)) if eq else 0.0]))
+        return 0
+
+    def tss_ce_fwd(self, logits, target, N, C, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, ohem, dtype):
         x = logits.float()
         logp = x.log_softmax(1)
         valid = target != ignore_index
@@ -274,12 +296,15 @@ class FakeBackend:
         if dlogits is not None:
             p = logp.exp()
             p.scatter_add_(1, t.unsqueeze(1), -torch.ones_like(p[:, :1]))
-            nv = float(nvalid.item())
-            dlogits.copy_(p * valid.unsqueeze(1) / nv if nv > 0 else torch.zeros_like(p))
+            if ohem is not None:
+                dlogits.copy_(p * (valid * self._ohem_weights(nll, ohem)).unsqueeze(1))
+            else:
+                nv = float(nvalid.item())
+                dlogits.copy_(p * valid.unsqueeze(1) / nv if nv > 0 else torch.zeros_like(p))
         return 0
 
     def tss_upsample_ce_fwd(self, x, target, N, C, Hi, Wi, Ho, Wo, ldx, ignore_index, loss_sum, nvalid, pixel_loss,
-                            dx32, lddx, dtype):
+                            dx32, lddx, ohem, dtype):
         xs = x.detach().float().clone().requires_grad_(True)
         with torch.enable_grad():
             logits = F.interpolate(xs, size=(Ho, Wo), mode='bilinear', align_corners=True)
@@ -287,8 +312,11 @@ class FakeBackend:
             t = torch.where(valid, target, torch.zeros_like(target))
             nll = -logits.log_softmax(1).gather(1, t.unsqueeze(1)).squeeze(1) * valid
             total = nll.double().sum()
+            plain = total.detach()
+            if ohem is not None:
+                total = (nll * self._ohem_weights(nll.detach(), ohem)).double().sum()
         if loss_sum is not None:
-            loss_sum += total.detach()
+            loss_sum += plain
         nvalid += int(valid.sum())
         if pixel_loss is not None:
             pixel_loss.copy_(nll.detach())

@@ -394,7 +394,7 @@ def test_fused_head_upsample_cross_entropy(N, C, Hi, Wi, frac, dtype):
         return dict(loss_sum=torch.zeros(1, dtype=torch.float64, device=device), nvalid=torch.zeros(1, dtype=torch.int64, device=device),
                     pixel_loss=torch.empty(N, Ho, Wo, device=device), dx32=torch.zeros(N, Hi, Wi, lp, device=device))
     bc, bg = bufs('cpu'), bufs('cuda')
-    kw = dict(N=N, C=C, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, ldx=pitch, ignore_index=255, lddx=lp, dtype=code)
+    kw = dict(N=N, C=C, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, ldx=pitch, ignore_index=255, lddx=lp, ohem=None, dtype=code)
     both('tss_upsample_ce_fwd', dict(x=xc, target=t, **bc, **kw), dict(x=xg, target=t.cuda(), **bg, **kw))
     assert int(bg['nvalid']) == int(bc['nvalid']) == int((t != 255).sum())            # integer: exact
     assert abs(float(bg['loss_sum']) - float(bc['loss_sum'])) <= 1e-5 * max(1.0, abs(float(bc['loss_sum'])))
@@ -414,6 +414,68 @@ def test_fused_head_upsample_cross_entropy(N, C, Hi, Wi, frac, dtype):
         assert abs(float(lg) - float(loss2)) < (1e-5 if dtype == torch.float32 else 5e-3) * abs(float(loss2))
     else:
         assert math.isnan(float(lg)) and math.isnan(float(lc))                          # no valid pixel: NaN like the reference
+
+
+# ------------------------------------------------------------------ OHEM -----------------
+@pytest.mark.parametrize('n,frac,kind', [(24 * 32 * 2, 0.05, 'many_hard'), (24 * 32 * 2, 0.05, 'few_hard'), (100003, 0.1, 'ties'),
+                                         (7, 0.5, 'tiny'), (1 << 20, 0.01, 'zeros'), (4099, 0.0, 'empty_top')])
+def test_ohem_select_against_sort(n, frac, kind):
+    """Radix select + case decision (tss_ohem_select) against the reference's sort-based formula."""
+    g = gen(n)
+    v = torch.rand(n, generator=g) * 3
+    if kind == 'few_hard':
+        v = v * 0.05
+    if kind == 'ties':
+        v = (v * 4).round() / 4                       # heavy ties, also exactly at the selected value
+    if kind == 'zeros':
+        v[torch.rand(n, generator=g) < 0.995] = 0.0   # (n_keep+1)-th largest is an ignored pixel's 0
+    thresh = 0.35667494393873245
+    n_keep = int(n * frac)
+    srt, _ = torch.sort(v, descending=True)
+    want = srt[srt > thresh].mean() if srt[n_keep] > thresh else srt[:n_keep].mean()
+    loss, rule = ops.ohem_select(v.cuda(), n_keep, thresh)
+    loss2, rule2 = ops.ohem_select(v.cuda(), n_keep, thresh)            # the workspace is left reusable
+    torch.cuda.synchronize()
+    if n_keep == 0 and not srt[0] > thresh:
+        assert math.isnan(float(loss))
+    else:
+        assert abs(float(loss) - float(want)) <= 1e-6 * abs(float(want)), (float(loss), float(want))
+        assert float(loss2) == float(loss) and torch.equal(rule2, rule)
+    cut, above, tie, wtie = [float(x) for x in rule.cpu()]
+    w = torch.where(v > cut, torch.full_like(v, above), torch.where(v == tie, torch.full_like(v, wtie), torch.zeros_like(v)))
+    if not math.isnan(float(loss)):
+        assert abs(float((w * v).sum()) - float(want)) <= 1e-4 * abs(float(want))   # the weights reproduce the loss
+        assert abs(float(w.sum()) - 1.0) < 1e-4
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('name', ['many_hard', 'few_hard'])
+def test_ohem_loss_matches_golden_and_oracle_gradient(name, dtype):
+    import os
+    from oracle.golden_inputs import ohem_case
+    from oracle.init_state import GOLDEN_DIR
+    from oracle.losses import ohem as oracle_ohem
+    from torch_semantic_segmentation_b200.losses import OHEMLoss
+    logits, target, kw = ohem_case(name)
+    gold = float(np.load(os.path.join(GOLDEN_DIR, 'ohem.npz'))[name])
+    x = logits.to(dtype).cuda().requires_grad_(True)
+    loss = OHEMLoss(**kw)(x, target.cuda())
+    loss.backward()
+    xr = logits.to(dtype).float().requires_grad_(True)
+    ref = oracle_ohem(xr, target, **kw)
+    ref.backward()
+    # per-pixel losses of ~2e-4 come out of logits of magnitude ~12: one fp32 ulp there is ~1e-6, so
+    # the bound is 1e-4 relative plus half an ulp of the logits' scale
+    assert abs(float(loss) - float(ref)) < 1e-4 * abs(float(ref)) + 5e-7
+    if dtype == torch.float32:
+        assert abs(float(loss) - gold) < 1e-4 * abs(gold) + 5e-7
+    # pixels tying with the selected order statistic: the reference's sort keeps an arbitrary subset,
+    # the kernel shares the slots evenly (same loss, equally valid subgradient) -> left out
+    pl = torch.nn.functional.cross_entropy(logits.to(dtype).float(), target, ignore_index=255, reduction='none')
+    srt, _ = torch.sort(pl.flatten(), descending=True)
+    vk = srt[int(pl.numel() * kw['numel_frac'])]
+    untied = ((pl - vk).abs() > 1e-5 * vk.abs()).unsqueeze(1)
+    assert rel(x.grad.cpu() * untied, xr.grad * untied) < TOL[dtype]
 
 
 @pytest.mark.parametrize('n', [0, 1, 7, 4096, 1024 * 2048 + 3])

@@ -229,3 +229,41 @@ def test_contextnet_train_forward_backward(dtype):
         for k in ('spatial.0.1.running_mean', 'spatial.0.1.running_var', 'context.0.1.running_var'):
             assert rel(msd[k], sd[k]) < 2e-2, k
         assert all(torch.isfinite(p.grad).all() for p in params.values())
+
+
+# ------------------------------------------------------------------ deep supervision + OHEM ----
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_deep_supervision_ohem_recipe(dtype):
+    """scripts/train_fastscnn.py:107-137 on the GPU: wrapped model, aux heads x8 / x32, OHEM(main) +
+    0.4 CE(aux1) + 0.4 CE(aux2); the loss is checked against stock torch ops applied to the outputs."""
+    from oracle.losses import ohem as oracle_ohem
+    from torch_semantic_segmentation_b200.losses import OHEMLoss
+    from torch_semantic_segmentation_b200.models.fastscnn import Classifier
+    from torch_semantic_segmentation_b200.wrappers import DeepSupervisionWrapper
+    from torch_semantic_segmentation_b200.wrappers.deep_supervision_wrapper import AuxiliaryHead
+    torch.manual_seed(0)
+    model = fastscnn(3, 19)
+    model = DeepSupervisionWrapper(model, [
+        (model.downsample, AuxiliaryHead(Classifier(64, 19), 8)),
+        (model.features, AuxiliaryHead(Classifier(128, 19), 32)),
+    ]).cuda().set_compute_dtype(dtype)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    x, y = train_batch('fastscnn')
+    model.train()
+    out, (aux1, aux2) = model(x.cuda())
+    assert out.shape == aux1.shape == aux2.shape == (2, 19, 96, 160)
+    loss = OHEMLoss(ignore_index=255, numel_frac=0.1)(out, y.cuda()) \
+        + 0.4 * CrossEntropyLoss(ignore_index=255)(aux1, y.cuda()) + 0.4 * CrossEntropyLoss(ignore_index=255)(aux2, y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    want = oracle_ohem(out.detach().float().cpu(), y, ignore_index=255, numel_frac=0.1) \
+        + 0.4 * F.cross_entropy(aux1.detach().float().cpu(), y, ignore_index=255) \
+        + 0.4 * F.cross_entropy(aux2.detach().float().cpu(), y, ignore_index=255)
+    tol = 1e-4 if dtype == torch.float32 else 1e-2      # bf16: the fused head interpolates in fp32, the check rounds the logits first
+    assert abs(float(loss) - float(want)) < tol * abs(float(want)), (float(loss), float(want))
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    model.eval()
+    with torch.no_grad():
+        assert model(x.cuda()).shape == (2, 19, 96, 160)

@@ -35,7 +35,7 @@ _PTR_DTYPE = {
     'int64_t': torch.int64, 'int': torch.int32,
 }
 
-_PROTO_RE = re.compile(r'^\s*(int|uint64_t|const char\*)\s+(tss_\w+)\s*\(([^)]*)\)\s*;', re.M | re.S)
+_PROTO_RE = re.compile(r'^\s*(int|int64_t|uint64_t|const char\*)\s+(tss_\w+)\s*\(([^)]*)\)\s*;', re.M | re.S)
 
 
 def dtype_code(dtype):
@@ -79,7 +79,7 @@ class _Backend:
         self.fns = {}
         for name, (ret, params) in self.protos.items():
             fn = getattr(self.lib, name)      # AttributeError = header/library drift
-            fn.restype = {'int': ctypes.c_int, 'uint64_t': ctypes.c_uint64,
+            fn.restype = {'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'uint64_t': ctypes.c_uint64,
                           'const char*': ctypes.c_char_p}[ret]
             fn.argtypes = [ctypes.c_void_p if kind == 'ptr' else _CTYPES[base]
                            for _, kind, base in params]

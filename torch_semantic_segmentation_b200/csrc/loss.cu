@@ -56,11 +56,13 @@ template <typename T, int C>
 __global__ void __launch_bounds__(kThreads)
 ce_fwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ target, int N, int64_t HW,
               int64_t ignore_index, const int64_t* __restrict__ nvalid, double* __restrict__ loss_sum,
-              float* __restrict__ pixel_loss, T* __restrict__ dlogits) {
+              float* __restrict__ pixel_loss, T* __restrict__ dlogits, const float* __restrict__ ohem) {
     pdl_wait();
     const int64_t quads_per_img = HW >> 2;
     const int64_t total = (int64_t)N * quads_per_img;
-    const float inv_n = dlogits != nullptr ? 1.f / (float)(*nvalid) : 0.f;   // inf when no valid pixel; masked below
+    const float inv_n = (dlogits != nullptr && ohem == nullptr) ? 1.f / (float)(*nvalid) : 0.f;   // inf when no valid pixel; masked below
+    float o_cut = 0.f, o_above = 0.f, o_tie = 0.f, o_wtie = 0.f;       // OHEM: per-pixel weight from the pixel's own loss
+    if (ohem != nullptr) { o_cut = __ldg(ohem); o_above = __ldg(ohem + 1); o_tie = __ldg(ohem + 2); o_wtie = __ldg(ohem + 3); }
     float lsum = 0.f;
     for (int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x; q < total; q += (int64_t)gridDim.x * kThreads) {
         const int64_t n = q / quads_per_img;
@@ -98,9 +100,12 @@ ce_fwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ target, 
         }
         if (pixel_loss != nullptr) *reinterpret_cast<float4*>(pixel_loss + n * HW + hw) = make_float4(pl[0], pl[1], pl[2], pl[3]);
         if (dlogits != nullptr) {
-            float k[4];
+            float k[4], wgt[4];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) k[p] = valid[p] ? inv_n / se[p] : 0.f;
+            for (int p = 0; p < 4; ++p) {
+                wgt[p] = ohem == nullptr ? inv_n : (pl[p] > o_cut ? o_above : (pl[p] == o_tie ? o_wtie : 0.f));
+                k[p] = valid[p] ? wgt[p] / se[p] : 0.f;
+            }
             T* gp = dlogits + n * C * HW + hw;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -108,7 +113,7 @@ ce_fwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ target, 
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     g[p] = x[c][p] * k[p];
-                    if (valid[p] && (int64_t)c == tg[p]) g[p] -= inv_n;
+                    if (valid[p] && (int64_t)c == tg[p]) g[p] -= wgt[p];
                 }
                 Quad<T>::st(gp + (int64_t)c * HW, g);
             }
@@ -136,13 +141,13 @@ __global__ void ce_finalize_kernel(const double* __restrict__ loss_sum, const in
 
 template <typename T, int C>
 int launch_ce(const void* logits, const int64_t* target, int N, int64_t HW, int64_t ignore_index,
-              const int64_t* nvalid, double* loss_sum, float* pixel_loss, void* dlogits, cudaStream_t st) {
+              const int64_t* nvalid, double* loss_sum, float* pixel_loss, void* dlogits, const float* ohem, cudaStream_t st) {
     const int64_t total = (int64_t)N * (HW >> 2);
     int64_t want = ceil_div64(total, kThreads);
     int64_t cap = (int64_t)tss_num_sms() * 8;
     const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
     tss_launch(ce_fwd_kernel<T, C>, grid, kThreads, 0, st, (const T*)logits, target, N, HW, ignore_index, nvalid,
-                                                   loss_sum, pixel_loss, (T*)dlogits);
+                                                   loss_sum, pixel_loss, (T*)dlogits, ohem);
     TSS_LAUNCH_CHECK("ce_fwd");
     return TSS_OK;
 }
@@ -161,7 +166,7 @@ int launch_ce(const void* logits, const int64_t* target, int N, int64_t HW, int6
 //   atomics per (source pixel, class) per CTA.  Gradients are accumulated UNSCALED; the valid
 //   count is produced by the same pass and applied by tss_upsample_ce_finalize.
 constexpr int kHeadCols = 256;
-constexpr int kHeadMaxRows = 32;      // output rows per source-row interval (ceil(1/scale) + 1 <= 32 for x2..x16)
+constexpr int kHeadMaxRows = 40;      // output rows per source-row interval: ceil(1/scale) + 1 (x32 heads: 34)
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -173,10 +178,12 @@ template <typename T, int C>
 __global__ void __launch_bounds__(kHeadCols, 2)
 upsample_ce_kernel(const T* __restrict__ x, const int64_t* __restrict__ target, float* __restrict__ dx32,
                    double* __restrict__ loss_sum, unsigned long long* __restrict__ nvalid,
-                   float* __restrict__ pixel_loss, int Hi, int Wi, int Ho, int Wo, int64_t ldx, int64_t lddx,
-                   int64_t ignore_index, float sh, float sw, int chunks) {
+                   float* __restrict__ pixel_loss, const float* __restrict__ ohem, int Hi, int Wi, int Ho, int Wo,
+                   int64_t ldx, int64_t lddx, int64_t ignore_index, float sh, float sw, int chunks) {
     pdl_wait();
     extern __shared__ float s_mem[];
+    float o_cut = 0.f, o_above = 0.f, o_tie = 0.f, o_wtie = 0.f;       // OHEM: per-pixel weight from the pixel's own loss
+    if (ohem != nullptr) { o_cut = __ldg(ohem); o_above = __ldg(ohem + 1); o_tie = __ldg(ohem + 2); o_wtie = __ldg(ohem + 3); }
     constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
     constexpr int TP = 2 * C + 1;
     __shared__ int s_nrows;
@@ -265,19 +272,21 @@ upsample_ce_kernel(const T* __restrict__ x, const int64_t* __restrict__ target, 
                 v[c] = ex2_approx(v[c] - mx);
                 se += v[c];
             }
+            float pl = 0.f;
             if (valid || pixel_loss != nullptr) {
                 // the target class' logit again, from the staged source (dynamic index: shared memory)
                 const float xa = fmaf(lw, p01[tg] - p00[tg], p00[tg]);
                 const float xb = fmaf(lw, p11[tg] - p10[tg], p10[tg]);
                 const float xt = fmaf(lh, xb - xa, xa);
-                const float pl = valid ? kLn2 * (__log2f(se) + mx - xt) : 0.f;
+                pl = valid ? kLn2 * (__log2f(se) + mx - xt) : 0.f;
                 if (pixel_loss != nullptr) pixel_loss[pix] = pl;
                 lsum += pl;
             }
             if (valid) {
                 ++cnt;
+                const float wgt = ohem == nullptr ? 1.f : (pl > o_cut ? o_above : (pl == o_tie ? o_wtie : 0.f));
                 const float inv = 1.f / se;
-                const float k0 = s_row_k0[r], k1 = s_row_k1[r];
+                const float k0 = s_row_k0[r] * wgt, k1 = s_row_k1[r] * wgt;
                 const float ik0 = inv * k0, ik1 = inv * k1;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
@@ -353,7 +362,7 @@ upsample_ce_finalize_kernel(const double* __restrict__ loss_sum, const int64_t* 
 
 template <typename T, int C>
 int launch_head(const void* x, const int64_t* target, float* dx32, double* loss_sum, int64_t* nvalid, float* pixel_loss,
-                int N, int Hi, int Wi, int Ho, int Wo, int64_t ldx, int64_t lddx, int64_t ignore_index, cudaStream_t st) {
+                const float* ohem, int N, int Hi, int Wi, int Ho, int Wo, int64_t ldx, int64_t lddx, int64_t ignore_index, cudaStream_t st) {
     const int chunks = (Wo + kHeadCols - 1) / kHeadCols;
     const float sw = ac_scale(Wi, Wo);
     int ncols_max = (int)((float)kHeadCols * sw) + 4;
@@ -367,7 +376,7 @@ int launch_head(const void* x, const int64_t* target, float* dx32, double* loss_
         attr_set = true;
     }
     tss_launch(kern, N * Hi * chunks, kHeadCols, smem, st, (const T*)x, target, dx32, loss_sum, (unsigned long long*)nvalid,
-                                                   pixel_loss, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index,
+                                                   pixel_loss, ohem, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index,
                                                    ac_scale(Hi, Ho), sw, chunks);
     TSS_LAUNCH_CHECK("upsample_ce_fwd");
     return TSS_OK;
@@ -391,20 +400,20 @@ extern "C" int tss_ce_count_valid(const int64_t* target, int64_t n, int64_t igno
 
 extern "C" int tss_ce_fwd(const void* logits, const int64_t* target, int N, int C, int64_t HW,
                           int64_t ignore_index, const int64_t* nvalid, double* loss_sum, float* pixel_loss,
-                          void* dlogits, int dtype, void* stream) {
+                          void* dlogits, const float* ohem, int dtype, void* stream) {
     TSS_REQUIRE(N > 0 && HW > 0, "ce_fwd: empty input");
     TSS_REQUIRE(HW % 4 == 0, "ce_fwd: H*W=%lld must be a multiple of 4", (long long)HW);
-    TSS_REQUIRE(dlogits == nullptr || nvalid != nullptr, "ce_fwd: gradient needs nvalid");
+    TSS_REQUIRE(dlogits == nullptr || nvalid != nullptr || ohem != nullptr, "ce_fwd: gradient needs nvalid (or OHEM weights)");
     cudaStream_t st = (cudaStream_t)stream;
     TSS_DISPATCH_DTYPE(dtype, "ce_fwd", {
         switch (C) {
-            case 19: return launch_ce<T, 19>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, st);
-            case 2: return launch_ce<T, 2>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, st);
-            case 8: return launch_ce<T, 8>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, st);
-            case 11: return launch_ce<T, 11>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, st);
-            case 12: return launch_ce<T, 12>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, st);
-            case 20: return launch_ce<T, 20>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, st);
-            case 21: return launch_ce<T, 21>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, st);
+            case 19: return launch_ce<T, 19>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, ohem, st);
+            case 2: return launch_ce<T, 2>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, ohem, st);
+            case 8: return launch_ce<T, 8>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, ohem, st);
+            case 11: return launch_ce<T, 11>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, ohem, st);
+            case 12: return launch_ce<T, 12>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, ohem, st);
+            case 20: return launch_ce<T, 20>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, ohem, st);
+            case 21: return launch_ce<T, 21>(logits, target, N, HW, ignore_index, nvalid, loss_sum, pixel_loss, dlogits, ohem, st);
             default:
                 tss_set_error("ce_fwd: C=%d not instantiated (19 Cityscapes/BDD, 11/12 CamVid, 20/21 VOC, 2, 8)", C);
                 return TSS_ERR_ARG;
@@ -420,17 +429,18 @@ extern "C" int tss_ce_finalize(const double* loss_sum, const int64_t* nvalid, fl
 
 extern "C" int tss_upsample_ce_fwd(const void* x, const int64_t* target, int N, int C, int Hi, int Wi, int Ho, int Wo,
                                    int64_t ldx, int64_t ignore_index, double* loss_sum, int64_t* nvalid,
-                                   float* pixel_loss, float* dx32, int64_t lddx, int dtype, void* stream) {
+                                   float* pixel_loss, float* dx32, int64_t lddx, const float* ohem, int dtype,
+                                   void* stream) {
     TSS_REQUIRE(N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "upsample_ce_fwd: empty input");
     TSS_REQUIRE(ldx >= C && (dx32 == nullptr || lddx >= C), "upsample_ce_fwd: pitch smaller than C=%d", C);
     TSS_REQUIRE(nvalid != nullptr, "upsample_ce_fwd: nvalid is required");
     cudaStream_t st = (cudaStream_t)stream;
     TSS_DISPATCH_DTYPE(dtype, "upsample_ce_fwd", {
         switch (C) {
-            case 19: return launch_head<T, 19>(x, target, dx32, loss_sum, nvalid, pixel_loss, N, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index, st);
-            case 11: return launch_head<T, 11>(x, target, dx32, loss_sum, nvalid, pixel_loss, N, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index, st);
-            case 12: return launch_head<T, 12>(x, target, dx32, loss_sum, nvalid, pixel_loss, N, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index, st);
-            case 21: return launch_head<T, 21>(x, target, dx32, loss_sum, nvalid, pixel_loss, N, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index, st);
+            case 19: return launch_head<T, 19>(x, target, dx32, loss_sum, nvalid, pixel_loss, ohem, N, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index, st);
+            case 11: return launch_head<T, 11>(x, target, dx32, loss_sum, nvalid, pixel_loss, ohem, N, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index, st);
+            case 12: return launch_head<T, 12>(x, target, dx32, loss_sum, nvalid, pixel_loss, ohem, N, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index, st);
+            case 21: return launch_head<T, 21>(x, target, dx32, loss_sum, nvalid, pixel_loss, ohem, N, Hi, Wi, Ho, Wo, ldx, lddx, ignore_index, st);
             default:
                 tss_set_error("upsample_ce_fwd: C=%d not instantiated (19 Cityscapes/BDD, 11/12 CamVid, 21 VOC)", C);
                 return TSS_ERR_ARG;

@@ -385,6 +385,66 @@ class UpsampleCrossEntropy(torch.autograd.Function):
         return dx, None, None, None, None
 
 
+class PixelCrossEntropy(torch.autograd.Function):
+    """``F.cross_entropy(..., reduction='none')`` (losses/ohem_loss.py:11-12): per-pixel loss, 0 at
+    ignored pixels.  Backward recomputes the softmax (one more pass over the logits)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        pixel = ops.ce_forward(logits, target, ignore_index, want_grad=False, want_pixel_loss=True)[2]
+        ctx.save_for_backward(logits, target)
+        ctx.ignore_index = ignore_index
+        return pixel
+
+    @staticmethod
+    def backward(ctx, gpix):
+        logits, target = ctx.saved_tensors
+        # d loss_i / d logits_i = softmax - onehot; computed with unit weight (nvalid = 1), then scaled per pixel
+        one = torch.ones(1, dtype=torch.int64, device=logits.device)
+        N, C, H, W = logits.shape
+        dl = torch.empty_like(logits, memory_format=torch.contiguous_format)
+        from . import _lib
+        _lib.call('tss_ce_fwd', logits=logits.contiguous(), target=target.long().contiguous(), N=N, C=C, HW=H * W,
+                  ignore_index=ctx.ignore_index, nvalid=one, loss_sum=None, pixel_loss=None, dlogits=dl, ohem=None,
+                  dtype=_lib.dtype_code(logits.dtype))
+        return dl * gpix.unsqueeze(1).to(dl.dtype), None, None
+
+
+class OhemCrossEntropy(torch.autograd.Function):
+    """``ohem_loss`` (losses/ohem_loss.py:10-21) on device: per-pixel CE -> radix select of the
+    (n+1)-th largest loss -> case decision -> OHEM-weighted gradient, with no sort and no host
+    synchronisation.  ``source`` is either the NCHW logits or, for the untouched output of one of this
+    package's models, the 1/8-resolution scores they were interpolated from (fused head)."""
+
+    @staticmethod
+    def forward(ctx, source, target, ignore_index, thresh, numel_frac, out_hw):
+        fused = out_hw is not None
+        if fused:
+            Ho, Wo = out_hw
+            pixel = ops.upsample_ce_forward(source, target, Ho, Wo, ignore_index, want_grad=False, want_pixel_loss=True)[2]
+        else:
+            pixel = ops.ce_forward(source, target, ignore_index, want_grad=False, want_pixel_loss=True)[2]
+        n = pixel.numel()
+        loss, rule = ops.ohem_select(pixel, int(n * numel_frac), thresh)
+        grad = None
+        if ctx.needs_input_grad[0]:
+            if fused:
+                grad = ops.upsample_ce_forward(source, target, Ho, Wo, ignore_index, want_grad=True, ohem=rule)[1]
+            else:
+                grad = ops.ce_forward(source, target, ignore_index, want_grad=True, ohem=rule)[1]
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        if grad is None:
+            return None, None, None, None, None, None
+        if not _unit_grad():
+            grad = grad * grad_out.to(grad.dtype)
+        return grad, None, None, None, None, None
+
+
 def attach_head(logits, scores):
     """Remember on the model's output which low-resolution scores it was interpolated from, so that
     ``losses.cross_entropy`` can take the fused head instead of re-reading the logits."""

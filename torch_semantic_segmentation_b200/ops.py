@@ -400,7 +400,23 @@ def bilinear_nchw_f32(x, Ho, Wo):
 
 
 # ------------------------------------------------------------------ loss / metrics -----
-def ce_forward(logits, target, ignore_index, want_grad, want_pixel_loss=False):
+_OHEM_WS = {}
+
+
+def ohem_select(pixel_loss, n_keep, thresh):
+    """-> loss (fp32 scalar tensor), weights (device float[4] rule for the CE kernels' ``ohem`` argument)."""
+    dev = pixel_loss.device
+    ws = _OHEM_WS.get(dev)
+    if ws is None:          # persistent, zero-initialised; every call leaves it reusable
+        ws = _OHEM_WS[dev] = torch.zeros(int(_lib.call('tss_ohem_workspace_bytes')), dtype=torch.uint8, device=dev)
+    out = torch.empty(8, dtype=torch.float32, device=dev)
+    flat = pixel_loss.reshape(-1)
+    _lib.call('tss_ohem_select', pixel_loss=flat, n=flat.numel(), n_keep=int(n_keep), thresh=float(thresh),
+              workspace=ws, loss=out[:1], weights=out[4:])
+    return out[0], out[4:]
+
+
+def ce_forward(logits, target, ignore_index, want_grad, want_pixel_loss=False, ohem=None):
     """-> loss (fp32 scalar tensor), dlogits (or None), pixel_loss (or None), nvalid (int64 (1,))."""
     N, C, H, W = logits.shape
     if not logits.is_contiguous():
@@ -414,14 +430,14 @@ def ce_forward(logits, target, ignore_index, want_grad, want_pixel_loss=False):
     dlogits = torch.empty_like(logits) if want_grad else None
     pixel = torch.empty((N, H, W), dtype=torch.float32, device=dev) if want_pixel_loss else None
     _lib.call('tss_ce_fwd', logits=logits, target=target, N=N, C=C, HW=H * W, ignore_index=ignore_index,
-              nvalid=nvalid, loss_sum=loss_sum, pixel_loss=pixel, dlogits=dlogits,
+              nvalid=nvalid, loss_sum=loss_sum, pixel_loss=pixel, dlogits=dlogits, ohem=ohem,
               dtype=dtype_code(logits.dtype))
     loss = torch.empty((), dtype=torch.float32, device=dev)
     _lib.call('tss_ce_finalize', loss_sum=loss_sum, nvalid=nvalid, loss=loss)
     return loss, dlogits, pixel, nvalid
 
 
-def upsample_ce_forward(scores, target, Ho, Wo, ignore_index, want_grad, want_pixel_loss=False):
+def upsample_ce_forward(scores, target, Ho, Wo, ignore_index, want_grad, want_pixel_loss=False, ohem=None):
     """Fused head on the 1/8-resolution NHWC class scores: -> loss (fp32 scalar tensor), gradient
     w.r.t. ``scores`` (same logical shape, channel pitch padded to 8; or None), per-pixel loss (or None)."""
     N, C, Hi, Wi, ldx = _g(scores, 'upsample_ce_forward')
@@ -439,9 +455,11 @@ def upsample_ce_forward(scores, target, Ho, Wo, ignore_index, want_grad, want_pi
     code = dtype_code(scores.dtype)
     _lib.call('tss_upsample_ce_fwd', x=scores, target=target, N=N, C=C, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, ldx=ldx,
               ignore_index=ignore_index, loss_sum=red[:1], nvalid=nvalid, pixel_loss=pixel, dx32=acc, lddx=pitch,
-              dtype=code)
+              ohem=ohem, dtype=code)
     loss = torch.empty((), dtype=torch.float32, device=dev)
     dx = torch.empty((N, Hi, Wi, pitch), dtype=scores.dtype, device=dev) if want_grad else None
+    if ohem is not None:       # OHEM-weighted gradient: already carries its per-pixel weights
+        nvalid = torch.ones(1, dtype=torch.int64, device=dev)
     _lib.call('tss_upsample_ce_finalize', loss_sum=red[:1], nvalid=nvalid, loss=loss, dx32=acc, dx=dx,
               n=N * Hi * Wi * pitch if want_grad else 0, dtype=code)
     if dx is not None:
