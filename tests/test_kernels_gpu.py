@@ -474,8 +474,9 @@ def test_ohem_loss_matches_golden_and_oracle_gradient(name, dtype):
     pl = torch.nn.functional.cross_entropy(logits.to(dtype).float(), target, ignore_index=255, reduction='none')
     srt, _ = torch.sort(pl.flatten(), descending=True)
     vk = srt[int(pl.numel() * kw['numel_frac'])]
-    untied = ((pl - vk).abs() > 1e-5 * vk.abs()).unsqueeze(1)
-    assert rel(x.grad.cpu() * untied, xr.grad * untied) < TOL[dtype]
+    untied = ((pl - vk).abs() > 1e-5 * vk.abs() + 1e-6).unsqueeze(1)     # + the fp32 noise band of the per-pixel losses
+    # 'few_hard': softmax - onehot ~ -2e-4 is itself a cancellation of O(1) terms (1e-7 absolute)
+    assert rel(x.grad.cpu() * untied, xr.grad * untied) < max(TOL[dtype], 2e-3 if name == 'few_hard' else 0.0)
 
 
 @pytest.mark.parametrize('n', [0, 1, 7, 4096, 1024 * 2048 + 3])

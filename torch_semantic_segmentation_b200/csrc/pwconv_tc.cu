@@ -216,11 +216,19 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
-                float lo[8], hi[8];
+                // 16 bf16 = one full 32-byte sector per thread and store instruction (st.global.v8.b32)
+                uint32_t o[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
-                store8(Y + row * ldy + col, lo);
-                store8(Y + row * ldy + col + 8, hi);
+                for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                bf16* dst = Y + row * ldy + col;
+                if ((((uintptr_t)dst) & 31) == 0) {
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                                 ::"l"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                                 : "memory");
+                } else {
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
