@@ -336,17 +336,26 @@ def main():
     e2e_value = world * BATCH * args.steps / (float(ems) / 1e3)
 
     def finish():
-        # every rank meets here (rank 0 after the single-rank roofline / CPU legs), tears the group
-        # down together, and a stuck teardown can never outlive the printed result
+        # All collectives of this run are behind us (the last one is the MAX of the e2e time) and the
+        # result line is printed: multi-rank processes leave without the NCCL teardown handshake, which
+        # can block for minutes when the ranks arrive far apart (rank 0 still runs its single-rank
+        # roofline / CPU legs) -- a stuck teardown must never outlive the measurement.
         sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            import signal
-            signal.signal(signal.SIGALRM, lambda *_: os._exit(0))
-            signal.alarm(300)
-            dist.barrier()
-            signal.alarm(30)
-            dist.destroy_process_group()
-            signal.alarm(0)
+            # the other ranks stay alive (CPU-side wait on the rendezvous store) until rank 0 is done, so
+            # that no NCCL peer disappears under a rank that is still working
+            import datetime
+            try:
+                store = dist.distributed_c10d._get_default_store()
+                if rank == 0:
+                    store.set('tss_bench_done', '1')
+                    time.sleep(0.5)
+                else:
+                    store.wait(['tss_bench_done'], datetime.timedelta(seconds=240))
+            except Exception:
+                pass
+            os._exit(0)
 
     if rank != 0:
         finish()

@@ -167,13 +167,9 @@ def main():
         dist.init_process_group('nccl', init_method='env://', device_id=device)
     {3: config3, 4: config4, 5: config5}[args.config](args, rank, world, device)
     sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        import signal
-        signal.signal(signal.SIGALRM, lambda *_: os._exit(0))
-        signal.alarm(120)
-        dist.barrier()
-        dist.destroy_process_group()
-        signal.alarm(0)
+        os._exit(0)      # no NCCL teardown handshake after the result is out
 
 
 if __name__ == '__main__':
