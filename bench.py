@@ -173,9 +173,11 @@ def time_kernel(fn, iters=20, flush=None):
     return max(both - only, 1e-6)
 
 
-def kernel_table(device):
+def kernel_table(device, runner=None):
     """Per-launch time and algorithmic bytes (SURVEY.md section 8d formulas) of the kernels of one
-    training step at the TRN shapes, each timed alone.  Returns rows sorted by share of the step."""
+    training step at the TRN shapes, each timed alone.  Returns rows sorted by share of the step.
+    `runner(name, launches_per_step, algorithmic_bytes, fn)` replaces the timing (tools/run_kernels.py
+    launches every op once under ncu with it)."""
     from torch_semantic_segmentation_b200 import ops
     bf = torch.bfloat16
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
@@ -186,6 +188,9 @@ def kernel_table(device):
         return ops.empty_nhwc(N, C, CROP // div, CROP // div, bf, device).normal_()
 
     def add(name, count, nbytes, fn):
+        if runner is not None:
+            runner(name, count, nbytes, fn)
+            return
         ms = time_kernel(fn, 10, flush)
         rows.append({'kernel': name, 'launches_per_step': count, 'ms': ms, 'bytes': nbytes,
                      'gbs': nbytes / ms / 1e6, 'share_ms': ms * count})
@@ -209,7 +214,8 @@ def kernel_table(device):
     # BatchNorm apply / backward on the largest activation (32 ch @ 1/2)
     sc = torch.ones(32, device=device)
     add('bn_apply 32ch@1/2', 1, 2 * 2 * 32 * px(2), lambda: ops.bn_apply(y2, sc, sc, relu=True))
-    add('bn_backward 32ch@1/2 (2 kernels)', 1, 2 * 32 * px(2) * (3 + 4), lambda: ops.bn_backward(y2, y2, y2, sc, sc, sc, True))
+    # backward = reduce (reads dz, y) + apply (reads dz, y, writes dy); the ReLU mask is recomputed from y
+    add('bn_backward 32ch@1/2 (2 kernels)', 1, 2 * 32 * px(2) * (2 + 3), lambda: ops.bn_backward(y2, None, y2, sc, sc, sc, True, beta=sc))
     # depthwise: the biggest (32 ch, s2, 1/2 -> 1/4) and the classifier / fusion size (128 ch @ 1/8)
     for C, div, s, d, cnt in [(32, 2, 2, 1, 1), (128, 8, 1, 1, 2), (128, 8, 1, 4, 1), (384, 8, 2, 1, 1), (384, 16, 1, 1, 2)]:
         xi = act(C, div)
@@ -369,8 +375,14 @@ def main():
             print('%-44s x%d  %8.3f ms  %8.1f MB  %7.0f GB/s  share %7.3f ms' % (
                 r['kernel'], r['launches_per_step'], r['ms'], r['bytes'] / 1e6, r['gbs'], r['share_ms']), file=sys.stderr)
     top = rows[0]
+    traffic = None        # dram__bytes_read.sum + dram__bytes_write.sum of the same op from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')) as f:
+            traffic = json.load(f).get(top['kernel'], {}).get('dram_bytes')
+    except Exception:
+        traffic = None
     roofline = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['gbs'], 'peak': peak, 'unit': 'GB/s',
-                'frac': top['gbs'] / peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': top['gbs'] / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'launch_ms': top['ms'], 'algorithmic_bytes': top['bytes']}
 
     cpu = None

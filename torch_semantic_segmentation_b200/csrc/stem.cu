@@ -3,7 +3,8 @@
 // pre-pass over the largest input tensor); output is NHWC in the activation dtype.
 // K = 27 is too small/awkward for a tensor-core tile, and the layer is bound by its
 // 2 x 113 MB (TRN) of output traffic plus 864 FMA per pixel, so this is a SIMT kernel:
-//   fwd  : one thread per output pixel, 32 accumulators, weights broadcast from smem.
+//   fwd  : one thread per pair of adjacent output pixels, 2 x 16 float2 accumulators (FFMA2 over
+//          channel pairs), weights broadcast from smem as 128-bit loads shared by both pixels.
 //   wgrad: persistent CTAs; per 8x32 pixel tile the input patch and dy tile are staged in
 //          shared memory, thread = (4 output channels, 1 input channel, pixel split) keeps
 //          36 accumulators; one cross-split reduction and 864 atomics per CTA at the end.
@@ -29,63 +30,89 @@ stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __r
     if (threadIdx.x < 2 * CO) s_stat[threadIdx.x] = 0.f;
     __syncthreads();
 
-    const int64_t total = (int64_t)N * Ho * Wo;
+    // a thread owns TWO horizontally adjacent output pixels: every 128-bit weight load from shared
+    // memory (the limiter of this layer: 216 of them per pixel) feeds 8 FMAs instead of 4, and the
+    // two 3x3 windows share one of their three input columns
+    const int Wp = (Wo + 1) >> 1;
+    const int64_t total = (int64_t)N * Ho * Wp;
     const int64_t p = (int64_t)blockIdx.x * kFwdThreads + threadIdx.x;
     const bool valid = p < total;
-    float acc[CO];
+    float2 acc[2][CO / 2];                     // [pixel][channel pair]: FFMA2
 #pragma unroll
-    for (int c = 0; c < CO; ++c) acc[c] = 0.f;
-
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int c = 0; c < CO / 2; ++c) acc[q][c] = make_float2(0.f, 0.f);
+    int wo = 0, ho = 0, n = 0;
+    bool second = false;
     if (valid) {
         int64_t t = p;
-        const int wo = (int)(t % Wo); t /= Wo;
-        const int ho = (int)(t % Ho);
-        const int n = (int)(t / Ho);
-        float in[27];
+        wo = (int)(t % Wp) * 2; t /= Wp;
+        ho = (int)(t % Ho);
+        n = (int)(t / Ho);
+        second = wo + 1 < Wo;
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
                 const int hi = 2 * ho - 1 + ky;
+                const bool row_ok = hi >= 0 && hi < H;
+                const float* xr = x + (((int64_t)n * 3 + ci) * H + hi) * W;
+                float in[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int wi = 2 * wo - 1 + j;
+                    in[j] = (row_ok && wi >= 0 && wi < W) ? __ldg(xr + wi) : 0.f;
+                }
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    const int wi = 2 * wo - 1 + kx;
-                    const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
-                    in[ci * 9 + ky * 3 + kx] = ok ? __ldg(x + (((int64_t)n * 3 + ci) * H + hi) * W + wi) : 0.f;
+                    const int tp = ci * 9 + ky * 3 + kx;
+                    const float2 i0 = make_float2(in[kx], in[kx]), i1 = make_float2(in[kx + 2], in[kx + 2]);
+#pragma unroll
+                    for (int c4 = 0; c4 < CO / 4; ++c4) {
+                        const float4 wv = *reinterpret_cast<const float4*>(&ws[tp][c4 * 4]);
+                        const float2 wa = make_float2(wv.x, wv.y), wb = make_float2(wv.z, wv.w);
+                        acc[0][c4 * 2 + 0] = ffma2(i0, wa, acc[0][c4 * 2 + 0]);
+                        acc[0][c4 * 2 + 1] = ffma2(i0, wb, acc[0][c4 * 2 + 1]);
+                        acc[1][c4 * 2 + 0] = ffma2(i1, wa, acc[1][c4 * 2 + 0]);
+                        acc[1][c4 * 2 + 1] = ffma2(i1, wb, acc[1][c4 * 2 + 1]);
+                    }
                 }
             }
+        if (!second) {
 #pragma unroll
-        for (int tp = 0; tp < 27; ++tp) {
-#pragma unroll
-            for (int c4 = 0; c4 < CO / 4; ++c4) {
-                const float4 wv = *reinterpret_cast<const float4*>(&ws[tp][c4 * 4]);
-                acc[c4 * 4 + 0] = fmaf(in[tp], wv.x, acc[c4 * 4 + 0]);
-                acc[c4 * 4 + 1] = fmaf(in[tp], wv.y, acc[c4 * 4 + 1]);
-                acc[c4 * 4 + 2] = fmaf(in[tp], wv.z, acc[c4 * 4 + 2]);
-                acc[c4 * 4 + 3] = fmaf(in[tp], wv.w, acc[c4 * 4 + 3]);
-            }
+            for (int c = 0; c < CO / 2; ++c) acc[1][c] = make_float2(0.f, 0.f);
         }
-        T* yp = y + p * CO;
+        T* yp = y + (((int64_t)n * Ho + ho) * Wo + wo) * CO;
 #pragma unroll
-        for (int c8 = 0; c8 < CO / 8; ++c8) {
-            float o[8];
+        for (int q = 0; q < 2; ++q) {
+            if (q == 1 && !second) break;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float v = acc[c8 * 8 + e];
-                if (shift != nullptr) v = fmaf(v, scale != nullptr ? __ldg(scale + c8 * 8 + e) : 1.f, __ldg(shift + c8 * 8 + e));
-                if (relu) v = fmaxf(v, 0.f);
-                o[e] = v;
+            for (int c8 = 0; c8 < CO / 8; ++c8) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float2 a2 = acc[q][c8 * 4 + (e >> 1)];
+                    float v = (e & 1) ? a2.y : a2.x;
+                    if (shift != nullptr) v = fmaf(v, scale != nullptr ? __ldg(scale + c8 * 8 + e) : 1.f, __ldg(shift + c8 * 8 + e));
+                    if (relu) v = fmaxf(v, 0.f);
+                    o[e] = v;
+                }
+                store8(yp + q * CO + c8 * 8, o);
             }
-            store8(yp + c8 * 8, o);
         }
     }
 
-    if (stats != nullptr) {     // raw (pre-affine) output statistics; invalid threads hold zeros
+    if (stats != nullptr) {     // raw (pre-affine) output statistics; invalid threads / pixels hold zeros
         const int lane = threadIdx.x & 31;
-        float sq[CO];
+        float sm[CO], sq[CO];
 #pragma unroll
-        for (int c = 0; c < CO; ++c) sq[c] = acc[c] * acc[c];
-        const float s1 = warp_transpose_sum32(acc, lane);
+        for (int c = 0; c < CO / 2; ++c) {
+            sm[2 * c] = acc[0][c].x + acc[1][c].x;
+            sm[2 * c + 1] = acc[0][c].y + acc[1][c].y;
+            sq[2 * c] = fmaf(acc[0][c].x, acc[0][c].x, acc[1][c].x * acc[1][c].x);
+            sq[2 * c + 1] = fmaf(acc[0][c].y, acc[0][c].y, acc[1][c].y * acc[1][c].y);
+        }
+        const float s1 = warp_transpose_sum32(sm, lane);
         const float s2 = warp_transpose_sum32(sq, lane);
         atomicAdd(&s_stat[lane], s1);
         atomicAdd(&s_stat[CO + lane], s2);
@@ -192,7 +219,7 @@ extern "C" int tss_stem3x3s2_fwd(const float* x, const float* w, void* y, int N,
     TSS_REQUIRE(Cout == CO, "stem3x3s2_fwd: Cout=%d unsupported (only %d)", Cout, CO);
     TSS_REQUIRE(scale == nullptr || shift != nullptr, "stem3x3s2_fwd: scale without shift");
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    const int64_t total = (int64_t)N * Ho * Wo;
+    const int64_t total = (int64_t)N * Ho * ((Wo + 1) / 2);        // a thread owns two adjacent output pixels
     TSS_DISPATCH_DTYPE(dtype, "stem3x3s2_fwd", {
         tss_launch(stem_fwd_kernel<T>, (unsigned)ceil_div64(total, kFwdThreads), kFwdThreads, 0, (cudaStream_t)stream, 
             x, w, (T*)y, N, H, W, Ho, Wo, scale, shift, flags & TSS_EPI_RELU, stats);
