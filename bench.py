@@ -29,6 +29,8 @@ METRIC = 'fastscnn_train_images_per_sec'
 UNIT = 'img/s'
 BATCH, CROP, CLASSES = 12, 768, 19
 CPU_SAMPLE_BATCH = 2
+WORKLOAD = ('Fast-SCNN training step (fwd + CE ignore_index=255 + bwd + grad all-reduce + AdamW), '
+            '19 classes, 12 crops of 768x768 per GPU, random-init weights')
 
 
 def parse():
@@ -83,8 +85,8 @@ def run_reference(args, rank):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warmup, 'ms_per_step': spt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'Fast-SCNN train step (fwd+CE ignore255+bwd+AdamW), 19 classes, 768x768 crops',
-                   'per_gpu_batch': BATCH, 'sample_batch': CPU_SAMPLE_BATCH},
+        'config': {'workload': WORKLOAD, 'global_batch': max(args.gpus, 1) * BATCH, 'parallelism': 'dp%d' % max(args.gpus, 1),
+                   'cpu_sample': 'each step = %d of the %d crops of one rank, stock PyTorch fp32 on the host cores' % (CPU_SAMPLE_BATCH, BATCH)},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
@@ -221,7 +223,7 @@ def kernel_table(device, runner=None):
         xi = act(C, div)
         wd = torch.randn(C, 1, 3, 3, device=device)
         sd = torch.zeros(2 * C, dtype=torch.float64, device=device)
-        yo = ops.dwconv_fwd(xi, wd, s, d)
+        yo = act(C, div * s)             # a gradient of the output's shape
         io = 2 * C * (px(div) + px(div * s))
         add('dwconv_fwd C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_fwd(xi, wd, s, d, stats=sd))
         add('dwconv_dgrad C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_dgrad(yo, wd, xi.shape[2], xi.shape[3], s, d))
@@ -396,8 +398,7 @@ def main():
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': 'Fast-SCNN training step (fwd + CE ignore_index=255 + bwd + grad all-reduce + AdamW), '
-                               '19 classes, 12 crops of 768x768 per GPU, random-init weights',
+        'config': {'workload': WORKLOAD,
                    'global_batch': world * BATCH, 'parallelism': 'dp%d' % world,
                    'l2': 'per-step working set (>3 GB of activations) far exceeds the 126 MB L2',
                    'launch_mode': 'cuda_graph' if use_graph else 'eager'},
