@@ -144,11 +144,13 @@ int tss_bn_apply(const void* y, const float* scale, const float* shift, const vo
 int tss_bn_bwd_reduce(const void* dz, const void* z, const void* y, const float* mean,
                       const float* rstd, const float* gamma, const float* beta, float* sums, int64_t M,
                       int C, int64_t lddz, int64_t ldz, int64_t ldy, int flags, int dtype, void* stream);
-/* backward, pass 2: dy = gamma*rstd*(g - sums[c]/M - xhat*sums[C+c]/M); optional dres = g.
- * dgamma[c] += sums[C+c], dbeta[c] += sums[c] (done by block 0; may be NULL). */
+/* backward, pass 2: dy = gamma*rstd*(g - sums[c]/count - xhat*sums[C+c]/count); optional dres = g.
+ * dgamma[c] += sums[C+c], dbeta[c] += sums[c] (done by block 0; may be NULL).  count = values per
+ * channel behind the statistics: 0 = the M rows of this call; M*world_size when the statistics and
+ * `sums` were all-reduced over a process group (SyncBN). */
 int tss_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean,
                      const float* rstd, const float* gamma, const float* beta, const float* sums, void* dy, void* dres,
-                     float* dgamma, float* dbeta, int64_t M, int C, int64_t lddz, int64_t ldz,
+                     float* dgamma, float* dbeta, int64_t M, int64_t count, int C, int64_t lddz, int64_t ldz,
                      int64_t ldy, int64_t lddy, int64_t lddres, int flags, int dtype, void* stream);
 /* g = dz * (z > 0): ReLU backward alone (fusion add, eval-free paths) */
 int tss_relu_bwd(const void* dz, const void* z, void* g, int64_t M, int C, int64_t lddz, int64_t ldz,

@@ -174,8 +174,9 @@ class FakeBackend:
         sums[C:] += (g * xh).sum(dim=(0, 2, 3))
         return 0
 
-    def tss_bn_bwd_apply(self, dz, z, y, mean, rstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C, lddz, ldz,
+    def tss_bn_bwd_apply(self, dz, z, y, mean, rstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, count, C, lddz, ldz,
                          ldy, lddy, lddres, flags, dtype):
+        M = count if count > 0 else M
         g = self._g(dz, z, flags, y, mean, rstd, gamma, beta)
         v = lambda t: t.detach().view(1, -1, 1, 1)
         xh = (y.float() - v(mean)) * v(rstd)

@@ -124,6 +124,48 @@ def _eval_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _syncbn_worker(rank, world, port, out):
+    """DP(k ranks, per-rank batch b) with SyncBN == single process on the batch k*b
+    (equal valid-pixel counts per rank, so that the mean of the local mean losses is the global mean)."""
+    _setup(rank, world, port)
+    from torch_semantic_segmentation_b200.distributed import convert_syncbn_model
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+
+    def make():
+        torch.manual_seed(0)
+        m = fastscnn(3, 19)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        return m.train()
+
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2 * world, 3, 64, 64, generator=g)
+    y = torch.randint(0, 19, (2 * world, 64, 64), generator=g)          # no ignored pixels: equal counts per rank
+    loss_fn = CrossEntropyLoss(ignore_index=255)
+    single = make()
+    loss_fn(single(x), y).backward()
+    want = torch.cat([p.grad.reshape(-1) for p in single.parameters()])
+    want_rm = single.downsample[0][1].running_mean.clone()
+
+    model = convert_syncbn_model(make())
+    lo = 2 * rank
+    loss = loss_fn(model(x[lo:lo + 2]), y[lo:lo + 2])
+    loss.backward()
+    got = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    dist.all_reduce(got)
+    got /= world                                                          # what the gradient all-reduce + 1/world does
+    err = float((got - want).norm() / want.norm())
+    rm_err = float((model.downsample[0][1].running_mean - want_rm).abs().max())
+    head, head_ref = model.classifier[3].weight.grad.clone(), single.classifier[3].weight.grad
+    dist.all_reduce(head)
+    head_err = float((head / world - head_ref).norm() / head_ref.norm())
+    if rank == 0:
+        torch.save({'err': err, 'rm_err': rm_err, 'head_err': head_err}, out)
+    dist.destroy_process_group()
+
+
 def _run(worker, tmp_path):
     out = str(tmp_path / 'result.pt')
     mp.spawn(worker, args=(2, _free_port(), out), nprocs=2, join=True)
@@ -142,6 +184,14 @@ def test_bucketed_gradient_allreduce_world2(tmp_path):
 def test_confusion_matrix_shards_sum_exactly_world2(tmp_path):
     r = _run(_eval_worker, tmp_path)
     assert r['equal'] and r['miou_equal'] and r['shard'] == (0, 4) and r['count'] > 0
+
+
+@pytest.mark.timeout(600)
+def test_syncbn_matches_single_process_on_the_concatenated_batch_world2(tmp_path):
+    r = _run(_syncbn_worker, tmp_path)
+    assert r['rm_err'] < 1e-6, r           # the statistics are those of the whole batch
+    assert r['head_err'] < 1e-4, r         # the well-conditioned head gradient
+    assert r['err'] < 1e-2, r              # all gradients (near-cancellations in front of the BN layers: fp32 noise)
 
 
 def test_shard_range_is_a_padding_free_partition():

@@ -89,9 +89,13 @@ def config4(args, rank, world, device):
 
     n_maps = args.maps
     lo, hi = shard_range(n_maps, world, rank)
-    maps = [synth_map(i, device) for i in range(lo, hi)]        # staged in HBM: 32 MB per pair
+    pairs = [synth_map(i, device) for i in range(lo, hi)]       # staged in HBM: 32 MB per pair
+    # evaluation batches of up to 16 maps (one kernel launch per batch, like a val loader with batch 16)
+    maps = [(torch.stack([p for p, _ in pairs[i:i + 16]]), torch.stack([l for _, l in pairs[i:i + 16]]))
+            for i in range(0, len(pairs), 16)]
+    del pairs
     cm = ConfusionMatrix(CLASSES, device=device)
-    for p, l in maps[:2]:
+    for p, l in maps[:1]:
         cm.update((p, l))
     cm.reset()
 

@@ -393,15 +393,16 @@ extern "C" int tss_bn_bwd_reduce(const void* dz, const void* z, const void* y, c
 
 extern "C" int tss_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* mean,
                                 const float* rstd, const float* gamma, const float* beta, const float* sums,
-                                void* dy, void* dres, float* dgamma, float* dbeta, int64_t M, int C, int64_t lddz,
-                                int64_t ldz, int64_t ldy, int64_t lddy, int64_t lddres, int flags, int dtype,
-                                void* stream) {
+                                void* dy, void* dres, float* dgamma, float* dbeta, int64_t M, int64_t count, int C,
+                                int64_t lddz, int64_t ldz, int64_t ldy, int64_t lddy, int64_t lddres, int flags,
+                                int dtype, void* stream) {
     if (int e = check_rows("bn_bwd_apply", M, C)) return e;
+    if (count <= 0) count = M;
     const int relu = flags & TSS_EPI_RELU;
     TSS_DISPATCH_DTYPE(dtype, "bn_bwd_apply", {
         tss_launch(bn_bwd_apply_kernel<T>, stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream, 
             (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, beta, sums, (T*)dy, (T*)dres, dgamma, dbeta,
-            M, C, lddz, ldz, ldy, lddy, lddres, relu, (float)(1.0 / (double)M));
+            M, C, lddz, ldz, ldy, lddy, lddres, relu, (float)(1.0 / (double)count));
         TSS_LAUNCH_CHECK("bn_bwd_apply");
         return TSS_OK;
     });

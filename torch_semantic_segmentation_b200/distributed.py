@@ -21,7 +21,9 @@ import torch.distributed as dist
 
 from . import functional as Fn
 
-__all__ = ['setup_distributed', 'broadcast_parameters', 'GradientAllReducer', 'shard_range']
+from .nn.blocks import convert_syncbn_model  # noqa: F401  (re-export: the apex name the scripts use)
+
+__all__ = ['setup_distributed', 'broadcast_parameters', 'GradientAllReducer', 'shard_range', 'convert_syncbn_model']
 
 
 def setup_distributed(enable=True, local_rank=0, backend=None):

@@ -142,6 +142,15 @@ def conv_forward(spec, x, weight, scale=None, shift=None, res=None, relu=False, 
     raise RuntimeError('unknown conv kind %r' % spec.kind)
 
 
+def _sync_group(bn):
+    """-> (world size, process group) if this BatchNorm layer synchronises its statistics across ranks."""
+    sync = getattr(bn, '_tss_sync', None)
+    if sync is None or not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return 1, None
+    group = None if sync is True else sync
+    return torch.distributed.get_world_size(group), group
+
+
 class ConvBNAct(torch.autograd.Function):
     """z = act(BN_train(conv(x, w)) [+ res])."""
 
@@ -155,7 +164,13 @@ class ConvBNAct(torch.autograd.Function):
         scratch = ops.layer_scratch(bn, weight.device)
         y = conv_forward(spec, x, weight, stats=scratch, packed=packed)
         N, _, H, W = y.shape
-        scale, shift, mean, rstd = ops.bn_finalize(scratch, N * H * W, bn, float(bn.momentum), float(bn.eps),
+        world, group = _sync_group(bn)
+        if world > 1:
+            # SyncBN (apex convert_syncbn_model, scripts/train_fastscnn.py:145): the per-channel sums of
+            # all ranks, one fp64 all-reduce per layer; every rank holds the same number of pixels
+            torch.distributed.all_reduce(scratch[:2 * C], group=group)
+        ctx.sync = (world, group)
+        scale, shift, mean, rstd = ops.bn_finalize(scratch, N * H * W * world, bn, float(bn.momentum), float(bn.eps),
                                                    update_running=bn.track_running_stats, clear_n=3 * C, C=C)
         bn._tss_dirty = False
         ctx.scratch = scratch
@@ -188,7 +203,7 @@ class ConvBNAct(torch.autograd.Function):
             sums = None      # a second backward without a forward in between: fresh zeros
         spec.bn._tss_dirty = True
         dy, dres = ops.bn_backward(dz, z, y, mean, rstd, gamma, spec.relu, want_dres=want_dres,
-                                   dgamma=gg_out, dbeta=gb_out, beta=beta, sums=sums)
+                                   dgamma=gg_out, dbeta=gb_out, beta=beta, sums=sums, sync=ctx.sync)
         dx = None
         dw = gw if gw is not None else torch.zeros_like(weight)
         # wgrad off the critical chain when it accumulates in place into the optimizer's arena

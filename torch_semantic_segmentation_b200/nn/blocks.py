@@ -206,6 +206,19 @@ class ClassScores(nn.Conv2d):
         return Fn.ConvBias.apply(x, self.weight, self.bias)
 
 
+def convert_syncbn_model(module, process_group=None):
+    """Counterpart of ``apex.parallel.convert_syncbn_model`` (scripts/train_fastscnn.py:145): every
+    BatchNorm2d of the fused blocks normalises with the statistics of ALL ranks' batches (one fp64
+    all-reduce of the 2C channel sums per layer in forward, one fp32 all-reduce of the 2C gradient
+    sums per layer in backward).  Every rank must hold the same number of pixels per step.  The
+    module is modified in place and returned.  Per-rank statistics (the default) avoid these 88
+    latency-bound collectives per step; see DESIGN.md section 6."""
+    for m in module.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m._tss_sync = True if process_group is None else process_group
+    return module
+
+
 def set_compute_dtype(module, dtype, pw_impl=None):
     """Select the activation storage type (fp32 verification mode / bf16) of every fused block."""
     if dtype not in (torch.float32, torch.bfloat16):

@@ -253,7 +253,7 @@ def bn_apply(y, scale, shift, y2=None, scale2=None, shift2=None, res=None, relu=
 
 
 def bn_backward(dz, z, y, mean, rstd, gamma, relu, want_dres=False, dgamma=None, dbeta=None, beta=None,
-                sums=None):
+                sums=None, sync=None):
     """-> dy, dres (or None).  dgamma/dbeta (fp32 (C,)) are accumulated into.  ``z=None`` with
     ``relu``: the ReLU mask is recomputed from ``y`` (needs ``beta``; no residual before the ReLU)."""
     N, C, H, W, lddz = _g(dz, 'bn_backward')
@@ -267,10 +267,21 @@ def bn_backward(dz, z, y, mean, rstd, gamma, relu, want_dres=False, dgamma=None,
     _lib.call('tss_bn_bwd_reduce', dz=dz, z=z if relu else None, y=y, mean=mean, rstd=rstd, gamma=gamma,
               beta=beta, sums=sums,
               M=M, C=C, lddz=lddz, ldz=ldz, ldy=ldy, flags=fl, dtype=code)
+    world = 1
+    if sync is not None and sync[0] > 1:
+        # SyncBN backward: dgamma / dbeta are the LOCAL sums (the data-parallel all-reduce averages them
+        # like every other gradient); the input gradient needs the sums over ALL ranks' pixels
+        world = sync[0]
+        if dbeta is not None:
+            dbeta += sums[:C]
+        if dgamma is not None:
+            dgamma += sums[C:]
+        dgamma = dbeta = None
+        torch.distributed.all_reduce(sums, group=sync[1])
     dy = empty_nhwc(N, C, H, W, dz.dtype, dz.device)
     dres = empty_nhwc(N, C, H, W, dz.dtype, dz.device) if want_dres else None
     _lib.call('tss_bn_bwd_apply', dz=dz, z=z if relu else None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta,
-              sums=sums, dy=dy, dres=dres, dgamma=dgamma, dbeta=dbeta, M=M, C=C, lddz=lddz, ldz=ldz,
+              sums=sums, dy=dy, dres=dres, dgamma=dgamma, dbeta=dbeta, M=M, count=M * world, C=C, lddz=lddz, ldz=ldz,
               ldy=ldy, lddy=C, lddres=C, flags=fl, dtype=code)
     return dy, dres
 
