@@ -175,6 +175,25 @@ def time_kernel(fn, iters=20, flush=None):
     return max(both - only, 1e-6)
 
 
+def kernel_family(op):
+    """The CUDA kernel function an op of the table runs (ops that launch the same kernel share a family)."""
+    if op.startswith('pwconv_wgrad'):
+        return 'wgrad_tc_kernel (pointwise wgrad, tcgen05)'
+    if op.startswith('pwconv_'):
+        return 'pw_tc_kernel (pointwise fwd + dgrad, tcgen05)'
+    if op.startswith('dwconv_wgrad'):
+        return 'dw_wgrad_tma_kernel (depthwise wgrad)'
+    if op.startswith('dwconv_dgrad') and ' s2 ' in op:
+        return 'dw_dgrad_s2_quad_kernel (depthwise stride-2 dgrad)'
+    if op.startswith('dwconv_'):
+        return 'dw_tma_kernel (depthwise fwd + stride-1 dgrad)'
+    if op.startswith('bn_backward'):
+        return 'bn_bwd_reduce_kernel + bn_bwd_apply_kernel (BatchNorm backward)'
+    if op.startswith('bn_apply'):
+        return 'bn_apply_kernel (BatchNorm forward apply)'
+    return op
+
+
 def kernel_table(device, runner=None):
     """Per-launch time and algorithmic bytes (SURVEY.md section 8d formulas) of the kernels of one
     training step at the TRN shapes, each timed alone.  Returns rows sorted by share of the step.
@@ -218,8 +237,17 @@ def kernel_table(device, runner=None):
     add('bn_apply 32ch@1/2', 1, 2 * 2 * 32 * px(2), lambda: ops.bn_apply(y2, sc, sc, relu=True))
     # backward = reduce (reads dz, y) + apply (reads dz, y, writes dy); the ReLU mask is recomputed from y
     add('bn_backward 32ch@1/2 (2 kernels)', 1, 2 * 32 * px(2) * (2 + 3), lambda: ops.bn_backward(y2, None, y2, sc, sc, sc, True, beta=sc))
-    # depthwise: the biggest (32 ch, s2, 1/2 -> 1/4) and the classifier / fusion size (128 ch @ 1/8)
-    for C, div, s, d, cnt in [(32, 2, 2, 1, 1), (128, 8, 1, 1, 2), (128, 8, 1, 4, 1), (384, 8, 2, 1, 1), (384, 16, 1, 1, 2)]:
+    # BatchNorm passes at the other resolutions (channel count, level, layers of that shape per step)
+    for C, div, cnt in [(32, 4, 1), (48, 4, 1), (48, 8, 1), (64, 8, 1), (128, 8, 7), (384, 8, 1), (384, 16, 6), (64, 16, 3),
+                        (384, 32, 1), (576, 32, 6), (96, 32, 3), (768, 32, 4), (128, 32, 4)]:
+        yb = act(C, div)
+        scb = torch.ones(C, device=device)
+        add('bn_apply %dch@1/%d' % (C, div), cnt, 2 * 2 * C * px(div), lambda: ops.bn_apply(yb, scb, scb, relu=True))
+        add('bn_backward %dch@1/%d (2 kernels)' % (C, div), cnt, 2 * C * px(div) * (2 + 3),
+            lambda: ops.bn_backward(yb, None, yb, scb, scb, scb, True, beta=scb))
+    # depthwise: every shape of the network (channels, input level, stride, dilation, layers of that shape)
+    for C, div, s, d, cnt in [(32, 2, 2, 1, 1), (48, 4, 2, 1, 1), (384, 8, 2, 1, 1), (384, 16, 1, 1, 2), (384, 16, 2, 1, 1),
+                              (576, 32, 1, 1, 3), (768, 32, 1, 1, 2), (128, 8, 1, 4, 1), (128, 8, 1, 1, 2)]:
         xi = act(C, div)
         wd = torch.randn(C, 1, 3, 3, device=device)
         sd = torch.zeros(2 * C, dtype=torch.float64, device=device)
@@ -228,8 +256,11 @@ def kernel_table(device, runner=None):
         add('dwconv_fwd C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_fwd(xi, wd, s, d, stats=sd))
         add('dwconv_dgrad C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_dgrad(yo, wd, xi.shape[2], xi.shape[3], s, d))
         add('dwconv_wgrad C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_wgrad(xi, yo, torch.zeros_like(wd), s, d))
-    # pointwise GEMMs: the tcgen05/TMEM/TMA kernels the bf16 model runs (impl 1)
-    for K, Nc, div, cnt in [(32, 48, 4, 1), (64, 384, 8, 1), (128, 128, 8, 3), (64, 128, 8, 1), (384, 64, 16, 3), (64, 384, 16, 3)]:
+    # pointwise GEMMs: the tcgen05/TMEM/TMA kernels the bf16 model runs (impl 1), every shape of the network
+    # (K -> N, level, layers of that shape)
+    for K, Nc, div, cnt in [(32, 48, 4, 1), (48, 64, 8, 1), (64, 384, 8, 1), (384, 64, 16, 3), (64, 384, 16, 3), (384, 96, 32, 1),
+                            (96, 576, 32, 3), (576, 96, 32, 2), (576, 128, 32, 1), (128, 768, 32, 2), (768, 128, 32, 2),
+                            (256, 128, 32, 1), (128, 128, 8, 3), (64, 128, 8, 1)]:
         xi = act(K, div)
         wp = torch.randn(Nc, K, 1, 1, device=device) * 0.05
         yo = act(Nc, div)
@@ -376,16 +407,33 @@ def main():
         for r in rows:
             print('%-44s x%d  %8.3f ms  %8.1f MB  %7.0f GB/s  share %7.3f ms' % (
                 r['kernel'], r['launches_per_step'], r['ms'], r['bytes'] / 1e6, r['gbs'], r['share_ms']), file=sys.stderr)
-    top = rows[0]
-    traffic = None        # dram__bytes_read.sum + dram__bytes_write.sum of the same op from the committed ncu capture
+    # The dominant KERNEL of the step = the kernel function with the largest summed time over its launches
+    # (the ncu launch list under profiles/ ranks them the same way).  Its roofline figures are per launch,
+    # averaged over the step's launches of that kernel: algorithmic bytes per launch / time per launch.
+    fams = {}
+    for r in rows:
+        f = fams.setdefault(kernel_family(r['kernel']), {'launches': 0, 'ms': 0.0, 'bytes': 0.0, 'ops': []})
+        f['launches'] += r['launches_per_step']
+        f['ms'] += r['ms'] * r['launches_per_step']
+        f['bytes'] += r['bytes'] * r['launches_per_step']
+        f['ops'].append(r['kernel'])
+    name, top = max(fams.items(), key=lambda kv: kv[1]['ms'])
+    traffic = None        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
     try:
         with open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')) as f:
-            traffic = json.load(f).get(top['kernel'], {}).get('dram_bytes')
+            tr = json.load(f)
+        by_op = {r['kernel']: r['launches_per_step'] for r in rows}
+        have = [o for o in top['ops'] if o in tr]
+        if have:
+            traffic = sum(tr[o]['dram_bytes'] * by_op[o] for o in have) / sum(by_op[o] for o in have)
     except Exception:
         traffic = None
-    roofline = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['gbs'], 'peak': peak, 'unit': 'GB/s',
-                'frac': top['gbs'] / peak, 'traffic': traffic, 'peak_source': peak_src,
-                'launch_ms': top['ms'], 'algorithmic_bytes': top['bytes']}
+    gbs = top['bytes'] / top['ms'] / 1e6
+    roofline = {'bound': 'hbm', 'kernel': name, 'achieved': gbs, 'peak': peak, 'unit': 'GB/s',
+                'frac': gbs / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'launch_ms': top['ms'] / top['launches'], 'algorithmic_bytes': top['bytes'] / top['launches'],
+                'launches_per_step': top['launches'], 'share_of_step_ms': top['ms'],
+                'slowest_single_op': {'kernel': rows[0]['kernel'], 'ms': rows[0]['ms'], 'gbs': rows[0]['gbs']}}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
