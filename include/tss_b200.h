@@ -92,6 +92,11 @@ int tss_pwconv_wgrad(const void* x, const void* dy, float* dw, float* db, int64_
                      int64_t ldx, int64_t lddy, int impl, int dtype, void* stream);
 /* bf16 copies of a (Nc,K) fp32 weight: wp[Nc][K] and wpT[K][Nc] (either may be NULL) */
 int tss_pack_weights_bf16(const float* w, void* wp, void* wpT, int Nc, int K, void* stream);
+/* the same for n_entries weights living in one fp32 parameter arena, in ONE launch (after the optimizer
+ * step): table (device int64 [n_entries][5]) = {element offset of the (Nc,K) weight in the arena, Nc, K,
+ * device address of wp, device address of wpT}; max_elems = max Nc*K over the table. */
+int tss_pack_weights_multi(const float* arena, const int64_t* table, int n_entries, int64_t max_elems,
+                           void* stream);
 
 /* ---- dense 3x3 convolution ---------------------------------------------------------------
  * Stem: replaces nn.Conv2d(3, 32, 3, stride=2, padding=1, bias=False) at fastscnn.py:30 /

@@ -86,6 +86,9 @@ class FakeBackend:
             wpT.copy_(w.view(Nc, K).t())
         return 0
 
+    def tss_pack_weights_multi(self, arena, table, n_entries, max_elems):
+        raise NotImplementedError('bf16 tensor-core packs are not used on the CPU emulation')
+
     # ---------------------------------------------------------------- dense 3x3 as a patch GEMM
     def tss_im2col3x3(self, x, col, N, H, W, C, dtype):
         xp = F.pad(x, (1, 1, 1, 1))

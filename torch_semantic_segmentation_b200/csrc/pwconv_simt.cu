@@ -227,6 +227,23 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
     if (wpT != nullptr) wpT[(int64_t)k * Nc + n] = v;
 }
 
+// all pointwise weights of a model in ONE launch: blockIdx.y = table row {offset of the fp32 (Nc,K)
+// weight in the parameter arena, Nc, K, wp pointer, wpT pointer}
+__global__ void pack_weights_multi_kernel(const float* __restrict__ arena, const int64_t* __restrict__ table) {
+    pdl_wait();
+    const int64_t* row = table + (int64_t)blockIdx.y * 5;
+    const float* w = arena + row[0];
+    const int Nc = (int)row[1], K = (int)row[2];
+    bf16* wp = reinterpret_cast<bf16*>(row[3]);
+    bf16* wpT = reinterpret_cast<bf16*>(row[4]);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Nc * K; i += gridDim.x * blockDim.x) {
+        const int n = i / K, k = i - n * K;
+        const bf16 v = __float2bfloat16_rn(w[i]);
+        wp[i] = v;
+        wpT[(int64_t)k * Nc + n] = v;
+    }
+}
+
 }  // namespace
 
 // implemented in pwconv_tc.cu
@@ -313,6 +330,16 @@ extern "C" int tss_pwconv_wgrad(const void* x, const void* dy, float* dw, float*
         TSS_LAUNCH_CHECK("pwconv_wgrad");
         return TSS_OK;
     });
+}
+
+extern "C" int tss_pack_weights_multi(const float* arena, const int64_t* table, int n_entries, int64_t max_elems,
+                                      void* stream) {
+    TSS_REQUIRE(n_entries > 0 && max_elems > 0, "pack_weights_multi: n_entries=%d max_elems=%lld", n_entries, (long long)max_elems);
+    int64_t gx = ceil_div64(max_elems, 256);
+    if (gx > 64) gx = 64;
+    tss_launch(pack_weights_multi_kernel, dim3((unsigned)gx, (unsigned)n_entries), 256, 0, (cudaStream_t)stream, arena, table);
+    TSS_LAUNCH_CHECK("pack_weights_multi");
+    return TSS_OK;
 }
 
 extern "C" int tss_pack_weights_bf16(const float* w, void* wp, void* wpT, int Nc, int K, void* stream) {

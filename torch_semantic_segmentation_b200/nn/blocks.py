@@ -72,6 +72,17 @@ class _FusedConvBN:
         w = self[ci].weight
         if self._kind(self[ci]) != 'pw' or w.shape[0] % 16 != 0 or w.shape[1] % 16 != 0:
             return None
+        opt = getattr(w, '_tss_optimizer', None)
+        if opt is not None:
+            # weight lives in a FlatAdamW arena: persistent packs refreshed by the optimizer's single
+            # multi-tensor launch after each step; only an outside in-place write (load_state_dict)
+            # bumps the tensor version and triggers a re-pack here
+            key = (id(opt), w._version, w.data_ptr())
+            hit = self._pack_cache.get(ci)
+            if hit is None or hit[0] != key:
+                hit = (key, opt.register_pack(w))
+                self._pack_cache[ci] = hit
+            return hit[1]
         key = _versions(w)
         hit = self._pack_cache.get(ci)
         if hit is None or hit[0] != key:

@@ -52,6 +52,7 @@ class FlatAdamW(torch.optim.Optimizer):
                 g = self.grad_arena[off:off + p.numel()].view_as(p)
                 p.grad = g
                 p._tss_grad = g          # kernels accumulate here directly (functional.py)
+                p._tss_optimizer = self  # pointwise blocks register their bf16 packs here (register_pack)
                 self.slots.append((p, off, p.numel()))
         g0 = self.param_groups[0]
         self.hyper = torch.tensor([g0['lr'], g0['betas'][0], g0['betas'][1], g0['eps'], g0['weight_decay'],
@@ -60,6 +61,34 @@ class FlatAdamW(torch.optim.Optimizer):
         if dev.type == 'cuda':
             self._host = self._host.pin_memory()
         self.grad_scale = 1.0          # e.g. 1/world_size after a SUM all-reduce
+        self._offsets = {id(p): off for p, off, _ in self.slots}
+        self._packs = {}               # id(param) -> (wp, wpT): bf16 TMA/UMMA operands of the pointwise convs
+        self._pack_rows = []
+        self._pack_table = None
+        self._pack_max = 0
+
+    def register_pack(self, p):
+        """Persistent bf16 copies (W, W^T) of a pointwise weight that lives in the arena.  They are packed
+        now and then refreshed by ONE multi-tensor launch after every ``step()`` (instead of one launch per
+        layer per forward), at fixed addresses (CUDA-graph friendly)."""
+        hit = self._packs.get(id(p))
+        if hit is None:
+            Nc, K = p.shape[0], p[0].numel()
+            wp = torch.empty((Nc, K), dtype=torch.bfloat16, device=p.device)
+            wpT = torch.empty((K, Nc), dtype=torch.bfloat16, device=p.device)
+            hit = self._packs[id(p)] = (wp, wpT)
+            self._pack_rows.append([self._offsets[id(p)], Nc, K, wp.data_ptr(), wpT.data_ptr()])
+            self._pack_table = torch.tensor(self._pack_rows, dtype=torch.int64, device=p.device)
+            self._pack_max = max(self._pack_max, Nc * K)
+        from . import _lib
+        _lib.call('tss_pack_weights_bf16', w=p.detach(), wp=hit[0], wpT=hit[1], Nc=hit[0].shape[0], K=hit[0].shape[1])
+        return hit
+
+    def _repack(self):
+        if self._pack_table is not None:
+            from . import _lib
+            _lib.call('tss_pack_weights_multi', arena=self.param_arena, table=self._pack_table,
+                      n_entries=len(self._pack_rows), max_elems=self._pack_max)
 
     def zero_grad(self, set_to_none=False):
         """One memset; the gradient views stay attached (``set_to_none`` is ignored)."""
@@ -87,6 +116,7 @@ class FlatAdamW(torch.optim.Optimizer):
         self._refresh_hyper()
         ops.adamw_step(self.param_arena, self.grad_arena, self.exp_avg, self.exp_avg_sq, self.hyper,
                        self.grad_scale)
+        self._repack()
         return loss
 
     @property
