@@ -230,17 +230,29 @@ upsample_logits_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int Hi, i
         s_row[i] = (1.f - lh) * to_f32(r0[w * ldx + c]) + lh * to_f32(r1[w * ldx + c]);
     }
     __syncthreads();
+    // a thread keeps ONE group of 8 output columns and walks the classes: the column geometry (source
+    // offsets and weights) is computed once into registers and reused for every class plane
     const int groups = Wo >> 3;
-    for (int i = threadIdx.x; i < groups * C; i += kThreads) {
-        const int c = i / groups, g = i - c * groups;
-        float o[8];
+    const int lanes = kThreads / groups > 0 ? kThreads / groups : 1;     // threads sharing one column group
+    const int lane = threadIdx.x / groups;                               // (0 when there are more groups than threads)
+    if (lane < lanes) {
+        for (int g = threadIdx.x % groups; g < groups; g += kThreads) {
+            int o0[8], o1[8];
+            float lw[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            int w0, w1; float lw;
-            ac_source(sw, g * 8 + e, Wi, w0, w1, lw);
-            o[e] = (1.f - lw) * s_row[w0 * C + c] + lw * s_row[w1 * C + c];
+            for (int e = 0; e < 8; ++e) {
+                int w0, w1;
+                ac_source(sw, g * 8 + e, Wi, w0, w1, lw[e]);
+                o0[e] = w0 * C;
+                o1[e] = w1 * C;
+            }
+            for (int c = lane; c < C; c += lanes) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = (1.f - lw[e]) * s_row[o0[e] + c] + lw[e] * s_row[o1[e] + c];
+                store8(y + (((int64_t)n * C + c) * Ho + ho) * Wo + g * 8, o);
+            }
         }
-        store8(y + (((int64_t)n * C + c) * Ho + ho) * Wo + g * 8, o);
     }
 }
 
