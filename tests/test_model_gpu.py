@@ -332,3 +332,16 @@ def test_flat_adamw_keeps_the_bf16_weight_packs_in_sync():
         model(x.cuda())
     torch.cuda.synchronize()
     assert torch.equal(opt._packs[id(w)][0], w.detach().reshape(w.shape[0], -1).to(torch.bfloat16))
+
+
+def test_graphed_evaluator_matches_eager():
+    model = make_model(torch.bfloat16)
+    x, y = train_batch('fastscnn')
+    data = [(x, y), (x.flip(0), y.flip(0)), (x, y)]
+    eager = create_segmentation_evaluator(model, 'cuda', num_classes=19).run(data)
+    ev = create_segmentation_evaluator(model, 'cuda', num_classes=19, cuda_graph=True)
+    graphed = ev.run(data)
+    assert torch.equal(graphed.metrics['confusion_matrix'], eager.metrics['confusion_matrix'])
+    assert float(graphed.metrics['miou']) == float(eager.metrics['miou'])
+    again = ev.run(data[:1])                                   # a second epoch: the matrix starts from zero again
+    assert int(again.metrics['confusion_matrix'].sum()) * 3 == int(eager.metrics['confusion_matrix'].sum())

@@ -246,6 +246,49 @@ class GraphedTrainStep:
         return self.loss
 
 
+class GraphedEvalStep:
+    """Inference forward + confusion-matrix update captured as ONE CUDA graph per batch shape (the eval
+    forward is ~55 kernels of 5-20 us: launched eagerly from Python it is host-bound at small batches)."""
+
+    def __init__(self, model, cm, x, y, warmup=2):
+        dev = x.device
+        self.x, self.y = torch.empty_like(x), torch.empty_like(y)
+        self.x.copy_(x)
+        self.y.copy_(y)
+        self.key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype)
+        cm._ensure(dev)
+        keep = cm.cm.clone()
+
+        def body():
+            with torch.no_grad():
+                out = model(self.x)
+                cm.update((out, self.y))
+            return out
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = body()
+        torch.cuda.synchronize(dev)
+        cm.cm.copy_(keep)                 # warm-up and capture did not count
+        cm.num_examples -= (warmup + 1) * y.shape[0]
+
+    def matches(self, x, y):
+        return (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype) == self.key
+
+    def __call__(self, x, y, non_blocking=True):
+        self.x.copy_(x, non_blocking=non_blocking)
+        self.y.copy_(y, non_blocking=non_blocking)
+        self.graph.replay()
+        return self.out, self.y
+
+
 # ------------------------------------------------------------------ the two factories -------
 def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False, logging=True,
                                 non_blocking=True, cuda_graph=False, prefetch=True):
@@ -321,14 +364,28 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
     return trainer
 
 
-def create_segmentation_evaluator(model, device, num_classes=19, loss_fn=None, non_blocking=True):
+def create_segmentation_evaluator(model, device, num_classes=19, loss_fn=None, non_blocking=True,
+                                  cuda_graph=False):
     """reference: engine.py:59-82.  ``state.metrics`` gets 'iou', 'miou', 'accuracy', 'dice'
-    (float64 tensors / scalars, ignite formulas) and, with ``loss_fn``, 'loss'."""
+    (float64 tensors / scalars, ignite formulas) and, with ``loss_fn``, 'loss'.  ``cuda_graph=True`` (an
+    addition, without ``loss_fn``) replays forward + confusion-matrix update as one CUDA graph per batch
+    shape; the returned ``y_pred`` is then the graph's output buffer (overwritten by the next batch)."""
     cm = M.ConfusionMatrix(num_classes)
     loss_acc = {'sum': None, 'n': 0}
+    graphs = {}
 
     def eval_fn(_evaluator, batch):
         model.eval()
+        if cuda_graph and loss_fn is None:
+            x, y = batch
+            key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype)
+            g = graphs.get(key)
+            if g is None:
+                xd, yd = _prepare_batch(batch, device=device, non_blocking=non_blocking)
+                g = graphs[key] = GraphedEvalStep(model, cm, xd, yd)
+            out = g(x, y, non_blocking)
+            cm.num_examples += y.shape[0]
+            return out
         with torch.no_grad():
             x, y = _prepare_batch(batch, device=device, non_blocking=non_blocking)
             y_pred = model(x)
