@@ -236,15 +236,16 @@ def kernel_table(device, runner=None):
     sc = torch.ones(32, device=device)
     add('bn_apply 32ch@1/2', 1, 2 * 2 * 32 * px(2), lambda: ops.bn_apply(y2, sc, sc, relu=True))
     # backward = reduce (reads dz, y) + apply (reads dz, y, writes dy); the ReLU mask is recomputed from y
-    add('bn_backward 32ch@1/2 (2 kernels)', 1, 2 * 32 * px(2) * (2 + 3), lambda: ops.bn_backward(y2, None, y2, sc, sc, sc, True, beta=sc))
+    g2 = act(32, 2)                   # the incoming gradient: a tensor of its own (dz and y are distinct streams)
+    add('bn_backward 32ch@1/2 (2 kernels)', 1, 2 * 32 * px(2) * (2 + 3), lambda: ops.bn_backward(g2, None, y2, sc, sc, sc, True, beta=sc))
     # BatchNorm passes at the other resolutions (channel count, level, layers of that shape per step)
     for C, div, cnt in [(32, 4, 1), (48, 4, 1), (48, 8, 1), (64, 8, 1), (128, 8, 7), (384, 8, 1), (384, 16, 6), (64, 16, 3),
                         (384, 32, 1), (576, 32, 6), (96, 32, 3), (768, 32, 4), (128, 32, 4)]:
-        yb = act(C, div)
+        yb, gb = act(C, div), act(C, div)
         scb = torch.ones(C, device=device)
         add('bn_apply %dch@1/%d' % (C, div), cnt, 2 * 2 * C * px(div), lambda: ops.bn_apply(yb, scb, scb, relu=True))
         add('bn_backward %dch@1/%d (2 kernels)' % (C, div), cnt, 2 * C * px(div) * (2 + 3),
-            lambda: ops.bn_backward(yb, None, yb, scb, scb, scb, True, beta=scb))
+            lambda: ops.bn_backward(gb, None, yb, scb, scb, scb, True, beta=scb))
     # depthwise: every shape of the network (channels, input level, stride, dilation, layers of that shape)
     for C, div, s, d, cnt in [(32, 2, 2, 1, 1), (48, 4, 2, 1, 1), (384, 8, 2, 1, 1), (384, 16, 1, 1, 2), (384, 16, 2, 1, 1),
                               (576, 32, 1, 1, 3), (768, 32, 1, 1, 2), (128, 8, 1, 4, 1), (128, 8, 1, 1, 2)]:

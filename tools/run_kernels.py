@@ -29,7 +29,11 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ops_log = []
 
+    only = sys.argv[sys.argv.index('--only') + 1] if '--only' in sys.argv else None   # op-name prefix filter
+
     def runner(name, count, nbytes, fn):
+        if only is not None and not name.startswith(only):
+            return
         if not once:
             fn()
         torch.cuda.synchronize()
