@@ -71,6 +71,7 @@ class Engine:
         # optional ``stage(batch) -> staged``: called for batch i+1 BEFORE batch i is processed, so that
         # its host->device copy (side stream) overlaps with the step running on batch i
         self.stage = None
+        self._pending, self._staged_next = _END, None
 
     def add_event_handler(self, event, handler, *args, **kwargs):
         self._handlers.setdefault(event.name, []).append((event, handler, args, kwargs))
@@ -83,6 +84,12 @@ class Engine:
 
     def terminate(self):
         self.should_terminate = True
+
+    def prefetch_next(self):
+        """Issue the host->device copy of the next batch now (idempotent; a no-op without ``stage``)."""
+        nxt = getattr(self, '_pending', _END)
+        if self.stage is not None and nxt is not _END and self._staged_next is None:
+            self._staged_next = self.stage(nxt)
 
     def _fire(self, event):
         count = self.state.epoch if 'EPOCH' in event.name else self.state.iteration
@@ -105,15 +112,19 @@ class Engine:
             self._fire(Events.EPOCH_STARTED)
             it = iter(data)
             nxt = next(it, _END)
-            staged = self.stage(nxt) if (self.stage is not None and nxt is not _END) else None
+            self._pending, self._staged_next = nxt, None
+            self.prefetch_next()
             while nxt is not _END:
-                batch, current = nxt, staged
+                batch, current = nxt, self._staged_next
                 nxt = next(it, _END)
-                staged = self.stage(nxt) if (self.stage is not None and nxt is not _END) else None
+                self._pending, self._staged_next = nxt, None
                 self.state.iteration += 1
                 self.state.batch = batch
                 self._fire(Events.ITERATION_STARTED)
+                # the process function may call prefetch_next() right after it has LAUNCHED its step (and
+                # before it waits for the result); otherwise the next batch is staged when it returns
                 self.state.output = self._process_function(self, batch if current is None else current)
+                self.prefetch_next()
                 self._fire(Events.ITERATION_COMPLETED)
                 if self.should_terminate:
                     break
@@ -327,6 +338,7 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
             loss = g(x, y, non_blocking)         # device->device into the graph's inputs when staged
             if staged is not None:
                 stager.release(staged)
+            _trainer.prefetch_next()             # the step is in flight: now copy batch i+1 under it
             return loss.item()
         optimizer.zero_grad()
         x, y = fetch(batch)
@@ -340,6 +352,7 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
         optimizer.step()
         if staged is not None:
             stager.release(staged)
+        _trainer.prefetch_next()
         return loss.item()
 
     trainer = Engine(update_fn)
