@@ -98,6 +98,19 @@ int tss_pack_weights_bf16(const float* w, void* wp, void* wpT, int Nc, int K, vo
 int tss_pack_weights_multi(const float* arena, const int64_t* table, int n_entries, int64_t max_elems,
                            void* stream);
 
+/* ---- fused depthwise 3x3 -> pointwise 1x1, inference --------------------------------------------
+ * The tail of the inverted-residual bottleneck (conv2 + conv3, fastscnn.py:149-161,
+ * contextnet.py:138-147) and the DS-conv block (fastscnn.py:188-199) with eval-mode BatchNorm, as ONE
+ * kernel: t = act1(dw3x3(x)*scale1+shift1) is produced tile by tile straight into the shared-memory
+ * operand of the tcgen05 GEMM y = act2(t . wp^T * scale2 + shift2 [+ res]); the depthwise output
+ * (6x the block's width in a bottleneck) never goes to HBM.  bf16 only; stride 1, dilation 1,
+ * padding 1; C % 64 == 0; Nc % 16 == 0, Nc <= 256; x[N][H][W][C] dense, wp = bf16 (Nc, C) from
+ * tss_pack_weights_bf16, w_dw the fp32 (C,1,3,3) parameter. */
+int tss_dwpw_fwd(const void* x, const float* w_dw, const float* scale1, const float* shift1, int flags1,
+                 const void* wp, void* y, int N, int H, int W, int C, int Nc, int64_t ldy,
+                 const float* scale2, const float* shift2, const void* res, int64_t ldr, int flags2,
+                 void* stream);
+
 /* ---- dense 3x3 convolution ---------------------------------------------------------------
  * Stem: replaces nn.Conv2d(3, 32, 3, stride=2, padding=1, bias=False) at fastscnn.py:30 /
  * contextnet.py:38,48.  x is the user's NCHW fp32 image batch (N,3,H,W) read in place

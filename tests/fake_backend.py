@@ -86,6 +86,13 @@ class FakeBackend:
             wpT.copy_(w.view(Nc, K).t())
         return 0
 
+    def tss_dwpw_fwd(self, x, w_dw, scale1, shift1, flags1, wp, y, N, H, W, C, Nc, ldy, scale2, shift2, res, ldr, flags2):
+        t = F.conv2d(x.float(), w_dw.detach().view(C, 1, 3, 3), None, 1, 1, 1, C)
+        t = _epilogue(t, scale1, shift1, None, flags1).to(x.dtype).float()
+        raw = F.conv2d(t, wp.float().view(Nc, C, 1, 1))
+        y.copy_(_epilogue(raw, scale2, shift2, res, flags2))
+        return 0
+
     def tss_pack_weights_multi(self, arena, table, n_entries, max_elems):
         raise NotImplementedError('bf16 tensor-core packs are not used on the CPU emulation')
 

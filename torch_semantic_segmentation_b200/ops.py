@@ -140,6 +140,19 @@ def pwconv_wgrad(x, dy, dw, db=None, impl=0):
               lddy=lddy, impl=impl, dtype=dtype_code(x.dtype))
 
 
+def dwpw_fwd(x, w_dw, scale1, shift1, relu1, wp, scale2, shift2, res=None, relu2=False):
+    """Inference: act2(BN2(pw(act1(BN1(dw3x3(x))))) [+ res]) in one kernel (stride 1, bf16)."""
+    N, C, H, W, ld = _g(x, 'dwpw_fwd')
+    if ld != C or x.dtype != torch.bfloat16:
+        raise RuntimeError('dwpw_fwd: expects a dense bf16 NHWC input')
+    Nc = wp.shape[0]
+    y = empty_nhwc(N, Nc, H, W, x.dtype, x.device)
+    _lib.call('tss_dwpw_fwd', x=x, w_dw=w_dw, scale1=scale1, shift1=shift1, flags1=_flags(relu1), wp=wp, y=y,
+              N=N, H=H, W=W, C=C, Nc=Nc, ldy=Nc, scale2=scale2, shift2=shift2, res=res,
+              ldr=_g(res, 'dwpw_fwd')[4] if res is not None else 0, flags2=_flags(relu2))
+    return y
+
+
 def pack_weights_bf16(w):
     Nc, K = w.shape[0], w.shape[1]
     wp = torch.empty((Nc, K), dtype=torch.bfloat16, device=w.device)
