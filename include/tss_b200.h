@@ -66,6 +66,11 @@ int tss_dwconv3x3_fwd(const void* x, const float* w, void* y, int N, int Hi, int
 /* grad wrt input: dx[N][Hi][Wi][C] from dy[N][Ho][Wo][C] (autograd of the above). */
 int tss_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int N, int Hi, int Wi, int C,
                         int stride, int dilation, int dtype, void* stream);
+/* Training, stride 1 / dilation 1: the dgrad above with the BatchNorm-backward reduction of the producing
+ * layer fused into its epilogue (see tss_pwconv_dgrad_bnred): g[N][H][W][C] = dz * mask(yp), sums += ... */
+int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g, int N, int H, int W, int C,
+                              const void* yp, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, int flags, float* sums, int dtype, void* stream);
 /* grad wrt weight: dw[C][3][3] (fp32) += sum_{n,ho,wo} x * dy  (warp-shuffle + block
  * reduction, fp32 atomics).  dw must be zeroed (or hold a gradient to accumulate into). */
 int tss_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi, int C,
@@ -90,6 +95,15 @@ int tss_pwconv_dgrad(const void* dy, const float* w, const void* wpT, void* dx, 
 /* dw[Nc][K] (fp32) += dy^T . x ; db[Nc] (fp32, may be NULL) += column sums of dy */
 int tss_pwconv_wgrad(const void* x, const void* dy, float* dw, float* db, int64_t M, int K, int Nc,
                      int64_t ldx, int64_t lddy, int impl, int dtype, void* stream);
+/* Training: the dgrad above (impl 1) with the BatchNorm-backward reduction of the PRODUCING layer fused
+ * into its epilogue.  The input of this 1x1 conv was z = act(BN(yp)) with yp[M][K] (pitch ldyp) the raw
+ * conv output of the previous layer; instead of dz the kernel stores g = dz * (z > 0) (mask recomputed
+ * from yp; all-ones without TSS_EPI_RELU) and accumulates sums[k] += sum_m g, sums[K+k] += sum_m g*xhat,
+ * xhat = (yp-mean)*rstd -- what tss_bn_bwd_reduce would compute in a pass of its own.  The producer's
+ * BatchNorm backward then only runs tss_bn_bwd_apply on (g, yp) with flags = 0.  sums zeroed by the caller. */
+int tss_pwconv_dgrad_bnred(const void* dy, const void* wpT, void* g, int64_t M, int K, int Nc, int64_t lddy,
+                           int64_t ldg, const void* yp, int64_t ldyp, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, int flags, float* sums, void* stream);
 /* bf16 copies of a (Nc,K) fp32 weight: wp[Nc][K] and wpT[K][Nc] (either may be NULL) */
 int tss_pack_weights_bf16(const float* w, void* wp, void* wpT, int Nc, int K, void* stream);
 /* the same for n_entries weights living in one fp32 parameter arena, in ONE launch (after the optimizer

@@ -71,6 +71,25 @@ class FakeBackend:
         dx.copy_(F.conv2d(dy.float(), w.view(Nc, K).t().reshape(K, Nc, 1, 1)))
         return 0
 
+    def _bnred(self, dz, g, yp, mean, rstd, gamma, beta, flags, sums):
+        v = lambda t: t.detach().view(1, -1, 1, 1)
+        C = dz.shape[1]
+        if flags & RELU:
+            sc = v(gamma) * v(rstd)
+            dz = dz * (torch.addcmul(v(beta) - v(mean) * sc, yp.float(), sc) > 0)
+        sums[:C] += dz.sum(dim=(0, 2, 3))
+        sums[C:] += (dz * (yp.float() - v(mean)) * v(rstd)).sum(dim=(0, 2, 3))
+        g.copy_(dz)
+        return 0
+
+    def tss_pwconv_dgrad_bnred(self, dy, wpT, g, M, K, Nc, lddy, ldg, yp, ldyp, mean, rstd, gamma, beta, flags, sums):
+        dz = F.conv2d(dy.float(), wpT.float().reshape(K, Nc, 1, 1))
+        return self._bnred(dz, g, yp, mean, rstd, gamma, beta, flags, sums)
+
+    def tss_dwconv3x3_dgrad_bnred(self, dy, w, g, N, H, W, C, yp, mean, rstd, gamma, beta, flags, sums, dtype):
+        dz = nngrad.conv2d_input((N, C, H, W), w.detach().view(C, 1, 3, 3), dy.float(), 1, 1, 1, C)
+        return self._bnred(dz, g, yp, mean, rstd, gamma, beta, flags, sums)
+
     def tss_pwconv_wgrad(self, x, dy, dw, db, M, K, Nc, ldx, lddy, impl, dtype):
         g = dy.float().permute(1, 0, 2, 3).reshape(Nc, -1)
         a = x.float().permute(1, 0, 2, 3).reshape(K, -1)

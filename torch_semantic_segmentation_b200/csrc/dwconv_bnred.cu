@@ -1,0 +1,172 @@
+// Depthwise 3x3 stride-1 dgrad with the BatchNorm-backward REDUCTION of the producing layer fused into
+// its epilogue (training): the kernel of dwconv_tma.cu (TMA-staged halo tile of dy, flipped taps,
+// FFMA2), whose output dz = gradient w.r.t. the activated input z = relu(BN(yp)) of this depthwise
+// conv.  The epilogue reads the matching yp values, applies the ReLU mask recomputed from yp, stores
+// g = dz * mask instead of dz and accumulates  sums[c] += sum g,  sums[C+c] += sum g * xhat  (what
+// bn_bwd_reduce_kernel would compute in a pass of its own over dz and yp).
+#include "tma.cuh"
+
+namespace {
+
+constexpr int TH = 8;
+constexpr int IH = TH + 2;
+
+template <typename T>
+__global__ void __launch_bounds__(192, 2)
+dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const float* __restrict__ w, T* __restrict__ g_out,
+                      int H, int W, int C, int CB, int TW, int tiles_w, int tiles_h, const T* __restrict__ yp,
+                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int relu, float* __restrict__ sums) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    const int IW = TW + 2;
+    const uint32_t tile_bytes = (uint32_t)IH * IW * CB * sizeof(T);
+    T* tile = (T*)smem;
+    uint64_t* bar = (uint64_t*)(smem + ((tile_bytes + 15) & ~15u));
+
+    int t = blockIdx.x;
+    const int tw = t % tiles_w; t /= tiles_w;
+    const int th = t % tiles_h;
+    const int n = t / tiles_h;
+    const int cb0 = blockIdx.y * CB;
+    const int h0 = th * TH, w0 = tw * TW;
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(bar), 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    pdl_wait();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(smem_u32(bar), tile_bytes);
+        tma_load_4d(smem_u32(tile), &tmG, smem_u32(bar), cb0, w0 - 1, h0 - 1, n);
+    }
+
+    const int CGB = CB >> 3;
+    const int cg = threadIdx.x % CGB, col = threadIdx.x / CGB;
+    const int c0 = cb0 + cg * 8;
+    float2 wr[9][4];                                      // flipped taps: dgrad of a stride-1 correlation
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            wr[k][e] = make_float2(__ldg(w + (c0 + 2 * e) * 9 + (8 - k)), __ldg(w + (c0 + 2 * e + 1) * 9 + (8 - k)));
+    float mu[8], rs[8], sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        mu[e] = __ldg(mean + c0 + e);
+        rs[e] = __ldg(rstd + c0 + e);
+        sc[e] = (gamma != nullptr ? __ldg(gamma + c0 + e) : 1.f) * rs[e];
+        sh[e] = (beta != nullptr ? __ldg(beta + c0 + e) : 0.f) - mu[e] * sc[e];
+    }
+
+    mbar_wait(smem_u32(bar), 0);
+
+    float2 acc[TH][4];
+#pragma unroll
+    for (int r = 0; r < TH; ++r) zero8p(acc[r]);
+    const T* tp = tile + (size_t)col * CB + cg * 8;
+#pragma unroll
+    for (int j = 0; j < IH; ++j) {
+        float2 v[3][4];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) load8p_smem(tp + ((size_t)j * IW + kx) * CB, v[kx]);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int r = j - ky;
+            if (r >= 0 && r < TH) {
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[r][e] = ffma2(v[kx][e], wr[ky * 3 + kx][e], acc[r][e]);
+            }
+        }
+    }
+
+    const int wo = w0 + col;
+    float s1[8], s2[8];
+    zero8(s1); zero8(s2);
+    if (wo < W) {
+        const int64_t base = (((int64_t)n * H + h0) * W + wo) * C + c0;
+#pragma unroll
+        for (int r = 0; r < TH; ++r) {
+            if (h0 + r < H) {
+                float yy[8], g[8];
+                load8(yp + base + (int64_t)r * W * C, yy);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float dz = (e & 1) ? acc[r][e >> 1].y : acc[r][e >> 1].x;
+                    const bool on = !relu || fmaf(yy[e], sc[e], sh[e]) > 0.f;
+                    g[e] = on ? dz : 0.f;
+                    s1[e] += g[e];
+                    s2[e] = fmaf(g[e], (yy[e] - mu[e]) * rs[e], s2[e]);
+                }
+                store8(g_out + base + (int64_t)r * W * C, g);
+            }
+        }
+    }
+    // column partials -> one atomic per channel and CTA (the dy tile is dead: reuse it)
+    __syncthreads();
+    float* part = (float*)tile;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        part[(size_t)col * CB + cg * 8 + e] = s1[e];
+        part[(size_t)(TW + col) * CB + cg * 8 + e] = s2[e];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * CB; i += blockDim.x) {
+        const int which = i / CB, ch = i - which * CB;
+        float s = 0.f;
+        for (int cidx = 0; cidx < TW; ++cidx) s += part[(size_t)(which * TW + cidx) * CB + ch];
+        atomicAdd(sums + which * C + cb0 + ch, s);
+    }
+}
+
+template <typename T> struct TmaTypeB;
+template <> struct TmaTypeB<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
+template <> struct TmaTypeB<bf16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
+
+}  // namespace
+
+bool tss_dw_tma_config(int C, int* CB, int* TW);     // dwconv_tma.cu
+
+extern "C" int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g, int N, int H, int W, int C,
+                                         const void* yp, const float* mean, const float* rstd, const float* gamma,
+                                         const float* beta, int flags, float* sums, int dtype, void* stream) {
+    TSS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "dwconv3x3_dgrad_bnred: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+    TSS_REQUIRE(yp != nullptr && mean != nullptr && rstd != nullptr && sums != nullptr, "dwconv3x3_dgrad_bnred: missing BatchNorm operands");
+    TSS_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)yp & 15) == 0, "dwconv3x3_dgrad_bnred: buffers must be 16-byte aligned");
+    int CB, TW;
+    TSS_REQUIRE(tss_dw_tma_config(C, &CB, &TW), "dwconv3x3_dgrad_bnred: no channel block for C=%d", C);
+    TssEncodeTiledFn enc = tss_encode_tiled();
+    TSS_REQUIRE(enc != nullptr, "dwconv3x3_dgrad_bnred: cuTensorMapEncodeTiled is not available from the driver");
+    TSS_DISPATCH_DTYPE(dtype, "dwconv3x3_dgrad_bnred", {
+        if (sizeof(T) == 4 && TW == 32) TW = 16;
+        const int IW = TW + 2;
+        CUtensorMap map;
+        cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t gstr[3] = {(cuuint64_t)C * sizeof(T), (cuuint64_t)W * C * sizeof(T), (cuuint64_t)H * W * C * sizeof(T)};
+        cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)IW, (cuuint32_t)IH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map, TmaTypeB<T>::v, 4, const_cast<void*>(dy), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TSS_REQUIRE(r == CUDA_SUCCESS, "dwconv3x3_dgrad_bnred: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
+        const int threads = (CB / 8) * TW;
+        const size_t tile_bytes = (size_t)IH * IW * CB * sizeof(T);
+        size_t smem = 128 + ((tile_bytes + 15) & ~(size_t)15) + 16;
+        const size_t part = (size_t)2 * TW * CB * sizeof(float) + 128;
+        if (smem < part) smem = part;
+        auto kern = dw_dgrad_bnred_kernel<T>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            TSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set = true;
+        }
+        dim3 grid((unsigned)((int64_t)N * tiles_h * tiles_w), (unsigned)(C / CB));
+        tss_launch(kern, grid, threads, smem, (cudaStream_t)stream, map, w, (T*)g, H, W, C, CB, TW, tiles_w, tiles_h, (const T*)yp,
+                   mean, rstd, gamma, beta, flags & TSS_EPI_RELU, sums);
+        TSS_LAUNCH_CHECK("dwconv3x3_dgrad_bnred");
+        return TSS_OK;
+    });
+}

@@ -1,0 +1,299 @@
+// Pointwise-conv dgrad on tcgen05 with the BatchNorm-backward REDUCTION of the producing layer fused
+// into its epilogue (training).
+//
+//   dz[M][C] = dY[M][Nc] . W[Nc][C]          gradient w.r.t. the activated input z of this 1x1 conv
+//   z = relu(BN(yp))  was produced by the previous layer from its raw conv output yp[M][C]; that
+//   layer's BatchNorm backward starts with   g = dz * (z > 0),  sums[c] += sum_m g,
+//   sums[C+c] += sum_m g * xhat,  xhat = (yp - mean) * rstd      (bn.cu: bn_bwd_reduce_kernel).
+// The dgrad epilogue already holds the dz tile in registers: it reads the matching yp tile (the ReLU
+// mask is recomputed from yp with the forward's arithmetic), stores g instead of dz and accumulates
+// the two sums with the same warp-transposed shuffle reduction the forward uses for its statistics.
+// The producer's BatchNorm backward then runs its apply pass only (no mask, no reduction): one full
+// read of dz and yp and one launch less per layer.  Main loop identical to pwconv_tc.cu.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;          // rows per tile = UMMA M
+constexpr int BK = 64;           // bf16 elements per k-block = 128 bytes = one swizzle row
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = BM * BK * 2;
+
+// ------------------------------------------------------------------ PTX wrappers ------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+
+// lanes 2j / 2j+1 end with the sum over the 32 lanes of v[j], j = lane >> 1
+__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int step = 16, n = 16; step >= 2; step >>= 1, n >>= 1) {
+        const bool upper = (lane & step) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = upper ? v[i] : v[i + n / 2];
+            const float keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+
+__global__ void __launch_bounds__(kThreads)
+pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   bf16* __restrict__ G, int64_t M, int K, int64_t ldg, int block_n, int stages, uint32_t tmem_cols,
+                   const bf16* __restrict__ yp, int64_t ldyp, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   int relu, float* __restrict__ sums, int sums_stride) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t b_bytes = (uint32_t)block_n * BK * 2;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)stages * kABytes;
+    uint64_t* bars = (uint64_t*)(sB + (size_t)stages * b_bytes);     // full[stages], empty[stages], tmem_full
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * stages + 1);
+    float* s_stat = (float*)(tmem_slot + 2);                          // [2][block_n]
+    float* s_const = s_stat + 2 * block_n;                            // [4][block_n]: mean, rstd, scale, shift
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * block_n;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(bars + s), 1);
+            mbar_init(smem_u32(bars + stages + s), 1);
+        }
+        mbar_init(smem_u32(bars + 2 * stages), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 2 * block_n; i += kThreads) s_stat[i] = 0.f;
+    pdl_wait();
+    for (int i = threadIdx.x; i < block_n; i += kThreads) {           // per-column constants of the producer's BatchNorm
+        const float mu = __ldg(mean + n0 + i), rs = __ldg(rstd + n0 + i);
+        const float sc = (gamma != nullptr ? __ldg(gamma + n0 + i) : 1.f) * rs;
+        s_const[i] = mu;
+        s_const[block_n + i] = rs;
+        s_const[2 * block_n + i] = sc;
+        s_const[3 * block_n + i] = (beta != nullptr ? __ldg(beta + n0 + i) : 0.f) - mu * sc;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ---------------- TMA producer
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % stages;
+                const uint32_t phase = (kb / stages) & 1;
+                mbar_wait(smem_u32(bars + stages + s), phase ^ 1);
+                const uint32_t full = smem_u32(bars + s);
+                mbar_expect_tx(full, kABytes + b_bytes);
+                tma_load_2d(smem_u32(sA + (size_t)s * kABytes), &tmA, full, kb * BK, (int)m0);
+                tma_load_2d(smem_u32(sB + (size_t)s * b_bytes), &tmB, full, kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ---------------- MMA issuer
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % stages;
+                const uint32_t phase = (kb / stages) & 1;
+                mbar_wait(smem_u32(bars + s), phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t adesc = make_desc_k_sw128(smem_u32(sA + (size_t)s * kABytes));
+                const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + (size_t)s * b_bytes));
+                int rem = K - kb * BK;
+                const int k16 = rem >= BK ? BK / 16 : (rem + 15) / 16;
+                for (int k = 0; k < k16; ++k)
+                    umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)(kb > 0 || k > 0));
+                umma_commit(smem_u32(bars + stages + s));
+            }
+            umma_commit(smem_u32(bars + 2 * stages));
+        }
+    } else {                                               // ---------------- epilogue warps 2..5
+        const int q = warp & 3;
+        const int row_in_tile = q * 32 + lane;
+        const int64_t row = m0 + row_in_tile;
+        const bool row_ok = row < M;
+        mbar_wait(smem_u32(bars + 2 * stages), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c = 0; c < block_n; c += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            const int col = n0 + c;
+            float y0[8], y1[8];
+            if (row_ok) {
+                load8(yp + row * ldyp + col, y0);
+                load8(yp + row * ldyp + col + 8, y1);
+            } else {                                       // rows >= M: dz is an exact zero (TMA zero fill)
+                zero8(y0); zero8(y1);
+            }
+            float gx[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float yy = i < 8 ? y0[i] : y1[i - 8];
+                const float mu = s_const[c + i], rs = s_const[block_n + c + i];
+                if (relu && !(fmaf(yy, s_const[2 * block_n + c + i], s_const[3 * block_n + c + i]) > 0.f)) v[i] = 0.f;
+                gx[i] = v[i] * ((yy - mu) * rs);
+            }
+            {
+                float sm[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sm[i] = v[i];
+                const float s1 = warp_transpose_sum16(sm, lane);
+                const float s2 = warp_transpose_sum16(gx, lane);
+                if ((lane & 1) == 0) {
+                    atomicAdd(&s_stat[c + (lane >> 1)], s1);
+                    atomicAdd(&s_stat[block_n + c + (lane >> 1)], s2);
+                }
+            }
+            if (row_ok) {
+                uint32_t o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                bf16* dst = G + row * ldg + col;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < block_n; i += kThreads) {
+        atomicAdd(sums + n0 + i, s_stat[i]);
+        atomicAdd(sums + sums_stride + n0 + i, s_stat[block_n + i]);
+    }
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+int make_map_bnred(CUtensorMap* map, const void* base, int64_t rows, int cols, int64_t ld, int box_rows) {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn enc = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    TSS_REQUIRE(enc != nullptr, "pwconv_dgrad_bnred: cuTensorMapEncodeTiled is not available from the driver");
+    TSS_REQUIRE(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0, "pwconv_dgrad_bnred: TMA needs 16-byte aligned base and pitch");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TSS_REQUIRE(r == CUDA_SUCCESS, "pwconv_dgrad_bnred: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return TSS_OK;
+}
+
+}  // namespace
+
+extern "C" int tss_pwconv_dgrad_bnred(const void* dy, const void* wpT, void* g, int64_t M, int K, int Nc, int64_t lddy,
+                                      int64_t ldg, const void* yp, int64_t ldyp, const float* mean, const float* rstd,
+                                      const float* gamma, const float* beta, int flags, float* sums, void* stream) {
+    // GEMM: G[M][K] = dY[M][Nc] . (W^T)[K][Nc]^T  -- reduction over Nc, K output columns (= the producer's channels)
+    TSS_REQUIRE(M > 0 && K > 0 && Nc > 0 && K % 16 == 0 && Nc % 8 == 0, "pwconv_dgrad_bnred: M=%lld K=%d Nc=%d", (long long)M, K, Nc);
+    TSS_REQUIRE(ldg % 8 == 0 && ldyp % 8 == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)yp & 15) == 0,
+                "pwconv_dgrad_bnred: output / yp must be 16-byte aligned with pitches that are multiples of 8");
+    TSS_REQUIRE(yp != nullptr && mean != nullptr && rstd != nullptr && sums != nullptr, "pwconv_dgrad_bnred: missing BatchNorm operands");
+    int bn = 0;
+    for (int b = 64; b >= 16; b -= 16)
+        if (K % b == 0) { bn = b; break; }
+    TSS_REQUIRE(bn >= 16, "pwconv_dgrad_bnred: no tile width for K=%d", K);
+    CUtensorMap tmA, tmB;
+    if (int e = make_map_bnred(&tmA, dy, M, Nc, lddy, BM)) return e;
+    if (int e = make_map_bnred(&tmB, wpT, K, Nc, Nc, bn)) return e;
+    const int num_kb = (Nc + BK - 1) / BK;
+    const int stages = num_kb < 4 ? num_kb : 4;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < bn) tmem_cols <<= 1;
+    const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 1) * 8 + 8 + 6 * bn * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        TSS_CUDA(cudaFuncSetAttribute(pw_tc_bnred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)ceil_div64(M, BM), (unsigned)(K / bn));
+    tss_launch(pw_tc_bnred_kernel, grid, kThreads, smem, (cudaStream_t)stream, tmA, tmB, (bf16*)g, M, Nc, ldg, bn, stages, tmem_cols,
+               (const bf16*)yp, ldyp, mean, rstd, gamma, beta, flags & TSS_EPI_RELU, sums, K);
+    TSS_LAUNCH_CHECK("pwconv_dgrad_bnred");
+    return TSS_OK;
+}

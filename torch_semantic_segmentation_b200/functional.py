@@ -142,6 +142,32 @@ def conv_forward(spec, x, weight, scale=None, shift=None, res=None, relu=False, 
     raise RuntimeError('unknown conv kind %r' % spec.kind)
 
 
+# Training: fold the BatchNorm-backward reduction of a producer layer into the dgrad epilogue of its single
+# consumer (csrc/pwconv_tc_bnred.cu, csrc/dwconv_bnred.cu): one full read of (dz, y) and one launch less per
+# fused layer (20 of the 44 BatchNorm layers of Fast-SCNN; 4.66 -> 4.57 ms/step on B200).  TSS_FUSE_BNRED=0
+# selects the stand-alone reduction everywhere.
+FUSE_BNRED = os.environ.get('TSS_FUSE_BNRED', '1') == '1'
+
+
+class _BnLink:
+    """What the consumer's dgrad needs to run the producer's BatchNorm-backward reduction: the producer's raw
+    conv output ``y``, its batch statistics and affine parameters, whether a ReLU follows, and the (zeroed)
+    ``sums`` buffer of the producer's per-layer scratch.  ``reduced`` tells the producer's backward that the
+    gradient it receives already is ``g = dz * mask`` and that ``sums`` is complete."""
+
+    __slots__ = ('y', 'mean', 'rstd', 'gamma', 'beta', 'relu', 'sums', 'bn', 'scratch', 'reduced')
+
+    def __init__(self, y, mean, rstd, gamma, beta, relu, scratch, bn, C):
+        self.y, self.mean, self.rstd, self.gamma, self.beta, self.relu = y, mean, rstd, gamma, beta, relu
+        self.scratch, self.bn = scratch, bn
+        self.sums = scratch[2 * C:].view(torch.float32)
+        self.reduced = False
+
+    def usable(self):
+        """The producer's sums buffer is still the zeroed one of its last forward."""
+        return not self.reduced and not self.bn._tss_dirty and self.scratch is getattr(self.bn, '_tss_scratch', None)
+
+
 def _sync_group(bn):
     """-> (world size, process group) if this BatchNorm layer synchronises its statistics across ranks."""
     sync = getattr(bn, '_tss_sync', None)
@@ -154,8 +180,10 @@ def _sync_group(bn):
 class ConvBNAct(torch.autograd.Function):
     """z = act(BN_train(conv(x, w)) [+ res])."""
 
+    last_link = None        # handed to nn.blocks right after apply(): the link of the layer just run
+
     @staticmethod
-    def forward(ctx, x, res, weight, gamma, beta, spec, packed):
+    def forward(ctx, x, res, weight, gamma, beta, spec, packed, producer=None):
         bn = spec.bn
         C = weight.shape[0]
         if bn.momentum is None:
@@ -183,6 +211,13 @@ class ConvBNAct(torch.autograd.Function):
         ctx.in_hw = (x.shape[2], x.shape[3])
         # the ReLU mask is recomputed from y in backward unless a residual was added before the ReLU
         ctx.save_for_backward(x, weight, gamma, beta, y, z if (spec.relu and res is not None) else None, mean, rstd)
+        # fused BatchNorm-backward reduction: `producer` = link of the layer that made x (this conv is its only
+        # consumer); `link` = what THIS layer offers to its own single consumer (no residual, per-rank statistics)
+        ctx.producer = producer
+        ctx.link = None
+        ConvBNAct.last_link = None
+        if FUSE_BNRED and res is None and world == 1:
+            ctx.link = ConvBNAct.last_link = _BnLink(y, mean, rstd, gamma, beta, spec.relu, scratch, bn, C)
         return z
 
     @staticmethod
@@ -198,12 +233,19 @@ class ConvBNAct(torch.autograd.Function):
         else:
             gg_out, gb_out = gg, gb
         want_dres = ctx.has_res and ctx.needs_input_grad[1]
-        sums = ctx.scratch[2 * C:].view(torch.float32)
-        if spec.bn._tss_dirty or ctx.scratch is not getattr(spec.bn, '_tss_scratch', None):
-            sums = None      # a second backward without a forward in between: fresh zeros
-        spec.bn._tss_dirty = True
-        dy, dres = ops.bn_backward(dz, z, y, mean, rstd, gamma, spec.relu, want_dres=want_dres,
-                                   dgamma=gg_out, dbeta=gb_out, beta=beta, sums=sums, sync=ctx.sync)
+        link = ctx.link
+        if link is not None and link.reduced:
+            # the consumer's dgrad already masked the gradient and accumulated both sums
+            dy, dres = ops.bn_backward(dz, None, y, mean, rstd, gamma, False, dgamma=gg_out, dbeta=gb_out, beta=beta,
+                                       sums=link.sums, prereduced=True)
+        else:
+            sums = ctx.scratch[2 * C:].view(torch.float32)
+            if spec.bn._tss_dirty or ctx.scratch is not getattr(spec.bn, '_tss_scratch', None):
+                sums = None      # a second backward without a forward in between: fresh zeros
+            spec.bn._tss_dirty = True
+            dy, dres = ops.bn_backward(dz, z, y, mean, rstd, gamma, spec.relu, want_dres=want_dres,
+                                       dgamma=gg_out, dbeta=gb_out, beta=beta, sums=sums, sync=ctx.sync)
+        prod = ctx.producer if (ctx.producer is not None and ctx.producer.usable()) else None
         dx = None
         dw = gw if gw is not None else torch.zeros_like(weight)
         # wgrad off the critical chain when it accumulates in place into the optimizer's arena
@@ -213,18 +255,26 @@ class ConvBNAct(torch.autograd.Function):
             impl = spec.impl if wpT is not None else 0
             lane(lambda: ops.pwconv_wgrad(x, dy, dw, impl=impl))
             if ctx.needs_input_grad[0]:
-                dx = ops.pwconv_dgrad(dy, weight, wpT=wpT, impl=impl)
+                if prod is not None and impl == 1 and weight.shape[1] % 16 == 0:
+                    dx = ops.pwconv_dgrad_bnred(dy, wpT, prod)
+                    prod.reduced, prod.bn._tss_dirty = True, True
+                else:
+                    dx = ops.pwconv_dgrad(dy, weight, wpT=wpT, impl=impl)
         elif spec.kind == 'dw':
             lane(lambda: ops.dwconv_wgrad(x, dy, dw, spec.stride, spec.dilation))
             if ctx.needs_input_grad[0]:
-                dx = ops.dwconv_dgrad(dy, weight, ctx.in_hw[0], ctx.in_hw[1], spec.stride, spec.dilation)
+                if prod is not None and spec.stride == 1 and spec.dilation == 1 and weight.shape[0] % 32 == 0:
+                    dx = ops.dwconv_dgrad_bnred(dy, weight, prod)
+                    prod.reduced, prod.bn._tss_dirty = True, True
+                else:
+                    dx = ops.dwconv_dgrad(dy, weight, ctx.in_hw[0], ctx.in_hw[1], spec.stride, spec.dilation)
         else:  # stem: the image needs no gradient
             if ctx.needs_input_grad[0]:
                 raise RuntimeError('gradient w.r.t. the input image is not implemented')
             lane(lambda: ops.stem_wgrad(x, dy, dw))
         grad_ready(*ctx.params)
         return (dx, dres, None if gw is not None else dw, None if gg is not None else gg_out,
-                None if gb is not None else gb_out, None, None)
+                None if gb is not None else gb_out, None, None, None)
 
 
 class Im2Col3x3(torch.autograd.Function):

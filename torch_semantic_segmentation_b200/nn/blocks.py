@@ -124,7 +124,11 @@ class _FusedConvBN:
             self._pack_cache[ci] = hit
         return hit[1]
 
-    def _conv_bn(self, ci, x, relu, res=None):
+    def _conv_bn(self, ci, x, relu, res=None, sole_consumer=False):
+        """``sole_consumer``: ``x`` is the output of another fused conv+BN pair and nothing else reads it (the
+        enclosing block guarantees it), so that layer's BatchNorm-backward reduction may be folded into this
+        conv's dgrad epilogue (functional.FUSE_BNRED)."""
+        producer = getattr(x, '_tss_bn_link', None) if sole_consumer else None
         conv, bn = self[ci], self[ci + 1]
         spec = self._spec(ci, relu)
         if spec.kind != 'stem':
@@ -145,7 +149,10 @@ class _FusedConvBN:
             packed = self._packed(ci)
         use_batch_stats = self.training or not bn.track_running_stats
         if use_batch_stats:
-            return Fn.ConvBNAct.apply(x, res, weight, bn.weight, bn.bias, spec, packed)
+            z = Fn.ConvBNAct.apply(x, res, weight, bn.weight, bn.bias, spec, packed, producer)
+            if Fn.ConvBNAct.last_link is not None:
+                z._tss_bn_link, Fn.ConvBNAct.last_link = Fn.ConvBNAct.last_link, None
+            return z
         if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
             raise RuntimeError('eval-mode BatchNorm with autograd is not implemented; '
                                'wrap inference in torch.no_grad()')
@@ -171,10 +178,10 @@ class ConvBNBlock(nn.Sequential, _FusedConvBN):
         self.use_activation = use_activation
         self._init_fused()
 
-    def forward(self, input, residual=None, relu=None):
+    def forward(self, input, residual=None, relu=None, sole_consumer=False):
         """``residual``/``relu`` let the enclosing block fuse its ``+input`` and trailing
         ``F.relu`` (fastscnn.py:158-161, 89) into this block's BatchNorm apply."""
-        return self._conv_bn(0, input, self.use_activation if relu is None else relu, residual)
+        return self._conv_bn(0, input, self.use_activation if relu is None else relu, residual, sole_consumer)
 
 
 class DSConvBNBlock(nn.Sequential, _FusedConvBN):
@@ -200,7 +207,7 @@ class DSConvBNBlock(nn.Sequential, _FusedConvBN):
         if y is not None:
             return y
         x = self._conv_bn(0, input, False)
-        return self._conv_bn(2, x, self.use_activation)
+        return self._conv_bn(2, x, self.use_activation, sole_consumer=True)
 
 
 def Conv2dBlock(in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
@@ -240,8 +247,8 @@ class BottleneckBlock(nn.Module):
         y = fused_dw_pw(self.conv2, 0, self.conv3, 0, x, self.conv2.use_activation, True, residual=res)
         if y is not None:
             return y
-        x = self.conv2(x)
-        return self.conv3(x, residual=res, relu=True)
+        x = self.conv2(x, sole_consumer=True)
+        return self.conv3(x, residual=res, relu=True, sole_consumer=True)
 
 
 class ClassScores(nn.Conv2d):

@@ -132,6 +132,29 @@ def pwconv_dgrad(dy, w, wpT=None, impl=0):
     return dx
 
 
+def pwconv_dgrad_bnred(dy, wpT, link):
+    """tcgen05 dgrad + the producer's BatchNorm-backward reduction (``link``: functional._BnLink) -> g."""
+    N, Nc, H, W, lddy = _g(dy, 'pwconv_dgrad_bnred')
+    K = wpT.shape[0]
+    g = empty_nhwc(N, K, H, W, dy.dtype, dy.device)
+    _lib.call('tss_pwconv_dgrad_bnred', dy=dy, wpT=wpT, g=g, M=N * H * W, K=K, Nc=Nc, lddy=lddy, ldg=K, yp=link.y,
+              ldyp=_g(link.y, 'pwconv_dgrad_bnred')[4], mean=link.mean, rstd=link.rstd, gamma=link.gamma,
+              beta=link.beta, flags=_flags(link.relu), sums=link.sums)
+    return g
+
+
+def dwconv_dgrad_bnred(dy, w, link):
+    """stride-1 depthwise dgrad + the producer's BatchNorm-backward reduction -> g."""
+    N, C, H, W, ld = _g(dy, 'dwconv_dgrad_bnred')
+    if ld != C or _g(link.y, 'dwconv_dgrad_bnred')[4] != C:
+        raise RuntimeError('dwconv_dgrad_bnred: pitched tensors not supported')
+    g = empty_nhwc(N, C, H, W, dy.dtype, dy.device)
+    _lib.call('tss_dwconv3x3_dgrad_bnred', dy=dy, w=w, g=g, N=N, H=H, W=W, C=C, yp=link.y, mean=link.mean,
+              rstd=link.rstd, gamma=link.gamma, beta=link.beta, flags=_flags(link.relu), sums=link.sums,
+              dtype=dtype_code(dy.dtype))
+    return g
+
+
 def pwconv_wgrad(x, dy, dw, db=None, impl=0):
     """dw (fp32 (Nc,K,1,1)) += dy^T x ; db (fp32 (Nc,)) += colsum(dy)."""
     N, K, H, W, ldx = _g(x, 'pwconv_wgrad')
@@ -266,7 +289,7 @@ def bn_apply(y, scale, shift, y2=None, scale2=None, shift2=None, res=None, relu=
 
 
 def bn_backward(dz, z, y, mean, rstd, gamma, relu, want_dres=False, dgamma=None, dbeta=None, beta=None,
-                sums=None, sync=None):
+                sums=None, sync=None, prereduced=False):
     """-> dy, dres (or None).  dgamma/dbeta (fp32 (C,)) are accumulated into.  ``z=None`` with
     ``relu``: the ReLU mask is recomputed from ``y`` (needs ``beta``; no residual before the ReLU)."""
     N, C, H, W, lddz = _g(dz, 'bn_backward')
@@ -277,7 +300,11 @@ def bn_backward(dz, z, y, mean, rstd, gamma, relu, want_dres=False, dgamma=None,
     code = dtype_code(dz.dtype)
     ldz = _g(z, 'bn_backward')[4] if z is not None else 0
     ldy = _g(y, 'bn_backward')[4]
-    _lib.call('tss_bn_bwd_reduce', dz=dz, z=z if relu else None, y=y, mean=mean, rstd=rstd, gamma=gamma,
+    if prereduced:      # dz already is g = dz * mask and `sums` already holds the two sums (fused into the
+        fl = 0          # dgrad epilogue of the consumer): the apply pass alone, without a mask
+        relu = False
+    else:
+        _lib.call('tss_bn_bwd_reduce', dz=dz, z=z if relu else None, y=y, mean=mean, rstd=rstd, gamma=gamma,
               beta=beta, sums=sums,
               M=M, C=C, lddz=lddz, ldz=ldz, ldy=ldy, flags=fl, dtype=code)
     world = 1
