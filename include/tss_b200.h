@@ -71,6 +71,10 @@ int tss_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int N, int Hi,
 int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g, int N, int H, int W, int C,
                               const void* yp, const float* mean, const float* rstd, const float* gamma,
                               const float* beta, int flags, float* sums, int dtype, void* stream);
+/* the same for stride 2 (g and yp have the conv's INPUT geometry (Hi, Wi), dy its output geometry) */
+int tss_dwconv3x3_dgrad_s2_bnred(const void* dy, const float* w, void* g, int N, int Hi, int Wi, int C,
+                                 const void* yp, const float* mean, const float* rstd, const float* gamma,
+                                 const float* beta, int flags, float* sums, int dtype, void* stream);
 /* grad wrt weight: dw[C][3][3] (fp32) += sum_{n,ho,wo} x * dy  (warp-shuffle + block
  * reduction, fp32 atomics).  dw must be zeroed (or hold a gradient to accumulate into). */
 int tss_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi, int C,

@@ -90,6 +90,10 @@ class FakeBackend:
         dz = nngrad.conv2d_input((N, C, H, W), w.detach().view(C, 1, 3, 3), dy.float(), 1, 1, 1, C)
         return self._bnred(dz, g, yp, mean, rstd, gamma, beta, flags, sums)
 
+    def tss_dwconv3x3_dgrad_s2_bnred(self, dy, w, g, N, Hi, Wi, C, yp, mean, rstd, gamma, beta, flags, sums, dtype):
+        dz = nngrad.conv2d_input((N, C, Hi, Wi), w.detach().view(C, 1, 3, 3), dy.float(), 2, 1, 1, C)
+        return self._bnred(dz, g, yp, mean, rstd, gamma, beta, flags, sums)
+
     def tss_pwconv_wgrad(self, x, dy, dw, db, M, K, Nc, ldx, lddy, impl, dtype):
         g = dy.float().permute(1, 0, 2, 3).reshape(Nc, -1)
         a = x.float().permute(1, 0, 2, 3).reshape(K, -1)

@@ -1,0 +1,75 @@
+"""Kernels that are built and CPU-checked (through tests/fake_backend.py) but not yet validated on a B200,
+hence not enabled by default.  Run with TSS_EXPERIMENTAL=1 on the GPU box; skipped otherwise so that an
+unvalidated kernel can never hang the default GPU suite.
+
+* stride-2 depthwise dgrad with the producer's BatchNorm-backward reduction fused into its epilogue
+  (csrc/dwconv_bnred.cu: dw_dgrad_s2_bnred_kernel; enabled in the model by TSS_FUSE_BNRED_S2=1)."""
+import os
+
+import pytest
+import torch
+
+from tests.fake_backend import FakeBackend
+from torch_semantic_segmentation_b200 import _lib
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('TSS_EXPERIMENTAL') != '1', reason='set TSS_EXPERIMENTAL=1')]
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def nhwc(N, C, H, W, g, dtype):
+    base = torch.randn(N, H, W, C, generator=g).to(dtype)
+    return base.permute(0, 3, 1, 2), base.cuda().permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('C,N,Hi,Wi,relu', [(32, 2, 40, 56, 1), (384, 2, 16, 24, 1), (48, 1, 9, 13, 0), (64, 3, 7, 5, 1), (8, 1, 1, 1, 1)])
+def test_dw_dgrad_stride2_with_fused_bn_reduction(C, N, Hi, Wi, relu, dtype):
+    g = torch.Generator().manual_seed(C + Hi)
+    Ho, Wo = (Hi - 1) // 2 + 1, (Wi - 1) // 2 + 1
+    dyc, dyg = nhwc(N, C, Ho, Wo, g, dtype)
+    ypc, ypg = nhwc(N, C, Hi, Wi, g, dtype)
+    w = torch.randn(C, 1, 3, 3, generator=g) / 3
+    mean, rstd = torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    gc, gg = nhwc(N, C, Hi, Wi, g, dtype)
+    sc, sg = torch.zeros(2 * C), torch.zeros(2 * C).cuda()
+    kw = dict(N=N, Hi=Hi, Wi=Wi, C=C, flags=relu, dtype=_lib.dtype_code(dtype))
+    FakeBackend().call('tss_dwconv3x3_dgrad_s2_bnred', dict(dy=dyc, w=w, g=gc, yp=ypc, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sc, **kw))
+    _lib.backend().call('tss_dwconv3x3_dgrad_s2_bnred', dict(dy=dyg, w=w.cuda(), g=gg, yp=ypg, mean=mean.cuda(), rstd=rstd.cuda(),
+                                                            gamma=gamma.cuda(), beta=beta.cuda(), sums=sg, **kw))
+    torch.cuda.synchronize()
+    tol = 1e-4 if dtype == torch.float32 else 5e-3
+    assert rel(gg, gc) < tol, rel(gg, gc)
+    assert rel(sg, sc) < 2e-3, rel(sg, sc)
+
+
+def test_training_step_with_stride2_fusion_matches_unfused():
+    from oracle.golden_inputs import train_batch
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+    x, y = train_batch('fastscnn')
+    grads = {}
+    keep = Fn.FUSE_BNRED_S2
+    for flag in (False, True):
+        Fn.FUSE_BNRED_S2 = flag
+        try:
+            torch.manual_seed(0)
+            model = fastscnn(3, 19).cuda().set_compute_dtype(torch.bfloat16).train()
+            for m in model.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+            before = _lib.launch_count()
+            CrossEntropyLoss(ignore_index=255)(model(x.cuda()), y.cuda()).backward()
+            torch.cuda.synchronize()
+            grads[flag] = ({k: p.grad.clone() for k, p in model.named_parameters()}, _lib.launch_count() - before)
+        finally:
+            Fn.FUSE_BNRED_S2 = keep
+    assert grads[True][1] == grads[False][1] - 4                  # four stand-alone reductions less
+    for k in ('classifier.3.weight', 'features.0.0.conv1.0.weight', 'downsample.1.0.weight', 'downsample.0.0.weight'):
+        assert rel(grads[True][0][k], grads[False][0][k]) < 3e-2, k

@@ -122,6 +122,118 @@ dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const float* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stride 2: the quad kernel of dwconv.cu (2x2 input pixels per 2x2 gradient neighbourhood, vertical
+// strips of R quads, persistent grid with a loop-invariant channel group per thread) with the same fused
+// reduction.  These are the largest BatchNorm-backward instances of the network (the producers are the
+// stem and the first expand conv).
+constexpr int kQuadThreads = 128;
+
+template <typename T, int R>
+__global__ void __launch_bounds__(kQuadThreads, 3)
+dw_dgrad_s2_bnred_kernel(const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ g_out,
+                         int N, int Hi, int Wi, int Ho, int Wo, int C, const T* __restrict__ yp,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, int relu, float* __restrict__ sums) {
+    pdl_wait();
+    extern __shared__ float s_sum[];   // [2*C]
+    for (int i = threadIdx.x; i < 2 * C; i += kQuadThreads) s_sum[i] = 0.f;
+    __syncthreads();
+    const int CG = C >> 3;
+    const int nstrips = (Ho + R - 1) / R;
+    const int64_t total = (int64_t)N * nstrips * Wo * CG;
+    const int64_t gstride = (int64_t)gridDim.x * kQuadThreads;
+    int64_t item = (int64_t)blockIdx.x * kQuadThreads + threadIdx.x;
+    const int c0 = (int)(item % CG) * 8;          // loop-invariant: gstride % CG == 0
+    float wr[9][8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) wr[k][e] = __ldg(w + (c0 + e) * 9 + k);
+    // the loop accumulates sum g and sum g*y; x-hat comes in at the end: sum g*xhat = rstd*(sum g*y - mean*sum g)
+    float sc[8], sh[8], s1[8], s2[8];
+    zero8(s1); zero8(s2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float m_ = __ldg(mean + c0 + e), r_ = __ldg(rstd + c0 + e);
+        sc[e] = (gamma != nullptr ? __ldg(gamma + c0 + e) : 1.f) * r_;
+        sh[e] = (beta != nullptr ? __ldg(beta + c0 + e) : 0.f) - m_ * sc[e];
+    }
+    // mask, accumulate and store one output pixel's 8 channels
+    auto emit = [&](float (&o)[8], int64_t off) {
+        float yy[8];
+        load8(yp + off, yy);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (relu && !(fmaf(yy[e], sc[e], sh[e]) > 0.f)) o[e] = 0.f;
+            s1[e] += o[e];
+            s2[e] = fmaf(o[e], yy[e], s2[e]);
+        }
+        store8(g_out + off, o);
+    };
+
+    for (; item < total; item += gstride) {
+        int64_t t = item / CG;
+        const int q = (int)(t % Wo); t /= Wo;
+        const int strip = (int)(t % nstrips);
+        const int n = (int)(t / nstrips);
+        const int p0 = strip * R;
+        const T* dyn = dy + (int64_t)n * Ho * Wo * C + c0;
+        const int64_t xn = (int64_t)n * Hi * Wi * C + c0;
+        const bool q1 = q + 1 < Wo;
+        const bool col1 = 2 * q + 1 < Wi;
+        float g0[2][8], g1[2][8];
+        load8(dyn + ((int64_t)p0 * Wo + q) * C, g0[0]);
+        if (q1) load8(dyn + ((int64_t)p0 * Wo + q + 1) * C, g0[1]); else zero8(g0[1]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int p = p0 + r;
+            if (p >= Ho) break;
+            if (p + 1 < Ho) {
+                load8(dyn + ((int64_t)(p + 1) * Wo + q) * C, g1[0]);
+                if (q1) load8(dyn + ((int64_t)(p + 1) * Wo + q + 1) * C, g1[1]); else zero8(g1[1]);
+            } else { zero8(g1[0]); zero8(g1[1]); }
+            float o[8];
+            const int64_t row0 = xn + ((int64_t)(2 * p) * Wi + 2 * q) * C;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = g0[0][e] * wr[4][e];
+            emit(o, row0);
+            if (col1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fmaf(g0[1][e], wr[3][e], g0[0][e] * wr[5][e]);
+                emit(o, row0 + C);
+            }
+            if (2 * p + 1 < Hi) {
+                const int64_t row1 = row0 + (int64_t)Wi * C;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fmaf(g1[0][e], wr[1][e], g0[0][e] * wr[7][e]);
+                emit(o, row1);
+                if (col1) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        o[e] = fmaf(g1[1][e], wr[0][e], fmaf(g1[0][e], wr[2][e], fmaf(g0[1][e], wr[6][e], g0[0][e] * wr[8][e])));
+                    emit(o, row1 + C);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { g0[0][e] = g1[0][e]; g0[1][e] = g1[1][e]; }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float m_ = __ldg(mean + c0 + e), r_ = __ldg(rstd + c0 + e);
+        atomicAdd(&s_sum[c0 + e], s1[e]);
+        atomicAdd(&s_sum[C + c0 + e], r_ * (s2[e] - m_ * s1[e]));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += kQuadThreads) {
+        const float v = s_sum[i];
+        if (v != 0.f) atomicAdd(sums + i, v);
+    }
+}
+
+int gcd_int2(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
 template <typename T> struct TmaTypeB;
 template <> struct TmaTypeB<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
 template <> struct TmaTypeB<bf16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
@@ -129,6 +241,32 @@ template <> struct TmaTypeB<bf16> { static constexpr CUtensorMapDataType v = CU_
 }  // namespace
 
 bool tss_dw_tma_config(int C, int* CB, int* TW);     // dwconv_tma.cu
+
+// stride 2, dilation 1: g has the INPUT geometry (Hi, Wi), dy the output geometry ((Hi-1)/2+1, (Wi-1)/2+1)
+extern "C" int tss_dwconv3x3_dgrad_s2_bnred(const void* dy, const float* w, void* g, int N, int Hi, int Wi, int C,
+                                            const void* yp, const float* mean, const float* rstd, const float* gamma,
+                                            const float* beta, int flags, float* sums, int dtype, void* stream) {
+    TSS_REQUIRE(N > 0 && Hi > 0 && Wi > 0 && C > 0 && C % 8 == 0 && C <= 2048, "dwconv3x3_dgrad_s2_bnred: bad shape N=%d H=%d W=%d C=%d", N, Hi, Wi, C);
+    TSS_REQUIRE(yp != nullptr && mean != nullptr && rstd != nullptr && sums != nullptr, "dwconv3x3_dgrad_s2_bnred: missing BatchNorm operands");
+    TSS_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)yp & 15) == 0, "dwconv3x3_dgrad_s2_bnred: buffers must be 16-byte aligned");
+    const int Ho = (Hi - 1) / 2 + 1, Wo = (Wi - 1) / 2 + 1;
+    constexpr int R = 4;
+    const int CG = C / 8;
+    const int64_t total = (int64_t)N * ((Ho + R - 1) / R) * Wo * CG;
+    // persistent grid whose total thread count is a multiple of CG (loop-invariant channel group per thread)
+    const int qd = CG / gcd_int2(CG, kQuadThreads);
+    int64_t grid = ceil_div64(total, kQuadThreads);
+    const int64_t cap = (int64_t)tss_num_sms() * 3;          // 3 resident CTAs of 128 threads per SM (168 registers)
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    grid = (grid + qd - 1) / qd * qd;
+    TSS_DISPATCH_DTYPE(dtype, "dwconv3x3_dgrad_s2_bnred", {
+        tss_launch(dw_dgrad_s2_bnred_kernel<T, R>, (unsigned)grid, kQuadThreads, (size_t)2 * C * sizeof(float), (cudaStream_t)stream,
+                   (const T*)dy, w, (T*)g, N, Hi, Wi, Ho, Wo, C, (const T*)yp, mean, rstd, gamma, beta, flags & TSS_EPI_RELU, sums);
+        TSS_LAUNCH_CHECK("dwconv3x3_dgrad_s2_bnred");
+        return TSS_OK;
+    });
+}
 
 extern "C" int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g, int N, int H, int W, int C,
                                          const void* yp, const float* mean, const float* rstd, const float* gamma,

@@ -147,6 +147,9 @@ def conv_forward(spec, x, weight, scale=None, shift=None, res=None, relu=False, 
 # fused layer (20 of the 44 BatchNorm layers of Fast-SCNN; 4.66 -> 4.57 ms/step on B200).  TSS_FUSE_BNRED=0
 # selects the stand-alone reduction everywhere.
 FUSE_BNRED = os.environ.get('TSS_FUSE_BNRED', '1') == '1'
+# the same for the stride-2 depthwise dgrad (the producers are the stem and the first expand conv: the largest
+# BatchNorm-backward instances).  Built and CPU-checked, not yet validated on a B200: off unless TSS_FUSE_BNRED_S2=1.
+FUSE_BNRED_S2 = os.environ.get('TSS_FUSE_BNRED_S2', '0') == '1'
 
 
 class _BnLink:
@@ -265,6 +268,9 @@ class ConvBNAct(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 if prod is not None and spec.stride == 1 and spec.dilation == 1 and weight.shape[0] % 32 == 0:
                     dx = ops.dwconv_dgrad_bnred(dy, weight, prod)
+                    prod.reduced, prod.bn._tss_dirty = True, True
+                elif prod is not None and FUSE_BNRED_S2 and spec.stride == 2 and spec.dilation == 1:
+                    dx = ops.dwconv_dgrad_s2_bnred(dy, weight, prod)
                     prod.reduced, prod.bn._tss_dirty = True, True
                 else:
                     dx = ops.dwconv_dgrad(dy, weight, ctx.in_hw[0], ctx.in_hw[1], spec.stride, spec.dilation)

@@ -33,6 +33,10 @@ class FastSCNN(nn.Module):
             DSConv2dBlock(32, 48, kernel_size=3, padding=1, stride=2),
             DSConv2dBlock(48, 64, kernel_size=3, padding=1, stride=2),
         )
+        # inside `downsample` each block is the only reader of its predecessor's output (forward hooks are
+        # documented on `downsample` / `features` as a whole, wrappers/deep_supervision_wrapper.py:28-37)
+        self.downsample[1].input_sole_consumer = True
+        self.downsample[2].input_sole_consumer = True
         self.features = nn.Sequential(
             BottleneckModule(64, 64, expansion=6, repeats=3, stride=2),
             BottleneckModule(64, 96, expansion=6, repeats=3, stride=2),

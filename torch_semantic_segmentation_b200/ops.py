@@ -155,6 +155,18 @@ def dwconv_dgrad_bnred(dy, w, link):
     return g
 
 
+def dwconv_dgrad_s2_bnred(dy, w, link):
+    """stride-2 depthwise dgrad + the producer's BatchNorm-backward reduction -> g (the producer's geometry)."""
+    N, C, Hi, Wi, ld = _g(link.y, 'dwconv_dgrad_s2_bnred')
+    if ld != C or _g(dy, 'dwconv_dgrad_s2_bnred')[4] != C:
+        raise RuntimeError('dwconv_dgrad_s2_bnred: pitched tensors not supported')
+    g = empty_nhwc(N, C, Hi, Wi, dy.dtype, dy.device)
+    _lib.call('tss_dwconv3x3_dgrad_s2_bnred', dy=dy, w=w, g=g, N=N, Hi=Hi, Wi=Wi, C=C, yp=link.y, mean=link.mean,
+              rstd=link.rstd, gamma=link.gamma, beta=link.beta, flags=_flags(link.relu), sums=link.sums,
+              dtype=dtype_code(dy.dtype))
+    return g
+
+
 def pwconv_wgrad(x, dy, dw, db=None, impl=0):
     """dw (fp32 (Nc,K,1,1)) += dy^T x ; db (fp32 (Nc,)) += colsum(dy)."""
     N, K, H, W, ldx = _g(x, 'pwconv_wgrad')
