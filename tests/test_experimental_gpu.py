@@ -3,7 +3,7 @@ hence not enabled by default.  Run with TSS_EXPERIMENTAL=1 on the GPU box; skipp
 unvalidated kernel can never hang the default GPU suite.
 
 * stride-2 depthwise dgrad with the producer's BatchNorm-backward reduction fused into its epilogue
-  (csrc/dwconv_bnred.cu: dw_dgrad_s2_bnred_kernel; enabled in the model by TSS_FUSE_BNRED_S2=1)."""
+  (csrc/dwconv_bnred.cu: dw_dgrad_s2_bnred_kernel; enabled in the model by TSS_FUSE_BNRED_EXT=1)."""
 import os
 
 import pytest
@@ -48,16 +48,16 @@ def test_dw_dgrad_stride2_with_fused_bn_reduction(C, N, Hi, Wi, relu, dtype):
     assert rel(sg, sc) < 2e-3, rel(sg, sc)
 
 
-def test_training_step_with_stride2_fusion_matches_unfused():
+def test_training_step_with_extended_fusion_matches_unfused():
     from oracle.golden_inputs import train_batch
     from torch_semantic_segmentation_b200 import functional as Fn
     from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
     from torch_semantic_segmentation_b200.models import fastscnn
     x, y = train_batch('fastscnn')
     grads = {}
-    keep = Fn.FUSE_BNRED_S2
+    keep = Fn.FUSE_BNRED_EXT
     for flag in (False, True):
-        Fn.FUSE_BNRED_S2 = flag
+        Fn.FUSE_BNRED_EXT = flag
         try:
             torch.manual_seed(0)
             model = fastscnn(3, 19).cuda().set_compute_dtype(torch.bfloat16).train()
@@ -69,7 +69,7 @@ def test_training_step_with_stride2_fusion_matches_unfused():
             torch.cuda.synchronize()
             grads[flag] = ({k: p.grad.clone() for k, p in model.named_parameters()}, _lib.launch_count() - before)
         finally:
-            Fn.FUSE_BNRED_S2 = keep
-    assert grads[True][1] == grads[False][1] - 4                  # four stand-alone reductions less
+            Fn.FUSE_BNRED_EXT = keep
+    assert grads[True][1] == grads[False][1] - 6                  # 4 stride-2 + 2 more stand-alone reductions less
     for k in ('classifier.3.weight', 'features.0.0.conv1.0.weight', 'downsample.1.0.weight', 'downsample.0.0.weight'):
         assert rel(grads[True][0][k], grads[False][0][k]) < 3e-2, k

@@ -147,9 +147,10 @@ def conv_forward(spec, x, weight, scale=None, shift=None, res=None, relu=False, 
 # fused layer (20 of the 44 BatchNorm layers of Fast-SCNN; 4.66 -> 4.57 ms/step on B200).  TSS_FUSE_BNRED=0
 # selects the stand-alone reduction everywhere.
 FUSE_BNRED = os.environ.get('TSS_FUSE_BNRED', '1') == '1'
-# the same for the stride-2 depthwise dgrad (the producers are the stem and the first expand conv: the largest
-# BatchNorm-backward instances).  Built and CPU-checked, not yet validated on a B200: off unless TSS_FUSE_BNRED_S2=1.
-FUSE_BNRED_S2 = os.environ.get('TSS_FUSE_BNRED_S2', '0') == '1'
+# Extended set: the stride-2 depthwise dgrad (its producers are the stem and the first expand conv: the largest
+# BatchNorm-backward instances) and two more single-consumer pairs at 1/8 resolution (fusion low-res branch,
+# classifier).  Built and CPU-checked, not yet validated on a B200: off unless TSS_FUSE_BNRED_EXT=1.
+FUSE_BNRED_EXT = os.environ.get('TSS_FUSE_BNRED_EXT', '0') == '1'
 
 
 class _BnLink:
@@ -269,7 +270,7 @@ class ConvBNAct(torch.autograd.Function):
                 if prod is not None and spec.stride == 1 and spec.dilation == 1 and weight.shape[0] % 32 == 0:
                     dx = ops.dwconv_dgrad_bnred(dy, weight, prod)
                     prod.reduced, prod.bn._tss_dirty = True, True
-                elif prod is not None and FUSE_BNRED_S2 and spec.stride == 2 and spec.dilation == 1:
+                elif prod is not None and FUSE_BNRED_EXT and spec.stride == 2 and spec.dilation == 1:
                     dx = ops.dwconv_dgrad_s2_bnred(dy, weight, prod)
                     prod.reduced, prod.bn._tss_dirty = True, True
                 else:

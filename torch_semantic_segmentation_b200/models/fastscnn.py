@@ -94,17 +94,19 @@ class FeatureFusionModule(nn.Module):
         x = self.lowres[1](x)
         high = self.highres[0](highres)
         # relu(lowres + highres): add and ReLU fused into the low-res branch's BatchNorm apply
-        return self.lowres[2](x, residual=high, relu=True)
+        return self.lowres[2](x, residual=high, relu=True, sole_consumer=Fn.FUSE_BNRED_EXT)
 
 
 def Classifier(in_channels, out_channels):
     """reference: models/fastscnn.py:92-98 (also imported by scripts/train_fastscnn.py:28)."""
-    return nn.Sequential(
+    head = nn.Sequential(
         DSConv2dBlock(in_channels, in_channels, kernel_size=3, padding=1),
         DSConv2dBlock(in_channels, in_channels, kernel_size=3, padding=1),
         nn.Dropout(0.1),
         ClassScores(in_channels, out_channels),
     )
+    head[1].input_sole_consumer = True      # only the second DS block reads the first one's output
+    return head
 
 
 class PyramidPoolingModule(nn.Module):

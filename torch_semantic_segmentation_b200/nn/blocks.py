@@ -207,7 +207,7 @@ class DSConvBNBlock(nn.Sequential, _FusedConvBN):
         if y is not None:
             return y
         # `input_sole_consumer` (set by the enclosing model where it holds): nothing but this block reads `input`
-        x = self._conv_bn(0, input, False, sole_consumer=Fn.FUSE_BNRED_S2 and getattr(self, 'input_sole_consumer', False))
+        x = self._conv_bn(0, input, False, sole_consumer=Fn.FUSE_BNRED_EXT and getattr(self, 'input_sole_consumer', False))
         return self._conv_bn(2, x, self.use_activation, sole_consumer=True)
 
 
