@@ -108,6 +108,20 @@ int tss_pwconv_wgrad(const void* x, const void* dy, float* dw, float* db, int64_
 int tss_pwconv_dgrad_bnred(const void* dy, const void* wpT, void* g, int64_t M, int K, int Nc, int64_t lddy,
                            int64_t ldg, const void* yp, int64_t ldyp, const float* mean, const float* rstd,
                            const float* gamma, const float* beta, int flags, float* sums, void* stream);
+/* Training, bf16: BatchNorm-backward APPLY of this 1x1 layer + its dgrad (+ optionally the producer's
+ * BatchNorm-backward reduction, as tss_pwconv_dgrad_bnred) in ONE tcgen05 kernel.  dz[M][Nc] is the gradient
+ * after the layer's BN/ReLU, y[M][Nc] its raw conv output, sums[2*Nc] the finished reduction (sum g, sum g*xhat
+ * with g = dz*mask; flags&TSS_EPI_RELU: the mask is recomputed from y, 0: dz already is g).  The kernel forms
+ * dy = gamma*rstd*(g - sums[c]/count - xhat*sums[Nc+c]/count) on the fly as the GEMM's A operand, stores it to
+ * dy (pitch lddy; for the weight gradient; may be NULL), accumulates dgamma += sums[Nc+c], dbeta += sums[c]
+ * (either may be NULL) and writes dx[M][K] = dy . w (wpT = bf16 [K][Nc]).  With yp != NULL, dx is masked by the
+ * producer's ReLU (pflags) and psums[2*K] accumulates the producer's two sums.  No residual, per-rank statistics. */
+int tss_pwconv_bwd_fused(const void* dz, const void* y, int64_t lddz, int64_t ldy, const float* mean,
+                         const float* rstd, const float* gamma, const float* beta, const float* sums, int flags,
+                         int64_t count, void* dy, int64_t lddy, float* dgamma, float* dbeta, const void* wpT,
+                         void* dx, int64_t M, int K, int Nc, int64_t lddx, const void* yp, int64_t ldyp,
+                         const float* pmean, const float* prstd, const float* pgamma, const float* pbeta,
+                         int pflags, float* psums, void* stream);
 /* bf16 copies of a (Nc,K) fp32 weight: wp[Nc][K] and wpT[K][Nc] (either may be NULL) */
 int tss_pack_weights_bf16(const float* w, void* wp, void* wpT, int Nc, int K, void* stream);
 /* the same for n_entries weights living in one fp32 parameter arena, in ONE launch (after the optimizer

@@ -68,7 +68,8 @@ class FakeBackend:
         return 0
 
     def tss_pwconv_dgrad(self, dy, w, wpT, dx, M, K, Nc, lddy, lddx, impl, dtype):
-        dx.copy_(F.conv2d(dy.float(), w.view(Nc, K).t().reshape(K, Nc, 1, 1)))
+        wt = wpT.float() if (impl == 1 and wpT is not None) else w.view(Nc, K).t()      # impl 1 multiplies with the bf16 pack
+        dx.copy_(F.conv2d(dy.float(), wt.reshape(K, Nc, 1, 1)))
         return 0
 
     def _bnred(self, dz, g, yp, mean, rstd, gamma, beta, flags, sums):
@@ -85,6 +86,16 @@ class FakeBackend:
     def tss_pwconv_dgrad_bnred(self, dy, wpT, g, M, K, Nc, lddy, ldg, yp, ldyp, mean, rstd, gamma, beta, flags, sums):
         dz = F.conv2d(dy.float(), wpT.float().reshape(K, Nc, 1, 1))
         return self._bnred(dz, g, yp, mean, rstd, gamma, beta, flags, sums)
+
+    def tss_pwconv_bwd_fused(self, dz, y, lddz, ldy, mean, rstd, gamma, beta, sums, flags, count, dy, lddy, dgamma,
+                             dbeta, wpT, dx, M, K, Nc, lddx, yp, ldyp, pmean, prstd, pgamma, pbeta, pflags, psums):
+        self.tss_bn_bwd_apply(dz, None, y, mean, rstd, gamma, beta, sums, dy, None, dgamma, dbeta, M, count, Nc, lddz, 0,
+                              ldy, lddy, 0, flags, 0)
+        out = F.conv2d(dy.float(), wpT.float().reshape(K, Nc, 1, 1))
+        if yp is None:
+            dx.copy_(out)
+            return 0
+        return self._bnred(out, dx, yp, pmean, prstd, pgamma, pbeta, pflags, psums)
 
     def tss_dwconv3x3_dgrad_bnred(self, dy, w, g, N, H, W, C, yp, mean, rstd, gamma, beta, flags, sums, dtype):
         dz = nngrad.conv2d_input((N, C, H, W), w.detach().view(C, 1, 3, 3), dy.float(), 1, 1, 1, C)

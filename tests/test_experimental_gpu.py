@@ -3,7 +3,9 @@ hence not enabled by default.  Run with TSS_EXPERIMENTAL=1 on the GPU box; skipp
 unvalidated kernel can never hang the default GPU suite.
 
 * stride-2 depthwise dgrad with the producer's BatchNorm-backward reduction fused into its epilogue
-  (csrc/dwconv_bnred.cu: dw_dgrad_s2_bnred_kernel; enabled in the model by TSS_FUSE_BNRED_EXT=1)."""
+  (csrc/dwconv_bnred.cu: dw_dgrad_s2_bnred_kernel; enabled in the model by TSS_FUSE_BNRED_EXT=1);
+* pointwise backward with the layer's BatchNorm-backward apply folded into the GEMM's A-operand producer
+  (csrc/pwconv_tc_bwd.cu: pw_tc_bwd_kernel; enabled in the model by TSS_FUSE_BNAPPLY=1)."""
 import os
 
 import pytest
@@ -71,5 +73,77 @@ def test_training_step_with_extended_fusion_matches_unfused():
         finally:
             Fn.FUSE_BNRED_EXT = keep
     assert grads[True][1] == grads[False][1] - 6                  # 4 stride-2 + 2 more stand-alone reductions less
+    for k in ('classifier.3.weight', 'features.0.0.conv1.0.weight', 'downsample.1.0.weight', 'downsample.0.0.weight'):
+        assert rel(grads[True][0][k], grads[False][0][k]) < 3e-2, k
+
+
+@pytest.mark.parametrize('link', [False, True])
+@pytest.mark.parametrize('M_shape,K,Nc,relu', [((2, 16, 24), 64, 384, 1), ((1, 9, 13), 128, 128, 1), ((2, 5, 7), 96, 576, 0),
+                                               ((3, 8, 8), 32, 48, 1), ((1, 1, 3), 16, 8, 1), ((2, 32, 64), 48, 64, 1),
+                                               ((1, 4, 4), 128, 768, 1)])
+def test_pw_backward_with_bn_apply_in_the_operand_producer(M_shape, K, Nc, relu, link):
+    """One kernel == tss_bn_bwd_apply -> tss_pwconv_dgrad(_bnred) (emulated on the CPU from the same bf16 inputs)."""
+    N, H, W = M_shape
+    M = N * H * W
+    g = torch.Generator().manual_seed(K + Nc + M)
+    dt = torch.bfloat16
+    dzc, dzg = nhwc(N, Nc, H, W, g, dt)
+    yc, yg = nhwc(N, Nc, H, W, g, dt)
+    ypc, ypg = nhwc(N, K, H, W, g, dt)
+    par = lambda C: (torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.5, torch.rand(C, generator=g) + 0.5,
+                     torch.randn(C, generator=g) * 0.3)
+    mean, rstd, gamma, beta = par(Nc)
+    pmean, prstd, pgamma, pbeta = par(K)
+    wpT = (torch.randn(K, Nc, generator=g) / Nc ** 0.5).to(dt)
+    fake = FakeBackend()
+    sums = torch.zeros(2 * Nc)
+    fake.call('tss_bn_bwd_reduce', dict(dz=dzc, z=None, y=yc, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, M=M, C=Nc,
+                                        lddz=Nc, ldz=0, ldy=Nc, flags=relu, dtype=1))
+    outs = {}
+    for name, be, dev in (('cpu', fake, 'cpu'), ('gpu', _lib.backend(), 'cuda')):
+        t = lambda v: v.to(dev) if v is not None else None
+        dy = torch.zeros(N, H, W, Nc, dtype=dt, device=dev).permute(0, 3, 1, 2)
+        dx = torch.zeros(N, H, W, K, dtype=dt, device=dev).permute(0, 3, 1, 2)
+        dgamma, dbeta, psums = torch.ones(Nc, device=dev), torch.ones(Nc, device=dev), torch.zeros(2 * K, device=dev)
+        be.call('tss_pwconv_bwd_fused', dict(
+            dz=dzg if dev == 'cuda' else dzc, y=yg if dev == 'cuda' else yc, lddz=Nc, ldy=Nc, mean=t(mean), rstd=t(rstd),
+            gamma=t(gamma), beta=t(beta), sums=t(sums), flags=relu, count=M, dy=dy, lddy=Nc, dgamma=dgamma, dbeta=dbeta,
+            wpT=t(wpT), dx=dx, M=M, K=K, Nc=Nc, lddx=K, yp=(ypg if dev == 'cuda' else ypc) if link else None,
+            ldyp=K if link else 0, pmean=t(pmean) if link else None, prstd=t(prstd) if link else None,
+            pgamma=t(pgamma) if link else None, pbeta=t(pbeta) if link else None, pflags=1 if link else 0,
+            psums=psums if link else None))
+        outs[name] = (dy, dx, dgamma, dbeta, psums)
+    torch.cuda.synchronize()
+    c, d = outs['cpu'], outs['gpu']
+    assert rel(d[0], c[0]) < 5e-3, ('dy', rel(d[0], c[0]))
+    assert rel(d[1], c[1]) < 8e-3, ('dx', rel(d[1], c[1]))
+    assert rel(d[2], c[2]) < 1e-6 and rel(d[3], c[3]) < 1e-6
+    if link:
+        assert rel(d[4], c[4]) < 5e-3, ('psums', rel(d[4], c[4]))
+
+
+def test_training_step_with_fused_bn_apply_matches_unfused():
+    from oracle.golden_inputs import train_batch
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+    x, y = train_batch('fastscnn')
+    grads = {}
+    keep = Fn.FUSE_BNAPPLY
+    for flag in (False, True):
+        Fn.FUSE_BNAPPLY = flag
+        try:
+            torch.manual_seed(0)
+            model = fastscnn(3, 19).cuda().set_compute_dtype(torch.bfloat16).train()
+            for m in model.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+            before = _lib.launch_count()
+            CrossEntropyLoss(ignore_index=255)(model(x.cuda()), y.cuda()).backward()
+            torch.cuda.synchronize()
+            grads[flag] = ({k: p.grad.clone() for k, p in model.named_parameters()}, _lib.launch_count() - before)
+        finally:
+            Fn.FUSE_BNAPPLY = keep
+    assert grads[True][1] == grads[False][1] - 22                 # one launch less per residual-free 1x1 layer
     for k in ('classifier.3.weight', 'features.0.0.conv1.0.weight', 'downsample.1.0.weight', 'downsample.0.0.weight'):
         assert rel(grads[True][0][k], grads[False][0][k]) < 3e-2, k

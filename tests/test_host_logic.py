@@ -204,3 +204,44 @@ def test_contextnet_train_step_matches_oracle(fake_backend):
     for k in sd:
         if 'running' in k:
             assert (msd[k] - sd[k]).abs().max() < 1e-5, k
+
+
+def test_gated_backward_fusions_are_plumbing_equivalent(fake_backend):
+    """bf16 + tensor-core pointwise path on the emulated ABI: the extended fused-reduction set and the
+    BatchNorm-apply-in-dgrad kernel (both off by default, functional.FUSE_BNRED_EXT / FUSE_BNAPPLY) give the very
+    gradients of the default path, with fewer launches."""
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.nn.blocks import set_compute_dtype
+    calls = {}
+    inner = fake_backend.call
+
+    def counting(name, kwargs):
+        calls[name] = calls.get(name, 0) + 1
+        return inner(name, kwargs)
+    fake_backend.call = counting
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(2, 3, 64, 64, generator=g), torch.randint(0, 19, (2, 64, 64), generator=g)
+    keep = Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY
+    runs = {}
+    try:
+        for ext, fused in ((False, False), (True, False), (False, True), (True, True)):
+            Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY = ext, fused
+            calls.clear()
+            torch.manual_seed(0)
+            model = set_compute_dtype(_no_dropout(fastscnn(3, 19)), torch.bfloat16, pw_impl=1).train()
+            CrossEntropyLoss(ignore_index=255)(model(x), y).backward()
+            runs[ext, fused] = (torch.cat([p.grad.reshape(-1) for p in model.parameters()]), dict(calls))
+    finally:
+        Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY = keep
+    base, base_calls = runs[False, False]
+    assert base_calls.get('tss_pwconv_bwd_fused', 0) == 0 and base_calls.get('tss_dwconv3x3_dgrad_s2_bnred', 0) == 0
+    for key, (grad, c) in runs.items():
+        assert sum(c.values()) <= sum(base_calls.values())
+    # the apply-in-dgrad kernel rounds exactly where the two kernels it replaces do: identical gradients
+    assert rel(runs[False, True][0], base) < 1e-6 and rel(runs[True, True][0], runs[True, False][0]) < 1e-6
+    # a fused reduction sums the fp32 accumulators instead of the bf16-rounded gradient: bf16 noise apart
+    assert rel(runs[True, False][0], base) < 5e-2
+    assert runs[False, True][1]['tss_pwconv_bwd_fused'] == 22
+    assert runs[False, True][1]['tss_bn_bwd_apply'] == base_calls['tss_bn_bwd_apply'] - 22
+    assert runs[True, False][1]['tss_dwconv3x3_dgrad_s2_bnred'] == 4
+    assert runs[True, False][1]['tss_bn_bwd_reduce'] == base_calls['tss_bn_bwd_reduce'] - 6

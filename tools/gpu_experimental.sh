@@ -1,0 +1,16 @@
+#!/bin/bash
+# GPU-box visit for the kernels that are built but gated off (tests/test_experimental_gpu.py): every step runs
+# under its own timeout so that an unvalidated kernel cannot hold the box.  Then an A/B of the training step with
+# each gate on, same bench command as the default arm (the gate that wins AND passes becomes the default).
+#   gpurun --timeout 1500 -- 'bash tools/gpu_experimental.sh r2x'
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+TAG=${1:-r2x}
+TSS_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_experimental_gpu.py -x -q > gpurun_out/experimental_${TAG}.log 2>&1
+echo "experimental tests rc=$?"; tail -5 gpurun_out/experimental_${TAG}.log
+for arm in "base" "TSS_FUSE_BNRED_EXT=1" "TSS_FUSE_BNAPPLY=1" "TSS_FUSE_BNRED_EXT=1 TSS_FUSE_BNAPPLY=1"; do
+    name=$(echo "$arm" | tr ' =' '__')
+    if [ "$arm" = "base" ]; then envs=""; else envs="$arm"; fi
+    env $envs timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_${TAG}_${name}.json 2> gpurun_out/ab_${TAG}_${name}.err
+    echo "$arm rc=$? $(python -c "import json,sys; d=json.loads(open('gpurun_out/ab_${TAG}_${name}.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'], d['gpu_launches'])" 2>&1 | tail -1)"
+done

@@ -151,6 +151,11 @@ FUSE_BNRED = os.environ.get('TSS_FUSE_BNRED', '1') == '1'
 # BatchNorm-backward instances) and two more single-consumer pairs at 1/8 resolution (fusion low-res branch,
 # classifier).  Built and CPU-checked, not yet validated on a B200: off unless TSS_FUSE_BNRED_EXT=1.
 FUSE_BNRED_EXT = os.environ.get('TSS_FUSE_BNRED_EXT', '0') == '1'
+# BatchNorm-backward APPLY folded into the A-operand producer of the pointwise dgrad (csrc/pwconv_tc_bwd.cu):
+# dy is formed in registers and goes straight into the swizzled shared-memory tile of the tcgen05 GEMM (one
+# launch and one read of dy less per 1x1 layer without a residual).  Built and CPU-checked through the
+# emulated ABI, not yet validated on a B200: off unless TSS_FUSE_BNAPPLY=1.
+FUSE_BNAPPLY = os.environ.get('TSS_FUSE_BNAPPLY', '0') == '1'
 
 
 class _BnLink:
@@ -238,6 +243,33 @@ class ConvBNAct(torch.autograd.Function):
             gg_out, gb_out = gg, gb
         want_dres = ctx.has_res and ctx.needs_input_grad[1]
         link = ctx.link
+        prod = ctx.producer if (ctx.producer is not None and ctx.producer.usable()) else None
+        dw = gw if gw is not None else torch.zeros_like(weight)
+        wpT = ctx.packed[1] if (spec.kind == 'pw' and ctx.packed is not None) else None
+        if (FUSE_BNAPPLY and spec.kind == 'pw' and wpT is not None and spec.impl == 1 and not ctx.has_res
+                and ctx.sync[0] == 1 and ctx.needs_input_grad[0] and dz.dtype == torch.bfloat16
+                and C % 8 == 0 and weight.shape[1] % 16 == 0):
+            # one kernel: this layer's BatchNorm-backward apply -> dgrad (-> the producer's reduction)
+            if link is not None and link.reduced:
+                sums, mask = link.sums, False
+            else:
+                sums = ctx.scratch[2 * C:].view(torch.float32)
+                if spec.bn._tss_dirty or ctx.scratch is not getattr(spec.bn, '_tss_scratch', None):
+                    sums = ops.zeros_f32(2 * C, weight.device)
+                spec.bn._tss_dirty = True
+                ops.bn_backward_reduce(dz, y, mean, rstd, gamma, beta, spec.relu, sums)
+                mask = spec.relu
+            dy, dx = ops.pwconv_bwd_fused(dz, y, mean, rstd, gamma, beta, sums, mask, wpT, dgamma=gg_out, dbeta=gb_out,
+                                          link=prod)
+            if prod is not None:
+                prod.reduced, prod.bn._tss_dirty = True, True
+            if gw is not None:
+                wgrad_lane.run(dy.device, lambda: ops.pwconv_wgrad(x, dy, dw, impl=1), x, dy)
+            else:
+                ops.pwconv_wgrad(x, dy, dw, impl=1)
+            grad_ready(*ctx.params)
+            return (dx, None, None if gw is not None else dw, None if gg is not None else gg_out,
+                    None if gb is not None else gb_out, None, None, None)
         if link is not None and link.reduced:
             # the consumer's dgrad already masked the gradient and accumulated both sums
             dy, dres = ops.bn_backward(dz, None, y, mean, rstd, gamma, False, dgamma=gg_out, dbeta=gb_out, beta=beta,
@@ -249,13 +281,10 @@ class ConvBNAct(torch.autograd.Function):
             spec.bn._tss_dirty = True
             dy, dres = ops.bn_backward(dz, z, y, mean, rstd, gamma, spec.relu, want_dres=want_dres,
                                        dgamma=gg_out, dbeta=gb_out, beta=beta, sums=sums, sync=ctx.sync)
-        prod = ctx.producer if (ctx.producer is not None and ctx.producer.usable()) else None
         dx = None
-        dw = gw if gw is not None else torch.zeros_like(weight)
         # wgrad off the critical chain when it accumulates in place into the optimizer's arena
         lane = (lambda fn: wgrad_lane.run(dy.device, fn, x, dy)) if gw is not None else (lambda fn: fn())
         if spec.kind == 'pw':
-            wpT = ctx.packed[1] if ctx.packed is not None else None
             impl = spec.impl if wpT is not None else 0
             lane(lambda: ops.pwconv_wgrad(x, dy, dw, impl=impl))
             if ctx.needs_input_grad[0]:

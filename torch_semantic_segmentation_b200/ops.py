@@ -143,6 +143,33 @@ def pwconv_dgrad_bnred(dy, wpT, link):
     return g
 
 
+def pwconv_bwd_fused(dz, y, mean, rstd, gamma, beta, sums, relu, wpT, dgamma=None, dbeta=None, link=None):
+    """BatchNorm-backward apply + tcgen05 dgrad (+ the producer's reduction, ``link``) in one kernel -> dy, dx.
+    ``sums`` is the finished reduction of this layer; ``relu``: the mask is recomputed from ``y``."""
+    N, Nc, H, W, lddz = _g(dz, 'pwconv_bwd_fused')
+    K = wpT.shape[0]
+    M = N * H * W
+    dy = empty_nhwc(N, Nc, H, W, dz.dtype, dz.device)
+    dx = empty_nhwc(N, K, H, W, dz.dtype, dz.device)
+    _lib.call('tss_pwconv_bwd_fused', dz=dz, y=y, lddz=lddz, ldy=_g(y, 'pwconv_bwd_fused')[4], mean=mean, rstd=rstd,
+              gamma=gamma, beta=beta, sums=sums, flags=_flags(relu), count=M, dy=dy, lddy=Nc, dgamma=dgamma,
+              dbeta=dbeta, wpT=wpT, dx=dx, M=M, K=K, Nc=Nc, lddx=K,
+              yp=link.y if link is not None else None,
+              ldyp=_g(link.y, 'pwconv_bwd_fused')[4] if link is not None else 0,
+              pmean=link.mean if link is not None else None, prstd=link.rstd if link is not None else None,
+              pgamma=link.gamma if link is not None else None, pbeta=link.beta if link is not None else None,
+              pflags=_flags(link.relu) if link is not None else 0, psums=link.sums if link is not None else None)
+    return dy, dx
+
+
+def bn_backward_reduce(dz, y, mean, rstd, gamma, beta, relu, sums):
+    """The reduction pass of ``bn_backward`` alone (mask recomputed from ``y``); ``sums`` zeroed by the caller."""
+    N, C, H, W, lddz = _g(dz, 'bn_backward_reduce')
+    _lib.call('tss_bn_bwd_reduce', dz=dz, z=None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums,
+              M=N * H * W, C=C, lddz=lddz, ldz=0, ldy=_g(y, 'bn_backward_reduce')[4], flags=_flags(relu),
+              dtype=dtype_code(dz.dtype))
+
+
 def dwconv_dgrad_bnred(dy, w, link):
     """stride-1 depthwise dgrad + the producer's BatchNorm-backward reduction -> g."""
     N, C, H, W, ld = _g(dy, 'dwconv_dgrad_bnred')
