@@ -312,6 +312,20 @@ int tss_confusion_from_logits(const void* logits, const int64_t* target, int N, 
 int tss_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float* hyper,
                    float grad_scale, void* stream);
 
+/* ---- input pipeline on the device --------------------------------------
+ * One launch for a batch of decoded samples: label ids -> train ids (TRAIN_MAPPING, data/cityscapes.py:17-20,88),
+ * then albu.RandomScale -> RandomCrop -> HorizontalFlip -> Normalize -> ToTensor (scripts/train_fastscnn.py:62-68)
+ * with the random draws supplied by the caller.  images: uint8 [N][H][W][3] (RGB), labels: uint8 [N][H][W] (or
+ * NULL together with out_label).  geom: DEVICE int32 [N][5] = {scaled height, scaled width, crop y, crop x,
+ * flip} per sample (scaled size = int(H*scale), int(W*scale); crop start inside the scaled image).
+ * lut: DEVICE int64 [256] (NULL = identity).  norm: HOST float [6] = mean*255 (3), 1/(std*255) (3).
+ * out_image: fp32 [N][3][ch][cw] (what the stem reads), out_label: int64 [N][ch][cw]; cw % 4 == 0.
+ * Bit-identical to the CPU pipeline: OpenCV's uint8 INTER_LINEAR fixed-point arithmetic (image) and
+ * INTER_NEAREST index rule (labels) are reproduced exactly; scale 1 / crop 0 is the evaluation transform. */
+int tss_augment_batch(const void* images, const void* labels, const int* geom, const int64_t* lut,
+                      const float* norm, float* out_image, int64_t* out_label, int N, int H, int W, int ch,
+                      int cw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -152,6 +152,28 @@ class FakeBackend:
             dst.copy_(src.detach().reshape(Cout, Cin, 9).permute(0, 2, 1).reshape(Cout, 9 * Cin, 1, 1))
         return 0
 
+    # ---------------------------------------------------------------- input pipeline
+    def tss_augment_batch(self, images, labels, geom, lut, norm, out_image, out_label, N, H, W, ch, cw):
+        import numpy as np
+        from oracle import augment as A            # tests/ infrastructure may use the oracle
+        mean, inv = np.array(norm.values[:3], dtype=np.float32), np.array(norm.values[3:], dtype=np.float32)
+        for n in range(N):
+            nh, nw, cy, cx, flip = (int(v) for v in geom[n])
+            img = A.resize_linear_u8(images[n].numpy(), nh, nw)[cy:cy + ch, cx:cx + cw]
+            if flip:
+                img = img[:, ::-1]
+            x = img.astype(np.float32)
+            x -= mean
+            x *= inv
+            out_image[n].copy_(torch.from_numpy(np.ascontiguousarray(x.transpose(2, 0, 1))))
+            if labels is not None:
+                lab = A.resize_nearest(labels[n].numpy(), nh, nw)[cy:cy + ch, cx:cx + cw]
+                if flip:
+                    lab = lab[:, ::-1]
+                lab = torch.from_numpy(np.ascontiguousarray(lab)).long()
+                out_label[n].copy_(lut[lab] if lut is not None else lab)
+        return 0
+
     # ---------------------------------------------------------------- stem
     def tss_stem3x3s2_fwd(self, x, w, y, N, H, W, Cout, scale, shift, flags, stats, dtype):
         raw = F.conv2d(x, w, None, 2, 1)

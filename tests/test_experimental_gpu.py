@@ -5,7 +5,9 @@ unvalidated kernel can never hang the default GPU suite.
 * stride-2 depthwise dgrad with the producer's BatchNorm-backward reduction fused into its epilogue
   (csrc/dwconv_bnred.cu: dw_dgrad_s2_bnred_kernel; enabled in the model by TSS_FUSE_BNRED_EXT=1);
 * pointwise backward with the layer's BatchNorm-backward apply folded into the GEMM's A-operand producer
-  (csrc/pwconv_tc_bwd.cu: pw_tc_bwd_kernel; enabled in the model by TSS_FUSE_BNAPPLY=1)."""
+  (csrc/pwconv_tc_bwd.cu: pw_tc_bwd_kernel; enabled in the model by TSS_FUSE_BNAPPLY=1);
+* the device input pipeline (csrc/augment.cu; its per-pixel arithmetic is already pinned on the host by
+  tests/test_data_cpu.py, the launch itself is what remains to be run)."""
 import os
 
 import pytest
@@ -147,3 +149,30 @@ def test_training_step_with_fused_bn_apply_matches_unfused():
     assert grads[True][1] == grads[False][1] - 22                 # one launch less per residual-free 1x1 layer
     for k in ('classifier.3.weight', 'features.0.0.conv1.0.weight', 'downsample.1.0.weight', 'downsample.0.0.weight'):
         assert rel(grads[True][0][k], grads[False][0][k]) < 3e-2, k
+
+
+def test_device_input_pipeline_is_bit_exact_with_the_cpu_pipeline():
+    import numpy as np
+    from oracle import augment as A
+    from torch_semantic_segmentation_b200.data import DeviceTransform, eval_transform
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'augment.npz'))
+    for seed, h, w, scale, hf, wf, flip, crop in A.GOLDEN_CASES:
+        img, lab = A.sample(seed, h, w)
+        t = DeviceTransform(crop=crop)
+        x, y = t(torch.from_numpy(img)[None].cuda(), torch.from_numpy(lab)[None].cuda(), draws=[(scale, hf, wf, bool(flip))])
+        np.testing.assert_array_equal(x[0].cpu().numpy(), gold['image_%d' % seed])
+        np.testing.assert_array_equal(y[0].cpu().numpy(), gold['label_%d' % seed].astype(np.int64))
+    # a Cityscapes-sized batch: the reference's crop at both ends of its scale range, and the evaluation transform
+    samples = [A.sample(40 + i, 1024, 2048) for i in range(2)]
+    images = torch.from_numpy(np.stack([s[0] for s in samples])).cuda()
+    labels = torch.from_numpy(np.stack([s[1] for s in samples])).cuda()
+    draws = [(1.5, 0.25, 0.75, True), (3.0, 0.9, 0.1, False)]
+    x, y = DeviceTransform(crop=(512, 768))(images, labels, draws=draws)
+    for i, d in enumerate(draws):
+        ex, ey = A.train_transform(samples[i][0], samples[i][1], d[0], d[1], d[2], d[3], (512, 768))
+        np.testing.assert_array_equal(x[i].cpu().numpy(), ex)
+        np.testing.assert_array_equal(y[i].cpu().numpy(), ey)
+    x, y = eval_transform()(images, labels)
+    ex, ey = A.eval_transform(*samples[1])
+    np.testing.assert_array_equal(x[1].cpu().numpy(), ex)
+    np.testing.assert_array_equal(y[1].cpu().numpy(), ey)

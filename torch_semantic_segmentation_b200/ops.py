@@ -579,3 +579,31 @@ def confusion_from_logits(logits, target, cm, want_pred=False):
 def adamw_step(p, g, m, v, hyper, grad_scale=1.0):
     _lib.call('tss_adamw_step', p=p, g=g, m=m, v=v, n=p.numel(), hyper=hyper, grad_scale=float(grad_scale))
     WEIGHTS_EPOCH[0] += 1
+
+
+# ------------------------------------------------------------------ input pipeline ------
+class _HostFloats:
+    """A small host float array argument (``const float*`` read by the launcher, not a kernel)."""
+
+    def __init__(self, values):
+        import ctypes
+        self.values = tuple(float(v) for v in values)
+        self.array = (ctypes.c_float * len(self.values))(*self.values)
+
+
+def augment_batch(images, labels, geom, lut, norm, crop):
+    """uint8 (N,H,W,3) frames + uint8 (N,H,W) label ids + per-sample draws ``geom`` (int32 (N,5) on the device)
+    -> fp32 (N,3,ch,cw) normalised crops, int64 (N,ch,cw) train ids.  ``norm``: 6 host floats."""
+    if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] != 3 or not images.is_contiguous():
+        raise RuntimeError('augment_batch: images must be a contiguous uint8 (N,H,W,3) tensor')
+    N, H, W, _ = images.shape
+    if labels is not None and (labels.dtype != torch.uint8 or tuple(labels.shape) != (N, H, W) or not labels.is_contiguous()):
+        raise RuntimeError('augment_batch: labels must be a contiguous uint8 (N,H,W) tensor')
+    if geom.dtype != torch.int32 or tuple(geom.shape) != (N, 5) or not geom.is_contiguous():
+        raise RuntimeError('augment_batch: geom must be a contiguous int32 (N,5) tensor')
+    ch, cw = crop
+    x = torch.empty((N, 3, ch, cw), dtype=torch.float32, device=images.device)
+    y = torch.empty((N, ch, cw), dtype=torch.int64, device=images.device) if labels is not None else None
+    _lib.call('tss_augment_batch', images=images, labels=labels, geom=geom, lut=lut, norm=_HostFloats(norm),
+              out_image=x, out_label=y, N=N, H=H, W=W, ch=ch, cw=cw)
+    return x, y
