@@ -312,6 +312,29 @@ int tss_confusion_from_logits(const void* logits, const int64_t* target, int N, 
 int tss_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float* hyper,
                    float grad_scale, void* stream);
 
+/* ---- pyramid pooling branches, grouped (training) ------------------------------------------------------
+ * PyramidPoolingModule (fastscnn.py:101-123): nbins x [AdaptiveAvgPool2d(b) -> Conv2d(C, Cb, 1) -> BatchNorm2d ->
+ * ReLU] -> bilinear (align_corners=True) -> cat([x, branches]).  pool = the output of tss_adaptive_pool_fwd:
+ * [N*sum(b*b)][C], branch-major.  y / z / dz / dy: [N*sum(b*b)][Cb] in the same row order (raw conv output /
+ * activated / gradients).  table: DEVICE int64 [nbins][10] of addresses per branch = {weight (Cb,C) fp32, gamma,
+ * beta, running_mean, running_var, num_batches_tracked (int64), dweight, dgamma, dbeta, 0}; 0 = absent.
+ * branches_fwd: conv + batch statistics + finalize (mean/rstd out: [nbins][Cb]; running statistics updated with
+ *   momentum, unbiased variance) + affine + ReLU, one launch.  A branch with a single value per channel is an error.
+ * concat_fwd: cat[N][H][W][C + nbins*Cb] = [x, up(z_0), ..., up(z_{nbins-1})].
+ * concat_bwd: dz = transpose of the up-samplings applied to dcat[..., C:] (dcat pitch lddcat).
+ * branches_bwd: ReLU mask (from y) + BatchNorm backward -> dy; dgamma += , dbeta += ; dpool[N*sum(b*b)][C] =
+ *   dy . w; dweight += dy^T . pool (two launches). */
+int tss_ppm_branches_fwd(const void* pool, const int64_t* table, void* y, void* z, float* mean, float* rstd,
+                         int N, int C, int Cb, const int* bins, int nbins, float momentum, float eps, int dtype,
+                         void* stream);
+int tss_ppm_concat_fwd(const void* x, const void* z, void* cat, int N, int H, int W, int C, int Cb,
+                       const int* bins, int nbins, int dtype, void* stream);
+int tss_ppm_concat_bwd(const void* dcat, void* dz, int N, int H, int W, int C, int Cb, int64_t lddcat,
+                       const int* bins, int nbins, int dtype, void* stream);
+int tss_ppm_branches_bwd(const void* dz, const void* y, const void* pool, const int64_t* table, const float* mean,
+                         const float* rstd, void* dy, void* dpool, int N, int C, int Cb, const int* bins, int nbins,
+                         int dtype, void* stream);
+
 /* ---- input pipeline on the device --------------------------------------
  * One launch for a batch of decoded samples: label ids -> train ids (TRAIN_MAPPING, data/cityscapes.py:17-20,88),
  * then albu.RandomScale -> RandomCrop -> HorizontalFlip -> Normalize -> ToTensor (scripts/train_fastscnn.py:62-68)

@@ -152,6 +152,84 @@ class FakeBackend:
             dst.copy_(src.detach().reshape(Cout, Cin, 9).permute(0, 2, 1).reshape(Cout, 9 * Cin, 1, 1))
         return 0
 
+    # ---------------------------------------------------------------- pyramid pooling, grouped
+    @staticmethod
+    def _at(addr, n, dtype=torch.float32):
+        """A tensor over ``n`` elements at a host address taken from the kernels' address table."""
+        import ctypes
+        if addr == 0:
+            return None
+        ctype = ctypes.c_float if dtype == torch.float32 else ctypes.c_int64
+        return torch.frombuffer((ctype * n).from_address(int(addr)), dtype=dtype)
+
+    @staticmethod
+    def _branch_rows(N, bins):
+        off = 0
+        for b in bins.values:
+            yield b, off, off + N * b * b
+            off += N * b * b
+
+    def tss_ppm_branches_fwd(self, pool, table, y, z, mean, rstd, N, C, Cb, bins, nbins, momentum, eps, dtype):
+        for i, (b, lo, hi) in enumerate(self._branch_rows(N, bins)):
+            t = table[i].tolist()
+            w, gamma, beta = self._at(t[0], Cb * C).view(Cb, C), self._at(t[1], Cb), self._at(t[2], Cb)
+            raw = pool[lo:hi].float() @ w.t()
+            M = hi - lo
+            assert M > 1
+            mu = raw.double().mean(0)
+            var = (raw.double() ** 2).mean(0) - mu * mu
+            rs = (1.0 / torch.sqrt(var.clamp_min(0) + eps)).float()
+            mean[i].copy_(mu.float())
+            rstd[i].copy_(rs)
+            y[lo:hi].copy_(raw)
+            sc = gamma * rs
+            z[lo:hi].copy_(torch.addcmul(beta - mu.float() * sc, y[lo:hi].float(), sc).clamp_min(0))
+            rm, rv, nbt = self._at(t[3], Cb), self._at(t[4], Cb), self._at(t[5], 1, torch.int64)
+            if rm is not None:
+                rm.mul_(1 - momentum).add_(momentum * mu.float())
+                rv.mul_(1 - momentum).add_(momentum * (var.clamp_min(0) * M / (M - 1)).float())
+            if nbt is not None:
+                nbt += 1
+        return 0
+
+    def tss_ppm_concat_fwd(self, x, z, cat, N, H, W, C, Cb, bins, nbins, dtype):
+        cat[:, :C].copy_(x)
+        for i, (b, lo, hi) in enumerate(self._branch_rows(N, bins)):
+            zi = z[lo:hi].view(N, b, b, Cb).permute(0, 3, 1, 2).float()
+            cat[:, C + i * Cb:C + (i + 1) * Cb].copy_(F.interpolate(zi, size=(H, W), mode='bilinear', align_corners=True))
+        return 0
+
+    def tss_ppm_concat_bwd(self, dcat, dz, N, H, W, C, Cb, lddcat, bins, nbins, dtype):
+        for i, (b, lo, hi) in enumerate(self._branch_rows(N, bins)):
+            with torch.enable_grad():
+                zi = torch.zeros(N, Cb, b, b, requires_grad=True)
+                up = F.interpolate(zi, size=(H, W), mode='bilinear', align_corners=True)
+                (g,) = torch.autograd.grad(up, zi, dcat[:, C + i * Cb:C + (i + 1) * Cb].float())
+            dz[lo:hi].copy_(g.permute(0, 2, 3, 1).reshape(hi - lo, Cb))
+        return 0
+
+    def tss_ppm_branches_bwd(self, dz, y, pool, table, mean, rstd, dy, dpool, N, C, Cb, bins, nbins, dtype):
+        for i, (b, lo, hi) in enumerate(self._branch_rows(N, bins)):
+            t = table[i].tolist()
+            w, gamma, beta = self._at(t[0], Cb * C).view(Cb, C), self._at(t[1], Cb), self._at(t[2], Cb)
+            M = hi - lo
+            sc = gamma * rstd[i]
+            yy = y[lo:hi].float()
+            g = dz[lo:hi].float() * (torch.addcmul(beta - mean[i] * sc, yy, sc) > 0)
+            xh = (yy - mean[i]) * rstd[i]
+            s1, s2 = g.sum(0), (g * xh).sum(0)
+            dy[lo:hi].copy_(sc * (g - s1 / M - xh * s2 / M))
+            dw, dgamma, dbeta = self._at(t[6], Cb * C), self._at(t[7], Cb), self._at(t[8], Cb)
+            if dbeta is not None:
+                dbeta += s1
+            if dgamma is not None:
+                dgamma += s2
+            d = dy[lo:hi].float()
+            dpool[lo:hi].copy_(d @ w)
+            if dw is not None:
+                dw += (d.t() @ pool[lo:hi].float()).reshape(-1)
+        return 0
+
     # ---------------------------------------------------------------- input pipeline
     def tss_augment_batch(self, images, labels, geom, lut, norm, out_image, out_label, N, H, W, ch, cw):
         import numpy as np

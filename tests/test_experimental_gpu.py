@@ -6,6 +6,7 @@ unvalidated kernel can never hang the default GPU suite.
   (csrc/dwconv_bnred.cu: dw_dgrad_s2_bnred_kernel; enabled in the model by TSS_FUSE_BNRED_EXT=1);
 * pointwise backward with the layer's BatchNorm-backward apply folded into the GEMM's A-operand producer
   (csrc/pwconv_tc_bwd.cu: pw_tc_bwd_kernel; enabled in the model by TSS_FUSE_BNAPPLY=1);
+* the pyramid-pooling branches as grouped launches (csrc/ppm.cu; enabled in the model by TSS_FUSE_PPM=1);
 * the device input pipeline (csrc/augment.cu; its per-pixel arithmetic is already pinned on the host by
   tests/test_data_cpu.py, the launch itself is what remains to be run)."""
 import os
@@ -176,3 +177,69 @@ def test_device_input_pipeline_is_bit_exact_with_the_cpu_pipeline():
     ex, ey = A.eval_transform(*samples[1])
     np.testing.assert_array_equal(x[1].cpu().numpy(), ex)
     np.testing.assert_array_equal(y[1].cpu().numpy(), ey)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape', [(12, 24, 24), (2, 32, 64), (3, 5, 7), (2, 1, 1)])
+def test_grouped_pyramid_pooling_matches_layer_by_layer(shape, dtype):
+    from torch_semantic_segmentation_b200 import functional as Fn, ops
+    from torch_semantic_segmentation_b200.models.fastscnn import PyramidPoolingModule
+    from torch_semantic_segmentation_b200.nn.blocks import set_compute_dtype
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    N, H, W = shape
+    keep = Fn.FUSE_PPM
+    runs = {}
+    try:
+        for flag in (False, True):
+            Fn.FUSE_PPM = flag
+            torch.manual_seed(0)
+            m = set_compute_dtype(PyramidPoolingModule(128, 128), dtype, pw_impl=0).cuda().train()
+            FlatAdamW(m.parameters(), lr=1e-3).zero_grad()
+            g = torch.Generator().manual_seed(1)
+            x = ops.as_nhwc(torch.randn(N, 128, H, W, generator=g).to(dtype).cuda()).requires_grad_()
+            before = _lib.launch_count()
+            out = m(x)
+            (out.float() * torch.randn(out.shape, generator=g).cuda()).sum().backward()
+            torch.cuda.synchronize()
+            runs[flag] = (out.detach(), x.grad, {k: p.grad.clone() for k, p in m.named_parameters()},
+                          {k: v.clone().float() for k, v in m.state_dict().items() if 'running' in k or 'tracked' in k},
+                          _lib.launch_count() - before)
+    finally:
+        Fn.FUSE_PPM = keep
+    a, b = runs[False], runs[True]
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert rel(b[0], a[0]) < tol and rel(b[1], a[1]) < 2 * tol
+    for k in a[2]:
+        assert rel(b[2][k], a[2][k]) < 3 * tol, k
+    for k in a[3]:
+        assert rel(b[3][k], a[3][k]) < tol, k
+    assert b[4] <= a[4] - 30
+
+
+def test_training_step_with_grouped_pyramid_pooling_matches_default():
+    from oracle.golden_inputs import train_batch
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    x, y = train_batch('fastscnn')
+    out = {}
+    keep = Fn.FUSE_PPM
+    for flag in (False, True):
+        Fn.FUSE_PPM = flag
+        try:
+            torch.manual_seed(0)
+            model = fastscnn(3, 19).cuda().train()
+            for m in model.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+            FlatAdamW(model.parameters(), lr=1e-3).zero_grad()
+            logits = model(x.cuda())
+            loss = CrossEntropyLoss(ignore_index=255)(logits, y.cuda())
+            loss.backward()
+            torch.cuda.synchronize()
+            out[flag] = (float(loss), logits.detach(), model.classifier[3].weight.grad.clone())
+        finally:
+            Fn.FUSE_PPM = keep
+    assert abs(out[True][0] - out[False][0]) < 1e-4 * abs(out[False][0])
+    assert rel(out[True][1], out[False][1]) < 1e-4 and rel(out[True][2], out[False][2]) < 1e-3

@@ -245,3 +245,40 @@ def test_gated_backward_fusions_are_plumbing_equivalent(fake_backend):
     assert runs[False, True][1]['tss_bn_bwd_apply'] == base_calls['tss_bn_bwd_apply'] - 22
     assert runs[True, False][1]['tss_dwconv3x3_dgrad_s2_bnred'] == 4
     assert runs[True, False][1]['tss_bn_bwd_reduce'] == base_calls['tss_bn_bwd_reduce'] - 6
+
+
+def test_grouped_pyramid_pooling_is_plumbing_equivalent(fake_backend):
+    """functional.FUSE_PPM (off by default): pool -> grouped branches -> concat and their backward give the
+    layer-by-layer module's output, input gradient, parameter gradients and BatchNorm buffers."""
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.models.fastscnn import PyramidPoolingModule
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    keep = Fn.FUSE_PPM
+    runs = {}
+    try:
+        for flag in (False, True):
+            Fn.FUSE_PPM = flag
+            torch.manual_seed(0)
+            m = PyramidPoolingModule(128, 128).train()
+            FlatAdamW(m.parameters(), lr=1e-3).zero_grad()
+            g = torch.Generator().manual_seed(1)
+            x = ops.as_nhwc(torch.randn(5, 128, 6, 9, generator=g)).requires_grad_()
+            before = fake_backend.launches
+            out = m(x)
+            (out * torch.randn(out.shape, generator=g)).sum().backward()
+            runs[flag] = (out.detach(), x.grad, {k: p.grad.clone() for k, p in m.named_parameters()},
+                          {k: v.clone().float() for k, v in m.state_dict().items() if 'running' in k or 'tracked' in k},
+                          fake_backend.launches - before)
+    finally:
+        Fn.FUSE_PPM = keep
+    a, b = runs[False], runs[True]
+    assert rel(b[0], a[0]) < 1e-5 and rel(b[1], a[1]) < 1e-5
+    assert all(rel(b[2][k], a[2][k]) < 1e-5 for k in a[2]) and all(rel(b[3][k], a[3][k]) < 1e-5 for k in a[3])
+    assert b[4] <= a[4] - 30
+    # a batch of one still fails like the reference (BatchNorm over a single value in the bin-1 branch)
+    Fn.FUSE_PPM = True
+    try:
+        with pytest.raises(RuntimeError, match='more than 1 value per channel'):
+            PyramidPoolingModule(128, 128).train()(torch.randn(1, 128, 6, 9))
+    finally:
+        Fn.FUSE_PPM = keep

@@ -156,6 +156,9 @@ FUSE_BNRED_EXT = os.environ.get('TSS_FUSE_BNRED_EXT', '0') == '1'
 # launch and one read of dy less per 1x1 layer without a residual).  Built and CPU-checked through the
 # emulated ABI, not yet validated on a B200: off unless TSS_FUSE_BNAPPLY=1.
 FUSE_BNAPPLY = os.environ.get('TSS_FUSE_BNAPPLY', '0') == '1'
+# The four pyramid-pooling branches as grouped launches (csrc/ppm.cu): 3 launches forward and 5 backward instead
+# of ~18 and ~26.  Same status: off unless TSS_FUSE_PPM=1.
+FUSE_PPM = os.environ.get('TSS_FUSE_PPM', '0') == '1'
 
 
 class _BnLink:
@@ -437,6 +440,37 @@ class PPMConcat(torch.autograd.Function):
             dzs.append(ops.bilinear_bwd(dcat[:, off:off + shp[1]], shp[2], shp[3]))
             off += shp[1]
         return (dx, *dzs)
+
+
+class PPMBranches(torch.autograd.Function):
+    """cat([x, up(relu(bn(conv1x1(pool_b(x)))))...]) for all pyramid bins (fastscnn.py:101-122) with grouped
+    kernels.  ``state`` carries the bins, the BatchNorm hyper-parameters and the device table of parameter /
+    buffer / gradient-arena addresses; ``params`` (weight, gamma, beta per branch) are only listed so that
+    autograd knows the node and the reducer hears about their gradients."""
+
+    @staticmethod
+    def forward(ctx, x, state, *params):
+        N, C, H, W = x.shape
+        Cb = params[0].shape[0]
+        pool, _ = ops.adaptive_pool_fwd(x, state.bins)
+        y, z, mean, rstd = ops.ppm_branches_fwd(pool, state.table, N, C, Cb, state.bins, state.momentum, state.eps)
+        cat = ops.ppm_concat_fwd(x, z, Cb, state.bins)
+        ctx.save_for_backward(pool, y, mean, rstd)
+        ctx.state, ctx.params, ctx.shape = state, params, (N, C, H, W, Cb)
+        return cat
+
+    @staticmethod
+    def backward(ctx, dcat):
+        pool, y, mean, rstd = ctx.saved_tensors
+        N, C, H, W, Cb = ctx.shape
+        st = ctx.state
+        dcat = ops.as_nhwc(dcat)
+        dz = ops.ppm_concat_bwd(dcat, C, Cb, st.bins)
+        dpool = ops.ppm_branches_bwd(dz, y, pool, st.table, mean, rstd, N, st.bins)
+        dx = ops.copy_rows(dcat[:, :C], ops.empty_nhwc(N, C, H, W, dcat.dtype, dcat.device))
+        ops.adaptive_pool_bwd(dpool, dx, st.bins, accumulate=True)
+        grad_ready(*ctx.params)
+        return (dx, None) + (None,) * len(ctx.params)
 
 
 class Bilinear(torch.autograd.Function):

@@ -109,6 +109,11 @@ def Classifier(in_channels, out_channels):
     return head
 
 
+class _GroupedPPM:
+    """bins, BatchNorm hyper-parameters and the device address table of the grouped pyramid kernels."""
+    __slots__ = ('key', 'bins', 'momentum', 'eps', 'table')
+
+
 class PyramidPoolingModule(nn.Module):
     """reference: models/fastscnn.py:101-123.  One pooling pass for all bins; the bilinear
     up-samplings write straight into the concat buffer."""
@@ -125,8 +130,42 @@ class PyramidPoolingModule(nn.Module):
         ])
         self.conv = Conv2dBlock(in_channels * 2, out_channels, kernel_size=1)
 
+    def _grouped_state(self, x):
+        """Device table of addresses for the grouped kernels (csrc/ppm.cu), or None when this call has to take the
+        layer-by-layer path (eval mode, no gradient arena, SyncBN, mixed BatchNorm settings)."""
+        if not (Fn.FUSE_PPM and self.training and torch.is_grad_enabled()):
+            return None
+        convs = [p[1][0] for p in self.pyramids]
+        bns = [p[1][1] for p in self.pyramids]
+        if any(getattr(bn, '_tss_sync', None) is not None or bn.momentum is None or not bn.affine for bn in bns):
+            return None
+        if len({(float(bn.momentum), float(bn.eps), bn.track_running_stats) for bn in bns}) != 1:
+            return None
+        if x.dtype != self.pyramids[0][1].compute_dtype or x.shape[0] * min(self.bins) ** 2 < 2:
+            return None
+        ptrs = []
+        for conv, bn in zip(convs, bns):
+            grads = [getattr(t, '_tss_grad', None) for t in (conv.weight, bn.weight, bn.bias)]
+            if any(g is None for g in grads) or conv.weight.device != x.device:
+                return None
+            stats = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if bn.track_running_stats else (None,) * 3
+            ptrs.append([conv.weight.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr()] +
+                        [t.data_ptr() if t is not None else 0 for t in stats] + [g.data_ptr() for g in grads] + [0])
+        key = (x.device, tuple(map(tuple, ptrs)))
+        st = getattr(self, '_grouped', None)
+        if st is None or st.key != key:
+            st = self._grouped = _GroupedPPM()
+            st.key, st.bins = key, self.bins
+            st.momentum, st.eps = float(bns[0].momentum), float(bns[0].eps)
+            st.table = torch.tensor(ptrs, dtype=torch.int64).to(x.device)
+        return st
+
     def forward(self, input):
         x = ops.as_nhwc(input)
+        st = self._grouped_state(x)
+        if st is not None:
+            params = [t for p in self.pyramids for t in (p[1][0].weight, p[1][1].weight, p[1][1].bias)]
+            return self.conv(Fn.PPMBranches.apply(x, st, *params))
         pooled = Fn.AdaptivePool.apply(x, self.bins)
         zs = [pyramid[1](p) for pyramid, p in zip(self.pyramids, pooled)]
         cat = Fn.PPMConcat.apply(x, *zs)

@@ -429,6 +429,48 @@ def adaptive_pool_bwd(dbuf, dx, bins=PYRAMID_BINS, accumulate=False):
     return dx
 
 
+# ------------------------------------------------------------------ pyramid pooling, grouped ------
+def ppm_branches_fwd(pool, table, N, C, Cb, bins, momentum, eps):
+    """All pyramid branches in one launch: 1x1 conv + BatchNorm(train) + ReLU on the pooled rows.
+    -> y (raw conv output), z (activated), mean, rstd ((nbins, Cb) fp32)."""
+    rows = pool.shape[0]
+    y = torch.empty((rows, Cb), dtype=pool.dtype, device=pool.device)
+    z = torch.empty((rows, Cb), dtype=pool.dtype, device=pool.device)
+    mean = torch.empty((len(bins), Cb), dtype=torch.float32, device=pool.device)
+    rstd = torch.empty((len(bins), Cb), dtype=torch.float32, device=pool.device)
+    _lib.call('tss_ppm_branches_fwd', pool=pool, table=table, y=y, z=z, mean=mean, rstd=rstd, N=N, C=C, Cb=Cb,
+              bins=_HostInts(bins), nbins=len(bins), momentum=float(momentum), eps=float(eps), dtype=dtype_code(pool.dtype))
+    return y, z, mean, rstd
+
+
+def ppm_concat_fwd(x, z, Cb, bins):
+    N, C, H, W, ld = _g(x, 'ppm_concat_fwd')
+    if ld != C:
+        raise RuntimeError('ppm_concat_fwd: pitched input not supported')
+    cat = empty_nhwc(N, C + len(bins) * Cb, H, W, x.dtype, x.device)
+    _lib.call('tss_ppm_concat_fwd', x=x, z=z, cat=cat, N=N, H=H, W=W, C=C, Cb=Cb, bins=_HostInts(bins),
+              nbins=len(bins), dtype=dtype_code(x.dtype))
+    return cat
+
+
+def ppm_concat_bwd(dcat, C, Cb, bins):
+    N, Ct, H, W, ld = _g(dcat, 'ppm_concat_bwd')
+    dz = torch.empty((N * sum(b * b for b in bins), Cb), dtype=dcat.dtype, device=dcat.device)
+    _lib.call('tss_ppm_concat_bwd', dcat=dcat, dz=dz, N=N, H=H, W=W, C=C, Cb=Cb, lddcat=ld, bins=_HostInts(bins),
+              nbins=len(bins), dtype=dtype_code(dcat.dtype))
+    return dz
+
+
+def ppm_branches_bwd(dz, y, pool, table, mean, rstd, N, bins):
+    """-> dpool; the parameter gradients are accumulated through the addresses in ``table``."""
+    C, Cb = pool.shape[1], y.shape[1]
+    dy = torch.empty_like(dz)
+    dpool = torch.empty_like(pool)
+    _lib.call('tss_ppm_branches_bwd', dz=dz, y=y, pool=pool, table=table, mean=mean, rstd=rstd, dy=dy, dpool=dpool,
+              N=N, C=C, Cb=Cb, bins=_HostInts(bins), nbins=len(bins), dtype=dtype_code(dz.dtype))
+    return dpool
+
+
 class _HostInts:
     """A small host int array argument (``const int*`` read by the launcher, not a kernel)."""
 
