@@ -1,0 +1,24 @@
+// State of the SIMT emulation + the few host-side library functions the launchers call (csrc/api.cu's role).
+#include <stdarg.h>
+
+#include "cuda_runtime.h"
+
+namespace tss_emu {
+thread_local Block* block = nullptr;
+alignas(1024) unsigned char dyn_smem[256 * 1024];
+}  // namespace tss_emu
+thread_local uint3 threadIdx, blockIdx;
+thread_local dim3 blockDim, gridDim;
+
+static char g_err[512];
+static unsigned long long g_launches = 0;
+bool tss_pdl_enabled() { return false; }
+void tss_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void tss_count_launch(int n) { g_launches += n; }
+extern "C" const char* tss_last_error(void) { return g_err; }
+extern "C" unsigned long long tss_launch_count(void) { return g_launches; }

@@ -62,11 +62,18 @@ bool tss_pdl_enabled();
 // of this grid has started (its last wave is running): they fill the SM slots this grid's tail
 // frees, parked in their own griddepcontrol.wait, and never starve this grid's own CTAs.
 __device__ __forceinline__ void pdl_wait() {
+#ifndef TSS_HOST_EMU
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifndef TSS_NO_PDL_TRIGGER
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
+#endif
 }
+
+// Dynamic shared memory of the CTA.  (tests/simt_emu/ redefines this for host builds of the plain SIMT kernels.)
+#ifndef TSS_DYN_SMEM
+#define TSS_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#endif
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t tss_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kThreads)
 ppm_branches_fwd_kernel(const T* __restrict__ pool, const int64_t* __restrict__ table, T* y, T* __restrict__ z,
                         float* __restrict__ mean_out, float* __restrict__ rstd_out, int C, int Cb, PpmBins bins,
                         float momentum, float eps) {
-    extern __shared__ __align__(16) float s_w[];                       // [8][C]
+    TSS_DYN_SMEM(float, s_w);                            // [8][C]
     __shared__ float s_part[(kThreads / 32) * 16];
     __shared__ double s_sum[16];
     __shared__ float s_aff[16];                          // scale[8], shift[8]
@@ -188,7 +188,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 ppm_concat_bwd_kernel(const T* __restrict__ dcat, T* __restrict__ dz, int N, int H, int W, int C, int Cb,
                       int64_t lddcat, PpmBins bins) {
-    extern __shared__ __align__(16) float s_tmp[];                     // [b][W][Cb]
+    TSS_DYN_SMEM(float, s_tmp);                          // [b][W][Cb]
     pdl_wait();
     const int n = blockIdx.x, br = blockIdx.y;
     const int b = bins.b[br];
@@ -314,7 +314,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 ppm_dgrad_wgrad_kernel(const T* __restrict__ dy, const T* __restrict__ pool, const int64_t* __restrict__ table,
                        T* __restrict__ dpool, int C, int Cb, PpmBins bins, int chunks) {
-    extern __shared__ __align__(16) float s_w[];                       // dgrad: [Cb][C]
+    TSS_DYN_SMEM(float, s_w);                            // dgrad: [Cb][C]
     pdl_wait();
     const int br = blockIdx.y;
     const int row0 = bins.row0[br], M = bins.row0[br + 1] - row0;
