@@ -21,4 +21,11 @@ void tss_set_error(const char* fmt, ...) {
 }
 void tss_count_launch(int n) { g_launches += n; }
 extern "C" const char* tss_last_error(void) { return g_err; }
-extern "C" unsigned long long tss_launch_count(void) { return g_launches; }
+extern "C" uint64_t tss_launch_count(void) { return g_launches; }
+
+#include "tcgen05_emu.h"
+namespace tss_emu {
+MBar mbars[sizeof(dyn_smem) / 8];
+std::mutex mbar_mutex;
+float tmem[128][512];
+}  // namespace tss_emu

@@ -1,0 +1,143 @@
+// Functional emulation of the tcgen05 / TMA / mbarrier subset wrapped by csrc/tc_ptx.cuh, for HOST builds on the
+// SIMT emulation (cuda_runtime.h next to this file).  Test infrastructure.
+//   * shared addresses are byte offsets into the emulated dynamic shared memory (256 KB: 18 bits, exactly what a
+//     UMMA descriptor's start-address field holds);
+//   * an mbarrier is {expected arrivals, pending arrivals, pending transaction bytes, phase} under one mutex;
+//     waiters spin with yield;
+//   * a TMA 2-D load copies the box into shared memory in the 128-byte-swizzled layout (16-byte chunk index XOR
+//     row & 7 inside 1024-byte atoms, out-of-bounds elements zero) and completes the transaction bytes;
+//   * tcgen05.mma decodes the instruction and matrix descriptors (K-major, SWIZZLE_128B, M x N x 16 per call, bf16
+//     inputs, fp32 accumulate) and multiplies synchronously at issue into an emulated TMEM [128 lanes][512 cols];
+//   * tcgen05.ld 32x32b.x16 gives thread i of a warp 16 consecutive columns of lane (lane base + i).
+#pragma once
+#include <mutex>
+
+#include "cuda_runtime.h"
+#include "cuda_bf16.h"
+#include "../../torch_semantic_segmentation_b200/csrc/common.cuh"
+
+// ---- the slice of the driver API the launchers touch (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint)
+typedef uint64_t cuuint64_t;
+typedef uint32_t cuuint32_t;
+typedef int CUresult;
+enum { CUDA_SUCCESS = 0 };
+enum CUtensorMapDataType { CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 = 9, CU_TENSOR_MAP_DATA_TYPE_FLOAT32 = 7 };
+enum CUtensorMapInterleave { CU_TENSOR_MAP_INTERLEAVE_NONE = 0 };
+enum CUtensorMapSwizzle { CU_TENSOR_MAP_SWIZZLE_NONE = 0, CU_TENSOR_MAP_SWIZZLE_128B = 3 };
+enum CUtensorMapL2promotion { CU_TENSOR_MAP_L2_PROMOTION_L2_128B = 2 };
+enum CUtensorMapFloatOOBfill { CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = 0 };
+struct CUtensorMap {
+    const unsigned char* base;
+    uint64_t dim[2], stride1;        // dim[0] = innermost extent (elements), stride1 = row pitch in bytes
+    uint32_t box[2];
+    int elem_bytes, swizzle;
+};
+inline CUresult tss_emu_encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* gdim,
+                                     const cuuint64_t* gstr, const cuuint32_t* box, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+    if (rank != 2 || dt != CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 || sw != CU_TENSOR_MAP_SWIZZLE_128B || box[0] * 2 != 128) return 1;
+    m->base = (const unsigned char*)base;
+    m->dim[0] = gdim[0]; m->dim[1] = gdim[1];
+    m->stride1 = gstr[0];
+    m->box[0] = box[0]; m->box[1] = box[1];
+    m->elem_bytes = 2; m->swizzle = 1;
+    return CUDA_SUCCESS;
+}
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0 };
+enum { cudaEnableDefault = 0 };
+inline cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, int, cudaDriverEntryPointQueryResult* q) {
+    *fn = (void*)&tss_emu_encode_tiled;
+    *q = cudaDriverEntryPointSuccess;
+    return cudaSuccess;
+}
+
+namespace tss_emu {
+struct MBar { int count, pending, tx; uint32_t phase; };
+extern MBar mbars[sizeof(dyn_smem) / 8];
+extern std::mutex mbar_mutex;
+extern float tmem[128][512];
+inline void mbar_check(MBar& b) {                   // caller holds the mutex
+    if (b.pending == 0 && b.tx == 0) { b.phase ^= 1u; b.pending = b.count; }
+}
+inline uint32_t swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
+inline float bf16_at(uint32_t addr) {
+    uint16_t h;
+    memcpy(&h, dyn_smem + addr, 2);
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+}  // namespace tss_emu
+
+inline uint32_t smem_u32(const void* p) { return (uint32_t)((const unsigned char*)p - tss_emu::dyn_smem); }
+inline void mbar_init(uint32_t bar, uint32_t count) {
+    std::lock_guard<std::mutex> l(tss_emu::mbar_mutex);
+    tss_emu::mbars[bar >> 3] = {(int)count, (int)count, 0, 0u};
+}
+inline void mbar_init_fence() {}
+inline void mbar_arrive(uint32_t bar) {
+    std::lock_guard<std::mutex> l(tss_emu::mbar_mutex);
+    tss_emu::MBar& b = tss_emu::mbars[bar >> 3];
+    b.pending -= 1;
+    tss_emu::mbar_check(b);
+}
+inline void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    std::lock_guard<std::mutex> l(tss_emu::mbar_mutex);
+    tss_emu::MBar& b = tss_emu::mbars[bar >> 3];
+    b.tx += (int)bytes;
+    b.pending -= 1;
+    tss_emu::mbar_check(b);
+}
+inline void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        {
+            std::lock_guard<std::mutex> l(tss_emu::mbar_mutex);
+            if ((tss_emu::mbars[bar >> 3].phase & 1u) != (parity & 1u)) return;     // the phase with this parity completed
+        }
+        std::this_thread::yield();
+    }
+}
+inline void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    for (uint32_t r = 0; r < map->box[1]; ++r)
+        for (uint32_t k = 0; k < map->box[0]; ++k) {
+            uint16_t v = 0;
+            const int64_t row = (int64_t)c1 + r, col = (int64_t)c0 + k;
+            if (row >= 0 && col >= 0 && (uint64_t)row < map->dim[1] && (uint64_t)col < map->dim[0])
+                memcpy(&v, map->base + (uint64_t)row * map->stride1 + (uint64_t)col * 2, 2);
+            memcpy(tss_emu::dyn_smem + tss_emu::swz128(dst + r * 128 + k * 2), &v, 2);
+        }
+    std::lock_guard<std::mutex> l(tss_emu::mbar_mutex);
+    tss_emu::MBar& b = tss_emu::mbars[bar >> 3];
+    b.tx -= (int)(map->box[0] * map->box[1] * 2);
+    tss_emu::mbar_check(b);
+}
+inline void fence_async_smem() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void tc_alloc(uint32_t slot, uint32_t) {
+    const uint32_t base = 0;
+    memcpy(tss_emu::dyn_smem + slot, &base, 4);
+}
+inline void tc_dealloc(uint32_t, uint32_t) {}
+inline void tc_fence_before() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void tc_fence_after() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const int N = (int)((idesc >> 17) & 0x3Fu) << 3, M = (int)((idesc >> 24) & 0x1Fu) << 4;
+    const uint32_t a0 = (uint32_t)(adesc & 0x3FFFu) << 4, b0 = (uint32_t)(bdesc & 0x3FFFu) << 4;
+    const uint32_t sbo_a = (uint32_t)((adesc >> 32) & 0x3FFFu) << 4, sbo_b = (uint32_t)((bdesc >> 32) & 0x3FFFu) << 4;
+    const uint32_t col0 = tmem_d & 0xFFFFu;
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            float acc = accumulate ? tss_emu::tmem[m][col0 + n] : 0.f;
+            for (int k = 0; k < 16; ++k) {
+                const float a = tss_emu::bf16_at(tss_emu::swz128(a0 + (m >> 3) * sbo_a + (m & 7) * 128 + k * 2));
+                const float b = tss_emu::bf16_at(tss_emu::swz128(b0 + (n >> 3) * sbo_b + (n & 7) * 128 + k * 2));
+                acc += a * b;
+            }
+            tss_emu::tmem[m][col0 + n] = acc;
+        }
+}
+inline void umma_commit(uint32_t bar) { mbar_arrive(bar); }
+inline void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    const uint32_t lane = (taddr >> 16) + (threadIdx.x & 31), col = taddr & 0xFFFFu;
+    for (int i = 0; i < 16; ++i) v[i] = tss_emu::tmem[lane][col + i];
+}

@@ -1,4 +1,5 @@
-"""The plain SIMT kernels that have not run on a B200 yet (csrc/ppm.cu, csrc/augment.cu), executed on the CPU by
+"""The plain SIMT kernels that have not run on a B200 yet (csrc/ppm.cu, csrc/augment.cu, the stride-2 kernel of
+csrc/dwconv_bnred.cu), executed on the CPU by
 tests/simt_emu/: the .cu files are compiled for the host with g++ against a small emulation of the CUDA subset
 they use (one OS thread per CUDA thread, barriers for __syncthreads, slot exchange for warp shuffles), and driven
 through the SAME C ABI and the same Python host code as on the GPU.  This checks the kernels' index arithmetic,
@@ -18,7 +19,8 @@ from torch_semantic_segmentation_b200 import _lib, ops
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, 'torch_semantic_segmentation_b200', 'csrc')
 EMU = os.path.join(ROOT, 'tests', 'simt_emu')
-SOURCES = ['ppm.cu', 'augment.cu']
+SOURCES = ['ppm.cu', 'augment.cu', 'dwconv_bnred.cu',        # dwconv_bnred.cu: the stride-2 (plain SIMT) kernel only
+           'pwconv_tc_bwd.cu']                               # on the functional tcgen05/TMA/mbarrier emulation
 
 
 def rel(a, b):
@@ -148,3 +150,69 @@ def test_input_pipeline_kernel_on_the_simt_emulation(emulated):
     np.testing.assert_array_equal(x[2].numpy(), ex)
     np.testing.assert_array_equal(y[2].numpy(), ey)
     assert emulated.emulated_calls - before == len(A.GOLDEN_CASES) + 2
+
+
+def _nhwc(N, C, H, W, g, dtype):
+    return torch.randn(N, H, W, C, generator=g).to(dtype).permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('C,N,Hi,Wi,relu', [(32, 2, 12, 16, 1), (48, 1, 9, 13, 0), (64, 3, 7, 5, 1), (8, 1, 1, 1, 1), (384, 1, 4, 6, 1)])
+def test_stride2_dgrad_with_fused_reduction_on_the_simt_emulation(emulated, C, N, Hi, Wi, relu, dtype):
+    g = torch.Generator().manual_seed(C + Hi)
+    Ho, Wo = (Hi - 1) // 2 + 1, (Wi - 1) // 2 + 1
+    dy, yp = _nhwc(N, C, Ho, Wo, g, dtype), _nhwc(N, C, Hi, Wi, g, dtype)
+    w = torch.randn(C, 1, 3, 3, generator=g) / 3
+    mean, rstd = torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    outs = {}
+    for name, be in (('ref', FakeBackend()), ('emu', emulated)):
+        gout = torch.zeros(N, Hi, Wi, C, dtype=dtype).permute(0, 3, 1, 2)
+        sums = torch.zeros(2 * C)
+        be.call('tss_dwconv3x3_dgrad_s2_bnred', dict(dy=dy, w=w, g=gout, N=N, Hi=Hi, Wi=Wi, C=C, yp=yp, mean=mean, rstd=rstd,
+                                                     gamma=gamma, beta=beta, flags=relu, sums=sums, dtype=_lib.dtype_code(dtype)))
+        outs[name] = (gout.float(), sums)
+    tol = 1e-5 if dtype == torch.float32 else 5e-3
+    assert rel(outs['emu'][0], outs['ref'][0]) < tol
+    assert rel(outs['emu'][1], outs['ref'][1]) < 2e-3
+
+
+@pytest.mark.parametrize('link', [False, True])
+@pytest.mark.parametrize('M_shape,K,Nc,relu', [((2, 9, 13), 64, 384, 1), ((1, 16, 8), 128, 128, 1), ((2, 5, 7), 96, 576, 0),
+                                               ((3, 8, 8), 32, 48, 1), ((1, 1, 3), 16, 8, 1), ((1, 12, 25), 48, 64, 1),
+                                               ((1, 4, 4), 128, 768, 1)])
+def test_pw_backward_with_bn_apply_on_the_tcgen05_emulation(emulated, M_shape, K, Nc, relu, link):
+    """csrc/pwconv_tc_bwd.cu through tests/simt_emu/tcgen05_emu.h: warp roles, mbarrier protocol (a deadlock shows
+    up as a test timeout), the thread-built swizzled A tile, channel / row tails, the fused producer reduction."""
+    N, H, W = M_shape
+    M = N * H * W
+    g = torch.Generator().manual_seed(K + Nc + M)
+    dt = torch.bfloat16
+    dz, y, yp = _nhwc(N, Nc, H, W, g, dt), _nhwc(N, Nc, H, W, g, dt), _nhwc(N, K, H, W, g, dt)
+    par = lambda C: (torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.5, torch.rand(C, generator=g) + 0.5,
+                     torch.randn(C, generator=g) * 0.3)
+    mean, rstd, gamma, beta = par(Nc)
+    pmean, prstd, pgamma, pbeta = par(K)
+    wpT = (torch.randn(K, Nc, generator=g) / Nc ** 0.5).to(dt)
+    fake = FakeBackend()
+    sums = torch.zeros(2 * Nc)
+    fake.call('tss_bn_bwd_reduce', dict(dz=dz, z=None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, M=M, C=Nc,
+                                        lddz=Nc, ldz=0, ldy=Nc, flags=relu, dtype=1))
+    outs = {}
+    for name, be in (('ref', fake), ('emu', emulated)):
+        dy = torch.zeros(N, H, W, Nc, dtype=dt).permute(0, 3, 1, 2)
+        dx = torch.zeros(N, H, W, K, dtype=dt).permute(0, 3, 1, 2)
+        dgamma, dbeta, psums = torch.ones(Nc), torch.ones(Nc), torch.zeros(2 * K)
+        be.call('tss_pwconv_bwd_fused', dict(
+            dz=dz, y=y, lddz=Nc, ldy=Nc, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, flags=relu, count=M, dy=dy,
+            lddy=Nc, dgamma=dgamma, dbeta=dbeta, wpT=wpT, dx=dx, M=M, K=K, Nc=Nc, lddx=K, yp=yp if link else None,
+            ldyp=K if link else 0, pmean=pmean if link else None, prstd=prstd if link else None,
+            pgamma=pgamma if link else None, pbeta=pbeta if link else None, pflags=1 if link else 0,
+            psums=psums if link else None))
+        outs[name] = (dy.float(), dx.float(), dgamma, dbeta, psums)
+    r, e = outs['ref'], outs['emu']
+    assert rel(e[0], r[0]) < 5e-3, ('dy', rel(e[0], r[0]))
+    assert rel(e[1], r[1]) < 8e-3, ('dx', rel(e[1], r[1]))
+    assert rel(e[2], r[2]) < 1e-6 and rel(e[3], r[3]) < 1e-6
+    if link:
+        assert rel(e[4], r[4]) < 5e-3, ('psums', rel(e[4], r[4]))

@@ -4,10 +4,15 @@
 // conv.  The epilogue reads the matching yp values, applies the ReLU mask recomputed from yp, stores
 // g = dz * mask instead of dz and accumulates  sums[c] += sum g,  sums[C+c] += sum g * xhat  (what
 // bn_bwd_reduce_kernel would compute in a pass of its own over dz and yp).
+#ifdef TSS_HOST_EMU            // tests/simt_emu: only the plain SIMT kernel (stride 2) is built for the host
+#include "common.cuh"
+#else
 #include "tma.cuh"
+#endif
 
 namespace {
 
+#ifndef TSS_HOST_EMU
 constexpr int TH = 8;
 constexpr int IH = TH + 2;
 
@@ -122,6 +127,8 @@ dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const float* __re
     }
 }
 
+#endif  // !TSS_HOST_EMU
+
 // ---------------------------------------------------------------------------------------------
 // Stride 2: the quad kernel of dwconv.cu (2x2 input pixels per 2x2 gradient neighbourhood, vertical
 // strips of R quads, persistent grid with a loop-invariant channel group per thread) with the same fused
@@ -136,7 +143,7 @@ dw_dgrad_s2_bnred_kernel(const T* __restrict__ dy, const float* __restrict__ w, 
                          const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                          const float* __restrict__ beta, int relu, float* __restrict__ sums) {
     pdl_wait();
-    extern __shared__ float s_sum[];   // [2*C]
+    TSS_DYN_SMEM(float, s_sum);        // [2*C]
     for (int i = threadIdx.x; i < 2 * C; i += kQuadThreads) s_sum[i] = 0.f;
     __syncthreads();
     const int CG = C >> 3;
@@ -234,9 +241,11 @@ dw_dgrad_s2_bnred_kernel(const T* __restrict__ dy, const float* __restrict__ w, 
 
 int gcd_int2(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
+#ifndef TSS_HOST_EMU
 template <typename T> struct TmaTypeB;
 template <> struct TmaTypeB<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
 template <> struct TmaTypeB<bf16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
+#endif
 
 }  // namespace
 
@@ -268,6 +277,7 @@ extern "C" int tss_dwconv3x3_dgrad_s2_bnred(const void* dy, const float* w, void
     });
 }
 
+#ifndef TSS_HOST_EMU
 extern "C" int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g, int N, int H, int W, int C,
                                          const void* yp, const float* mean, const float* rstd, const float* gamma,
                                          const float* beta, int flags, float* sums, int dtype, void* stream) {
@@ -308,3 +318,4 @@ extern "C" int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g
         return TSS_OK;
     });
 }
+#endif  // !TSS_HOST_EMU
