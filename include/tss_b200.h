@@ -178,6 +178,14 @@ int tss_bn_finalize(double* stats, int64_t count, const float* gamma, const floa
                     float* running_mean, float* running_var, int64_t* num_batches_tracked,
                     float momentum, float eps, float* scale, float* shift, float* mean,
                     float* rstd, int C, int64_t clear_n, void* stream);
+/* finalize + apply in ONE launch (training): z = act(BN(y) [+ res]) with scale / shift derived from stats inside
+ * the kernel; mean / rstd written for the backward pass, running statistics updated, stats[0..clear_n) zeroed by
+ * the last CTA to have read it.  ticket: device int, zero on entry and zero again on exit. */
+int tss_bn_finalize_apply(double* stats, int64_t count, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                          float momentum, float eps, float* mean, float* rstd, int* ticket, int64_t clear_n,
+                          const void* y, const void* res, void* z, int64_t M, int C, int64_t ldy, int64_t ldr,
+                          int64_t ldz, int flags, int dtype, void* stream);
 /* eval mode: scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale */
 int tss_bn_fold(const float* gamma, const float* beta, const float* running_mean,
                 const float* running_var, float eps, float* scale, float* shift, int C,

@@ -318,6 +318,14 @@ class FakeBackend:
         sums[C:] += (g * xh).sum(dim=(0, 2, 3))
         return 0
 
+    def tss_bn_finalize_apply(self, stats, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum,
+                              eps, mean, rstd, ticket, clear_n, y, res, z, M, C, ldy, ldr, ldz, flags, dtype):
+        assert int(ticket) == 0
+        scale, shift = torch.empty(C), torch.empty(C)
+        self.tss_bn_finalize(stats, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
+                             scale, shift, mean, rstd, C, clear_n)
+        return self.tss_bn_apply(y, scale, shift, None, None, None, res, z, M, C, ldy, 0, ldr, ldz, flags, dtype)
+
     def tss_bn_bwd_apply(self, dz, z, y, mean, rstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, count, C, lddz, ldz,
                          ldy, lddy, lddres, flags, dtype):
         M = count if count > 0 else M

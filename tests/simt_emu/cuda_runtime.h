@@ -95,6 +95,8 @@ inline float atomicAdd(float* p, float v) {
     while (!r.compare_exchange_weak(old, old + v)) {}
     return old;
 }
+inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline double atomicAdd(double* p, double v) {
     std::atomic_ref<double> r(*p);
     double old = r.load();

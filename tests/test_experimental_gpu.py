@@ -7,6 +7,7 @@ unvalidated kernel can never hang the default GPU suite.
 * pointwise backward with the layer's BatchNorm-backward apply folded into the GEMM's A-operand producer
   (csrc/pwconv_tc_bwd.cu: pw_tc_bwd_kernel; enabled in the model by TSS_FUSE_BNAPPLY=1);
 * the pyramid-pooling branches as grouped launches (csrc/ppm.cu; enabled in the model by TSS_FUSE_PPM=1);
+* BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu; TSS_FUSE_BNFIN=1);
 * the device input pipeline (csrc/augment.cu; its per-pixel arithmetic is already pinned on the host by
   tests/test_data_cpu.py, the launch itself is what remains to be run)."""
 import os
@@ -243,3 +244,36 @@ def test_training_step_with_grouped_pyramid_pooling_matches_default():
             Fn.FUSE_PPM = keep
     assert abs(out[True][0] - out[False][0]) < 1e-4 * abs(out[False][0])
     assert rel(out[True][1], out[False][1]) < 1e-4 and rel(out[True][2], out[False][2]) < 1e-3
+
+
+def test_training_step_with_finalize_folded_into_apply_matches_default():
+    from oracle.golden_inputs import train_batch
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+    x, y = train_batch('fastscnn')
+    out = {}
+    keep = Fn.FUSE_BNFIN
+    for flag in (False, True):
+        Fn.FUSE_BNFIN = flag
+        try:
+            torch.manual_seed(0)
+            model = fastscnn(3, 19).cuda().train()
+            for m in model.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+            before = _lib.launch_count()
+            for _ in range(2):                                  # twice: the scratch / ticket must be clean for the second step
+                model.zero_grad()
+                logits = model(x.cuda())
+                loss = CrossEntropyLoss(ignore_index=255)(logits, y.cuda())
+                loss.backward()
+            torch.cuda.synchronize()
+            out[flag] = (float(loss), logits.detach(), model.classifier[3].weight.grad.clone(),
+                         model.downsample[0][1].running_var.clone(), _lib.launch_count() - before)
+        finally:
+            Fn.FUSE_BNFIN = keep
+    assert abs(out[True][0] - out[False][0]) < 1e-5 * abs(out[False][0])
+    assert rel(out[True][1], out[False][1]) < 1e-5 and rel(out[True][2], out[False][2]) < 1e-4
+    assert rel(out[True][3], out[False][3]) < 1e-6
+    assert out[True][4] == out[False][4] - 2 * 44

@@ -221,19 +221,23 @@ def test_gated_backward_fusions_are_plumbing_equivalent(fake_backend):
     fake_backend.call = counting
     g = torch.Generator().manual_seed(1)
     x, y = torch.randn(2, 3, 64, 64, generator=g), torch.randint(0, 19, (2, 64, 64), generator=g)
-    keep = Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY
+    keep = Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY, Fn.FUSE_BNFIN
     runs = {}
     try:
-        for ext, fused in ((False, False), (True, False), (False, True), (True, True)):
-            Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY = ext, fused
+        for ext, fused in ((False, False), (True, False), (False, True), (True, True), ('fin', False)):
+            Fn.FUSE_BNFIN = ext == 'fin'
+            Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY = ext is True, fused
             calls.clear()
             torch.manual_seed(0)
             model = set_compute_dtype(_no_dropout(fastscnn(3, 19)), torch.bfloat16, pw_impl=1).train()
             CrossEntropyLoss(ignore_index=255)(model(x), y).backward()
             runs[ext, fused] = (torch.cat([p.grad.reshape(-1) for p in model.parameters()]), dict(calls))
     finally:
-        Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY = keep
+        Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY, Fn.FUSE_BNFIN = keep
     base, base_calls = runs[False, False]
+    # finalize folded into the apply kernel: same arithmetic, 44 launches less
+    assert rel(runs['fin', False][0], base) < 1e-6
+    assert runs['fin', False][1]['tss_bn_finalize_apply'] == 44 and 'tss_bn_finalize' not in runs['fin', False][1]
     assert base_calls.get('tss_pwconv_bwd_fused', 0) == 0 and base_calls.get('tss_dwconv3x3_dgrad_s2_bnred', 0) == 0
     for key, (grad, c) in runs.items():
         assert sum(c.values()) <= sum(base_calls.values())

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, 'torch_semantic_segmentation_b200', 'csrc')
 EMU = os.path.join(ROOT, 'tests', 'simt_emu')
 SOURCES = ['ppm.cu', 'augment.cu', 'dwconv_bnred.cu',        # dwconv_bnred.cu: the stride-2 (plain SIMT) kernel only
-           'pwconv_tc_bwd.cu']                               # on the functional tcgen05/TMA/mbarrier emulation
+           'bn_fused.cu', 'pwconv_tc_bwd.cu']                               # on the functional tcgen05/TMA/mbarrier emulation
 
 
 def rel(a, b):
@@ -216,3 +216,33 @@ def test_pw_backward_with_bn_apply_on_the_tcgen05_emulation(emulated, M_shape, K
     assert rel(e[2], r[2]) < 1e-6 and rel(e[3], r[3]) < 1e-6
     if link:
         assert rel(e[4], r[4]) < 5e-3, ('psums', rel(e[4], r[4]))
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('N,C,H,W,relu,with_res', [(2, 32, 9, 7, 1, 0), (1, 384, 5, 3, 1, 1), (3, 48, 16, 24, 0, 1), (2, 8, 1, 1, 1, 0)])
+def test_finalize_folded_into_apply_on_the_simt_emulation(emulated, N, C, H, W, relu, with_res, dtype):
+    g = torch.Generator().manual_seed(C + H)
+    y = _nhwc(N, C, H, W, g, dtype)
+    res = _nhwc(N, C, H, W, g, dtype) if with_res else None
+    M = N * H * W
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    outs = {}
+    for name, be in (('ref', FakeBackend()), ('emu', emulated)):
+        scratch = torch.zeros(3 * C, dtype=torch.float64)
+        scratch[:C] = y.double().sum(dim=(0, 2, 3))
+        scratch[C:2 * C] = (y.double() ** 2).sum(dim=(0, 2, 3))
+        scratch[2 * C:] = 7.0                                        # stale backward sums: must be cleared too
+        rm, rv, nbt = torch.zeros(C), torch.ones(C), torch.zeros((), dtype=torch.int64)
+        mean, rstd, ticket = torch.zeros(C), torch.zeros(C), torch.zeros(1, dtype=torch.int32)
+        z = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2)
+        be.call('tss_bn_finalize_apply', dict(stats=scratch, count=M, gamma=gamma, beta=beta, running_mean=rm, running_var=rv,
+                                              num_batches_tracked=nbt, momentum=0.1, eps=1e-5, mean=mean, rstd=rstd, ticket=ticket,
+                                              clear_n=3 * C, y=y, res=res, z=z, M=M, C=C, ldy=C, ldr=C if with_res else 0, ldz=C,
+                                              flags=relu, dtype=_lib.dtype_code(dtype)))
+        outs[name] = (z.float(), mean, rstd, rm, rv, int(nbt), float(scratch.abs().max()), int(ticket))
+    r, e = outs['ref'], outs['emu']
+    tol = 1e-6 if dtype == torch.float32 else 4e-3
+    assert rel(e[0], r[0]) < tol
+    for i in (1, 2, 3, 4):
+        assert rel(e[i], r[i]) < 1e-6
+    assert e[5] == 1 and e[6] == 0.0 and e[7] == 0              # counted once, scratch cleared, ticket reset

@@ -159,6 +159,9 @@ FUSE_BNAPPLY = os.environ.get('TSS_FUSE_BNAPPLY', '0') == '1'
 # The four pyramid-pooling branches as grouped launches (csrc/ppm.cu): 3 launches forward and 5 backward instead
 # of ~18 and ~26.  Same status: off unless TSS_FUSE_PPM=1.
 FUSE_PPM = os.environ.get('TSS_FUSE_PPM', '0') == '1'
+# BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu): one launch less per layer on the forward
+# chain (44 per step).  Same status: off unless TSS_FUSE_BNFIN=1.
+FUSE_BNFIN = os.environ.get('TSS_FUSE_BNFIN', '0') == '1'
 
 
 class _BnLink:
@@ -210,11 +213,15 @@ class ConvBNAct(torch.autograd.Function):
             # all ranks, one fp64 all-reduce per layer; every rank holds the same number of pixels
             torch.distributed.all_reduce(scratch[:2 * C], group=group)
         ctx.sync = (world, group)
-        scale, shift, mean, rstd = ops.bn_finalize(scratch, N * H * W * world, bn, float(bn.momentum), float(bn.eps),
-                                                   update_running=bn.track_running_stats, clear_n=3 * C, C=C)
+        if FUSE_BNFIN:
+            z, mean, rstd = ops.bn_finalize_apply(scratch, N * H * W * world, bn, float(bn.momentum), float(bn.eps), y, res=res,
+                                                  relu=spec.relu, update_running=bn.track_running_stats, clear_n=3 * C, C=C)
+        else:
+            scale, shift, mean, rstd = ops.bn_finalize(scratch, N * H * W * world, bn, float(bn.momentum), float(bn.eps),
+                                                       update_running=bn.track_running_stats, clear_n=3 * C, C=C)
+            z = ops.bn_apply(y, scale, shift, res=res, relu=spec.relu)
         bn._tss_dirty = False
         ctx.scratch = scratch
-        z = ops.bn_apply(y, scale, shift, res=res, relu=spec.relu)
         ctx.spec, ctx.packed = spec, packed
         ctx.params = (weight, gamma, beta)
         ctx.arena = (getattr(weight, '_tss_grad', None), getattr(gamma, '_tss_grad', None),

@@ -307,6 +307,27 @@ def bn_finalize(stats, count, bn, momentum, eps, update_running=True, clear_n=0,
     return out[0], out[1], out[2], out[3]
 
 
+def bn_finalize_apply(stats, count, bn, momentum, eps, y, res=None, relu=False, update_running=True, clear_n=0, C=None):
+    """``bn_finalize`` + ``bn_apply`` as one launch -> z, mean, rstd."""
+    N, Cy, H, W, ldy = _g(y, 'bn_finalize_apply')
+    C = Cy if C is None else C
+    out = torch.empty((2, C), dtype=torch.float32, device=stats.device)
+    ticket = getattr(bn, '_tss_ticket', None)
+    if ticket is None or ticket.device != stats.device:
+        ticket = bn._tss_ticket = torch.zeros(1, dtype=torch.int32, device=stats.device)
+    track = update_running and bn.running_mean is not None
+    z = empty_nhwc(N, C, H, W, y.dtype, y.device)
+    _lib.call('tss_bn_finalize_apply', stats=stats, count=count, gamma=bn.weight, beta=bn.bias,
+              running_mean=bn.running_mean if track else None, running_var=bn.running_var if track else None,
+              num_batches_tracked=bn.num_batches_tracked if track else None, momentum=momentum, eps=eps,
+              mean=out[0], rstd=out[1], ticket=ticket, clear_n=clear_n, y=y, res=res, z=z, M=N * H * W, C=C, ldy=ldy,
+              ldr=_g(res, 'bn_finalize_apply')[4] if res is not None else 0, ldz=C, flags=_flags(relu),
+              dtype=dtype_code(y.dtype))
+    if track:
+        WEIGHTS_EPOCH[0] += 1
+    return z, out[0], out[1]
+
+
 def bn_fold(bn):
     C = bn.num_features
     out = torch.empty((2, C), dtype=torch.float32, device=bn.running_mean.device)
