@@ -151,6 +151,15 @@ int tss_dwpw_fwd(const void* x, const float* w_dw, const float* scale1, const fl
 int tss_stem3x3s2_fwd(const float* x, const float* w, void* y, int N, int H, int W, int Cout,
                       const float* scale, const float* shift, int flags, double* stats,
                       int dtype, void* stream);
+/* the same on tcgen05 (bf16 output only): the 27-tap patches of 128 consecutive output pixels are built by the
+ * threads as the swizzled A operand of an implicit GEMM (image and weights rounded to bf16, fp32 accumulate). */
+int tss_stem3x3s2_fwd_tc(const float* x, const float* w, void* y, int N, int H, int W, int Cout,
+                         const float* scale, const float* shift, int flags, double* stats, void* stream);
+/* weight gradient of the stem on tcgen05 (bf16 dy): dw (Cout,3,3,3) fp32 += sum over pixels; both GEMM operands
+ * (dy transposed, image patches) are built K-major in shared memory by the threads, the pixel index is the
+ * reduction dimension. */
+int tss_stem3x3s2_wgrad_tc(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout,
+                           void* stream);
 int tss_stem3x3s2_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout,
                         int dtype, void* stream);
 /* Dense 3x3, stride 1, padding 1, C -> Cout between equal-sized NHWC maps: replaces

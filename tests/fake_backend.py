@@ -259,6 +259,16 @@ class FakeBackend:
         y.copy_(_epilogue(raw, scale, shift, None, flags))
         return 0
 
+    def tss_stem3x3s2_fwd_tc(self, x, w, y, N, H, W, Cout, scale, shift, flags, stats):
+        raw = F.conv2d(x.bfloat16().float(), w.detach().bfloat16().float(), None, 2, 1)      # operands rounded to bf16
+        _stats(stats, raw)
+        y.copy_(_epilogue(raw, scale, shift, None, flags))
+        return 0
+
+    def tss_stem3x3s2_wgrad_tc(self, x, dy, dw, N, H, W, Cout):
+        dw += nngrad.conv2d_weight(x.bfloat16().float(), dw.shape, dy.float(), 2, 1)          # image rounded to bf16
+        return 0
+
     def tss_stem3x3s2_wgrad(self, x, dy, dw, N, H, W, Cout, dtype):
         dw += nngrad.conv2d_weight(x, dw.shape, dy.float(), 2, 1)
         return 0

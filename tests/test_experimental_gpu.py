@@ -8,6 +8,7 @@ unvalidated kernel can never hang the default GPU suite.
   (csrc/pwconv_tc_bwd.cu: pw_tc_bwd_kernel; enabled in the model by TSS_FUSE_BNAPPLY=1);
 * the pyramid-pooling branches as grouped launches (csrc/ppm.cu; enabled in the model by TSS_FUSE_PPM=1);
 * BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu; TSS_FUSE_BNFIN=1);
+* the stem convolution and its weight gradient on tcgen05 (csrc/stem_tc.cu; TSS_STEM_TC=1);
 * the device input pipeline (csrc/augment.cu; its per-pixel arithmetic is already pinned on the host by
   tests/test_data_cpu.py, the launch itself is what remains to be run)."""
 import os
@@ -277,3 +278,29 @@ def test_training_step_with_finalize_folded_into_apply_matches_default():
     assert rel(out[True][1], out[False][1]) < 1e-5 and rel(out[True][2], out[False][2]) < 1e-4
     assert rel(out[True][3], out[False][3]) < 1e-6
     assert out[True][4] == out[False][4] - 2 * 44
+
+
+@pytest.mark.parametrize('N,H,W', [(2, 64, 96), (1, 32, 300), (1, 7, 9), (12, 768, 768)])
+def test_stem_on_tensor_cores_matches_the_simt_stem(N, H, W):
+    g = torch.Generator().manual_seed(H + W)
+    x = torch.randn(N, 3, H, W, generator=g).cuda()
+    w = (torch.randn(32, 3, 3, 3, generator=g) / 5).cuda()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    be = _lib.backend()
+    ys, sts, dws = [], [], []
+    dy = torch.randn(N, Ho, Wo, 32, generator=g).to(torch.bfloat16).cuda().permute(0, 3, 1, 2)
+    for tc in (False, True):
+        y = torch.zeros(N, Ho, Wo, 32, dtype=torch.bfloat16, device='cuda').permute(0, 3, 1, 2)
+        stats = torch.zeros(64, dtype=torch.float64, device='cuda')
+        dw = torch.zeros(32, 3, 3, 3, device='cuda')
+        if tc:
+            be.call('tss_stem3x3s2_fwd_tc', dict(x=x, w=w, y=y, N=N, H=H, W=W, Cout=32, scale=None, shift=None, flags=0, stats=stats))
+            be.call('tss_stem3x3s2_wgrad_tc', dict(x=x, dy=dy, dw=dw, N=N, H=H, W=W, Cout=32))
+        else:
+            be.call('tss_stem3x3s2_fwd', dict(x=x, w=w, y=y, N=N, H=H, W=W, Cout=32, scale=None, shift=None, flags=0, stats=stats, dtype=1))
+            be.call('tss_stem3x3s2_wgrad', dict(x=x, dy=dy, dw=dw, N=N, H=H, W=W, Cout=32, dtype=1))
+        torch.cuda.synchronize()
+        ys.append(y.float()); sts.append(stats); dws.append(dw)
+    assert rel(ys[1], ys[0]) < 1e-2                       # image and weights rounded to bf16 on the tensor-core path
+    assert rel(sts[1], sts[0]) < 1e-2
+    assert rel(dws[1], dws[0]) < 1e-2

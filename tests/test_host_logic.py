@@ -286,3 +286,39 @@ def test_grouped_pyramid_pooling_is_plumbing_equivalent(fake_backend):
             PyramidPoolingModule(128, 128).train()(torch.randn(1, 128, 6, 9))
     finally:
         Fn.FUSE_PPM = keep
+
+
+def test_tensor_core_stem_gate_is_plumbing_equivalent(fake_backend):
+    """functional.STEM_TC (off by default): the training step with the stem routed to the tcgen05 entry points.
+    The image is rounded to bf16 there, so the learning-to-downsample output agrees at bf16 level (the tiny
+    whole network behind it -- BatchNorm over 2 values in the bin-1 pyramid branch -- amplifies that noise, so the
+    final logits are not compared)."""
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.nn.blocks import set_compute_dtype
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(2, 3, 64, 64, generator=g), torch.randint(0, 19, (2, 64, 64), generator=g)
+    keep = Fn.STEM_TC
+    calls = {}
+    inner = fake_backend.call
+
+    def counting(name, kwargs):
+        calls[name] = calls.get(name, 0) + 1
+        return inner(name, kwargs)
+    fake_backend.call = counting
+    runs = {}
+    try:
+        for flag in (False, True):
+            Fn.STEM_TC = flag
+            calls.clear()
+            torch.manual_seed(0)
+            model = set_compute_dtype(_no_dropout(fastscnn(3, 19)), torch.bfloat16, pw_impl=1).train()
+            seen = {}
+            model.downsample.register_forward_hook(lambda m, i, o: seen.__setitem__('d', o.detach().float()))
+            CrossEntropyLoss(ignore_index=255)(model(x), y).backward()
+            runs[flag] = (seen['d'], model.downsample[0][0].weight.grad.clone(), dict(calls))
+    finally:
+        Fn.STEM_TC = keep
+    assert rel(runs[True][0], runs[False][0]) < 3e-2
+    assert torch.isfinite(runs[True][1]).all() and float(runs[True][1].abs().sum()) > 0
+    assert runs[True][2].get('tss_stem3x3s2_fwd_tc') == 1 and runs[True][2].get('tss_stem3x3s2_wgrad_tc') == 1
+    assert 'tss_stem3x3s2_fwd' not in runs[True][2] and 'tss_stem3x3s2_fwd_tc' not in runs[False][2]

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, 'torch_semantic_segmentation_b200', 'csrc')
 EMU = os.path.join(ROOT, 'tests', 'simt_emu')
 SOURCES = ['ppm.cu', 'augment.cu', 'dwconv_bnred.cu',        # dwconv_bnred.cu: the stride-2 (plain SIMT) kernel only
-           'bn_fused.cu', 'pwconv_tc_bwd.cu']                               # on the functional tcgen05/TMA/mbarrier emulation
+           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu']                               # on the functional tcgen05/TMA/mbarrier emulation
 
 
 def rel(a, b):
@@ -246,3 +246,43 @@ def test_finalize_folded_into_apply_on_the_simt_emulation(emulated, N, C, H, W, 
     for i in (1, 2, 3, 4):
         assert rel(e[i], r[i]) < 1e-6
     assert e[5] == 1 and e[6] == 0.0 and e[7] == 0              # counted once, scratch cleared, ticket reset
+
+
+@pytest.mark.parametrize('N,H,W,mode', [(2, 16, 24, 'train'), (1, 32, 300, 'train'), (1, 7, 9, 'eval'), (3, 2, 2, 'train'),
+                                          (1, 64, 520, 'eval')])
+def test_stem_on_the_tcgen05_emulation(emulated, N, H, W, mode):
+    """csrc/stem_tc.cu: thread-built implicit-GEMM operands (image patches and weights), K = 27 padded to 32,
+    tiles of 128 output pixels with a row tail, statistics or the folded eval epilogue."""
+    g = torch.Generator().manual_seed(H + W)
+    x = torch.randn(N, 3, H, W, generator=g)
+    w = torch.randn(32, 3, 3, 3, generator=g) / 5
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    scale = shift = None
+    if mode == 'eval':
+        scale, shift = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.2
+    outs = {}
+    for name, be in (('ref', FakeBackend()), ('emu', emulated)):
+        y = torch.zeros(N, Ho, Wo, 32, dtype=torch.bfloat16).permute(0, 3, 1, 2)
+        stats = torch.zeros(64, dtype=torch.float64) if mode == 'train' else None
+        be.call('tss_stem3x3s2_fwd_tc', dict(x=x, w=w, y=y, N=N, H=H, W=W, Cout=32, scale=scale, shift=shift,
+                                             flags=1 if mode == 'eval' else 0, stats=stats))
+        outs[name] = (y.float(), stats)
+    assert rel(outs['emu'][0], outs['ref'][0]) < 4e-3
+    if mode == 'train':
+        assert rel(outs['emu'][1], outs['ref'][1]) < 1e-5
+
+
+@pytest.mark.parametrize('N,H,W', [(2, 16, 24), (1, 32, 300), (1, 7, 9), (3, 2, 2), (1, 20, 260)])
+def test_stem_weight_gradient_on_the_tcgen05_emulation(emulated, N, H, W):
+    """csrc/stem_tc.cu wgrad: pixel index as the reduction dimension, thread-built transposed operands, 2-stage
+    mbarrier ring over a persistent CTA's share of the k-blocks, accumulation into dw."""
+    g = torch.Generator().manual_seed(H * W)
+    x = torch.randn(N, 3, H, W, generator=g)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dy = _nhwc(N, 32, Ho, Wo, g, torch.bfloat16)
+    outs = {}
+    for name, be in (('ref', FakeBackend()), ('emu', emulated)):
+        dw = torch.full((32, 3, 3, 3), 0.5)                          # accumulates onto what is there
+        be.call('tss_stem3x3s2_wgrad_tc', dict(x=x, dy=dy, dw=dw, N=N, H=H, W=W, Cout=32))
+        outs[name] = dw
+    assert rel(outs['emu'] - 0.5, outs['ref'] - 0.5) < 2e-3

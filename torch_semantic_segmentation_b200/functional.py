@@ -138,9 +138,16 @@ def conv_forward(spec, x, weight, scale=None, shift=None, res=None, relu=False, 
         return ops.dwconv_fwd(x, weight, spec.stride, spec.dilation, scale=scale, shift=shift,
                               relu=relu, stats=stats)
     if spec.kind == 'stem':
+        if STEM_TC and spec.dtype == torch.bfloat16 and weight.shape[0] == 32:
+            return ops.stem_fwd_tc(x, weight, scale=scale, shift=shift, relu=relu, stats=stats)
         return ops.stem_fwd(x, weight, spec.dtype, scale=scale, shift=shift, relu=relu, stats=stats)
     raise RuntimeError('unknown conv kind %r' % spec.kind)
 
+
+# Stem convolution on tcgen05 with a thread-built implicit-GEMM operand (csrc/stem_tc.cu) instead of the SIMT
+# kernel (864 FMAs per output pixel).  Built, checked on the SIMT emulation, not yet run on a B200: off unless
+# TSS_STEM_TC=1.
+STEM_TC = os.environ.get('TSS_STEM_TC', '0') == '1'
 
 # Training: fold the BatchNorm-backward reduction of a producer layer into the dgrad epilogue of its single
 # consumer (csrc/pwconv_tc_bnred.cu, csrc/dwconv_bnred.cu): one full read of (dz, y) and one launch less per
@@ -317,7 +324,10 @@ class ConvBNAct(torch.autograd.Function):
         else:  # stem: the image needs no gradient
             if ctx.needs_input_grad[0]:
                 raise RuntimeError('gradient w.r.t. the input image is not implemented')
-            lane(lambda: ops.stem_wgrad(x, dy, dw))
+            if STEM_TC and dy.dtype == torch.bfloat16 and weight.shape[0] == 32:
+                lane(lambda: ops.stem_wgrad_tc(x, dy, dw))
+            else:
+                lane(lambda: ops.stem_wgrad(x, dy, dw))
         grad_ready(*ctx.params)
         return (dx, dres, None if gw is not None else dw, None if gg is not None else gg_out,
                 None if gb is not None else gb_out, None, None, None)

@@ -236,6 +236,26 @@ def stem_fwd(x, w, dtype, scale=None, shift=None, relu=False, stats=None):
     return y
 
 
+def stem_fwd_tc(x, w, scale=None, shift=None, relu=False, stats=None):
+    """``stem_fwd`` on the tensor cores (bf16 output)."""
+    N, Cin, H, W = x.shape
+    if Cin != 3 or x.dtype != torch.float32 or not x.is_contiguous():
+        raise RuntimeError('stem_fwd_tc: expects a contiguous float32 (N,3,H,W) batch')
+    Cout = w.shape[0]
+    y = empty_nhwc(N, Cout, (H - 1) // 2 + 1, (W - 1) // 2 + 1, torch.bfloat16, x.device)
+    _lib.call('tss_stem3x3s2_fwd_tc', x=x, w=w, y=y, N=N, H=H, W=W, Cout=Cout, scale=scale, shift=shift,
+              flags=_flags(relu), stats=stats)
+    return y
+
+
+def stem_wgrad_tc(x, dy, dw):
+    """``stem_wgrad`` on the tensor cores (bf16 gradient, dense NHWC)."""
+    N, _, H, W = x.shape
+    if dy.dtype != torch.bfloat16 or _g(dy, 'stem_wgrad_tc')[4] != dy.shape[1]:
+        raise RuntimeError('stem_wgrad_tc: expects a dense bfloat16 NHWC gradient')
+    _lib.call('tss_stem3x3s2_wgrad_tc', x=x, dy=dy, dw=dw, N=N, H=H, W=W, Cout=dy.shape[1])
+
+
 def stem_wgrad(x, dy, dw):
     N, _, H, W = x.shape
     _lib.call('tss_stem3x3s2_wgrad', x=x, dy=dy, dw=dw, N=N, H=H, W=W, Cout=dy.shape[1],
