@@ -20,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, 'torch_semantic_segmentation_b200', 'csrc')
 EMU = os.path.join(ROOT, 'tests', 'simt_emu')
 SOURCES = ['ppm.cu', 'augment.cu', 'dwconv_bnred.cu',        # dwconv_bnred.cu: the stride-2 (plain SIMT) kernel only
-           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu']                               # on the functional tcgen05/TMA/mbarrier emulation
+           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu',
+           'pwconv_tc_bnred.cu']                             # validated on the B200: calibrates the emulation itself                               # on the functional tcgen05/TMA/mbarrier emulation
 
 
 def rel(a, b):
@@ -286,3 +287,29 @@ def test_stem_weight_gradient_on_the_tcgen05_emulation(emulated, N, H, W):
         be.call('tss_stem3x3s2_wgrad_tc', dict(x=x, dy=dy, dw=dw, N=N, H=H, W=W, Cout=32))
         outs[name] = dw
     assert rel(outs['emu'] - 0.5, outs['ref'] - 0.5) < 2e-3
+
+
+@pytest.mark.parametrize('M_shape,K,Nc,relu', [((2, 9, 13), 64, 384, 1), ((1, 16, 8), 128, 128, 1), ((2, 5, 7), 96, 576, 0),
+                                               ((3, 8, 8), 32, 48, 1), ((1, 12, 25), 48, 64, 1)])
+def test_emulation_agrees_with_a_kernel_validated_on_the_gpu(emulated, M_shape, K, Nc, relu):
+    """csrc/pwconv_tc_bnred.cu is part of the default path and parity-green on the B200
+    (tests/test_fused_bn_reduction_gpu.py).  Its host build must give the same answers on the emulation: this pins
+    the emulation's model of TMA swizzling, UMMA descriptors, TMEM addressing and mbarrier phases to a kernel
+    whose behaviour on the hardware is known."""
+    N, H, W = M_shape
+    M = N * H * W
+    g = torch.Generator().manual_seed(K + Nc + M)
+    dt = torch.bfloat16
+    dy, yp = _nhwc(N, Nc, H, W, g, dt), _nhwc(N, K, H, W, g, dt)
+    mean, rstd = torch.randn(K, generator=g) * 0.2, torch.rand(K, generator=g) + 0.5
+    gamma, beta = torch.rand(K, generator=g) + 0.5, torch.randn(K, generator=g) * 0.3
+    wpT = (torch.randn(K, Nc, generator=g) / Nc ** 0.5).to(dt)
+    outs = {}
+    for name, be in (('ref', FakeBackend()), ('emu', emulated)):
+        gout = torch.zeros(N, H, W, K, dtype=dt).permute(0, 3, 1, 2)
+        sums = torch.zeros(2 * K)
+        be.call('tss_pwconv_dgrad_bnred', dict(dy=dy, wpT=wpT, g=gout, M=M, K=K, Nc=Nc, lddy=Nc, ldg=K, yp=yp, ldyp=K, mean=mean,
+                                               rstd=rstd, gamma=gamma, beta=beta, flags=relu, sums=sums))
+        outs[name] = (gout.float(), sums)
+    assert rel(outs['emu'][0], outs['ref'][0]) < 5e-3
+    assert rel(outs['emu'][1], outs['ref'][1]) < 5e-3

@@ -10,10 +10,9 @@
 // the two sums with the same warp-transposed shuffle reduction the forward uses for its statistics.
 // The producer's BatchNorm backward then runs its apply pass only (no mask, no reduction): one full
 // read of dz and yp and one launch less per layer.  Main loop identical to pwconv_tc.cu.
-#include <cuda.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -21,69 +20,6 @@ constexpr int BM = 128;          // rows per tile = UMMA M
 constexpr int BK = 64;           // bf16 elements per k-block = 128 bytes = one swizzle row
 constexpr int kThreads = 192;
 constexpr uint32_t kABytes = BM * BK * 2;
-
-// ------------------------------------------------------------------ PTX wrappers ------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address
-    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset
-    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-    return d;
-}
 
 // lanes 2j / 2j+1 end with the sum over the 32 lanes of v[j], j = lane >> 1
 __device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
@@ -107,7 +43,7 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                    const bf16* __restrict__ yp, int64_t ldyp, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                    int relu, float* __restrict__ sums, int sums_stride) {
-    extern __shared__ uint8_t smem_raw[];
+    TSS_DYN_SMEM(uint8_t, smem_raw);
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t b_bytes = (uint32_t)block_n * BK * 2;
     uint8_t* sA = smem;
@@ -128,11 +64,10 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_init(smem_u32(bars + stages + s), 1);
         }
         mbar_init(smem_u32(bars + 2 * stages), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        tc_alloc(smem_u32(tmem_slot), tmem_cols);
     }
     for (int i = threadIdx.x; i < 2 * block_n; i += kThreads) s_stat[i] = 0.f;
     pdl_wait();
@@ -144,9 +79,9 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         s_const[2 * block_n + i] = sc;
         s_const[3 * block_n + i] = (beta != nullptr ? __ldg(beta + n0 + i) : 0.f) - mu * sc;
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -168,7 +103,7 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const int s = kb % stages;
                 const uint32_t phase = (kb / stages) & 1;
                 mbar_wait(smem_u32(bars + s), phase);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tc_fence_after();
                 const uint64_t adesc = make_desc_k_sw128(smem_u32(sA + (size_t)s * kABytes));
                 const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + (size_t)s * b_bytes));
                 int rem = K - kb * BK;
@@ -185,7 +120,7 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int64_t row = m0 + row_in_tile;
         const bool row_ok = row < M;
         mbar_wait(smem_u32(bars + 2 * stages), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tc_fence_after();
         for (int c = 0; c < block_n; c += 16) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
@@ -225,7 +160,7 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tc_fence_before();
     }
     __syncthreads();
     for (int i = threadIdx.x; i < block_n; i += kThreads) {
@@ -234,8 +169,8 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     if (warp == 1) {
         __syncwarp();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        tc_fence_after();
+        tc_dealloc(tmem_base, tmem_cols);
     }
 }
 
