@@ -344,6 +344,10 @@ int tss_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, floa
 int tss_ppm_branches_fwd(const void* pool, const int64_t* table, void* y, void* z, float* mean, float* rstd,
                          int N, int C, int Cb, const int* bins, int nbins, float momentum, float eps, int dtype,
                          void* stream);
+/* eval mode: z = relu(conv * scale + shift) with the folded BatchNorm; table columns 1 and 2 hold the addresses of
+ * the per-branch scale / shift vectors (tss_bn_fold) instead of gamma / beta. */
+int tss_ppm_branches_eval(const void* pool, const int64_t* table, void* z, int N, int C, int Cb, const int* bins,
+                          int nbins, int dtype, void* stream);
 int tss_ppm_concat_fwd(const void* x, const void* z, void* cat, int N, int H, int W, int C, int Cb,
                        const int* bins, int nbins, int dtype, void* stream);
 int tss_ppm_concat_bwd(const void* dcat, void* dz, int N, int H, int W, int C, int Cb, int64_t lddcat,

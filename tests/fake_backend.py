@@ -192,6 +192,13 @@ class FakeBackend:
                 nbt += 1
         return 0
 
+    def tss_ppm_branches_eval(self, pool, table, z, N, C, Cb, bins, nbins, dtype):
+        for i, (b, lo, hi) in enumerate(self._branch_rows(N, bins)):
+            t = table[i].tolist()
+            w, sc, sh = self._at(t[0], Cb * C).view(Cb, C), self._at(t[1], Cb), self._at(t[2], Cb)
+            z[lo:hi].copy_(torch.addcmul(sh, pool[lo:hi].float() @ w.t(), sc).clamp_min(0))
+        return 0
+
     def tss_ppm_concat_fwd(self, x, z, cat, N, H, W, C, Cb, bins, nbins, dtype):
         cat[:, :C].copy_(x)
         for i, (b, lo, hi) in enumerate(self._branch_rows(N, bins)):

@@ -46,7 +46,7 @@ struct Block {
     std::barrier<> all;
     std::vector<std::unique_ptr<std::barrier<>>> warps;
     std::vector<uint32_t> slots;
-    explicit Block(int threads) : all(threads), slots(((threads + 31) / 32) * 32) {
+    explicit Block(int threads) : all(threads), slots(2 * ((threads + 31) / 32) * 32) {
         for (int w = 0; w < (threads + 31) / 32; ++w) {
             const int n = threads - w * 32 < 32 ? threads - w * 32 : 32;
             warps.emplace_back(new std::barrier<>(n));
@@ -66,13 +66,17 @@ inline void __syncwarp(unsigned = 0xffffffffu) { tss_emu::block->warps[threadIdx
 
 template <typename V> inline V __shfl_xor_sync(unsigned, V v, int lane_mask) {
     static_assert(sizeof(V) == 4, "32-bit shuffles only");
+    // one barrier per shuffle: the exchange slots are double-buffered on the call parity, so a lane that races
+    // ahead into the next shuffle writes the other buffer and cannot clobber a value a slower lane still reads
+    static thread_local unsigned parity = 0;
     tss_emu::Block* b = tss_emu::block;
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    memcpy(&b->slots[warp * 32 + lane], &v, 4);
+    uint32_t* slots = b->slots.data() + (size_t)parity * (b->slots.size() / 2) + warp * 32;
+    parity ^= 1u;
+    memcpy(&slots[lane], &v, 4);
     b->warps[warp]->arrive_and_wait();
     V out;
-    memcpy(&out, &b->slots[warp * 32 + (lane ^ (unsigned)lane_mask)], 4);
-    b->warps[warp]->arrive_and_wait();
+    memcpy(&out, &slots[lane ^ (unsigned)lane_mask], 4);
     return out;
 }
 

@@ -108,8 +108,7 @@ def _ppm_run(backend, flag, N, H, W, dtype):
         Fn.FUSE_PPM = keep
 
 
-@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize('shape', [(3, 6, 9), (2, 8, 8), (20, 1, 2)])
+@pytest.mark.parametrize('shape,dtype', [((3, 6, 9), torch.float32), ((2, 8, 8), torch.bfloat16), ((20, 1, 2), torch.float32)])
 def test_grouped_pyramid_kernels_on_the_simt_emulation(emulated, shape, dtype):
     N, H, W = shape
     before = emulated.emulated_calls
@@ -313,3 +312,35 @@ def test_emulation_agrees_with_a_kernel_validated_on_the_gpu(emulated, M_shape, 
         outs[name] = (gout.float(), sums)
     assert rel(outs['emu'][0], outs['ref'][0]) < 5e-3
     assert rel(outs['emu'][1], outs['ref'][1]) < 5e-3
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_grouped_pyramid_eval_on_the_simt_emulation(emulated, dtype):
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.models.fastscnn import PyramidPoolingModule
+    from torch_semantic_segmentation_b200.nn.blocks import set_compute_dtype
+    keep = Fn.FUSE_PPM
+    outs = {}
+    try:
+        for name, be, flag in (('ref', FakeBackend(), False), ('emu', emulated, True)):
+            _lib.set_backend(be)
+            Fn.FUSE_PPM = flag
+            torch.manual_seed(0)
+            m = set_compute_dtype(PyramidPoolingModule(128, 128), dtype, pw_impl=0)
+            with torch.no_grad():
+                for bn in [p[1][1] for p in m.pyramids]:
+                    bn.running_mean.normal_(0, 0.2)
+                    bn.running_var.uniform_(0.5, 1.5)
+                    bn.weight.uniform_(0.5, 1.5)
+                    bn.bias.normal_(0, 0.2)
+            m.eval()
+            g = torch.Generator().manual_seed(1)
+            x = ops.as_nhwc(torch.randn(1, 128, 8, 16, generator=g).to(dtype))
+            before = getattr(be, 'emulated_calls', 0)
+            with torch.no_grad():
+                outs[name] = m(x).float()
+            if flag:
+                assert be.emulated_calls - before == 2          # branches + concat
+    finally:
+        Fn.FUSE_PPM = keep
+    assert rel(outs['emu'], outs['ref']) < (1e-5 if dtype == torch.float32 else 2e-2)

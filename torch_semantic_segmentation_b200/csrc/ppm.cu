@@ -68,7 +68,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 ppm_branches_fwd_kernel(const T* __restrict__ pool, const int64_t* __restrict__ table, T* y, T* __restrict__ z,
                         float* __restrict__ mean_out, float* __restrict__ rstd_out, int C, int Cb, PpmBins bins,
-                        float momentum, float eps) {
+                        float momentum, float eps, int eval_mode) {
     TSS_DYN_SMEM(float, s_w);                            // [8][C]
     __shared__ float s_part[(kThreads / 32) * 16];
     __shared__ double s_sum[16];
@@ -99,6 +99,15 @@ ppm_branches_fwd_kernel(const T* __restrict__ pool, const int64_t* __restrict__ 
                 acc[c] = fmaf(xv[6], wb.z, acc[c]); acc[c] = fmaf(xv[7], wb.w, acc[c]);
             }
         }
+        if (eval_mode) {          // folded BatchNorm: table columns 1, 2 hold scale / shift (running statistics)
+            const float* sc = table_ptr<const float>(table, br, T_GAMMA);
+            const float* sh = table_ptr<const float>(table, br, T_BETA);
+            float o[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c] = fmaxf(fmaf(acc[c], __ldg(sc + c0 + c), __ldg(sh + c0 + c)), 0.f);
+            store8(z + (size_t)(row0 + r) * Cb + c0, o);
+            continue;
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             st[c] += acc[c];
@@ -106,6 +115,7 @@ ppm_branches_fwd_kernel(const T* __restrict__ pool, const int64_t* __restrict__ 
         }
         store8(y + (size_t)(row0 + r) * Cb + c0, acc);
     }
+    if (eval_mode) return;                                  // uniform over the grid
     block_sum16(st, s_part, s_sum);
     if (threadIdx.x < 8) {
         const int c = c0 + threadIdx.x;
@@ -395,8 +405,23 @@ extern "C" int tss_ppm_branches_fwd(const void* pool, const int64_t* table, void
     TSS_REQUIRE(smem <= 40 * 1024, "ppm_branches_fwd: C=%d too large", C);
     TSS_DISPATCH_DTYPE(dtype, "ppm_branches_fwd", {
         tss_launch(ppm_branches_fwd_kernel<T>, dim3(nbins, Cb / 8), kThreads, smem, (cudaStream_t)stream, (const T*)pool, table,
-                   (T*)y, (T*)z, mean, rstd, C, Cb, pb, momentum, eps);
+                   (T*)y, (T*)z, mean, rstd, C, Cb, pb, momentum, eps, 0);
         TSS_LAUNCH_CHECK("ppm_branches_fwd");
+        return TSS_OK;
+    });
+}
+
+extern "C" int tss_ppm_branches_eval(const void* pool, const int64_t* table, void* z, int N, int C, int Cb,
+                                     const int* bins, int nbins, int dtype, void* stream) {
+    PpmBins pb;
+    if (int e = make_bins(pb, bins, nbins, N, "ppm_branches_eval")) return e;
+    TSS_REQUIRE(N > 0 && C > 0 && C % 8 == 0 && Cb > 0 && Cb % 8 == 0, "ppm_branches_eval: N=%d C=%d Cb=%d", N, C, Cb);
+    const size_t smem = (size_t)8 * C * sizeof(float);
+    TSS_REQUIRE(smem <= 40 * 1024, "ppm_branches_eval: C=%d too large", C);
+    TSS_DISPATCH_DTYPE(dtype, "ppm_branches_eval", {
+        tss_launch(ppm_branches_fwd_kernel<T>, dim3(nbins, Cb / 8), kThreads, smem, (cudaStream_t)stream, (const T*)pool, table,
+                   (T*)nullptr, (T*)z, (float*)nullptr, (float*)nullptr, C, Cb, pb, 0.f, 0.f, 1);
+        TSS_LAUNCH_CHECK("ppm_branches_eval");
         return TSS_OK;
     });
 }

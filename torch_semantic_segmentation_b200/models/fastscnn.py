@@ -160,8 +160,32 @@ class PyramidPoolingModule(nn.Module):
             st.table = torch.tensor(ptrs, dtype=torch.int64).to(x.device)
         return st
 
+    def _grouped_eval(self, x):
+        """Eval mode with folded BatchNorm: pool -> all branches -> concat in three launches (instead of ten)."""
+        blocks = [p[1] for p in self.pyramids]
+        if not Fn.FUSE_PPM or self.training or torch.is_grad_enabled() or x.dtype != blocks[0].compute_dtype:
+            return None
+        if any(not b[1].track_running_stats or b[0].weight.device != x.device for b in blocks):
+            return None
+        folded = [b._folded(0) for b in blocks]
+        ptrs = [[b[0].weight.data_ptr(), f[0].data_ptr(), f[1].data_ptr()] + [0] * 7 for b, f in zip(blocks, folded)]
+        key = (x.device, tuple(map(tuple, ptrs)))
+        st = getattr(self, '_grouped_ev', None)
+        if st is None or st.key != key:
+            st = self._grouped_ev = _GroupedPPM()
+            st.key, st.bins, st.momentum, st.eps = key, self.bins, 0.0, 0.0
+            st.table = torch.tensor(ptrs, dtype=torch.int64).to(x.device)
+        N, C, H, W = x.shape
+        Cb = blocks[0][0].weight.shape[0]
+        pool, _ = ops.adaptive_pool_fwd(x, self.bins)
+        z = ops.ppm_branches_eval(pool, st.table, N, C, Cb, self.bins)
+        return ops.ppm_concat_fwd(x, z, Cb, self.bins)
+
     def forward(self, input):
         x = ops.as_nhwc(input)
+        cat = self._grouped_eval(x)
+        if cat is not None:
+            return self.conv(cat)
         st = self._grouped_state(x)
         if st is not None:
             params = [t for p in self.pyramids for t in (p[1][0].weight, p[1][1].weight, p[1][1].bias)]

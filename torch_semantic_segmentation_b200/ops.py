@@ -484,6 +484,14 @@ def ppm_branches_fwd(pool, table, N, C, Cb, bins, momentum, eps):
     return y, z, mean, rstd
 
 
+def ppm_branches_eval(pool, table, N, C, Cb, bins):
+    """Eval mode: all pyramid branches (1x1 conv + folded BatchNorm + ReLU) in one launch -> z."""
+    z = torch.empty((pool.shape[0], Cb), dtype=pool.dtype, device=pool.device)
+    _lib.call('tss_ppm_branches_eval', pool=pool, table=table, z=z, N=N, C=C, Cb=Cb, bins=_HostInts(bins),
+              nbins=len(bins), dtype=dtype_code(pool.dtype))
+    return z
+
+
 def ppm_concat_fwd(x, z, Cb, bins):
     N, C, H, W, ld = _g(x, 'ppm_concat_fwd')
     if ld != C:
