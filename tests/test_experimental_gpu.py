@@ -304,3 +304,26 @@ def test_stem_on_tensor_cores_matches_the_simt_stem(N, H, W):
     assert rel(ys[1], ys[0]) < 1e-2                       # image and weights rounded to bf16 on the tensor-core path
     assert rel(sts[1], sts[0]) < 1e-2
     assert rel(dws[1], dws[0]) < 1e-2
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_grouped_pyramid_pooling_eval_matches_layer_by_layer(dtype):
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.models import fastscnn
+    keep = Fn.FUSE_PPM
+    outs = {}
+    try:
+        for flag in (False, True):
+            Fn.FUSE_PPM = flag
+            torch.manual_seed(0)
+            model = fastscnn(3, 19).cuda().set_compute_dtype(dtype).eval()
+            g = torch.Generator().manual_seed(3)
+            x = torch.randn(1, 3, 256, 512, generator=g).cuda()
+            before = _lib.launch_count()
+            with torch.no_grad():
+                outs[flag] = (model(x).float(), _lib.launch_count() - before)
+            torch.cuda.synchronize()
+    finally:
+        Fn.FUSE_PPM = keep
+    assert rel(outs[True][0], outs[False][0]) < (1e-4 if dtype == torch.float32 else 2e-2)
+    assert outs[True][1] <= outs[False][1] - 7
