@@ -128,7 +128,14 @@ class FakeBackend:
         return 0
 
     def tss_pack_weights_multi(self, arena, table, n_entries, max_elems):
-        raise NotImplementedError('bf16 tensor-core packs are not used on the CPU emulation')
+        import ctypes
+        for off, Nc, K, wp, wpT in table.tolist():
+            w = arena[off:off + Nc * K].view(Nc, K)
+            for addr, src in ((wp, w), (wpT, w.t())):
+                if addr:
+                    dst = torch.frombuffer((ctypes.c_uint16 * (Nc * K)).from_address(int(addr)), dtype=torch.bfloat16)
+                    dst.copy_(src.reshape(-1))
+        return 0
 
     # ---------------------------------------------------------------- dense 3x3 as a patch GEMM
     def tss_im2col3x3(self, x, col, N, H, W, C, dtype):
