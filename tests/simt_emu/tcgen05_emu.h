@@ -28,19 +28,29 @@ enum CUtensorMapL2promotion { CU_TENSOR_MAP_L2_PROMOTION_L2_128B = 2 };
 enum CUtensorMapFloatOOBfill { CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = 0 };
 struct CUtensorMap {
     const unsigned char* base;
-    uint64_t dim[2], stride1;        // dim[0] = innermost extent (elements), stride1 = row pitch in bytes
-    uint32_t box[2];
+    uint32_t rank;
+    uint64_t dim[4], stride[4];      // dim[0] = innermost extent (elements); stride[i] = byte pitch of dimension i (stride[0] = element)
+    uint32_t box[4];
     int elem_bytes, swizzle;
 };
 inline CUresult tss_emu_encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* gdim,
                                      const cuuint64_t* gstr, const cuuint32_t* box, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
-    if (rank != 2 || dt != CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 || sw != CU_TENSOR_MAP_SWIZZLE_128B || box[0] * 2 != 128) return 1;
+    if (rank < 2 || rank > 4) return 1;
+    m->elem_bytes = dt == CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 ? 2 : 4;
+    if (sw == CU_TENSOR_MAP_SWIZZLE_128B && (rank != 2 || box[0] * (uint32_t)m->elem_bytes != 128)) return 1;
+    if (sw != CU_TENSOR_MAP_SWIZZLE_128B && sw != CU_TENSOR_MAP_SWIZZLE_NONE) return 1;
+    if (((uintptr_t)base & 15) != 0) return 1;
     m->base = (const unsigned char*)base;
-    m->dim[0] = gdim[0]; m->dim[1] = gdim[1];
-    m->stride1 = gstr[0];
-    m->box[0] = box[0]; m->box[1] = box[1];
-    m->elem_bytes = 2; m->swizzle = 1;
+    m->rank = rank;
+    m->stride[0] = (uint64_t)m->elem_bytes;
+    for (uint32_t i = 0; i < 4; ++i) {
+        m->dim[i] = i < rank ? gdim[i] : 1;
+        m->box[i] = i < rank ? box[i] : 1;
+        if (i >= 1) m->stride[i] = i < rank ? gstr[i - 1] : 0;
+        if (i >= 1 && i < rank && gstr[i - 1] % 16 != 0) return 1;
+    }
+    m->swizzle = sw == CU_TENSOR_MAP_SWIZZLE_128B;
     return CUDA_SUCCESS;
 }
 enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0 };
@@ -98,20 +108,38 @@ inline void mbar_wait(uint32_t bar, uint32_t parity) {
         std::this_thread::yield();
     }
 }
-inline void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    for (uint32_t r = 0; r < map->box[1]; ++r)
-        for (uint32_t k = 0; k < map->box[0]; ++k) {
-            uint16_t v = 0;
-            const int64_t row = (int64_t)c1 + r, col = (int64_t)c0 + k;
-            if (row >= 0 && col >= 0 && (uint64_t)row < map->dim[1] && (uint64_t)col < map->dim[0])
-                memcpy(&v, map->base + (uint64_t)row * map->stride1 + (uint64_t)col * 2, 2);
-            memcpy(tss_emu::dyn_smem + tss_emu::swz128(dst + r * 128 + k * 2), &v, 2);
-        }
+inline void tma_load_nd(uint32_t dst, const CUtensorMap* map, uint32_t bar, const int (&c)[4]) {
+    const uint32_t eb = (uint32_t)map->elem_bytes;
+    uint32_t off = 0;                                    // dense box in shared memory, innermost dimension first
+    for (uint32_t i3 = 0; i3 < map->box[3]; ++i3)
+        for (uint32_t i2 = 0; i2 < map->box[2]; ++i2)
+            for (uint32_t i1 = 0; i1 < map->box[1]; ++i1)
+                for (uint32_t i0 = 0; i0 < map->box[0]; ++i0, off += eb) {
+                    const int64_t x[4] = {(int64_t)c[0] + i0, (int64_t)c[1] + i1, (int64_t)c[2] + i2, (int64_t)c[3] + i3};
+                    unsigned char v[4] = {0, 0, 0, 0};
+                    bool in = true;
+                    uint64_t src = 0;
+                    for (int d = 0; d < 4; ++d) {
+                        in = in && x[d] >= 0 && (uint64_t)x[d] < map->dim[d];
+                        src += (uint64_t)x[d] * map->stride[d];
+                    }
+                    if (in) memcpy(v, map->base + src, eb);
+                    memcpy(tss_emu::dyn_smem + (map->swizzle ? tss_emu::swz128(dst + off) : dst + off), v, eb);
+                }
     std::lock_guard<std::mutex> l(tss_emu::mbar_mutex);
     tss_emu::MBar& b = tss_emu::mbars[bar >> 3];
-    b.tx -= (int)(map->box[0] * map->box[1] * 2);
+    b.tx -= (int)off;
     tss_emu::mbar_check(b);
 }
+inline void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    const int c[4] = {c0, c1, 0, 0};
+    tma_load_nd(dst, map, bar, c);
+}
+inline void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    const int c[4] = {c0, c1, c2, c3};
+    tma_load_nd(dst, map, bar, c);
+}
+inline void mbar_fence_init() {}
 inline void fence_async_smem() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void tc_alloc(uint32_t slot, uint32_t) {
     const uint32_t base = 0;

@@ -21,7 +21,7 @@ CSRC = os.path.join(ROOT, 'torch_semantic_segmentation_b200', 'csrc')
 EMU = os.path.join(ROOT, 'tests', 'simt_emu')
 SOURCES = ['ppm.cu', 'augment.cu', 'dwconv_bnred.cu',        # dwconv_bnred.cu: the stride-2 (plain SIMT) kernel only
            'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu',
-           'pwconv_tc_bnred.cu']                             # validated on the B200: calibrates the emulation itself                               # on the functional tcgen05/TMA/mbarrier emulation
+           'pwconv_tc_bnred.cu', 'dwconv.cu', 'dwconv_tma.cu']       # validated on the B200: calibrate the emulation itself                               # on the functional tcgen05/TMA/mbarrier emulation
 
 
 def rel(a, b):
@@ -344,3 +344,39 @@ def test_grouped_pyramid_eval_on_the_simt_emulation(emulated, dtype):
     finally:
         Fn.FUSE_PPM = keep
     assert rel(outs['emu'], outs['ref']) < (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('C,N,H,W,stride,dil', [(64, 2, 12, 20, 1, 1), (48, 1, 9, 13, 1, 1), (384, 1, 5, 7, 1, 1), (32, 1, 16, 24, 2, 1),
+                                                (128, 1, 12, 12, 1, 4)])
+def test_emulation_agrees_with_the_validated_depthwise_kernels(emulated, C, N, H, W, stride, dil, dtype):
+    """csrc/dwconv_tma.cu / dwconv.cu are parity-green on the B200 (tests/test_kernels_gpu.py): forward with
+    statistics, dgrad, wgrad and the stride-1 dgrad with fused reduction must give the same answers on the
+    emulation -- this pins its model of 4-D TMA boxes (halo coordinates, zero fill) and of the mbarrier pipelines."""
+    g = torch.Generator().manual_seed(C + H + stride)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    x, dy = _nhwc(N, C, H, W, g, dtype), _nhwc(N, C, Ho, Wo, g, dtype)
+    w = torch.randn(C, 1, 3, 3, generator=g) / 3
+    code = _lib.dtype_code(dtype)
+    outs = {}
+    for name, be in (('ref', FakeBackend()), ('emu', emulated)):
+        y = torch.zeros(N, Ho, Wo, C, dtype=dtype).permute(0, 3, 1, 2)
+        stats = torch.zeros(2 * C, dtype=torch.float64)
+        be.call('tss_dwconv3x3_fwd', dict(x=x, w=w, y=y, N=N, Hi=H, Wi=W, C=C, stride=stride, dilation=dil, scale=None, shift=None,
+                                          flags=0, stats=stats, dtype=code))
+        dx = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2)
+        be.call('tss_dwconv3x3_dgrad', dict(dy=dy, w=w, dx=dx, N=N, Hi=H, Wi=W, C=C, stride=stride, dilation=dil, dtype=code))
+        dw = torch.zeros(C, 1, 3, 3)
+        be.call('tss_dwconv3x3_wgrad', dict(x=x, dy=dy, dw=dw, N=N, Hi=H, Wi=W, C=C, stride=stride, dilation=dil, dtype=code))
+        outs[name] = [y.float(), stats, dx.float(), dw]
+        if stride == 1 and dil == 1 and C % 32 == 0:
+            mean, rstd = torch.linspace(-0.2, 0.2, C), torch.linspace(0.5, 1.5, C)
+            gamma, beta = torch.linspace(0.5, 1.5, C), torch.linspace(-0.3, 0.3, C)
+            gout = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2)
+            sums = torch.zeros(2 * C)
+            be.call('tss_dwconv3x3_dgrad_bnred', dict(dy=dy, w=w, g=gout, N=N, H=H, W=W, C=C, yp=x, mean=mean, rstd=rstd, gamma=gamma,
+                                                      beta=beta, flags=1, sums=sums, dtype=code))
+            outs[name] += [gout.float(), sums]
+    tol = 1e-5 if dtype == torch.float32 else 5e-3
+    for a, b in zip(outs['emu'], outs['ref']):
+        assert rel(a, b) < max(tol, 2e-3 if a.dtype == torch.float32 and a.dim() == 1 else tol), rel(a, b)

@@ -34,7 +34,7 @@ dw_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restric
               const float* __restrict__ scale, const float* __restrict__ shift, int flags,
               double* __restrict__ stats) {
     pdl_wait();
-    extern __shared__ float s_stats[];   // [2*C] when stats != nullptr
+    TSS_DYN_SMEM(float, s_stats);        // [2*C] when stats != nullptr
     const int CG = C >> 3;
     const int nstrips = (Ho + R - 1) / R;
     const int64_t total = (int64_t)N * nstrips * Wo * CG;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kThreads)
 dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw,
                 int N, int Hi, int Wi, int Ho, int Wo, int C, int PL) {
     pdl_wait();
-    extern __shared__ float s_red[];   // [PL][C]
+    TSS_DYN_SMEM(float, s_red);        // [PL][C]
     const int CG = C >> 3;
     const int cg = threadIdx.x % CG;
     const int pl = threadIdx.x / CG;

@@ -4,15 +4,10 @@
 // conv.  The epilogue reads the matching yp values, applies the ReLU mask recomputed from yp, stores
 // g = dz * mask instead of dz and accumulates  sums[c] += sum g,  sums[C+c] += sum g * xhat  (what
 // bn_bwd_reduce_kernel would compute in a pass of its own over dz and yp).
-#ifdef TSS_HOST_EMU            // tests/simt_emu: only the plain SIMT kernel (stride 2) is built for the host
-#include "common.cuh"
-#else
 #include "tma.cuh"
-#endif
 
 namespace {
 
-#ifndef TSS_HOST_EMU
 constexpr int TH = 8;
 constexpr int IH = TH + 2;
 
@@ -22,7 +17,7 @@ dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const float* __re
                       int H, int W, int C, int CB, int TW, int tiles_w, int tiles_h, const T* __restrict__ yp,
                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                       const float* __restrict__ beta, int relu, float* __restrict__ sums) {
-    extern __shared__ uint8_t smem_raw[];
+    TSS_DYN_SMEM(uint8_t, smem_raw);
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     const int IW = TW + 2;
     const uint32_t tile_bytes = (uint32_t)IH * IW * CB * sizeof(T);
@@ -126,8 +121,6 @@ dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const float* __re
         atomicAdd(sums + which * C + cb0 + ch, s);
     }
 }
-
-#endif  // !TSS_HOST_EMU
 
 // ---------------------------------------------------------------------------------------------
 // Stride 2: the quad kernel of dwconv.cu (2x2 input pixels per 2x2 gradient neighbourhood, vertical
@@ -241,11 +234,9 @@ dw_dgrad_s2_bnred_kernel(const T* __restrict__ dy, const float* __restrict__ w, 
 
 int gcd_int2(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
-#ifndef TSS_HOST_EMU
 template <typename T> struct TmaTypeB;
 template <> struct TmaTypeB<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
 template <> struct TmaTypeB<bf16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
-#endif
 
 }  // namespace
 
@@ -277,7 +268,6 @@ extern "C" int tss_dwconv3x3_dgrad_s2_bnred(const void* dy, const float* w, void
     });
 }
 
-#ifndef TSS_HOST_EMU
 extern "C" int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g, int N, int H, int W, int C,
                                          const void* yp, const float* mean, const float* rstd, const float* gamma,
                                          const float* beta, int flags, float* sums, int dtype, void* stream) {
@@ -318,4 +308,3 @@ extern "C" int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g
         return TSS_OK;
     });
 }
-#endif  // !TSS_HOST_EMU

@@ -25,7 +25,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
               const float* __restrict__ scale, const float* __restrict__ shift, int flags,
               double* __restrict__ stats) {
     constexpr int IH = Geo<S, D, TH>::IH;
-    extern __shared__ uint8_t smem_raw[];
+    TSS_DYN_SMEM(uint8_t, smem_raw);
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     const int IW = (TW - 1) * S + 2 * D + 1;
     const uint32_t tile_bytes = (uint32_t)IH * IW * CB * sizeof(T);
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(192, 2)
 dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                     float* __restrict__ dw, int CB, int TW, int tiles_w, int tiles_h, int ntiles, uint32_t stage_bytes) {
     constexpr int IH = Geo<S, D, TH>::IH;
-    extern __shared__ uint8_t smem_raw[];
+    TSS_DYN_SMEM(uint8_t, smem_raw);
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     const int IW = (TW - 1) * S + 2 * D + 1;
     const uint32_t x_bytes = (uint32_t)IH * IW * CB * sizeof(T);

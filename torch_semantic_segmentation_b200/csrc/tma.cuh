@@ -1,8 +1,12 @@
 // TMA / mbarrier helpers shared by the tensor-core GEMMs and the TMA-staged depthwise kernels.
 #pragma once
+#ifdef TSS_HOST_EMU            // tests/simt_emu: functional emulation of the same functions for host builds
+#include "tcgen05_emu.h"
+#else
 #include <cuda.h>
 
 #include "common.cuh"
+#endif
 
 typedef CUresult (*TssEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -21,6 +25,7 @@ static inline TssEncodeTiledFn tss_encode_tiled() {
     return fn;
 }
 
+#ifndef TSS_HOST_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -57,3 +62,4 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+#endif  // !TSS_HOST_EMU
