@@ -75,6 +75,17 @@ int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g, int N, in
 int tss_dwconv3x3_dgrad_s2_bnred(const void* dy, const float* w, void* g, int N, int Hi, int Wi, int C,
                                  const void* yp, const float* mean, const float* rstd, const float* gamma,
                                  const float* beta, int flags, float* sums, int dtype, void* stream);
+/* Training, stride 1 / dilation 1: BatchNorm-backward APPLY of this depthwise layer + its dgrad + the producer's
+ * BatchNorm-backward reduction in ONE kernel (the depthwise counterpart of tss_pwconv_bwd_fused).  dz, y
+ * [N][H][W][C]: gradient after this layer's BN/ReLU and its raw conv output (two TMA halo tiles); sums[2C]: the
+ * finished reduction of this layer (flags&TSS_EPI_RELU: mask recomputed from y; 0: dz already masked).  dy
+ * (may be NULL): the BatchNorm-backward output, stored for the weight gradient.  g: masked gradient for the producer
+ * (yp, pmean, ..., psums as in tss_dwconv3x3_dgrad_bnred).  dgamma += sums[C+c], dbeta += sums[c]. */
+int tss_dwconv3x3_bwd_fused(const void* dz, const void* y, const float* w, const float* mean, const float* rstd,
+                            const float* gamma, const float* beta, const float* sums, int flags, int64_t count,
+                            void* dy, float* dgamma, float* dbeta, void* g, int N, int H, int W, int C,
+                            const void* yp, const float* pmean, const float* prstd, const float* pgamma,
+                            const float* pbeta, int pflags, float* psums, int dtype, void* stream);
 /* grad wrt weight: dw[C][3][3] (fp32) += sum_{n,ho,wo} x * dy  (warp-shuffle + block
  * reduction, fp32 atomics).  dw must be zeroed (or hold a gradient to accumulate into). */
 int tss_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi, int C,

@@ -101,6 +101,14 @@ class FakeBackend:
         dz = nngrad.conv2d_input((N, C, H, W), w.detach().view(C, 1, 3, 3), dy.float(), 1, 1, 1, C)
         return self._bnred(dz, g, yp, mean, rstd, gamma, beta, flags, sums)
 
+    def tss_dwconv3x3_bwd_fused(self, dz, y, w, mean, rstd, gamma, beta, sums, flags, count, dy, dgamma, dbeta, g, N, H, W, C,
+                                yp, pmean, prstd, pgamma, pbeta, pflags, psums, dtype):
+        out = dy if dy is not None else torch.empty_like(dz)
+        self.tss_bn_bwd_apply(dz, None, y, mean, rstd, gamma, beta, sums, out, None, dgamma, dbeta, N * H * W, count, C, C, 0, C,
+                              C, 0, flags, dtype)
+        d = nngrad.conv2d_input((N, C, H, W), w.detach().view(C, 1, 3, 3), out.float(), 1, 1, 1, C)
+        return self._bnred(d, g, yp, pmean, prstd, pgamma, pbeta, pflags, psums)
+
     def tss_dwconv3x3_dgrad_s2_bnred(self, dy, w, g, N, Hi, Wi, C, yp, mean, rstd, gamma, beta, flags, sums, dtype):
         dz = nngrad.conv2d_input((N, C, Hi, Wi), w.detach().view(C, 1, 3, 3), dy.float(), 2, 1, 1, C)
         return self._bnred(dz, g, yp, mean, rstd, gamma, beta, flags, sums)

@@ -7,6 +7,7 @@ unvalidated kernel can never hang the default GPU suite.
 * pointwise backward with the layer's BatchNorm-backward apply folded into the GEMM's A-operand producer
   (csrc/pwconv_tc_bwd.cu: pw_tc_bwd_kernel; enabled in the model by TSS_FUSE_BNAPPLY=1);
 * the pyramid-pooling branches as grouped launches (csrc/ppm.cu; enabled in the model by TSS_FUSE_PPM=1);
+* the same for the stride-1 depthwise layers (csrc/dwconv_bwd_fused.cu; TSS_FUSE_BNAPPLY_DW=1);
 * BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu; TSS_FUSE_BNFIN=1);
 * the stem convolution and its weight gradient on tcgen05 (csrc/stem_tc.cu; TSS_STEM_TC=1);
 * the device input pipeline (csrc/augment.cu; its per-pixel arithmetic is already pinned on the host by
@@ -327,3 +328,39 @@ def test_grouped_pyramid_pooling_eval_matches_layer_by_layer(dtype):
         Fn.FUSE_PPM = keep
     assert rel(outs[True][0], outs[False][0]) < (1e-4 if dtype == torch.float32 else 2e-2)
     assert outs[True][1] <= outs[False][1] - 7
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('C,N,H,W,relu', [(384, 2, 48, 48, 1), (64, 2, 12, 20, 1), (96, 1, 9, 40, 0), (128, 1, 17, 33, 1), (576, 2, 24, 24, 1)])
+def test_dw_backward_with_bn_apply_matches_the_two_kernel_path(C, N, H, W, relu, dtype):
+    """tss_dwconv3x3_bwd_fused == tss_bn_bwd_apply -> tss_dwconv3x3_dgrad_bnred, both on the GPU."""
+    g = torch.Generator().manual_seed(C + H + W)
+    mk = lambda: torch.randn(N, H, W, C, generator=g).to(dtype).cuda().permute(0, 3, 1, 2)
+    dz, y, yp = mk(), mk(), mk()
+    w = (torch.randn(C, 1, 3, 3, generator=g) / 3).cuda()
+    par = lambda: [t.cuda() for t in (torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.5,
+                                      torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3)]
+    mean, rstd, gamma, beta = par()
+    pmean, prstd, pgamma, pbeta = par()
+    M = N * H * W
+    be = _lib.backend()
+    code = _lib.dtype_code(dtype)
+    sums = torch.zeros(2 * C, device='cuda')
+    be.call('tss_bn_bwd_reduce', dict(dz=dz, z=None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, M=M, C=C, lddz=C,
+                                      ldz=0, ldy=C, flags=relu, dtype=code))
+    new = lambda: torch.zeros(N, H, W, C, dtype=dtype, device='cuda').permute(0, 3, 1, 2)
+    dy1, g1, dy2, g2 = new(), new(), new(), new()
+    dga1, dbe1, ps1 = torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda'), torch.zeros(2 * C, device='cuda')
+    dga2, dbe2, ps2 = torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda'), torch.zeros(2 * C, device='cuda')
+    be.call('tss_bn_bwd_apply', dict(dz=dz, z=None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, dy=dy1, dres=None,
+                                     dgamma=dga1, dbeta=dbe1, M=M, count=M, C=C, lddz=C, ldz=0, ldy=C, lddy=C, lddres=0, flags=relu,
+                                     dtype=code))
+    be.call('tss_dwconv3x3_dgrad_bnred', dict(dy=dy1, w=w, g=g1, N=N, H=H, W=W, C=C, yp=yp, mean=pmean, rstd=prstd, gamma=pgamma,
+                                              beta=pbeta, flags=1, sums=ps1, dtype=code))
+    be.call('tss_dwconv3x3_bwd_fused', dict(dz=dz, y=y, w=w, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, flags=relu,
+                                            count=M, dy=dy2, dgamma=dga2, dbeta=dbe2, g=g2, N=N, H=H, W=W, C=C, yp=yp, pmean=pmean,
+                                            prstd=prstd, pgamma=pgamma, pbeta=pbeta, pflags=1, psums=ps2, dtype=code))
+    torch.cuda.synchronize()
+    tol = 1e-5 if dtype == torch.float32 else 6e-3
+    assert rel(dy2, dy1) < tol and rel(g2, g1) < 2 * tol
+    assert rel(dga2, dga1) < 1e-6 and rel(dbe2, dbe1) < 1e-6 and rel(ps2, ps1) < max(tol, 2e-3)

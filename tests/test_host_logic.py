@@ -221,11 +221,12 @@ def test_gated_backward_fusions_are_plumbing_equivalent(fake_backend):
     fake_backend.call = counting
     g = torch.Generator().manual_seed(1)
     x, y = torch.randn(2, 3, 64, 64, generator=g), torch.randint(0, 19, (2, 64, 64), generator=g)
-    keep = Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY, Fn.FUSE_BNFIN
+    keep = Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY, Fn.FUSE_BNFIN, Fn.FUSE_BNAPPLY_DW
     runs = {}
     try:
-        for ext, fused in ((False, False), (True, False), (False, True), (True, True), ('fin', False)):
+        for ext, fused in ((False, False), (True, False), (False, True), (True, True), ('fin', False), ('dw', False)):
             Fn.FUSE_BNFIN = ext == 'fin'
+            Fn.FUSE_BNAPPLY_DW = ext == 'dw'
             Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY = ext is True, fused
             calls.clear()
             torch.manual_seed(0)
@@ -233,8 +234,12 @@ def test_gated_backward_fusions_are_plumbing_equivalent(fake_backend):
             CrossEntropyLoss(ignore_index=255)(model(x), y).backward()
             runs[ext, fused] = (torch.cat([p.grad.reshape(-1) for p in model.parameters()]), dict(calls))
     finally:
-        Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY, Fn.FUSE_BNFIN = keep
+        Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY, Fn.FUSE_BNFIN, Fn.FUSE_BNAPPLY_DW = keep
     base, base_calls = runs[False, False]
+    # BatchNorm-backward apply folded into the stride-1 depthwise dgrads that carry a fused reduction
+    assert rel(runs['dw', False][0], base) < 1e-6
+    assert runs['dw', False][1]['tss_dwconv3x3_bwd_fused'] == base_calls['tss_dwconv3x3_dgrad_bnred']
+    assert runs['dw', False][1]['tss_bn_bwd_apply'] == base_calls['tss_bn_bwd_apply'] - base_calls['tss_dwconv3x3_dgrad_bnred']
     # finalize folded into the apply kernel: same arithmetic, 44 launches less
     assert rel(runs['fin', False][0], base) < 1e-6
     assert runs['fin', False][1]['tss_bn_finalize_apply'] == 44 and 'tss_bn_finalize' not in runs['fin', False][1]

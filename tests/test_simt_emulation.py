@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, 'torch_semantic_segmentation_b200', 'csrc')
 EMU = os.path.join(ROOT, 'tests', 'simt_emu')
 SOURCES = ['ppm.cu', 'augment.cu', 'dwconv_bnred.cu',        # dwconv_bnred.cu: the stride-2 (plain SIMT) kernel only
-           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu',
+           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu', 'dwconv_bwd_fused.cu',
            'pwconv_tc_bnred.cu', 'dwconv.cu', 'dwconv_tma.cu']       # validated on the B200: calibrate the emulation itself                               # on the functional tcgen05/TMA/mbarrier emulation
 
 
@@ -380,3 +380,39 @@ def test_emulation_agrees_with_the_validated_depthwise_kernels(emulated, C, N, H
     tol = 1e-5 if dtype == torch.float32 else 5e-3
     for a, b in zip(outs['emu'], outs['ref']):
         assert rel(a, b) < max(tol, 2e-3 if a.dtype == torch.float32 and a.dim() == 1 else tol), rel(a, b)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('C,N,H,W,relu', [(64, 2, 12, 20, 1), (384, 1, 5, 7, 1), (96, 1, 9, 40, 0), (32, 3, 1, 1, 1), (128, 1, 17, 33, 1)])
+def test_depthwise_backward_with_bn_apply_on_the_emulation(emulated, C, N, H, W, relu, dtype):
+    """csrc/dwconv_bwd_fused.cu: two TMA halo tiles (dz, y) -> dy in shared memory (zero outside the image) ->
+    flipped-tap stencil -> producer mask + reduction; dy interior stored for the weight gradient."""
+    g = torch.Generator().manual_seed(C + H + W)
+    dz, y, yp = _nhwc(N, C, H, W, g, dtype), _nhwc(N, C, H, W, g, dtype), _nhwc(N, C, H, W, g, dtype)
+    w = torch.randn(C, 1, 3, 3, generator=g) / 3
+    par = lambda: (torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.5, torch.rand(C, generator=g) + 0.5,
+                   torch.randn(C, generator=g) * 0.3)
+    mean, rstd, gamma, beta = par()
+    pmean, prstd, pgamma, pbeta = par()
+    M = N * H * W
+    fake = FakeBackend()
+    sums = torch.zeros(2 * C)
+    code = _lib.dtype_code(dtype)
+    fake.call('tss_bn_bwd_reduce', dict(dz=dz, z=None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, M=M, C=C,
+                                        lddz=C, ldz=0, ldy=C, flags=relu, dtype=code))
+    outs = {}
+    for name, be in (('ref', fake), ('emu', emulated)):
+        dy = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2)
+        gout = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2)
+        dgamma, dbeta, psums = torch.ones(C), torch.ones(C), torch.zeros(2 * C)
+        be.call('tss_dwconv3x3_bwd_fused', dict(dz=dz, y=y, w=w, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, flags=relu,
+                                                count=M, dy=dy, dgamma=dgamma, dbeta=dbeta, g=gout, N=N, H=H, W=W, C=C, yp=yp,
+                                                pmean=pmean, prstd=prstd, pgamma=pgamma, pbeta=pbeta, pflags=1, psums=psums,
+                                                dtype=code))
+        outs[name] = (dy.float(), gout.float(), dgamma, dbeta, psums)
+    r, e = outs['ref'], outs['emu']
+    tol = 2e-5 if dtype == torch.float32 else 6e-3
+    assert rel(e[0], r[0]) < tol, ('dy', rel(e[0], r[0]))
+    assert rel(e[1], r[1]) < 2 * tol, ('g', rel(e[1], r[1]))
+    assert rel(e[2], r[2]) < 1e-6 and rel(e[3], r[3]) < 1e-6
+    assert rel(e[4], r[4]) < max(tol, 2e-3), ('psums', rel(e[4], r[4]))

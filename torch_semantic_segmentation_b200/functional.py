@@ -163,6 +163,10 @@ FUSE_BNRED_EXT = os.environ.get('TSS_FUSE_BNRED_EXT', '0') == '1'
 # launch and one read of dy less per 1x1 layer without a residual).  Built and CPU-checked through the
 # emulated ABI, not yet validated on a B200: off unless TSS_FUSE_BNAPPLY=1.
 FUSE_BNAPPLY = os.environ.get('TSS_FUSE_BNAPPLY', '0') == '1'
+# The same for the stride-1 depthwise layers whose dgrad already carries the producer's reduction
+# (csrc/dwconv_bwd_fused.cu: dz and y arrive as two TMA halo tiles, dy replaces dz in shared memory).
+# Off unless TSS_FUSE_BNAPPLY_DW=1.
+FUSE_BNAPPLY_DW = os.environ.get('TSS_FUSE_BNAPPLY_DW', '0') == '1'
 # The four pyramid-pooling branches as grouped launches (csrc/ppm.cu): 3 launches forward and 5 backward instead
 # of ~18 and ~26.  Same status: off unless TSS_FUSE_PPM=1.
 FUSE_PPM = os.environ.get('TSS_FUSE_PPM', '0') == '1'
@@ -284,6 +288,28 @@ class ConvBNAct(torch.autograd.Function):
                 wgrad_lane.run(dy.device, lambda: ops.pwconv_wgrad(x, dy, dw, impl=1), x, dy)
             else:
                 ops.pwconv_wgrad(x, dy, dw, impl=1)
+            grad_ready(*ctx.params)
+            return (dx, None, None if gw is not None else dw, None if gg is not None else gg_out,
+                    None if gb is not None else gb_out, None, None, None)
+        if (FUSE_BNAPPLY_DW and spec.kind == 'dw' and prod is not None and spec.stride == 1 and spec.dilation == 1
+                and C % 32 == 0 and not ctx.has_res and ctx.sync[0] == 1 and ctx.needs_input_grad[0]
+                and ops.geom(dz)[4] == C):
+            # one kernel: this layer's BatchNorm-backward apply -> depthwise dgrad -> the producer's reduction
+            if link is not None and link.reduced:
+                sums, mask = link.sums, False
+            else:
+                sums = ctx.scratch[2 * C:].view(torch.float32)
+                if spec.bn._tss_dirty or ctx.scratch is not getattr(spec.bn, '_tss_scratch', None):
+                    sums = ops.zeros_f32(2 * C, weight.device)
+                spec.bn._tss_dirty = True
+                ops.bn_backward_reduce(dz, y, mean, rstd, gamma, beta, spec.relu, sums)
+                mask = spec.relu
+            dy, dx = ops.dwconv_bwd_fused(dz, y, weight, mean, rstd, gamma, beta, sums, mask, prod, dgamma=gg_out, dbeta=gb_out)
+            prod.reduced, prod.bn._tss_dirty = True, True
+            if gw is not None:
+                wgrad_lane.run(dy.device, lambda: ops.dwconv_wgrad(x, dy, dw, 1, 1), x, dy)
+            else:
+                ops.dwconv_wgrad(x, dy, dw, 1, 1)
             grad_ready(*ctx.params)
             return (dx, None, None if gw is not None else dw, None if gg is not None else gg_out,
                     None if gb is not None else gb_out, None, None, None)
