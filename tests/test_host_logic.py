@@ -327,3 +327,43 @@ def test_tensor_core_stem_gate_is_plumbing_equivalent(fake_backend):
     assert torch.isfinite(runs[True][1]).all() and float(runs[True][1].abs().sum()) > 0
     assert runs[True][2].get('tss_stem3x3s2_fwd_tc') == 1 and runs[True][2].get('tss_stem3x3s2_wgrad_tc') == 1
     assert 'tss_stem3x3s2_fwd' not in runs[True][2] and 'tss_stem3x3s2_fwd_tc' not in runs[False][2]
+
+
+@pytest.mark.parametrize('arch', ['fastscnn', 'contextnet14'])
+def test_all_gates_together_train_and_eval(fake_backend, arch):
+    """Every off-by-default kernel gate switched on at once: two optimisation steps and an eval forward agree with
+    the default path at bf16 level (the tensor-core stem rounds the image to bf16), with far fewer launches."""
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.models.contextnet import contextnet14
+    from torch_semantic_segmentation_b200.nn.blocks import set_compute_dtype
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    flags = ['FUSE_BNRED_EXT', 'FUSE_BNAPPLY', 'FUSE_BNAPPLY_DW', 'FUSE_PPM', 'FUSE_BNFIN', 'STEM_TC']
+    keep = {f: getattr(Fn, f) for f in flags}
+    factory = {'fastscnn': fastscnn, 'contextnet14': contextnet14}[arch]
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(4, 3, 64, 96, generator=g), torch.randint(0, 19, (4, 64, 96), generator=g)
+    runs = {}
+    try:
+        for on in (False, True):
+            for f in flags:
+                setattr(Fn, f, on)
+            torch.manual_seed(0)
+            model = set_compute_dtype(_no_dropout(factory(3, 19)), torch.bfloat16, pw_impl=1).train()
+            opt = FlatAdamW(model.parameters(), lr=1e-3)
+            before, losses = fake_backend.launches, []
+            for _ in range(2):
+                opt.zero_grad()
+                loss = CrossEntropyLoss(ignore_index=255)(model(x), y)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss.detach()))
+            with torch.no_grad():
+                out = model.eval()(x).float()
+            runs[on] = (losses, out, fake_backend.launches - before)
+    finally:
+        for f, v in keep.items():
+            setattr(Fn, f, v)
+    for a, b in zip(runs[True][0], runs[False][0]):
+        assert abs(a - b) < 5e-3 * abs(b), (runs[True][0], runs[False][0])
+    assert rel(runs[True][1], runs[False][1]) < 6e-2
+    assert runs[True][2] < runs[False][2] - 100
