@@ -34,6 +34,7 @@ struct dim3 {
 };
 struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct alignas(16) longlong2 { long long x, y; };
 inline float2 make_float2(float x, float y) { return {x, y}; }
@@ -54,6 +55,7 @@ struct Block {
     }
 };
 extern thread_local Block* block;
+extern thread_local unsigned slot_parity;
 extern unsigned char dyn_smem[256 * 1024];
 }  // namespace tss_emu
 extern thread_local uint3 threadIdx, blockIdx;
@@ -68,7 +70,7 @@ template <typename V> inline V __shfl_xor_sync(unsigned, V v, int lane_mask) {
     static_assert(sizeof(V) == 4, "32-bit shuffles only");
     // one barrier per shuffle: the exchange slots are double-buffered on the call parity, so a lane that races
     // ahead into the next shuffle writes the other buffer and cannot clobber a value a slower lane still reads
-    static thread_local unsigned parity = 0;
+    unsigned& parity = tss_emu::slot_parity;             // shared by every warp-exchange primitive of the thread
     tss_emu::Block* b = tss_emu::block;
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t* slots = b->slots.data() + (size_t)parity * (b->slots.size() / 2) + warp * 32;
@@ -79,6 +81,47 @@ template <typename V> inline V __shfl_xor_sync(unsigned, V v, int lane_mask) {
     memcpy(&out, &slots[lane ^ (unsigned)lane_mask], 4);
     return out;
 }
+
+// all 32 values of the warp (lanes of a partial last warp that do not exist read as absent)
+inline void tss_emu_warp_gather(uint32_t v, uint32_t (&all)[32], int& nlanes) {
+    unsigned& parity = tss_emu::slot_parity;
+    tss_emu::Block* b = tss_emu::block;
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t* slots = b->slots.data() + (size_t)parity * (b->slots.size() / 2) + warp * 32;
+    parity ^= 1u;
+    slots[lane] = v;
+    b->warps[warp]->arrive_and_wait();
+    const int total = (int)blockDim.x - (int)warp * 32;
+    nlanes = total < 32 ? total : 32;
+    for (int i = 0; i < nlanes; ++i) all[i] = slots[i];
+    b->warps[warp]->arrive_and_wait();            // gathers read every slot: nobody may overwrite before all have read
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+    uint32_t all[32]; int n;
+    tss_emu_warp_gather(pred ? 1u : 0u, all, n);
+    unsigned r = 0;
+    for (int i = 0; i < n; ++i) r |= (all[i] ? 1u : 0u) << i;
+    return r;
+}
+inline unsigned __match_any_sync(unsigned, int v) {
+    uint32_t all[32]; int n;
+    tss_emu_warp_gather((uint32_t)v, all, n);
+    unsigned r = 0;
+    for (int i = 0; i < n; ++i) r |= (all[i] == (uint32_t)v ? 1u : 0u) << i;
+    return r;
+}
+inline unsigned __match_all_sync(unsigned, int v, int* pred) {
+    uint32_t all[32]; int n;
+    tss_emu_warp_gather((uint32_t)v, all, n);
+    bool same = true;
+    for (int i = 0; i < n; ++i) same = same && all[i] == (uint32_t)v;
+    *pred = same ? 1 : 0;
+    return same ? (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) : 0u;
+}
+inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return std::atomic_ref<unsigned long long>(*p).fetch_add(v); }
 
 template <typename V> inline V __ldg(const V* p) { return *p; }
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }

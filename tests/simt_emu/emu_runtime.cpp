@@ -5,6 +5,7 @@
 
 namespace tss_emu {
 thread_local Block* block = nullptr;
+thread_local unsigned slot_parity = 0;
 alignas(1024) unsigned char dyn_smem[256 * 1024];
 }  // namespace tss_emu
 thread_local uint3 threadIdx, blockIdx;

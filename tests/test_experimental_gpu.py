@@ -10,6 +10,7 @@ unvalidated kernel can never hang the default GPU suite.
 * the same for the stride-1 depthwise layers (csrc/dwconv_bwd_fused.cu; TSS_FUSE_BNAPPLY_DW=1);
 * BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu; TSS_FUSE_BNFIN=1);
 * the stem convolution and its weight gradient on tcgen05 (csrc/stem_tc.cu; TSS_STEM_TC=1);
+* the warp-private confusion-matrix kernel (csrc/metrics.cu; TSS_CM_VARIANT=1);
 * the device input pipeline (csrc/augment.cu; its per-pixel arithmetic is already pinned on the host by
   tests/test_data_cpu.py, the launch itself is what remains to be run)."""
 import os
@@ -364,3 +365,25 @@ def test_dw_backward_with_bn_apply_matches_the_two_kernel_path(C, N, H, W, relu,
     tol = 1e-5 if dtype == torch.float32 else 6e-3
     assert rel(dy2, dy1) < tol and rel(g2, g1) < 2 * tol
     assert rel(dga2, dga1) < 1e-6 and rel(dbe2, dbe1) < 1e-6 and rel(ps2, ps1) < max(tol, 2e-3)
+
+
+@pytest.mark.parametrize('kind', ['random', 'piecewise'])
+def test_warp_private_confusion_matrix_is_exact(kind, monkeypatch):
+    import numpy as np
+    from oracle import confusion as o_cm
+    monkeypatch.setenv('TSS_CM_VARIANT', '1')
+    g = torch.Generator().manual_seed(11)
+    n = 1024 * 2048 + 3
+    if kind == 'piecewise':
+        pred = torch.randint(0, 19, (n // 97 + 1,), generator=g).repeat_interleave(97)[:n]
+        label = torch.randint(0, 19, (n // 211 + 1,), generator=g).repeat_interleave(211)[:n]
+    else:
+        pred, label = torch.randint(0, 19, (n,), generator=g), torch.randint(0, 19, (n,), generator=g)
+    label = label.clone()
+    label[torch.rand(n, generator=g) < 0.1] = 255
+    cm = torch.zeros(19, 19, dtype=torch.int64, device='cuda')
+    for _ in range(3):                                     # accumulates
+        _lib.backend().call('tss_confusion_from_labels', dict(pred=pred.cuda(), target=label.cuda(), n=n, C=19, cm=cm))
+    torch.cuda.synchronize()
+    want = 3 * o_cm.confusion_matrix(pred.numpy(), label.numpy(), 19)
+    assert np.array_equal(cm.cpu().numpy(), want)

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, 'torch_semantic_segmentation_b200', 'csrc')
 EMU = os.path.join(ROOT, 'tests', 'simt_emu')
 SOURCES = ['ppm.cu', 'augment.cu', 'dwconv_bnred.cu',        # dwconv_bnred.cu: the stride-2 (plain SIMT) kernel only
-           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu', 'dwconv_bwd_fused.cu',
+           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu', 'dwconv_bwd_fused.cu', 'metrics.cu',
            'pwconv_tc_bnred.cu', 'dwconv.cu', 'dwconv_tma.cu']       # validated on the B200: calibrate the emulation itself                               # on the functional tcgen05/TMA/mbarrier emulation
 
 
@@ -416,3 +416,25 @@ def test_depthwise_backward_with_bn_apply_on_the_emulation(emulated, C, N, H, W,
     assert rel(e[1], r[1]) < 2 * tol, ('g', rel(e[1], r[1]))
     assert rel(e[2], r[2]) < 1e-6 and rel(e[3], r[3]) < 1e-6
     assert rel(e[4], r[4]) < max(tol, 2e-3), ('psums', rel(e[4], r[4]))
+
+
+@pytest.mark.parametrize('variant', ['0', '1'])
+@pytest.mark.parametrize('kind', ['random', 'piecewise', 'odd'])
+def test_confusion_matrix_kernels_on_the_simt_emulation(emulated, monkeypatch, variant, kind):
+    """csrc/metrics.cu: the default kernel (validated on the B200; calibrates the warp-vote emulation) and the
+    warp-private variant (TSS_CM_VARIANT=1, not yet run on the GPU) are exact against the oracle's bincount."""
+    from oracle import confusion as o_cm
+    monkeypatch.setenv('TSS_CM_VARIANT', variant)
+    g = torch.Generator().manual_seed(5)
+    n = 4099 if kind == 'odd' else 8192
+    if kind == 'piecewise':
+        pred = torch.randint(0, 19, (n // 64,), generator=g).repeat_interleave(64)
+        label = torch.randint(0, 19, (n // 128,), generator=g).repeat_interleave(128)
+    else:
+        pred, label = torch.randint(0, 19, (n,), generator=g), torch.randint(0, 19, (n,), generator=g)
+    label = label.clone()
+    label[torch.rand(n, generator=g) < 0.1] = 255
+    cm = torch.zeros(19, 19, dtype=torch.int64)
+    emulated.call('tss_confusion_from_labels', dict(pred=pred, target=label, n=n, C=19, cm=cm))
+    want = o_cm.confusion_matrix(pred.numpy(), label.numpy(), 19)
+    assert (cm.numpy() == want).all() and int(cm.sum()) == int((label != 255).sum())

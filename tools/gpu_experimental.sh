@@ -14,3 +14,15 @@ for arm in "base" "TSS_FUSE_BNRED_EXT=1" "TSS_FUSE_BNAPPLY=1" "TSS_FUSE_PPM=1" "
     env $envs timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_${TAG}_${name}.json 2> gpurun_out/ab_${TAG}_${name}.err
     echo "$arm rc=$? $(python -c "import json,sys; d=json.loads(open('gpurun_out/ab_${TAG}_${name}.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'], d['gpu_launches'])" 2>&1 | tail -1)"
 done
+# confusion matrix over 500 random maps (BASELINE.json configs[3]): default kernel vs the warp-private variant
+for v in 0 1; do
+    TSS_CM_VARIANT=$v timeout 300 python tools/bench_configs.py --config 4 > gpurun_out/cm_${TAG}_variant$v.json 2> gpurun_out/cm_${TAG}_variant$v.err
+    echo "TSS_CM_VARIANT=$v rc=$? $(tail -1 gpurun_out/cm_${TAG}_variant$v.json | cut -c1-300)"
+done
+# inference batch sweep with the grouped pyramid path and the tensor-core stem
+for arm in "base" "TSS_FUSE_PPM=1 TSS_STEM_TC=1"; do
+    name=$(echo "$arm" | tr ' =' '__')
+    if [ "$arm" = "base" ]; then envs=""; else envs="$arm"; fi
+    env $envs timeout 300 python tools/bench_configs.py --config 5 --batches 1,16 > gpurun_out/inf_${TAG}_${name}.json 2> gpurun_out/inf_${TAG}_${name}.err
+    echo "inference $arm rc=$? $(tail -1 gpurun_out/inf_${TAG}_${name}.json | cut -c1-300)"
+done

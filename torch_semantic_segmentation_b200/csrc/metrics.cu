@@ -3,6 +3,8 @@
 // __match_any_sync so that one shared atomic carries the whole group (semantic maps are
 // piecewise constant, so whole warps usually collapse to one or two atomics); one global
 // 64-bit atomic per non-empty bin per CTA at the end.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -126,6 +128,68 @@ cm_logits_kernel(const T* __restrict__ logits, const int64_t* __restrict__ targe
     flush_hist(s_hist, C * C, cm);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Variant for maps WITHOUT spatial coherence (the 500-map benchmark of BASELINE.json draws every pixel at random):
+// __match_any_sync loops over the distinct keys of the warp, ~30 of them per call there.  Here each warp owns a
+// private histogram in shared memory; a warp whose lanes all agree (the common case on real label maps, one
+// __match_all_sync) still issues a single atomic, any other warp lets every lane add to its own bin -- the
+// shared-memory atomic unit resolves the few same-bin lanes.  Selected with TSS_CM_VARIANT=1 (launcher below).
+__device__ __forceinline__ void warp_private_inc(unsigned int* s_warp_hist, int bin, bool active) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned ballot = __ballot_sync(0xffffffffu, active);
+    if (ballot == 0u) return;
+    int uniform = 0;
+    __match_all_sync(0xffffffffu, active ? bin : -1, &uniform);
+    if (uniform) {                                        // every lane active with the same bin
+        if (lane == 0) atomicAdd(&s_warp_hist[bin], 32u);
+    } else if (active) {
+        atomicAdd(&s_warp_hist[bin], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+cm_labels_private_kernel(const int64_t* __restrict__ pred, const int64_t* __restrict__ target, int64_t n, int C,
+                         unsigned long long* __restrict__ cm) {
+    TSS_DYN_SMEM(unsigned int, s_hist);                   // [warps][C*C]
+    pdl_wait();
+    const int bins = C * C;
+    for (int i = threadIdx.x; i < (kThreads / 32) * bins; i += kThreads) s_hist[i] = 0;
+    __syncthreads();
+    unsigned int* mine = s_hist + (threadIdx.x >> 5) * bins;
+    const int64_t n2 = n >> 1;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    const int64_t iters = (n2 + stride - 1) / stride;     // warp-uniform trip count: the warp votes stay convergent
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    for (int64_t it = 0; it < iters; ++it, i += stride) {
+        const bool in = i < n2;
+        longlong2 p = make_longlong2(0, -1), t = make_longlong2(-1, -1);
+        if (in) {
+            p = __ldg(reinterpret_cast<const longlong2*>(pred) + i);
+            t = __ldg(reinterpret_cast<const longlong2*>(target) + i);
+        }
+        const bool a0 = in && t.x >= 0 && t.x < C && p.x >= 0 && p.x < C;
+        const bool a1 = in && t.y >= 0 && t.y < C && p.y >= 0 && p.y < C;
+        warp_private_inc(mine, a0 ? (int)(t.x * C + p.x) : 0, a0);
+        warp_private_inc(mine, a1 ? (int)(t.y * C + p.y) : 0, a1);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t t = target[n - 1], p = pred[n - 1];
+        if (t >= 0 && t < C && p >= 0 && p < C) atomicAdd(&mine[t * C + p], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins; b += kThreads) {
+        unsigned long long v = 0;
+        for (int w = 0; w < kThreads / 32; ++w) v += s_hist[w * bins + b];
+        if (v) atomicAdd(cm + b, v);
+    }
+}
+
+static int cm_variant() {                                // read per launch: a test can switch it inside one process
+    const char* e = getenv("TSS_CM_VARIANT");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+}
+
 inline int cm_grid(int64_t items) {
     int64_t want = ceil_div64(items, kThreads * 4);
     int64_t cap = (int64_t)tss_num_sms() * 8;
@@ -141,6 +205,12 @@ extern "C" int tss_confusion_from_labels(const int64_t* pred, const int64_t* tar
     TSS_REQUIRE(C > 0 && C <= kMaxC, "confusion_from_labels: C=%d (max %d)", C, kMaxC);
     if (n == 0) return TSS_OK;
     TSS_REQUIRE((((uintptr_t)pred | (uintptr_t)target) & 15) == 0, "confusion_from_labels: maps must be 16-byte aligned");
+    if (cm_variant() == 1) {
+        tss_launch(cm_labels_private_kernel, cm_grid(n / 2 + 1), kThreads, (size_t)(kThreads / 32) * C * C * sizeof(unsigned int),
+                   (cudaStream_t)stream, pred, target, n, C, (unsigned long long*)cm);
+        TSS_LAUNCH_CHECK("confusion_from_labels(private)");
+        return TSS_OK;
+    }
     tss_launch(cm_labels_kernel, cm_grid(n / 2 + 1), kThreads, 0, (cudaStream_t)stream, pred, target, n, C,
                                                                                (unsigned long long*)cm);
     TSS_LAUNCH_CHECK("confusion_from_labels");
