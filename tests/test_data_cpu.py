@@ -91,6 +91,11 @@ def test_eval_transform_and_trainer_on_transformed_batches(fake_backend):
     t = DeviceTransform(crop=(64, 96), scale_limit=(0.5, 2.0), seed=1)
     state = trainer.run(list(t.batches([(images, labels)] * 2, 'cpu')), max_epochs=1)
     assert state.iteration == 2 and np.isfinite(state.output)
+    # the same through the trainer's own hook: the loader yields the decoded uint8 batch
+    trainer = create_segmentation_trainer(model, opt, CrossEntropyLoss(ignore_index=255), 'cpu', logging=False,
+                                          transform=DeviceTransform(crop=(64, 96), scale_limit=(0.5, 2.0), seed=1))
+    state = trainer.run([(images, labels)] * 2, max_epochs=1)
+    assert state.iteration == 2 and np.isfinite(state.output)
 
 
 def test_kernel_arithmetic_compiled_for_the_host_matches_opencv(tmp_path):

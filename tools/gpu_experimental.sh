@@ -26,3 +26,6 @@ for arm in "base" "TSS_FUSE_PPM=1 TSS_STEM_TC=1"; do
     env $envs timeout 300 python tools/bench_configs.py --config 5 --batches 1,16 > gpurun_out/inf_${TAG}_${name}.json 2> gpurun_out/inf_${TAG}_${name}.err
     echo "inference $arm rc=$? $(tail -1 gpurun_out/inf_${TAG}_${name}.json | cut -c1-300)"
 done
+# end-to-end leg fed with uint8 frames (device input pipeline in front of the graphed step)
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-uint8 > gpurun_out/ab_${TAG}_e2e_uint8.json 2> gpurun_out/ab_${TAG}_e2e_uint8.err
+echo "e2e-uint8 rc=$? $(python -c "import json; d=json.loads(open('gpurun_out/ab_${TAG}_e2e_uint8.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['e2e'])" 2>&1 | tail -1)"

@@ -83,28 +83,53 @@ class DeviceTransform:
         return rows
 
     # ------------------------------------------------------------------ the transform
-    def __call__(self, images, label_ids=None, draws=None):
-        if images.dim() != 4 or images.shape[3] != 3:
-            raise ValueError('images: uint8 (N, H, W, 3) expected, got %s' % (tuple(images.shape),))
+    def output_size(self, H, W):
+        """(height, width) of the transformed batch for frames of H x W (needs a crop or no scaling)."""
+        if self.crop is not None:
+            return self.crop
+        if self.scale_limit is not None:
+            raise ValueError('without a crop every sample of the batch needs the same scale')
+        return (H, W)
+
+    def draw_geometry(self, N, H, W, draws=None):
+        """The random draws of one batch as the kernel's (N,5) int32 table (host tensor, pinned on CUDA builds)."""
+        rows = self.geometry(self.draw(N) if draws is None else draws, H, W)
+        if self.crop is None and len({(r[0], r[1]) for r in rows}) != 1:
+            raise ValueError('without a crop every sample of the batch needs the same scale')
+        geom = torch.tensor(rows, dtype=torch.int32)
+        return geom.pin_memory() if torch.cuda.is_available() else geom
+
+    def apply(self, images, label_ids, geom):
+        """Run the kernel with a geometry table that already is on the device (CUDA-graph friendly: the table can be
+        a static buffer refreshed before every replay)."""
         N, H, W, _ = images.shape
-        if draws is None:
-            draws = self.draw(N)
-        rows = self.geometry(draws, H, W)
         crop = self.crop
         if crop is None:
-            sizes = {(r[0], r[1]) for r in rows}
-            if len(sizes) != 1:
+            if self.scale_limit is not None:
                 raise ValueError('without a crop every sample of the batch needs the same scale')
-            crop = next(iter(sizes))
+            crop = (H, W)
         dev = images.device
-        geom = torch.tensor(rows, dtype=torch.int32)
-        if dev.type == 'cuda':
-            geom = geom.pin_memory().to(dev, non_blocking=True)
         lut = self._lut.get(dev)
         if lut is None:
             lut = self._lut[dev] = self._table.to(dev)
         return ops.augment_batch(images.contiguous(), label_ids.contiguous() if label_ids is not None else None,
                                  geom, lut, self.norm, crop)
+
+    def __call__(self, images, label_ids=None, draws=None):
+        if images.dim() != 4 or images.shape[3] != 3:
+            raise ValueError('images: uint8 (N, H, W, 3) expected, got %s' % (tuple(images.shape),))
+        N, H, W, _ = images.shape
+        geom = self.draw_geometry(N, H, W, draws)
+        crop = self.crop if self.crop is not None else (int(geom[0, 0]), int(geom[0, 1]))
+        geom = geom.to(images.device, non_blocking=True)
+        if self.crop is None and crop != (H, W):
+            # a common scale for the whole batch without a crop: the output is the scaled frame
+            keep, self.crop = self.crop, crop
+            try:
+                return self.apply(images, label_ids, geom)
+            finally:
+                self.crop = keep
+        return self.apply(images, label_ids, geom)
 
     def batches(self, loader, device):
         """Wrap a loader of decoded ``(images_u8, label_ids_u8)`` batches: yields transformed device batches, the

@@ -216,17 +216,24 @@ class GraphedTrainStep:
     one graph launch, which is what a 1.1 M-parameter net needs to stay GPU-bound.  The batch is
     copied straight from (pinned) host memory into the graph's static input buffers."""
 
-    def __init__(self, model, optimizer, loss_fn, x, y, warmup=3):
+    def __init__(self, model, optimizer, loss_fn, x, y, warmup=3, transform=None):
         dev = x.device
         self.x = torch.empty_like(x)
         self.y = torch.empty_like(y)
         self.x.copy_(x)
         self.y.copy_(y)
         self.key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype)
+        # device-side input pipeline (data.DeviceTransform): the graph's inputs are the decoded uint8 frames; the
+        # random draws of a step live in a small static table that is refreshed before every replay
+        self.transform = transform
+        self.geom = None
+        if transform is not None:
+            self.geom = transform.draw_geometry(x.shape[0], x.shape[1], x.shape[2]).to(dev)
 
         def body():
             optimizer.zero_grad()
-            loss = loss_fn(model(self.x), self.y)
+            xs, ys = (self.x, self.y) if transform is None else transform.apply(self.x, self.y, self.geom)
+            loss = loss_fn(model(xs), ys)
             with unit_loss_grad():
                 loss.backward()
             optimizer.step()
@@ -253,6 +260,8 @@ class GraphedTrainStep:
     def __call__(self, x, y, non_blocking=True):
         self.x.copy_(x, non_blocking=non_blocking)
         self.y.copy_(y, non_blocking=non_blocking)
+        if self.transform is not None:
+            self.geom.copy_(self.transform.draw_geometry(x.shape[0], x.shape[1], x.shape[2]), non_blocking=non_blocking)
         self.graph.replay()
         return self.loss
 
@@ -302,14 +311,16 @@ class GraphedEvalStep:
 
 # ------------------------------------------------------------------ the two factories -------
 def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False, logging=True,
-                                non_blocking=True, cuda_graph=False, prefetch=True):
+                                non_blocking=True, cuda_graph=False, prefetch=True, transform=None):
     """reference: engine.py:22-56.  ``cuda_graph=True`` (an addition) replays the step as one
     CUDA graph; it needs fixed batch shapes and a capturable optimizer (``optim.FlatAdamW`` or
     ``torch.optim.AdamW(capturable=True)``).  The first batch is used for warm-up and capture
     (its optimisation steps are real steps).  ``prefetch=True`` (an addition) issues the host->device
     copy of batch i+1 on a copy stream before the step on batch i is launched, so the copy (141 MB per
     step of 12 x 768 x 768 fp32 images + int64 labels) overlaps with compute; ``engine.py:27`` copies
-    synchronously in front of every step."""
+    synchronously in front of every step.  ``transform`` (an addition): a ``data.DeviceTransform``; the loader then
+    yields decoded uint8 frames and label ids ((N,H,W,3), (N,H,W)) and scale / crop / flip / normalise / label
+    mapping run on the device in front of the model (scripts/train_fastscnn.py:62-72 does them in the workers)."""
     if use_f16 and hasattr(model, 'set_compute_dtype'):
         model.set_compute_dtype(torch.bfloat16)
     graphed = {}
@@ -328,7 +339,7 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
             g = graphed.get('step')
             if g is None:
                 xd, yd = fetch(batch)
-                graphed['step'] = g = GraphedTrainStep(model, optimizer, loss_fn, xd, yd)
+                graphed['step'] = g = GraphedTrainStep(model, optimizer, loss_fn, xd, yd, transform=transform)
                 if staged is not None:
                     stager.release(staged)
                 return g.loss.item()
@@ -342,6 +353,8 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
             return loss.item()
         optimizer.zero_grad()
         x, y = fetch(batch)
+        if transform is not None:
+            x, y = transform(x, y)
 
         y_pred = model(x)
         loss = loss_fn(y_pred, y)
