@@ -295,7 +295,7 @@ def main():
     from torch_semantic_segmentation_b200 import _lib
     from torch_semantic_segmentation_b200.distributed import GradientAllReducer, broadcast_parameters
     from torch_semantic_segmentation_b200.engine import GraphedTrainStep, create_segmentation_trainer
-    from torch_semantic_segmentation_b200.functional import unit_loss_grad
+    from torch_semantic_segmentation_b200.functional import enable_deferred_logits as Fn_enable_deferred, unit_loss_grad
     from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
     from torch_semantic_segmentation_b200.models import fastscnn
     from torch_semantic_segmentation_b200.optim import FlatAdamW
@@ -325,6 +325,7 @@ def main():
         opt.step()
         return loss.detach()
 
+    Fn_enable_deferred(model, loss_fn)                # gated (TSS_DEFER_LOGITS=1): no full-resolution logits in training
     if use_graph:
         graphed = GraphedTrainStep(model, opt, loss_fn, x, y)      # static inputs = the resident batch
 

@@ -11,6 +11,7 @@ unvalidated kernel can never hang the default GPU suite.
 * BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu; TSS_FUSE_BNFIN=1);
 * the stem convolution and its weight gradient on tcgen05 (csrc/stem_tc.cu; TSS_STEM_TC=1);
 * the warp-private confusion-matrix kernel (csrc/metrics.cu; TSS_CM_VARIANT=1);
+* deferred logits (TSS_DEFER_LOGITS=1: host-side only, existing kernels);
 * the device input pipeline (csrc/augment.cu; its per-pixel arithmetic is already pinned on the host by
   tests/test_data_cpu.py, the launch itself is what remains to be run)."""
 import os
@@ -387,3 +388,32 @@ def test_warp_private_confusion_matrix_is_exact(kind, monkeypatch):
     torch.cuda.synchronize()
     want = 3 * o_cm.confusion_matrix(pred.numpy(), label.numpy(), 19)
     assert np.array_equal(cm.cpu().numpy(), want)
+
+
+def test_deferred_logits_training_step_matches_default():
+    from oracle.golden_inputs import train_batch
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+    x, y = train_batch('fastscnn')
+    loss_fn = CrossEntropyLoss(ignore_index=255)
+    keep = Fn.DEFER_LOGITS
+    out = {}
+    try:
+        for flag in (False, True):
+            Fn.DEFER_LOGITS = flag
+            torch.manual_seed(0)
+            model = fastscnn(3, 19).cuda().set_compute_dtype(torch.bfloat16).train()
+            for m in model.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+            assert Fn.enable_deferred_logits(model, loss_fn) == flag
+            before = _lib.launch_count()
+            loss = loss_fn(model(x.cuda()), y.cuda())
+            loss.backward()
+            torch.cuda.synchronize()
+            out[flag] = (float(loss), model.classifier[3].weight.grad.clone(), _lib.launch_count() - before)
+    finally:
+        Fn.DEFER_LOGITS = keep
+    assert out[True][0] == out[False][0] and rel(out[True][1], out[False][1]) < 1e-6
+    assert out[True][2] == out[False][2] - 1

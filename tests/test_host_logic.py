@@ -367,3 +367,50 @@ def test_all_gates_together_train_and_eval(fake_backend, arch):
         assert abs(a - b) < 5e-3 * abs(b), (runs[True][0], runs[False][0])
     assert rel(runs[True][1], runs[False][1]) < 6e-2
     assert runs[True][2] < runs[False][2] - 100
+
+
+@pytest.mark.parametrize('loss_name', ['ce', 'ohem'])
+def test_deferred_logits_give_the_same_step_without_the_upsampling(fake_backend, loss_name):
+    """functional.DEFER_LOGITS (off by default): in training the model hands the fused head its 1/8 scores directly;
+    same loss and gradients, one full-resolution up-sampling (and its 269 MB at the benchmark shape) less."""
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.losses import OHEMLoss
+    calls = {}
+    inner = fake_backend.call
+
+    def counting(name, kwargs):
+        calls[name] = calls.get(name, 0) + 1
+        return inner(name, kwargs)
+    fake_backend.call = counting
+    x, y = train_batch('fastscnn')
+    loss_fn = CrossEntropyLoss(ignore_index=255) if loss_name == 'ce' else OHEMLoss(ignore_index=255)
+    keep = Fn.DEFER_LOGITS
+    runs = {}
+    try:
+        for flag in (False, True):
+            Fn.DEFER_LOGITS = flag
+            calls.clear()
+            torch.manual_seed(0)
+            model = _no_dropout(fastscnn(3, 19)).train()
+            assert Fn.enable_deferred_logits(model, loss_fn) == flag
+            out = model(x)
+            assert isinstance(out, Fn.DeferredLogits) == flag and tuple(out.shape) == (x.shape[0], 19, x.shape[2], x.shape[3])
+            loss = loss_fn(out, y)
+            loss.backward()
+            runs[flag] = (float(loss.detach()), torch.cat([p.grad.reshape(-1) for p in model.parameters()]), dict(calls))
+            if flag:
+                full = out.materialize()                    # anything else can still have the tensor
+                assert tuple(full.shape) == tuple(out.shape)
+                with torch.no_grad():
+                    assert not isinstance(model.eval()(x), Fn.DeferredLogits)      # eval mode always materialises
+    finally:
+        Fn.DEFER_LOGITS = keep
+    assert runs[True][0] == runs[False][0] and rel(runs[True][1], runs[False][1]) < 1e-7
+    assert runs[False][2].get('tss_upsample_logits_fwd') == 1 and 'tss_upsample_logits_fwd' not in runs[True][2]
+    # a loss that cannot take the handle leaves the model alone
+    model = fastscnn(3, 19)
+    Fn.DEFER_LOGITS = True
+    try:
+        assert Fn.enable_deferred_logits(model, torch.nn.CrossEntropyLoss()) is False and model.defer_logits is False
+    finally:
+        Fn.DEFER_LOGITS = keep

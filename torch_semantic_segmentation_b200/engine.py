@@ -15,6 +15,7 @@ pytorch-ignite and NVIDIA apex, neither of which this path needs:
 import torch
 
 from . import metrics as M
+from . import functional as Fn
 from .functional import unit_loss_grad
 
 __all__ = ['create_segmentation_trainer', 'create_segmentation_evaluator', 'Engine', 'Events', 'State']
@@ -323,6 +324,7 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
     mapping run on the device in front of the model (scripts/train_fastscnn.py:62-72 does them in the workers)."""
     if use_f16 and hasattr(model, 'set_compute_dtype'):
         model.set_compute_dtype(torch.bfloat16)
+    Fn.enable_deferred_logits(model, loss_fn)     # nobody but loss_fn sees y_pred inside update_fn
     graphed = {}
     stager = _BatchStager(device, non_blocking) if (prefetch and torch.device(device).type == 'cuda') else None
 

@@ -630,8 +630,53 @@ def attach_head(logits, scores):
     return logits
 
 
+# Training with this package's losses: the full-resolution logits (269 MB of bf16 per 12 x 768 x 768 step) are only
+# ever consumed by the fused head, which works from the 1/8 class scores.  With defer_logits set on the model (the
+# trainer does it when the loss declares ``accepts_deferred_logits``, and only under TSS_DEFER_LOGITS=1 until the
+# path has run on a B200) the training forward returns this handle instead of launching the x8 up-sampling;
+# anything else that wants the tensor calls ``materialize()``.
+DEFER_LOGITS = os.environ.get('TSS_DEFER_LOGITS', '0') == '1'
+
+
+class DeferredLogits:
+    """(N, C, 8h, 8w) logits that have not been interpolated from their (N, C, h, w) NHWC ``scores`` yet."""
+
+    __slots__ = ('scores', 'height', 'width')
+
+    def __init__(self, scores, height, width):
+        self.scores, self.height, self.width = scores, height, width
+
+    @property
+    def shape(self):
+        return torch.Size((self.scores.shape[0], self.scores.shape[1], self.height, self.width))
+
+    def dim(self):
+        return 4
+
+    def materialize(self):
+        return attach_head(UpsampleLogits.apply(self.scores, self.height, self.width), self.scores)
+
+
+def model_output(module, scores, height, width):
+    """What a model's forward returns for the class scores: the up-sampled logits, or the deferred handle in
+    training mode when the module opted in."""
+    if module.training and getattr(module, 'defer_logits', False) and torch.is_grad_enabled():
+        return DeferredLogits(scores, height, width)
+    return attach_head(UpsampleLogits.apply(scores, height, width), scores)
+
+
+def enable_deferred_logits(model, loss_fn):
+    """Trainer / bench hook: switch the model to deferred logits iff the gate is on and the loss can take them."""
+    on = bool(DEFER_LOGITS and getattr(loss_fn, 'accepts_deferred_logits', False) and hasattr(model, 'defer_logits'))
+    if hasattr(model, 'defer_logits'):
+        model.defer_logits = on
+    return on
+
+
 def fused_head_source(logits):
     """-> the NHWC scores ``logits`` was up-sampled from, if it is still the untouched model output."""
+    if isinstance(logits, DeferredLogits):
+        return logits.scores
     head = getattr(logits, '_tss_head', None)
     if head is None or head[1] != logits._version:
         return None

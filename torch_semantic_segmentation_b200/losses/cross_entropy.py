@@ -19,6 +19,9 @@ __all__ = ['CrossEntropyLoss', 'cross_entropy']
 
 
 def cross_entropy(input, target, ignore_index=-100, reduction='mean', fused_head=True):
+    if isinstance(input, Fn.DeferredLogits) and not (reduction == 'mean' and fused_head
+                                                     and input.scores.shape[1] in (11, 12, 19, 21)):
+        input = input.materialize()          # this call needs the real tensor
     if input.dim() != 4 or target.dim() != 3:
         raise ValueError('cross_entropy expects (N,C,H,W) logits and (N,H,W) targets')
     if reduction == 'mean':
@@ -36,6 +39,7 @@ def cross_entropy(input, target, ignore_index=-100, reduction='mean', fused_head
 
 
 class CrossEntropyLoss(nn.Module):
+    accepts_deferred_logits = True       # functional.DeferredLogits
 
     def __init__(self, ignore_index=-100, reduction='mean', fused_head=True):
         super().__init__()

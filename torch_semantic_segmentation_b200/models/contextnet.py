@@ -111,6 +111,7 @@ class ContextNet(nn.Module):
         )
         self.feature_fusion = FeatureFusionModule((128, 128), 128)
         self.classifier = Classifier(128, out_channels)
+        self.defer_logits = False        # functional.DeferredLogits in training mode (set by the trainer)
 
     def set_compute_dtype(self, dtype, pw_impl=None):
         """float32 (verification mode, default) or bfloat16 (tcgen05 pointwise convolutions)."""
@@ -132,5 +133,4 @@ class ContextNet(nn.Module):
         fusion = self.feature_fusion(context, spatial)
         classes = self.classifier(fusion)
         classes = ops.as_nhwc(classes)
-        logits = Fn.UpsampleLogits.apply(classes, classes.shape[2] * 8, classes.shape[3] * 8)
-        return Fn.attach_head(logits, classes)
+        return Fn.model_output(self, classes, classes.shape[2] * 8, classes.shape[3] * 8)

@@ -45,6 +45,7 @@ class FastSCNN(nn.Module):
         )
         self.fusion = FeatureFusionModule((128, 64), 128, scale_factor=4)
         self.classifier = Classifier(128, out_channels)
+        self.defer_logits = False        # functional.DeferredLogits in training mode (set by the trainer, see there)
 
     def set_compute_dtype(self, dtype, pw_impl=None):
         """float32 (verification mode, default) or bfloat16 (the B200 production path: pointwise
@@ -65,8 +66,7 @@ class FastSCNN(nn.Module):
         fusion = self.fusion(features, downsample)
         classes = self.classifier(fusion)
         classes = ops.as_nhwc(classes)
-        logits = Fn.UpsampleLogits.apply(classes, classes.shape[2] * 8, classes.shape[3] * 8)
-        return Fn.attach_head(logits, classes)
+        return Fn.model_output(self, classes, classes.shape[2] * 8, classes.shape[3] * 8)
 
 
 class FeatureFusionModule(nn.Module):
