@@ -340,6 +340,15 @@ int tss_confusion_from_logits(const void* logits, const int64_t* target, int N, 
 int tss_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float* hyper,
                    float grad_scale, void* stream);
 
+/* ---- dropout -------------------------------------------------------------------------------------------
+ * nn.Dropout(p) (fastscnn.py:96, contextnet.py:84) on a dense tensor of n elements (n % 8 == 0) without a mask
+ * tensor: y = x * keep / (1 - p) with keep from Philox4x32-10 keyed by (seed, offset, element group).
+ * rng: DEVICE int64[3] = {seed, offset, ticket (0)}; the forward kernel stores the offset it used in used[0] and
+ * advances rng[1] (CUDA-graph replays draw fresh masks); the backward kernel regenerates the mask from
+ * (rng[0], used[0]): dx = dy * keep / (1 - p). */
+int tss_dropout_fwd(const void* x, void* y, int64_t n, float p, int64_t* rng, int64_t* used, int dtype, void* stream);
+int tss_dropout_bwd(const void* dy, void* dx, int64_t n, float p, int64_t* rng, int64_t* used, int dtype, void* stream);
+
 /* ---- pyramid pooling branches, grouped (training) ------------------------------------------------------
  * PyramidPoolingModule (fastscnn.py:101-123): nbins x [AdaptiveAvgPool2d(b) -> Conv2d(C, Cb, 1) -> BatchNorm2d ->
  * ReLU] -> bilinear (align_corners=True) -> cat([x, branches]).  pool = the output of tss_adaptive_pool_fwd:

@@ -167,6 +167,24 @@ class FakeBackend:
             dst.copy_(src.detach().reshape(Cout, Cin, 9).permute(0, 2, 1).reshape(Cout, 9 * Cin, 1, 1))
         return 0
 
+    # ---------------------------------------------------------------- dropout
+    def _dropout(self, x, y, n, p, seed, offset):
+        from tests.philox_ref import keep_mask
+        keep, scale = keep_mask(int(seed), int(offset), n, p)
+        flat = x.permute(0, 2, 3, 1).reshape(-1).float()              # NHWC element order
+        out = torch.where(torch.from_numpy(keep), flat * float(scale), torch.zeros_like(flat))
+        y.copy_(out.view(x.shape[0], x.shape[2], x.shape[3], x.shape[1]).permute(0, 3, 1, 2))
+        return 0
+
+    def tss_dropout_fwd(self, x, y, n, p, rng, used, dtype):
+        assert int(rng[2]) == 0
+        used[0] = rng[1]
+        rng[1] += 1
+        return self._dropout(x, y, n, p, rng[0], used[0])
+
+    def tss_dropout_bwd(self, dy, dx, n, p, rng, used, dtype):
+        return self._dropout(dy, dx, n, p, rng[0], used[0])
+
     # ---------------------------------------------------------------- pyramid pooling, grouped
     @staticmethod
     def _at(addr, n, dtype=torch.float32):

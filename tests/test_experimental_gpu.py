@@ -11,6 +11,7 @@ unvalidated kernel can never hang the default GPU suite.
 * BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu; TSS_FUSE_BNFIN=1);
 * the stem convolution and its weight gradient on tcgen05 (csrc/stem_tc.cu; TSS_STEM_TC=1);
 * the warp-private confusion-matrix kernel (csrc/metrics.cu; TSS_CM_VARIANT=1);
+* the library's own dropout kernel (csrc/dropout.cu; TSS_OWN_DROPOUT=1);
 * deferred logits (TSS_DEFER_LOGITS=1: host-side only, existing kernels);
 * the device input pipeline (csrc/augment.cu; its per-pixel arithmetic is already pinned on the host by
   tests/test_data_cpu.py, the launch itself is what remains to be run)."""
@@ -417,3 +418,22 @@ def test_deferred_logits_training_step_matches_default():
         Fn.DEFER_LOGITS = keep
     assert out[True][0] == out[False][0] and rel(out[True][1], out[False][1]) < 1e-6
     assert out[True][2] == out[False][2] - 1
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+def test_own_dropout_matches_the_philox_reference(dtype):
+    from tests.philox_ref import keep_mask
+    from torch_semantic_segmentation_b200 import ops
+    N, C, H, W, p = 3, 128, 96, 96, 0.1
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, H, W, C, generator=g).to(dtype).cuda().permute(0, 3, 1, 2)
+    rng = ops.rng_state('cuda', seed=987654321)
+    for step in range(2):
+        y, used = ops.dropout_fwd(x, p)
+        dx = ops.dropout_bwd(x, p, used)
+        torch.cuda.synchronize()
+        assert int(used) == step and int(rng[1]) == step + 1 and int(rng[2]) == 0
+        keep, scale = keep_mask(987654321, step, x.numel(), p)
+        keep = torch.from_numpy(keep).view(N, H, W, C).permute(0, 3, 1, 2).cuda()
+        want = torch.where(keep, x.float() * float(scale), torch.zeros((), device='cuda')).to(dtype)
+        assert torch.equal(y, want) and torch.equal(dx, want)

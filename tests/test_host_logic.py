@@ -414,3 +414,36 @@ def test_deferred_logits_give_the_same_step_without_the_upsampling(fake_backend,
         assert Fn.enable_deferred_logits(model, torch.nn.CrossEntropyLoss()) is False and model.defer_logits is False
     finally:
         Fn.DEFER_LOGITS = keep
+
+
+def test_own_dropout_gate(fake_backend):
+    """functional.OWN_DROPOUT (off by default): the classifier's nn.Dropout(0.1) on the library kernel -- inverted
+    dropout whose backward regenerates the forward's mask; a fresh mask per step; eval mode and p = 0 untouched."""
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.nn.blocks import Dropout
+    keep = Fn.OWN_DROPOUT
+    Fn.OWN_DROPOUT = True
+    try:
+        ops.rng_state('cpu', seed=1234)
+        d = Dropout(0.1).train()
+        x = ops.as_nhwc(torch.ones(2, 16, 5, 7)).requires_grad_()
+        y1 = d(x)
+        y1.sum().backward()
+        kept = y1.detach() != 0
+        assert 0.8 < float(kept.float().mean()) < 0.98
+        assert torch.allclose(y1.detach()[kept], torch.full((), 1 / 0.9), rtol=1e-4)
+        assert torch.equal(x.grad != 0, kept) and torch.allclose(x.grad[kept], torch.full((), 1 / 0.9), rtol=1e-4)
+        y2 = d(x)
+        assert not torch.equal(y2.detach() != 0, kept)                       # the offset advanced
+        assert torch.equal(d.eval()(x), x) and torch.equal(Dropout(0.0).train()(x), x)
+        ops.rng_state('cpu', seed=1234)                                      # same seed, same masks
+        assert torch.equal(Dropout(0.1).train()(x).detach() != 0, kept)
+        x, y = train_batch('fastscnn')
+        torch.manual_seed(0)
+        model = fastscnn(3, 19).train()
+        before = fake_backend.launches
+        CrossEntropyLoss(ignore_index=255)(model(x), y).backward()
+        assert all(torch.isfinite(p.grad).all() for p in model.parameters())
+        assert isinstance(model.classifier[2], torch.nn.Dropout) and list(model.classifier[2].state_dict()) == []
+    finally:
+        Fn.OWN_DROPOUT = keep

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, 'torch_semantic_segmentation_b200', 'csrc')
 EMU = os.path.join(ROOT, 'tests', 'simt_emu')
 SOURCES = ['ppm.cu', 'augment.cu', 'dwconv_bnred.cu',        # dwconv_bnred.cu: the stride-2 (plain SIMT) kernel only
-           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu', 'dwconv_bwd_fused.cu', 'metrics.cu',
+           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu', 'dwconv_bwd_fused.cu', 'metrics.cu', 'dropout.cu',
            'pwconv_tc_bnred.cu', 'dwconv.cu', 'dwconv_tma.cu']       # validated on the B200: calibrate the emulation itself                               # on the functional tcgen05/TMA/mbarrier emulation
 
 
@@ -438,3 +438,29 @@ def test_confusion_matrix_kernels_on_the_simt_emulation(emulated, monkeypatch, v
     emulated.call('tss_confusion_from_labels', dict(pred=pred, target=label, n=n, C=19, cm=cm))
     want = o_cm.confusion_matrix(pred.numpy(), label.numpy(), 19)
     assert (cm.numpy() == want).all() and int(cm.sum()) == int((label != 255).sum())
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_dropout_kernels_on_the_simt_emulation(emulated, dtype):
+    """csrc/dropout.cu: the Philox mask is bit-identical to the numpy restatement, the backward pass regenerates the
+    forward's mask from (seed, used offset), and the device-side offset advances once per forward launch."""
+    from tests.philox_ref import keep_mask
+    g = torch.Generator().manual_seed(3)
+    N, C, H, W, p = 2, 128, 9, 7, 0.1
+    x, dy = _nhwc(N, C, H, W, g, dtype), _nhwc(N, C, H, W, g, dtype)
+    rng = torch.tensor([0x1234567890ABCDEF % (2 ** 62), 41, 0], dtype=torch.int64)
+    n = x.numel()
+    code = _lib.dtype_code(dtype)
+    for step in range(2):
+        y = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2)
+        dx = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2)
+        used = torch.zeros(1, dtype=torch.int64)
+        emulated.call('tss_dropout_fwd', dict(x=x, y=y, n=n, p=p, rng=rng, used=used, dtype=code))
+        emulated.call('tss_dropout_bwd', dict(dy=dy, dx=dx, n=n, p=p, rng=rng, used=used, dtype=code))
+        assert int(used) == 41 + step and int(rng[1]) == 42 + step and int(rng[2]) == 0
+        keep, scale = keep_mask(int(rng[0]), int(used), n, p)
+        keep = torch.from_numpy(keep).view(N, H, W, C).permute(0, 3, 1, 2)
+        want_y = torch.where(keep, x.float() * float(scale), torch.zeros(())).to(dtype)
+        want_dx = torch.where(keep, dy.float() * float(scale), torch.zeros(())).to(dtype)
+        assert torch.equal(y, want_y) and torch.equal(dx, want_dx)
+        assert abs(float(keep.float().mean()) - (1 - p)) < 0.02

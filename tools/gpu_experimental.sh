@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 TAG=${1:-r2x}
 TSS_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_experimental_gpu.py -x -q > gpurun_out/experimental_${TAG}.log 2>&1
 echo "experimental tests rc=$?"; tail -5 gpurun_out/experimental_${TAG}.log
-for arm in "base" "TSS_FUSE_BNRED_EXT=1" "TSS_FUSE_BNAPPLY=1" "TSS_FUSE_PPM=1" "TSS_FUSE_BNAPPLY_DW=1" "TSS_FUSE_BNFIN=1" "TSS_STEM_TC=1" "TSS_DEFER_LOGITS=1" "TSS_FUSE_BNRED_EXT=1 TSS_FUSE_BNAPPLY=1 TSS_FUSE_BNAPPLY_DW=1 TSS_FUSE_PPM=1 TSS_FUSE_BNFIN=1 TSS_STEM_TC=1 TSS_DEFER_LOGITS=1"; do
+for arm in "base" "TSS_FUSE_BNRED_EXT=1" "TSS_FUSE_BNAPPLY=1" "TSS_FUSE_PPM=1" "TSS_FUSE_BNAPPLY_DW=1" "TSS_FUSE_BNFIN=1" "TSS_STEM_TC=1" "TSS_DEFER_LOGITS=1" "TSS_OWN_DROPOUT=1" "TSS_FUSE_BNRED_EXT=1 TSS_FUSE_BNAPPLY=1 TSS_FUSE_BNAPPLY_DW=1 TSS_FUSE_PPM=1 TSS_FUSE_BNFIN=1 TSS_STEM_TC=1 TSS_DEFER_LOGITS=1 TSS_OWN_DROPOUT=1"; do
     name=$(echo "$arm" | tr ' =' '__')
     if [ "$arm" = "base" ]; then envs=""; else envs="$arm"; fi
     env $envs timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_${TAG}_${name}.json 2> gpurun_out/ab_${TAG}_${name}.err

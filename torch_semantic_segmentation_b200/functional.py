@@ -516,6 +516,25 @@ class PPMBranches(torch.autograd.Function):
         return (dx, None) + (None,) * len(ctx.params)
 
 
+# nn.Dropout of the classifiers on the library's own kernel (csrc/dropout.cu: counter-based mask, regenerated in
+# the backward pass, no mask tensor, no ATen kernels on the path).  Off unless TSS_OWN_DROPOUT=1 (not yet run on a B200).
+OWN_DROPOUT = os.environ.get('TSS_OWN_DROPOUT', '0') == '1'
+
+
+class Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p):
+        y, used = ops.dropout_fwd(ops.as_nhwc(x), p)
+        ctx.p = p
+        ctx.save_for_backward(used)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (used,) = ctx.saved_tensors
+        return ops.dropout_bwd(ops.as_nhwc(dy).contiguous(memory_format=torch.channels_last), ctx.p, used), None
+
+
 class Bilinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, Ho, Wo):

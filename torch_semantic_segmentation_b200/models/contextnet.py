@@ -12,7 +12,7 @@ from torch import nn
 
 from .. import ops
 from .. import functional as Fn
-from ..nn.blocks import ConvBNBlock, BottleneckBlock, ClassScores, set_compute_dtype
+from ..nn.blocks import ConvBNBlock, BottleneckBlock, ClassScores, Dropout, set_compute_dtype
 
 __all__ = ['ContextNet', 'contextnet12', 'contextnet14', 'contextnet18']
 
@@ -56,7 +56,7 @@ def Classifier(in_channels, out_channels):
         ConvBlock(in_channels, in_channels, 1),
         DWConvBlock(in_channels, in_channels, 3, padding=1),
         ConvBlock(in_channels, in_channels, 1),
-        nn.Dropout(p=0.1),
+        Dropout(p=0.1),
         ClassScores(in_channels, out_channels),
     )
 

@@ -13,7 +13,7 @@ from torch import nn
 
 from .. import ops
 from .. import functional as Fn
-from ..nn.blocks import (Conv2dBlock, DWConv2dBlock, DSConv2dBlock, BottleneckBlock, ClassScores,
+from ..nn.blocks import (Conv2dBlock, DWConv2dBlock, DSConv2dBlock, BottleneckBlock, ClassScores, Dropout,
                          set_compute_dtype)
 
 __all__ = ['FastSCNN', 'fastscnn', 'Classifier']
@@ -102,7 +102,7 @@ def Classifier(in_channels, out_channels):
     head = nn.Sequential(
         DSConv2dBlock(in_channels, in_channels, kernel_size=3, padding=1),
         DSConv2dBlock(in_channels, in_channels, kernel_size=3, padding=1),
-        nn.Dropout(0.1),
+        Dropout(0.1),
         ClassScores(in_channels, out_channels),
     )
     head[1].input_sole_consumer = True      # only the second DS block reads the first one's output

@@ -279,6 +279,17 @@ def convert_syncbn_model(module, process_group=None):
     return module
 
 
+class Dropout(nn.Dropout):
+    """``nn.Dropout`` (same constructor, no state) whose training forward can run on the library's kernel
+    (``functional.OWN_DROPOUT``); everything else -- eval mode, p = 0, CPU tensors -- is the stock module."""
+
+    def forward(self, input):
+        if (Fn.OWN_DROPOUT and self.training and 0.0 < self.p < 1.0 and input.dim() == 4 and input.shape[1] % 8 == 0
+                and ops.geom(input) is not None and ops.geom(input)[4] == input.shape[1]):
+            return Fn.Dropout.apply(input, self.p)
+        return super().forward(input)
+
+
 def set_compute_dtype(module, dtype, pw_impl=None):
     """Select the activation storage type (fp32 verification mode / bf16) of every fused block."""
     if dtype not in (torch.float32, torch.bfloat16):

@@ -712,3 +712,40 @@ def augment_batch(images, labels, geom, lut, norm, crop):
     _lib.call('tss_augment_batch', images=images, labels=labels, geom=geom, lut=lut, norm=_HostFloats(norm),
               out_image=x, out_label=y, N=N, H=H, W=W, ch=ch, cw=cw)
     return x, y
+
+
+# ------------------------------------------------------------------ dropout -------------
+_RNG = {}
+
+
+def rng_state(device, seed=None):
+    """Per-device {seed, offset, ticket} of the library's counter-based generator (int64[3]); the seed comes from
+    torch's generator on first use (``torch.manual_seed`` before the first training forward keeps runs repeatable)."""
+    device = torch.device(device)
+    st = _RNG.get(device)
+    if st is None or seed is not None:
+        s = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed)
+        st = _RNG[device] = torch.tensor([s, 0, 0], dtype=torch.int64).to(device)
+    return st
+
+
+def dropout_fwd(x, p):
+    """-> y, used (the offset the mask was drawn with, int64[1] on the device; keep it for the backward pass)."""
+    N, C, H, W, ld = _g(x, 'dropout_fwd')
+    if ld != C:
+        raise RuntimeError('dropout_fwd: pitched tensors not supported')
+    y = empty_nhwc(N, C, H, W, x.dtype, x.device)
+    used = torch.empty(1, dtype=torch.int64, device=x.device)
+    _lib.call('tss_dropout_fwd', x=x, y=y, n=x.numel(), p=float(p), rng=rng_state(x.device), used=used,
+              dtype=dtype_code(x.dtype))
+    return y, used
+
+
+def dropout_bwd(dy, p, used):
+    N, C, H, W, ld = _g(dy, 'dropout_bwd')
+    if ld != C:
+        raise RuntimeError('dropout_bwd: pitched tensors not supported')
+    dx = empty_nhwc(N, C, H, W, dy.dtype, dy.device)
+    _lib.call('tss_dropout_bwd', dy=dy, dx=dx, n=dy.numel(), p=float(p), rng=rng_state(dy.device), used=used,
+              dtype=dtype_code(dy.dtype))
+    return dx
