@@ -447,3 +447,18 @@ def test_own_dropout_gate(fake_backend):
         assert isinstance(model.classifier[2], torch.nn.Dropout) and list(model.classifier[2].state_dict()) == []
     finally:
         Fn.OWN_DROPOUT = keep
+
+
+def test_experimental_kernel_tool_dry_run():
+    """tools/experimental_kernels.py (GPU microbenchmarks of the gated kernels next to the kernels they replace):
+    every call signature is exercised on the emulated ABI so that the tool cannot rot before its next GPU visit."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'experimental_kernels.py'), '--dry'], capture_output=True,
+                         text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rows = [json.loads(line) for line in out.stdout.splitlines() if line.startswith('{')]
+    assert len(rows) >= 30 and not [r for r in rows if 'error' in r], [r for r in rows if 'error' in r]
