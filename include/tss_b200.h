@@ -75,6 +75,14 @@ int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g, int N, in
 int tss_dwconv3x3_dgrad_s2_bnred(const void* dy, const float* w, void* g, int N, int Hi, int Wi, int C,
                                  const void* yp, const float* mean, const float* rstd, const float* gamma,
                                  const float* beta, int flags, float* sums, int dtype, void* stream);
+/* Training: depthwise forward and weight gradient whose input is the RAW conv output x of the producing layer;
+ * its BatchNorm (+ReLU with in_flags&TSS_EPI_RELU) z = act(x*in_scale + in_shift) is applied while the input tile is
+ * read, so the activated tensor is never materialised (zero padding applies to z).  dilation 1, stride 1 or 2;
+ * fwd accumulates the output statistics like tss_dwconv3x3_fwd; wgrad: dw += sum z * dy. */
+int tss_dwconv3x3_fwd_bnin(const void* x, const float* in_scale, const float* in_shift, int in_flags, const float* w,
+                           void* y, int N, int Hi, int Wi, int C, int stride, double* stats, int dtype, void* stream);
+int tss_dwconv3x3_wgrad_bnin(const void* x, const float* in_scale, const float* in_shift, int in_flags, const void* dy,
+                             float* dw, int N, int Hi, int Wi, int C, int stride, int dtype, void* stream);
 /* Training, stride 1 / dilation 1: BatchNorm-backward APPLY of this depthwise layer + its dgrad + the producer's
  * BatchNorm-backward reduction in ONE kernel (the depthwise counterpart of tss_pwconv_bwd_fused).  dz, y
  * [N][H][W][C]: gradient after this layer's BN/ReLU and its raw conv output (two TMA halo tiles); sums[2C]: the

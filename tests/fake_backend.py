@@ -50,6 +50,21 @@ class FakeBackend:
         y.copy_(_epilogue(raw, scale, shift, None, flags))
         return 0
 
+    @staticmethod
+    def _in_act(x, in_scale, in_shift, in_flags):
+        z = x.float() * in_scale.view(1, -1, 1, 1) + in_shift.view(1, -1, 1, 1)
+        return z.clamp_min(0) if in_flags & RELU else z
+
+    def tss_dwconv3x3_fwd_bnin(self, x, in_scale, in_shift, in_flags, w, y, N, Hi, Wi, C, stride, stats, dtype):
+        raw = F.conv2d(self._in_act(x, in_scale, in_shift, in_flags), w.view(C, 1, 3, 3), None, stride, 1, 1, C)
+        _stats(stats, raw)
+        y.copy_(raw)
+        return 0
+
+    def tss_dwconv3x3_wgrad_bnin(self, x, in_scale, in_shift, in_flags, dy, dw, N, Hi, Wi, C, stride, dtype):
+        dw += nngrad.conv2d_weight(self._in_act(x, in_scale, in_shift, in_flags), (C, 1, 3, 3), dy.float(), stride, 1, 1, C).view_as(dw)
+        return 0
+
     def tss_dwconv3x3_dgrad(self, dy, w, dx, N, Hi, Wi, C, stride, dilation, dtype):
         dx.copy_(nngrad.conv2d_input((N, C, Hi, Wi), w.view(C, 1, 3, 3), dy.float(), stride, dilation, dilation, C))
         return 0

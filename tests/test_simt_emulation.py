@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, 'torch_semantic_segmentation_b200', 'csrc')
 EMU = os.path.join(ROOT, 'tests', 'simt_emu')
 SOURCES = ['ppm.cu', 'augment.cu', 'dwconv_bnred.cu',        # dwconv_bnred.cu: the stride-2 (plain SIMT) kernel only
-           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu', 'dwconv_bwd_fused.cu', 'metrics.cu', 'dropout.cu',
+           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu', 'dwconv_bwd_fused.cu', 'metrics.cu', 'dropout.cu', 'dwconv_bnin.cu',
            'pwconv_tc_bnred.cu', 'dwconv.cu', 'dwconv_tma.cu']       # validated on the B200: calibrate the emulation itself                               # on the functional tcgen05/TMA/mbarrier emulation
 
 
@@ -464,3 +464,31 @@ def test_dropout_kernels_on_the_simt_emulation(emulated, dtype):
         want_dx = torch.where(keep, dy.float() * float(scale), torch.zeros(())).to(dtype)
         assert torch.equal(y, want_y) and torch.equal(dx, want_dx)
         assert abs(float(keep.float().mean()) - (1 - p)) < 0.02
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('C,N,H,W,stride,relu', [(64, 2, 12, 20, 1, 1), (384, 1, 5, 7, 2, 1), (96, 1, 9, 40, 1, 0), (32, 2, 16, 24, 2, 1),
+                                                 (48, 1, 7, 33, 1, 1)])
+def test_depthwise_kernels_with_the_input_batchnorm_folded_in(emulated, C, N, H, W, stride, relu, dtype):
+    """csrc/dwconv_bnin.cu: forward (with statistics) and weight gradient on act(BN(raw input)) without materialising
+    it; zero padding applies to the ACTIVATED tensor although TMA zero-fills the raw one."""
+    g = torch.Generator().manual_seed(C + H + stride)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    x, dy = _nhwc(N, C, H, W, g, dtype), _nhwc(N, C, Ho, Wo, g, dtype)
+    w = torch.randn(C, 1, 3, 3, generator=g) / 3
+    sc, sh = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.5 + 0.3      # BN(0) != 0
+    code = _lib.dtype_code(dtype)
+    outs = {}
+    for name, be in (('ref', FakeBackend()), ('emu', emulated)):
+        y = torch.zeros(N, Ho, Wo, C, dtype=dtype).permute(0, 3, 1, 2)
+        stats = torch.zeros(2 * C, dtype=torch.float64)
+        be.call('tss_dwconv3x3_fwd_bnin', dict(x=x, in_scale=sc, in_shift=sh, in_flags=relu, w=w, y=y, N=N, Hi=H, Wi=W, C=C,
+                                               stride=stride, stats=stats, dtype=code))
+        dw = torch.zeros(C, 1, 3, 3)
+        be.call('tss_dwconv3x3_wgrad_bnin', dict(x=x, in_scale=sc, in_shift=sh, in_flags=relu, dy=dy, dw=dw, N=N, Hi=H, Wi=W, C=C,
+                                                 stride=stride, dtype=code))
+        outs[name] = (y.float(), stats, dw)
+    tol = 1e-5 if dtype == torch.float32 else 5e-3
+    assert rel(outs['emu'][0], outs['ref'][0]) < tol
+    assert rel(outs['emu'][1], outs['ref'][1]) < 1e-5
+    assert rel(outs['emu'][2], outs['ref'][2]) < 1e-4

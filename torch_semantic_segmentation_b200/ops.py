@@ -103,6 +103,26 @@ def dwconv_wgrad(x, dy, dw, stride, dilation):
               dilation=dilation, dtype=dtype_code(x.dtype))
 
 
+def dwconv_fwd_bnin(x, in_scale, in_shift, in_relu, w, stride, stats):
+    """Depthwise forward on ``act(x * in_scale + in_shift)`` without materialising it (``x``: raw conv output)."""
+    N, C, Hi, Wi, ld = _g(x, 'dwconv_fwd_bnin')
+    if ld != C:
+        raise RuntimeError('dwconv_fwd_bnin: pitched input not supported')
+    Ho, Wo = (Hi - 1) // stride + 1, (Wi - 1) // stride + 1
+    y = empty_nhwc(N, C, Ho, Wo, x.dtype, x.device)
+    _lib.call('tss_dwconv3x3_fwd_bnin', x=x, in_scale=in_scale, in_shift=in_shift, in_flags=_flags(in_relu), w=w, y=y, N=N,
+              Hi=Hi, Wi=Wi, C=C, stride=stride, stats=stats, dtype=dtype_code(x.dtype))
+    return y
+
+
+def dwconv_wgrad_bnin(x, in_scale, in_shift, in_relu, dy, dw, stride):
+    N, C, Hi, Wi, ld = _g(x, 'dwconv_wgrad_bnin')
+    if ld != C or _g(dy, 'dwconv_wgrad_bnin')[4] != C:
+        raise RuntimeError('dwconv_wgrad_bnin: pitched input not supported')
+    _lib.call('tss_dwconv3x3_wgrad_bnin', x=x, in_scale=in_scale, in_shift=in_shift, in_flags=_flags(in_relu), dy=dy, dw=dw,
+              N=N, Hi=Hi, Wi=Wi, C=C, stride=stride, dtype=dtype_code(x.dtype))
+
+
 # ------------------------------------------------------------------ pointwise 1x1 ------
 def _pad8(c):
     return (c + 7) // 8 * 8
