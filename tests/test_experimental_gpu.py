@@ -8,6 +8,8 @@ unvalidated kernel can never hang the default GPU suite.
   (csrc/pwconv_tc_bwd.cu: pw_tc_bwd_kernel; enabled in the model by TSS_FUSE_BNAPPLY=1);
 * the pyramid-pooling branches as grouped launches (csrc/ppm.cu; enabled in the model by TSS_FUSE_PPM=1);
 * the same for the stride-1 depthwise layers (csrc/dwconv_bwd_fused.cu; TSS_FUSE_BNAPPLY_DW=1);
+* depthwise forward / weight gradient that apply the producer's BatchNorm while reading (csrc/dwconv_bnin.cu;
+  TSS_FUSE_BNIN=1);
 * BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu; TSS_FUSE_BNFIN=1);
 * the stem convolution and its weight gradient on tcgen05 (csrc/stem_tc.cu; TSS_STEM_TC=1);
 * the warp-private confusion-matrix kernel (csrc/metrics.cu; TSS_CM_VARIANT=1);
@@ -437,3 +439,34 @@ def test_own_dropout_matches_the_philox_reference(dtype):
         keep = torch.from_numpy(keep).view(N, H, W, C).permute(0, 3, 1, 2).cuda()
         want = torch.where(keep, x.float() * float(scale), torch.zeros((), device='cuda')).to(dtype)
         assert torch.equal(y, want) and torch.equal(dx, want)
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('C,N,H,W,stride', [(384, 2, 96, 96, 2), (384, 2, 48, 48, 1), (576, 2, 24, 24, 1), (96, 1, 9, 40, 1), (32, 2, 16, 24, 2)])
+def test_dw_kernels_with_input_batchnorm_match_apply_then_conv(C, N, H, W, stride, dtype):
+    """tss_dwconv3x3_fwd_bnin / wgrad_bnin == tss_bn_apply followed by tss_dwconv3x3_fwd / wgrad, both on the GPU."""
+    g = torch.Generator().manual_seed(C + H + stride)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    mk = lambda h, w_: torch.randn(N, h, w_, C, generator=g).to(dtype).cuda().permute(0, 3, 1, 2)
+    x, dy = mk(H, W), mk(Ho, Wo)
+    w = (torch.randn(C, 1, 3, 3, generator=g) / 3).cuda()
+    sc, sh = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.5 + 0.3).cuda()
+    be = _lib.backend()
+    code = _lib.dtype_code(dtype)
+    new = lambda h, w_: torch.zeros(N, h, w_, C, dtype=dtype, device='cuda').permute(0, 3, 1, 2)
+    z, y1, y2 = new(H, W), new(Ho, Wo), new(Ho, Wo)
+    st1, st2 = torch.zeros(2 * C, dtype=torch.float64, device='cuda'), torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+    dw1, dw2 = torch.zeros(C, 1, 3, 3, device='cuda'), torch.zeros(C, 1, 3, 3, device='cuda')
+    M = N * H * W
+    be.call('tss_bn_apply', dict(y=x, scale=sc, shift=sh, y2=None, scale2=None, shift2=None, res=None, z=z, M=M, C=C, ldy=C, ldy2=0,
+                                 ldr=0, ldz=C, flags=1, dtype=code))
+    be.call('tss_dwconv3x3_fwd', dict(x=z, w=w, y=y1, N=N, Hi=H, Wi=W, C=C, stride=stride, dilation=1, scale=None, shift=None, flags=0,
+                                      stats=st1, dtype=code))
+    be.call('tss_dwconv3x3_wgrad', dict(x=z, dy=dy, dw=dw1, N=N, Hi=H, Wi=W, C=C, stride=stride, dilation=1, dtype=code))
+    be.call('tss_dwconv3x3_fwd_bnin', dict(x=x, in_scale=sc, in_shift=sh, in_flags=1, w=w, y=y2, N=N, Hi=H, Wi=W, C=C, stride=stride,
+                                           stats=st2, dtype=code))
+    be.call('tss_dwconv3x3_wgrad_bnin', dict(x=x, in_scale=sc, in_shift=sh, in_flags=1, dy=dy, dw=dw2, N=N, Hi=H, Wi=W, C=C,
+                                             stride=stride, dtype=code))
+    torch.cuda.synchronize()
+    tol = 1e-5 if dtype == torch.float32 else 8e-3           # bf16: the unfused path rounds z to bf16 before the stencil
+    assert rel(y2, y1) < tol and rel(st2, st1) < tol and rel(dw2, dw1) < tol

@@ -337,7 +337,8 @@ def test_all_gates_together_train_and_eval(fake_backend, arch):
     from torch_semantic_segmentation_b200.models.contextnet import contextnet14
     from torch_semantic_segmentation_b200.nn.blocks import set_compute_dtype
     from torch_semantic_segmentation_b200.optim import FlatAdamW
-    flags = ['FUSE_BNRED_EXT', 'FUSE_BNAPPLY', 'FUSE_BNAPPLY_DW', 'FUSE_PPM', 'FUSE_BNFIN', 'STEM_TC']
+    flags = ['FUSE_BNRED_EXT', 'FUSE_BNAPPLY', 'FUSE_BNAPPLY_DW', 'FUSE_PPM', 'FUSE_BNFIN', 'FUSE_BNIN', 'STEM_TC', 'DEFER_LOGITS',
+             'OWN_DROPOUT']
     keep = {f: getattr(Fn, f) for f in flags}
     factory = {'fastscnn': fastscnn, 'contextnet14': contextnet14}[arch]
     g = torch.Generator().manual_seed(1)
@@ -462,3 +463,42 @@ def test_experimental_kernel_tool_dry_run():
     assert out.returncode == 0, out.stderr[-2000:]
     rows = [json.loads(line) for line in out.stdout.splitlines() if line.startswith('{')]
     assert len(rows) >= 30 and not [r for r in rows if 'error' in r], [r for r in rows if 'error' in r]
+
+
+@pytest.mark.parametrize('arch', ['fastscnn', 'contextnet14'])
+def test_bottleneck_without_the_expanded_activation(fake_backend, arch):
+    """functional.FUSE_BNIN (off by default): conv1's BatchNorm + ReLU applied by the depthwise conv2 while it reads its
+    input; same forward and gradients, one bn_apply less per bottleneck, no other change in the call list."""
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.models.contextnet import contextnet14
+    factory = {'fastscnn': fastscnn, 'contextnet14': contextnet14}[arch]
+    calls = {}
+    inner = fake_backend.call
+
+    def counting(name, kwargs):
+        calls[name] = calls.get(name, 0) + 1
+        return inner(name, kwargs)
+    fake_backend.call = counting
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(3, 3, 64, 96, generator=g), torch.randint(0, 19, (3, 64, 96), generator=g)
+    keep = Fn.FUSE_BNIN
+    runs = {}
+    try:
+        for flag in (False, True):
+            Fn.FUSE_BNIN = flag
+            calls.clear()
+            torch.manual_seed(0)
+            model = _no_dropout(factory(3, 19)).train()
+            out = model(x)
+            CrossEntropyLoss(ignore_index=255)(out, y).backward()
+            runs[flag] = (out.detach(), torch.cat([p.grad.reshape(-1) for p in model.parameters()]), dict(calls),
+                          {k: v.clone().float() for k, v in model.state_dict().items() if 'running' in k})
+    finally:
+        Fn.FUSE_BNIN = keep
+    a, b = runs[False], runs[True]
+    assert rel(b[0], a[0]) < 1e-5 and rel(b[1], a[1]) < 2e-3          # fp32; gradients in front of BatchNorm layers cancel
+    assert all(rel(b[3][k], a[3][k]) < 1e-5 for k in a[3])
+    n = b[2]['tss_dwconv3x3_fwd_bnin']
+    assert n >= 9 and b[2]['tss_dwconv3x3_wgrad_bnin'] == n
+    assert b[2]['tss_bn_apply'] == a[2]['tss_bn_apply'] - n
+    assert b[2]['tss_dwconv3x3_fwd'] == a[2]['tss_dwconv3x3_fwd'] - n

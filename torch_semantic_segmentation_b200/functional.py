@@ -173,6 +173,10 @@ FUSE_PPM = os.environ.get('TSS_FUSE_PPM', '0') == '1'
 # BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu): one launch less per layer on the forward
 # chain (44 per step).  Same status: off unless TSS_FUSE_BNFIN=1.
 FUSE_BNFIN = os.environ.get('TSS_FUSE_BNFIN', '0') == '1'
+# Inside a bottleneck, conv1's BatchNorm + ReLU applied by conv2 (depthwise) while it reads its input tile
+# (csrc/dwconv_bnin.cu): the expanded activation is never materialised, conv1's apply pass disappears.
+# Off unless TSS_FUSE_BNIN=1.
+FUSE_BNIN = os.environ.get('TSS_FUSE_BNIN', '0') == '1'
 
 
 class _BnLink:
@@ -203,20 +207,34 @@ def _sync_group(bn):
     return torch.distributed.get_world_size(group), group
 
 
+def _dw_wgrad_fn(ctx, x, dy, dw, spec):
+    """The depthwise weight gradient of a layer: on the activated input, or on the producer's raw output with its
+    BatchNorm applied on the fly when the forward pass ran that way."""
+    aff = ctx.in_affine
+    if aff is not None:
+        return lambda: ops.dwconv_wgrad_bnin(x, aff[0], aff[1], aff[2], dy, dw, spec.stride)
+    return lambda: ops.dwconv_wgrad(x, dy, dw, spec.stride, spec.dilation)
+
+
 class ConvBNAct(torch.autograd.Function):
     """z = act(BN_train(conv(x, w)) [+ res])."""
 
     last_link = None        # handed to nn.blocks right after apply(): the link of the layer just run
+    last_affine = None      # (scale, shift, relu) of a layer whose apply pass was left to its consumer
 
     @staticmethod
-    def forward(ctx, x, res, weight, gamma, beta, spec, packed, producer=None):
+    def forward(ctx, x, res, weight, gamma, beta, spec, packed, producer=None, defer_apply=False, in_affine=None):
         bn = spec.bn
         C = weight.shape[0]
         if bn.momentum is None:
             raise RuntimeError('BatchNorm2d(momentum=None) (cumulative average) is not supported')
         # per-layer scratch [statistics 2C fp64 | backward sums 2C fp32]: finalize re-zeroes all of it
         scratch = ops.layer_scratch(bn, weight.device)
-        y = conv_forward(spec, x, weight, stats=scratch, packed=packed)
+        if in_affine is not None:      # x is the RAW output of the producer; its BatchNorm (+ReLU) is applied on the fly
+            y = ops.dwconv_fwd_bnin(x, in_affine[0], in_affine[1], in_affine[2], weight, spec.stride, scratch)
+        else:
+            y = conv_forward(spec, x, weight, stats=scratch, packed=packed)
+        ctx.in_affine = in_affine
         N, _, H, W = y.shape
         world, group = _sync_group(bn)
         if world > 1:
@@ -224,7 +242,14 @@ class ConvBNAct(torch.autograd.Function):
             # all ranks, one fp64 all-reduce per layer; every rank holds the same number of pixels
             torch.distributed.all_reduce(scratch[:2 * C], group=group)
         ctx.sync = (world, group)
-        if FUSE_BNFIN:
+        ConvBNAct.last_affine = None
+        if defer_apply:
+            # the single consumer (a depthwise conv, nn.blocks) applies scale / shift / ReLU while reading: z is y
+            scale, shift, mean, rstd = ops.bn_finalize(scratch, N * H * W * world, bn, float(bn.momentum), float(bn.eps),
+                                                       update_running=bn.track_running_stats, clear_n=3 * C, C=C)
+            z = y
+            ConvBNAct.last_affine = (scale, shift, spec.relu)
+        elif FUSE_BNFIN:
             z, mean, rstd = ops.bn_finalize_apply(scratch, N * H * W * world, bn, float(bn.momentum), float(bn.eps), y, res=res,
                                                   relu=spec.relu, update_running=bn.track_running_stats, clear_n=3 * C, C=C)
         else:
@@ -290,7 +315,7 @@ class ConvBNAct(torch.autograd.Function):
                 ops.pwconv_wgrad(x, dy, dw, impl=1)
             grad_ready(*ctx.params)
             return (dx, None, None if gw is not None else dw, None if gg is not None else gg_out,
-                    None if gb is not None else gb_out, None, None, None)
+                    None if gb is not None else gb_out, None, None, None, None, None)
         if (FUSE_BNAPPLY_DW and spec.kind == 'dw' and prod is not None and spec.stride == 1 and spec.dilation == 1
                 and C % 32 == 0 and not ctx.has_res and ctx.sync[0] == 1 and ctx.needs_input_grad[0]
                 and ops.geom(dz)[4] == C):
@@ -306,13 +331,14 @@ class ConvBNAct(torch.autograd.Function):
                 mask = spec.relu
             dy, dx = ops.dwconv_bwd_fused(dz, y, weight, mean, rstd, gamma, beta, sums, mask, prod, dgamma=gg_out, dbeta=gb_out)
             prod.reduced, prod.bn._tss_dirty = True, True
+            dw_wgrad = _dw_wgrad_fn(ctx, x, dy, dw, spec)
             if gw is not None:
-                wgrad_lane.run(dy.device, lambda: ops.dwconv_wgrad(x, dy, dw, 1, 1), x, dy)
+                wgrad_lane.run(dy.device, dw_wgrad, x, dy)
             else:
-                ops.dwconv_wgrad(x, dy, dw, 1, 1)
+                dw_wgrad()
             grad_ready(*ctx.params)
             return (dx, None, None if gw is not None else dw, None if gg is not None else gg_out,
-                    None if gb is not None else gb_out, None, None, None)
+                    None if gb is not None else gb_out, None, None, None, None, None)
         if link is not None and link.reduced:
             # the consumer's dgrad already masked the gradient and accumulated both sums
             dy, dres = ops.bn_backward(dz, None, y, mean, rstd, gamma, False, dgamma=gg_out, dbeta=gb_out, beta=beta,
@@ -337,7 +363,7 @@ class ConvBNAct(torch.autograd.Function):
                 else:
                     dx = ops.pwconv_dgrad(dy, weight, wpT=wpT, impl=impl)
         elif spec.kind == 'dw':
-            lane(lambda: ops.dwconv_wgrad(x, dy, dw, spec.stride, spec.dilation))
+            lane(_dw_wgrad_fn(ctx, x, dy, dw, spec))
             if ctx.needs_input_grad[0]:
                 if prod is not None and spec.stride == 1 and spec.dilation == 1 and weight.shape[0] % 32 == 0:
                     dx = ops.dwconv_dgrad_bnred(dy, weight, prod)
@@ -356,7 +382,7 @@ class ConvBNAct(torch.autograd.Function):
                 lane(lambda: ops.stem_wgrad(x, dy, dw))
         grad_ready(*ctx.params)
         return (dx, dres, None if gw is not None else dw, None if gg is not None else gg_out,
-                None if gb is not None else gb_out, None, None, None)
+                None if gb is not None else gb_out, None, None, None, None, None)
 
 
 class Im2Col3x3(torch.autograd.Function):

@@ -124,11 +124,12 @@ class _FusedConvBN:
             self._pack_cache[ci] = hit
         return hit[1]
 
-    def _conv_bn(self, ci, x, relu, res=None, sole_consumer=False):
+    def _conv_bn(self, ci, x, relu, res=None, sole_consumer=False, defer_apply=False):
         """``sole_consumer``: ``x`` is the output of another fused conv+BN pair and nothing else reads it (the
         enclosing block guarantees it), so that layer's BatchNorm-backward reduction may be folded into this
         conv's dgrad epilogue (functional.FUSE_BNRED)."""
         producer = getattr(x, '_tss_bn_link', None) if sole_consumer else None
+        in_affine = getattr(x, '_tss_in_affine', None)       # x is a RAW conv output whose BatchNorm this conv applies
         conv, bn = self[ci], self[ci + 1]
         spec = self._spec(ci, relu)
         if spec.kind != 'stem':
@@ -149,10 +150,18 @@ class _FusedConvBN:
             packed = self._packed(ci)
         use_batch_stats = self.training or not bn.track_running_stats
         if use_batch_stats:
-            z = Fn.ConvBNAct.apply(x, res, weight, bn.weight, bn.bias, spec, packed, producer)
+            # `defer_apply`: the enclosing block promises that the single consumer is a depthwise conv that applies
+            # this layer's BatchNorm + ReLU itself (functional.FUSE_BNIN); `_tss_in_affine` is that hand-over
+            if in_affine is not None and not (spec.kind == 'dw' and spec.dilation == 1 and spec.stride in (1, 2)):
+                raise RuntimeError('a tensor with a pending BatchNorm reached a layer that cannot apply it')
+            z = Fn.ConvBNAct.apply(x, res, weight, bn.weight, bn.bias, spec, packed, producer, defer_apply, in_affine)
             if Fn.ConvBNAct.last_link is not None:
                 z._tss_bn_link, Fn.ConvBNAct.last_link = Fn.ConvBNAct.last_link, None
+            if Fn.ConvBNAct.last_affine is not None:
+                z._tss_in_affine, Fn.ConvBNAct.last_affine = Fn.ConvBNAct.last_affine, None
             return z
+        if in_affine is not None:
+            raise RuntimeError('a tensor with a pending BatchNorm reached an eval-mode layer')
         if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
             raise RuntimeError('eval-mode BatchNorm with autograd is not implemented; '
                                'wrap inference in torch.no_grad()')
@@ -178,10 +187,10 @@ class ConvBNBlock(nn.Sequential, _FusedConvBN):
         self.use_activation = use_activation
         self._init_fused()
 
-    def forward(self, input, residual=None, relu=None, sole_consumer=False):
+    def forward(self, input, residual=None, relu=None, sole_consumer=False, defer_apply=False):
         """``residual``/``relu`` let the enclosing block fuse its ``+input`` and trailing
         ``F.relu`` (fastscnn.py:158-161, 89) into this block's BatchNorm apply."""
-        return self._conv_bn(0, input, self.use_activation if relu is None else relu, residual, sole_consumer)
+        return self._conv_bn(0, input, self.use_activation if relu is None else relu, residual, sole_consumer, defer_apply)
 
 
 class DSConvBNBlock(nn.Sequential, _FusedConvBN):
@@ -242,8 +251,15 @@ class BottleneckBlock(nn.Module):
         self.conv3 = Conv2dBlock(expansion_channels, out_channels, kernel_size=1, use_activation=False)
         self.has_residual = stride == 1 and in_channels == out_channels   # "x.shape == input.shape"
 
+    def _defer_conv1_apply(self):
+        """conv2 can apply conv1's BatchNorm + ReLU while reading its input (functional.FUSE_BNIN)."""
+        c2, bn1 = self.conv2[0], self.conv1[1]
+        return bool(Fn.FUSE_BNIN and self.training and torch.is_grad_enabled() and c2.dilation[0] == 1
+                    and c2.stride[0] in (1, 2) and c2.in_channels % 32 == 0 and bn1.track_running_stats
+                    and getattr(bn1, '_tss_sync', None) is None and getattr(self.conv2[1], '_tss_sync', None) is None)
+
     def forward(self, input):
-        x = self.conv1(input)
+        x = self.conv1(input, defer_apply=self._defer_conv1_apply())
         res = input if self.has_residual else None
         y = fused_dw_pw(self.conv2, 0, self.conv3, 0, x, self.conv2.use_activation, True, residual=res)
         if y is not None:
