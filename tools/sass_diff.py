@@ -5,6 +5,10 @@ refactor or an addition left the kernels already measured on the GPU byte-identi
 
     git worktree add build/old_tree <commit> && make -C build/old_tree -j8
     python tools/sass_diff.py build/old_tree/build build
+
+Caveat: ptxas is not deterministic for every kernel -- compiling the unchanged dwpw_tc.cu six times in a row gave two
+different uniform-register allocations (UR8 vs UR10 in the same instruction) -- so a CHANGED line for a file whose
+source did not change has to be confirmed by rebuilding that object a few times.
 """
 import glob
 import hashlib
