@@ -34,6 +34,22 @@ def ConvBlock(in_channels, out_channels, kernel_size, padding=0, stride=1, use_r
     return ConvBNBlock(in_channels, out_channels, kernel_size, stride, padding, 1, 1, use_relu)
 
 
+class _Chain(nn.Sequential):
+    """``nn.Sequential`` (same child indices, same state_dict keys) of conv+BN blocks in which every block is the only
+    reader of its predecessor's output: with functional.FUSE_BNRED_EXT the predecessor's BatchNorm-backward reduction
+    is folded into each block's dgrad (the spatial branch holds the largest activations of the network)."""
+
+    def forward(self, input):
+        x, prev = input, None
+        for module in self:
+            if isinstance(module, ConvBNBlock) and isinstance(prev, ConvBNBlock):
+                x = module(x, sole_consumer=Fn.FUSE_BNRED_EXT)
+            else:
+                x = module(x)
+            prev = module
+        return x
+
+
 def DWConvBlock(in_channels, out_channels, kernel_size, padding=0, stride=1, dilation=1, use_relu=True):
     """reference: models/contextnet.py:150-165."""
     if in_channels != out_channels:
@@ -51,7 +67,7 @@ def LinearBottleneck(in_channels, out_channels, num_blocks, expansion=6, stride=
 
 def Classifier(in_channels, out_channels):
     """reference: models/contextnet.py:79-87."""
-    return nn.Sequential(
+    return _Chain(
         DWConvBlock(in_channels, in_channels, 3, padding=1),
         ConvBlock(in_channels, in_channels, 1),
         DWConvBlock(in_channels, in_channels, 3, padding=1),
@@ -90,7 +106,7 @@ class ContextNet(nn.Module):
     def __init__(self, in_channels, out_channels, scale_factor=4):
         super().__init__()
         self.scale_factor = scale_factor
-        self.spatial = nn.Sequential(
+        self.spatial = _Chain(
             ConvBlock(in_channels, 32, 3, padding=1, stride=2),
             DWConvBlock(32, 32, kernel_size=3, padding=1, stride=2),
             ConvBlock(32, 64, 1),
