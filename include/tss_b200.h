@@ -127,6 +127,13 @@ int tss_pwconv_wgrad(const void* x, const void* dy, float* dw, float* db, int64_
 int tss_pwconv_dgrad_bnred(const void* dy, const void* wpT, void* g, int64_t M, int K, int Nc, int64_t lddy,
                            int64_t ldg, const void* yp, int64_t ldyp, const float* mean, const float* rstd,
                            const float* gamma, const float* beta, int flags, float* sums, void* stream);
+/* Training, bf16: 1x1 forward whose input x[M][K] (pitch ldx) is the RAW conv output of the producing layer; its
+ * BatchNorm (+ReLU with in_flags&TSS_EPI_RELU) z = act(x*in_scale + in_shift) is applied by the threads that build the
+ * GEMM's A operand.  z (pitch ldz, may be NULL) is stored for the weight gradient; y[M][Nc] = z . wp^T (raw output),
+ * stats[2*Nc] accumulates its BatchNorm statistics like tss_pwconv_fwd. */
+int tss_pwconv_fwd_bnin(const void* x, int64_t ldx, const float* in_scale, const float* in_shift, int in_flags, void* z,
+                        int64_t ldz, const void* wp, void* y, int64_t ldy, int64_t M, int K, int Nc, double* stats,
+                        void* stream);
 /* Training, bf16: BatchNorm-backward APPLY of this 1x1 layer + its dgrad (+ optionally the producer's
  * BatchNorm-backward reduction, as tss_pwconv_dgrad_bnred) in ONE tcgen05 kernel.  dz[M][Nc] is the gradient
  * after the layer's BN/ReLU, y[M][Nc] its raw conv output, sums[2*Nc] the finished reduction (sum g, sum g*xhat

@@ -82,6 +82,16 @@ class FakeBackend:
         y.copy_(_epilogue(raw, scale, shift, res, flags))
         return 0
 
+    def tss_pwconv_fwd_bnin(self, x, ldx, in_scale, in_shift, in_flags, z, ldz, wp, y, ldy, M, K, Nc, stats):
+        act = self._in_act(x, in_scale, in_shift, in_flags)
+        if z is not None:
+            z.copy_(act)
+            act = z.float()                       # the GEMM multiplies the rounded operand
+        raw = F.conv2d(act, wp.float().view(Nc, K, 1, 1))
+        _stats(stats, raw)
+        y.copy_(raw)
+        return 0
+
     def tss_pwconv_dgrad(self, dy, w, wpT, dx, M, K, Nc, lddy, lddx, impl, dtype):
         wt = wpT.float() if (impl == 1 and wpT is not None) else w.view(Nc, K).t()      # impl 1 multiplies with the bf16 pack
         dx.copy_(F.conv2d(dy.float(), wt.reshape(K, Nc, 1, 1)))

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, 'torch_semantic_segmentation_b200', 'csrc')
 EMU = os.path.join(ROOT, 'tests', 'simt_emu')
 SOURCES = ['ppm.cu', 'augment.cu', 'dwconv_bnred.cu',        # dwconv_bnred.cu: the stride-2 (plain SIMT) kernel only
-           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu', 'dwconv_bwd_fused.cu', 'metrics.cu', 'dropout.cu', 'dwconv_bnin.cu',
+           'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu', 'dwconv_bwd_fused.cu', 'metrics.cu', 'dropout.cu', 'dwconv_bnin.cu', 'pwconv_tc_fwd_bnin.cu',
            'pwconv_tc_bnred.cu', 'dwconv.cu', 'dwconv_tma.cu']       # validated on the B200: calibrate the emulation itself                               # on the functional tcgen05/TMA/mbarrier emulation
 
 
@@ -492,3 +492,28 @@ def test_depthwise_kernels_with_the_input_batchnorm_folded_in(emulated, C, N, H,
     assert rel(outs['emu'][0], outs['ref'][0]) < tol
     assert rel(outs['emu'][1], outs['ref'][1]) < 1e-5
     assert rel(outs['emu'][2], outs['ref'][2]) < 1e-4
+
+
+@pytest.mark.parametrize('M_shape,K,Nc,relu', [((2, 9, 13), 384, 64, 1), ((1, 16, 8), 128, 128, 1), ((2, 5, 7), 576, 96, 0),
+                                               ((3, 8, 8), 48, 32, 1), ((1, 1, 3), 8, 16, 1), ((1, 12, 25), 768, 128, 1)])
+def test_pw_forward_with_the_input_batchnorm_on_the_tcgen05_emulation(emulated, M_shape, K, Nc, relu):
+    """csrc/pwconv_tc_fwd_bnin.cu: the A operand is relu(BN(raw input)) built by the threads, z stored once, the raw
+    output and its statistics come from the TMEM accumulator."""
+    N, H, W = M_shape
+    M = N * H * W
+    g = torch.Generator().manual_seed(K + Nc + M)
+    dt = torch.bfloat16
+    x = _nhwc(N, K, H, W, g, dt)
+    sc, sh = torch.rand(K, generator=g) + 0.5, torch.randn(K, generator=g) * 0.4
+    wp = (torch.randn(Nc, K, generator=g) / K ** 0.5).to(dt)
+    outs = {}
+    for name, be in (('ref', FakeBackend()), ('emu', emulated)):
+        y = torch.zeros(N, H, W, Nc, dtype=dt).permute(0, 3, 1, 2)
+        z = torch.zeros(N, H, W, K, dtype=dt).permute(0, 3, 1, 2)
+        stats = torch.zeros(2 * Nc, dtype=torch.float64)
+        be.call('tss_pwconv_fwd_bnin', dict(x=x, ldx=K, in_scale=sc, in_shift=sh, in_flags=relu, z=z, ldz=K, wp=wp, y=y, ldy=Nc, M=M,
+                                            K=K, Nc=Nc, stats=stats))
+        outs[name] = (y.float(), z.float(), stats)
+    assert rel(outs['emu'][1], outs['ref'][1]) < 1e-4            # z: fma vs mul+add before the bf16 rounding
+    assert rel(outs['emu'][0], outs['ref'][0]) < 5e-3
+    assert rel(outs['emu'][2], outs['ref'][2]) < 1e-3

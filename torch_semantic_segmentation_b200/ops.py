@@ -143,6 +143,18 @@ def pwconv_fwd(x, w, scale=None, shift=None, res=None, relu=False, stats=None, o
     return out
 
 
+def pwconv_fwd_bnin(x, in_scale, in_shift, in_relu, wp, stats):
+    """1x1 forward on ``act(x * in_scale + in_shift)`` built inside the GEMM (``x``: raw conv output, bf16)
+    -> y (raw output), z (the activated input, stored once for the weight gradient)."""
+    N, K, H, W, ldx = _g(x, 'pwconv_fwd_bnin')
+    Nc = wp.shape[0]
+    y = empty_nhwc(N, Nc, H, W, x.dtype, x.device)
+    z = empty_nhwc(N, K, H, W, x.dtype, x.device)
+    _lib.call('tss_pwconv_fwd_bnin', x=x, ldx=ldx, in_scale=in_scale, in_shift=in_shift, in_flags=_flags(in_relu), z=z, ldz=K,
+              wp=wp, y=y, ldy=Nc, M=N * H * W, K=K, Nc=Nc, stats=stats)
+    return y, z
+
+
 def pwconv_dgrad(dy, w, wpT=None, impl=0):
     N, Nc, H, W, lddy = _g(dy, 'pwconv_dgrad')
     K = w.shape[1]
