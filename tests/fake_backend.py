@@ -50,10 +50,15 @@ class FakeBackend:
         y.copy_(_epilogue(raw, scale, shift, None, flags))
         return 0
 
-    @staticmethod
-    def _in_act(x, in_scale, in_shift, in_flags):
+    # The kernels that apply the producer's BatchNorm while reading never round the activated value to the storage
+    # type (they are more accurate than apply-then-read).  round_in_act = True emulates that rounding, which makes the
+    # hand-over paths bit-identical to the default path: a plumbing check without bf16 noise.
+    round_in_act = False
+
+    def _in_act(self, x, in_scale, in_shift, in_flags):
         z = x.float() * in_scale.view(1, -1, 1, 1) + in_shift.view(1, -1, 1, 1)
-        return z.clamp_min(0) if in_flags & RELU else z
+        z = z.clamp_min(0) if in_flags & RELU else z
+        return z.to(x.dtype).float() if self.round_in_act else z
 
     def tss_dwconv3x3_fwd_bnin(self, x, in_scale, in_shift, in_flags, w, y, N, Hi, Wi, C, stride, stats, dtype):
         raw = F.conv2d(self._in_act(x, in_scale, in_shift, in_flags), w.view(C, 1, 3, 3), None, stride, 1, 1, C)
@@ -77,7 +82,8 @@ class FakeBackend:
     def tss_pwconv_fwd(self, x, w, wp, y, M, K, Nc, ldx, ldy, scale, shift, res, ldr, flags, stats, impl, dtype):
         assert x.shape[1] == K and y.shape[1] == Nc and x.shape[0] * x.shape[2] * x.shape[3] == M
         assert x.stride(3) == ldx or x.shape[3] == 1
-        raw = F.conv2d(x.float(), w.view(Nc, K, 1, 1).float())
+        w_eff = wp.float() if (impl == 1 and wp is not None) else w.float()      # impl 1 multiplies with the bf16 pack
+        raw = F.conv2d(x.float(), w_eff.view(Nc, K, 1, 1))
         _stats(stats, raw)
         y.copy_(_epilogue(raw, scale, shift, res, flags))
         return 0

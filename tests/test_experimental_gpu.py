@@ -10,6 +10,8 @@ unvalidated kernel can never hang the default GPU suite.
 * the same for the stride-1 depthwise layers (csrc/dwconv_bwd_fused.cu; TSS_FUSE_BNAPPLY_DW=1);
 * depthwise forward / weight gradient that apply the producer's BatchNorm while reading (csrc/dwconv_bnin.cu;
   TSS_FUSE_BNIN=1);
+* pointwise forward that applies the producer's BatchNorm in its operand producer (csrc/pwconv_tc_fwd_bnin.cu;
+  TSS_FUSE_BNIN_PW=1);
 * BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu; TSS_FUSE_BNFIN=1);
 * the stem convolution and its weight gradient on tcgen05 (csrc/stem_tc.cu; TSS_STEM_TC=1);
 * the warp-private confusion-matrix kernel (csrc/metrics.cu; TSS_CM_VARIANT=1);
@@ -470,3 +472,29 @@ def test_dw_kernels_with_input_batchnorm_match_apply_then_conv(C, N, H, W, strid
     torch.cuda.synchronize()
     tol = 1e-5 if dtype == torch.float32 else 8e-3           # bf16: the unfused path rounds z to bf16 before the stencil
     assert rel(y2, y1) < tol and rel(st2, st1) < tol and rel(dw2, dw1) < tol
+
+
+@pytest.mark.parametrize('M_shape,K,Nc,relu', [((12, 48, 48), 384, 64, 1), ((12, 24, 24), 576, 96, 1), ((12, 24, 24), 768, 128, 1),
+                                               ((2, 5, 7), 576, 96, 0), ((1, 1, 3), 16, 16, 1)])
+def test_pw_forward_with_input_batchnorm_matches_apply_then_gemm(M_shape, K, Nc, relu):
+    """tss_pwconv_fwd_bnin == tss_bn_apply followed by tss_pwconv_fwd (impl 1), both on the GPU."""
+    N, H, W = M_shape
+    M = N * H * W
+    g = torch.Generator().manual_seed(K + Nc + M)
+    dt = torch.bfloat16
+    x = torch.randn(N, H, W, K, generator=g).to(dt).cuda().permute(0, 3, 1, 2)
+    sc, sh = (torch.rand(K, generator=g) + 0.5).cuda(), (torch.randn(K, generator=g) * 0.4).cuda()
+    w = (torch.randn(Nc, K, 1, 1, generator=g) / K ** 0.5).cuda()
+    wp = w.view(Nc, K).to(dt).contiguous()
+    be = _lib.backend()
+    new = lambda C: torch.zeros(N, H, W, C, dtype=dt, device='cuda').permute(0, 3, 1, 2)
+    z1, y1, z2, y2 = new(K), new(Nc), new(K), new(Nc)
+    st1, st2 = torch.zeros(2 * Nc, dtype=torch.float64, device='cuda'), torch.zeros(2 * Nc, dtype=torch.float64, device='cuda')
+    be.call('tss_bn_apply', dict(y=x, scale=sc, shift=sh, y2=None, scale2=None, shift2=None, res=None, z=z1, M=M, C=K, ldy=K, ldy2=0,
+                                 ldr=0, ldz=K, flags=relu, dtype=1))
+    be.call('tss_pwconv_fwd', dict(x=z1, w=w, wp=wp, y=y1, M=M, K=K, Nc=Nc, ldx=K, ldy=Nc, scale=None, shift=None, res=None, ldr=0,
+                                   flags=0, stats=st1, impl=1, dtype=1))
+    be.call('tss_pwconv_fwd_bnin', dict(x=x, ldx=K, in_scale=sc, in_shift=sh, in_flags=relu, z=z2, ldz=K, wp=wp, y=y2, ldy=Nc, M=M, K=K,
+                                        Nc=Nc, stats=st2))
+    torch.cuda.synchronize()
+    assert rel(z2, z1) < 1e-6 and rel(y2, y1) < 5e-3 and rel(st2, st1) < 1e-3

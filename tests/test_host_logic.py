@@ -337,7 +337,7 @@ def test_all_gates_together_train_and_eval(fake_backend, arch):
     from torch_semantic_segmentation_b200.models.contextnet import contextnet14
     from torch_semantic_segmentation_b200.nn.blocks import set_compute_dtype
     from torch_semantic_segmentation_b200.optim import FlatAdamW
-    flags = ['FUSE_BNRED_EXT', 'FUSE_BNAPPLY', 'FUSE_BNAPPLY_DW', 'FUSE_PPM', 'FUSE_BNFIN', 'FUSE_BNIN', 'STEM_TC', 'DEFER_LOGITS',
+    flags = ['FUSE_BNRED_EXT', 'FUSE_BNAPPLY', 'FUSE_BNAPPLY_DW', 'FUSE_PPM', 'FUSE_BNFIN', 'FUSE_BNIN', 'FUSE_BNIN_PW', 'STEM_TC', 'DEFER_LOGITS',
              'OWN_DROPOUT']
     keep = {f: getattr(Fn, f) for f in flags}
     factory = {'fastscnn': fastscnn, 'contextnet14': contextnet14}[arch]
@@ -502,3 +502,82 @@ def test_bottleneck_without_the_expanded_activation(fake_backend, arch):
     assert n >= 9 and b[2]['tss_dwconv3x3_wgrad_bnin'] == n
     assert b[2]['tss_bn_apply'] == a[2]['tss_bn_apply'] - n
     assert b[2]['tss_dwconv3x3_fwd'] == a[2]['tss_dwconv3x3_fwd'] - n
+
+
+@pytest.mark.parametrize('arch', ['fastscnn', 'contextnet14'])
+def test_bottleneck_hand_over_from_depthwise_to_pointwise(fake_backend, arch):
+    """functional.FUSE_BNIN_PW (off by default; bf16 tensor-core mode): conv2's BatchNorm + ReLU applied inside conv3's
+    GEMM; also together with FUSE_BNIN (conv1 -> conv2): neither activated tensor of the bottleneck is read in forward."""
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.models.contextnet import contextnet14
+    from torch_semantic_segmentation_b200.nn.blocks import set_compute_dtype
+    factory = {'fastscnn': fastscnn, 'contextnet14': contextnet14}[arch]
+    calls = {}
+    inner = fake_backend.call
+
+    def counting(name, kwargs):
+        calls[name] = calls.get(name, 0) + 1
+        return inner(name, kwargs)
+    fake_backend.call = counting
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(3, 3, 64, 96, generator=g), torch.randint(0, 19, (3, 64, 96), generator=g)
+    keep = Fn.FUSE_BNIN, Fn.FUSE_BNIN_PW
+    runs = {}
+    try:
+        for key in ((False, False), (False, True), (True, True)):
+            Fn.FUSE_BNIN, Fn.FUSE_BNIN_PW = key
+            calls.clear()
+            torch.manual_seed(0)
+            model = set_compute_dtype(_no_dropout(factory(3, 19)), torch.bfloat16, pw_impl=1).train()
+            seen = {}
+            # compared right behind the first bottleneck group: deeper in the tiny net bf16 noise is amplified (PPM bin 1)
+            (model.features[0] if arch == 'fastscnn' else model.context[3]).register_forward_hook(
+                lambda m, i, o: seen.__setitem__('f', o.detach().float()))
+            CrossEntropyLoss(ignore_index=255)(model(x), y).backward()
+            runs[key] = (seen['f'], dict(calls), [p.grad for p in model.parameters()])
+    finally:
+        Fn.FUSE_BNIN, Fn.FUSE_BNIN_PW = keep
+    base = runs[False, False]
+    for key in ((False, True), (True, True)):
+        r = runs[key]
+        assert rel(r[0], base[0]) < 6e-2                           # bf16: fma vs mul+add before a rounding, amplified downstream
+        assert all(torch.isfinite(gr).all() for gr in r[2])
+        n = r[1]['tss_pwconv_fwd_bnin']
+        assert n >= 9 and r[1]['tss_pwconv_fwd'] == base[1]['tss_pwconv_fwd'] - n
+    n = runs[False, True][1]['tss_pwconv_fwd_bnin']
+    assert runs[False, True][1]['tss_bn_apply'] == base[1]['tss_bn_apply'] - n
+    assert runs[True, True][1]['tss_bn_apply'] == base[1]['tss_bn_apply'] - n - runs[True, True][1]['tss_dwconv3x3_fwd_bnin']
+
+
+def test_single_bottleneck_with_both_hand_overs_is_tight(fake_backend):
+    """One BottleneckBlock (bf16, tensor-core pointwise mode) with FUSE_BNIN + FUSE_BNIN_PW against the default path.
+    With the emulation rounding the on-the-fly activation like a stored tensor the two are BIT-identical (plumbing);
+    without it they differ by bf16 rounding only in the forward output (the fused path is the more accurate one)."""
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.nn.blocks import BottleneckBlock, set_compute_dtype
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    keep = Fn.FUSE_BNIN, Fn.FUSE_BNIN_PW
+    runs = {}
+    try:
+        for rounding in (True, False):
+            fake_backend.round_in_act = rounding
+            for key in ((False, False), (True, True)):
+                Fn.FUSE_BNIN, Fn.FUSE_BNIN_PW = key
+                for stride, cout in ((1, 64), (2, 96)):
+                    torch.manual_seed(0)
+                    blk = set_compute_dtype(BottleneckBlock(64, cout, stride=stride), torch.bfloat16, pw_impl=1).train()
+                    FlatAdamW(blk.parameters(), lr=1e-3).zero_grad()
+                    g = torch.Generator().manual_seed(1)
+                    x = ops.as_nhwc(torch.randn(4, 64, 8, 12, generator=g).to(torch.bfloat16)).requires_grad_()
+                    out = blk(x)
+                    (out.float() * torch.randn(out.shape, generator=g)).sum().backward()
+                    runs[rounding, key, stride] = (out.detach().float(), x.grad.float(),
+                                                   torch.cat([p.grad.reshape(-1) for p in blk.parameters()]))
+    finally:
+        Fn.FUSE_BNIN, Fn.FUSE_BNIN_PW = keep
+        fake_backend.round_in_act = False
+    for stride in (1, 2):
+        a, b = runs[True, (False, False), stride], runs[True, (True, True), stride]
+        assert all(torch.equal(p, q) for p, q in zip(a, b))
+        a, b = runs[False, (False, False), stride], runs[False, (True, True), stride]
+        assert rel(b[0], a[0]) < 1e-2

@@ -11,7 +11,7 @@ TSS_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_experimental_gpu.py -
 echo "experimental tests rc=$?"; grep -E "^FAILED|passed|failed|error" gpurun_out/experimental_${TAG}.log | tail -40
 timeout 600 python tools/experimental_kernels.py > gpurun_out/experimental_kernels_${TAG}.jsonl 2> gpurun_out/experimental_kernels_${TAG}.err
 echo "experimental kernels rc=$?"; cat gpurun_out/experimental_kernels_${TAG}.jsonl | cut -c1-220
-for arm in "base" "TSS_FUSE_BNRED_EXT=1" "TSS_FUSE_BNAPPLY=1" "TSS_FUSE_PPM=1" "TSS_FUSE_BNAPPLY_DW=1" "TSS_FUSE_BNFIN=1" "TSS_FUSE_BNIN=1" "TSS_STEM_TC=1" "TSS_DEFER_LOGITS=1" "TSS_OWN_DROPOUT=1" "TSS_FUSE_BNRED_EXT=1 TSS_FUSE_BNAPPLY=1 TSS_FUSE_BNAPPLY_DW=1 TSS_FUSE_PPM=1 TSS_FUSE_BNFIN=1 TSS_FUSE_BNIN=1 TSS_STEM_TC=1 TSS_DEFER_LOGITS=1 TSS_OWN_DROPOUT=1"; do
+for arm in "base" "TSS_FUSE_BNRED_EXT=1" "TSS_FUSE_BNAPPLY=1" "TSS_FUSE_PPM=1" "TSS_FUSE_BNAPPLY_DW=1" "TSS_FUSE_BNFIN=1" "TSS_FUSE_BNIN=1" "TSS_FUSE_BNIN_PW=1" "TSS_STEM_TC=1" "TSS_DEFER_LOGITS=1" "TSS_OWN_DROPOUT=1" "TSS_FUSE_BNRED_EXT=1 TSS_FUSE_BNAPPLY=1 TSS_FUSE_BNAPPLY_DW=1 TSS_FUSE_PPM=1 TSS_FUSE_BNFIN=1 TSS_FUSE_BNIN=1 TSS_FUSE_BNIN_PW=1 TSS_STEM_TC=1 TSS_DEFER_LOGITS=1 TSS_OWN_DROPOUT=1"; do
     name=$(echo "$arm" | tr ' =' '__')
     if [ "$arm" = "base" ]; then envs=""; else envs="$arm"; fi
     env $envs timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_${TAG}_${name}.json 2> gpurun_out/ab_${TAG}_${name}.err

@@ -177,6 +177,10 @@ FUSE_BNFIN = os.environ.get('TSS_FUSE_BNFIN', '0') == '1'
 # (csrc/dwconv_bnin.cu): the expanded activation is never materialised, conv1's apply pass disappears.
 # Off unless TSS_FUSE_BNIN=1.
 FUSE_BNIN = os.environ.get('TSS_FUSE_BNIN', '0') == '1'
+# The same hand-over from conv2 (depthwise) to conv3 (tensor-core pointwise, csrc/pwconv_tc_fwd_bnin.cu): the activated
+# tensor is written once by the GEMM's operand producer (the weight gradient needs it) and never read in the forward
+# pass.  Off unless TSS_FUSE_BNIN_PW=1.
+FUSE_BNIN_PW = os.environ.get('TSS_FUSE_BNIN_PW', '0') == '1'
 
 
 class _BnLink:
@@ -230,7 +234,13 @@ class ConvBNAct(torch.autograd.Function):
             raise RuntimeError('BatchNorm2d(momentum=None) (cumulative average) is not supported')
         # per-layer scratch [statistics 2C fp64 | backward sums 2C fp32]: finalize re-zeroes all of it
         scratch = ops.layer_scratch(bn, weight.device)
-        if in_affine is not None:      # x is the RAW output of the producer; its BatchNorm (+ReLU) is applied on the fly
+        x_saved = x
+        if in_affine is not None and spec.kind == 'pw':
+            # x is the RAW output of the producer: the GEMM's operand producer applies its BatchNorm (+ReLU) and stores
+            # the activated tensor once -- that is what the weight gradient (and nothing else) reads
+            y, x_saved = ops.pwconv_fwd_bnin(x, in_affine[0], in_affine[1], in_affine[2], packed[0], scratch)
+            in_affine = None
+        elif in_affine is not None:    # depthwise: applied behind every read of the input tile, forward and wgrad
             y = ops.dwconv_fwd_bnin(x, in_affine[0], in_affine[1], in_affine[2], weight, spec.stride, scratch)
         else:
             y = conv_forward(spec, x, weight, stats=scratch, packed=packed)
@@ -265,7 +275,7 @@ class ConvBNAct(torch.autograd.Function):
         ctx.has_res = res is not None
         ctx.in_hw = (x.shape[2], x.shape[3])
         # the ReLU mask is recomputed from y in backward unless a residual was added before the ReLU
-        ctx.save_for_backward(x, weight, gamma, beta, y, z if (spec.relu and res is not None) else None, mean, rstd)
+        ctx.save_for_backward(x_saved, weight, gamma, beta, y, z if (spec.relu and res is not None) else None, mean, rstd)
         # fused BatchNorm-backward reduction: `producer` = link of the layer that made x (this conv is its only
         # consumer); `link` = what THIS layer offers to its own single consumer (no residual, per-rank statistics)
         ctx.producer = producer

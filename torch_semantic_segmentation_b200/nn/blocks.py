@@ -152,7 +152,8 @@ class _FusedConvBN:
         if use_batch_stats:
             # `defer_apply`: the enclosing block promises that the single consumer is a depthwise conv that applies
             # this layer's BatchNorm + ReLU itself (functional.FUSE_BNIN); `_tss_in_affine` is that hand-over
-            if in_affine is not None and not (spec.kind == 'dw' and spec.dilation == 1 and spec.stride in (1, 2)):
+            if in_affine is not None and not ((spec.kind == 'dw' and spec.dilation == 1 and spec.stride in (1, 2))
+                                              or (spec.kind == 'pw' and packed is not None and spec.impl == 1)):
                 raise RuntimeError('a tensor with a pending BatchNorm reached a layer that cannot apply it')
             z = Fn.ConvBNAct.apply(x, res, weight, bn.weight, bn.bias, spec, packed, producer, defer_apply, in_affine)
             if Fn.ConvBNAct.last_link is not None:
@@ -258,13 +259,22 @@ class BottleneckBlock(nn.Module):
                     and c2.stride[0] in (1, 2) and c2.in_channels % 32 == 0 and bn1.track_running_stats
                     and getattr(bn1, '_tss_sync', None) is None and getattr(self.conv2[1], '_tss_sync', None) is None)
 
+    def _defer_conv2_apply(self):
+        """conv3 (tensor-core pointwise) can apply conv2's BatchNorm + ReLU in its operand producer
+        (functional.FUSE_BNIN_PW)."""
+        c3 = self.conv3
+        return bool(Fn.FUSE_BNIN_PW and self.training and torch.is_grad_enabled() and c3.pw_impl == 1
+                    and c3.compute_dtype == torch.bfloat16 and c3[0].in_channels % 16 == 0 and c3[0].out_channels % 16 == 0
+                    and self.conv2[1].track_running_stats and getattr(self.conv2[1], '_tss_sync', None) is None
+                    and getattr(c3[1], '_tss_sync', None) is None)
+
     def forward(self, input):
         x = self.conv1(input, defer_apply=self._defer_conv1_apply())
         res = input if self.has_residual else None
         y = fused_dw_pw(self.conv2, 0, self.conv3, 0, x, self.conv2.use_activation, True, residual=res)
         if y is not None:
             return y
-        x = self.conv2(x, sole_consumer=True)
+        x = self.conv2(x, sole_consumer=True, defer_apply=self._defer_conv2_apply())
         return self.conv3(x, residual=res, relu=True, sole_consumer=True)
 
 
