@@ -39,11 +39,27 @@ class _Chain(nn.Sequential):
     reader of its predecessor's output: with functional.FUSE_BNRED_EXT the predecessor's BatchNorm-backward reduction
     is folded into each block's dgrad (the spatial branch holds the largest activations of the network)."""
 
+    @staticmethod
+    def _hands_over(dw, pw):
+        """``dw`` (depthwise block) may leave its BatchNorm + ReLU to ``pw`` (tensor-core pointwise block):
+        functional.FUSE_BNIN_PW."""
+        if not (Fn.FUSE_BNIN_PW and isinstance(dw, ConvBNBlock) and isinstance(pw, ConvBNBlock) and dw.training
+                and torch.is_grad_enabled()):
+            return False
+        c_dw, c_pw = dw[0], pw[0]
+        return bool(c_dw.groups == c_dw.in_channels and c_dw.groups > 1 and c_pw.kernel_size == (1, 1) and c_pw.groups == 1
+                    and pw.pw_impl == 1 and pw.compute_dtype == torch.bfloat16 and c_pw.in_channels % 16 == 0
+                    and c_pw.out_channels % 16 == 0 and dw[1].track_running_stats
+                    and getattr(dw[1], '_tss_sync', None) is None and getattr(pw[1], '_tss_sync', None) is None)
+
     def forward(self, input):
         x, prev = input, None
-        for module in self:
-            if isinstance(module, ConvBNBlock) and isinstance(prev, ConvBNBlock):
-                x = module(x, sole_consumer=Fn.FUSE_BNRED_EXT)
+        modules = list(self)
+        for i, module in enumerate(modules):
+            if isinstance(module, ConvBNBlock):
+                nxt = modules[i + 1] if i + 1 < len(modules) else None
+                x = module(x, sole_consumer=Fn.FUSE_BNRED_EXT and isinstance(prev, ConvBNBlock),
+                           defer_apply=self._hands_over(module, nxt))
             else:
                 x = module(x)
             prev = module

@@ -217,7 +217,13 @@ class DSConvBNBlock(nn.Sequential, _FusedConvBN):
         if y is not None:
             return y
         # `input_sole_consumer` (set by the enclosing model where it holds): nothing but this block reads `input`
-        x = self._conv_bn(0, input, False, sole_consumer=Fn.FUSE_BNRED_EXT and getattr(self, 'input_sole_consumer', False))
+        # the pointwise half can apply the depthwise half's BatchNorm in its operand producer (functional.FUSE_BNIN_PW)
+        defer = bool(Fn.FUSE_BNIN_PW and self.training and torch.is_grad_enabled() and self.pw_impl == 1
+                     and self.compute_dtype == torch.bfloat16 and self[2].in_channels % 16 == 0 and self[2].out_channels % 16 == 0
+                     and self[1].track_running_stats and getattr(self[1], '_tss_sync', None) is None
+                     and getattr(self[3], '_tss_sync', None) is None)
+        x = self._conv_bn(0, input, False, sole_consumer=Fn.FUSE_BNRED_EXT and getattr(self, 'input_sole_consumer', False),
+                          defer_apply=defer)
         return self._conv_bn(2, x, self.use_activation, sole_consumer=True)
 
 
