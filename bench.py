@@ -472,7 +472,8 @@ def main():
         'config': {'workload': WORKLOAD,
                    'global_batch': world * BATCH, 'parallelism': 'dp%d' % world,
                    'l2': 'per-step working set (>3 GB of activations) far exceeds the 126 MB L2',
-                   'launch_mode': 'cuda_graph' if use_graph else 'eager'},
+                   'launch_mode': 'cuda_graph' if use_graph else 'eager',
+                   'gates': sorted(k for k, v in os.environ.items() if k.startswith('TSS_') and v not in ('', '0'))},
         'loss': float(loss),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes,
                 'd2h_bytes_per_step': 4, 'ms_per_step': float(ems) / args.steps, 'input': e2e_input},
