@@ -9,7 +9,7 @@ LIB := torch_semantic_segmentation_b200/libtss_b200.so
 
 all: $(LIB)
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/tma.cuh $(CSRC)/augment_math.h include/tss_b200.h
+build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/tma.cuh $(CSRC)/augment_math.h $(CSRC)/tc_ptx.cuh include/tss_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
