@@ -23,7 +23,7 @@ for v in 0 1; do
     echo "TSS_CM_VARIANT=$v rc=$? $(tail -1 gpurun_out/cm_${TAG}_variant$v.json | cut -c1-300)"
 done
 # inference batch sweep with the grouped pyramid path and the tensor-core stem
-for arm in "base" "TSS_FUSE_PPM=1 TSS_STEM_TC=1" "TSS_FUSE_MIN_TILES=16" "TSS_FUSE_MIN_TILES=16 TSS_FUSE_PPM=1 TSS_STEM_TC=1"; do
+for arm in "base" "TSS_FUSE_PPM=1 TSS_STEM_TC=1"; do
     name=$(echo "$arm" | tr ' =' '__')
     if [ "$arm" = "base" ]; then envs=""; else envs="$arm"; fi
     env $envs timeout 300 python tools/bench_configs.py --config 5 --batches 1,16 > gpurun_out/inf_${TAG}_${name}.json 2> gpurun_out/inf_${TAG}_${name}.err
