@@ -498,3 +498,28 @@ def test_pw_forward_with_input_batchnorm_matches_apply_then_gemm(M_shape, K, Nc,
                                         Nc=Nc, stats=st2))
     torch.cuda.synchronize()
     assert rel(z2, z1) < 1e-6 and rel(y2, y1) < 5e-3 and rel(st2, st1) < 1e-3
+
+
+def test_graph_replays_follow_a_learning_rate_schedule():
+    """Default path (FlatAdamW + cuda_graph=True): param_groups['lr'] changed between replays reaches the device
+    (GraphedTrainStep refreshes the pinned staging buffer before each replay).  Parked here until it has run once."""
+    from oracle.golden_inputs import train_batch
+    from torch_semantic_segmentation_b200.engine import GraphedTrainStep
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    x, y = train_batch('fastscnn')
+    x, y = x.cuda(), y.cuda()
+    torch.manual_seed(0)
+    model = fastscnn(3, 19).cuda().set_compute_dtype(torch.bfloat16).train()
+    opt = FlatAdamW(model.parameters(), lr=1e-3)
+    step = GraphedTrainStep(model, opt, CrossEntropyLoss(ignore_index=255), x, y)
+    step(x, y)
+    torch.cuda.synchronize()
+    assert abs(float(opt.hyper[0]) - 1e-3) < 1e-9
+    opt.param_groups[0]['lr'] = 0.0
+    before = opt.param_arena.clone()
+    step(x, y)
+    torch.cuda.synchronize()
+    assert float(opt.hyper[0]) == 0.0
+    assert torch.equal(opt.param_arena, before)              # lr 0 and decoupled weight decay lr*wd = 0: nothing moves

@@ -581,3 +581,20 @@ def test_single_bottleneck_with_both_hand_overs_is_tight(fake_backend):
         assert all(torch.equal(p, q) for p, q in zip(a, b))
         a, b = runs[False, (False, False), stride], runs[False, (True, True), stride]
         assert rel(b[0], a[0]) < 1e-2
+
+
+def test_flat_adamw_stages_hyper_parameters_for_graph_replays(fake_backend):
+    """A scheduler changes param_groups between steps; write_host_hyper() (called before every graph replay) puts the new
+    values where the captured pinned->device copy reads them, and an eager step uses them too."""
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    torch.manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(16))
+    opt = FlatAdamW([p], lr=1e-3, weight_decay=1e-5)
+    opt.param_groups[0]['lr'] = 5e-4
+    opt.write_host_hyper()
+    assert abs(float(opt._host[0]) - 5e-4) < 1e-10 and abs(float(opt._host[4]) - 1e-5) < 1e-12
+    p.grad.fill_(1.0)
+    before = p.detach().clone()
+    opt.step()
+    assert abs(float(opt.hyper[0]) - 5e-4) < 1e-10
+    assert torch.allclose(before - p.detach(), torch.full_like(before, 5e-4), rtol=1e-2)      # first Adam step = lr * sign(g)

@@ -226,6 +226,7 @@ class GraphedTrainStep:
         self.key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype)
         # device-side input pipeline (data.DeviceTransform): the graph's inputs are the decoded uint8 frames; the
         # random draws of a step live in a small static table that is refreshed before every replay
+        self.optimizer = optimizer
         self.transform = transform
         self.geom = None
         if transform is not None:
@@ -263,6 +264,9 @@ class GraphedTrainStep:
         self.y.copy_(y, non_blocking=non_blocking)
         if self.transform is not None:
             self.geom.copy_(self.transform.draw_geometry(x.shape[0], x.shape[1], x.shape[2]), non_blocking=non_blocking)
+        refresh = getattr(self.optimizer, 'write_host_hyper', None)
+        if refresh is not None:
+            refresh()        # a learning-rate scheduler may have changed param_groups since the last replay
         self.graph.replay()
         return self.loss
 

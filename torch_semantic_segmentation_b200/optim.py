@@ -96,10 +96,16 @@ class FlatAdamW(torch.optim.Optimizer):
         wgrad_lane.join(self.grad_arena.device if self.grad_arena.is_cuda else None)
         self.grad_arena.zero_()
 
-    def _refresh_hyper(self):
+    def write_host_hyper(self):
+        """param_groups -> the pinned staging buffer of the hyper-parameters.  Host work only.  A captured
+        ``step()`` replays the pinned->device copy, so a CUDA-graph replay picks up whatever this wrote last: call it
+        before every replay (engine.GraphedTrainStep does) and learning-rate schedules keep working under graphs."""
         g = self.param_groups[0]
         self._host[0], self._host[1], self._host[2] = g['lr'], g['betas'][0], g['betas'][1]
         self._host[3], self._host[4] = g['eps'], g['weight_decay']
+
+    def _refresh_hyper(self):
+        self.write_host_hyper()
         self.hyper[:5].copy_(self._host, non_blocking=True)
 
     @torch.no_grad()
