@@ -523,3 +523,36 @@ def test_graph_replays_follow_a_learning_rate_schedule():
     torch.cuda.synchronize()
     assert float(opt.hyper[0]) == 0.0
     assert torch.equal(opt.param_arena, before)              # lr 0 and decoupled weight decay lr*wd = 0: nothing moves
+
+
+def test_one_graph_per_staging_slot_trains_like_the_copying_path():
+    """engine.SLOT_GRAPHS (TSS_SLOT_GRAPHS=1, host side only): graphs bound to the two staging slots read their batch in
+    place; six different batches through the trainer end with the same parameters as the default path."""
+    import torch_semantic_segmentation_b200.engine as E
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randn(2, 3, 64, 96, generator=g).pin_memory(), torch.randint(0, 19, (2, 64, 96), generator=g).pin_memory())
+               for _ in range(6)]
+    keep = E.SLOT_GRAPHS
+    out = {}
+    try:
+        for flag in (False, True):
+            E.SLOT_GRAPHS = flag
+            torch.manual_seed(0)
+            model = fastscnn(3, 19).cuda()
+            for m in model.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+            opt = FlatAdamW(model.parameters(), lr=1e-3)
+            trainer = E.create_segmentation_trainer(model, opt, CrossEntropyLoss(ignore_index=255), 'cuda', use_f16=True,
+                                                    logging=False, cuda_graph=True)
+            state = trainer.run(batches, max_epochs=1)
+            torch.cuda.synchronize()
+            out[flag] = (state.output, opt.param_arena.clone(), state.iteration)
+    finally:
+        E.SLOT_GRAPHS = keep
+    assert out[True][2] == out[False][2] == 6
+    # the first batch gets 3 warm-up steps + capture in both modes; the slot-1 graph is captured without warm-up steps
+    assert rel(out[True][1], out[False][1]) < 5e-3 and abs(out[True][0] - out[False][0]) < 5e-2 * abs(out[False][0])

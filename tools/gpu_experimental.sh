@@ -32,3 +32,6 @@ done
 # end-to-end leg fed with uint8 frames (device input pipeline in front of the graphed step)
 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-uint8 > gpurun_out/ab_${TAG}_e2e_uint8.json 2> gpurun_out/ab_${TAG}_e2e_uint8.err
 echo "e2e-uint8 rc=$? $(python -c "import json; d=json.loads(open('gpurun_out/ab_${TAG}_e2e_uint8.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['e2e'])" 2>&1 | tail -1)"
+# end-to-end leg with one graph per staging slot (no device-to-device copy of the batch)
+TSS_SLOT_GRAPHS=1 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_${TAG}_slot_graphs.json 2> gpurun_out/ab_${TAG}_slot_graphs.err
+echo "slot-graphs rc=$? $(python -c "import json; d=json.loads(open('gpurun_out/ab_${TAG}_slot_graphs.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['e2e'])" 2>&1 | tail -1)"

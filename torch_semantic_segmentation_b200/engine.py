@@ -12,6 +12,8 @@ pytorch-ignite and NVIDIA apex, neither of which this path needs:
 * the evaluator feeds ONE device-side confusion matrix (the reference keeps four identical
   ones, engine.py:65-72) and derives ``iou`` / ``miou`` / ``accuracy`` / ``dice`` from it.
 """
+import os
+
 import torch
 
 from . import metrics as M
@@ -159,6 +161,11 @@ def _prepare_batch(batch, device=None, non_blocking=False):
             y.to(device=device, non_blocking=non_blocking))
 
 
+# One CUDA graph per staging slot of the trainer (no device-to-device copy of the batch into the graph's inputs).
+# Host-side change only; off unless TSS_SLOT_GRAPHS=1 until it has run on a B200.
+SLOT_GRAPHS = os.environ.get('TSS_SLOT_GRAPHS', '0') == '1'
+
+
 class _StagedBatch:
     """A batch whose host->device copy was issued ahead of time on a side stream."""
 
@@ -217,12 +224,15 @@ class GraphedTrainStep:
     one graph launch, which is what a 1.1 M-parameter net needs to stay GPU-bound.  The batch is
     copied straight from (pinned) host memory into the graph's static input buffers."""
 
-    def __init__(self, model, optimizer, loss_fn, x, y, warmup=3, transform=None):
+    def __init__(self, model, optimizer, loss_fn, x, y, warmup=3, transform=None, bind=False):
         dev = x.device
-        self.x = torch.empty_like(x)
-        self.y = torch.empty_like(y)
-        self.x.copy_(x)
-        self.y.copy_(y)
+        if bind:      # the graph reads (x, y) in place: a staging slot of the trainer, refilled by its copy stream
+            self.x, self.y = x, y
+        else:
+            self.x = torch.empty_like(x)
+            self.y = torch.empty_like(y)
+            self.x.copy_(x)
+            self.y.copy_(y)
         self.key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype)
         # device-side input pipeline (data.DeviceTransform): the graph's inputs are the decoded uint8 frames; the
         # random draws of a step live in a small static table that is refreshed before every replay
@@ -260,8 +270,10 @@ class GraphedTrainStep:
         return (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype) == self.key
 
     def __call__(self, x, y, non_blocking=True):
-        self.x.copy_(x, non_blocking=non_blocking)
-        self.y.copy_(y, non_blocking=non_blocking)
+        if x is not self.x:
+            self.x.copy_(x, non_blocking=non_blocking)
+        if y is not self.y:
+            self.y.copy_(y, non_blocking=non_blocking)
         if self.transform is not None:
             self.geom.copy_(self.transform.draw_geometry(x.shape[0], x.shape[1], x.shape[2]), non_blocking=non_blocking)
         refresh = getattr(self.optimizer, 'write_host_hyper', None)
@@ -342,12 +354,21 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
         model.train()
         staged = batch if isinstance(batch, _StagedBatch) else None
         if cuda_graph:
-            g = graphed.get('step')
+            # SLOT_GRAPHS (gated): one captured graph per staging slot, reading the slot in place -- no device-to-device
+            # copy of the batch into the graph's inputs (141 MB read + written per step at the benchmark shape)
+            key = ('step', staged.slot) if (SLOT_GRAPHS and staged is not None) else 'step'
+            g = graphed.get(key)
             if g is None:
                 xd, yd = fetch(batch)
-                graphed['step'] = g = GraphedTrainStep(model, optimizer, loss_fn, xd, yd, transform=transform)
+                first = not graphed
+                graphed[key] = g = GraphedTrainStep(model, optimizer, loss_fn, xd, yd, transform=transform,
+                                                    warmup=3 if first else 0, bind=key != 'step')
+                if not first:
+                    g.graph.replay()         # capturing does not execute: this is the step on the current batch
                 if staged is not None:
                     stager.release(staged)
+                if SLOT_GRAPHS:
+                    _trainer.prefetch_next()
                 return g.loss.item()
             x, y = fetch(batch) if staged is not None else batch
             if not g.matches(x, y):
