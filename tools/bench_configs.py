@@ -62,7 +62,10 @@ def config3(args, rank, world, device):
     y = torch.randint(0, CLASSES, (batch, H, W), generator=g, device=device)
     y[torch.rand(batch, H, W, generator=g, device=device) < 0.1] = 255
     model.train()
-    step = GraphedTrainStep(model, opt, CrossEntropyLoss(ignore_index=255), x, y)
+    loss_fn = CrossEntropyLoss(ignore_index=255)
+    from torch_semantic_segmentation_b200.functional import enable_deferred_logits
+    enable_deferred_logits(model, loss_fn)         # gated (TSS_DEFER_LOGITS=1), like bench.py
+    step = GraphedTrainStep(model, opt, loss_fn, x, y)
     for _ in range(3):
         step.graph.replay()
     ms = timed(step.graph.replay, args.steps, world, device)
@@ -70,7 +73,8 @@ def config3(args, rank, world, device):
         print(json.dumps({'config': 3, 'metric': 'contextnet14_train_images_per_sec', 'unit': 'img/s',
                           'value': world * batch * args.steps / (ms / 1e3), 'ms_per_step': ms / args.steps,
                           'n_gpus': world, 'per_gpu_batch': batch, 'resolution': [H, W], 'dtype': 'bf16',
-                          'loss': float(step.loss), 'kernels_per_step': step.kernels_per_step}))
+                          'loss': float(step.loss), 'kernels_per_step': step.kernels_per_step,
+                          'gates': sorted(k for k, v in os.environ.items() if k.startswith('TSS_') and v not in ('', '0'))}))
 
 
 def synth_map(i, device):
