@@ -186,6 +186,13 @@ int tss_stem3x3s2_fwd_tc(const float* x, const float* w, void* y, int N, int H, 
  * reduction dimension. */
 int tss_stem3x3s2_wgrad_tc(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout,
                            void* stream);
+/* the same with the stem's BatchNorm-backward APPLY folded into the operand producer: dz is the gradient after the
+ * stem's BN/ReLU, y its raw conv output, sums[2*Cout] the finished reduction (flags&TSS_EPI_RELU: mask recomputed from
+ * y).  dy is never materialised (the stem has no input gradient, the weight gradient is its only reader);
+ * dgamma += sums[Cout+c], dbeta += sums[c]. */
+int tss_stem3x3s2_wgrad_tc_bn(const float* x, const void* dz, const void* y, const float* mean, const float* rstd,
+                              const float* gamma, const float* beta, const float* sums, int flags, int64_t count,
+                              float* dw, float* dgamma, float* dbeta, int N, int H, int W, int Cout, void* stream);
 int tss_stem3x3s2_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout,
                         int dtype, void* stream);
 /* Dense 3x3, stride 1, padding 1, C -> Cout between equal-sized NHWC maps: replaces

@@ -340,6 +340,13 @@ class FakeBackend:
         dw += nngrad.conv2d_weight(x.bfloat16().float(), dw.shape, dy.float(), 2, 1)          # image rounded to bf16
         return 0
 
+    def tss_stem3x3s2_wgrad_tc_bn(self, x, dz, y, mean, rstd, gamma, beta, sums, flags, count, dw, dgamma, dbeta, N, H, W, Cout):
+        dy = torch.empty_like(dz)
+        Ho, Wo = dz.shape[2], dz.shape[3]
+        self.tss_bn_bwd_apply(dz, None, y, mean, rstd, gamma, beta, sums, dy, None, dgamma, dbeta, N * Ho * Wo, count, Cout, Cout, 0,
+                              Cout, Cout, 0, flags, 1)
+        return self.tss_stem3x3s2_wgrad_tc(x, dy, dw, N, H, W, Cout)
+
     def tss_stem3x3s2_wgrad(self, x, dy, dw, N, H, W, Cout, dtype):
         dw += nngrad.conv2d_weight(x, dw.shape, dy.float(), 2, 1)
         return 0

@@ -556,3 +556,30 @@ def test_one_graph_per_staging_slot_trains_like_the_copying_path():
     assert out[True][2] == out[False][2] == 6
     # the first batch gets 3 warm-up steps + capture in both modes; the slot-1 graph is captured without warm-up steps
     assert rel(out[True][1], out[False][1]) < 5e-3 and abs(out[True][0] - out[False][0]) < 5e-2 * abs(out[False][0])
+
+
+@pytest.mark.parametrize('N,H,W', [(2, 64, 96), (1, 32, 300), (12, 768, 768)])
+def test_stem_wgrad_with_bn_apply_matches_apply_then_wgrad(N, H, W):
+    """tss_stem3x3s2_wgrad_tc_bn == tss_bn_bwd_apply followed by tss_stem3x3s2_wgrad_tc, both on the GPU."""
+    g = torch.Generator().manual_seed(H + W)
+    x = torch.randn(N, 3, H, W, generator=g).cuda()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    mk = lambda: torch.randn(N, Ho, Wo, 32, generator=g).to(torch.bfloat16).cuda().permute(0, 3, 1, 2)
+    dz, y = mk(), mk()
+    mean, rstd = (torch.randn(32, generator=g) * 0.2).cuda(), (torch.rand(32, generator=g) + 0.5).cuda()
+    gamma, beta = (torch.rand(32, generator=g) + 0.5).cuda(), (torch.randn(32, generator=g) * 0.3).cuda()
+    M = N * Ho * Wo
+    be = _lib.backend()
+    sums = torch.zeros(64, device='cuda')
+    be.call('tss_bn_bwd_reduce', dict(dz=dz, z=None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, M=M, C=32, lddz=32,
+                                      ldz=0, ldy=32, flags=1, dtype=1))
+    dy = torch.zeros(N, Ho, Wo, 32, dtype=torch.bfloat16, device='cuda').permute(0, 3, 1, 2)
+    dw1, dw2 = torch.zeros(32, 3, 3, 3, device='cuda'), torch.zeros(32, 3, 3, 3, device='cuda')
+    dg1, db1, dg2, db2 = (torch.zeros(32, device='cuda') for _ in range(4))
+    be.call('tss_bn_bwd_apply', dict(dz=dz, z=None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, dy=dy, dres=None,
+                                     dgamma=dg1, dbeta=db1, M=M, count=M, C=32, lddz=32, ldz=0, ldy=32, lddy=32, lddres=0, flags=1, dtype=1))
+    be.call('tss_stem3x3s2_wgrad_tc', dict(x=x, dy=dy, dw=dw1, N=N, H=H, W=W, Cout=32))
+    be.call('tss_stem3x3s2_wgrad_tc_bn', dict(x=x, dz=dz, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, flags=1, count=M,
+                                              dw=dw2, dgamma=dg2, dbeta=db2, N=N, H=H, W=W, Cout=32))
+    torch.cuda.synchronize()
+    assert rel(dw2, dw1) < 5e-3 and rel(dg2, dg1) < 1e-6 and rel(db2, db1) < 1e-6

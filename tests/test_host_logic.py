@@ -337,7 +337,7 @@ def test_all_gates_together_train_and_eval(fake_backend, arch):
     from torch_semantic_segmentation_b200.models.contextnet import contextnet14
     from torch_semantic_segmentation_b200.nn.blocks import set_compute_dtype
     from torch_semantic_segmentation_b200.optim import FlatAdamW
-    flags = ['FUSE_BNRED_EXT', 'FUSE_BNAPPLY', 'FUSE_BNAPPLY_DW', 'FUSE_PPM', 'FUSE_BNFIN', 'FUSE_BNIN', 'FUSE_BNIN_PW', 'STEM_TC', 'DEFER_LOGITS',
+    flags = ['FUSE_BNRED_EXT', 'FUSE_BNAPPLY', 'FUSE_BNAPPLY_DW', 'FUSE_PPM', 'FUSE_BNFIN', 'FUSE_BNIN', 'FUSE_BNIN_PW', 'STEM_TC', 'STEM_BWD_FUSED', 'DEFER_LOGITS',
              'OWN_DROPOUT']
     keep = {f: getattr(Fn, f) for f in flags}
     factory = {'fastscnn': fastscnn, 'contextnet14': contextnet14}[arch]
@@ -598,3 +598,35 @@ def test_flat_adamw_stages_hyper_parameters_for_graph_replays(fake_backend):
     opt.step()
     assert abs(float(opt.hyper[0]) - 5e-4) < 1e-10
     assert torch.allclose(before - p.detach(), torch.full_like(before, 5e-4), rtol=1e-2)      # first Adam step = lr * sign(g)
+
+
+def test_stem_backward_without_the_dy_tensor(fake_backend):
+    """functional.STEM_BWD_FUSED (with STEM_TC; off by default): the stem's BatchNorm-backward apply happens inside the
+    weight-gradient kernel; identical gradients (emulated ABI), one bn_bwd_apply less."""
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.nn.blocks import set_compute_dtype
+    calls = {}
+    inner = fake_backend.call
+
+    def counting(name, kwargs):
+        calls[name] = calls.get(name, 0) + 1
+        return inner(name, kwargs)
+    fake_backend.call = counting
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(2, 3, 64, 64, generator=g), torch.randint(0, 19, (2, 64, 64), generator=g)
+    keep = Fn.STEM_TC, Fn.STEM_BWD_FUSED
+    runs = {}
+    try:
+        for fused in (False, True):
+            Fn.STEM_TC, Fn.STEM_BWD_FUSED = True, fused
+            calls.clear()
+            torch.manual_seed(0)
+            model = set_compute_dtype(_no_dropout(fastscnn(3, 19)), torch.bfloat16, pw_impl=1).train()
+            CrossEntropyLoss(ignore_index=255)(model(x), y).backward()
+            runs[fused] = ({k: p.grad.clone() for k, p in model.named_parameters()}, dict(calls))
+    finally:
+        Fn.STEM_TC, Fn.STEM_BWD_FUSED = keep
+    for k in runs[False][0]:
+        assert torch.equal(runs[True][0][k], runs[False][0][k]), k
+    assert runs[True][1]['tss_stem3x3s2_wgrad_tc_bn'] == 1 and 'tss_stem3x3s2_wgrad_tc' not in runs[True][1]
+    assert runs[True][1]['tss_bn_bwd_apply'] == runs[False][1]['tss_bn_bwd_apply'] - 1

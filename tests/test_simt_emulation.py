@@ -517,3 +517,27 @@ def test_pw_forward_with_the_input_batchnorm_on_the_tcgen05_emulation(emulated, 
     assert rel(outs['emu'][1], outs['ref'][1]) < 1e-4            # z: fma vs mul+add before the bf16 rounding
     assert rel(outs['emu'][0], outs['ref'][0]) < 5e-3
     assert rel(outs['emu'][2], outs['ref'][2]) < 1e-3
+
+
+@pytest.mark.parametrize('N,H,W,relu', [(2, 16, 24, 1), (1, 32, 300, 1), (1, 7, 9, 0), (3, 2, 2, 1)])
+def test_stem_weight_gradient_with_bn_apply_on_the_tcgen05_emulation(emulated, N, H, W, relu):
+    """csrc/stem_tc.cu, wgrad with the stem's BatchNorm-backward apply in the operand producer (no dy tensor)."""
+    g = torch.Generator().manual_seed(H * W + relu)
+    x = torch.randn(N, 3, H, W, generator=g)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dz, y = _nhwc(N, 32, Ho, Wo, g, torch.bfloat16), _nhwc(N, 32, Ho, Wo, g, torch.bfloat16)
+    mean, rstd = torch.randn(32, generator=g) * 0.2, torch.rand(32, generator=g) + 0.5
+    gamma, beta = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.3
+    M = N * Ho * Wo
+    fake = FakeBackend()
+    sums = torch.zeros(64)
+    fake.call('tss_bn_bwd_reduce', dict(dz=dz, z=None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, M=M, C=32, lddz=32,
+                                        ldz=0, ldy=32, flags=relu, dtype=1))
+    outs = {}
+    for name, be in (('ref', fake), ('emu', emulated)):
+        dw, dga, dbe = torch.full((32, 3, 3, 3), 0.25), torch.ones(32), torch.ones(32)
+        be.call('tss_stem3x3s2_wgrad_tc_bn', dict(x=x, dz=dz, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, flags=relu,
+                                                  count=M, dw=dw, dgamma=dga, dbeta=dbe, N=N, H=H, W=W, Cout=32))
+        outs[name] = (dw - 0.25, dga, dbe)
+    assert rel(outs['emu'][0], outs['ref'][0]) < 5e-3
+    assert rel(outs['emu'][1], outs['ref'][1]) < 1e-6 and rel(outs['emu'][2], outs['ref'][2]) < 1e-6

@@ -11,7 +11,7 @@ TSS_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_experimental_gpu.py -
 echo "experimental tests rc=$?"; grep -E "^FAILED|passed|failed|error" gpurun_out/experimental_${TAG}.log | tail -40
 timeout 600 python tools/experimental_kernels.py > gpurun_out/experimental_kernels_${TAG}.jsonl 2> gpurun_out/experimental_kernels_${TAG}.err
 echo "experimental kernels rc=$?"; cat gpurun_out/experimental_kernels_${TAG}.jsonl | cut -c1-220
-for arm in "base" "TSS_FUSE_BNRED_EXT=1" "TSS_FUSE_BNAPPLY=1" "TSS_FUSE_PPM=1" "TSS_FUSE_BNAPPLY_DW=1" "TSS_FUSE_BNFIN=1" "TSS_FUSE_BNIN=1" "TSS_FUSE_BNIN_PW=1" "TSS_STEM_TC=1" "TSS_DEFER_LOGITS=1" "TSS_OWN_DROPOUT=1" "TSS_FUSE_BNRED_EXT=1 TSS_FUSE_BNAPPLY=1 TSS_FUSE_BNAPPLY_DW=1 TSS_FUSE_PPM=1 TSS_FUSE_BNFIN=1 TSS_FUSE_BNIN=1 TSS_FUSE_BNIN_PW=1 TSS_STEM_TC=1 TSS_DEFER_LOGITS=1 TSS_OWN_DROPOUT=1"; do
+for arm in "base" "TSS_FUSE_BNRED_EXT=1" "TSS_FUSE_BNAPPLY=1" "TSS_FUSE_PPM=1" "TSS_FUSE_BNAPPLY_DW=1" "TSS_FUSE_BNFIN=1" "TSS_FUSE_BNIN=1" "TSS_FUSE_BNIN_PW=1" "TSS_STEM_TC=1" "TSS_STEM_TC=1 TSS_STEM_BWD_FUSED=1" "TSS_DEFER_LOGITS=1" "TSS_OWN_DROPOUT=1" "TSS_FUSE_BNRED_EXT=1 TSS_FUSE_BNAPPLY=1 TSS_FUSE_BNAPPLY_DW=1 TSS_FUSE_PPM=1 TSS_FUSE_BNFIN=1 TSS_FUSE_BNIN=1 TSS_FUSE_BNIN_PW=1 TSS_STEM_TC=1 TSS_STEM_BWD_FUSED=1 TSS_DEFER_LOGITS=1 TSS_OWN_DROPOUT=1"; do
     name=$(echo "$arm" | tr ' =' '__')
     if [ "$arm" = "base" ]; then envs=""; else envs="$arm"; fi
     env $envs timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_${TAG}_${name}.json 2> gpurun_out/ab_${TAG}_${name}.err
@@ -36,7 +36,7 @@ echo "e2e-uint8 rc=$? $(python -c "import json; d=json.loads(open('gpurun_out/ab
 TSS_SLOT_GRAPHS=1 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_${TAG}_slot_graphs.json 2> gpurun_out/ab_${TAG}_slot_graphs.err
 echo "slot-graphs rc=$? $(python -c "import json; d=json.loads(open('gpurun_out/ab_${TAG}_slot_graphs.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['e2e'])" 2>&1 | tail -1)"
 # ContextNet-14 training step (BASELINE.json configs[2], 8 x 1024 x 2048 per GPU): default vs every training gate
-ALL="TSS_FUSE_BNRED_EXT=1 TSS_FUSE_BNAPPLY=1 TSS_FUSE_BNAPPLY_DW=1 TSS_FUSE_BNFIN=1 TSS_FUSE_BNIN=1 TSS_FUSE_BNIN_PW=1 TSS_STEM_TC=1 TSS_DEFER_LOGITS=1 TSS_OWN_DROPOUT=1"
+ALL="TSS_FUSE_BNRED_EXT=1 TSS_FUSE_BNAPPLY=1 TSS_FUSE_BNAPPLY_DW=1 TSS_FUSE_BNFIN=1 TSS_FUSE_BNIN=1 TSS_FUSE_BNIN_PW=1 TSS_STEM_TC=1 TSS_STEM_BWD_FUSED=1 TSS_DEFER_LOGITS=1 TSS_OWN_DROPOUT=1"
 for arm in "base" "$ALL"; do
     if [ "$arm" = "base" ]; then envs=""; name=base; else envs="$arm"; name=all; fi
     env $envs timeout 400 python tools/bench_configs.py --config 3 --steps 10 > gpurun_out/cn_${TAG}_${name}.json 2> gpurun_out/cn_${TAG}_${name}.err

@@ -167,7 +167,10 @@ constexpr int kWgPix = 64;                      // pixels per k-block
 
 __global__ void __launch_bounds__(kWgThreads)
 stem_tc_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw, int N, int H, int W,
-                     int Ho, int Wo, int chunks_w, int64_t nblocks) {
+                     int Ho, int Wo, int chunks_w, int64_t nblocks, const bf16* __restrict__ yraw,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ sums, int relu, float inv_count,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
     TSS_DYN_SMEM(uint8_t, smem_raw);
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                   // [kWgStages][128 rows][128 B]
@@ -196,6 +199,26 @@ stem_tc_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, f
     tc_fence_after();
     pdl_wait();
     const uint32_t tmem_base = *tmem_slot;
+    // yraw != nullptr: `dy` holds the gradient AFTER the stem's BatchNorm/ReLU and the BatchNorm-backward apply happens
+    // here, while the operand is built: dy_c = A*g + B*y + D per output channel (pwconv_tc_bwd.cu), SH for the mask
+    float cA[2] = {1.f, 1.f}, cSH[2] = {0.f, 0.f}, cB[2] = {0.f, 0.f}, cD[2] = {0.f, 0.f};
+    if (yraw != nullptr && warp < 4) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = ((int)threadIdx.x + 128 * h) >> 3;      // the output channel of this thread's chunk task h
+            const float mu = __ldg(mean + c), rs = __ldg(rstd + c);
+            cA[h] = (gamma != nullptr ? __ldg(gamma + c) : 1.f) * rs;
+            cSH[h] = (beta != nullptr ? __ldg(beta + c) : 0.f) - mu * cA[h];
+            const float a1 = __ldg(sums + c), a2 = __ldg(sums + CO + c);
+            const float k2 = cA[h] * a2 * inv_count;
+            cB[h] = -rs * k2;
+            cD[h] = fmaf(mu * rs, k2, -cA[h] * a1 * inv_count);
+            if (blockIdx.x == 0 && (threadIdx.x & 7) == 0) {      // one thread per channel, first CTA only
+                if (dbeta != nullptr) dbeta[c] += a1;
+                if (dgamma != nullptr) dgamma[c] += a2;
+            }
+        }
+    }
     // this CTA's contiguous share of the k-blocks
     const int64_t per = (nblocks + gridDim.x - 1) / gridDim.x;
     const int64_t kb0 = (int64_t)blockIdx.x * per;
@@ -222,9 +245,23 @@ stem_tc_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, f
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
                     const int w0 = wo0 + pc * 8 + e;
-                    const bf16* src = dy + (((int64_t)n * Ho + ho) * Wo + w0) * CO + row;
-                    const uint16_t lo = w0 < Wo ? __ldg(reinterpret_cast<const unsigned short*>(src)) : (uint16_t)0;
-                    const uint16_t hi = w0 + 1 < Wo ? __ldg(reinterpret_cast<const unsigned short*>(src + CO)) : (uint16_t)0;
+                    const int64_t off = (((int64_t)n * Ho + ho) * Wo + w0) * CO + row;
+                    uint16_t lo = w0 < Wo ? __ldg(reinterpret_cast<const unsigned short*>(dy + off)) : (uint16_t)0;
+                    uint16_t hi = w0 + 1 < Wo ? __ldg(reinterpret_cast<const unsigned short*>(dy + off + CO)) : (uint16_t)0;
+                    if (yraw != nullptr) {
+                        float v[2];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const bool in = w0 + q < Wo;
+                            const float g = __uint_as_float((uint32_t)(q ? hi : lo) << 16);
+                            const float yy = in ? __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(yraw + off + q * CO)) << 16) : 0.f;
+                            const float gg = (relu && !(fmaf(yy, cA[h], cSH[h]) > 0.f)) ? 0.f : g;
+                            v[q] = in ? fmaf(cA[h], gg, fmaf(cB[h], yy, cD[h])) : 0.f;
+                        }
+                        const uint32_t p2 = pack_bf16x2(v[0], v[1]);
+                        lo = (uint16_t)(p2 & 0xffffu);
+                        hi = (uint16_t)(p2 >> 16);
+                    }
                     pk[e >> 1] = (uint32_t)lo | ((uint32_t)hi << 16);
                 }
                 a_chunk[h] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -322,7 +359,29 @@ extern "C" int tss_stem3x3s2_wgrad_tc(const float* x, const void* dy, float* dw,
     if (grid > nblocks) grid = nblocks;
     const size_t smem = 1024 + (size_t)kWgStages * (kABytes + kBBytes) + (2 * kWgStages + 1) * 8 + 8;
     tss_launch(stem_tc_wgrad_kernel, (unsigned)grid, kWgThreads, smem, (cudaStream_t)stream, x, (const bf16*)dy, dw, N, H, W, Ho, Wo,
-               chunks_w, nblocks);
+               chunks_w, nblocks, (const bf16*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr,
+               (const float*)nullptr, (const float*)nullptr, 0, 0.f, (float*)nullptr, (float*)nullptr);
     TSS_LAUNCH_CHECK("stem3x3s2_wgrad_tc");
+    return TSS_OK;
+}
+
+extern "C" int tss_stem3x3s2_wgrad_tc_bn(const float* x, const void* dz, const void* y, const float* mean, const float* rstd,
+                                         const float* gamma, const float* beta, const float* sums, int flags, int64_t count,
+                                         float* dw, float* dgamma, float* dbeta, int N, int H, int W, int Cout, void* stream) {
+    TSS_REQUIRE(N > 0 && H > 0 && W > 0, "stem3x3s2_wgrad_tc_bn: empty input");
+    TSS_REQUIRE(Cout == CO, "stem3x3s2_wgrad_tc_bn: Cout=%d unsupported (only %d)", Cout, CO);
+    TSS_REQUIRE(dz != nullptr && y != nullptr && mean != nullptr && rstd != nullptr && sums != nullptr,
+                "stem3x3s2_wgrad_tc_bn: missing BatchNorm operands");
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    if (count <= 0) count = (int64_t)N * Ho * Wo;
+    const int chunks_w = (Wo + kWgPix - 1) / kWgPix;
+    const int64_t nblocks = (int64_t)N * Ho * chunks_w;
+    int64_t grid = (int64_t)tss_num_sms() * 2;
+    if (grid > nblocks) grid = nblocks;
+    const size_t smem = 1024 + (size_t)kWgStages * (kABytes + kBBytes) + (2 * kWgStages + 1) * 8 + 8;
+    tss_launch(stem_tc_wgrad_kernel, (unsigned)grid, kWgThreads, smem, (cudaStream_t)stream, x, (const bf16*)dz, dw, N, H, W, Ho, Wo,
+               chunks_w, nblocks, (const bf16*)y, mean, rstd, gamma, beta, sums, flags & TSS_EPI_RELU, (float)(1.0 / (double)count),
+               dgamma, dbeta);
+    TSS_LAUNCH_CHECK("stem3x3s2_wgrad_tc_bn");
     return TSS_OK;
 }

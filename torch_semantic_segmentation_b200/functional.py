@@ -148,6 +148,9 @@ def conv_forward(spec, x, weight, scale=None, shift=None, res=None, relu=False, 
 # kernel (864 FMAs per output pixel).  Built, checked on the SIMT emulation, not yet run on a B200: off unless
 # TSS_STEM_TC=1.
 STEM_TC = os.environ.get('TSS_STEM_TC', '0') == '1'
+# With the tensor-core stem: its BatchNorm-backward apply inside the weight gradient's operand producer -- the largest
+# activation of the net (32 channels at 1/2 resolution) is not rewritten as dy.  Off unless TSS_STEM_BWD_FUSED=1.
+STEM_BWD_FUSED = os.environ.get('TSS_STEM_BWD_FUSED', '0') == '1'
 
 # Training: fold the BatchNorm-backward reduction of a producer layer into the dgrad epilogue of its single
 # consumer (csrc/pwconv_tc_bnred.cu, csrc/dwconv_bnred.cu): one full read of (dz, y) and one launch less per
@@ -325,6 +328,26 @@ class ConvBNAct(torch.autograd.Function):
                 ops.pwconv_wgrad(x, dy, dw, impl=1)
             grad_ready(*ctx.params)
             return (dx, None, None if gw is not None else dw, None if gg is not None else gg_out,
+                    None if gb is not None else gb_out, None, None, None, None, None)
+        if (STEM_TC and STEM_BWD_FUSED and spec.kind == 'stem' and dz.dtype == torch.bfloat16 and C == 32 and not ctx.has_res
+                and ctx.sync[0] == 1 and not ctx.needs_input_grad[0] and ops.geom(dz)[4] == C):
+            # the stem has no input gradient: BatchNorm-backward apply + weight gradient in one kernel, no dy tensor
+            if link is not None and link.reduced:
+                sums, mask = link.sums, False
+            else:
+                sums = ctx.scratch[2 * C:].view(torch.float32)
+                if spec.bn._tss_dirty or ctx.scratch is not getattr(spec.bn, '_tss_scratch', None):
+                    sums = ops.zeros_f32(2 * C, weight.device)
+                spec.bn._tss_dirty = True
+                ops.bn_backward_reduce(dz, y, mean, rstd, gamma, beta, spec.relu, sums)
+                mask = spec.relu
+            fused = lambda: ops.stem_wgrad_tc_bn(x, dz, y, mean, rstd, gamma, beta, sums, mask, dw, dgamma=gg_out, dbeta=gb_out)
+            if gw is not None:
+                wgrad_lane.run(dz.device, fused, x, dz, y, sums)
+            else:
+                fused()
+            grad_ready(*ctx.params)
+            return (None, None, None if gw is not None else dw, None if gg is not None else gg_out,
                     None if gb is not None else gb_out, None, None, None, None, None)
         if (FUSE_BNAPPLY_DW and spec.kind == 'dw' and prod is not None and spec.stride == 1 and spec.dilation == 1
                 and C % 32 == 0 and not ctx.has_res and ctx.sync[0] == 1 and ctx.needs_input_grad[0]

@@ -302,6 +302,17 @@ def stem_wgrad_tc(x, dy, dw):
     _lib.call('tss_stem3x3s2_wgrad_tc', x=x, dy=dy, dw=dw, N=N, H=H, W=W, Cout=dy.shape[1])
 
 
+def stem_wgrad_tc_bn(x, dz, y, mean, rstd, gamma, beta, sums, relu, dw, dgamma=None, dbeta=None):
+    """Stem weight gradient on the tensor cores with the BatchNorm-backward apply folded in (no dy tensor)."""
+    N, _, H, W = x.shape
+    C = dz.shape[1]
+    if dz.dtype != torch.bfloat16 or _g(dz, 'stem_wgrad_tc_bn')[4] != C or _g(y, 'stem_wgrad_tc_bn')[4] != C:
+        raise RuntimeError('stem_wgrad_tc_bn: expects dense bfloat16 NHWC tensors')
+    _lib.call('tss_stem3x3s2_wgrad_tc_bn', x=x, dz=dz, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums,
+              flags=_flags(relu), count=dz.shape[0] * dz.shape[2] * dz.shape[3], dw=dw, dgamma=dgamma, dbeta=dbeta, N=N, H=H, W=W,
+              Cout=C)
+
+
 def stem_wgrad(x, dy, dw):
     N, _, H, W = x.shape
     _lib.call('tss_stem3x3s2_wgrad', x=x, dy=dy, dw=dw, N=N, H=H, W=W, Cout=dy.shape[1],
