@@ -52,6 +52,19 @@ class _Chain(nn.Sequential):
                     and c_pw.out_channels % 16 == 0 and dw[1].track_running_stats
                     and getattr(dw[1], '_tss_sync', None) is None and getattr(pw[1], '_tss_sync', None) is None)
 
+    @staticmethod
+    def _hands_over_to_dw(blk, dw):
+        """``blk`` (any conv+BN block) may leave its BatchNorm + ReLU to the depthwise block ``dw`` that follows:
+        functional.FUSE_BNIN."""
+        if not (Fn.FUSE_BNIN and isinstance(blk, ConvBNBlock) and isinstance(dw, ConvBNBlock) and blk.training
+                and torch.is_grad_enabled()):
+            return False
+        c = dw[0]
+        return bool(c.groups == c.in_channels and c.groups > 1 and c.kernel_size == (3, 3) and c.dilation[0] == 1
+                    and c.stride[0] in (1, 2) and (c.in_channels % 32 == 0 or c.in_channels % 48 == 0)
+                    and blk[1].track_running_stats and getattr(blk[1], '_tss_sync', None) is None
+                    and getattr(dw[1], '_tss_sync', None) is None)
+
     def forward(self, input):
         x, prev = input, None
         modules = list(self)
@@ -59,7 +72,7 @@ class _Chain(nn.Sequential):
             if isinstance(module, ConvBNBlock):
                 nxt = modules[i + 1] if i + 1 < len(modules) else None
                 x = module(x, sole_consumer=Fn.FUSE_BNRED_EXT and isinstance(prev, ConvBNBlock),
-                           defer_apply=self._hands_over(module, nxt))
+                           defer_apply=self._hands_over(module, nxt) or self._hands_over_to_dw(module, nxt))
             else:
                 x = module(x)
             prev = module

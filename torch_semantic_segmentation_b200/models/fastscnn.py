@@ -13,7 +13,7 @@ from torch import nn
 
 from .. import ops
 from .. import functional as Fn
-from ..nn.blocks import (Conv2dBlock, DWConv2dBlock, DSConv2dBlock, BottleneckBlock, ClassScores, Dropout,
+from ..nn.blocks import (Conv2dBlock, DWConv2dBlock, DSConv2dBlock, DSConvBNBlock, BottleneckBlock, ClassScores, Dropout,
                          set_compute_dtype)
 
 __all__ = ['FastSCNN', 'fastscnn', 'Classifier']
@@ -28,7 +28,7 @@ class FastSCNN(nn.Module):
 
     def __init__(self, in_channels, out_channels):
         super().__init__()
-        self.downsample = nn.Sequential(
+        self.downsample = _DownsampleChain(
             Conv2dBlock(in_channels, 32, kernel_size=3, padding=1, stride=2),
             DSConv2dBlock(32, 48, kernel_size=3, padding=1, stride=2),
             DSConv2dBlock(48, 64, kernel_size=3, padding=1, stride=2),
@@ -67,6 +67,27 @@ class FastSCNN(nn.Module):
         classes = self.classifier(fusion)
         classes = ops.as_nhwc(classes)
         return Fn.model_output(self, classes, classes.shape[2] * 8, classes.shape[3] * 8)
+
+
+class _DownsampleChain(nn.Sequential):
+    """``nn.Sequential`` (same child indices and state_dict keys) for learning-to-downsample, in which every block is the
+    only reader of its predecessor's output: with functional.FUSE_BNIN a block leaves its BatchNorm + ReLU to the
+    depthwise conv that follows (the stem's output -- 32 channels at 1/2 resolution, the largest activation of the
+    network -- is then never materialised).  Forward hooks on the chain as a whole see the last block's real output."""
+
+    def forward(self, input):
+        x = input
+        modules = list(self)
+        for i, module in enumerate(modules):
+            nxt = modules[i + 1] if i + 1 < len(modules) else None
+            last_bn = module[3] if isinstance(module, DSConvBNBlock) else module[1]      # the BatchNorm that would be deferred
+            defer = bool(Fn.FUSE_BNIN and isinstance(nxt, DSConvBNBlock) and nxt.takes_pending_input()
+                         and last_bn.track_running_stats and getattr(last_bn, '_tss_sync', None) is None)
+            if isinstance(module, DSConvBNBlock):
+                x = module(x, defer_out=defer)
+            else:
+                x = module(x, defer_apply=defer)
+        return x
 
 
 class FeatureFusionModule(nn.Module):

@@ -212,7 +212,15 @@ class DSConvBNBlock(nn.Sequential, _FusedConvBN):
         self.use_activation = use_activation
         self._init_fused()
 
-    def forward(self, input):
+    def takes_pending_input(self):
+        """This block's depthwise half can apply a producer's BatchNorm + ReLU while reading (functional.FUSE_BNIN)."""
+        c = self[0]
+        return bool(self.training and torch.is_grad_enabled() and c.dilation[0] == 1 and c.stride[0] in (1, 2)
+                    and (c.in_channels % 32 == 0 or c.in_channels % 48 == 0) and getattr(self[1], '_tss_sync', None) is None)
+
+    def forward(self, input, defer_out=False):
+        """``defer_out``: the enclosing chain promises that the only reader of this block's output is a depthwise conv
+        that applies the pointwise half's BatchNorm + ReLU itself."""
         y = fused_dw_pw(self, 0, self, 2, input, False, self.use_activation)
         if y is not None:
             return y
@@ -224,7 +232,7 @@ class DSConvBNBlock(nn.Sequential, _FusedConvBN):
                      and getattr(self[3], '_tss_sync', None) is None)
         x = self._conv_bn(0, input, False, sole_consumer=Fn.FUSE_BNRED_EXT and getattr(self, 'input_sole_consumer', False),
                           defer_apply=defer)
-        return self._conv_bn(2, x, self.use_activation, sole_consumer=True)
+        return self._conv_bn(2, x, self.use_activation, sole_consumer=True, defer_apply=defer_out)
 
 
 def Conv2dBlock(in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
