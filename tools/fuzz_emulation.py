@@ -68,5 +68,44 @@ for trial in range(int(sys.argv[2]) if len(sys.argv) > 2 else 12):
         be.call('tss_stem3x3s2_wgrad_tc', dict(x=x, dy=dyy, dw=dw, N=N, H=H, W=W, Cout=32))
         outs[name] = (yv.float(), st, dw)
     note('stem y', rel(outs['emu'][0], outs['ref'][0]), 5e-3); note('stem stats', rel(outs['emu'][1], outs['ref'][1]), 1e-4); note('stem dw', rel(outs['emu'][2], outs['ref'][2]), 5e-3)
+    # ---- depthwise fwd / wgrad with the input BatchNorm, pointwise fwd with the input BatchNorm
+    C = random.choice([32, 48, 64, 96, 192, 384, 576]); N, H, W = random.randint(1, 2), random.randint(1, 21), random.randint(1, 41)
+    stride = random.choice([1, 2]); relu = random.randint(0, 1)
+    dt = random.choice([torch.float32, torch.bfloat16]); code = _lib.dtype_code(dt)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    xx, dyy = nh(N, C, H, W, dt), nh(N, C, Ho, Wo, dt)
+    w = torch.randn(C, 1, 3, 3, generator=g) / 3
+    sc, sh = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.5 + 0.3
+    outs = {}
+    for name, be in (('ref', fake), ('emu', emu)):
+        yv = torch.zeros(N, Ho, Wo, C, dtype=dt).permute(0, 3, 1, 2); st = torch.zeros(2 * C, dtype=torch.float64); dw = torch.zeros(C, 1, 3, 3)
+        be.call('tss_dwconv3x3_fwd_bnin', dict(x=xx, in_scale=sc, in_shift=sh, in_flags=relu, w=w, y=yv, N=N, Hi=H, Wi=W, C=C, stride=stride, stats=st, dtype=code))
+        be.call('tss_dwconv3x3_wgrad_bnin', dict(x=xx, in_scale=sc, in_shift=sh, in_flags=relu, dy=dyy, dw=dw, N=N, Hi=H, Wi=W, C=C, stride=stride, dtype=code))
+        outs[name] = (yv.float(), st, dw)
+    tol = 2e-5 if dt == torch.float32 else 6e-3
+    note('dwbnin y', rel(outs['emu'][0], outs['ref'][0]), tol); note('dwbnin stats', rel(outs['emu'][1], outs['ref'][1]), 1e-4); note('dwbnin dw', rel(outs['emu'][2], outs['ref'][2]), 1e-3)
+    N, H, W = random.randint(1, 3), random.randint(1, 11), random.randint(1, 13)
+    K = 8 * random.randint(1, 96); Nc = 16 * random.randint(1, 8); relu = random.randint(0, 1); M = N * H * W
+    xx = nh(N, K, H, W, torch.bfloat16); sc, sh = torch.rand(K, generator=g) + 0.5, torch.randn(K, generator=g) * 0.4
+    wp = (torch.randn(Nc, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    outs = {}
+    for name, be in (('ref', fake), ('emu', emu)):
+        yv = torch.zeros(N, H, W, Nc, dtype=torch.bfloat16).permute(0, 3, 1, 2); zv = torch.zeros(N, H, W, K, dtype=torch.bfloat16).permute(0, 3, 1, 2)
+        st = torch.zeros(2 * Nc, dtype=torch.float64)
+        be.call('tss_pwconv_fwd_bnin', dict(x=xx, ldx=K, in_scale=sc, in_shift=sh, in_flags=relu, z=zv, ldz=K, wp=wp, y=yv, ldy=Nc, M=M, K=K, Nc=Nc, stats=st))
+        outs[name] = (yv.float(), zv.float(), st)
+    note('pwbnin y', rel(outs['emu'][0], outs['ref'][0]), 6e-3); note('pwbnin z', rel(outs['emu'][1], outs['ref'][1]), 1e-3); note('pwbnin stats', rel(outs['emu'][2], outs['ref'][2]), 2e-3)
+    # ---- stem weight gradient with the BatchNorm-backward apply
+    N, H, W = random.randint(1, 2), random.randint(1, 30), random.randint(1, 200); relu = random.randint(0, 1)
+    x = torch.randn(N, 3, H, W, generator=g); Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1; M = N * Ho * Wo
+    dz, yy = nh(N, 32, Ho, Wo, torch.bfloat16), nh(N, 32, Ho, Wo, torch.bfloat16)
+    mean, rstd, gamma, beta = par(32); sums = torch.zeros(64)
+    fake.call('tss_bn_bwd_reduce', dict(dz=dz, z=None, y=yy, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, M=M, C=32, lddz=32, ldz=0, ldy=32, flags=relu, dtype=1))
+    outs = {}
+    for name, be in (('ref', fake), ('emu', emu)):
+        dw, dga, dbe = torch.zeros(32, 3, 3, 3), torch.zeros(32), torch.zeros(32)
+        be.call('tss_stem3x3s2_wgrad_tc_bn', dict(x=x, dz=dz, y=yy, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, flags=relu, count=M, dw=dw, dgamma=dga, dbeta=dbe, N=N, H=H, W=W, Cout=32))
+        outs[name] = (dw, dga)
+    note('stem bn dw', rel(outs['emu'][0], outs['ref'][0]), 6e-3); note('stem bn dgamma', rel(outs['emu'][1], outs['ref'][1]), 1e-6)
     print('trial', trial, 'ok', flush=True)
 print({k: '%.2e' % v for k, v in worst.items()})
