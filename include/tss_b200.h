@@ -88,7 +88,8 @@ int tss_dwconv3x3_wgrad_bnin(const void* x, const float* in_scale, const float* 
  * [N][H][W][C]: gradient after this layer's BN/ReLU and its raw conv output (two TMA halo tiles); sums[2C]: the
  * finished reduction of this layer (flags&TSS_EPI_RELU: mask recomputed from y; 0: dz already masked).  dy
  * (may be NULL): the BatchNorm-backward output, stored for the weight gradient.  g: masked gradient for the producer
- * (yp, pmean, ..., psums as in tss_dwconv3x3_dgrad_bnred).  dgamma += sums[C+c], dbeta += sums[c]. */
+ * (yp, pmean, ..., psums as in tss_dwconv3x3_dgrad_bnred; yp == NULL: no producer, g is the plain input gradient).
+ * dgamma += sums[C+c], dbeta += sums[c]. */
 int tss_dwconv3x3_bwd_fused(const void* dz, const void* y, const float* w, const float* mean, const float* rstd,
                             const float* gamma, const float* beta, const float* sums, int flags, int64_t count,
                             void* dy, float* dgamma, float* dbeta, void* g, int N, int H, int W, int C,

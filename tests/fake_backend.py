@@ -138,6 +138,9 @@ class FakeBackend:
         self.tss_bn_bwd_apply(dz, None, y, mean, rstd, gamma, beta, sums, out, None, dgamma, dbeta, N * H * W, count, C, C, 0, C,
                               C, 0, flags, dtype)
         d = nngrad.conv2d_input((N, C, H, W), w.detach().view(C, 1, 3, 3), out.float(), 1, 1, 1, C)
+        if yp is None:
+            g.copy_(d)
+            return 0
         return self._bnred(d, g, yp, pmean, prstd, pgamma, pbeta, pflags, psums)
 
     def tss_dwconv3x3_dgrad_s2_bnred(self, dy, w, g, N, Hi, Wi, C, yp, mean, rstd, gamma, beta, flags, sums, dtype):

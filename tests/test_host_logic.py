@@ -238,8 +238,10 @@ def test_gated_backward_fusions_are_plumbing_equivalent(fake_backend):
     base, base_calls = runs[False, False]
     # BatchNorm-backward apply folded into the stride-1 depthwise dgrads that carry a fused reduction
     assert rel(runs['dw', False][0], base) < 1e-6
-    assert runs['dw', False][1]['tss_dwconv3x3_bwd_fused'] == base_calls['tss_dwconv3x3_dgrad_bnred']
-    assert runs['dw', False][1]['tss_bn_bwd_apply'] == base_calls['tss_bn_bwd_apply'] - base_calls['tss_dwconv3x3_dgrad_bnred']
+    n_dw = runs['dw', False][1]['tss_dwconv3x3_bwd_fused']
+    assert n_dw >= base_calls['tss_dwconv3x3_dgrad_bnred']          # also the stride-1 layers without a producer link
+    assert 'tss_dwconv3x3_dgrad_bnred' not in runs['dw', False][1]
+    assert runs['dw', False][1]['tss_bn_bwd_apply'] == base_calls['tss_bn_bwd_apply'] - n_dw
     # finalize folded into the apply kernel: same arithmetic, 44 launches less
     assert rel(runs['fin', False][0], base) < 1e-6
     assert runs['fin', False][1]['tss_bn_finalize_apply'] == 44 and 'tss_bn_finalize' not in runs['fin', False][1]

@@ -383,6 +383,31 @@ def test_emulation_agrees_with_the_validated_depthwise_kernels(emulated, C, N, H
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('C,N,H,W', [(128, 2, 12, 20), (96, 1, 9, 40)])
+def test_depthwise_backward_with_bn_apply_without_a_producer(emulated, C, N, H, W, dtype):
+    g = torch.Generator().manual_seed(C + H)
+    dz, y = _nhwc(N, C, H, W, g, dtype), _nhwc(N, C, H, W, g, dtype)
+    w = torch.randn(C, 1, 3, 3, generator=g) / 3
+    mean, rstd = torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    M, code = N * H * W, _lib.dtype_code(dtype)
+    fake = FakeBackend()
+    sums = torch.zeros(2 * C)
+    fake.call('tss_bn_bwd_reduce', dict(dz=dz, z=None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, M=M, C=C,
+                                        lddz=C, ldz=0, ldy=C, flags=1, dtype=code))
+    outs = {}
+    for name, be in (('ref', fake), ('emu', emulated)):
+        dy = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2)
+        gout = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2)
+        be.call('tss_dwconv3x3_bwd_fused', dict(dz=dz, y=y, w=w, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums, flags=1,
+                                                count=M, dy=dy, dgamma=None, dbeta=None, g=gout, N=N, H=H, W=W, C=C, yp=None,
+                                                pmean=None, prstd=None, pgamma=None, pbeta=None, pflags=0, psums=None, dtype=code))
+        outs[name] = (dy.float(), gout.float())
+    tol = 2e-5 if dtype == torch.float32 else 6e-3
+    assert rel(outs['emu'][0], outs['ref'][0]) < tol and rel(outs['emu'][1], outs['ref'][1]) < 2 * tol
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('C,N,H,W,relu', [(64, 2, 12, 20, 1), (384, 1, 5, 7, 1), (96, 1, 9, 40, 0), (32, 3, 1, 1, 1), (128, 1, 17, 33, 1)])
 def test_depthwise_backward_with_bn_apply_on_the_emulation(emulated, C, N, H, W, relu, dtype):
     """csrc/dwconv_bwd_fused.cu: two TMA halo tiles (dz, y) -> dy in shared memory (zero outside the image) ->

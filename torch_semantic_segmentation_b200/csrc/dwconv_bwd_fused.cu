@@ -123,6 +123,16 @@ dw_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
         }
     }
 
+    const int wo = w0 + col;
+    if (yp == nullptr) {                                  // no producer to reduce for: the plain input gradient
+        if (wo < W) {
+            const int64_t base = (((int64_t)n * H + h0) * W + wo) * C + c0;
+#pragma unroll
+            for (int r = 0; r < TH; ++r)
+                if (h0 + r < H) store8p(g_out + base + (int64_t)r * W * C, acc[r]);
+        }
+        return;                                           // uniform over the grid
+    }
     float mu[8], rs[8], sc[8], sh[8];                     // the producer's BatchNorm (reduction)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -131,7 +141,6 @@ dw_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
         sc[e] = (pgamma != nullptr ? __ldg(pgamma + c0 + e) : 1.f) * rs[e];
         sh[e] = (pbeta != nullptr ? __ldg(pbeta + c0 + e) : 0.f) - mu[e] * sc[e];
     }
-    const int wo = w0 + col;
     float s1[8], s2[8];
     zero8(s1); zero8(s2);
     if (wo < W) {
@@ -186,7 +195,7 @@ extern "C" int tss_dwconv3x3_bwd_fused(const void* dz, const void* y, const floa
                                        void* stream) {
     TSS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "dwconv3x3_bwd_fused: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
     TSS_REQUIRE(mean != nullptr && rstd != nullptr && sums != nullptr, "dwconv3x3_bwd_fused: missing BatchNorm operands");
-    TSS_REQUIRE(yp != nullptr && pmean != nullptr && prstd != nullptr && psums != nullptr, "dwconv3x3_bwd_fused: missing producer operands");
+    TSS_REQUIRE(yp == nullptr || (pmean != nullptr && prstd != nullptr && psums != nullptr), "dwconv3x3_bwd_fused: missing producer operands");
     TSS_REQUIRE((((uintptr_t)dz | (uintptr_t)y | (uintptr_t)dy | (uintptr_t)g | (uintptr_t)yp) & 15) == 0,
                 "dwconv3x3_bwd_fused: buffers must be 16-byte aligned");
     if (count <= 0) count = (int64_t)N * H * W;

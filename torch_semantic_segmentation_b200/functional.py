@@ -349,7 +349,7 @@ class ConvBNAct(torch.autograd.Function):
             grad_ready(*ctx.params)
             return (None, None, None if gw is not None else dw, None if gg is not None else gg_out,
                     None if gb is not None else gb_out, None, None, None, None, None)
-        if (FUSE_BNAPPLY_DW and spec.kind == 'dw' and prod is not None and spec.stride == 1 and spec.dilation == 1
+        if (FUSE_BNAPPLY_DW and spec.kind == 'dw' and spec.stride == 1 and spec.dilation == 1
                 and C % 32 == 0 and not ctx.has_res and ctx.sync[0] == 1 and ctx.needs_input_grad[0]
                 and ops.geom(dz)[4] == C):
             # one kernel: this layer's BatchNorm-backward apply -> depthwise dgrad -> the producer's reduction
@@ -363,7 +363,8 @@ class ConvBNAct(torch.autograd.Function):
                 ops.bn_backward_reduce(dz, y, mean, rstd, gamma, beta, spec.relu, sums)
                 mask = spec.relu
             dy, dx = ops.dwconv_bwd_fused(dz, y, weight, mean, rstd, gamma, beta, sums, mask, prod, dgamma=gg_out, dbeta=gb_out)
-            prod.reduced, prod.bn._tss_dirty = True, True
+            if prod is not None:
+                prod.reduced, prod.bn._tss_dirty = True, True
             dw_wgrad = _dw_wgrad_fn(ctx, x, dy, dw, spec)
             if gw is not None:
                 wgrad_lane.run(dy.device, dw_wgrad, x, dy)

@@ -215,16 +215,19 @@ def dwconv_dgrad_bnred(dy, w, link):
 
 
 def dwconv_bwd_fused(dz, y, w, mean, rstd, gamma, beta, sums, relu, link, dgamma=None, dbeta=None):
-    """BatchNorm-backward apply + stride-1 depthwise dgrad + the producer's reduction (``link``) -> dy, g."""
+    """BatchNorm-backward apply + stride-1 depthwise dgrad (+ the producer's reduction when there is a ``link``)
+    -> dy, g."""
     N, C, H, W, ld = _g(dz, 'dwconv_bwd_fused')
-    if ld != C or _g(y, 'dwconv_bwd_fused')[4] != C or _g(link.y, 'dwconv_bwd_fused')[4] != C:
+    if ld != C or _g(y, 'dwconv_bwd_fused')[4] != C or (link is not None and _g(link.y, 'dwconv_bwd_fused')[4] != C):
         raise RuntimeError('dwconv_bwd_fused: pitched tensors not supported')
     dy = empty_nhwc(N, C, H, W, dz.dtype, dz.device)
     g = empty_nhwc(N, C, H, W, dz.dtype, dz.device)
+    lk = link
     _lib.call('tss_dwconv3x3_bwd_fused', dz=dz, y=y, w=w, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums,
-              flags=_flags(relu), count=N * H * W, dy=dy, dgamma=dgamma, dbeta=dbeta, g=g, N=N, H=H, W=W, C=C, yp=link.y,
-              pmean=link.mean, prstd=link.rstd, pgamma=link.gamma, pbeta=link.beta, pflags=_flags(link.relu),
-              psums=link.sums, dtype=dtype_code(dz.dtype))
+              flags=_flags(relu), count=N * H * W, dy=dy, dgamma=dgamma, dbeta=dbeta, g=g, N=N, H=H, W=W, C=C,
+              yp=lk.y if lk else None, pmean=lk.mean if lk else None, prstd=lk.rstd if lk else None,
+              pgamma=lk.gamma if lk else None, pbeta=lk.beta if lk else None, pflags=_flags(lk.relu) if lk else 0,
+              psums=lk.sums if lk else None, dtype=dtype_code(dz.dtype))
     return dy, g
 
 
