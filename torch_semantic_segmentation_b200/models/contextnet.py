@@ -12,7 +12,7 @@ from torch import nn
 
 from .. import ops
 from .. import functional as Fn
-from ..nn.blocks import ConvBNBlock, BottleneckBlock, ClassScores, Dropout, set_compute_dtype
+from ..nn.blocks import ConvBNBlock, BottleneckBlock, ClassScores, Dropout, hands_over_to_pointwise, set_compute_dtype
 
 __all__ = ['ContextNet', 'contextnet12', 'contextnet14', 'contextnet18']
 
@@ -41,16 +41,7 @@ class _Chain(nn.Sequential):
 
     @staticmethod
     def _hands_over(dw, pw):
-        """``dw`` (depthwise block) may leave its BatchNorm + ReLU to ``pw`` (tensor-core pointwise block):
-        functional.FUSE_BNIN_PW."""
-        if not (Fn.FUSE_BNIN_PW and isinstance(dw, ConvBNBlock) and isinstance(pw, ConvBNBlock) and dw.training
-                and torch.is_grad_enabled()):
-            return False
-        c_dw, c_pw = dw[0], pw[0]
-        return bool(c_dw.groups == c_dw.in_channels and c_dw.groups > 1 and c_pw.kernel_size == (1, 1) and c_pw.groups == 1
-                    and pw.pw_impl == 1 and pw.compute_dtype == torch.bfloat16 and c_pw.in_channels % 16 == 0
-                    and c_pw.out_channels % 16 == 0 and dw[1].track_running_stats
-                    and getattr(dw[1], '_tss_sync', None) is None and getattr(pw[1], '_tss_sync', None) is None)
+        return hands_over_to_pointwise(dw, pw)
 
     @staticmethod
     def _hands_over_to_dw(blk, dw):
@@ -121,7 +112,7 @@ class FeatureFusionModule(nn.Module):
     def forward(self, lowres, highres):
         lowres = ops.as_nhwc(lowres)
         x = Fn.Bilinear.apply(lowres, highres.shape[2], highres.shape[3])
-        x = self.lowres[0](x)
+        x = self.lowres[0](x, defer_apply=hands_over_to_pointwise(self.lowres[0], self.lowres[1]))
         high = self.highres(highres)
         # relu(lowres + highres): add and ReLU fused into the low-res branch's BatchNorm apply
         return self.lowres[1](x, residual=high, relu=True)

@@ -14,7 +14,7 @@ from torch import nn
 from .. import ops
 from .. import functional as Fn
 from ..nn.blocks import (Conv2dBlock, DWConv2dBlock, DSConv2dBlock, DSConvBNBlock, BottleneckBlock, ClassScores, Dropout,
-                         set_compute_dtype)
+                         hands_over_to_pointwise, set_compute_dtype)
 
 __all__ = ['FastSCNN', 'fastscnn', 'Classifier']
 
@@ -112,7 +112,7 @@ class FeatureFusionModule(nn.Module):
         lowres = ops.as_nhwc(lowres)
         s = self.scale_factor
         x = Fn.Bilinear.apply(lowres, lowres.shape[2] * s, lowres.shape[3] * s)
-        x = self.lowres[1](x)
+        x = self.lowres[1](x, defer_apply=hands_over_to_pointwise(self.lowres[1], self.lowres[2]))
         high = self.highres[0](highres)
         # relu(lowres + highres): add and ReLU fused into the low-res branch's BatchNorm apply
         return self.lowres[2](x, residual=high, relu=True, sole_consumer=Fn.FUSE_BNRED_EXT)

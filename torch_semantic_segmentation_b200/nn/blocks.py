@@ -235,6 +235,19 @@ class DSConvBNBlock(nn.Sequential, _FusedConvBN):
         return self._conv_bn(2, x, self.use_activation, sole_consumer=True, defer_apply=defer_out)
 
 
+def hands_over_to_pointwise(dw, pw):
+    """The depthwise block ``dw`` may leave its BatchNorm (+ReLU) to the tensor-core pointwise block ``pw`` that is its
+    only reader (functional.FUSE_BNIN_PW)."""
+    if not (Fn.FUSE_BNIN_PW and isinstance(dw, ConvBNBlock) and isinstance(pw, ConvBNBlock) and dw.training
+            and torch.is_grad_enabled()):
+        return False
+    c_dw, c_pw = dw[0], pw[0]
+    return bool(c_dw.groups == c_dw.in_channels and c_dw.groups > 1 and c_pw.kernel_size == (1, 1) and c_pw.groups == 1
+                and pw.pw_impl == 1 and pw.compute_dtype == torch.bfloat16 and c_pw.in_channels % 16 == 0
+                and c_pw.out_channels % 16 == 0 and dw[1].track_running_stats
+                and getattr(dw[1], '_tss_sync', None) is None and getattr(pw[1], '_tss_sync', None) is None)
+
+
 def Conv2dBlock(in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
                 use_activation=True):
     return ConvBNBlock(in_channels, out_channels, kernel_size, stride, padding, dilation, 1, use_activation)
