@@ -214,6 +214,32 @@ def _sync_group(bn):
     return torch.distributed.get_world_size(group), group
 
 
+def _finished_sums(ctx, dz):
+    """The two BatchNorm-backward sums of the layer, for the kernels that fold its apply pass into something else:
+    -> (sums, mask).  Either the consumer's dgrad epilogue already produced them (``dz`` is then masked: mask False), or
+    the stand-alone reduction runs now (mask = the layer's ReLU, recomputed from the raw output by the fused kernel)."""
+    spec, link = ctx.spec, ctx.link
+    x, weight, gamma, beta, y, z, mean, rstd = ctx.saved_tensors
+    C = weight.shape[0]
+    if link is not None and link.reduced:
+        return link.sums, False
+    sums = ctx.scratch[2 * C:].view(torch.float32)
+    if spec.bn._tss_dirty or ctx.scratch is not getattr(spec.bn, '_tss_scratch', None):
+        sums = ops.zeros_f32(2 * C, weight.device)      # a second backward without a forward in between
+    spec.bn._tss_dirty = True
+    ops.bn_backward_reduce(dz, y, mean, rstd, gamma, beta, spec.relu, sums)
+    return sums, spec.relu
+
+
+def _conv_grads(ctx, dx, dres, dw, gg_out, gb_out):
+    """What ConvBNAct.backward returns: gradients that were accumulated straight into the optimizer's arena are
+    reported as None (and announced to the reducer through grad_ready)."""
+    gw, gg, gb = ctx.arena
+    grad_ready(*ctx.params)
+    return (dx, dres, None if gw is not None else dw, None if gg is not None else gg_out,
+            None if gb is not None else gb_out, None, None, None, None, None)
+
+
 def _dw_wgrad_fn(ctx, x, dy, dw, spec):
     """The depthwise weight gradient of a layer: on the activated input, or on the producer's raw output with its
     BatchNorm applied on the fly when the forward pass ran that way."""
@@ -309,15 +335,7 @@ class ConvBNAct(torch.autograd.Function):
                 and ctx.sync[0] == 1 and ctx.needs_input_grad[0] and dz.dtype == torch.bfloat16
                 and C % 8 == 0 and weight.shape[1] % 16 == 0):
             # one kernel: this layer's BatchNorm-backward apply -> dgrad (-> the producer's reduction)
-            if link is not None and link.reduced:
-                sums, mask = link.sums, False
-            else:
-                sums = ctx.scratch[2 * C:].view(torch.float32)
-                if spec.bn._tss_dirty or ctx.scratch is not getattr(spec.bn, '_tss_scratch', None):
-                    sums = ops.zeros_f32(2 * C, weight.device)
-                spec.bn._tss_dirty = True
-                ops.bn_backward_reduce(dz, y, mean, rstd, gamma, beta, spec.relu, sums)
-                mask = spec.relu
+            sums, mask = _finished_sums(ctx, dz)
             dy, dx = ops.pwconv_bwd_fused(dz, y, mean, rstd, gamma, beta, sums, mask, wpT, dgamma=gg_out, dbeta=gb_out,
                                           link=prod)
             if prod is not None:
@@ -326,42 +344,22 @@ class ConvBNAct(torch.autograd.Function):
                 wgrad_lane.run(dy.device, lambda: ops.pwconv_wgrad(x, dy, dw, impl=1), x, dy)
             else:
                 ops.pwconv_wgrad(x, dy, dw, impl=1)
-            grad_ready(*ctx.params)
-            return (dx, None, None if gw is not None else dw, None if gg is not None else gg_out,
-                    None if gb is not None else gb_out, None, None, None, None, None)
+            return _conv_grads(ctx, dx, None, dw, gg_out, gb_out)
         if (STEM_TC and STEM_BWD_FUSED and spec.kind == 'stem' and dz.dtype == torch.bfloat16 and C == 32 and not ctx.has_res
                 and ctx.sync[0] == 1 and not ctx.needs_input_grad[0] and ops.geom(dz)[4] == C):
             # the stem has no input gradient: BatchNorm-backward apply + weight gradient in one kernel, no dy tensor
-            if link is not None and link.reduced:
-                sums, mask = link.sums, False
-            else:
-                sums = ctx.scratch[2 * C:].view(torch.float32)
-                if spec.bn._tss_dirty or ctx.scratch is not getattr(spec.bn, '_tss_scratch', None):
-                    sums = ops.zeros_f32(2 * C, weight.device)
-                spec.bn._tss_dirty = True
-                ops.bn_backward_reduce(dz, y, mean, rstd, gamma, beta, spec.relu, sums)
-                mask = spec.relu
+            sums, mask = _finished_sums(ctx, dz)
             fused = lambda: ops.stem_wgrad_tc_bn(x, dz, y, mean, rstd, gamma, beta, sums, mask, dw, dgamma=gg_out, dbeta=gb_out)
             if gw is not None:
                 wgrad_lane.run(dz.device, fused, x, dz, y, sums)
             else:
                 fused()
-            grad_ready(*ctx.params)
-            return (None, None, None if gw is not None else dw, None if gg is not None else gg_out,
-                    None if gb is not None else gb_out, None, None, None, None, None)
+            return _conv_grads(ctx, None, None, dw, gg_out, gb_out)
         if (FUSE_BNAPPLY_DW and spec.kind == 'dw' and spec.stride == 1 and spec.dilation == 1
                 and C % 32 == 0 and not ctx.has_res and ctx.sync[0] == 1 and ctx.needs_input_grad[0]
                 and ops.geom(dz)[4] == C):
             # one kernel: this layer's BatchNorm-backward apply -> depthwise dgrad -> the producer's reduction
-            if link is not None and link.reduced:
-                sums, mask = link.sums, False
-            else:
-                sums = ctx.scratch[2 * C:].view(torch.float32)
-                if spec.bn._tss_dirty or ctx.scratch is not getattr(spec.bn, '_tss_scratch', None):
-                    sums = ops.zeros_f32(2 * C, weight.device)
-                spec.bn._tss_dirty = True
-                ops.bn_backward_reduce(dz, y, mean, rstd, gamma, beta, spec.relu, sums)
-                mask = spec.relu
+            sums, mask = _finished_sums(ctx, dz)
             dy, dx = ops.dwconv_bwd_fused(dz, y, weight, mean, rstd, gamma, beta, sums, mask, prod, dgamma=gg_out, dbeta=gb_out)
             if prod is not None:
                 prod.reduced, prod.bn._tss_dirty = True, True
@@ -370,9 +368,7 @@ class ConvBNAct(torch.autograd.Function):
                 wgrad_lane.run(dy.device, dw_wgrad, x, dy)
             else:
                 dw_wgrad()
-            grad_ready(*ctx.params)
-            return (dx, None, None if gw is not None else dw, None if gg is not None else gg_out,
-                    None if gb is not None else gb_out, None, None, None, None, None)
+            return _conv_grads(ctx, dx, None, dw, gg_out, gb_out)
         if link is not None and link.reduced:
             # the consumer's dgrad already masked the gradient and accumulated both sums
             dy, dres = ops.bn_backward(dz, None, y, mean, rstd, gamma, False, dgamma=gg_out, dbeta=gb_out, beta=beta,
@@ -414,9 +410,7 @@ class ConvBNAct(torch.autograd.Function):
                 lane(lambda: ops.stem_wgrad_tc(x, dy, dw))
             else:
                 lane(lambda: ops.stem_wgrad(x, dy, dw))
-        grad_ready(*ctx.params)
-        return (dx, dres, None if gw is not None else dw, None if gg is not None else gg_out,
-                None if gb is not None else gb_out, None, None, None, None, None)
+        return _conv_grads(ctx, dx, dres, dw, gg_out, gb_out)
 
 
 class Im2Col3x3(torch.autograd.Function):
