@@ -583,3 +583,51 @@ def test_stem_wgrad_with_bn_apply_matches_apply_then_wgrad(N, H, W):
                                               dw=dw2, dgamma=dg2, dbeta=db2, N=N, H=H, W=W, Cout=32))
     torch.cuda.synchronize()
     assert rel(dw2, dw1) < 5e-3 and rel(dg2, dg1) < 1e-6 and rel(db2, db1) < 1e-6
+
+
+@pytest.mark.parametrize('arch', ['fastscnn', 'contextnet14'])
+def test_all_training_gates_together_on_the_gpu(arch):
+    """Every off-by-default training gate at once, bf16: three optimisation steps through the real kernels agree with the
+    default path at bf16 level, with far fewer launches (the GPU counterpart of
+    tests/test_host_logic.py::test_all_gates_together_train_and_eval)."""
+    from oracle.golden_inputs import train_batch
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+    from torch_semantic_segmentation_b200.models.contextnet import contextnet14
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    flags = ['FUSE_BNRED_EXT', 'FUSE_BNAPPLY', 'FUSE_BNAPPLY_DW', 'FUSE_PPM', 'FUSE_BNFIN', 'FUSE_BNIN', 'FUSE_BNIN_PW', 'STEM_TC',
+             'STEM_BWD_FUSED', 'DEFER_LOGITS', 'OWN_DROPOUT']
+    keep = {f: getattr(Fn, f) for f in flags}
+    factory = {'fastscnn': fastscnn, 'contextnet14': contextnet14}[arch]
+    x, y = train_batch('fastscnn')
+    x, y = x.cuda(), y.cuda()
+    runs = {}
+    try:
+        for on in (False, True):
+            for f in flags:
+                setattr(Fn, f, on)
+            torch.manual_seed(0)
+            model = factory(3, 19).cuda().set_compute_dtype(torch.bfloat16).train()
+            for m in model.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+            opt = FlatAdamW(model.parameters(), lr=1e-3)
+            loss_fn = CrossEntropyLoss(ignore_index=255)
+            Fn.enable_deferred_logits(model, loss_fn)
+            before, losses = _lib.launch_count(), []
+            for _ in range(3):
+                opt.zero_grad()
+                loss = loss_fn(model(x), y)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss.detach()))
+            torch.cuda.synchronize()
+            runs[on] = (losses, _lib.launch_count() - before, bool(torch.isfinite(opt.param_arena).all()))
+    finally:
+        for f, v in keep.items():
+            setattr(Fn, f, v)
+    assert runs[True][2] and runs[False][2]
+    for a, b in zip(runs[True][0], runs[False][0]):
+        assert abs(a - b) < 1e-2 * abs(b), (runs[True][0], runs[False][0])
+    assert runs[True][1] < runs[False][1] - 200          # three steps
