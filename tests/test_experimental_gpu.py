@@ -631,3 +631,33 @@ def test_all_training_gates_together_on_the_gpu(arch):
     for a, b in zip(runs[True][0], runs[False][0]):
         assert abs(a - b) < 1e-2 * abs(b), (runs[True][0], runs[False][0])
     assert runs[True][1] < runs[False][1] - 200          # three steps
+
+
+def test_graphed_eval_follows_graphed_training():
+    """Default path: train with CUDA-graph replays, evaluate with the graphed evaluator, train on, evaluate again -- the
+    second evaluation must see the new weights and BatchNorm statistics (eval operands refreshed in place;
+    GraphedTrainStep bumps ops.WEIGHTS_EPOCH).  Checked against an eager evaluation of the same model."""
+    from oracle.golden_inputs import train_batch
+    from torch_semantic_segmentation_b200.engine import GraphedTrainStep, create_segmentation_evaluator
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    x, y = train_batch('fastscnn')
+    xd, yd = x.cuda(), y.cuda()
+    torch.manual_seed(0)
+    model = fastscnn(3, 19).cuda().set_compute_dtype(torch.bfloat16)
+    opt = FlatAdamW(model.parameters(), lr=5e-3)
+    step = GraphedTrainStep(model.train(), opt, CrossEntropyLoss(ignore_index=255), xd, yd)
+    graphed = create_segmentation_evaluator(model, 'cuda', num_classes=19, cuda_graph=True)
+    eager = create_segmentation_evaluator(model, 'cuda', num_classes=19, cuda_graph=False)
+    cms = []
+    for _round in range(2):
+        model.train()
+        for _ in range(5):
+            step(xd, yd)
+        torch.cuda.synchronize()
+        a = graphed.run([(x, y)]).metrics['confusion_matrix'].clone()
+        b = eager.run([(x, y)]).metrics['confusion_matrix'].clone()
+        assert torch.equal(a, b), _round
+        cms.append(a)
+    assert not torch.equal(cms[0], cms[1])                     # training moved the predictions between the two evaluations

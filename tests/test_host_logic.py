@@ -632,3 +632,34 @@ def test_stem_backward_without_the_dy_tensor(fake_backend):
         assert torch.equal(runs[True][0][k], runs[False][0][k]), k
     assert runs[True][1]['tss_stem3x3s2_wgrad_tc_bn'] == 1 and 'tss_stem3x3s2_wgrad_tc' not in runs[True][1]
     assert runs[True][1]['tss_bn_bwd_apply'] == runs[False][1]['tss_bn_bwd_apply'] - 1
+
+
+def test_eval_operands_are_refreshed_in_place_after_training(fake_backend):
+    """Folded BatchNorm scale/shift (and bf16 weight packs) are derived once and then refreshed IN PLACE: a captured eval
+    graph or an address table keeps reading the same buffers and still sees the statistics of the latest training step.
+    engine.GraphedTrainStep bumps ops.WEIGHTS_EPOCH after every replay for the same reason (a replay runs no Python)."""
+    from torch_semantic_segmentation_b200.nn.blocks import refresh_cached_operands
+    torch.manual_seed(0)
+    model = _no_dropout(fastscnn(3, 19))
+    x, y = train_batch('fastscnn')
+    with torch.no_grad():
+        out0 = model.eval()(x)
+    blk = model.downsample[0]
+    scale0, shift0 = blk._folded(0)
+    ptr, before = scale0.data_ptr(), scale0.clone()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    model.train()
+    CrossEntropyLoss(ignore_index=255)(model(x), y).backward()
+    opt.step()
+    refresh_cached_operands(model.eval())
+    scale1, shift1 = blk._folded(0)
+    assert scale1.data_ptr() == ptr and not torch.equal(scale1, before)                  # same buffer, new values
+    bn = blk[1]
+    want = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+    assert rel(scale1, want) < 1e-6
+    with torch.no_grad():
+        out1 = model(x)
+    assert not torch.equal(out1, out0)
+    epoch = ops.WEIGHTS_EPOCH[0]
+    refresh_cached_operands(model)
+    assert ops.WEIGHTS_EPOCH[0] == epoch and blk._folded(0)[0].data_ptr() == ptr          # idempotent

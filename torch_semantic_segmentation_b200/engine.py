@@ -280,6 +280,10 @@ class GraphedTrainStep:
         if refresh is not None:
             refresh()        # a learning-rate scheduler may have changed param_groups since the last replay
         self.graph.replay()
+        # the replay rewrote parameters and BatchNorm buffers behind autograd's back, without running the Python that
+        # bumps this counter in eager mode: caches derived from them (eval-mode folded BatchNorm, weight packs) are stale
+        from . import ops
+        ops.WEIGHTS_EPOCH[0] += 1
         return self.loss
 
 
@@ -455,6 +459,11 @@ def create_segmentation_evaluator(model, device, num_classes=19, loss_fn=None, n
     def _reset(engine):
         cm.reset()
         loss_acc['sum'], loss_acc['n'] = None, 0
+        if graphs:
+            # captured forwards read the folded BatchNorm / packed weights by address: refresh them in place first
+            from .nn.blocks import refresh_cached_operands
+            model.eval()
+            refresh_cached_operands(model)
 
     @evaluator.on(Events.EPOCH_COMPLETED)
     def _compute(engine):

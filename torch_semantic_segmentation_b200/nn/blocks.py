@@ -95,7 +95,9 @@ class _FusedConvBN:
         key = _versions(bn.weight, bn.bias, bn.running_mean, bn.running_var)
         hit = self._fold_cache.get(ci)
         if hit is None or hit[0] != key:
-            hit = (key, ops.bn_fold(bn))
+            # refreshed IN PLACE once it exists: captured eval graphs and address tables keep reading the same buffers
+            pair = ops.bn_fold(bn, out=hit[1][0]._base if (hit is not None and hit[1][0]._base is not None) else None)
+            hit = (key, pair)
             self._fold_cache[ci] = hit
         return hit[1]
 
@@ -120,7 +122,7 @@ class _FusedConvBN:
         key = _versions(w)
         hit = self._pack_cache.get(ci)
         if hit is None or hit[0] != key:
-            hit = (key, ops.pack_weights_bf16(w))
+            hit = (key, ops.pack_weights_bf16(w, out=hit[1] if hit is not None else None))      # in place, as above
             self._pack_cache[ci] = hit
         return hit[1]
 
@@ -341,6 +343,18 @@ class Dropout(nn.Dropout):
                 and ops.geom(input) is not None and ops.geom(input)[4] == input.shape[1]):
             return Fn.Dropout.apply(input, self.p)
         return super().forward(input)
+
+
+def refresh_cached_operands(module):
+    """Bring every derived eval-mode operand that has been built so far (folded BatchNorm scale/shift, bf16 weight packs)
+    up to date IN PLACE.  A captured CUDA graph does not run the Python that would notice a stale cache, so whoever
+    replays eval graphs calls this first (engine.create_segmentation_evaluator does, once per run)."""
+    for m in module.modules():
+        if isinstance(m, _FusedConvBN):
+            for ci in list(m._fold_cache):
+                m._folded(ci)
+            for ci in list(m._pack_cache):
+                m._packed(ci)
 
 
 def set_compute_dtype(module, dtype, pw_impl=None):

@@ -264,10 +264,14 @@ def dwpw_fwd(x, w_dw, scale1, shift1, relu1, wp, scale2, shift2, res=None, relu2
     return y
 
 
-def pack_weights_bf16(w):
+def pack_weights_bf16(w, out=None):
+    """-> (wp, wpT) bf16 copies of a pointwise weight; ``out``: an existing pair to refresh in place."""
     Nc, K = w.shape[0], w.shape[1]
-    wp = torch.empty((Nc, K), dtype=torch.bfloat16, device=w.device)
-    wpT = torch.empty((K, Nc), dtype=torch.bfloat16, device=w.device)
+    if out is not None and out[0].device == w.device and tuple(out[0].shape) == (Nc, K) and tuple(out[1].shape) == (K, Nc):
+        wp, wpT = out
+    else:
+        wp = torch.empty((Nc, K), dtype=torch.bfloat16, device=w.device)
+        wpT = torch.empty((K, Nc), dtype=torch.bfloat16, device=w.device)
     _lib.call('tss_pack_weights_bf16', w=w, wp=wp, wpT=wpT, Nc=Nc, K=K)
     return wp, wpT
 
@@ -408,9 +412,12 @@ def bn_finalize_apply(stats, count, bn, momentum, eps, y, res=None, relu=False, 
     return z, out[0], out[1]
 
 
-def bn_fold(bn):
+def bn_fold(bn, out=None):
+    """-> scale, shift of the eval-mode BatchNorm.  ``out`` ((2, C) fp32): refresh an existing pair in place, so that
+    whoever holds its address (a captured CUDA graph, an address table) sees the new values."""
     C = bn.num_features
-    out = torch.empty((2, C), dtype=torch.float32, device=bn.running_mean.device)
+    if out is None or out.device != bn.running_mean.device or tuple(out.shape) != (2, C):
+        out = torch.empty((2, C), dtype=torch.float32, device=bn.running_mean.device)
     _lib.call('tss_bn_fold', gamma=bn.weight, beta=bn.bias, running_mean=bn.running_mean,
               running_var=bn.running_var, eps=bn.eps, scale=out[0], shift=out[1], C=C)
     return out[0], out[1]
