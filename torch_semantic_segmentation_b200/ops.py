@@ -548,6 +548,7 @@ def ppm_branches_fwd(pool, table, N, C, Cb, bins, momentum, eps):
     rstd = torch.empty((len(bins), Cb), dtype=torch.float32, device=pool.device)
     _lib.call('tss_ppm_branches_fwd', pool=pool, table=table, y=y, z=z, mean=mean, rstd=rstd, N=N, C=C, Cb=Cb,
               bins=_HostInts(bins), nbins=len(bins), momentum=float(momentum), eps=float(eps), dtype=dtype_code(pool.dtype))
+    WEIGHTS_EPOCH[0] += 1          # the kernel updated the branches' running statistics
     return y, z, mean, rstd
 
 
