@@ -663,3 +663,14 @@ def test_eval_operands_are_refreshed_in_place_after_training(fake_backend):
     epoch = ops.WEIGHTS_EPOCH[0]
     refresh_cached_operands(model)
     assert ops.WEIGHTS_EPOCH[0] == epoch and blk._folded(0)[0].data_ptr() == ptr          # idempotent
+
+
+def test_gate_defaults_and_environment_override(monkeypatch):
+    """Only what has been measured on the GPU is on by default (gates.py); TSS_<NAME> overrides for A/B runs."""
+    from torch_semantic_segmentation_b200 import gates
+    assert [k for k, v in gates.DEFAULTS.items() if v] == ['FUSE_BNRED']
+    monkeypatch.delenv('TSS_FUSE_PPM', raising=False)
+    assert gates.gate('FUSE_PPM') is False and gates.gate('FUSE_BNRED') is True
+    monkeypatch.setenv('TSS_FUSE_PPM', '1')
+    monkeypatch.setenv('TSS_FUSE_BNRED', '0')
+    assert gates.gate('FUSE_PPM') is True and gates.gate('FUSE_BNRED') is False

@@ -18,6 +18,7 @@ import torch
 
 from . import metrics as M
 from . import functional as Fn
+from .gates import gate
 from .functional import unit_loss_grad
 
 __all__ = ['create_segmentation_trainer', 'create_segmentation_evaluator', 'Engine', 'Events', 'State']
@@ -163,7 +164,7 @@ def _prepare_batch(batch, device=None, non_blocking=False):
 
 # One CUDA graph per staging slot of the trainer (no device-to-device copy of the batch into the graph's inputs).
 # Host-side change only; off unless TSS_SLOT_GRAPHS=1 until it has run on a B200.
-SLOT_GRAPHS = os.environ.get('TSS_SLOT_GRAPHS', '0') == '1'
+SLOT_GRAPHS = gate('SLOT_GRAPHS')
 
 
 class _StagedBatch:

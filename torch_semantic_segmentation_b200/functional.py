@@ -22,6 +22,7 @@ import threading
 import torch
 
 from . import ops
+from .gates import gate
 
 _tls = threading.local()
 
@@ -147,43 +148,43 @@ def conv_forward(spec, x, weight, scale=None, shift=None, res=None, relu=False, 
 # Stem convolution on tcgen05 with a thread-built implicit-GEMM operand (csrc/stem_tc.cu) instead of the SIMT
 # kernel (864 FMAs per output pixel).  Built, checked on the SIMT emulation, not yet run on a B200: off unless
 # TSS_STEM_TC=1.
-STEM_TC = os.environ.get('TSS_STEM_TC', '0') == '1'
+STEM_TC = gate('STEM_TC')
 # With the tensor-core stem: its BatchNorm-backward apply inside the weight gradient's operand producer -- the largest
 # activation of the net (32 channels at 1/2 resolution) is not rewritten as dy.  Off unless TSS_STEM_BWD_FUSED=1.
-STEM_BWD_FUSED = os.environ.get('TSS_STEM_BWD_FUSED', '0') == '1'
+STEM_BWD_FUSED = gate('STEM_BWD_FUSED')
 
 # Training: fold the BatchNorm-backward reduction of a producer layer into the dgrad epilogue of its single
 # consumer (csrc/pwconv_tc_bnred.cu, csrc/dwconv_bnred.cu): one full read of (dz, y) and one launch less per
 # fused layer (20 of the 44 BatchNorm layers of Fast-SCNN; 4.66 -> 4.57 ms/step on B200).  TSS_FUSE_BNRED=0
 # selects the stand-alone reduction everywhere.
-FUSE_BNRED = os.environ.get('TSS_FUSE_BNRED', '1') == '1'
+FUSE_BNRED = gate('FUSE_BNRED')
 # Extended set: the stride-2 depthwise dgrad (its producers are the stem and the first expand conv: the largest
 # BatchNorm-backward instances) and two more single-consumer pairs at 1/8 resolution (fusion low-res branch,
 # classifier).  Built and CPU-checked, not yet validated on a B200: off unless TSS_FUSE_BNRED_EXT=1.
-FUSE_BNRED_EXT = os.environ.get('TSS_FUSE_BNRED_EXT', '0') == '1'
+FUSE_BNRED_EXT = gate('FUSE_BNRED_EXT')
 # BatchNorm-backward APPLY folded into the A-operand producer of the pointwise dgrad (csrc/pwconv_tc_bwd.cu):
 # dy is formed in registers and goes straight into the swizzled shared-memory tile of the tcgen05 GEMM (one
 # launch and one read of dy less per 1x1 layer without a residual).  Built and CPU-checked through the
 # emulated ABI, not yet validated on a B200: off unless TSS_FUSE_BNAPPLY=1.
-FUSE_BNAPPLY = os.environ.get('TSS_FUSE_BNAPPLY', '0') == '1'
+FUSE_BNAPPLY = gate('FUSE_BNAPPLY')
 # The same for the stride-1 depthwise layers whose dgrad already carries the producer's reduction
 # (csrc/dwconv_bwd_fused.cu: dz and y arrive as two TMA halo tiles, dy replaces dz in shared memory).
 # Off unless TSS_FUSE_BNAPPLY_DW=1.
-FUSE_BNAPPLY_DW = os.environ.get('TSS_FUSE_BNAPPLY_DW', '0') == '1'
+FUSE_BNAPPLY_DW = gate('FUSE_BNAPPLY_DW')
 # The four pyramid-pooling branches as grouped launches (csrc/ppm.cu): 3 launches forward and 5 backward instead
 # of ~18 and ~26.  Same status: off unless TSS_FUSE_PPM=1.
-FUSE_PPM = os.environ.get('TSS_FUSE_PPM', '0') == '1'
+FUSE_PPM = gate('FUSE_PPM')
 # BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu): one launch less per layer on the forward
 # chain (44 per step).  Same status: off unless TSS_FUSE_BNFIN=1.
-FUSE_BNFIN = os.environ.get('TSS_FUSE_BNFIN', '0') == '1'
+FUSE_BNFIN = gate('FUSE_BNFIN')
 # Inside a bottleneck, conv1's BatchNorm + ReLU applied by conv2 (depthwise) while it reads its input tile
 # (csrc/dwconv_bnin.cu): the expanded activation is never materialised, conv1's apply pass disappears.
 # Off unless TSS_FUSE_BNIN=1.
-FUSE_BNIN = os.environ.get('TSS_FUSE_BNIN', '0') == '1'
+FUSE_BNIN = gate('FUSE_BNIN')
 # The same hand-over from conv2 (depthwise) to conv3 (tensor-core pointwise, csrc/pwconv_tc_fwd_bnin.cu): the activated
 # tensor is written once by the GEMM's operand producer (the weight gradient needs it) and never read in the forward
 # pass.  Off unless TSS_FUSE_BNIN_PW=1.
-FUSE_BNIN_PW = os.environ.get('TSS_FUSE_BNIN_PW', '0') == '1'
+FUSE_BNIN_PW = gate('FUSE_BNIN_PW')
 
 
 class _BnLink:
@@ -572,7 +573,7 @@ class PPMBranches(torch.autograd.Function):
 
 # nn.Dropout of the classifiers on the library's own kernel (csrc/dropout.cu: counter-based mask, regenerated in
 # the backward pass, no mask tensor, no ATen kernels on the path).  Off unless TSS_OWN_DROPOUT=1 (not yet run on a B200).
-OWN_DROPOUT = os.environ.get('TSS_OWN_DROPOUT', '0') == '1'
+OWN_DROPOUT = gate('OWN_DROPOUT')
 
 
 class Dropout(torch.autograd.Function):
@@ -708,7 +709,7 @@ def attach_head(logits, scores):
 # trainer does it when the loss declares ``accepts_deferred_logits``, and only under TSS_DEFER_LOGITS=1 until the
 # path has run on a B200) the training forward returns this handle instead of launching the x8 up-sampling;
 # anything else that wants the tensor calls ``materialize()``.
-DEFER_LOGITS = os.environ.get('TSS_DEFER_LOGITS', '0') == '1'
+DEFER_LOGITS = gate('DEFER_LOGITS')
 
 
 class DeferredLogits:
