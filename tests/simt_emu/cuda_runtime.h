@@ -23,7 +23,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 #define __grid_constant__
 
@@ -118,6 +118,18 @@ inline unsigned __match_all_sync(unsigned, int v, int* pred) {
     *pred = same ? 1 : 0;
     return same ? (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) : 0u;
 }
+inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+    uint32_t all[32]; int n;
+    tss_emu_warp_gather(v, all, n);
+    unsigned r = 0;
+    for (int i = 0; i < n; ++i) r += all[i];
+    return r;
+}
+inline int __reduce_add_sync(unsigned m, int v) { return (int)__reduce_add_sync(m, (unsigned)v); }
+inline float __expf(float x) { return expf(x); }
+inline float __logf(float x) { return logf(x); }
+inline float __log2f(float x) { return log2f(x); }
+inline float __exp2f(float x) { return exp2f(x); }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
@@ -170,6 +182,7 @@ struct cudaLaunchConfig_t {
     unsigned numAttrs;
 };
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 4; return cudaSuccess; }   // 4 "SMs": small grids

@@ -30,3 +30,15 @@ MBar mbars[sizeof(dyn_smem) / 8];
 std::mutex mbar_mutex;
 float tmem[128][512];
 }  // namespace tss_emu
+
+// The two tcgen05 GEMMs that are not converted to the emulation yet (csrc/pwconv_tc.cu): the SIMT front (pwconv_simt.cu)
+// refers to them for impl 1; a host build reports an error instead of leaving the symbols unresolved.
+int tss_pwconv_fwd_tc(const void*, const void*, void*, int64_t, int, int, int64_t, int64_t, const float*, const float*,
+                      const void*, int64_t, int, double*, cudaStream_t) {
+    tss_set_error("pwconv_fwd (impl 1) is not part of the host emulation");
+    return 1;
+}
+int tss_pwconv_wgrad_tc(const void*, const void*, float*, int64_t, int, int, int64_t, int64_t, cudaStream_t) {
+    tss_set_error("pwconv_wgrad (impl 1) is not part of the host emulation");
+    return 1;
+}

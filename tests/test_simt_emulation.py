@@ -19,6 +19,7 @@ from torch_semantic_segmentation_b200 import _lib, ops
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, 'torch_semantic_segmentation_b200', 'csrc')
 EMU = os.path.join(ROOT, 'tests', 'simt_emu')
+FULL_EXCLUDE = ('pwconv_tc.cu', 'dwpw_tc.cu', 'api.cu')       # raw-asm tcgen05 GEMMs not converted yet; api.cu's role is emu_runtime.cpp
 SOURCES = ['ppm.cu', 'augment.cu', 'dwconv_bnred.cu',        # dwconv_bnred.cu: the stride-2 (plain SIMT) kernel only
            'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu', 'dwconv_bwd_fused.cu', 'metrics.cu', 'dropout.cu', 'dwconv_bnin.cu', 'pwconv_tc_fwd_bnin.cu',
            'pwconv_tc_bnred.cu', 'dwconv.cu', 'dwconv_tma.cu']       # validated on the B200: calibrate the emulation itself                               # on the functional tcgen05/TMA/mbarrier emulation
@@ -566,3 +567,69 @@ def test_stem_weight_gradient_with_bn_apply_on_the_tcgen05_emulation(emulated, N
         outs[name] = (dw - 0.25, dga, dbe)
     assert rel(outs['emu'][0], outs['ref'][0]) < 5e-3
     assert rel(outs['emu'][1], outs['ref'][1]) < 1e-6 and rel(outs['emu'][2], outs['ref'][2]) < 1e-6
+
+
+@pytest.mark.skipif(os.environ.get('TSS_EMU_FULL') != '1', reason='~2 min: set TSS_EMU_FULL=1')
+def test_whole_training_step_and_evaluation_on_the_emulation(tmp_path):
+    """EVERY kernel call of one fp32 Fast-SCNN optimisation step (forward, fused head, backward, AdamW: ~325 calls) and
+    of an evaluation forward + confusion matrix runs as real kernel code on the emulation and is compared, call by call
+    on identical inputs, with the torch emulation of the ABI.  (End-to-end comparisons of this tiny net are dominated by
+    the 2-sample BatchNorm of the pyramid's bin-1 branch; per-call comparisons are not.)"""
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.metrics import ConfusionMatrix
+    from torch_semantic_segmentation_b200.models import fastscnn
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    so = str(tmp_path / 'host_emu_all.so')
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith('.cu') and f not in FULL_EXCLUDE)
+    subprocess.check_call(['g++', '-std=c++20', '-O1', '-ffp-contract=off', '-DTSS_HOST_EMU', '-x', 'c++', '-shared', '-fPIC', '-pthread',
+                           '-I', EMU, '-I', CSRC] + [os.path.join(CSRC, f) for f in files] + [os.path.join(EMU, 'emu_runtime.cpp'), '-o', so])
+    emu, fake = EmulatedBackend(so), FakeBackend()
+    inner, bad, seen = emu.call, [], set()
+
+    def checked(name, kw):
+        if 'table' in kw or not hasattr(emu.lib, name):          # address tables point at the originals / not emulated
+            return inner(name, kw)
+        clones = {}
+        for k, v in kw.items():
+            if isinstance(v, torch.Tensor):
+                base = v._base if v._base is not None else v
+                cb = base.clone()
+                clones[k] = cb.as_strided(v.shape, v.stride(), v.storage_offset()) if v._base is not None else cb
+            else:
+                clones[k] = v
+        fake.call(name, clones)
+        r = inner(name, kw)
+        seen.add(name)
+        for k, v in kw.items():
+            if isinstance(v, torch.Tensor) and v.numel() > 0:
+                e = rel(v, clones[k])
+                if e > (2e-3 if (v.dtype == torch.float32 and v.dim() == 1) else 2e-4):
+                    bad.append((name, k, e, tuple(v.shape)))
+        return r
+    emu.call = checked
+    prev = _lib._backend
+    _lib.set_backend(emu)
+    try:
+        torch.manual_seed(0)
+        model = fastscnn(3, 19).train()
+        opt = FlatAdamW(model.parameters(), lr=1e-3)
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(2, 3, 32, 64, generator=g)
+        y = torch.randint(0, 19, (2, 32, 64), generator=g)
+        y[0, :4] = 255
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        opt.zero_grad()
+        loss = CrossEntropyLoss(ignore_index=255)(model(x), y)
+        loss.backward()
+        opt.step()
+        assert torch.isfinite(loss.detach())
+        cm = ConfusionMatrix(19)
+        with torch.no_grad():
+            cm.update((model.eval()(x), y))
+        assert int(cm.compute(sync=False).sum()) == int((y != 255).sum())
+    finally:
+        _lib.set_backend(prev)
+    assert not bad, bad[:5]
+    assert len(seen) >= 20 and emu.emulated_calls > 330, (len(seen), emu.emulated_calls)

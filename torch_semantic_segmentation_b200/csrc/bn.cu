@@ -117,7 +117,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T*
                      float* __restrict__ sums, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy,
                      int relu, int PL) {
     pdl_wait();
-    extern __shared__ float s_sum[];   // [2*C]
+    TSS_DYN_SMEM(float, s_sum);   // [2*C]
     const int CG = C >> 3;
     const int cg = threadIdx.x % CG;
     const int pl = threadIdx.x / CG;

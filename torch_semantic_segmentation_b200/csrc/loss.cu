@@ -169,9 +169,13 @@ constexpr int kHeadCols = 256;
 constexpr int kHeadMaxRows = 40;      // output rows per source-row interval: ceil(1/scale) + 1 (x32 heads: 34)
 
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef TSS_HOST_EMU
+    return exp2f(x);            // host build for tests/simt_emu
+#else
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 
 template <typename T, int C>
@@ -181,7 +185,7 @@ upsample_ce_kernel(const T* __restrict__ x, const int64_t* __restrict__ target, 
                    float* __restrict__ pixel_loss, const float* __restrict__ ohem, int Hi, int Wi, int Ho, int Wo,
                    int64_t ldx, int64_t lddx, int64_t ignore_index, float sh, float sw, int chunks) {
     pdl_wait();
-    extern __shared__ float s_mem[];
+    TSS_DYN_SMEM(float, s_mem);
     float o_cut = 0.f, o_above = 0.f, o_tie = 0.f, o_wtie = 0.f;       // OHEM: per-pixel weight from the pixel's own loss
     if (ohem != nullptr) { o_cut = __ldg(ohem); o_above = __ldg(ohem + 1); o_tie = __ldg(ohem + 2); o_wtie = __ldg(ohem + 3); }
     constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;

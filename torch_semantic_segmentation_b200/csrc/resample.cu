@@ -22,7 +22,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, int N, int H, int W, int C, Bins bins, int PL) {
     pdl_wait();
-    extern __shared__ float s_acc[];   // [C]
+    TSS_DYN_SMEM(float, s_acc);   // [C]
     const int cells = bins.off[bins.n];
     const int n = blockIdx.x / cells;
     int cell = blockIdx.x - n * cells;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kThreads)
 upsample_logits_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int Hi, int Wi, int Ho, int Wo, int C,
                            int64_t ldx, float sh, float sw) {
     pdl_wait();
-    extern __shared__ float s_row[];   // [Wi][C]
+    TSS_DYN_SMEM(float, s_row);   // [Wi][C]
     const int n = blockIdx.x / Ho, ho = blockIdx.x - n * Ho;
     int h0, h1; float lh;
     ac_source(sh, ho, Hi, h0, h1, lh);
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kThreads)
 upsample_logits_bwd_kernel(const T* __restrict__ dy, float* __restrict__ dx, int Hi, int Wi, int Ho, int Wo,
                            int C, int64_t lddx, float sh, float sw) {
     pdl_wait();
-    extern __shared__ float s_t[];     // [2][Wo]
+    TSS_DYN_SMEM(float, s_t);     // [2][Wo]
     const int hi = blockIdx.x % Hi;
     const int c = (blockIdx.x / Hi) % C;
     const int n = blockIdx.x / (Hi * C);

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kWgThreads)
 stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw,
                   int N, int H, int W, int Ho, int Wo, int tiles_h, int tiles_w) {
     pdl_wait();
-    extern __shared__ __align__(16) float smem[];
+    TSS_DYN_SMEM(float, smem);
     float* in_s = smem;                 // [3][PH][PWP]
     float* dy_s = smem + kPatch;        // [TH*TW][CO]
     const int tid = threadIdx.x;
