@@ -320,7 +320,7 @@ def main():
         opt.zero_grad()
         out = model(x)
         loss = loss_fn(out, y)
-        with unit_loss_grad():
+        with unit_loss_grad(loss):
             loss.backward()
         opt.step()
         return loss.detach()

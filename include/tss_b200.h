@@ -301,14 +301,15 @@ int tss_cast_from_f32(const float* src, void* dst, int64_t n, int dtype, void* s
  * replaces nn.CrossEntropyLoss(ignore_index=255) (scripts/train_fastscnn.py:132) and the
  * F.cross_entropy(reduction='none') inside losses/ohem_loss.py:11-12.
  * logits NCHW [N][C][HW] (C <= 32, HW % 4 == 0), target int64 [N][HW].
- * count_valid: nvalid[0] = #(target != ignore_index).
+ * count_valid: nvalid[0] = #(target != ignore_index and 0 <= target < num_classes) -- the pixels that carry a loss
+ * in fwd (torch raises on a label outside [0, C); here it is treated as ignored, consistently in both kernels).
  * fwd: ONE pass computes per-pixel loss, the loss sum (loss_sum[0] += , fp64) and, if
  * dlogits != NULL, the gradient of the MEAN loss: (softmax - onehot)/nvalid[0] (0 at ignored
  * pixels).  pixel_loss (fp32 [N][HW], may be NULL) receives the reduction='none' values.
  * ohem != NULL (device float[4] = {cut, w_above, tie, w_tie} from tss_ohem_select): the gradient of
  * pixel i is weighted by (loss_i > cut ? w_above : loss_i == tie ? w_tie : 0) instead of 1/nvalid. */
-int tss_ce_count_valid(const int64_t* target, int64_t n, int64_t ignore_index, int64_t* nvalid,
-                       void* stream);
+int tss_ce_count_valid(const int64_t* target, int64_t n, int64_t ignore_index, int64_t num_classes,
+                       int64_t* nvalid, void* stream);
 int tss_ce_fwd(const void* logits, const int64_t* target, int N, int C, int64_t HW,
                int64_t ignore_index, const int64_t* nvalid, double* loss_sum, float* pixel_loss,
                void* dlogits, const float* ohem, int dtype, void* stream);

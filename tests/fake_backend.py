@@ -501,8 +501,8 @@ class FakeBackend:
         return 0
 
     # ---------------------------------------------------------------- loss / metrics
-    def tss_ce_count_valid(self, target, n, ignore_index, nvalid):
-        nvalid.fill_(int((target != ignore_index).sum()))
+    def tss_ce_count_valid(self, target, n, ignore_index, num_classes, nvalid):
+        nvalid.fill_(int(((target != ignore_index) & (target >= 0) & (target < num_classes)).sum()))
         return 0
 
     @staticmethod

@@ -373,6 +373,27 @@ def test_cross_entropy(N, H, W, frac, dtype):
     assert rel(pixel, ref_px) < 1e-5
 
 
+def test_cross_entropy_stray_labels_do_not_dilute_the_mean():
+    """A label outside [0, C) that is not ignore_index (torch raises on it) carries no loss and no gradient in the
+    kernels; it must not be counted in the mean's denominator either."""
+    g = gen(5)
+    logits = torch.randn(1, 19, 8, 12, generator=g)
+    target = torch.randint(0, 19, (1, 8, 12), generator=g)
+    target[0, 0, :5] = 255
+    stray = target.clone()
+    stray[0, 1, :4] = 37
+    stray[0, 2, :3] = -2
+    clean = stray.clone()
+    clean[(stray < 0) | (stray >= 19)] = 255
+    loss, dl, _, nvalid = ops.ce_forward(logits.cuda(), stray.cuda(), 255, want_grad=True)
+    ref_in = logits.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_in, clean, ignore_index=255)
+    ref.backward()
+    assert int(nvalid) == int((clean != 255).sum())
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    assert rel(dl, ref_in.grad) < 1e-5
+
+
 # ------------------------------------------------------------------ confusion matrix ---
 @pytest.mark.parametrize('dtype', DTYPES)
 @pytest.mark.parametrize('N,C,Hi,Wi,frac', [(2, 19, 12, 20, 0.1), (1, 19, 4, 4, 0.0), (2, 19, 3, 5, 0.5), (1, 11, 6, 7, 0.1),

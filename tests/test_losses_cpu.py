@@ -86,3 +86,73 @@ def test_deep_supervision_recipe_of_the_reference_script(fake_backend):
     model.eval()
     with torch.no_grad():
         assert model(x).shape == (2, 19, 96, 160)            # eval mode: the model's output only
+
+
+class _Recipe(torch.nn.Module):
+    """scripts/train_fastscnn.py:131-137: OHEM on the main output + 0.4 * CE on each auxiliary output."""
+
+    def __init__(self, numel_frac=0.1):
+        super().__init__()
+        self.ohem, self.ce = OHEMLoss(ignore_index=255, numel_frac=numel_frac), CrossEntropyLoss(ignore_index=255)
+
+    def forward(self, y_pred, y):
+        out, (aux1, aux2) = y_pred
+        return self.ohem(out, y) + 0.4 * self.ce(aux1, y) + 0.4 * self.ce(aux2, y)
+
+
+def _wrapped_fastscnn():
+    torch.manual_seed(0)
+    model = fastscnn(3, 19)
+    model = DeepSupervisionWrapper(model, [
+        (model.downsample, AuxiliaryHead(Classifier(64, 19), 8)),
+        (model.features, AuxiliaryHead(Classifier(128, 19), 32)),
+    ])
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    return model
+
+
+def stock_head_gradients(model, x, y, weight):
+    """Gradient of ``weight * CE(upsample(conv1x1(f)))`` w.r.t. the last conv of auxiliary head 0, with stock torch ops
+    on the feature ``f`` that conv saw in ``model(x)``."""
+    seen = {}
+    last = model.auxiliary[0][0][3]
+    h = last.register_forward_hook(lambda m, args, out: seen.setdefault('f', args[0].detach().float().cpu()))
+    model.train()
+    model(x)
+    h.remove()
+    w = last.weight.detach().float().cpu().clone().requires_grad_(True)
+    b = last.bias.detach().float().cpu().clone().requires_grad_(True)
+    logits = torch.nn.functional.interpolate(torch.nn.functional.conv2d(seen['f'], w, b), scale_factor=8,
+                                             mode='bilinear', align_corners=True)
+    (weight * torch.nn.functional.cross_entropy(logits, y.cpu(), ignore_index=255)).backward()
+    return w.grad, b.grad
+
+
+def test_trainer_honours_the_loss_weights_of_the_recipe(fake_backend):
+    """The trainer's backward must give the auxiliary terms their 0.4 (a process-wide 'the seed
+    gradient is 1' promise made every loss term back-propagate with weight 1).  lr = 0 keeps the weights and
+    leaves the step's gradients in ``.grad``."""
+    from torch_semantic_segmentation_b200.engine import create_segmentation_trainer
+    model = _wrapped_fastscnn()
+    x, y = train_batch('fastscnn')
+    gw, gb = stock_head_gradients(model, x, y, 0.4)
+    # BatchNorm running statistics moved in that probe forward, batch statistics (training mode) did not
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)
+    trainer = create_segmentation_trainer(model, opt, _Recipe(), 'cpu', logging=False)
+    trainer.run([(x, y)], max_epochs=1)
+    last = model.auxiliary[0][0][3]
+    assert rel(last.weight.grad, gw) < 1e-4, rel(last.weight.grad, gw)
+    assert rel(last.bias.grad, gb) < 1e-4
+    # and a plain single-term loss still takes the unscaled fast path with the right value
+    model2 = _wrapped_fastscnn()
+    g1w, _ = stock_head_gradients(model2, x, y, 1.0)
+
+    class OnlyAux(torch.nn.Module):
+        def forward(self, y_pred, t):
+            return CrossEntropyLoss(ignore_index=255)(y_pred[1][0], t)
+    trainer2 = create_segmentation_trainer(model2, torch.optim.SGD(model2.parameters(), lr=0.0), OnlyAux(), 'cpu',
+                                           logging=False)
+    trainer2.run([(x, y)], max_epochs=1)
+    assert rel(model2.auxiliary[0][0][3].weight.grad, g1w) < 1e-4

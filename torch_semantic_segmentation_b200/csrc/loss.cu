@@ -33,16 +33,19 @@ template <> struct Quad<bf16> {
 };
 
 __global__ void __launch_bounds__(kThreads)
-count_valid_kernel(const int64_t* __restrict__ target, int64_t n, int64_t ignore_index,
+count_valid_kernel(const int64_t* __restrict__ target, int64_t n, int64_t ignore_index, int64_t num_classes,
                    unsigned long long* __restrict__ nvalid) {
     pdl_wait();
+    // the same predicate as ce_fwd_kernel / upsample_ce_kernel: a label outside [0, C) carries no loss and no
+    // gradient there, so it must not sit in the mean's denominator either
+    auto counts = [=](int64_t t) { return (unsigned int)(t != ignore_index && t >= 0 && t < num_classes); };
     unsigned int cnt = 0;
     const int64_t n2 = n >> 1;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kThreads) {
         const longlong2 t = __ldg(reinterpret_cast<const longlong2*>(target) + i);
-        cnt += (t.x != ignore_index) + (t.y != ignore_index);
+        cnt += counts(t.x) + counts(t.y);
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) cnt += target[n - 1] != ignore_index;
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) cnt += counts(target[n - 1]);
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     __shared__ unsigned int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
@@ -388,16 +391,17 @@ int launch_head(const void* x, const int64_t* target, float* dx32, double* loss_
 
 }  // namespace
 
-extern "C" int tss_ce_count_valid(const int64_t* target, int64_t n, int64_t ignore_index, int64_t* nvalid,
-                                  void* stream) {
+extern "C" int tss_ce_count_valid(const int64_t* target, int64_t n, int64_t ignore_index, int64_t num_classes,
+                                  int64_t* nvalid, void* stream) {
     TSS_REQUIRE(n > 0, "ce_count_valid: empty target");
+    TSS_REQUIRE(num_classes > 0, "ce_count_valid: num_classes must be positive");
     TSS_REQUIRE(((uintptr_t)target & 15) == 0, "ce_count_valid: target must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     TSS_CUDA(cudaMemsetAsync(nvalid, 0, sizeof(int64_t), st));
     int64_t want = ceil_div64(n / 2 + 1, kThreads * 4);
     int64_t cap = (int64_t)tss_num_sms() * 8;
     const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
-    tss_launch(count_valid_kernel, grid, kThreads, 0, st, target, n, ignore_index, (unsigned long long*)nvalid);
+    tss_launch(count_valid_kernel, grid, kThreads, 0, st, target, n, ignore_index, num_classes, (unsigned long long*)nvalid);
     TSS_LAUNCH_CHECK("ce_count_valid");
     return TSS_OK;
 }

@@ -200,6 +200,9 @@ class _BatchStager:
             slot = self.slots[k] = (torch.empty(x.shape, dtype=x.dtype, device=self.device),
                                     torch.empty(y.shape, dtype=y.dtype, device=self.device))
             self.free[k] = None
+            # the caching allocator may have handed out a block that kernels already enqueued on the compute stream
+            # still use (freed on the host, not yet on the device): the first copy into a NEW slot waits for them
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
         if self.free[k] is not None:
             self.stream.wait_event(self.free[k])
         with torch.cuda.stream(self.stream):
@@ -247,16 +250,17 @@ class GraphedTrainStep:
             optimizer.zero_grad()
             xs, ys = (self.x, self.y) if transform is None else transform.apply(self.x, self.y, self.geom)
             loss = loss_fn(model(xs), ys)
-            with unit_loss_grad():
+            with unit_loss_grad(loss):
                 loss.backward()
             optimizer.step()
             return loss.detach()
 
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        self.warmup_loss = None
         with torch.cuda.stream(side):
             for _ in range(warmup):          # allocator / cuBLAS-free warm-up on a side stream
-                body()
+                self.warmup_loss = body()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         from . import _lib
@@ -265,7 +269,7 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss = body()
         self.kernels_per_step = _lib.launch_count() - before   # libtss_b200 kernel nodes in the graph
-        self.warmup_steps = warmup + 1        # steps the optimizer already took on the example batch
+        self.warmup_steps = warmup            # steps the optimizer really took on the example batch (capture runs nothing)
 
     def matches(self, x, y):
         return (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype) == self.key
@@ -368,13 +372,18 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
                 first = not graphed
                 graphed[key] = g = GraphedTrainStep(model, optimizer, loss_fn, xd, yd, transform=transform,
                                                     warmup=3 if first else 0, bind=key != 'step')
-                if not first:
-                    g.graph.replay()         # capturing does not execute: this is the step on the current batch
+                if first:
+                    # capture executes nothing and g.loss is a never-written buffer of the graph's pool: the step(s) on
+                    # this batch were the warm-up ones, its loss is the last warm-up step's
+                    out = g.warmup_loss
+                else:
+                    g.graph.replay()         # this is the step on the current batch
+                    out = g.loss
                 if staged is not None:
                     stager.release(staged)
                 if SLOT_GRAPHS:
                     _trainer.prefetch_next()
-                return g.loss.item()
+                return out.item()
             x, y = fetch(batch) if staged is not None else batch
             if not g.matches(x, y):
                 raise RuntimeError('cuda_graph=True needs a fixed batch shape; got %s' % (tuple(x.shape),))
@@ -391,7 +400,7 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
         y_pred = model(x)
         loss = loss_fn(y_pred, y)
 
-        with unit_loss_grad():      # backward() seeds d(loss)/d(loss) = 1: no rescale pass needed
+        with unit_loss_grad(loss):      # backward() seeds d(loss)/d(loss) = 1: no rescale pass needed
             loss.backward()
 
         optimizer.step()

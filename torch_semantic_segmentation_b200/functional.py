@@ -28,23 +28,33 @@ _tls = threading.local()
 
 
 class unit_loss_grad:
-    """Context manager: promise that ``loss.backward()`` is called with the implicit
-    gradient 1.0, so that :class:`CrossEntropy` can hand its fused gradient on without
-    a rescaling pass over the logits-sized tensor."""
+    """``with unit_loss_grad(loss): loss.backward()`` -- tells the loss Function that produced ``loss`` that the
+    gradient it is about to receive is the implicit seed 1.0, so that it can hand its fused gradient on without a
+    rescaling pass.  The mark is put on ``loss.grad_fn`` itself and only if that node IS one of this module's loss
+    Functions: a loss term that reaches the total through any other node (``0.4 * ce(aux)``, a sum of terms) is not
+    marked and multiplies its gradient by the ``grad_out`` autograd hands it (train_fastscnn.py:134-136 weights
+    the auxiliary terms by 0.4)."""
 
-    # process-wide on purpose: backward runs on autograd's per-device worker thread while the
-    # thread that called backward() is blocked inside this context manager
-    depth = 0
+    def __init__(self, loss=None):
+        node = getattr(loss, 'grad_fn', None)
+        self.node = node if (node is not None and type(node).__name__ in _SEEDED_LOSS_NODES) else None
 
     def __enter__(self):
-        unit_loss_grad.depth += 1
+        if self.node is not None:
+            self.node._tss_unit_seed = True
+        return self
 
     def __exit__(self, *exc):
-        unit_loss_grad.depth -= 1
+        if self.node is not None:
+            self.node._tss_unit_seed = False
 
 
-def _unit_grad():
-    return unit_loss_grad.depth > 0
+# autograd names the backward node of ``class X(Function)`` ``XBackward``
+_SEEDED_LOSS_NODES = ('UpsampleCrossEntropyBackward', 'OhemCrossEntropyBackward', 'CrossEntropyBackward')
+
+
+def _unit_grad(ctx):
+    return getattr(ctx, '_tss_unit_seed', False)
 
 
 _grad_ready_hook = None
@@ -632,7 +642,7 @@ class UpsampleCrossEntropy(torch.autograd.Function):
         (dx,) = ctx.saved_tensors
         if dx is None:
             return None, None, None, None, None
-        if not _unit_grad():
+        if not _unit_grad(ctx):
             dx = dx * grad_out.to(dx.dtype)       # 1/64 of the logits' size: not worth a kernel
         return dx, None, None, None, None
 
@@ -692,7 +702,7 @@ class OhemCrossEntropy(torch.autograd.Function):
         (grad,) = ctx.saved_tensors
         if grad is None:
             return None, None, None, None, None, None
-        if not _unit_grad():
+        if not _unit_grad(ctx):
             grad = grad * grad_out.to(grad.dtype)
         return grad, None, None, None, None, None
 
@@ -772,6 +782,7 @@ class CrossEntropy(torch.autograd.Function):
         (dlogits,) = ctx.saved_tensors
         if dlogits is None:
             return None, None, None
-        if not _unit_grad():
-            dlogits = ops.scale_inplace(dlogits, grad_out.to(torch.float32).reshape(1))
+        if not _unit_grad(ctx):
+            # out of place: the saved gradient stays the unit-weight one if backward runs again (retain_graph)
+            dlogits = dlogits * grad_out.to(dlogits.dtype)
         return dlogits, None, None

@@ -674,7 +674,8 @@ def ce_forward(logits, target, ignore_index, want_grad, want_pixel_loss=False, o
         target = target.long().contiguous()
     dev = logits.device
     nvalid = torch.empty(1, dtype=torch.int64, device=dev)
-    _lib.call('tss_ce_count_valid', target=target, n=target.numel(), ignore_index=ignore_index, nvalid=nvalid)
+    _lib.call('tss_ce_count_valid', target=target, n=target.numel(), ignore_index=ignore_index, num_classes=C,
+              nvalid=nvalid)
     loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
     dlogits = torch.empty_like(logits) if want_grad else None
     pixel = torch.empty((N, H, W), dtype=torch.float32, device=dev) if want_pixel_loss else None
