@@ -47,3 +47,27 @@ def ohem_case(name):
     # few hard pixels: make the logits nearly perfect so that loss[n] <= thresh -> top-n
     onehot = torch.zeros_like(logits).scatter_(1, target.clamp(max=18).unsqueeze(1), 12.0)
     return logits * 0.1 + onehot, target, dict(ignore_index=255, numel_frac=0.05)
+
+
+def scene_batch(n, h, w, seed, classes=19, ignore_frac=0.05):
+    """Cityscapes-like synthetic scenes for whole-network parity at the benchmark shapes: piecewise-smooth class
+    regions (19 smooth random fields, argmax), image = class colour + smooth shading + a little sensor noise, every
+    image with its own class mix, gain and colour offset; labels carry ``ignore_frac`` of 255.  Unlike white noise
+    with independent random labels (the throughput benchmark's input) the labels are a function
+    of the image, so the gradients carry signal instead of being the residual of a cancellation, and per-image
+    diversity keeps the batch statistics of the pooled pyramid branches away from zero variance."""
+    import torch.nn.functional as F
+    g = _gen(seed)
+    fields = torch.randn(n, classes, max(h // 32, 2), max(w // 32, 2), generator=g)
+    fields = fields + 1.5 * torch.randn(n, classes, 1, 1, generator=g)
+    fields = F.interpolate(fields, size=(h, w), mode='bilinear', align_corners=False)
+    y = fields.argmax(1)
+    palette = torch.randn(classes, 3, generator=g)
+    x = palette[y].permute(0, 3, 1, 2).contiguous()
+    shade = F.interpolate(torch.randn(n, 3, max(h // 16, 2), max(w // 16, 2), generator=g), size=(h, w),
+                          mode='bilinear', align_corners=False)
+    x = x + 0.5 * shade + 0.1 * torch.randn(n, 3, h, w, generator=g)
+    x = x * torch.exp(torch.randn(n, 1, 1, 1, generator=g) * 0.5) + torch.randn(n, 3, 1, 1, generator=g) * 0.7
+    y = y.clone()
+    y[torch.rand(n, h, w, generator=g) < ignore_frac] = 255
+    return x.contiguous(), y

@@ -1,0 +1,208 @@
+"""Data parallelism on real GPUs over NCCL (world size 2; skipped on a single-GPU box): the same invariants as
+tests/test_distributed_cpu.py, but with the sm_100a kernels, the side-stream bucketed all-reduce, the wgrad lane and
+the CUDA-graphed step -- the code that SCALE_rNN.json measures.
+
+* DP(2 ranks) gradients after the bucketed NCCL all-reduce + 1/world averaging == the mean of the single-process
+  gradients of the two ranks' batches (per-rank BatchNorm statistics, scripts/train_fastscnn.py:150 apex DDP);
+* with SyncBN (scripts/train_fastscnn.py:145) the DP gradients == single-process gradients on the concatenated batch;
+* every rank holds identical parameters after eager and after graph-replayed optimisation steps;
+* confusion-matrix shards sum (int64 all-reduce) to the single-process matrix, exactly.
+
+Run here with ``gpurun --gpus 2 -- python -m pytest tests/test_distributed_gpu.py -m gpu``.
+"""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _setup(rank, world, port):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', init_method='env://', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+
+
+def _batch(seed, n=2, h=96, w=160, ignore=True):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 3, h, w, generator=g)
+    y = torch.randint(0, 19, (n, h, w), generator=g)
+    if ignore:
+        y[torch.rand(n, h, w, generator=g) < 0.1] = 255
+    return x.cuda(), y.cuda()
+
+
+def _make(seed, dtype):
+    from torch_semantic_segmentation_b200.models import fastscnn
+    torch.manual_seed(seed)
+    m = fastscnn(3, 19).cuda().set_compute_dtype(dtype)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    return m.train()
+
+
+def _flat_grads(model):
+    return torch.cat([p.grad.reshape(-1).float() for p in model.parameters()])
+
+
+def _train_worker(rank, world, port, out, dtype_name):
+    _setup(rank, world, port)
+    from torch_semantic_segmentation_b200.distributed import GradientAllReducer, broadcast_parameters
+    from torch_semantic_segmentation_b200.engine import GraphedTrainStep
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    dtype = getattr(torch, dtype_name)
+    loss_fn = CrossEntropyLoss(ignore_index=255)
+    singles = []
+    for r in range(world):                                   # both ranks' single-process gradients on rank 0's weights
+        m = _make(0, dtype)
+        x, y = _batch(100 + r)
+        loss_fn(m(x), y).backward()
+        singles.append(_flat_grads(m))
+    want = sum(singles) / world
+
+    model = _make(rank, dtype)                               # different init per rank: the broadcast must fix that
+    broadcast_parameters(model)
+    opt = FlatAdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    reducer = GradientAllReducer(opt, num_buckets=4).install()
+    x, y = _batch(100 + rank)
+    opt.zero_grad()
+    loss_fn(model(x), y).backward()
+    launched_in_backward = sum(1 for b in reducer.buckets if b[4])
+    reducer.finish()
+    torch.cuda.synchronize()
+    got = _flat_grads(model) * opt.grad_scale
+    err = float((got - want).norm() / want.norm())
+    # the all-reduced arena is bit-identical on both ranks (NCCL sums in one order for everybody)
+    mine = opt.grad_arena.clone()
+    both = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(both, mine)
+    grads_identical = bool(torch.equal(both[0], both[1]))
+    opt.step()
+
+    def params_same():
+        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        return all(torch.equal(gathered[0], g) for g in gathered)
+    same_eager = params_same()
+    # the CUDA-graphed step (what bench.py replays at N > 1): NCCL all-reduces captured inside the graph
+    g = GraphedTrainStep(model, opt, loss_fn, x, y)
+    losses = []
+    for _ in range(3):
+        losses.append(float(g(x, y)))
+    torch.cuda.synchronize()
+    same_graph = params_same()
+    if rank == 0:
+        torch.save({'err': err, 'grads_identical': grads_identical, 'same_eager': same_eager, 'same_graph': same_graph,
+                    'launched_in_backward': launched_in_backward, 'buckets': len(reducer.buckets), 'losses': losses}, out)
+    dist.destroy_process_group()
+
+
+def _syncbn_worker(rank, world, port, out, dtype_name):
+    _setup(rank, world, port)
+    from torch_semantic_segmentation_b200.distributed import convert_syncbn_model
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    dtype = getattr(torch, dtype_name)
+    x, y = _batch(7, n=2 * world, ignore=False)              # no ignored pixels: equal valid counts per rank
+    loss_fn = CrossEntropyLoss(ignore_index=255)
+    single = _make(0, dtype)
+    loss_fn(single(x), y).backward()
+    want = _flat_grads(single)
+    want_rm = single.downsample[0][1].running_mean.clone()
+    model = convert_syncbn_model(_make(0, dtype))
+    lo = 2 * rank
+    loss_fn(model(x[lo:lo + 2]), y[lo:lo + 2]).backward()
+    got = _flat_grads(model)
+    dist.all_reduce(got)
+    got /= world
+    torch.cuda.synchronize()
+    err = float((got - want).norm() / want.norm())
+    rm_err = float((model.downsample[0][1].running_mean - want_rm).abs().max())
+    head, head_ref = model.classifier[3].weight.grad.clone().float(), single.classifier[3].weight.grad.float()
+    dist.all_reduce(head)
+    head_err = float((head / world - head_ref).norm() / head_ref.norm())
+    if rank == 0:
+        torch.save({'err': err, 'rm_err': rm_err, 'head_err': head_err}, out)
+    dist.destroy_process_group()
+
+
+def _eval_worker(rank, world, port, out, _dtype_name):
+    _setup(rank, world, port)
+    from torch_semantic_segmentation_b200.distributed import shard_range
+    from torch_semantic_segmentation_b200.metrics import ConfusionMatrix, metrics_from_cm
+    n_maps = 7
+
+    def pair(i):
+        g = torch.Generator().manual_seed(4321 + i)
+        p = torch.randint(0, 19, (1, 128, 256), generator=g)
+        l = torch.randint(0, 19, (1, 128, 256), generator=g)
+        l[torch.rand(1, 128, 256, generator=g) < 0.1] = 255
+        return p.cuda(), l.cuda()
+
+    lo, hi = shard_range(n_maps, world, rank)
+    cm = ConfusionMatrix(19)
+    for i in range(lo, hi):
+        cm.update(pair(i))
+    total = cm.compute()                                     # int64 NCCL all-reduce
+    if rank == 0:
+        single = ConfusionMatrix(19)
+        for i in range(n_maps):
+            single.update(pair(i))
+        ref = single.compute(sync=False)
+        torch.save({'equal': bool(torch.equal(total.cpu(), ref.cpu())), 'shard': (lo, hi), 'count': int(total.sum()),
+                    'miou_equal': float(metrics_from_cm(total)['miou']) == float(metrics_from_cm(ref)['miou'])}, out)
+    dist.destroy_process_group()
+
+
+def _run(worker, tmp_path, dtype_name='float32'):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (gpurun --gpus 2)')
+    out = str(tmp_path / 'result.pt')
+    mp.spawn(worker, args=(2, _free_port(), out, dtype_name), nprocs=2, join=True)
+    return torch.load(out)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('dtype_name,bound', [('float32', 1e-4), ('bfloat16', 2e-2)])
+def test_nccl_bucketed_gradient_allreduce_world2(tmp_path, dtype_name, bound):
+    r = _run(_train_worker, tmp_path, dtype_name)
+    # fp32: the only difference to the single-process gradients is the order of two fp32 additions per element;
+    # bf16: atomics inside the bf16 kernels make two runs of the same batch differ at rounding level
+    assert r['err'] < bound, r
+    assert r['grads_identical'], 'ranks hold different all-reduced gradients'
+    assert r['same_eager'], 'ranks diverged after one eager optimizer step'
+    assert r['same_graph'], 'ranks diverged after graph-replayed optimizer steps'
+    assert r['buckets'] >= 2 and r['launched_in_backward'] >= 1
+    assert all(l == l for l in r['losses'])
+
+
+@pytest.mark.timeout(600)
+def test_nccl_syncbn_matches_single_process_on_the_concatenated_batch_world2(tmp_path):
+    r = _run(_syncbn_worker, tmp_path)
+    assert r['rm_err'] < 1e-5, r
+    assert r['head_err'] < 1e-4, r
+    assert r['err'] < 1e-2, r
+
+
+@pytest.mark.timeout(600)
+def test_nccl_confusion_matrix_shards_sum_exactly_world2(tmp_path):
+    r = _run(_eval_worker, tmp_path)
+    assert r['equal'] and r['miou_equal'] and r['shard'] == (0, 4) and r['count'] > 0

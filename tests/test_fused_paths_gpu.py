@@ -1,24 +1,22 @@
-"""Kernels that are built and CPU-checked (through tests/fake_backend.py) but not yet validated on a B200,
-hence not enabled by default.  Run with TSS_EXPERIMENTAL=1 on the GPU box; skipped otherwise so that an
-unvalidated kernel can never hang the default GPU suite.
+"""The fused / alternative kernel paths behind torch_semantic_segmentation_b200/gates.py, on the GPU.
 
-* stride-2 depthwise dgrad with the producer's BatchNorm-backward reduction fused into its epilogue
-  (csrc/dwconv_bnred.cu: dw_dgrad_s2_bnred_kernel; enabled in the model by TSS_FUSE_BNRED_EXT=1);
-* pointwise backward with the layer's BatchNorm-backward apply folded into the GEMM's A-operand producer
-  (csrc/pwconv_tc_bwd.cu: pw_tc_bwd_kernel; enabled in the model by TSS_FUSE_BNAPPLY=1);
-* the pyramid-pooling branches as grouped launches (csrc/ppm.cu; enabled in the model by TSS_FUSE_PPM=1);
-* the same for the stride-1 depthwise layers (csrc/dwconv_bwd_fused.cu; TSS_FUSE_BNAPPLY_DW=1);
-* depthwise forward / weight gradient that apply the producer's BatchNorm while reading (csrc/dwconv_bnin.cu;
-  TSS_FUSE_BNIN=1);
-* pointwise forward that applies the producer's BatchNorm in its operand producer (csrc/pwconv_tc_fwd_bnin.cu;
-  TSS_FUSE_BNIN_PW=1);
-* BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu; TSS_FUSE_BNFIN=1);
-* the stem convolution and its weight gradient on tcgen05 (csrc/stem_tc.cu; TSS_STEM_TC=1);
-* the warp-private confusion-matrix kernel (csrc/metrics.cu; TSS_CM_VARIANT=1);
-* the library's own dropout kernel (csrc/dropout.cu; TSS_OWN_DROPOUT=1);
-* deferred logits (TSS_DEFER_LOGITS=1: host-side only, existing kernels);
-* the device input pipeline (csrc/augment.cu; its per-pixel arithmetic is already pinned on the host by
-  tests/test_data_cpu.py, the launch itself is what remains to be run)."""
+Round 1 left these built but never run on hardware; round 2 ran all of them on a B200 (gpurun_out/experimental_r2a.log:
+73 of 81 passed at the first visit).  Kernel-level tests run by default whether or not the gate they belong to is on
+(a gate is on only if it also won the step A/B, gates.py); the few tests still marked ``experimental`` are open items.
+
+* stride-2 depthwise dgrad with the producer's BatchNorm-backward reduction in its epilogue (csrc/dwconv_bnred.cu; FUSE_BNRED_EXT);
+* pointwise backward with the BatchNorm-backward apply in the GEMM's A-operand producer (csrc/pwconv_tc_bwd.cu; FUSE_BNAPPLY);
+* the same for stride-1 depthwise layers (csrc/dwconv_bwd_fused.cu; FUSE_BNAPPLY_DW);
+* the pyramid-pooling branches as grouped launches (csrc/ppm.cu; FUSE_PPM);
+* depthwise forward / weight gradient applying the producer's BatchNorm while reading (csrc/dwconv_bnin.cu; FUSE_BNIN);
+* pointwise forward applying the producer's BatchNorm in its operand producer (csrc/pwconv_tc_fwd_bnin.cu; FUSE_BNIN_PW);
+* BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu; FUSE_BNFIN);
+* the stem convolution and its weight gradient on tcgen05 (csrc/stem_tc.cu; STEM_TC, default on);
+* the warp-private confusion-matrix kernel (csrc/metrics.cu; default on);
+* the library's own dropout kernel (csrc/dropout.cu; OWN_DROPOUT, default on);
+* deferred logits (DEFER_LOGITS, default on: host-side only);
+* the device input pipeline (csrc/augment.cu), bit-exact against the OpenCV-pinned CPU pipeline;
+* graph replays under a learning-rate schedule, graphed evaluation after graphed training (the benchmarked path)."""
 import os
 
 import pytest
@@ -27,8 +25,9 @@ import torch
 from tests.fake_backend import FakeBackend
 from torch_semantic_segmentation_b200 import _lib
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('TSS_EXPERIMENTAL') != '1', reason='set TSS_EXPERIMENTAL=1')]
+pytestmark = pytest.mark.gpu
+# still open after the B200 visits of round 2: run with TSS_EXPERIMENTAL=1
+experimental = pytest.mark.skipif(os.environ.get('TSS_EXPERIMENTAL') != '1', reason='open item: set TSS_EXPERIMENTAL=1')
 
 
 def rel(a, b):
@@ -63,6 +62,7 @@ def test_dw_dgrad_stride2_with_fused_bn_reduction(C, N, Hi, Wi, relu, dtype):
     assert rel(sg, sc) < 2e-3, rel(sg, sc)
 
 
+@experimental
 def test_training_step_with_extended_fusion_matches_unfused():
     from oracle.golden_inputs import train_batch
     from torch_semantic_segmentation_b200 import functional as Fn
@@ -135,6 +135,7 @@ def test_pw_backward_with_bn_apply_in_the_operand_producer(M_shape, K, Nc, relu,
         assert rel(d[4], c[4]) < 5e-3, ('psums', rel(d[4], c[4]))
 
 
+@experimental
 def test_training_step_with_fused_bn_apply_matches_unfused():
     from oracle.golden_inputs import train_batch
     from torch_semantic_segmentation_b200 import functional as Fn
@@ -189,6 +190,7 @@ def test_device_input_pipeline_is_bit_exact_with_the_cpu_pipeline():
     np.testing.assert_array_equal(y[1].cpu().numpy(), ey)
 
 
+@experimental
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('shape', [(12, 24, 24), (2, 32, 64), (3, 5, 7), (2, 1, 1)])
 def test_grouped_pyramid_pooling_matches_layer_by_layer(shape, dtype):
@@ -255,6 +257,7 @@ def test_training_step_with_grouped_pyramid_pooling_matches_default():
     assert rel(out[True][1], out[False][1]) < 1e-4 and rel(out[True][2], out[False][2]) < 1e-3
 
 
+@experimental
 def test_training_step_with_finalize_folded_into_apply_matches_default():
     from oracle.golden_inputs import train_batch
     from torch_semantic_segmentation_b200 import functional as Fn
@@ -525,6 +528,7 @@ def test_graph_replays_follow_a_learning_rate_schedule():
     assert torch.equal(opt.param_arena, before)              # lr 0 and decoupled weight decay lr*wd = 0: nothing moves
 
 
+@experimental
 def test_one_graph_per_staging_slot_trains_like_the_copying_path():
     """engine.SLOT_GRAPHS (TSS_SLOT_GRAPHS=1, host side only): graphs bound to the two staging slots read their batch in
     place; six different batches through the trainer end with the same parameters as the default path."""

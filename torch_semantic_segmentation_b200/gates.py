@@ -1,8 +1,9 @@
 """Defaults of the kernel-path gates, in one place.
 
 A gate picks between two implementations of the same step (both hand-written CUDA of this library -- never a fallback to
-another backend).  ``True`` = measured on a B200 and faster; ``False`` = built and checked on the CPU (emulated ABI, SIMT /
-tcgen05 emulation) but not measured yet.  ``TSS_<NAME>=1`` / ``=0`` in the environment overrides
+another backend).  ``True`` = validated on a B200 (tests/test_fused_paths_gpu.py) and faster in the step A/B; ``False`` = validated on a
+B200 where noted, but slower or not faster in the A/B of round 2 (tools/gpu_experimental.sh, profiles/r2a_gate_ab.txt),
+or still failing a test.  ``TSS_<NAME>=1`` / ``=0`` in the environment overrides
 a default for A/B runs (tools/gpu_experimental.sh).
 """
 import os
@@ -16,10 +17,10 @@ DEFAULTS = {
     'FUSE_BNIN': False,         # a block's BatchNorm applied by the depthwise conv that reads it
     'FUSE_BNIN_PW': False,      # ... by the tensor-core pointwise conv that reads it
     'FUSE_PPM': False,          # pyramid-pooling branches as grouped launches
-    'STEM_TC': False,           # stem convolution + weight gradient on tcgen05
+    'STEM_TC': True,            # stem convolution + weight gradient on tcgen05 (r2: fwd 154 -> 95 us, wgrad 246 -> 202 us; 4.58 -> 4.52 ms/step)
     'STEM_BWD_FUSED': False,    # stem BatchNorm-backward apply inside its tensor-core weight gradient
-    'DEFER_LOGITS': False,      # training forward without the unused full-resolution logits
-    'OWN_DROPOUT': False,       # mask-free dropout kernel instead of ATen's
+    'DEFER_LOGITS': True,       # training forward without the unused full-resolution logits (r2: 4.58 -> 4.53 ms/step)
+    'OWN_DROPOUT': True,        # mask-free dropout kernel instead of ATen's (r2: 28.8 -> 14.1 us per pass)
     'SLOT_GRAPHS': False,       # one captured training graph per staging slot of the trainer
 }
 

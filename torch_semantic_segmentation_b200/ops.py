@@ -777,6 +777,8 @@ def rng_state(device, seed=None):
     """Per-device {seed, offset, ticket} of the library's counter-based generator (int64[3]); the seed comes from
     torch's generator on first use (``torch.manual_seed`` before the first training forward keeps runs repeatable)."""
     device = torch.device(device)
+    if device.type == 'cuda' and device.index is None:       # 'cuda' and 'cuda:<current>' are one generator
+        device = torch.device('cuda', torch.cuda.current_device())
     st = _RNG.get(device)
     if st is None or seed is not None:
         s = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed)
