@@ -149,6 +149,12 @@ int tss_pwconv_bwd_fused(const void* dz, const void* y, int64_t lddz, int64_t ld
                          void* dx, int64_t M, int K, int Nc, int64_t lddx, const void* yp, int64_t ldyp,
                          const float* pmean, const float* prstd, const float* pgamma, const float* pbeta,
                          int pflags, float* psums, void* stream);
+/* Class-score convolution nn.Conv2d(K, Nc, 1) WITH bias and Nc not a multiple of 16 (fastscnn.py:97, contextnet.py:86)
+ * on the tensor-core kernels: zero-padded operands wp[Np][K] (Np % 16 == 0), wpT[K][Npt] (Npt % 8 == 0 = the channel
+ * pitch of the incoming gradient) and bias_pad[Np] (fp32).  Then tss_pwconv_fwd(impl 1, Nc = Np, shift = bias_pad),
+ * tss_pwconv_dgrad(impl 1, Nc = Npt) and tss_pwconv_wgrad(impl 1, Nc, db) (dw rows < Nc only, db += column sums). */
+int tss_class_scores_pack(const float* w, const float* bias, void* wp, void* wpT, float* bias_pad, int Nc,
+                          int K, int Np, int Npt, void* stream);
 /* bf16 copies of a (Nc,K) fp32 weight: wp[Nc][K] and wpT[K][Nc] (either may be NULL) */
 int tss_pack_weights_bf16(const float* w, void* wp, void* wpT, int Nc, int K, void* stream);
 /* the same for n_entries weights living in one fp32 parameter arena, in ONE launch (after the optimizer

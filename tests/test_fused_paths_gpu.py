@@ -62,16 +62,18 @@ def test_dw_dgrad_stride2_with_fused_bn_reduction(C, N, Hi, Wi, relu, dtype):
     assert rel(sg, sc) < 2e-3, rel(sg, sc)
 
 
-@experimental
 def test_training_step_with_extended_fusion_matches_unfused():
+    """Whole training step with the gate on against the gate off.  The bf16 step is not reproducible from run to run to
+    better than ~2 % on the gradients in front of a BatchNorm (fp32 atomics in the statistics, then 45 layers of
+    amplification: tools/diag_gates.py), so the unfused path's own run-to-run distance is the yardstick."""
     from oracle.golden_inputs import train_batch
     from torch_semantic_segmentation_b200 import functional as Fn
     from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
     from torch_semantic_segmentation_b200.models import fastscnn
     x, y = train_batch('fastscnn')
-    grads = {}
     keep = Fn.FUSE_BNRED_EXT
-    for flag in (False, True):
+
+    def run(flag):
         Fn.FUSE_BNRED_EXT = flag
         try:
             torch.manual_seed(0)
@@ -80,14 +82,18 @@ def test_training_step_with_extended_fusion_matches_unfused():
                 if isinstance(m, torch.nn.Dropout):
                     m.p = 0.0
             before = _lib.launch_count()
-            CrossEntropyLoss(ignore_index=255)(model(x.cuda()), y.cuda()).backward()
+            loss = CrossEntropyLoss(ignore_index=255)(model(x.cuda()), y.cuda())
+            loss.backward()
             torch.cuda.synchronize()
-            grads[flag] = ({k: p.grad.clone() for k, p in model.named_parameters()}, _lib.launch_count() - before)
+            return {k: p.grad.clone() for k, p in model.named_parameters()}, _lib.launch_count() - before, float(loss.detach())
         finally:
             Fn.FUSE_BNRED_EXT = keep
-    assert grads[True][1] == grads[False][1] - 6                  # 4 stride-2 + 2 more stand-alone reductions less
+    base, again, fused = run(False), run(False), run(True)
+    assert fused[1] == base[1] - 6                  # 4 stride-2 + 2 more stand-alone reductions less
+    assert fused[2] == base[2]                                  # the forward pass is untouched
     for k in ('classifier.3.weight', 'features.0.0.conv1.0.weight', 'downsample.1.0.weight', 'downsample.0.0.weight'):
-        assert rel(grads[True][0][k], grads[False][0][k]) < 3e-2, k
+        noise = rel(again[0][k], base[0][k])
+        assert rel(fused[0][k], base[0][k]) < max(3e-2, 3 * noise), (k, noise)
 
 
 @pytest.mark.parametrize('link', [False, True])
@@ -135,16 +141,18 @@ def test_pw_backward_with_bn_apply_in_the_operand_producer(M_shape, K, Nc, relu,
         assert rel(d[4], c[4]) < 5e-3, ('psums', rel(d[4], c[4]))
 
 
-@experimental
 def test_training_step_with_fused_bn_apply_matches_unfused():
+    """Whole training step with the gate on against the gate off.  The bf16 step is not reproducible from run to run to
+    better than ~2 % on the gradients in front of a BatchNorm (fp32 atomics in the statistics, then 45 layers of
+    amplification: tools/diag_gates.py), so the unfused path's own run-to-run distance is the yardstick."""
     from oracle.golden_inputs import train_batch
     from torch_semantic_segmentation_b200 import functional as Fn
     from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
     from torch_semantic_segmentation_b200.models import fastscnn
     x, y = train_batch('fastscnn')
-    grads = {}
     keep = Fn.FUSE_BNAPPLY
-    for flag in (False, True):
+
+    def run(flag):
         Fn.FUSE_BNAPPLY = flag
         try:
             torch.manual_seed(0)
@@ -153,14 +161,18 @@ def test_training_step_with_fused_bn_apply_matches_unfused():
                 if isinstance(m, torch.nn.Dropout):
                     m.p = 0.0
             before = _lib.launch_count()
-            CrossEntropyLoss(ignore_index=255)(model(x.cuda()), y.cuda()).backward()
+            loss = CrossEntropyLoss(ignore_index=255)(model(x.cuda()), y.cuda())
+            loss.backward()
             torch.cuda.synchronize()
-            grads[flag] = ({k: p.grad.clone() for k, p in model.named_parameters()}, _lib.launch_count() - before)
+            return {k: p.grad.clone() for k, p in model.named_parameters()}, _lib.launch_count() - before, float(loss.detach())
         finally:
             Fn.FUSE_BNAPPLY = keep
-    assert grads[True][1] == grads[False][1] - 22                 # one launch less per residual-free 1x1 layer
+    base, again, fused = run(False), run(False), run(True)
+    assert fused[1] == base[1] - 22                 # one launch less per residual-free 1x1 layer
+    assert fused[2] == base[2]                                  # the forward pass is untouched
     for k in ('classifier.3.weight', 'features.0.0.conv1.0.weight', 'downsample.1.0.weight', 'downsample.0.0.weight'):
-        assert rel(grads[True][0][k], grads[False][0][k]) < 3e-2, k
+        noise = rel(again[0][k], base[0][k])
+        assert rel(fused[0][k], base[0][k]) < max(3e-2, 3 * noise), (k, noise)
 
 
 def test_device_input_pipeline_is_bit_exact_with_the_cpu_pipeline():
@@ -665,3 +677,40 @@ def test_graphed_eval_follows_graphed_training():
         assert torch.equal(a, b), _round
         cms.append(a)
     assert not torch.equal(cms[0], cms[1])                     # training moved the predictions between the two evaluations
+
+
+@pytest.mark.parametrize('Nc,shape', [(19, (12, 96, 96)), (19, (2, 12, 20)), (11, (1, 5, 7)), (21, (3, 9, 13))])
+def test_class_scores_on_tensor_cores_match_the_simt_gemms(Nc, shape):
+    """nn.Conv2d(128, Nc, 1) with bias (fastscnn.py:97) through the tcgen05 GEMMs with zero-padded operands
+    (functional.CLASS_TC) against the SIMT fp32-accumulate GEMMs: forward, dgrad, wgrad, bias gradient."""
+    from torch_semantic_segmentation_b200 import functional as Fn
+    from torch_semantic_segmentation_b200 import ops
+    N, H, W = shape
+    K = 128
+    g = torch.Generator().manual_seed(Nc + H)
+    x = torch.randn(N, H, W, K, generator=g).to(torch.bfloat16).cuda().permute(0, 3, 1, 2)
+    w = (torch.randn(Nc, K, 1, 1, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(Nc, generator=g).cuda()
+    pitch = (Nc + 7) // 8 * 8                                    # what the fused head hands back
+    dy_buf = torch.zeros(N, H, W, pitch, dtype=torch.bfloat16, device='cuda')
+    dy_buf[..., :Nc] = torch.randn(N, H, W, Nc, generator=g).to(torch.bfloat16).cuda()
+    dy = dy_buf[..., :Nc].permute(0, 3, 1, 2)
+    keep = Fn.CLASS_TC
+    out = {}
+    try:
+        for flag in (False, True):
+            Fn.CLASS_TC = flag
+            xi = x.clone().requires_grad_(True)
+            wi, bi = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            before = _lib.launch_count()
+            y = Fn.ConvBias.apply(xi, wi, bi)
+            y.backward(dy)
+            torch.cuda.synchronize()
+            out[flag] = (y.detach().float().clone(), xi.grad.float(), wi.grad.clone(), bi.grad.clone(), _lib.launch_count() - before)
+    finally:
+        Fn.CLASS_TC = keep
+    ref = torch.nn.functional.conv2d(x.float(), w, b)
+    assert rel(out[True][0], ref) < 5e-3 and rel(out[False][0], ref) < 5e-3
+    assert ops.geom(Fn.ConvBias.apply(x, w, b))[4] >= 32 or Nc <= 16
+    for i, tol in ((1, 8e-3), (2, 1e-3), (3, 1e-4)):              # dx is rounded to bf16; dw, db are fp32 accumulations
+        assert rel(out[True][i], out[False][i]) < tol, (i, rel(out[True][i], out[False][i]))

@@ -244,6 +244,42 @@ __global__ void pack_weights_multi_kernel(const float* __restrict__ arena, const
     }
 }
 
+// Class-score convolution nn.Conv2d(K, Nc, 1) with bias and Nc not a multiple of 16 (19 classes; fastscnn.py:97) on the
+// tensor-core GEMMs: zero-padded bf16 operands wp[Np][K] (forward B operand), wpT[K][Npt] (dgrad B operand, Npt = the
+// gradient's channel pitch) and the bias as a padded fp32 shift vector.  One tiny launch per forward.
+__global__ void class_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias, bf16* __restrict__ wp,
+                                  bf16* __restrict__ wpT, float* __restrict__ bias_pad, int Nc, int K, int Np, int Npt) {
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Np * K) {
+        const int n = i / K, k = i - n * K;
+        wp[i] = __float2bfloat16_rn(n < Nc ? w[n * K + k] : 0.f);
+    }
+    if (i < K * Npt) {
+        const int k = i / Npt, n = i - k * Npt;
+        wpT[i] = __float2bfloat16_rn(n < Nc ? w[n * K + k] : 0.f);
+    }
+    if (i < Np) bias_pad[i] = (bias != nullptr && i < Nc) ? bias[i] : 0.f;
+}
+
+// out[c] += sum over rows of x[m][c]  (bias gradient of the class-score conv; C <= 32, x row pitch ld)
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t M, int C, int64_t ld) {
+    pdl_wait();
+    __shared__ float s_sum[32];
+    if (threadIdx.x < 32) s_sum[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int c = threadIdx.x & 31;              // lane = channel: a warp reads one row (<= 64 contiguous bytes)
+    const int r = threadIdx.x >> 5;
+    float acc = 0.f;
+    if (c < C)
+        for (int64_t m = (int64_t)blockIdx.x * 8 + r; m < M; m += (int64_t)gridDim.x * 8) acc += to_f32(x[m * ld + c]);
+    if (c < C) atomicAdd(&s_sum[c], acc);
+    __syncthreads();
+    if (threadIdx.x < C) atomicAdd(out + threadIdx.x, s_sum[threadIdx.x]);
+}
+
 }  // namespace
 
 // implemented in pwconv_tc.cu
@@ -314,8 +350,17 @@ extern "C" int tss_pwconv_wgrad(const void* x, const void* dy, float* dw, float*
     TSS_REQUIRE(impl == 0 || impl == 1, "pwconv_wgrad: unknown impl %d", impl);
     cudaStream_t st = (cudaStream_t)stream;
     if (impl == 1) {
-        TSS_REQUIRE(dtype == TSS_BF16 && db == nullptr, "pwconv_wgrad: impl 1 needs bf16 activations and no bias gradient");
-        return tss_pwconv_wgrad_tc(x, dy, dw, M, K, Nc, ldx, lddy, st);
+        TSS_REQUIRE(dtype == TSS_BF16, "pwconv_wgrad: impl 1 needs bf16 activations");
+        if (int e = tss_pwconv_wgrad_tc(x, dy, dw, M, K, Nc, ldx, lddy, st)) return e;
+        if (db != nullptr) {
+            TSS_REQUIRE(Nc <= 32, "pwconv_wgrad: impl 1 bias gradient needs Nc <= 32 (got %d)", Nc);
+            int64_t grid = ceil_div64(M, 8 * 16);
+            const int64_t cap = (int64_t)tss_num_sms() * 4;
+            if (grid > cap) grid = cap;
+            tss_launch(colsum_kernel<bf16>, (unsigned)grid, 256, 0, st, (const bf16*)dy, db, M, Nc, lddy);
+            TSS_LAUNCH_CHECK("pwconv_wgrad(bias)");
+        }
+        return TSS_OK;
     }
     const int gx = (Nc + WT - 1) / WT, gy = (K + WT - 1) / WT;
     int64_t target = (int64_t)tss_num_sms() * 4;
@@ -339,6 +384,18 @@ extern "C" int tss_pack_weights_multi(const float* arena, const int64_t* table, 
     if (gx > 64) gx = 64;
     tss_launch(pack_weights_multi_kernel, dim3((unsigned)gx, (unsigned)n_entries), 256, 0, (cudaStream_t)stream, arena, table);
     TSS_LAUNCH_CHECK("pack_weights_multi");
+    return TSS_OK;
+}
+
+extern "C" int tss_class_scores_pack(const float* w, const float* bias, void* wp, void* wpT, float* bias_pad, int Nc,
+                                     int K, int Np, int Npt, void* stream) {
+    TSS_REQUIRE(Nc > 0 && K > 0 && Np >= Nc && Np % 16 == 0 && Npt >= Nc && Npt % 8 == 0,
+                "class_scores_pack: Nc=%d K=%d Np=%d Npt=%d", Nc, K, Np, Npt);
+    TSS_REQUIRE(w != nullptr && wp != nullptr && wpT != nullptr && bias_pad != nullptr, "class_scores_pack: missing buffer");
+    const int n = (Np > Npt ? Np : Npt) * K;
+    tss_launch(class_pack_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, w, bias, (bf16*)wp, (bf16*)wpT, bias_pad, Nc,
+               K, Np, Npt);
+    TSS_LAUNCH_CHECK("class_scores_pack");
     return TSS_OK;
 }
 

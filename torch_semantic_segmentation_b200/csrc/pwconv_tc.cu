@@ -425,7 +425,8 @@ int wgrad_tile_cap() {
 
 int tss_pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int K, int Nc, int64_t ldx,
                         int64_t lddy, cudaStream_t st) {
-    TSS_REQUIRE(Nc % 16 == 0 && K % 16 == 0, "pwconv_wgrad_tc: needs Nc %% 16 == 0 and K %% 16 == 0 (Nc=%d K=%d)", Nc, K);
+    // Nc is the M dimension of the MMA (128 rows per CTA): any Nc works, TMA zero-fills the columns of dy beyond it
+    TSS_REQUIRE(Nc >= 1 && K % 16 == 0, "pwconv_wgrad_tc: needs K %% 16 == 0 (Nc=%d K=%d)", Nc, K);
     TSS_REQUIRE(((uintptr_t)dw & 15) == 0, "pwconv_wgrad_tc: dw must be 16-byte aligned");
     const int bk = pick_block_n(K, wgrad_tile_cap());
     TSS_REQUIRE(bk >= 16, "pwconv_wgrad_tc: no tile width for K=%d", K);

@@ -10,7 +10,7 @@ import os
 
 DEFAULTS = {
     'FUSE_BNRED': True,         # BatchNorm-backward reduction in the consumer's dgrad epilogue (4.66 -> 4.57 ms/step)
-    'FUSE_BNRED_EXT': False,    # ... also stride-2 depthwise dgrad and more single-consumer pairs
+    'FUSE_BNRED_EXT': True,     # ... also stride-2 depthwise dgrad and more single-consumer pairs (r2: 4.58 -> 4.48 ms/step)
     'FUSE_BNAPPLY': False,      # BatchNorm-backward apply in the operand producer of the pointwise dgrad
     'FUSE_BNAPPLY_DW': False,   # ... and in the stride-1 depthwise dgrad
     'FUSE_BNFIN': False,        # BatchNorm finalize inside the apply kernel
@@ -21,6 +21,7 @@ DEFAULTS = {
     'STEM_BWD_FUSED': False,    # stem BatchNorm-backward apply inside its tensor-core weight gradient
     'DEFER_LOGITS': True,       # training forward without the unused full-resolution logits (r2: 4.58 -> 4.53 ms/step)
     'OWN_DROPOUT': True,        # mask-free dropout kernel instead of ATen's (r2: 28.8 -> 14.1 us per pass)
+    'CLASS_TC': False,          # class-score conv (19 classes + bias) on the tcgen05 GEMMs with zero-padded operands
     'SLOT_GRAPHS': False,       # one captured training graph per staging slot of the trainer
 }
 

@@ -251,6 +251,42 @@ def pwconv_wgrad(x, dy, dw, db=None, impl=0):
               lddy=lddy, impl=impl, dtype=dtype_code(x.dtype))
 
 
+def class_scores_pack(w, bias, grad_pitch=None):
+    """Zero-padded tensor-core operands of the class-score conv (Nc not a multiple of 16, with bias):
+    -> wp (Np, K) bf16, wpT (K, Npt) bf16, bias_pad (Np,) fp32; Npt = channel pitch of the gradient that will come back."""
+    Nc, K = w.shape[0], w.shape[1]
+    Np = (Nc + 15) // 16 * 16
+    Npt = _pad8(Nc) if grad_pitch is None else int(grad_pitch)
+    wp = torch.empty((Np, K), dtype=torch.bfloat16, device=w.device)
+    wpT = torch.empty((K, Npt), dtype=torch.bfloat16, device=w.device)
+    bpad = torch.empty(Np, dtype=torch.float32, device=w.device)
+    _lib.call('tss_class_scores_pack', w=w, bias=bias, wp=wp, wpT=wpT, bias_pad=bpad, Nc=Nc, K=K, Np=Np, Npt=Npt)
+    return wp, wpT, bpad
+
+
+def class_scores_fwd(x, w, packed):
+    """(N, Nc, H, W) scores in a padded channel pitch, on the tcgen05 GEMM (``packed`` from class_scores_pack)."""
+    N, K, H, W, ldx = _g(x, 'class_scores_fwd')
+    Nc = w.shape[0]
+    wp, _, bpad = packed
+    out = empty_nhwc(N, Nc, H, W, x.dtype, x.device, pitch=max(_pad8(Nc) + 8, wp.shape[0]))
+    _lib.call('tss_pwconv_fwd', x=x, w=w, wp=wp, y=out, M=N * H * W, K=K, Nc=wp.shape[0], ldx=ldx, ldy=_g(out, 'class_scores_fwd')[4],
+              scale=None, shift=bpad, res=None, ldr=0, flags=0, stats=None, impl=1, dtype=dtype_code(x.dtype))
+    return out
+
+
+def class_scores_dgrad(dy, w, packed):
+    N, Nc, H, W, lddy = _g(dy, 'class_scores_dgrad')
+    K = w.shape[1]
+    wpT = packed[1]
+    if lddy < wpT.shape[1]:
+        raise RuntimeError('class_scores_dgrad: gradient pitch %d < packed pitch %d' % (lddy, wpT.shape[1]))
+    dx = empty_nhwc(N, K, H, W, dy.dtype, dy.device)
+    _lib.call('tss_pwconv_dgrad', dy=dy, w=w, wpT=wpT, dx=dx, M=N * H * W, K=K, Nc=wpT.shape[1], lddy=lddy, lddx=K, impl=1,
+              dtype=dtype_code(dy.dtype))
+    return dx
+
+
 def dwpw_fwd(x, w_dw, scale1, shift1, relu1, wp, scale2, shift2, res=None, relu2=False):
     """Inference: act2(BN2(pw(act1(BN1(dw3x3(x))))) [+ res]) in one kernel (stride 1, bf16)."""
     N, C, H, W, ld = _g(x, 'dwpw_fwd')
