@@ -15,6 +15,26 @@ inline int stream_grid(int64_t items, int per_sm = 8) {
     return (int)(want < cap ? want : cap);
 }
 
+// launch shape of the (channel group, row lane) kernels: CG = C/8 groups x PL row lanes per CTA, U rows in flight per thread
+struct RowsLaunch {
+    int threads, PL;
+    int64_t M;
+    int grid(int U) const {
+        int64_t want = ceil_div64(M, (int64_t)PL * U);          // >= 1 batch of U rows per row lane
+        const int64_t cap = (int64_t)tss_num_sms() * 8;
+        if (want < 1) want = 1;
+        return (int)(want < cap ? want : cap);
+    }
+};
+inline RowsLaunch rows_launch(int64_t M, int C) {
+    RowsLaunch r;
+    const int CG = C / 8;
+    r.M = M;
+    r.PL = CG <= kThreads ? kThreads / CG : 0;
+    r.threads = r.PL * CG;
+    return r;
+}
+
 __device__ __forceinline__ void ldg8f(const float* __restrict__ p, float (&v)[8]) {
     float4 a = __ldg(reinterpret_cast<const float4*>(p));
     float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -66,44 +86,64 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 }
 
 // ------------------------------------------------------------------ apply -------------
-template <typename T>
+// Thread = (8-channel group, row lane): the per-channel constants are loaded ONCE into registers and the thread walks
+// rows with U independent 128-bit loads in flight per operand.  (Round 1 mapped a flat item index to (row, group) with a
+// 64-bit division and re-loaded scale / shift for every 16 bytes of data: 4 parameter loads per data load, and the
+// kernels sat at 0.36 of the HBM roofline with 10-16 us floors on tensors that fit in L2.)
+template <typename T, int U, bool kExtra>       // kExtra: a second normalised branch (y2) and / or a residual are added
 __global__ void __launch_bounds__(kThreads)
 bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                 const T* __restrict__ y2, const float* __restrict__ scale2, const float* __restrict__ shift2,
                 const T* __restrict__ res, T* __restrict__ z, int64_t M, int C,
-                int64_t ldy, int64_t ldy2, int64_t ldr, int64_t ldz, int relu) {
-    pdl_wait();
+                int64_t ldy, int64_t ldy2, int64_t ldr, int64_t ldz, int relu, int PL) {
     const int CG = C >> 3;
-    const int64_t total = M * CG;
-    for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
-         item += (int64_t)gridDim.x * kThreads) {
-        const int64_t m = item / CG;
-        const int c0 = (int)(item - m * CG) * 8;
-        float v[8], sc[8], sh[8];
-        load8(y + m * ldy + c0, v);
-        ldg8f(scale + c0, sc);
-        ldg8f(shift + c0, sh);
+    const int cg = threadIdx.x % CG;
+    const int pl = threadIdx.x / CG;
+    const int c0 = cg * 8;
+    pdl_wait();
+    if (pl >= PL) return;
+    float sc[8], sh[8], sc2[8], sh2[8];
+    ldg8f(scale + c0, sc);
+    ldg8f(shift + c0, sh);
+    if (kExtra && y2 != nullptr) { ldg8f(scale2 + c0, sc2); ldg8f(shift2 + c0, sh2); }
+    const int64_t step = (int64_t)gridDim.x * PL;
+    for (int64_t m0 = (int64_t)blockIdx.x * PL + pl; m0 < M; m0 += U * step) {
+        Raw8<T> ry[U], ry2[kExtra ? U : 1], rr[kExtra ? U : 1];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
-        if (y2 != nullptr) {
-            float u[8];
-            load8(y2 + m * ldy2 + c0, u);
-            ldg8f(scale2 + c0, sc);
-            ldg8f(shift2 + c0, sh);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += fmaf(u[e], sc[e], sh[e]);
+        for (int u = 0; u < U; ++u) {
+            const int64_t m = m0 + u * step;
+            if (m < M) {
+                ry[u].ld(y + m * ldy + c0);
+                if (kExtra && y2 != nullptr) ry2[u].ld(y2 + m * ldy2 + c0);
+                if (kExtra && res != nullptr) rr[u].ld(res + m * ldr + c0);
+            }
         }
-        if (res != nullptr) {
-            float u[8];
-            load8(res + m * ldr + c0, u);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += u[e];
-        }
-        if (relu) {
+        for (int u = 0; u < U; ++u) {
+            const int64_t m = m0 + u * step;
+            if (m >= M) break;
+            float v[8];
+            ry[u].get(v);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
+            if (kExtra && y2 != nullptr) {
+                float w[8];
+                ry2[u].get(w);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += fmaf(w[e], sc2[e], sh2[e]);
+            }
+            if (kExtra && res != nullptr) {
+                float w[8];
+                rr[u].get(w);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += w[e];
+            }
+            if (relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            store8(z + m * ldz + c0, v);
         }
-        store8(z + m * ldz + c0, v);
     }
 }
 
@@ -189,8 +229,10 @@ bn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T*
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, s_sum[i]);
 }
 
-// pass 2: dy = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)); optional dres = g
-template <typename T>
+// pass 2: dy = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)); optional dres = g.  Same thread mapping as bn_apply_kernel:
+// per-channel constants a = gamma*rstd, k1 = sum(g)/n, k2 = rstd*sum(g*xhat)/n, mu (and the forward's scale / shift for
+// the recomputed ReLU mask) live in registers; dy = a*(g - k1 - (y - mu)*k2).
+template <typename T, int U, bool kRes>         // kRes: residual layers (mask from the activated tensor z, dres = g stored)
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y,
                     const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -198,55 +240,76 @@ bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* 
                     const float* __restrict__ sums,
                     T* __restrict__ dy, T* __restrict__ dres, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy,
-                    int64_t lddy, int64_t lddres, int relu, float inv_m) {
-    pdl_wait();
+                    int64_t lddy, int64_t lddres, int relu, float inv_m, int PL) {
     const int CG = C >> 3;
-    const int64_t total = M * CG;
+    const int cg = threadIdx.x % CG;
+    const int pl = threadIdx.x / CG;
+    const int c0 = cg * 8;
+    pdl_wait();
     if (blockIdx.x == 0) {
-        for (int c = threadIdx.x; c < C; c += kThreads) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
             if (dbeta != nullptr) dbeta[c] += sums[c];
             if (dgamma != nullptr) dgamma[c] += sums[C + c];
         }
     }
-    for (int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x; item < total;
-         item += (int64_t)gridDim.x * kThreads) {
-        const int64_t m = item / CG;
-        const int c0 = (int)(item - m * CG) * 8;
-        float g[8], yy[8], mu[8], rs[8], ga[8], a1[8], a2[8];
-        load8(dz + m * lddz + c0, g);
-        load8(y + m * ldy + c0, yy);
+    if (pl >= PL) return;
+    float a[8], k1[8], k2[8], mu[8], sh[8];
+    {
+        float rs[8], s1[8], s2[8];
         ldg8f(mean + c0, mu);
         ldg8f(rstd + c0, rs);
-        if (gamma != nullptr) ldg8f(gamma + c0, ga);
+        ldg8f(sums + c0, s1);
+        ldg8f(sums + C + c0, s2);
+        if (gamma != nullptr) ldg8f(gamma + c0, a);
         else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ga[e] = 1.f;
+            for (int e = 0; e < 8; ++e) a[e] = 1.f;
         }
-        ldg8f(sums + c0, a1);
-        ldg8f(sums + C + c0, a2);
-        if (relu) {
-            if (z != nullptr) {
-                float zz[8];
-                load8(z + m * ldz + c0, zz);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float sc = ga[e] * rs[e];
-                    const float sh = (beta != nullptr ? __ldg(beta + c0 + e) : 0.f) - mu[e] * sc;
-                    g[e] = fmaf(yy[e], sc, sh) > 0.f ? g[e] : 0.f;
-                }
-            }
-        }
-        if (dres != nullptr) store8(dres + m * lddres + c0, g);
-        float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float xh = (yy[e] - mu[e]) * rs[e];
-            o[e] = ga[e] * rs[e] * (g[e] - a1[e] * inv_m - xh * a2[e] * inv_m);
+            a[e] *= rs[e];                                   // = the forward's scale
+            k1[e] = s1[e] * inv_m;
+            k2[e] = rs[e] * (s2[e] * inv_m);
+            sh[e] = (beta != nullptr ? __ldg(beta + c0 + e) : 0.f) - mu[e] * a[e];
         }
-        store8(dy + m * lddy + c0, o);
+    }
+    const bool mask_z = kRes && relu && z != nullptr;
+    const int64_t step = (int64_t)gridDim.x * PL;
+    for (int64_t m0 = (int64_t)blockIdx.x * PL + pl; m0 < M; m0 += U * step) {
+        Raw8<T> rg[U], ry[U], rz[kRes ? U : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t m = m0 + u * step;
+            if (m < M) {
+                rg[u].ld(dz + m * lddz + c0);
+                ry[u].ld(y + m * ldy + c0);
+                if (mask_z) rz[u].ld(z + m * ldz + c0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t m = m0 + u * step;
+            if (m >= M) break;
+            float g[8], yy[8];
+            rg[u].get(g);
+            ry[u].get(yy);
+            if (relu) {
+                if (mask_z) {
+                    float zz[8];
+                    rz[u].get(zz);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) g[e] = fmaf(yy[e], a[e], sh[e]) > 0.f ? g[e] : 0.f;
+                }
+            }
+            if (kRes && dres != nullptr) store8(dres + m * lddres + c0, g);
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = a[e] * (g[e] - k1[e] - (yy[e] - mu[e]) * k2[e]);
+            store8(dy + m * lddy + c0, o);
+        }
     }
 }
 
@@ -361,10 +424,14 @@ extern "C" int tss_bn_apply(const void* y, const float* scale, const float* shif
                             void* stream) {
     if (int e = check_rows("bn_apply", M, C)) return e;
     TSS_REQUIRE(y2 == nullptr || (scale2 != nullptr && shift2 != nullptr), "bn_apply: y2 without scale2/shift2");
+    const RowsLaunch rl = rows_launch(M, C);
+    TSS_REQUIRE(rl.threads > 0, "bn_apply: C=%d too large", C);
     TSS_DISPATCH_DTYPE(dtype, "bn_apply", {
-        tss_launch(bn_apply_kernel<T>, stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream, 
+        constexpr int U = sizeof(T) == 2 ? 4 : 2;
+        auto kern = (y2 != nullptr || res != nullptr) ? bn_apply_kernel<T, U, true> : bn_apply_kernel<T, U, false>;
+        tss_launch(kern, rl.grid(U), rl.threads, 0, (cudaStream_t)stream,
             (const T*)y, scale, shift, (const T*)y2, scale2, shift2, (const T*)res, (T*)z, M, C, ldy, ldy2,
-            ldr, ldz, flags & TSS_EPI_RELU);
+            ldr, ldz, flags & TSS_EPI_RELU, rl.PL);
         TSS_LAUNCH_CHECK("bn_apply");
         return TSS_OK;
     });
@@ -399,10 +466,14 @@ extern "C" int tss_bn_bwd_apply(const void* dz, const void* z, const void* y, co
     if (int e = check_rows("bn_bwd_apply", M, C)) return e;
     if (count <= 0) count = M;
     const int relu = flags & TSS_EPI_RELU;
+    const RowsLaunch rl = rows_launch(M, C);
+    TSS_REQUIRE(rl.threads > 0, "bn_bwd_apply: C=%d too large", C);
     TSS_DISPATCH_DTYPE(dtype, "bn_bwd_apply", {
-        tss_launch(bn_bwd_apply_kernel<T>, stream_grid(M * (C / 8)), kThreads, 0, (cudaStream_t)stream, 
+        constexpr int U = sizeof(T) == 2 ? 4 : 2;
+        auto kern = (z != nullptr || dres != nullptr) ? bn_bwd_apply_kernel<T, U, true> : bn_bwd_apply_kernel<T, U, false>;
+        tss_launch(kern, rl.grid(U), rl.threads, 0, (cudaStream_t)stream,
             (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, beta, sums, (T*)dy, (T*)dres, dgamma, dbeta,
-            M, C, lddz, ldz, ldy, lddy, lddres, relu, (float)(1.0 / (double)count));
+            M, C, lddz, ldz, ldy, lddy, lddres, relu, (float)(1.0 / (double)count), rl.PL);
         TSS_LAUNCH_CHECK("bn_bwd_apply");
         return TSS_OK;
     });

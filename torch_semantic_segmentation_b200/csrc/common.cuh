@@ -91,6 +91,19 @@ inline cudaError_t tss_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Driver-API entry points (cuTensorMapEncodeTiled) need the primary context bound to the CALLING thread.  The runtime binds
+// it lazily at a thread's first runtime call, and PyTorch does not call cudaSetDevice on a thread that stays on device 0:
+// a descriptor encode that is the first CUDA call of autograd's backward worker fails with CUDA_ERROR_INVALID_CONTEXT
+// (201).  One cudaFree(nullptr) per thread binds it.
+#ifndef TSS_HOST_EMU
+static inline void tss_bind_context() {
+    static thread_local bool bound = false;
+    if (!bound) { cudaFree(nullptr); bound = true; }
+}
+#else
+static inline void tss_bind_context() {}
+#endif
+
 static inline int tss_num_sms() {
     static int sms = 0;
     if (sms == 0) {

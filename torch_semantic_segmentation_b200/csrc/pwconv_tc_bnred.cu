@@ -178,6 +178,7 @@ int make_map_bnred(CUtensorMap* map, const void* base, int64_t rows, int cols, i
     typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    tss_bind_context();
     static EncodeTiledFn enc = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;

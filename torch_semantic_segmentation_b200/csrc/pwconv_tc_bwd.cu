@@ -271,6 +271,7 @@ int make_map_bwd(CUtensorMap* map, const void* base, int64_t rows, int cols, int
     typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    tss_bind_context();
     static EncodeTiledFn enc = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;

@@ -225,6 +225,7 @@ extern "C" int tss_pwconv_fwd_bnin(const void* x, int64_t ldx, const float* in_s
     typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    tss_bind_context();
     static EncodeTiledFn enc = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;

@@ -14,6 +14,7 @@ typedef CUresult (*TssEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 static inline TssEncodeTiledFn tss_encode_tiled() {
+    tss_bind_context();
     static TssEncodeTiledFn fn = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
