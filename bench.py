@@ -42,6 +42,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of a CUDA graph')
     ap.add_argument('--kernels', action='store_true', help='also dump the per-kernel table to stderr')
+    ap.add_argument('--headline-only', action='store_true',
+                    help='skip the 1024x2048 training leg, the 500-map mIoU leg and the bs1 inference leg (A/B runs)')
     ap.add_argument('--e2e-uint8', action='store_true',
                     help='end-to-end leg fed with decoded uint8 frames + label ids, normalised / mapped on the device by '
                          'data.DeviceTransform (28 MB instead of 141 MB host->device per step); off until that kernel has '
@@ -81,7 +83,9 @@ def cpu_train_throughput(steps, warmup, batch=CPU_SAMPLE_BATCH):
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
+    # bounded: a CPU step on the 2-crop sample takes 0.15-0.3 s; more than 40 steps add nothing but wall time.  The line
+    # says what was asked for and what ran (config.requested / steps / warmup) instead of clamping silently.
+    steps, warmup = max(1, min(args.steps, 40)), max(1, min(args.warmup, 5))
     value, spt, cores = cpu_train_throughput(steps, warmup)
     sample = ('%d steps of %d crops %dx%d (of the %d-crop step), fp32, %d torch threads'
               % (steps, CPU_SAMPLE_BATCH, CROP, CROP, BATCH, cores))
@@ -90,7 +94,9 @@ def run_reference(args, rank):
         'steps': steps, 'warmup': warmup, 'ms_per_step': spt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'global_batch': max(args.gpus, 1) * BATCH, 'parallelism': 'dp%d' % max(args.gpus, 1),
-                   'cpu_sample': 'each step = %d of the %d crops of one rank, stock PyTorch fp32 on the host cores' % (CPU_SAMPLE_BATCH, BATCH)},
+                   'cpu_sample': 'each step = %d of the %d crops of one rank, stock PyTorch fp32 on the host cores' % (CPU_SAMPLE_BATCH, BATCH),
+                   'requested': {'steps': args.steps, 'warmup': args.warmup},
+                   'ran': {'steps': steps, 'warmup': warmup, 'note': 'steps capped at 40, warm-up at 5 (CPU arm; img/s is per image, the sample size does not enter it)'}},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
@@ -280,6 +286,161 @@ def kernel_table(device, runner=None):
     return rows
 
 
+# ------------------------------------------------------------------ the metric's other legs --
+STEP_ALGORITHMIC_BYTES = 3 * 1849e6 + 595e6      # 3 x the fused-ideal forward traffic + the CE head, per 12 x 768 x 768 step
+FWD_ALGORITHMIC_BYTES_1024x2048 = 549e6          # fused-ideal inference forward per 1024 x 2048 image
+
+
+def train_1024x2048(world, rank, device, steps, batch=4):
+    """BASELINE.json `metric`: Fast-SCNN training at the full 1024 x 2048 resolution (per-GPU batch `batch`, stated in the
+    result; 4 x 1024 x 2048 = 8.4 Mpx per step against 7.1 Mpx for configs[1]'s 12 crops), same step as the headline."""
+    import torch.distributed as dist
+    from torch_semantic_segmentation_b200.distributed import GradientAllReducer, broadcast_parameters
+    from torch_semantic_segmentation_b200.engine import GraphedTrainStep
+    from torch_semantic_segmentation_b200.functional import enable_deferred_logits
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    torch.manual_seed(0)
+    model = fastscnn(3, CLASSES).to(device).set_compute_dtype(torch.bfloat16)
+    broadcast_parameters(model)
+    opt = FlatAdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    GradientAllReducer(opt, num_buckets=4).install()
+    loss_fn = CrossEntropyLoss(ignore_index=255)
+    g = torch.Generator(device=device).manual_seed(4321 + rank)
+    x = torch.randn(batch, 3, 1024, 2048, generator=g, device=device)
+    y = torch.randint(0, CLASSES, (batch, 1024, 2048), generator=g, device=device)
+    y[torch.rand(batch, 1024, 2048, generator=g, device=device) < 0.1] = 255
+    model.train()
+    enable_deferred_logits(model, loss_fn)
+    step = GraphedTrainStep(model, opt, loss_fn, x, y)
+    for _ in range(3):
+        step.graph.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step.graph.replay()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    per = float(ms) / steps
+    out = {'value': world * batch / (per / 1e3), 'unit': 'img/s', 'ms_per_step': per, 'per_gpu_batch': batch,
+           'resolution': [1024, 2048], 'steps': steps, 'loss': float(step.loss), 'dtype': 'bf16'}
+    del step, model, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def miou_500_exact(world, rank, device, n_maps=500):
+    """BASELINE.json configs[3]: confusion matrix over 500 synthetic 1024 x 2048 prediction / label maps, sharded over the
+    ranks without padding, ONE int64 all-reduce; every rank's shard is recounted on the host by the oracle
+    (oracle/confusion.py: numpy bincount, the definition) and compared bit for bit, and so is the mIoU (float64)."""
+    import numpy as np
+    import torch.distributed as dist
+    from oracle import confusion as o_cm
+    from torch_semantic_segmentation_b200.distributed import shard_range
+    from torch_semantic_segmentation_b200.metrics import ConfusionMatrix, metrics_from_cm
+    lo, hi = shard_range(n_maps, world, rank)
+
+    def pair(i):
+        g = torch.Generator(device=device).manual_seed(4321 + i)
+        p = torch.randint(0, CLASSES, (1024, 2048), generator=g, device=device)
+        l = torch.randint(0, CLASSES, (1024, 2048), generator=g, device=device)
+        l[torch.rand(1024, 2048, generator=g, device=device) < 0.1] = 255
+        return p, l
+    pairs = [pair(i) for i in range(lo, hi)]
+    batches = [(torch.stack([p for p, _ in pairs[i:i + 16]]), torch.stack([l for _, l in pairs[i:i + 16]]))
+               for i in range(0, len(pairs), 16)]
+    cm = ConfusionMatrix(CLASSES, device=device)
+    cm.update(batches[0])
+    cm.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for b in batches:
+        cm.update(b)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    local = cm.compute(sync=False).clone()
+    total = cm.compute()                       # one int64 all-reduce (SUM)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    want = np.zeros((CLASSES, CLASSES), dtype=np.int64)
+    for p, l in pairs:                          # the oracle on the host, on the very maps the GPU counted
+        want += o_cm.confusion_matrix(p.cpu().numpy(), l.cpu().numpy(), CLASSES)
+    ok = torch.tensor([int(np.array_equal(local.cpu().numpy(), want))], device=device)
+    want_total = torch.from_numpy(want).to(device)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        dist.all_reduce(want_total)
+    miou = float(metrics_from_cm(total)['miou'])
+    miou_oracle = float(o_cm.metrics(want_total.cpu().numpy())['miou'])
+    px = n_maps * 1024 * 2048
+    return {'maps': n_maps, 'ms': float(ms), 'maps_per_s': n_maps / (float(ms) / 1e3), 'gbs_per_gpu': 16.0 * px / world / float(ms) / 1e6,
+            'hbm_frac': 16.0 * px / world / float(ms) / 1e6 / measured_peak()[0],
+            'confusion_matrix_bit_exact_vs_oracle': bool(int(ok)) and bool(torch.equal(total, want_total)),
+            'miou': miou, 'miou_oracle': miou_oracle, 'miou_bit_exact': miou == miou_oracle,
+            'pixels_counted': int(total.sum()), 'shards': world}
+
+
+def infer_bs1(device, iterations=200, warmup=20):
+    """BASELINE.json `metric`: bs1 inference FPS at 1 x 3 x 1024 x 2048 (eval mode, bf16, CUDA-graphed forward).
+    `fps` follows the reference's benchmark_model (utils/benchmark.py:6-29: per-iteration host time, fps = 1 / mean) with
+    a synchronize inside every iteration (the reference's loop would time asynchronous launches on a GPU);
+    `fps_device` = back-to-back replays between two CUDA events."""
+    import numpy as np
+    from torch_semantic_segmentation_b200 import _lib
+    from torch_semantic_segmentation_b200.models import fastscnn
+    torch.manual_seed(0)
+    model = fastscnn(3, CLASSES).to(device).set_compute_dtype(torch.bfloat16).eval()
+    x = torch.randn(1, 3, 1024, 2048, device=device)
+    with torch.no_grad():
+        for _ in range(3):
+            model(x)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            out = model(x)
+        kernels = _lib.launch_count() - before
+    for _ in range(warmup):
+        graph.replay()
+    torch.cuda.synchronize()
+    record = np.zeros(iterations)
+    for it in range(iterations):
+        t0 = time.perf_counter()
+        graph.replay()
+        torch.cuda.synchronize()
+        record[it] = time.perf_counter() - t0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iterations):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / iterations
+    peak = measured_peak()[0]
+    res = {'fps': float(1.0 / record.mean()), 'mean_ms': float(record.mean() * 1e3), 'min_ms': float(record.min() * 1e3),
+           'fps_device': 1e3 / dev_ms, 'device_ms': dev_ms, 'iterations': iterations, 'kernels_per_forward': kernels,
+           'hbm_ideal_frac': (FWD_ALGORITHMIC_BYTES_1024x2048 / (peak * 1e9)) / (dev_ms / 1e3),
+           'out_shape': list(out.shape), 'dtype': 'bf16'}
+    del graph, out, model
+    torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------ our arm -----------------
 def main():
     args = parse()
@@ -397,6 +558,14 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * BATCH * args.steps / (float(ems) / 1e3)
 
+    # ---- the other legs of BASELINE.json's metric: every rank takes part (data-parallel / sharded) ----------------
+    del trainer, graphed
+    torch.cuda.empty_cache()
+    extra = {}
+    if not args.headline_only:
+        extra['train_1024x2048'] = train_1024x2048(world, rank, device, max(5, min(args.steps, 20)))
+        extra['miou_500_exact'] = miou_500_exact(world, rank, device)
+
     def finish():
         # All collectives of this run are behind us (the last one is the MAX of the e2e time) and the
         # result line is printed: multi-rank processes leave without the NCCL teardown handshake, which
@@ -458,6 +627,8 @@ def main():
                 'launches_per_step': top['launches'], 'share_of_step_ms': top['ms'],
                 'slowest_single_op': {'kernel': rows[0]['kernel'], 'ms': rows[0]['ms'], 'gbs': rows[0]['gbs']}}
 
+    if not args.headline_only:
+        extra['infer_bs1'] = infer_bs1(device)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         v, spt, cores = cpu_train_throughput(3, 1)
@@ -480,7 +651,11 @@ def main():
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': roofline,
+        'step_roofline': {'algorithmic_bytes': STEP_ALGORITHMIC_BYTES, 'source': 'SURVEY.md section 8d: 3 x 1849 MB + 595 MB per step',
+                          'achieved': STEP_ALGORITHMIC_BYTES / (ms_total / args.steps) / 1e6, 'peak': peak, 'unit': 'GB/s',
+                          'frac': STEP_ALGORITHMIC_BYTES / (ms_total / args.steps) / 1e6 / peak},
         'cpu_baseline': cpu,
+        **extra,
     }))
     finish()
 
