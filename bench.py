@@ -390,7 +390,7 @@ def miou_500_exact(world, rank, device, n_maps=500):
     px = n_maps * 1024 * 2048
     return {'maps': n_maps, 'ms': float(ms), 'maps_per_s': n_maps / (float(ms) / 1e3), 'gbs_per_gpu': 16.0 * px / world / float(ms) / 1e6,
             'hbm_frac': 16.0 * px / world / float(ms) / 1e6 / measured_peak()[0],
-            'confusion_matrix_bit_exact_vs_oracle': bool(int(ok)) and bool(torch.equal(total, want_total)),
+            'confusion_matrix_bit_exact_vs_oracle': bool(int(ok)) and bool(torch.equal(total.cpu(), want_total.cpu())),
             'miou': miou, 'miou_oracle': miou_oracle, 'miou_bit_exact': miou == miou_oracle,
             'pixels_counted': int(total.sum()), 'shards': world}
 

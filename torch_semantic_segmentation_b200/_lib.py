@@ -45,8 +45,9 @@ def dtype_code(dtype):
         raise RuntimeError('tss_b200: unsupported activation dtype %s (float32 or bfloat16)' % dtype)
 
 
-def parse_header(path=HEADER_PATH):
-    """-> {name: (restype, [(param_name, kind, base_type)])}, kind in {'ptr', 'val'}."""
+def parse_header(path=HEADER_PATH, with_const=False):
+    """-> {name: (restype, [(param_name, kind, base_type)])}, kind in {'ptr', 'val'}; ``with_const`` appends whether
+    the parameter is declared ``const`` (an input) -- library.py derives the operators' mutation annotations from it."""
     with open(path) as f:
         text = re.sub(r'/\*.*?\*/', '', f.read(), flags=re.S)
     protos = {}
@@ -59,8 +60,8 @@ def parse_header(path=HEADER_PATH):
                 m = re.match(r'^(const\s+)?(\w+)\s*(\*?)\s*(\w+)$', a)
                 if not m:
                     raise RuntimeError('cannot parse parameter %r of %s' % (a, name))
-                _, base, star, pname = m.groups()
-                params.append((pname, 'ptr' if star else 'val', base))
+                const, base, star, pname = m.groups()
+                params.append((pname, 'ptr' if star else 'val', base) + ((bool(const),) if with_const else ()))
         protos[name] = (ret, params)
     return protos
 
@@ -151,6 +152,11 @@ def set_backend(b):
 
 
 def call(name, **kwargs):
+    """Run one entry point of the C ABI.  Kernel launchers go through their registered ``torch.ops.tss_b200`` operator
+    (library.py: schema + fake implementation generated from the header), whose implementation is the ctypes call."""
+    from . import library
+    if name in library.OPS:
+        return library.dispatch(name, kwargs)
     return backend().call(name, kwargs)
 
 

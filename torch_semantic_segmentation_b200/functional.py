@@ -21,6 +21,7 @@ import threading
 
 import torch
 
+from . import library  # noqa: F401  (registers the tss_b200 operators)
 from . import ops
 from .gates import gate
 
@@ -617,29 +618,22 @@ class Dropout(torch.autograd.Function):
         return ops.dropout_bwd(ops.as_nhwc(dy).contiguous(memory_format=torch.channels_last), ctx.p, used), None
 
 
-class Bilinear(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, Ho, Wo):
-        ctx.in_hw = (x.shape[2], x.shape[3])
-        return ops.bilinear_fwd(x, Ho, Wo)
+class Bilinear:
+    """``F.interpolate(mode='bilinear', align_corners=True)`` on NHWC tensors: the registered, differentiable operator
+    ``torch.ops.tss_b200.bilinear`` (library.py: schema, fake implementation, autograd formula)."""
 
     @staticmethod
-    def backward(ctx, dy):
-        return ops.bilinear_bwd(ops.as_nhwc(dy), ctx.in_hw[0], ctx.in_hw[1]), None, None
+    def apply(x, Ho, Wo):
+        return torch.ops.tss_b200.bilinear(x, Ho, Wo)
 
 
-class UpsampleLogits(torch.autograd.Function):
-    """NHWC class scores -> NCHW-contiguous full-resolution logits (the reference's output layout)."""
-
-    @staticmethod
-    def forward(ctx, x, Ho, Wo):
-        g = ops.geom(x)
-        ctx.in_hw, ctx.pitch = (x.shape[2], x.shape[3]), max(g[4], (x.shape[1] + 7) // 8 * 8)
-        return ops.upsample_logits_fwd(x, Ho, Wo)
+class UpsampleLogits:
+    """NHWC class scores -> NCHW-contiguous full-resolution logits (the reference's output layout):
+    ``torch.ops.tss_b200.upsample_logits``."""
 
     @staticmethod
-    def backward(ctx, dy):
-        return ops.upsample_logits_bwd(dy, ctx.in_hw[0], ctx.in_hw[1], ctx.pitch), None, None
+    def apply(x, Ho, Wo):
+        return torch.ops.tss_b200.upsample_logits(x, Ho, Wo)
 
 
 class UpsampleCrossEntropy(torch.autograd.Function):
