@@ -193,6 +193,11 @@ int tss_stem3x3s2_fwd_tc(const float* x, const float* w, void* y, int N, int H, 
  * reduction dimension. */
 int tss_stem3x3s2_wgrad_tc(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout,
                            void* stream);
+/* the same through a patch matrix: patches (bf16 [N*Ho*Wo][32], workspace) receives the 27 taps of every output pixel
+ * (coalesced), then dw32 (fp32 [32][32], workspace) = dy^T . patches on the TMA-fed tensor-core weight-gradient GEMM of the
+ * pointwise convs, and dw (Cout,3,3,3) += dw32[:, :27]. */
+int tss_stem3x3s2_wgrad_patches(const float* x, const void* dy, void* patches, float* dw32, float* dw, int N,
+                                int H, int W, int Cout, void* stream);
 /* the same with the stem's BatchNorm-backward APPLY folded into the operand producer: dz is the gradient after the
  * stem's BN/ReLU, y its raw conv output, sums[2*Cout] the finished reduction (flags&TSS_EPI_RELU: mask recomputed from
  * y).  dy is never materialised (the stem has no input gradient, the weight gradient is its only reader);

@@ -303,6 +303,27 @@ def test_training_step_with_finalize_folded_into_apply_matches_default():
     assert out[True][4] == out[False][4] - 2 * 44
 
 
+@pytest.mark.parametrize('N,H,W', [(2, 64, 96), (1, 32, 300), (1, 7, 9), (3, 33, 515), (12, 768, 768)])
+def test_stem_weight_gradient_through_the_patch_matrix(N, H, W):
+    """tss_stem3x3s2_wgrad_patches (coalesced patch matrix + the TMA-fed pointwise weight-gradient GEMM) against the SIMT
+    stem weight gradient; the patch matrix itself against F.unfold."""
+    g = torch.Generator().manual_seed(H * 3 + W)
+    x = torch.randn(N, 3, H, W, generator=g).cuda()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dy = torch.randn(N, Ho, Wo, 32, generator=g).to(torch.bfloat16).cuda().permute(0, 3, 1, 2)
+    be = _lib.backend()
+    ref = torch.zeros(32, 3, 3, 3, device='cuda')
+    be.call('tss_stem3x3s2_wgrad', dict(x=x, dy=dy, dw=ref, N=N, H=H, W=W, Cout=32, dtype=1))
+    dw = torch.full((32, 3, 3, 3), 0.5, device='cuda')                       # accumulates into what is there
+    patches = torch.full((N * Ho * Wo, 32), float('nan'), dtype=torch.bfloat16, device='cuda')
+    dw32 = torch.full((32, 32), float('nan'), device='cuda')
+    be.call('tss_stem3x3s2_wgrad_patches', dict(x=x, dy=dy, patches=patches, dw32=dw32, dw=dw, N=N, H=H, W=W, Cout=32))
+    torch.cuda.synchronize()
+    want = torch.nn.functional.unfold(x, 3, padding=1, stride=2).transpose(1, 2).reshape(-1, 27)      # (ci, ky, kx) order
+    assert torch.equal(patches[:, :27].float(), want.to(torch.bfloat16).float()) and float(patches[:, 27:].abs().max()) == 0.0
+    assert rel(dw - 0.5, ref) < 1e-2                       # the image is rounded to bf16 on this path
+
+
 @pytest.mark.parametrize('N,H,W', [(2, 64, 96), (1, 32, 300), (1, 7, 9), (12, 768, 768)])
 def test_stem_on_tensor_cores_matches_the_simt_stem(N, H, W):
     g = torch.Generator().manual_seed(H + W)

@@ -113,6 +113,8 @@ def test_opcheck_on_the_gpu():
 
 @pytest.mark.gpu
 def test_functional_operators_match_stock_torch_on_the_gpu():
+    torch.backends.cudnn.allow_tf32 = False          # the yardstick must be true fp32 (cuDNN convolutions default to TF32)
+    torch.backends.cuda.matmul.allow_tf32 = False
     g = torch.Generator().manual_seed(5)
     x = ops.empty_nhwc(2, 32, 24, 40, torch.float32, 'cuda').copy_(torch.randn(2, 32, 24, 40, generator=g).cuda()).requires_grad_(True)
     wd = torch.randn(32, 1, 3, 3, generator=g).cuda().requires_grad_(True)

@@ -330,7 +330,80 @@ stem_tc_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, f
     }
 }
 
+// ------------------------------------------------------------------ weight gradient through a patch matrix -------
+// The thread-built operands above make the weight gradient the slowest kernel of the step per byte (2-byte strided loads
+// of dy for the A operand: 200-250 us for 198 MB).  Alternative: write the 27-tap patches once as a dense bf16 matrix
+// P[pixel][32] (taps 27..31 zero) with fully coalesced traffic, then dW = dy^T . P is exactly the pointwise weight
+// gradient, whose tensor-core kernel takes BOTH operands from HBM with TMA as they sit there (pwconv_tc.cu:
+// wgrad_tc_kernel, MN-major boxes).  +226 MB of traffic (P written and read once), all of it at streaming speed.
+constexpr int kPatchPix = 128;
+
+__global__ void __launch_bounds__(kPatchPix)
+stem_patches_kernel(const float* __restrict__ x, bf16* __restrict__ P, int H, int W, int Ho, int Wo, int tiles_w) {
+    __shared__ float s_x[9][2 * kPatchPix + 2];          // rows (ci, ky); input columns 2*wo0-1 .. 2*wo0+256
+    pdl_wait();
+    const int tw = blockIdx.x % tiles_w;
+    const int ho = (blockIdx.x / tiles_w) % Ho;
+    const int n = blockIdx.x / (tiles_w * Ho);
+    const int wo0 = tw * kPatchPix, wi0 = 2 * wo0 - 1;
+    constexpr int kSpan = 2 * kPatchPix + 1;              // 257 input columns feed 128 output pixels
+    for (int idx = threadIdx.x; idx < 9 * kSpan; idx += kPatchPix) {
+        const int r = idx / kSpan, j = idx - r * kSpan;
+        const int ci = r / 3, ky = r - ci * 3;
+        const int hi = 2 * ho - 1 + ky, wi = wi0 + j;
+        float v = 0.f;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(x + (((int64_t)n * 3 + ci) * H + hi) * W + wi);
+        s_x[r][j] = v;
+    }
+    __syncthreads();
+    const int wo = wo0 + (int)threadIdx.x;
+    if (wo >= Wo) return;
+    float v[32];
+#pragma unroll
+    for (int t = kTaps; t < 32; ++t) v[t] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 9; ++r)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) v[r * 3 + kx] = s_x[r][2 * threadIdx.x + kx];
+    uint4* dst = reinterpret_cast<uint4*>(P + (((int64_t)n * Ho + ho) * Wo + wo) * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        dst[j] = make_uint4(pack_bf16x2(v[8 * j + 0], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                            pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+}
+
+// dw[co][t] += dw32[co][t], t < 27  (the GEMM's [32][32] result -> the (32,3,3,3) parameter gradient)
+__global__ void stem_wgrad_unpack_kernel(const float* __restrict__ dw32, float* __restrict__ dw) {
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < CO * kTaps) dw[i] += dw32[(i / kTaps) * 32 + (i % kTaps)];
+}
+
 }  // namespace
+
+// pwconv_tc.cu
+int tss_pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int K, int Nc, int64_t ldx,
+                        int64_t lddy, cudaStream_t st);
+
+extern "C" int tss_stem3x3s2_wgrad_patches(const float* x, const void* dy, void* patches, float* dw32, float* dw, int N,
+                                           int H, int W, int Cout, void* stream) {
+    TSS_REQUIRE(N > 0 && H > 0 && W > 0, "stem3x3s2_wgrad_patches: empty input");
+    TSS_REQUIRE(Cout == CO, "stem3x3s2_wgrad_patches: Cout=%d unsupported (only %d)", Cout, CO);
+    TSS_REQUIRE(patches != nullptr && dw32 != nullptr && dw != nullptr, "stem3x3s2_wgrad_patches: missing workspace");
+    TSS_REQUIRE((((uintptr_t)patches | (uintptr_t)dw32 | (uintptr_t)dy) & 15) == 0, "stem3x3s2_wgrad_patches: buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const int tiles_w = (Wo + kPatchPix - 1) / kPatchPix;
+    const int64_t M = (int64_t)N * Ho * Wo;
+    TSS_REQUIRE((int64_t)N * Ho * tiles_w < (1ll << 31), "stem3x3s2_wgrad_patches: grid too large");
+    tss_launch(stem_patches_kernel, (unsigned)((int64_t)N * Ho * tiles_w), kPatchPix, 0, st, x, (bf16*)patches, H, W, Ho, Wo, tiles_w);
+    TSS_LAUNCH_CHECK("stem3x3s2_wgrad_patches(im2col)");
+    TSS_CUDA(cudaMemsetAsync(dw32, 0, (size_t)CO * 32 * sizeof(float), st));
+    if (int e = tss_pwconv_wgrad_tc(patches, dy, dw32, M, 32, CO, 32, CO, st)) return e;
+    tss_launch(stem_wgrad_unpack_kernel, (CO * kTaps + 255) / 256, 256, 0, st, (const float*)dw32, dw);
+    TSS_LAUNCH_CHECK("stem3x3s2_wgrad_patches(unpack)");
+    return TSS_OK;
+}
 
 extern "C" int tss_stem3x3s2_fwd_tc(const float* x, const float* w, void* y, int N, int H, int W, int Cout,
                                     const float* scale, const float* shift, int flags, double* stats, void* stream) {

@@ -9,6 +9,7 @@ stream.  Nothing here computes on the host and nothing falls back to torch ops.
 import torch
 
 from . import _lib
+from .gates import gate
 from ._lib import EPI_RELU, dtype_code
 
 PYRAMID_BINS = (1, 2, 3, 6)
@@ -342,6 +343,13 @@ def stem_wgrad_tc(x, dy, dw):
     N, _, H, W = x.shape
     if dy.dtype != torch.bfloat16 or _g(dy, 'stem_wgrad_tc')[4] != dy.shape[1]:
         raise RuntimeError('stem_wgrad_tc: expects a dense bfloat16 NHWC gradient')
+    if gate('STEM_WGRAD_PATCHES'):
+        # patch matrix + the TMA-fed pointwise weight-gradient GEMM instead of thread-built operands
+        M = N * dy.shape[2] * dy.shape[3]
+        patches = torch.empty((M, 32), dtype=torch.bfloat16, device=x.device)
+        dw32 = torch.empty((32, 32), dtype=torch.float32, device=x.device)
+        _lib.call('tss_stem3x3s2_wgrad_patches', x=x, dy=dy, patches=patches, dw32=dw32, dw=dw, N=N, H=H, W=W, Cout=dy.shape[1])
+        return
     _lib.call('tss_stem3x3s2_wgrad_tc', x=x, dy=dy, dw=dw, N=N, H=H, W=W, Cout=dy.shape[1])
 
 
