@@ -44,10 +44,12 @@ def parse():
     ap.add_argument('--kernels', action='store_true', help='also dump the per-kernel table to stderr')
     ap.add_argument('--headline-only', action='store_true',
                     help='skip the 1024x2048 training leg, the 500-map mIoU leg and the bs1 inference leg (A/B runs)')
-    ap.add_argument('--e2e-uint8', action='store_true',
-                    help='end-to-end leg fed with decoded uint8 frames + label ids, normalised / mapped on the device by '
-                         'data.DeviceTransform (28 MB instead of 141 MB host->device per step); off until that kernel has '
-                         'been validated on the GPU')
+    ap.add_argument('--e2e-fp32', action='store_true',
+                    help='end-to-end leg fed with fp32 crops + int64 labels (what the reference DataLoader yields after its '
+                         'CPU transforms: 141 MB host->device per step) instead of decoded uint8 frames + uint8 label ids '
+                         'normalised / mapped on the device by data.DeviceTransform (28 MB per step, the default)')
+    ap.add_argument('--e2e-sync-loss', action='store_true',
+                    help='end-to-end leg with loss.item() inside every step (engine.py:39) instead of the lazy read-back')
     return ap.parse_args()
 
 
@@ -526,7 +528,7 @@ def main():
 
     # ---- end to end: the public engine API, batch in pinned host memory -------------------
     e2e_input = 'fp32 crops + int64 labels (what the reference DataLoader yields)'
-    if args.e2e_uint8:
+    if not args.e2e_fp32:
         # the same crops as decoded uint8 frames + Cityscapes label ids whose train ids are exactly y
         from torch_semantic_segmentation_b200.data import DeviceTransform, TRAIN_MAPPING
         inverse = torch.zeros(256, dtype=torch.uint8)
@@ -544,7 +546,7 @@ def main():
         transform = None
         h2d_bytes = xh.numel() * 4 + yh.numel() * 8
     trainer = create_segmentation_trainer(model, opt, loss_fn, device, use_f16=True, logging=False,
-                                          cuda_graph=use_graph, transform=transform)
+                                          cuda_graph=use_graph, transform=transform, lazy_loss=not args.e2e_sync_loss)
     trainer.run([(xh, yh)] * 2)
     barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -647,7 +649,10 @@ def main():
                    'gates': sorted(k for k, v in os.environ.items() if k.startswith('TSS_') and v not in ('', '0'))},
         'loss': float(loss),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes,
-                'd2h_bytes_per_step': 4, 'ms_per_step': float(ems) / args.steps, 'input': e2e_input},
+                'd2h_bytes_per_step': 4, 'ms_per_step': float(ems) / args.steps, 'input': e2e_input,
+                'loss_readback': 'loss.item() every step' if args.e2e_sync_loss else
+                                 'every step reads one loss back from pinned memory: the previous step\'s (lazy_loss=True)',
+                'api': 'create_segmentation_trainer(...).run(loader)'},
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': roofline,

@@ -198,6 +198,11 @@ int tss_stem3x3s2_wgrad_tc(const float* x, const void* dy, float* dw, int N, int
  * pointwise convs, and dw (Cout,3,3,3) += dw32[:, :27]. */
 int tss_stem3x3s2_wgrad_patches(const float* x, const void* dy, void* patches, float* dw32, float* dw, int N,
                                 int H, int W, int Cout, void* stream);
+/* its two halves: the patch matrix depends on the image only (the training forward launches it on a side stream, off the
+ * backward pass's tail), the GEMM + unpack on the gradient */
+int tss_stem3x3s2_patches(const float* x, void* patches, int N, int H, int W, void* stream);
+int tss_stem3x3s2_wgrad_from_patches(const void* patches, const void* dy, float* dw32, float* dw, int64_t M, int Cout,
+                                     void* stream);
 /* the same with the stem's BatchNorm-backward APPLY folded into the operand producer: dz is the gradient after the
  * stem's BN/ReLU, y its raw conv output, sums[2*Cout] the finished reduction (flags&TSS_EPI_RELU: mask recomputed from
  * y).  dy is never materialised (the stem has no input gradient, the weight gradient is its only reader);

@@ -351,6 +351,22 @@ class FakeBackend:
         dw += nngrad.conv2d_weight(x.bfloat16().float(), dw.shape, dy.float(), 2, 1)          # image rounded to bf16
         return 0
 
+    def tss_stem3x3s2_patches(self, x, patches, N, H, W):
+        cols = F.unfold(x, 3, padding=1, stride=2).transpose(1, 2).reshape(-1, 27)          # (ci, ky, kx) order
+        patches.zero_()
+        patches[:, :27].copy_(cols)
+        return 0
+
+    def tss_stem3x3s2_wgrad_from_patches(self, patches, dy, dw32, dw, M, Cout):
+        g = dy.permute(0, 2, 3, 1).reshape(M, Cout).float()
+        dw32.copy_(g.t() @ patches.float())
+        dw += dw32[:, :27].reshape(dw.shape)
+        return 0
+
+    def tss_stem3x3s2_wgrad_patches(self, x, dy, patches, dw32, dw, N, H, W, Cout):
+        self.tss_stem3x3s2_patches(x, patches, N, H, W)
+        return self.tss_stem3x3s2_wgrad_from_patches(patches, dy, dw32, dw, patches.shape[0], Cout)
+
     def tss_stem3x3s2_wgrad_tc_bn(self, x, dz, y, mean, rstd, gamma, beta, sums, flags, count, dw, dgamma, dbeta, N, H, W, Cout):
         dy = torch.empty_like(dz)
         Ho, Wo = dz.shape[2], dz.shape[3]

@@ -327,7 +327,7 @@ def test_tensor_core_stem_gate_is_plumbing_equivalent(fake_backend):
         Fn.STEM_TC = keep
     assert rel(runs[True][0], runs[False][0]) < 3e-2
     assert torch.isfinite(runs[True][1]).all() and float(runs[True][1].abs().sum()) > 0
-    assert runs[True][2].get('tss_stem3x3s2_fwd_tc') == 1 and runs[True][2].get('tss_stem3x3s2_wgrad_tc') == 1
+    assert runs[True][2].get('tss_stem3x3s2_fwd_tc') == 1 and (runs[True][2].get('tss_stem3x3s2_wgrad_tc') == 1 or runs[True][2].get('tss_stem3x3s2_wgrad_from_patches') == 1)
     assert 'tss_stem3x3s2_fwd' not in runs[True][2] and 'tss_stem3x3s2_fwd_tc' not in runs[False][2]
 
 
@@ -629,7 +629,10 @@ def test_stem_backward_without_the_dy_tensor(fake_backend):
     finally:
         Fn.STEM_TC, Fn.STEM_BWD_FUSED = keep
     for k in runs[False][0]:
-        assert torch.equal(runs[True][0][k], runs[False][0][k]), k
+        if k == 'downsample.0.0.weight':      # the unfused default multiplies dy with a patch matrix: another summation order
+            assert rel(runs[True][0][k], runs[False][0][k]) < 1e-5, k
+        else:
+            assert torch.equal(runs[True][0][k], runs[False][0][k]), k
     assert runs[True][1]['tss_stem3x3s2_wgrad_tc_bn'] == 1 and 'tss_stem3x3s2_wgrad_tc' not in runs[True][1]
     assert runs[True][1]['tss_bn_bwd_apply'] == runs[False][1]['tss_bn_bwd_apply'] - 1
 
@@ -668,7 +671,7 @@ def test_eval_operands_are_refreshed_in_place_after_training(fake_backend):
 def test_gate_defaults_and_environment_override(monkeypatch):
     """Only what has been measured on the GPU is on by default (gates.py); TSS_<NAME> overrides for A/B runs."""
     from torch_semantic_segmentation_b200 import gates
-    assert sorted(k for k, v in gates.DEFAULTS.items() if v) == ['CLASS_TC', 'DEFER_LOGITS', 'FUSE_BNRED', 'FUSE_BNRED_EXT', 'OWN_DROPOUT', 'STEM_TC']
+    assert sorted(k for k, v in gates.DEFAULTS.items() if v) == ['CLASS_TC', 'DEFER_LOGITS', 'FUSE_BNRED', 'FUSE_BNRED_EXT', 'OWN_DROPOUT', 'SLOT_GRAPHS', 'STEM_TC', 'STEM_WGRAD_PATCHES']
     monkeypatch.delenv('TSS_FUSE_PPM', raising=False)
     assert gates.gate('FUSE_PPM') is False and gates.gate('FUSE_BNRED') is True
     monkeypatch.setenv('TSS_FUSE_PPM', '1')

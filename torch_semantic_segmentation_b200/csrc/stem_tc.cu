@@ -385,24 +385,37 @@ __global__ void stem_wgrad_unpack_kernel(const float* __restrict__ dw32, float* 
 int tss_pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int K, int Nc, int64_t ldx,
                         int64_t lddy, cudaStream_t st);
 
-extern "C" int tss_stem3x3s2_wgrad_patches(const float* x, const void* dy, void* patches, float* dw32, float* dw, int N,
-                                           int H, int W, int Cout, void* stream) {
-    TSS_REQUIRE(N > 0 && H > 0 && W > 0, "stem3x3s2_wgrad_patches: empty input");
-    TSS_REQUIRE(Cout == CO, "stem3x3s2_wgrad_patches: Cout=%d unsupported (only %d)", Cout, CO);
-    TSS_REQUIRE(patches != nullptr && dw32 != nullptr && dw != nullptr, "stem3x3s2_wgrad_patches: missing workspace");
-    TSS_REQUIRE((((uintptr_t)patches | (uintptr_t)dw32 | (uintptr_t)dy) & 15) == 0, "stem3x3s2_wgrad_patches: buffers must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
+extern "C" int tss_stem3x3s2_patches(const float* x, void* patches, int N, int H, int W, void* stream) {
+    TSS_REQUIRE(N > 0 && H > 0 && W > 0, "stem3x3s2_patches: empty input");
+    TSS_REQUIRE(patches != nullptr && ((uintptr_t)patches & 15) == 0, "stem3x3s2_patches: patches must be 16-byte aligned");
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const int tiles_w = (Wo + kPatchPix - 1) / kPatchPix;
-    const int64_t M = (int64_t)N * Ho * Wo;
-    TSS_REQUIRE((int64_t)N * Ho * tiles_w < (1ll << 31), "stem3x3s2_wgrad_patches: grid too large");
-    tss_launch(stem_patches_kernel, (unsigned)((int64_t)N * Ho * tiles_w), kPatchPix, 0, st, x, (bf16*)patches, H, W, Ho, Wo, tiles_w);
-    TSS_LAUNCH_CHECK("stem3x3s2_wgrad_patches(im2col)");
+    TSS_REQUIRE((int64_t)N * Ho * tiles_w < (1ll << 31), "stem3x3s2_patches: grid too large");
+    tss_launch(stem_patches_kernel, (unsigned)((int64_t)N * Ho * tiles_w), kPatchPix, 0, (cudaStream_t)stream, x, (bf16*)patches, H, W,
+               Ho, Wo, tiles_w);
+    TSS_LAUNCH_CHECK("stem3x3s2_patches");
+    return TSS_OK;
+}
+
+extern "C" int tss_stem3x3s2_wgrad_from_patches(const void* patches, const void* dy, float* dw32, float* dw, int64_t M, int Cout,
+                                                void* stream) {
+    TSS_REQUIRE(M > 0, "stem3x3s2_wgrad_from_patches: empty input");
+    TSS_REQUIRE(Cout == CO, "stem3x3s2_wgrad_from_patches: Cout=%d unsupported (only %d)", Cout, CO);
+    TSS_REQUIRE(patches != nullptr && dw32 != nullptr && dw != nullptr, "stem3x3s2_wgrad_from_patches: missing buffer");
+    TSS_REQUIRE((((uintptr_t)patches | (uintptr_t)dw32 | (uintptr_t)dy) & 15) == 0, "stem3x3s2_wgrad_from_patches: buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
     TSS_CUDA(cudaMemsetAsync(dw32, 0, (size_t)CO * 32 * sizeof(float), st));
     if (int e = tss_pwconv_wgrad_tc(patches, dy, dw32, M, 32, CO, 32, CO, st)) return e;
     tss_launch(stem_wgrad_unpack_kernel, (CO * kTaps + 255) / 256, 256, 0, st, (const float*)dw32, dw);
-    TSS_LAUNCH_CHECK("stem3x3s2_wgrad_patches(unpack)");
+    TSS_LAUNCH_CHECK("stem3x3s2_wgrad_from_patches(unpack)");
     return TSS_OK;
+}
+
+extern "C" int tss_stem3x3s2_wgrad_patches(const float* x, const void* dy, void* patches, float* dw32, float* dw, int N,
+                                           int H, int W, int Cout, void* stream) {
+    if (int e = tss_stem3x3s2_patches(x, patches, N, H, W, stream)) return e;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    return tss_stem3x3s2_wgrad_from_patches(patches, dy, dw32, dw, (int64_t)N * Ho * Wo, Cout, stream);
 }
 
 extern "C" int tss_stem3x3s2_fwd_tc(const float* x, const float* w, void* y, int N, int H, int W, int Cout,

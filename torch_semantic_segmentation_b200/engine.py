@@ -222,6 +222,31 @@ class _BatchStager:
         self.free[staged.slot] = ev
 
 
+class _LossReader:
+    """What ``update_fn`` returns for the step's loss.  ``lazy=False``: ``loss.item()`` -- the reference's contract
+    (engine.py:39), one host synchronisation per step, during which the GPU idles while the host prepares the next
+    launch.  ``lazy=True``: the loss is copied to pinned host memory behind the step and the PREVIOUS step's value is
+    returned (the first step returns its own), so the host always runs one step ahead of the device."""
+
+    def __init__(self, device, lazy):
+        self.lazy = lazy and torch.device(device).type == 'cuda'
+        self.slots = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)] if self.lazy else None
+        self.k, self.pending = 0, None
+
+    def __call__(self, loss):
+        if not self.lazy:
+            return loss.item()
+        k, self.k = self.k, self.k ^ 1
+        self.slots[k].copy_(loss.detach().reshape(1).float(), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        prev, self.pending = self.pending, (k, done)
+        if prev is None:
+            prev = self.pending
+        prev[1].synchronize()
+        return float(self.slots[prev[0]])
+
+
 class GraphedTrainStep:
     """The whole optimisation step (zero_grad, forward, loss, backward, gradient all-reduce,
     optimizer) captured ONCE as a CUDA graph and replayed per batch: ~350 kernel launches become
@@ -337,7 +362,7 @@ class GraphedEvalStep:
 
 # ------------------------------------------------------------------ the two factories -------
 def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False, logging=True,
-                                non_blocking=True, cuda_graph=False, prefetch=True, transform=None):
+                                non_blocking=True, cuda_graph=False, prefetch=True, transform=None, lazy_loss=False):
     """reference: engine.py:22-56.  ``cuda_graph=True`` (an addition) replays the step as one
     CUDA graph; it needs fixed batch shapes and a capturable optimizer (``optim.FlatAdamW`` or
     ``torch.optim.AdamW(capturable=True)``).  The first batch is used for warm-up and capture
@@ -346,12 +371,15 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
     step of 12 x 768 x 768 fp32 images + int64 labels) overlaps with compute; ``engine.py:27`` copies
     synchronously in front of every step.  ``transform`` (an addition): a ``data.DeviceTransform``; the loader then
     yields decoded uint8 frames and label ids ((N,H,W,3), (N,H,W)) and scale / crop / flip / normalise / label
-    mapping run on the device in front of the model (scripts/train_fastscnn.py:62-72 does them in the workers)."""
+    mapping run on the device in front of the model (scripts/train_fastscnn.py:62-72 does them in the workers).
+    ``lazy_loss=True`` (an addition): ``state.output`` of iteration i is the loss of iteration i-1 (``_LossReader``), which
+    removes the per-step host synchronisation of ``engine.py:39`` from the critical path."""
     if use_f16 and hasattr(model, 'set_compute_dtype'):
         model.set_compute_dtype(torch.bfloat16)
     Fn.enable_deferred_logits(model, loss_fn)     # nobody but loss_fn sees y_pred inside update_fn
     graphed = {}
     stager = _BatchStager(device, non_blocking) if (prefetch and torch.device(device).type == 'cuda') else None
+    read_loss = _LossReader(device, lazy_loss)
 
     def fetch(batch):
         """-> (x, y) on the device; a staged batch only has to be waited for."""
@@ -383,7 +411,7 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
                     stager.release(staged)
                 if SLOT_GRAPHS:
                     _trainer.prefetch_next()
-                return out.item()
+                return read_loss(out)
             x, y = fetch(batch) if staged is not None else batch
             if not g.matches(x, y):
                 raise RuntimeError('cuda_graph=True needs a fixed batch shape; got %s' % (tuple(x.shape),))
@@ -391,7 +419,7 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
             if staged is not None:
                 stager.release(staged)
             _trainer.prefetch_next()             # the step is in flight: now copy batch i+1 under it
-            return loss.item()
+            return read_loss(loss)
         optimizer.zero_grad()
         x, y = fetch(batch)
         if transform is not None:
@@ -407,7 +435,7 @@ def create_segmentation_trainer(model, optimizer, loss_fn, device, use_f16=False
         if staged is not None:
             stager.release(staged)
         _trainer.prefetch_next()
-        return loss.item()
+        return read_loss(loss)
 
     trainer = Engine(update_fn)
     if stager is not None:

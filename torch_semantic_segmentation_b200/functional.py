@@ -286,6 +286,15 @@ class ConvBNAct(torch.autograd.Function):
         else:
             y = conv_forward(spec, x, weight, stats=scratch, packed=packed)
         ctx.in_affine = in_affine
+        ctx.patches = None
+        if (spec.kind == 'stem' and STEM_TC and gate('STEM_WGRAD_PATCHES') and spec.dtype == torch.bfloat16 and C == 32
+                and x.is_cuda and wgrad_lane.enabled and getattr(weight, '_tss_grad', None) is not None):
+            # the stem's weight gradient reads the image as a patch matrix that does not depend on the backward pass:
+            # built now, on the weight-gradient side stream, under the rest of the forward pass
+            side = wgrad_lane.stream(x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):
+                ctx.patches = ops.stem_patches(x)
         N, _, H, W = y.shape
         world, group = _sync_group(bn)
         if world > 1:
@@ -418,7 +427,10 @@ class ConvBNAct(torch.autograd.Function):
         else:  # stem: the image needs no gradient
             if ctx.needs_input_grad[0]:
                 raise RuntimeError('gradient w.r.t. the input image is not implemented')
-            if STEM_TC and dy.dtype == torch.bfloat16 and weight.shape[0] == 32:
+            if ctx.patches is not None and dy.dtype == torch.bfloat16:
+                patches = ctx.patches        # made on the lane's stream in forward: stream order is the dependency
+                lane(lambda: ops.stem_wgrad_from_patches(patches, dy, dw))
+            elif STEM_TC and dy.dtype == torch.bfloat16 and weight.shape[0] == 32:
                 lane(lambda: ops.stem_wgrad_tc(x, dy, dw))
             else:
                 lane(lambda: ops.stem_wgrad(x, dy, dw))

@@ -345,12 +345,26 @@ def stem_wgrad_tc(x, dy, dw):
         raise RuntimeError('stem_wgrad_tc: expects a dense bfloat16 NHWC gradient')
     if gate('STEM_WGRAD_PATCHES'):
         # patch matrix + the TMA-fed pointwise weight-gradient GEMM instead of thread-built operands
-        M = N * dy.shape[2] * dy.shape[3]
-        patches = torch.empty((M, 32), dtype=torch.bfloat16, device=x.device)
-        dw32 = torch.empty((32, 32), dtype=torch.float32, device=x.device)
-        _lib.call('tss_stem3x3s2_wgrad_patches', x=x, dy=dy, patches=patches, dw32=dw32, dw=dw, N=N, H=H, W=W, Cout=dy.shape[1])
+        stem_wgrad_from_patches(stem_patches(x), dy, dw)
         return
     _lib.call('tss_stem3x3s2_wgrad_tc', x=x, dy=dy, dw=dw, N=N, H=H, W=W, Cout=dy.shape[1])
+
+
+def stem_patches(x):
+    """bf16 patch matrix (N*Ho*Wo, 32) of the stem convolution: the 27 taps of every output pixel, 5 zero columns."""
+    N, _, H, W = x.shape
+    M = N * ((H - 1) // 2 + 1) * ((W - 1) // 2 + 1)
+    patches = torch.empty((M, 32), dtype=torch.bfloat16, device=x.device)
+    _lib.call('tss_stem3x3s2_patches', x=x, patches=patches, N=N, H=H, W=W)
+    return patches
+
+
+def stem_wgrad_from_patches(patches, dy, dw):
+    """dw (32,3,3,3) += dy^T . patches on the TMA-fed tensor-core weight-gradient GEMM of the pointwise convs."""
+    if dy.dtype != torch.bfloat16 or _g(dy, 'stem_wgrad_from_patches')[4] != dy.shape[1]:
+        raise RuntimeError('stem_wgrad_from_patches: expects a dense bfloat16 NHWC gradient')
+    dw32 = torch.empty((32, 32), dtype=torch.float32, device=dy.device)
+    _lib.call('tss_stem3x3s2_wgrad_from_patches', patches=patches, dy=dy, dw32=dw32, dw=dw, M=patches.shape[0], Cout=dy.shape[1])
 
 
 def stem_wgrad_tc_bn(x, dz, y, mean, rstd, gamma, beta, sums, relu, dw, dgamma=None, dbeta=None):
