@@ -4,6 +4,8 @@
 // conv.  The epilogue reads the matching yp values, applies the ReLU mask recomputed from yp, stores
 // g = dz * mask instead of dz and accumulates  sums[c] += sum g,  sums[C+c] += sum g * xhat  (what
 // bn_bwd_reduce_kernel would compute in a pass of its own over dz and yp).
+#include <stdlib.h>
+
 #include "tma.cuh"
 
 namespace {
@@ -13,7 +15,8 @@ constexpr int IH = TH + 2;
 
 template <typename T>
 __global__ void __launch_bounds__(192, 2)
-dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const float* __restrict__ w, T* __restrict__ g_out,
+dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmY,
+                      const float* __restrict__ w, T* __restrict__ g_out,
                       int H, int W, int C, int CB, int TW, int tiles_w, int tiles_h, const T* __restrict__ yp,
                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                       const float* __restrict__ beta, int relu, float* __restrict__ sums) {
@@ -22,7 +25,11 @@ dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const float* __re
     const int IW = TW + 2;
     const uint32_t tile_bytes = (uint32_t)IH * IW * CB * sizeof(T);
     T* tile = (T*)smem;
-    uint64_t* bar = (uint64_t*)(smem + ((tile_bytes + 15) & ~15u));
+    // the producer's raw output for the tile's TH x TW pixels arrives by TMA too, under the same barrier: the epilogue
+    // reads it from shared memory instead of starting a second round of global loads after the convolution
+    const uint32_t ytile_bytes = (uint32_t)TH * TW * CB * sizeof(T);
+    T* ytile = (T*)(smem + ((tile_bytes + 127) & ~127u));
+    uint64_t* bar = (uint64_t*)((uint8_t*)ytile + ((ytile_bytes + 15) & ~15u));
 
     int t = blockIdx.x;
     const int tw = t % tiles_w; t /= tiles_w;
@@ -38,8 +45,9 @@ dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const float* __re
     __syncthreads();
     pdl_wait();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(smem_u32(bar), tile_bytes);
+        mbar_expect_tx(smem_u32(bar), tile_bytes + ytile_bytes);
         tma_load_4d(smem_u32(tile), &tmG, smem_u32(bar), cb0, w0 - 1, h0 - 1, n);
+        tma_load_4d(smem_u32(ytile), &tmY, smem_u32(bar), cb0, w0, h0, n);
     }
 
     const int CGB = CB >> 3;
@@ -92,7 +100,7 @@ dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const float* __re
         for (int r = 0; r < TH; ++r) {
             if (h0 + r < H) {
                 float yy[8], g[8];
-                load8(yp + base + (int64_t)r * W * C, yy);
+                load8_smem(ytile + ((size_t)r * TW + col) * CB + cg * 8, yy);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float dz = (e & 1) ? acc[r][e >> 1].y : acc[r][e >> 1].x;
@@ -129,8 +137,8 @@ dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const float* __re
 // stem and the first expand conv).
 constexpr int kQuadThreads = 128;
 
-template <typename T, int R>
-__global__ void __launch_bounds__(kQuadThreads, 3)
+template <typename T, int R, int kMinBlocks>
+__global__ void __launch_bounds__(kQuadThreads, kMinBlocks)
 dw_dgrad_s2_bnred_kernel(const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ g_out,
                          int N, int Hi, int Wi, int Ho, int Wo, int C, const T* __restrict__ yp,
                          const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -159,10 +167,11 @@ dw_dgrad_s2_bnred_kernel(const T* __restrict__ dy, const float* __restrict__ w, 
         sc[e] = (gamma != nullptr ? __ldg(gamma + c0 + e) : 1.f) * r_;
         sh[e] = (beta != nullptr ? __ldg(beta + c0 + e) : 0.f) - m_ * sc[e];
     }
-    // mask, accumulate and store one output pixel's 8 channels
-    auto emit = [&](float (&o)[8], int64_t off) {
+    // mask, accumulate and store one output pixel's 8 channels (the producer's raw output arrives as a raw vector that
+    // was requested a whole quad earlier)
+    auto emit = [&](float (&o)[8], const Raw8<T>& ryy, int64_t off) {
         float yy[8];
-        load8(yp + off, yy);
+        ryy.get(yy);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             if (relu && !(fmaf(yy[e], sc[e], sh[e]) > 0.f)) o[e] = 0.f;
@@ -189,30 +198,43 @@ dw_dgrad_s2_bnred_kernel(const T* __restrict__ dy, const float* __restrict__ w, 
         for (int r = 0; r < R; ++r) {
             const int p = p0 + r;
             if (p >= Ho) break;
+            // all six loads of this quad row (2 gradient vectors of the next row, 4 producer outputs) are issued before
+            // the first of them is used: six 128-bit requests in flight per thread instead of one or two
+            const bool row1 = 2 * p + 1 < Hi;
+            const int64_t off00 = xn + ((int64_t)(2 * p) * Wi + 2 * q) * C;
+            const int64_t off10 = off00 + (int64_t)Wi * C;
+            Raw8<T> rn[2], ry[4];
+            rn[0].zero(); rn[1].zero();
+            ry[0].ld(yp + off00);
+            if (col1) ry[1].ld(yp + off00 + C);
+            if (row1) {
+                ry[2].ld(yp + off10);
+                if (col1) ry[3].ld(yp + off10 + C);
+            }
             if (p + 1 < Ho) {
-                load8(dyn + ((int64_t)(p + 1) * Wo + q) * C, g1[0]);
-                if (q1) load8(dyn + ((int64_t)(p + 1) * Wo + q + 1) * C, g1[1]); else zero8(g1[1]);
-            } else { zero8(g1[0]); zero8(g1[1]); }
+                rn[0].ld(dyn + ((int64_t)(p + 1) * Wo + q) * C);
+                if (q1) rn[1].ld(dyn + ((int64_t)(p + 1) * Wo + q + 1) * C);
+            }
+            rn[0].get(g1[0]);
+            rn[1].get(g1[1]);
             float o[8];
-            const int64_t row0 = xn + ((int64_t)(2 * p) * Wi + 2 * q) * C;
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = g0[0][e] * wr[4][e];
-            emit(o, row0);
+            emit(o, ry[0], off00);
             if (col1) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = fmaf(g0[1][e], wr[3][e], g0[0][e] * wr[5][e]);
-                emit(o, row0 + C);
+                emit(o, ry[1], off00 + C);
             }
-            if (2 * p + 1 < Hi) {
-                const int64_t row1 = row0 + (int64_t)Wi * C;
+            if (row1) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = fmaf(g1[0][e], wr[1][e], g0[0][e] * wr[7][e]);
-                emit(o, row1);
+                emit(o, ry[2], off10);
                 if (col1) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
                         o[e] = fmaf(g1[1][e], wr[0][e], fmaf(g1[0][e], wr[2][e], fmaf(g0[1][e], wr[6][e], g0[0][e] * wr[8][e])));
-                    emit(o, row1 + C);
+                    emit(o, ry[3], off10 + C);
                 }
             }
 #pragma unroll
@@ -256,12 +278,15 @@ extern "C" int tss_dwconv3x3_dgrad_s2_bnred(const void* dy, const float* w, void
     // persistent grid whose total thread count is a multiple of CG (loop-invariant channel group per thread)
     const int qd = CG / gcd_int2(CG, kQuadThreads);
     int64_t grid = ceil_div64(total, kQuadThreads);
-    const int64_t cap = (int64_t)tss_num_sms() * 3;          // 3 resident CTAs of 128 threads per SM (168 registers)
+    // 3 resident CTAs of 128 threads per SM (168 registers, a few spills) or 2 (no spills): TSS_S2_OCC picks, default 3
+    static const int occ = [] { const char* e = getenv("TSS_S2_OCC"); return (e != nullptr && e[0] == '2') ? 2 : 3; }();
+    const int64_t cap = (int64_t)tss_num_sms() * occ;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     grid = (grid + qd - 1) / qd * qd;
     TSS_DISPATCH_DTYPE(dtype, "dwconv3x3_dgrad_s2_bnred", {
-        tss_launch(dw_dgrad_s2_bnred_kernel<T, R>, (unsigned)grid, kQuadThreads, (size_t)2 * C * sizeof(float), (cudaStream_t)stream,
+        auto kern = occ == 2 ? dw_dgrad_s2_bnred_kernel<T, R, 2> : dw_dgrad_s2_bnred_kernel<T, R, 3>;
+        tss_launch(kern, (unsigned)grid, kQuadThreads, (size_t)2 * C * sizeof(float), (cudaStream_t)stream,
                    (const T*)dy, w, (T*)g, N, Hi, Wi, Ho, Wo, C, (const T*)yp, mean, rstd, gamma, beta, flags & TSS_EPI_RELU, sums);
         TSS_LAUNCH_CHECK("dwconv3x3_dgrad_s2_bnred");
         return TSS_OK;
@@ -289,10 +314,16 @@ extern "C" int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g
         CUresult r = enc(&map, TmaTypeB<T>::v, 4, const_cast<void*>(dy), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         TSS_REQUIRE(r == CUDA_SUCCESS, "dwconv3x3_dgrad_bnred: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        CUtensorMap mapy;
+        cuuint32_t boxy[4] = {(cuuint32_t)CB, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+        r = enc(&mapy, TmaTypeB<T>::v, 4, const_cast<void*>(yp), gdim, gstr, boxy, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TSS_REQUIRE(r == CUDA_SUCCESS, "dwconv3x3_dgrad_bnred: cuTensorMapEncodeTiled (yp) failed (%d)", (int)r);
         const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
         const int threads = (CB / 8) * TW;
         const size_t tile_bytes = (size_t)IH * IW * CB * sizeof(T);
-        size_t smem = 128 + ((tile_bytes + 15) & ~(size_t)15) + 16;
+        const size_t ytile_bytes = (size_t)TH * TW * CB * sizeof(T);
+        size_t smem = 128 + ((tile_bytes + 127) & ~(size_t)127) + ((ytile_bytes + 15) & ~(size_t)15) + 16;
         const size_t part = (size_t)2 * TW * CB * sizeof(float) + 128;
         if (smem < part) smem = part;
         auto kern = dw_dgrad_bnred_kernel<T>;
@@ -302,7 +333,7 @@ extern "C" int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g
             attr_set = true;
         }
         dim3 grid((unsigned)((int64_t)N * tiles_h * tiles_w), (unsigned)(C / CB));
-        tss_launch(kern, grid, threads, smem, (cudaStream_t)stream, map, w, (T*)g, H, W, C, CB, TW, tiles_w, tiles_h, (const T*)yp,
+        tss_launch(kern, grid, threads, smem, (cudaStream_t)stream, map, mapy, w, (T*)g, H, W, C, CB, TW, tiles_w, tiles_h, (const T*)yp,
                    mean, rstd, gamma, beta, flags & TSS_EPI_RELU, sums);
         TSS_LAUNCH_CHECK("dwconv3x3_dgrad_bnred");
         return TSS_OK;
