@@ -464,8 +464,19 @@ int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, 
     TSS_REQUIRE(ldy % 8 == 0 && (res == nullptr || ldr % 8 == 0), "pwconv_tc: output / residual pitch must be a multiple of 8");
     TSS_REQUIRE(((uintptr_t)y & 15) == 0 && ((uintptr_t)res & 15) == 0, "pwconv_tc: output / residual must be 16-byte aligned");
     TSS_REQUIRE(scale == nullptr || shift != nullptr, "pwconv_tc: scale without shift");
-    const int bn = pick_block_n(Nc, fwd_tile_cap());
+    int bn = pick_block_n(Nc, fwd_tile_cap());
     TSS_REQUIRE(bn >= 16, "pwconv_tc: no tile width for Nc=%d", Nc);
+    // Small maps (1/16, 1/32 resolution: 216 / 54 row tiles) leave most of the 148 SMs without a CTA at the default tile
+    // width: narrow the column tile until there are at least `fill` CTAs per SM (the A tile is re-read from L2).
+    {
+        static const int fill = [] { const char* e = getenv("TSS_PW_FILL"); return e ? atoi(e) : 2; }();
+        const int64_t m_tiles = ceil_div64(M, BM);
+        while (fill > 0 && bn > 16 && m_tiles * (Nc / bn) < (int64_t)fill * tss_num_sms()) {
+            const int nb = pick_block_n(Nc, bn - 16);
+            if (nb < 16) break;
+            bn = nb;
+        }
+    }
     CUtensorMap tmA, tmB;
     if (int e = make_map(&tmA, x, M, K, ldx, BM)) return e;
     if (int e = make_map(&tmB, wp, Nc, K, K, bn)) return e;
