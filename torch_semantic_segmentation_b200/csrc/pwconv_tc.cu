@@ -654,9 +654,15 @@ int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, 
     if (int e = make_map(&tmA, x, M, K, ldx, BM)) return e;
     if (int e = make_map(&tmB, wp, Nc, K, K, bn)) return e;
     const int num_kb = (K + BK - 1) / BK;
-    static const int persist = [] { const char* e = getenv("TSS_PW_PERSIST"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+    // 0 = never, 1 = where it measured faster (the default), 2 = always.  Per-shape times on B200 (tools/time_ops.py, us,
+    // one-tile-per-CTA -> persistent): forward 32->48 @1/4 62 -> 35, 48->64 @1/8 19 -> 15, dgrad into 64 channels @1/8 26 -> 22,
+    // 128->128 @1/8 dgrad 18 -> 14; but forward 64->384 @1/8 (6 column tiles) 50 -> 105, 96->576 @1/32 8 -> 12: with several
+    // column tiles the epilogue of a tile is the bound and 2 resident persistent CTAs drain fewer tiles at a time than 6
+    // one-tile CTAs.  So: at most two column tiles and at least two waves of row tiles.
+    static const int persist = [] { const char* e = getenv("TSS_PW_PERSIST"); return e != nullptr ? atoi(e) : 1; }();
     const int64_t m_tiles = ceil_div64(M, BM);
-    if (persist && m_tiles < (1ll << 30)) {
+    const bool persist_wins = Nc / bn <= 2 && m_tiles >= 4 * (int64_t)tss_num_sms();
+    if ((persist == 2 || (persist == 1 && persist_wins)) && m_tiles < (1ll << 30)) {
         // persistent CTAs, double-buffered TMEM accumulator, statistics flushed once per CTA
         const int stages = 4;
         uint32_t tmem_cols = 32;
