@@ -39,6 +39,16 @@ def _setup(rank, world, port):
                             device_id=torch.device('cuda', rank))
 
 
+def _finish():
+    """Leave without the NCCL teardown handshake (dist.destroy_process_group can block for minutes when the ranks arrive
+    apart; bench.py does the same): results are on disk, every collective is behind us."""
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def _batch(seed, n=2, h=96, w=160, ignore=True):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(n, 3, h, w, generator=g)
@@ -113,7 +123,7 @@ def _train_worker(rank, world, port, out, dtype_name):
     if rank == 0:
         torch.save({'err': err, 'grads_identical': grads_identical, 'same_eager': same_eager, 'same_graph': same_graph,
                     'launched_in_backward': launched_in_backward, 'buckets': len(reducer.buckets), 'losses': losses}, out)
-    dist.destroy_process_group()
+    _finish()
 
 
 def _syncbn_worker(rank, world, port, out, dtype_name):
@@ -141,7 +151,7 @@ def _syncbn_worker(rank, world, port, out, dtype_name):
     head_err = float((head / world - head_ref).norm() / head_ref.norm())
     if rank == 0:
         torch.save({'err': err, 'rm_err': rm_err, 'head_err': head_err}, out)
-    dist.destroy_process_group()
+    _finish()
 
 
 def _eval_worker(rank, world, port, out, _dtype_name):
@@ -169,7 +179,7 @@ def _eval_worker(rank, world, port, out, _dtype_name):
         ref = single.compute(sync=False)
         torch.save({'equal': bool(torch.equal(total.cpu(), ref.cpu())), 'shard': (lo, hi), 'count': int(total.sum()),
                     'miou_equal': float(metrics_from_cm(total)['miou']) == float(metrics_from_cm(ref)['miou'])}, out)
-    dist.destroy_process_group()
+    _finish()
 
 
 def _run(worker, tmp_path, dtype_name='float32'):
@@ -180,7 +190,7 @@ def _run(worker, tmp_path, dtype_name='float32'):
     return torch.load(out)
 
 
-@pytest.mark.timeout(600)
+@pytest.mark.timeout(240)
 @pytest.mark.parametrize('dtype_name,bound', [('float32', 1e-4), ('bfloat16', 2e-2)])
 def test_nccl_bucketed_gradient_allreduce_world2(tmp_path, dtype_name, bound):
     r = _run(_train_worker, tmp_path, dtype_name)
@@ -194,7 +204,7 @@ def test_nccl_bucketed_gradient_allreduce_world2(tmp_path, dtype_name, bound):
     assert all(l == l for l in r['losses'])
 
 
-@pytest.mark.timeout(600)
+@pytest.mark.timeout(240)
 def test_nccl_syncbn_matches_single_process_on_the_concatenated_batch_world2(tmp_path):
     r = _run(_syncbn_worker, tmp_path)
     assert r['rm_err'] < 1e-5, r
@@ -202,7 +212,7 @@ def test_nccl_syncbn_matches_single_process_on_the_concatenated_batch_world2(tmp
     assert r['err'] < 1e-2, r
 
 
-@pytest.mark.timeout(600)
+@pytest.mark.timeout(240)
 def test_nccl_confusion_matrix_shards_sum_exactly_world2(tmp_path):
     r = _run(_eval_worker, tmp_path)
     assert r['equal'] and r['miou_equal'] and r['shard'] == (0, 4) and r['count'] > 0
