@@ -39,6 +39,11 @@ def _setup(rank, world, port):
                             device_id=torch.device('cuda', rank))
 
 
+def _say(rank, what):
+    """Progress to stderr (pytest -s shows it): the place of a hang is visible in the log of a killed run."""
+    print('[rank %d] %s' % (rank, what), file=sys.stderr, flush=True)
+
+
 def _finish():
     """Leave without the NCCL teardown handshake (dist.destroy_process_group can block for minutes when the ranks arrive
     apart; bench.py does the same): results are on disk, every collective is behind us."""
@@ -87,9 +92,17 @@ def _train_worker(rank, world, port, out, dtype_name):
         loss_fn(m(x), y).backward()
         singles.append(_flat_grads(m))
     want = sum(singles) / world
+    # yardstick: the same single-process gradient computed twice (fp32 atomics, then 45 BatchNorm layers of amplification)
+    m = _make(0, dtype)
+    x, y = _batch(100)
+    loss_fn(m(x), y).backward()
+    noise = float((_flat_grads(m) - singles[0]).norm() / singles[0].norm())
+    n_head = sum(p.numel() for p in m.classifier[3].parameters())       # the last parameters of the flat vector
 
+    _say(rank, 'single-process references done')
     model = _make(rank, dtype)                               # different init per rank: the broadcast must fix that
     broadcast_parameters(model)
+    _say(rank, 'parameters broadcast')
     opt = FlatAdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
     reducer = GradientAllReducer(opt, num_buckets=4).install()
     x, y = _batch(100 + rank)
@@ -98,8 +111,10 @@ def _train_worker(rank, world, port, out, dtype_name):
     launched_in_backward = sum(1 for b in reducer.buckets if b[4])
     reducer.finish()
     torch.cuda.synchronize()
+    _say(rank, 'eager step reduced')
     got = _flat_grads(model) * opt.grad_scale
     err = float((got - want).norm() / want.norm())
+    head_err = float((got[-n_head:] - want[-n_head:]).norm() / want[-n_head:].norm())
     # the all-reduced arena is bit-identical on both ranks (NCCL sums in one order for everybody)
     mine = opt.grad_arena.clone()
     both = [torch.empty_like(mine) for _ in range(world)]
@@ -114,14 +129,17 @@ def _train_worker(rank, world, port, out, dtype_name):
         return all(torch.equal(gathered[0], g) for g in gathered)
     same_eager = params_same()
     # the CUDA-graphed step (what bench.py replays at N > 1): NCCL all-reduces captured inside the graph
+    _say(rank, 'capturing the graphed step')
     g = GraphedTrainStep(model, opt, loss_fn, x, y)
+    _say(rank, 'captured')
     losses = []
     for _ in range(3):
         losses.append(float(g(x, y)))
     torch.cuda.synchronize()
     same_graph = params_same()
+    _say(rank, 'graph replays done')
     if rank == 0:
-        torch.save({'err': err, 'grads_identical': grads_identical, 'same_eager': same_eager, 'same_graph': same_graph,
+        torch.save({'err': err, 'head_err': head_err, 'noise': noise, 'grads_identical': grads_identical, 'same_eager': same_eager, 'same_graph': same_graph,
                     'launched_in_backward': launched_in_backward, 'buckets': len(reducer.buckets), 'losses': losses}, out)
     _finish()
 
@@ -194,9 +212,11 @@ def _run(worker, tmp_path, dtype_name='float32'):
 @pytest.mark.parametrize('dtype_name,bound', [('float32', 1e-4), ('bfloat16', 2e-2)])
 def test_nccl_bucketed_gradient_allreduce_world2(tmp_path, dtype_name, bound):
     r = _run(_train_worker, tmp_path, dtype_name)
-    # fp32: the only difference to the single-process gradients is the order of two fp32 additions per element;
-    # bf16: atomics inside the bf16 kernels make two runs of the same batch differ at rounding level
-    assert r['err'] < bound, r
+    # the classifier's gradient (short backward path) is held to the bound itself; the whole vector to the run-to-run
+    # distance of the single-process gradient (deep gradients of this net are reproducible to ~1e-2 in fp32, see
+    # tests/test_baseline_shapes_gpu.py), measured in the same process
+    assert r['head_err'] < bound, r
+    assert r['err'] < max(bound, 3 * r['noise']), r
     assert r['grads_identical'], 'ranks hold different all-reduced gradients'
     assert r['same_eager'], 'ranks diverged after one eager optimizer step'
     assert r['same_graph'], 'ranks diverged after graph-replayed optimizer steps'
