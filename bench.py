@@ -199,8 +199,10 @@ def kernel_family(op):
         return 'dw_dgrad_s2_quad_kernel (depthwise stride-2 dgrad)'
     if op.startswith('dwconv_'):
         return 'dw_tma_kernel (depthwise fwd + stride-1 dgrad)'
-    if op.startswith('bn_backward'):
-        return 'bn_bwd_reduce_kernel + bn_bwd_apply_kernel (BatchNorm backward)'
+    if op.startswith('bn_bwd_reduce'):
+        return 'bn_bwd_reduce_kernel (BatchNorm backward, stand-alone reduction)'
+    if op.startswith('bn_bwd_apply'):
+        return 'bn_bwd_apply_kernel (BatchNorm backward apply)'
     if op.startswith('bn_apply'):
         return 'bn_apply_kernel (BatchNorm forward apply)'
     return op
@@ -242,22 +244,25 @@ def kernel_table(device, runner=None):
     w = torch.randn(32, 3, 3, 3, device=device)
     st = torch.zeros(64, dtype=torch.float64, device=device)
     y2 = act(32, 2)
-    add('stem3x3s2_fwd', 1, 4 * 3 * px(1) + 2 * 32 * px(2), lambda: ops.stem_fwd(x, w, bf, stats=st))
-    add('stem3x3s2_wgrad', 1, 4 * 3 * px(1) + 2 * 32 * px(2), lambda: ops.stem_wgrad(x, y2, torch.zeros_like(w)))
-    # BatchNorm apply / backward on the largest activation (32 ch @ 1/2)
-    sc = torch.ones(32, device=device)
-    add('bn_apply 32ch@1/2', 1, 2 * 2 * 32 * px(2), lambda: ops.bn_apply(y2, sc, sc, relu=True))
-    # backward = reduce (reads dz, y) + apply (reads dz, y, writes dy); the ReLU mask is recomputed from y
-    g2 = act(32, 2)                   # the incoming gradient: a tensor of its own (dz and y are distinct streams)
-    add('bn_backward 32ch@1/2 (2 kernels)', 1, 2 * 32 * px(2) * (2 + 3), lambda: ops.bn_backward(g2, None, y2, sc, sc, sc, True, beta=sc))
-    # BatchNorm passes at the other resolutions (channel count, level, layers of that shape per step)
-    for C, div, cnt in [(32, 4, 1), (48, 4, 1), (48, 8, 1), (64, 8, 1), (128, 8, 7), (384, 8, 1), (384, 16, 6), (64, 16, 3),
-                        (384, 32, 1), (576, 32, 6), (96, 32, 3), (768, 32, 4), (128, 32, 4)]:
+    add('stem3x3s2_fwd (tcgen05)', 1, 4 * 3 * px(1) + 2 * 32 * px(2), lambda: ops.stem_fwd_tc(x, w, stats=st))
+    add('stem3x3s2_patches', 1, 4 * 3 * px(1) + 2 * 32 * px(2), lambda: ops.stem_patches(x))
+    patches = ops.stem_patches(x)
+    add('stem3x3s2_wgrad_from_patches', 1, 2 * 2 * 32 * px(2), lambda: ops.stem_wgrad_from_patches(patches, y2, torch.zeros_like(w)))
+    # BatchNorm passes: forward apply (reads y, writes z), backward reduce (reads dz, y), backward apply (reads dz, y, writes
+    # dy; the ReLU mask is recomputed from y) -- one row per kernel and shape (channels, level, layers of that shape per
+    # step; the reduce of 26 of the 44 layers is folded into the consumer's dgrad epilogue and does not appear here)
+    for C, div, cnt, cnt_red in [(32, 2, 1, 0), (32, 4, 1, 0), (48, 4, 1, 1), (48, 8, 1, 0), (64, 8, 1, 1), (128, 8, 7, 4), (384, 8, 1, 0),
+                                 (384, 16, 6, 0), (64, 16, 3, 3), (384, 32, 1, 0), (576, 32, 6, 0), (96, 32, 3, 3), (768, 32, 4, 0),
+                                 (128, 32, 4, 4)]:
         yb, gb = act(C, div), act(C, div)
         scb = torch.ones(C, device=device)
+        sums = torch.zeros(2 * C, device=device)
         add('bn_apply %dch@1/%d' % (C, div), cnt, 2 * 2 * C * px(div), lambda: ops.bn_apply(yb, scb, scb, relu=True))
-        add('bn_backward %dch@1/%d (2 kernels)' % (C, div), cnt, 2 * C * px(div) * (2 + 3),
-            lambda: ops.bn_backward(gb, None, yb, scb, scb, scb, True, beta=scb))
+        if cnt_red:
+            add('bn_bwd_reduce %dch@1/%d' % (C, div), cnt_red, 2 * 2 * C * px(div),
+                lambda: ops.bn_backward_reduce(gb, yb, scb, scb, scb, scb, True, sums))
+        add('bn_bwd_apply %dch@1/%d' % (C, div), cnt, 2 * 3 * C * px(div),
+            lambda: ops.bn_backward(gb, None, yb, scb, scb, scb, False, beta=scb, sums=sums, prereduced=True))
     # depthwise: every shape of the network (channels, input level, stride, dilation, layers of that shape)
     for C, div, s, d, cnt in [(32, 2, 2, 1, 1), (48, 4, 2, 1, 1), (384, 8, 2, 1, 1), (384, 16, 1, 1, 2), (384, 16, 2, 1, 1),
                               (576, 32, 1, 1, 3), (768, 32, 1, 1, 2), (128, 8, 1, 4, 1), (128, 8, 1, 1, 2)]:
@@ -601,36 +606,32 @@ def main():
         for r in rows:
             print('%-44s x%d  %8.3f ms  %8.1f MB  %7.0f GB/s  share %7.3f ms' % (
                 r['kernel'], r['launches_per_step'], r['ms'], r['bytes'] / 1e6, r['gbs'], r['share_ms']), file=sys.stderr)
-    # The dominant KERNEL of the step = the kernel function with the largest summed time over its launches
-    # (the ncu launch list under profiles/ ranks them the same way).  Its roofline figures are per launch,
-    # averaged over the step's launches of that kernel: algorithmic bytes per launch / time per launch.
+    # `roofline` = the single (kernel, shape) row with the largest share of the step (time per launch x launches of that
+    # shape per step), timed alone in this run: algorithmic bytes of ONE launch / its device time.  `kernel_families`
+    # = the same table summed per kernel function (what the ncu launch lists under profiles/ rank).
     fams = {}
     for r in rows:
-        f = fams.setdefault(kernel_family(r['kernel']), {'launches': 0, 'ms': 0.0, 'bytes': 0.0, 'ops': []})
+        f = fams.setdefault(kernel_family(r['kernel']), {'launches': 0, 'ms': 0.0, 'bytes': 0.0})
         f['launches'] += r['launches_per_step']
         f['ms'] += r['ms'] * r['launches_per_step']
         f['bytes'] += r['bytes'] * r['launches_per_step']
-        f['ops'].append(r['kernel'])
-    name, top = max(fams.items(), key=lambda kv: kv[1]['ms'])
-    traffic = None        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    families = [{'kernel': k, 'launches_per_step': v['launches'], 'ms_per_step': v['ms'], 'gbs': v['bytes'] / v['ms'] / 1e6,
+                 'frac': v['bytes'] / v['ms'] / 1e6 / peak} for k, v in sorted(fams.items(), key=lambda kv: -kv[1]['ms'])]
+    top = rows[0]
+    traffic = None        # dram__bytes_read.sum + dram__bytes_write.sum of that launch from the committed ncu --set full capture
     try:
         with open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')) as f:
             tr = json.load(f)
-        by_op = {r['kernel']: r['launches_per_step'] for r in rows}
-        have = [o for o in top['ops'] if o in tr]
-        if have:
-            traffic = sum(tr[o]['dram_bytes'] * by_op[o] for o in have) / sum(by_op[o] for o in have)
+        if top['kernel'] in tr:
+            traffic = tr[top['kernel']]['dram_bytes']
     except Exception:
         traffic = None
-    gbs = top['bytes'] / top['ms'] / 1e6
-    roofline = {'bound': 'hbm', 'kernel': name, 'achieved': gbs, 'peak': peak, 'unit': 'GB/s',
-                'frac': gbs / peak, 'traffic': traffic, 'peak_source': peak_src,
-                'launch_ms': top['ms'] / top['launches'], 'algorithmic_bytes': top['bytes'] / top['launches'],
-                'launches_per_step': top['launches'], 'share_of_step_ms': top['ms'],
-                'slowest_single_op': {'kernel': rows[0]['kernel'], 'ms': rows[0]['ms'], 'gbs': rows[0]['gbs']}}
+    roofline = {'bound': 'hbm', 'kernel': '%s [%s]' % (top['kernel'], kernel_family(top['kernel'])), 'achieved': top['gbs'], 'peak': peak,
+                'unit': 'GB/s', 'frac': top['gbs'] / peak, 'traffic': traffic, 'traffic_source': 'profiles/kernel_traffic.json (ncu --set full)',
+                'peak_source': peak_src, 'launch_ms': top['ms'], 'algorithmic_bytes': top['bytes'],
+                'launches_per_step': top['launches_per_step'], 'share_of_step_ms': top['share_ms'],
+                'timing': 'this run: the launch alone in a CUDA graph behind a 256 MB L2 flush, 10 replays between CUDA events, flush-only graph subtracted'}
 
-    if not args.headline_only:
-        extra['infer_bs1'] = infer_bs1(device)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         v, spt, cores = cpu_train_throughput(3, 1)
@@ -656,6 +657,7 @@ def main():
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': roofline,
+        'kernel_families': families[:8],
         'step_roofline': {'algorithmic_bytes': STEP_ALGORITHMIC_BYTES, 'source': 'SURVEY.md section 8d: 3 x 1849 MB + 595 MB per step',
                           'achieved': STEP_ALGORITHMIC_BYTES / (ms_total / args.steps) / 1e6, 'peak': peak, 'unit': 'GB/s',
                           'frac': STEP_ALGORITHMIC_BYTES / (ms_total / args.steps) / 1e6 / peak},
