@@ -120,7 +120,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint8_t* sB = smem + (size_t)stages * kABytes;
     uint64_t* bars = (uint64_t*)(sB + (size_t)stages * b_bytes);     // full[stages], empty[stages], tmem_full
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * stages + 1);
-    float* s_stat = (float*)(tmem_slot + 2);                          // [2][block_n]
+    float* s_stat = (float*)(tmem_slot + 2);                          // [4 epilogue warps][2][block_n]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
@@ -140,7 +140,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (stats != nullptr)
-        for (int i = threadIdx.x; i < 2 * block_n; i += kThreads) s_stat[i] = 0.f;
+        for (int i = threadIdx.x; i < 8 * block_n; i += kThreads) s_stat[i] = 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -194,9 +194,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 for (int i = 0; i < 16; ++i) { sm[i] = v[i]; sq[i] = v[i] * v[i]; }
                 const float s1 = warp_transpose_sum16(sm, lane);
                 const float s2 = warp_transpose_sum16(sq, lane);
-                if ((lane & 1) == 0) {
-                    atomicAdd(&s_stat[c + (lane >> 1)], s1);
-                    atomicAdd(&s_stat[block_n + c + (lane >> 1)], s2);
+                if ((lane & 1) == 0) {                     // this warp's private slice: plain read-modify-write, one lane per column
+                    float* mine = s_stat + q * 2 * block_n;   // (a shared-memory float atomicAdd is a CAS spin loop in SASS)
+                    mine[c + (lane >> 1)] += s1;
+                    mine[block_n + c + (lane >> 1)] += s2;
                 }
             }
             if (row_ok) {
@@ -237,8 +238,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     __syncthreads();
     if (stats != nullptr) {
         for (int i = threadIdx.x; i < block_n; i += kThreads) {
-            atomicAdd(stats + n0 + i, (double)s_stat[i]);
-            atomicAdd(stats + stats_stride + n0 + i, (double)s_stat[block_n + i]);
+            const float a = (s_stat[i] + s_stat[2 * block_n + i]) + (s_stat[4 * block_n + i] + s_stat[6 * block_n + i]);
+            const float b = (s_stat[block_n + i] + s_stat[3 * block_n + i]) + (s_stat[5 * block_n + i] + s_stat[7 * block_n + i]);
+            atomicAdd(stats + n0 + i, (double)a);
+            atomicAdd(stats + stats_stride + n0 + i, (double)b);
         }
     }
     if (warp == 1) {
@@ -270,7 +273,7 @@ pw_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     uint64_t* tmem_full = bars + 2 * stages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
-    float* s_stat = (float*)(tmem_slot + 2);                          // [2][block_n]
+    float* s_stat = (float*)(tmem_slot + 2);                          // [4 epilogue warps][2][block_n]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * block_n;
@@ -293,7 +296,7 @@ pw_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (stats != nullptr)
-        for (int i = threadIdx.x; i < 2 * block_n; i += kThreads) s_stat[i] = 0.f;
+        for (int i = threadIdx.x; i < 8 * block_n; i += kThreads) s_stat[i] = 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -361,9 +364,10 @@ pw_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     for (int i = 0; i < 16; ++i) { sm[i] = v[i]; sq[i] = v[i] * v[i]; }
                     const float s1 = warp_transpose_sum16(sm, lane);
                     const float s2 = warp_transpose_sum16(sq, lane);
-                    if ((lane & 1) == 0) {
-                        atomicAdd(&s_stat[c + (lane >> 1)], s1);
-                        atomicAdd(&s_stat[block_n + c + (lane >> 1)], s2);
+                    if ((lane & 1) == 0) {                 // this warp's private slice: plain read-modify-write
+                        float* mine = s_stat + q * 2 * block_n;
+                        mine[c + (lane >> 1)] += s1;
+                        mine[block_n + c + (lane >> 1)] += s2;
                     }
                 }
                 if (row_ok) {
@@ -408,8 +412,10 @@ pw_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     __syncthreads();
     if (stats != nullptr && my_tiles > 0) {
         for (int i = threadIdx.x; i < block_n; i += kThreads) {
-            atomicAdd(stats + n0 + i, (double)s_stat[i]);
-            atomicAdd(stats + stats_stride + n0 + i, (double)s_stat[block_n + i]);
+            const float a = (s_stat[i] + s_stat[2 * block_n + i]) + (s_stat[4 * block_n + i] + s_stat[6 * block_n + i]);
+            const float b = (s_stat[block_n + i] + s_stat[3 * block_n + i]) + (s_stat[5 * block_n + i] + s_stat[7 * block_n + i]);
+            atomicAdd(stats + n0 + i, (double)a);
+            atomicAdd(stats + stats_stride + n0 + i, (double)b);
         }
     }
     if (warp == 1) {
@@ -667,7 +673,7 @@ int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, 
         const int stages = 4;
         uint32_t tmem_cols = 32;
         while ((int)tmem_cols < 2 * bn) tmem_cols <<= 1;
-        const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 4) * 8 + 8 + 2 * bn * sizeof(float);
+        const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 4) * 8 + 8 + 8 * bn * sizeof(float);
         static bool attr_set_p = false;
         if (!attr_set_p) {
             TSS_CUDA(cudaFuncSetAttribute(pw_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -687,7 +693,7 @@ int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, 
     const int stages = num_kb < 4 ? num_kb : 4;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < bn) tmem_cols <<= 1;
-    const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 1) * 8 + 8 + 2 * bn * sizeof(float);
+    const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 1) * 8 + 8 + 8 * bn * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         TSS_CUDA(cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -50,8 +50,8 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint8_t* sB = smem + (size_t)stages * kABytes;
     uint64_t* bars = (uint64_t*)(sB + (size_t)stages * b_bytes);     // full[stages], empty[stages], tmem_full
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * stages + 1);
-    float* s_stat = (float*)(tmem_slot + 2);                          // [2][block_n]
-    float* s_const = s_stat + 2 * block_n;                            // [4][block_n]: mean, rstd, scale, shift
+    float* s_stat = (float*)(tmem_slot + 2);                          // [4 epilogue warps][2][block_n]
+    float* s_const = s_stat + 8 * block_n;                            // [4][block_n]: mean, rstd, scale, shift
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
@@ -69,7 +69,7 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 1) {
         tc_alloc(smem_u32(tmem_slot), tmem_cols);
     }
-    for (int i = threadIdx.x; i < 2 * block_n; i += kThreads) s_stat[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * block_n; i += kThreads) s_stat[i] = 0.f;
     pdl_wait();
     for (int i = threadIdx.x; i < block_n; i += kThreads) {           // per-column constants of the producer's BatchNorm
         const float mu = __ldg(mean + n0 + i), rs = __ldg(rstd + n0 + i);
@@ -146,9 +146,10 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 for (int i = 0; i < 16; ++i) sm[i] = v[i];
                 const float s1 = warp_transpose_sum16(sm, lane);
                 const float s2 = warp_transpose_sum16(gx, lane);
-                if ((lane & 1) == 0) {
-                    atomicAdd(&s_stat[c + (lane >> 1)], s1);
-                    atomicAdd(&s_stat[block_n + c + (lane >> 1)], s2);
+                if ((lane & 1) == 0) {                     // this warp's private slice: plain read-modify-write, one lane per column
+                    float* mine = s_stat + q * 2 * block_n;   // (a shared-memory float atomicAdd is a CAS spin loop in SASS)
+                    mine[c + (lane >> 1)] += s1;
+                    mine[block_n + c + (lane >> 1)] += s2;
                 }
             }
             if (row_ok) {
@@ -164,8 +165,9 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     __syncthreads();
     for (int i = threadIdx.x; i < block_n; i += kThreads) {
-        atomicAdd(sums + n0 + i, s_stat[i]);
-        atomicAdd(sums + sums_stride + n0 + i, s_stat[block_n + i]);
+        atomicAdd(sums + n0 + i, (s_stat[i] + s_stat[2 * block_n + i]) + (s_stat[4 * block_n + i] + s_stat[6 * block_n + i]));
+        atomicAdd(sums + sums_stride + n0 + i,
+                  (s_stat[block_n + i] + s_stat[3 * block_n + i]) + (s_stat[5 * block_n + i] + s_stat[7 * block_n + i]));
     }
     if (warp == 1) {
         __syncwarp();
@@ -221,7 +223,7 @@ extern "C" int tss_pwconv_dgrad_bnred(const void* dy, const void* wpT, void* g, 
     const int stages = num_kb < 4 ? num_kb : 4;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < bn) tmem_cols <<= 1;
-    const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 1) * 8 + 8 + 6 * bn * sizeof(float);
+    const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 1) * 8 + 8 + 12 * bn * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         TSS_CUDA(cudaFuncSetAttribute(pw_tc_bnred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
