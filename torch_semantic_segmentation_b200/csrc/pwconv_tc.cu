@@ -670,7 +670,10 @@ int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, 
     const bool persist_wins = Nc / bn <= 2 && m_tiles >= 4 * (int64_t)tss_num_sms();
     if ((persist == 2 || (persist == 1 && persist_wins)) && m_tiles < (1ll << 30)) {
         // persistent CTAs, double-buffered TMEM accumulator, statistics flushed once per CTA
-        const int stages = 4;
+        static const int stages_env = [] { const char* e = getenv("TSS_PW_STAGES"); return e ? atoi(e) : 0; }();
+        // the ring only has to cover the TMA latency across tiles: 2 stages when a tile is one k-block (4 CTAs of 48 KB
+        // per SM instead of 2 of 96 KB: twice the epilogue warps), 4 otherwise
+        const int stages = stages_env > 0 ? stages_env : (num_kb == 1 ? 2 : 4);
         uint32_t tmem_cols = 32;
         while ((int)tmem_cols < 2 * bn) tmem_cols <<= 1;
         const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 4) * 8 + 8 + 8 * bn * sizeof(float);
@@ -679,7 +682,8 @@ int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, 
             TSS_CUDA(cudaFuncSetAttribute(pw_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr_set_p = true;
         }
-        static const int per_sm = [] { const char* e = getenv("TSS_PW_CTAS_PER_SM"); return e ? atoi(e) : 2; }();
+        static const int per_sm_env = [] { const char* e = getenv("TSS_PW_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+        const int per_sm = per_sm_env > 0 ? per_sm_env : (stages <= 2 ? 4 : 2);
         const int n_tiles = Nc / bn;
         int64_t gx = ((int64_t)tss_num_sms() * per_sm + n_tiles - 1) / n_tiles;     // resident CTAs shared by the column tiles
         if (gx > m_tiles) gx = m_tiles;
