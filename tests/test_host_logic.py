@@ -671,7 +671,7 @@ def test_eval_operands_are_refreshed_in_place_after_training(fake_backend):
 def test_gate_defaults_and_environment_override(monkeypatch):
     """Only what has been measured on the GPU is on by default (gates.py); TSS_<NAME> overrides for A/B runs."""
     from torch_semantic_segmentation_b200 import gates
-    assert sorted(k for k, v in gates.DEFAULTS.items() if v) == ['CLASS_TC', 'DEFER_LOGITS', 'FUSE_BNRED', 'FUSE_BNRED_EXT', 'OWN_DROPOUT', 'SLOT_GRAPHS', 'STEM_TC', 'STEM_WGRAD_PATCHES']
+    assert sorted(k for k, v in gates.DEFAULTS.items() if v) == ['CLASS_TC', 'DEFER_LOGITS', 'FUSE_BNRED', 'FUSE_BNRED_EXT', 'FUSE_PPM_EVAL', 'OWN_DROPOUT', 'SLOT_GRAPHS', 'STEM_TC', 'STEM_WGRAD_PATCHES']
     monkeypatch.delenv('TSS_FUSE_PPM', raising=False)
     assert gates.gate('FUSE_PPM') is False and gates.gate('FUSE_BNRED') is True
     monkeypatch.setenv('TSS_FUSE_PPM', '1')

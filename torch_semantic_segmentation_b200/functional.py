@@ -157,11 +157,11 @@ def conv_forward(spec, x, weight, scale=None, shift=None, res=None, relu=False, 
 
 
 # Stem convolution on tcgen05 with a thread-built implicit-GEMM operand (csrc/stem_tc.cu) instead of the SIMT
-# kernel (864 FMAs per output pixel).  Built, checked on the SIMT emulation, not yet run on a B200: off unless
-# TSS_STEM_TC=1.
+# kernel (864 FMAs per output pixel).  On by default (B200: forward 154 -> 95 us).
 STEM_TC = gate('STEM_TC')
 # With the tensor-core stem: its BatchNorm-backward apply inside the weight gradient's operand producer -- the largest
-# activation of the net (32 channels at 1/2 resolution) is not rewritten as dy.  Off unless TSS_STEM_BWD_FUSED=1.
+# activation of the net (32 channels at 1/2 resolution) is not rewritten as dy.  Validated on the B200, slower in the step
+# (4.71 vs 4.52 ms): off unless TSS_STEM_BWD_FUSED=1.
 STEM_BWD_FUSED = gate('STEM_BWD_FUSED')
 
 # Training: fold the BatchNorm-backward reduction of a producer layer into the dgrad epilogue of its single
@@ -171,30 +171,34 @@ STEM_BWD_FUSED = gate('STEM_BWD_FUSED')
 FUSE_BNRED = gate('FUSE_BNRED')
 # Extended set: the stride-2 depthwise dgrad (its producers are the stem and the first expand conv: the largest
 # BatchNorm-backward instances) and two more single-consumer pairs at 1/8 resolution (fusion low-res branch,
-# classifier).  Built and CPU-checked, not yet validated on a B200: off unless TSS_FUSE_BNRED_EXT=1.
+# classifier).  On by default (B200: 4.58 -> 4.48 ms/step).
 FUSE_BNRED_EXT = gate('FUSE_BNRED_EXT')
 # BatchNorm-backward APPLY folded into the A-operand producer of the pointwise dgrad (csrc/pwconv_tc_bwd.cu):
 # dy is formed in registers and goes straight into the swizzled shared-memory tile of the tcgen05 GEMM (one
-# launch and one read of dy less per 1x1 layer without a residual).  Built and CPU-checked through the
-# emulated ABI, not yet validated on a B200: off unless TSS_FUSE_BNAPPLY=1.
+# launch and one read of dy less per 1x1 layer without a residual).  Validated on the B200, slower in the step (4.64 vs
+# 4.58 ms: thread-built operands lose against TMA-fed ones on the small maps): off unless TSS_FUSE_BNAPPLY=1.
 FUSE_BNAPPLY = gate('FUSE_BNAPPLY')
 # The same for the stride-1 depthwise layers whose dgrad already carries the producer's reduction
 # (csrc/dwconv_bwd_fused.cu: dz and y arrive as two TMA halo tiles, dy replaces dz in shared memory).
-# Off unless TSS_FUSE_BNAPPLY_DW=1.
+# Validated on the B200, no gain in the step: off unless TSS_FUSE_BNAPPLY_DW=1.
 FUSE_BNAPPLY_DW = gate('FUSE_BNAPPLY_DW')
 # The four pyramid-pooling branches as grouped launches (csrc/ppm.cu): 3 launches forward and 5 backward instead
-# of ~18 and ~26.  Same status: off unless TSS_FUSE_PPM=1.
+# of ~18 and ~26.  Validated on the B200 (except 2 samples per channel in fp32, an open tolerance item), no gain in the
+# training step: off unless TSS_FUSE_PPM=1.
 FUSE_PPM = gate('FUSE_PPM')
+# ... in eval mode only (folded BatchNorm): 7 launches less per inference forward (bs1 1024x2048: 2366 -> 2425 FPS on B200)
+FUSE_PPM_EVAL = gate('FUSE_PPM_EVAL')
 # BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu): one launch less per layer on the forward
-# chain (44 per step).  Same status: off unless TSS_FUSE_BNFIN=1.
+# chain (44 per step).  Validated on the B200, slower in the step (the fp64 statistics arithmetic in every CTA costs more
+# than the 44 tiny launches): off unless TSS_FUSE_BNFIN=1.
 FUSE_BNFIN = gate('FUSE_BNFIN')
 # Inside a bottleneck, conv1's BatchNorm + ReLU applied by conv2 (depthwise) while it reads its input tile
 # (csrc/dwconv_bnin.cu): the expanded activation is never materialised, conv1's apply pass disappears.
-# Off unless TSS_FUSE_BNIN=1.
+# Kernels validated on the B200; CUDA-graph capture of the whole step still fails with them: off unless TSS_FUSE_BNIN=1.
 FUSE_BNIN = gate('FUSE_BNIN')
 # The same hand-over from conv2 (depthwise) to conv3 (tensor-core pointwise, csrc/pwconv_tc_fwd_bnin.cu): the activated
 # tensor is written once by the GEMM's operand producer (the weight gradient needs it) and never read in the forward
-# pass.  Off unless TSS_FUSE_BNIN_PW=1.
+# pass.  Same status as FUSE_BNIN: off unless TSS_FUSE_BNIN_PW=1.
 FUSE_BNIN_PW = gate('FUSE_BNIN_PW')
 
 
@@ -612,7 +616,7 @@ class PPMBranches(torch.autograd.Function):
 
 
 # nn.Dropout of the classifiers on the library's own kernel (csrc/dropout.cu: counter-based mask, regenerated in
-# the backward pass, no mask tensor, no ATen kernels on the path).  Off unless TSS_OWN_DROPOUT=1 (not yet run on a B200).
+# the backward pass, no mask tensor, no ATen kernels on the path).  On by default (B200: 28.8 -> 14.1 us per pass).
 OWN_DROPOUT = gate('OWN_DROPOUT')
 
 
@@ -739,8 +743,8 @@ def attach_head(logits, scores):
 
 # Training with this package's losses: the full-resolution logits (269 MB of bf16 per 12 x 768 x 768 step) are only
 # ever consumed by the fused head, which works from the 1/8 class scores.  With defer_logits set on the model (the
-# trainer does it when the loss declares ``accepts_deferred_logits``, and only under TSS_DEFER_LOGITS=1 until the
-# path has run on a B200) the training forward returns this handle instead of launching the x8 up-sampling;
+# trainer does it when the loss declares ``accepts_deferred_logits``; gate DEFER_LOGITS, on by default) the training
+# forward returns this handle instead of launching the x8 up-sampling;
 # anything else that wants the tensor calls ``materialize()``.
 DEFER_LOGITS = gate('DEFER_LOGITS')
 

@@ -16,7 +16,8 @@ DEFAULTS = {
     'FUSE_BNFIN': False,        # BatchNorm finalize inside the apply kernel
     'FUSE_BNIN': False,         # a block's BatchNorm applied by the depthwise conv that reads it
     'FUSE_BNIN_PW': False,      # ... by the tensor-core pointwise conv that reads it
-    'FUSE_PPM': False,          # pyramid-pooling branches as grouped launches
+    'FUSE_PPM': False,          # pyramid-pooling branches as grouped launches (training: 4.60 vs 4.58 ms/step, not kept)
+    'FUSE_PPM_EVAL': True,      # ... in eval mode (folded BatchNorm): bs1 inference 2366 -> 2425 FPS
     'STEM_TC': True,            # stem convolution + weight gradient on tcgen05 (r2: fwd 154 -> 95 us, wgrad 246 -> 202 us; 4.58 -> 4.52 ms/step)
     'STEM_BWD_FUSED': False,    # stem BatchNorm-backward apply inside its tensor-core weight gradient
     'DEFER_LOGITS': True,       # training forward without the unused full-resolution logits (r2: 4.58 -> 4.53 ms/step)

@@ -184,7 +184,7 @@ class PyramidPoolingModule(nn.Module):
     def _grouped_eval(self, x):
         """Eval mode with folded BatchNorm: pool -> all branches -> concat in three launches (instead of ten)."""
         blocks = [p[1] for p in self.pyramids]
-        if not Fn.FUSE_PPM or self.training or torch.is_grad_enabled() or x.dtype != blocks[0].compute_dtype:
+        if not (Fn.FUSE_PPM or Fn.FUSE_PPM_EVAL) or self.training or torch.is_grad_enabled() or x.dtype != blocks[0].compute_dtype:
             return None
         if any(not b[1].track_running_stats or b[0].weight.device != x.device for b in blocks):
             return None
