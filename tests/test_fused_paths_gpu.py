@@ -356,11 +356,11 @@ def test_stem_on_tensor_cores_matches_the_simt_stem(N, H, W):
 def test_grouped_pyramid_pooling_eval_matches_layer_by_layer(dtype):
     from torch_semantic_segmentation_b200 import functional as Fn
     from torch_semantic_segmentation_b200.models import fastscnn
-    keep = Fn.FUSE_PPM
+    keep = (Fn.FUSE_PPM, Fn.FUSE_PPM_EVAL)
     outs = {}
     try:
         for flag in (False, True):
-            Fn.FUSE_PPM = flag
+            Fn.FUSE_PPM = Fn.FUSE_PPM_EVAL = flag
             torch.manual_seed(0)
             model = fastscnn(3, 19).cuda().set_compute_dtype(dtype).eval()
             g = torch.Generator().manual_seed(3)
@@ -370,7 +370,7 @@ def test_grouped_pyramid_pooling_eval_matches_layer_by_layer(dtype):
                 outs[flag] = (model(x).float(), _lib.launch_count() - before)
             torch.cuda.synchronize()
     finally:
-        Fn.FUSE_PPM = keep
+        Fn.FUSE_PPM, Fn.FUSE_PPM_EVAL = keep
     assert rel(outs[True][0], outs[False][0]) < (1e-4 if dtype == torch.float32 else 2e-2)
     assert outs[True][1] <= outs[False][1] - 7
 
