@@ -119,19 +119,26 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int row_in_tile = q * 32 + lane;
         const int64_t row = m0 + row_in_tile;
         const bool row_ok = row < M;
+        // this thread's row of the producer's raw output (block_n <= 64 columns = 8 x 16 bytes) is requested NOW, while the
+        // TMA / MMA main loop is still running, instead of chunk by chunk after the accumulator is complete
+        uint4 ypre[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            ypre[j] = make_uint4(0, 0, 0, 0);              // rows >= M: dz is an exact zero (TMA zero fill)
+            if (row_ok && j * 8 < block_n) ypre[j] = __ldg(reinterpret_cast<const uint4*>(yp + row * ldyp + n0 + j * 8));
+        }
         mbar_wait(smem_u32(bars + 2 * stages), 0);
         tc_fence_after();
-        for (int c = 0; c < block_n; c += 16) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c = cc * 16;
+            if (c >= block_n) break;
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
             const int col = n0 + c;
             float y0[8], y1[8];
-            if (row_ok) {
-                load8(yp + row * ldyp + col, y0);
-                load8(yp + row * ldyp + col + 8, y1);
-            } else {                                       // rows >= M: dz is an exact zero (TMA zero fill)
-                zero8(y0); zero8(y1);
-            }
+            unpack8(ypre[2 * cc], y0);
+            unpack8(ypre[2 * cc + 1], y1);
             float gx[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
