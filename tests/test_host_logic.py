@@ -181,6 +181,26 @@ def test_contextnet_eval_forward_matches_oracle(fake_backend, shape):
     assert rel(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize('variant', ['contextnet12', 'contextnet18'])
+def test_contextnet_12_and_18_match_oracle(fake_backend, variant):
+    """The other two factories of contextnet.py:13-25 (context branch on the input shrunk by 2 / 8): eval forward and one
+    training step's loss against the oracle (pinned to the live reference by tests/test_oracle.py)."""
+    from torch_semantic_segmentation_b200.models import contextnet as cn
+    torch.manual_seed(0)
+    model = _no_dropout(getattr(cn, variant)(3, 19))
+    sd0 = init_state('contextnet14', 0)               # same layers, same construction order: same random init
+    assert all(torch.equal(model.state_dict()[k], sd0[k]) for k in sd0)
+    x = torch.randn(2, 3, 128, 192, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        out = model.eval()(x)
+    ref = model_forward(variant, sd0, x, False)
+    assert out.shape == ref.shape == (2, 19, 128, 192) and rel(out, ref) < 1e-5
+    y = torch.randint(0, 19, (2, 128, 192), generator=torch.Generator().manual_seed(7))
+    loss = CrossEntropyLoss(ignore_index=255)(model.train()(x), y)
+    ref_loss, _, _ = loss_and_grads(variant, split_state(sd0), x, y, dropout_mask=1.0)
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+
+
 def test_contextnet_train_step_matches_oracle(fake_backend):
     from torch_semantic_segmentation_b200.models.contextnet import contextnet14
     torch.manual_seed(0)

@@ -213,6 +213,31 @@ def test_contextnet_eval_forward_matches_golden_and_oracle():
     assert low.dtype == torch.bfloat16 and rel(low, ref) < 2e-2
 
 
+@pytest.mark.parametrize('variant', ['contextnet12', 'contextnet18'])
+def test_contextnet_12_and_18_on_the_gpu(variant):
+    """contextnet12 / contextnet18 (contextnet.py:13-25): eval forward fp32 + bf16 and a training step's loss, vs the oracle."""
+    from torch_semantic_segmentation_b200.models import contextnet as cn
+    torch.manual_seed(0)
+    model = getattr(cn, variant)(3, 19).cuda()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    sd0 = init_state('contextnet14', 0)
+    x = torch.randn(2, 3, 128, 192, generator=torch.Generator().manual_seed(6))
+    ref = model_forward(variant, sd0, x, False)
+    with torch.no_grad():
+        out = model.eval()(x.cuda())
+        low = model.set_compute_dtype(torch.bfloat16).eval()(x.cuda())
+    assert out.shape == ref.shape and rel(out, ref) < 1e-4 and rel(low, ref) < 2e-2
+    y = torch.randint(0, 19, (2, 128, 192), generator=torch.Generator().manual_seed(7))
+    model.set_compute_dtype(torch.float32).train()
+    loss = CrossEntropyLoss(ignore_index=255)(model(x.cuda()), y.cuda())
+    loss.backward()
+    ref_loss, _, ref_grads = loss_and_grads(variant, split_state(sd0), x, y, dropout_mask=1.0)
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+    assert rel(dict(model.named_parameters())['classifier.5.weight'].grad, ref_grads['classifier.5.weight']) < 1e-4
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_contextnet_train_forward_backward(dtype):
     model = make_contextnet(dtype).train()

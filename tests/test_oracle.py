@@ -117,3 +117,22 @@ def test_oracle_against_live_reference(arch):
     model.eval()
     with torch.no_grad():
         torch.testing.assert_close(model_forward(arch, sd, x, False), model(x), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present on this box')
+@pytest.mark.parametrize('variant', ['contextnet12', 'contextnet18'])
+def test_oracle_contextnet_variants_against_live_reference(variant):
+    """contextnet12 / contextnet18 (contextnet.py:13-25) share ContextNet-14's layers and differ in the factor by which
+    the context branch's input is shrunk (2 / 8): the oracle's scale argument against the reference's own factories."""
+    sys.path.insert(0, REF)
+    try:
+        from torch_semantic_segmentation.models import contextnet as ref_cn
+    finally:
+        sys.path.remove(REF)
+    torch.manual_seed(4)
+    model = getattr(ref_cn, variant)(3, 19).eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = torch.randn(2, 3, 128, 192)
+    with torch.no_grad():
+        torch.testing.assert_close(model_forward(variant, sd, x, False), model(x), rtol=1e-5, atol=1e-6)
+
