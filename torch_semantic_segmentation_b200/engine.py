@@ -291,7 +291,10 @@ class GraphedTrainStep:
         from . import _lib
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
+        # capture on the SAME side stream the warm-up ran on: autograd remembers the stream on which a parameter's
+        # AccumulateGrad first ran and makes the end of every later backward wait for it -- a foreign, non-capturing
+        # stream at that point invalidates the capture ("dependency created on uncaptured work in another stream")
+        with torch.cuda.graph(self.graph, stream=side):
             self.loss = body()
         self.kernels_per_step = _lib.launch_count() - before   # libtss_b200 kernel nodes in the graph
         self.warmup_steps = warmup            # steps the optimizer really took on the example batch (capture runs nothing)
@@ -344,7 +347,7 @@ class GraphedEvalStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.out = body()
         torch.cuda.synchronize(dev)
         cm.cm.copy_(keep)                 # warm-up and capture did not count

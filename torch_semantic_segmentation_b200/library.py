@@ -73,6 +73,7 @@ def _nothing(*args):
 
 
 OPS = {}        # C name -> (operator, parameter names in schema order)
+_CAPTURE_CHECK = __import__('os').environ.get('TSS_CAPTURE_CHECK') == '1'
 
 
 def _register_launchers():
@@ -105,6 +106,13 @@ def dispatch(name, kwargs):
             v = torch.tensor(v.values, dtype=HOST_ARRAYS[pname])
         args.append(v)
     op(*args)
+    if _CAPTURE_CHECK:
+        # debugging aid (TSS_CAPTURE_CHECK=1): a CUDA-graph capture that an operation has invalidated makes this query
+        # raise, so the traceback names the first library call after the offending one
+        try:
+            torch.cuda.is_current_stream_capturing()
+        except Exception as exc:
+            raise RuntimeError('CUDA graph capture invalidated at or before %s' % name) from exc
     return 0
 
 
