@@ -697,3 +697,30 @@ def test_gate_defaults_and_environment_override(monkeypatch):
     monkeypatch.setenv('TSS_FUSE_PPM', '1')
     monkeypatch.setenv('TSS_FUSE_BNRED', '0')
     assert gates.gate('FUSE_PPM') is True and gates.gate('FUSE_BNRED') is False
+
+
+def test_flat_adamw_state_dict_round_trip(fake_backend):
+    """the moments and the step counter live outside Optimizer.state; a resumed run must continue with the
+    same bias correction.  Two optimisers, one checkpointed and reloaded after 2 steps, end with identical parameters."""
+    from torch_semantic_segmentation_b200.optim import FlatAdamW
+    x, y = train_batch('fastscnn')
+
+    def run(resume):
+        torch.manual_seed(0)
+        model = _no_dropout(fastscnn(3, 19)).train()
+        opt = FlatAdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
+        loss_fn = CrossEntropyLoss(ignore_index=255)
+        for i in range(4):
+            if resume and i == 2:
+                ckpt = (model.state_dict(), opt.state_dict())
+                torch.manual_seed(0)
+                model = _no_dropout(fastscnn(3, 19)).train()
+                opt = FlatAdamW(model.parameters(), lr=5e-3, weight_decay=0.0)      # other hyper-parameters: must be restored
+                model.load_state_dict(ckpt[0])
+                opt.load_state_dict(ckpt[1])
+                assert opt.param_groups[0]['lr'] == 1e-3 and opt.step_count == 2
+            opt.zero_grad()
+            loss_fn(model(x), y).backward()
+            opt.step()
+        return opt.param_arena.clone()
+    assert torch.equal(run(False), run(True))

@@ -57,9 +57,12 @@ class FlatAdamW(torch.optim.Optimizer):
         g0 = self.param_groups[0]
         self.hyper = torch.tensor([g0['lr'], g0['betas'][0], g0['betas'][1], g0['eps'], g0['weight_decay'],
                                    0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
-        self._host = torch.empty(5, dtype=torch.float32)
+        # two pinned staging buffers used in turn: the host never rewrites the one an in-flight copy may still read
+        self._hosts = [torch.empty(5, dtype=torch.float32) for _ in range(2)]
         if dev.type == 'cuda':
-            self._host = self._host.pin_memory()
+            self._hosts = [h.pin_memory() for h in self._hosts]
+        self._host = self._hosts[0]
+        self._host_turn = 0
         self.grad_scale = 1.0          # e.g. 1/world_size after a SUM all-reduce
         self._offsets = {id(p): off for p, off, _ in self.slots}
         self._packs = {}               # id(param) -> (wp, wpT): bf16 TMA/UMMA operands of the pointwise convs
@@ -96,16 +99,28 @@ class FlatAdamW(torch.optim.Optimizer):
         wgrad_lane.join(self.grad_arena.device if self.grad_arena.is_cuda else None)
         self.grad_arena.zero_()
 
-    def write_host_hyper(self):
-        """param_groups -> the pinned staging buffer of the hyper-parameters.  Host work only.  A captured
-        ``step()`` replays the pinned->device copy, so a CUDA-graph replay picks up whatever this wrote last: call it
-        before every replay (engine.GraphedTrainStep does) and learning-rate schedules keep working under graphs."""
+    def _fill(self, buf):
         g = self.param_groups[0]
-        self._host[0], self._host[1], self._host[2] = g['lr'], g['betas'][0], g['betas'][1]
-        self._host[3], self._host[4] = g['eps'], g['weight_decay']
+        buf[0], buf[1], buf[2] = g['lr'], g['betas'][0], g['betas'][1]
+        buf[3], buf[4] = g['eps'], g['weight_decay']
+
+    def write_host_hyper(self):
+        """param_groups -> the pinned staging buffers of the hyper-parameters.  Host work only.  A captured
+        ``step()`` replays the pinned->device copy from whichever buffer was current at capture time, so a CUDA-graph
+        replay picks up whatever this wrote last: call it before every replay (engine.GraphedTrainStep does) and
+        learning-rate schedules keep working under graphs.  (With ``lazy_loss`` the host runs one step ahead of the device:
+        the copy at the end of step i may then already see the values written for step i+1.)"""
+        for buf in self._hosts:
+            self._fill(buf)
 
     def _refresh_hyper(self):
-        self.write_host_hyper()
+        capturing = self.hyper.is_cuda and torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            # eager mode: the two staging buffers take turns, so that the host never rewrites the one an in-flight
+            # asynchronous copy of the previous step may still be reading
+            self._host_turn ^= 1
+            self._host = self._hosts[self._host_turn]
+        self._fill(self._host)
         self.hyper[:5].copy_(self._host, non_blocking=True)
 
     @torch.no_grad()
@@ -128,3 +143,24 @@ class FlatAdamW(torch.optim.Optimizer):
     @property
     def step_count(self):
         return int(self.hyper[5].item())
+
+    # torch.optim.Optimizer keeps per-parameter state in ``self.state``; here the moments are two flat arenas and the
+    # step counter lives on the device, so checkpointing (ModelCheckpoint in the reference's scripts saves
+    # ``optimizer.state_dict()``) has to carry them explicitly.
+    def state_dict(self):
+        sd = super().state_dict()
+        sd['flat_adamw'] = {'exp_avg': self.exp_avg.detach().cpu().clone(), 'exp_avg_sq': self.exp_avg_sq.detach().cpu().clone(),
+                            'counters': self.hyper[5:].detach().cpu().clone(), 'numel': self.numel}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat = state_dict.pop('flat_adamw', None)
+        super().load_state_dict(state_dict)
+        if flat is not None:
+            if int(flat['numel']) != self.numel:
+                raise ValueError('FlatAdamW.load_state_dict: arena of %d elements, checkpoint has %d' % (self.numel, int(flat['numel'])))
+            self.exp_avg.copy_(flat['exp_avg'])
+            self.exp_avg_sq.copy_(flat['exp_avg_sq'])
+            self.hyper[5:].copy_(flat['counters'])
+        self.write_host_hyper()
