@@ -16,6 +16,16 @@ build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/tma.cuh $(CSRC)/augment_math.
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
 
+# Instrumented copy for tools/trace_kernels.py (TSS_MARK timestamps inside the kernels); never loaded by the product.
+TRACE_LIB := torch_semantic_segmentation_b200/libtss_b200_trace.so
+TRACE_OBJS := $(patsubst $(CSRC)/%.cu,build_trace/%.o,$(SRCS))
+build_trace/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/tma.cuh $(CSRC)/augment_math.h $(CSRC)/tc_ptx.cuh include/tss_b200.h
+	@mkdir -p build_trace
+	$(NVCC) $(NVCCFLAGS) -DTSS_TRACE -c $< -o $@
+$(TRACE_LIB): $(TRACE_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(TRACE_OBJS) -cudart static
+trace: $(TRACE_LIB)
+
 clean:
-	rm -rf build $(LIB)
-.PHONY: all clean
+	rm -rf build build_trace $(LIB) $(TRACE_LIB)
+.PHONY: all clean trace

@@ -49,6 +49,9 @@ uint64_t tss_launch_count(void);
 /* Programmatic dependent launch between consecutive kernels of a stream / graph (on by default;
  * env TSS_PDL=0 or tss_set_pdl(0) selects plain serialized launches).  Process-wide. */
 int tss_set_pdl(int enabled);
+/* Debugging aid: cudaStreamIsCapturing of a stream handle: 0 = not capturing, 1 = capture active, 2 = capture
+ * invalidated by an earlier call, < 0 = -(cudaError_t).  Launches nothing. */
+int64_t tss_capture_status(int64_t stream_handle);
 
 /* ---- depthwise 3x3 convolution, padding == dilation ("same" for stride 1) --------------
  * replaces nn.Conv2d(C, C, 3, stride, padding=dilation, dilation, groups=C, bias=False)

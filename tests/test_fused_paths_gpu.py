@@ -278,9 +278,9 @@ def test_training_step_with_finalize_folded_into_apply_matches_default():
     from torch_semantic_segmentation_b200.models import fastscnn
     x, y = train_batch('fastscnn')
     out = {}
-    keep = Fn.FUSE_BNFIN
+    keep = Fn.FUSE_BNFIN, Fn.FUSE_BNIN
     for flag in (False, True):
-        Fn.FUSE_BNFIN = flag
+        Fn.FUSE_BNFIN, Fn.FUSE_BNIN = flag, False               # (the launch count below: no apply pass handed to a consumer)
         try:
             torch.manual_seed(0)
             model = fastscnn(3, 19).cuda().train()
@@ -297,7 +297,7 @@ def test_training_step_with_finalize_folded_into_apply_matches_default():
             out[flag] = (float(loss), logits.detach(), model.classifier[3].weight.grad.clone(),
                          model.downsample[0][1].running_var.clone(), _lib.launch_count() - before)
         finally:
-            Fn.FUSE_BNFIN = keep
+            Fn.FUSE_BNFIN, Fn.FUSE_BNIN = keep
     # fp32 mode: both paths do the same arithmetic (fp64 statistics -> fp32 scale / shift), equal to fp32 rounding
     assert abs(out[True][0] - out[False][0]) < 1e-4 * abs(out[False][0])
     assert rel(out[True][1], out[False][1]) < 1e-4 and rel(out[True][2], out[False][2]) < 1e-3

@@ -242,6 +242,7 @@ def test_gated_backward_fusions_are_plumbing_equivalent(fake_backend):
     g = torch.Generator().manual_seed(1)
     x, y = torch.randn(2, 3, 64, 64, generator=g), torch.randint(0, 19, (2, 64, 64), generator=g)
     keep = Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY, Fn.FUSE_BNFIN, Fn.FUSE_BNAPPLY_DW
+    keep_bnin, Fn.FUSE_BNIN = Fn.FUSE_BNIN, False      # the launch counts below are those of the chain without hand-overs
     runs = {}
     try:
         for ext, fused in ((False, False), (True, False), (False, True), (True, True), ('fin', False), ('dw', False)):
@@ -255,6 +256,7 @@ def test_gated_backward_fusions_are_plumbing_equivalent(fake_backend):
             runs[ext, fused] = (torch.cat([p.grad.reshape(-1) for p in model.parameters()]), dict(calls))
     finally:
         Fn.FUSE_BNRED_EXT, Fn.FUSE_BNAPPLY, Fn.FUSE_BNFIN, Fn.FUSE_BNAPPLY_DW = keep
+        Fn.FUSE_BNIN = keep_bnin
     base, base_calls = runs[False, False]
     # BatchNorm-backward apply folded into the stride-1 depthwise dgrads that carry a fused reduction
     assert rel(runs['dw', False][0], base) < 1e-6
@@ -487,9 +489,45 @@ def test_experimental_kernel_tool_dry_run():
     assert len(rows) >= 30 and not [r for r in rows if 'error' in r], [r for r in rows if 'error' in r]
 
 
+def test_forward_hooks_see_activated_outputs_with_deferred_batchnorm(fake_backend):
+    """A forward hook on a block whose BatchNorm apply pass would be handed over to its consumer (functional.FUSE_BNIN)
+    keeps the block on the ordinary path: the hook sees BatchNorm + ReLU output, as it does on the reference."""
+    from torch_semantic_segmentation_b200 import functional as Fn
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 64, 96, generator=g)
+    keep, Fn.FUSE_BNIN = Fn.FUSE_BNIN, True
+    try:
+        torch.manual_seed(0)
+        model = _no_dropout(fastscnn(3, 19)).train()
+        seen = {}
+        taps = {'stem': model.downsample[0], 'conv1': model.features[0][0].conv1}
+        handles = [m.register_forward_hook(lambda mod, inp, out, k=k: seen.__setitem__(k, out.detach().clone())) for k, m in taps.items()]
+        calls = {}
+        inner = fake_backend.call
+
+        def counting(name, kwargs):
+            calls[name] = calls.get(name, 0) + 1
+            return inner(name, kwargs)
+        fake_backend.call = counting
+        hooked = model(x).detach()
+        n_hooked = calls.get('tss_dwconv3x3_fwd_bnin', 0)
+        for h in handles:
+            h.remove()
+        calls.clear()
+        torch.manual_seed(0)
+        plain = _no_dropout(fastscnn(3, 19)).train()
+        out = plain(x).detach()
+    finally:
+        Fn.FUSE_BNIN = keep
+    assert all(float(v.min()) >= 0.0 for v in seen.values())                   # ReLU outputs, not raw convolutions
+    assert all(abs(float(v.float().mean())) > 1e-3 for v in seen.values())
+    assert calls['tss_dwconv3x3_fwd_bnin'] == n_hooked + 2                       # exactly the two observed blocks opted out
+    assert rel(hooked, out) < 1e-5
+
+
 @pytest.mark.parametrize('arch', ['fastscnn', 'contextnet14'])
 def test_bottleneck_without_the_expanded_activation(fake_backend, arch):
-    """functional.FUSE_BNIN (off by default): conv1's BatchNorm + ReLU applied by the depthwise conv2 while it reads its
+    """functional.FUSE_BNIN: conv1's BatchNorm + ReLU applied by the depthwise conv2 while it reads its
     input; same forward and gradients, one bn_apply less per bottleneck, no other change in the call list."""
     from torch_semantic_segmentation_b200 import functional as Fn
     from torch_semantic_segmentation_b200.models.contextnet import contextnet14
@@ -691,7 +729,7 @@ def test_eval_operands_are_refreshed_in_place_after_training(fake_backend):
 def test_gate_defaults_and_environment_override(monkeypatch):
     """Only what has been measured on the GPU is on by default (gates.py); TSS_<NAME> overrides for A/B runs."""
     from torch_semantic_segmentation_b200 import gates
-    assert sorted(k for k, v in gates.DEFAULTS.items() if v) == ['CLASS_TC', 'DEFER_LOGITS', 'FUSE_BNRED', 'FUSE_BNRED_EXT', 'FUSE_PPM_EVAL', 'OWN_DROPOUT', 'SLOT_GRAPHS', 'STEM_TC', 'STEM_WGRAD_PATCHES']
+    assert sorted(k for k, v in gates.DEFAULTS.items() if v) == ['CLASS_TC', 'DEFER_LOGITS', 'FUSE_BNIN', 'FUSE_BNRED', 'FUSE_BNRED_EXT', 'FUSE_PPM_EVAL', 'OWN_DROPOUT', 'SLOT_GRAPHS', 'STEM_TC', 'STEM_WGRAD_PATCHES']
     monkeypatch.delenv('TSS_FUSE_PPM', raising=False)
     assert gates.gate('FUSE_PPM') is False and gates.gate('FUSE_BNRED') is True
     monkeypatch.setenv('TSS_FUSE_PPM', '1')

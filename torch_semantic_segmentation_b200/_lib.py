@@ -17,7 +17,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtss_b200.so')
+LIB_PATH = os.environ.get('TSS_LIB') or os.path.join(_HERE, 'libtss_b200.so')      # TSS_LIB: tools/trace_kernels.py
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'tss_b200.h')
 
 TSS_F32, TSS_BF16 = 0, 1

@@ -70,6 +70,36 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
+// ---------------------------------------------------------------- in-kernel timeline ----
+// `make trace` builds libtss_b200_trace.so with -DTSS_TRACE: TSS_MARK(slot) then stores %globaltimer (ns) of the calling
+// thread into trace[cta * 16 + slot] (tools/trace_kernels.py reads the buffer and prints where a CTA's time goes).
+// The product library is built without it: the marks compile to nothing.
+#ifdef TSS_TRACE
+#define TSS_TRACE_SLOTS 16
+#define TSS_TRACE_MAX_CTAS 65536
+unsigned long long* tss_trace_buffer_host();                 // api.cu (set by tss_trace_set)
+static __device__ unsigned long long* g_tss_trace;           // one copy per translation unit, bound by tss_launch
+__device__ __forceinline__ void tss_trace_mark(int slot) {
+    unsigned long long* buf = g_tss_trace;
+    if (buf == nullptr) return;
+    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (cta >= TSS_TRACE_MAX_CTAS) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    buf[(size_t)cta * TSS_TRACE_SLOTS + slot] = t;
+    if (slot == 0) {
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        buf[(size_t)cta * TSS_TRACE_SLOTS + TSS_TRACE_SLOTS - 1] = sm;
+    }
+}
+#define TSS_MARK(slot) do { if (threadIdx.x == 0) tss_trace_mark(slot); } while (0)
+#define TSS_MARK_IF(cond, slot) do { if (cond) tss_trace_mark(slot); } while (0)
+#else
+#define TSS_MARK(slot) ((void)0)
+#define TSS_MARK_IF(cond, slot) ((void)0)
+#endif
+
 // Dynamic shared memory of the CTA.  (tests/simt_emu/ redefines this for host builds of the plain SIMT kernels.)
 #ifndef TSS_DYN_SMEM
 #define TSS_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
@@ -78,6 +108,16 @@ __device__ __forceinline__ void pdl_wait() {
 template <typename... KArgs, typename... Args>
 inline cudaError_t tss_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {
+#ifdef TSS_TRACE
+    {   // bind this translation unit's trace pointer (synchronous copy: set the buffer and warm up outside graph capture)
+        static unsigned long long* bound = reinterpret_cast<unsigned long long*>(-1);
+        unsigned long long* want = tss_trace_buffer_host();
+        if (want != bound) {
+            cudaMemcpyToSymbol(g_tss_trace, &want, sizeof(want));
+            bound = want;
+        }
+    }
+#endif
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;

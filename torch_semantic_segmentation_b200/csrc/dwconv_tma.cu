@@ -175,13 +175,16 @@ dw_tma_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const float* _
     uint64_t* bars = (uint64_t*)(smem + 2 * (size_t)stage_bytes);
     float* part = (float*)(bars + 2);          // [2][TW][CB]: every thread's running statistics (its private 16 slots)
     const int cb0 = blockIdx.y * CB;
+    TSS_MARK(0);
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(bars), 1);
         mbar_init(smem_u32(bars + 1), 1);
         mbar_fence_init();
     }
     __syncthreads();
+    TSS_MARK(1);
     pdl_wait();
+    TSS_MARK(2);
 
     auto issue = [&](int tile, int stage) {
         int t = tile;
@@ -212,6 +215,7 @@ dw_tma_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const float* _
         for (int e = 0; e < 8; ++e) { my1[e] = 0.f; my2[e] = 0.f; }
     }
 
+    TSS_MARK(3);                                   // weights requested, statistics slots zeroed
     for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
         const int stage = it & 1;
         const int next = tile + gridDim.x;
@@ -222,6 +226,7 @@ dw_tma_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const float* _
         const int n = t / tiles_h;
         const int ho0 = th * TH, wo0 = tw * TW;
         mbar_wait(smem_u32(bars + stage), (uint32_t)(it >> 1) & 1);
+        TSS_MARK_IF(threadIdx.x == 0 && it < 3, 4 + 3 * it);           // tile `it` has landed
         float2 acc[TH][4];
 #pragma unroll
         for (int r = 0; r < TH; ++r) zero8p(acc[r]);
@@ -250,6 +255,7 @@ dw_tma_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const float* _
                 }
             }
         }
+        TSS_MARK_IF(threadIdx.x == 0 && it < 3, 5 + 3 * it);           // ... computed
         const int wo = wo0 + col;
         if (wo < Wo) {
             T* yp = y + (((int64_t)n * Ho + ho0) * Wo + wo) * C + c0;
@@ -287,7 +293,9 @@ dw_tma_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const float* _
             }
         }
         __syncthreads();                       // everyone is done with this stage: it may be refilled
+        TSS_MARK_IF(threadIdx.x == 0 && it < 3, 6 + 3 * it);           // ... stored
     }
+    TSS_MARK(13);
     if (stats != nullptr) {                    // (the loop's last __syncthreads published every thread's slots)
         for (int i = threadIdx.x; i < 2 * CB; i += blockDim.x) {
             const int which = i / CB, ch = i - which * CB;
@@ -296,6 +304,7 @@ dw_tma_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const float* _
             atomicAdd(stats + which * C + cb0 + ch, (double)s);
         }
     }
+    TSS_MARK(14);
 }
 
 

@@ -126,6 +126,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int n0 = blockIdx.y * block_n;
     const int num_kb = (K + BK - 1) / BK;
+    TSS_MARK(0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -145,7 +146,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    TSS_MARK(1);
     pdl_wait();          // everything above is on-chip setup; global memory is touched from here on
+    TSS_MARK(2);
 
     if (warp == 0) {
         if (lane == 0) {                                   // ---------------- TMA producer
@@ -158,6 +161,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 tma_load_2d(smem_u32(sA + (size_t)s * kABytes), &tmA, full, kb * BK, (int)m0);
                 tma_load_2d(smem_u32(sB + (size_t)s * b_bytes), &tmB, full, kb * BK, n0);
             }
+            TSS_MARK_IF(true, 3);
         }
     } else if (warp == 1) {
         if (lane == 0) {                                   // ---------------- MMA issuer
@@ -167,6 +171,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const int s = kb % stages;
                 const uint32_t phase = (kb / stages) & 1;
                 mbar_wait(smem_u32(bars + s), phase);
+                TSS_MARK_IF(kb == 0, 4);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t adesc = make_desc_k_sw128(smem_u32(sA + (size_t)s * kABytes));
                 const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + (size_t)s * b_bytes));
@@ -177,6 +182,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 umma_commit(smem_u32(bars + stages + s));                    // smem stage free once these MMAs retire
             }
             umma_commit(smem_u32(bars + 2 * stages));                        // accumulator complete
+            TSS_MARK_IF(true, 5);
         }
     } else {                                               // ---------------- epilogue warps 2..5
         const int q = warp & 3;                            // TMEM lane quarter this warp may access
@@ -184,6 +190,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int64_t row = m0 + row_in_tile;
         const bool row_ok = row < M;
         mbar_wait(smem_u32(bars + 2 * stages), 0);
+        TSS_MARK_IF(threadIdx.x == 64, 6);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int c = 0; c < block_n; c += 16) {
             float v[16];
@@ -233,9 +240,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
             }
         }
+        TSS_MARK_IF(threadIdx.x == 64, 7);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
+    TSS_MARK(8);
     if (stats != nullptr) {
         for (int i = threadIdx.x; i < block_n; i += kThreads) {
             const float a = (s_stat[i] + s_stat[2 * block_n + i]) + (s_stat[4 * block_n + i] + s_stat[6 * block_n + i]);
@@ -244,6 +253,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             atomicAdd(stats + stats_stride + n0 + i, (double)b);
         }
     }
+    TSS_MARK(9);
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -57,6 +57,7 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int n0 = blockIdx.y * block_n;
     const int num_kb = (K + BK - 1) / BK;
+    TSS_MARK(0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -70,7 +71,9 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tc_alloc(smem_u32(tmem_slot), tmem_cols);
     }
     for (int i = threadIdx.x; i < 8 * block_n; i += kThreads) s_stat[i] = 0.f;
+    TSS_MARK(1);
     pdl_wait();
+    TSS_MARK(2);
     for (int i = threadIdx.x; i < block_n; i += kThreads) {           // per-column constants of the producer's BatchNorm
         const float mu = __ldg(mean + n0 + i), rs = __ldg(rstd + n0 + i);
         const float sc = (gamma != nullptr ? __ldg(gamma + n0 + i) : 1.f) * rs;
@@ -95,6 +98,7 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 tma_load_2d(smem_u32(sA + (size_t)s * kABytes), &tmA, full, kb * BK, (int)m0);
                 tma_load_2d(smem_u32(sB + (size_t)s * b_bytes), &tmB, full, kb * BK, n0);
             }
+            TSS_MARK_IF(true, 3);
         }
     } else if (warp == 1) {
         if (lane == 0) {                                   // ---------------- MMA issuer
@@ -103,6 +107,7 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const int s = kb % stages;
                 const uint32_t phase = (kb / stages) & 1;
                 mbar_wait(smem_u32(bars + s), phase);
+                TSS_MARK_IF(kb == 0, 4);
                 tc_fence_after();
                 const uint64_t adesc = make_desc_k_sw128(smem_u32(sA + (size_t)s * kABytes));
                 const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + (size_t)s * b_bytes));
@@ -113,6 +118,7 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 umma_commit(smem_u32(bars + stages + s));
             }
             umma_commit(smem_u32(bars + 2 * stages));
+            TSS_MARK_IF(true, 5);
         }
     } else {                                               // ---------------- epilogue warps 2..5
         const int q = warp & 3;
@@ -127,7 +133,9 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             ypre[j] = make_uint4(0, 0, 0, 0);              // rows >= M: dz is an exact zero (TMA zero fill)
             if (row_ok && j * 8 < block_n) ypre[j] = __ldg(reinterpret_cast<const uint4*>(yp + row * ldyp + n0 + j * 8));
         }
+        TSS_MARK_IF(threadIdx.x == 64, 10);
         mbar_wait(smem_u32(bars + 2 * stages), 0);
+        TSS_MARK_IF(threadIdx.x == 64, 6);
         tc_fence_after();
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
@@ -168,14 +176,17 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
             }
         }
+        TSS_MARK_IF(threadIdx.x == 64, 7);
         tc_fence_before();
     }
     __syncthreads();
+    TSS_MARK(8);
     for (int i = threadIdx.x; i < block_n; i += kThreads) {
         atomicAdd(sums + n0 + i, (s_stat[i] + s_stat[2 * block_n + i]) + (s_stat[4 * block_n + i] + s_stat[6 * block_n + i]));
         atomicAdd(sums + sums_stride + n0 + i,
                   (s_stat[block_n + i] + s_stat[3 * block_n + i]) + (s_stat[5 * block_n + i] + s_stat[7 * block_n + i]));
     }
+    TSS_MARK(9);
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();

@@ -18,6 +18,7 @@ import torch
 
 from . import metrics as M
 from . import functional as Fn
+from . import library
 from .gates import gate
 from .functional import unit_loss_grad
 
@@ -247,6 +248,22 @@ class _LossReader:
         return float(self.slots[prev[0]])
 
 
+_capture_streams = {}
+
+
+def _capture_stream(dev):
+    """ONE warm-up / capture stream per device for every graphed step of the process.  autograd remembers the stream on
+    which a parameter's AccumulateGrad node was created and makes the end of every backward pass that runs the node wait
+    for that stream; a node that outlives its step (any lingering reference to a tensor with a ``grad_fn``) would carry a
+    foreign, non-capturing stream into the next capture ("dependency created on uncaptured work in another stream")."""
+    dev = torch.device(dev)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _capture_streams.get(key)
+    if st is None:
+        st = _capture_streams[key] = torch.cuda.Stream(dev)
+    return st
+
+
 class GraphedTrainStep:
     """The whole optimisation step (zero_grad, forward, loss, backward, gradient all-reduce,
     optimizer) captured ONCE as a CUDA graph and replayed per batch: ~350 kernel launches become
@@ -275,12 +292,16 @@ class GraphedTrainStep:
             optimizer.zero_grad()
             xs, ys = (self.x, self.y) if transform is None else transform.apply(self.x, self.y, self.geom)
             loss = loss_fn(model(xs), ys)
+            if library._CAPTURE_CHECK and torch.cuda.is_current_stream_capturing():
+                library.instrument_backward(loss.grad_fn)
             with unit_loss_grad(loss):
                 loss.backward()
+            if library._CAPTURE_CHECK:
+                library.check_capture('the end of backward')
             optimizer.step()
             return loss.detach()
 
-        side = torch.cuda.Stream(dev)
+        side = _capture_stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         self.warmup_loss = None
         with torch.cuda.stream(side):
@@ -339,7 +360,7 @@ class GraphedEvalStep:
                 cm.update((out, self.y))
             return out
 
-        side = torch.cuda.Stream(dev)
+        side = _capture_stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):

@@ -194,12 +194,28 @@ FUSE_PPM_EVAL = gate('FUSE_PPM_EVAL')
 FUSE_BNFIN = gate('FUSE_BNFIN')
 # Inside a bottleneck, conv1's BatchNorm + ReLU applied by conv2 (depthwise) while it reads its input tile
 # (csrc/dwconv_bnin.cu): the expanded activation is never materialised, conv1's apply pass disappears.
-# Kernels validated on the B200; CUDA-graph capture of the whole step still fails with them: off unless TSS_FUSE_BNIN=1.
+# Kernels validated on the B200, on by default since the reference cycle that broke graph capture is gone (3.67 -> 3.58 ms/step).
 FUSE_BNIN = gate('FUSE_BNIN')
 # The same hand-over from conv2 (depthwise) to conv3 (tensor-core pointwise, csrc/pwconv_tc_fwd_bnin.cu): the activated
 # tensor is written once by the GEMM's operand producer (the weight gradient needs it) and never read in the forward
 # pass.  Same status as FUSE_BNIN: off unless TSS_FUSE_BNIN_PW=1.
 FUSE_BNIN_PW = gate('FUSE_BNIN_PW')
+
+
+def _row_range(name):
+    lo, _, hi = os.environ.get(name, ':').partition(':')
+    return (int(lo) if lo else 0, int(hi) if hi else 1 << 62)
+
+
+_BNIN_ROWS = {'dw': _row_range('TSS_BNIN_ROWS'), 'pw': _row_range('TSS_BNIN_PW_ROWS')}
+
+
+def bnin_rows_ok(kind, t):
+    """A/B aid: ``TSS_BNIN_ROWS=lo:hi`` / ``TSS_BNIN_PW_ROWS=lo:hi`` restrict the hand-over of a BatchNorm apply pass to
+    its depthwise / pointwise consumer to tensors of lo <= N*H*W <= hi pixels (``t``: the NCHW-shaped tensor handed over)."""
+    lo, hi = _BNIN_ROWS[kind]
+    rows = t.shape[0] * t.shape[2] * t.shape[3]
+    return lo <= rows <= hi
 
 
 class _BnLink:
@@ -336,7 +352,10 @@ class ConvBNAct(torch.autograd.Function):
         ctx.link = None
         ConvBNAct.last_link = None
         if FUSE_BNRED and res is None and world == 1:
-            ctx.link = ConvBNAct.last_link = _BnLink(y, mean, rstd, gamma, beta, spec.relu, scratch, bn, C)
+            # (`z is y` when the apply pass is deferred: the link then holds a detached alias -- the returned tensor carries
+            # the link as an attribute, and a link that pointed back at it would be a reference cycle that keeps this step's
+            # autograd graph, with the streams its AccumulateGrad nodes were created on, alive into the next capture)
+            ctx.link = ConvBNAct.last_link = _BnLink(y.detach() if z is y else y, mean, rstd, gamma, beta, spec.relu, scratch, bn, C)
         return z
 
     @staticmethod

@@ -14,8 +14,8 @@ DEFAULTS = {
     'FUSE_BNAPPLY': False,      # BatchNorm-backward apply in the operand producer of the pointwise dgrad
     'FUSE_BNAPPLY_DW': False,   # ... and in the stride-1 depthwise dgrad
     'FUSE_BNFIN': False,        # BatchNorm finalize inside the apply kernel
-    'FUSE_BNIN': False,         # a block's BatchNorm applied by the depthwise conv that reads it
-    'FUSE_BNIN_PW': False,      # ... by the tensor-core pointwise conv that reads it
+    'FUSE_BNIN': True,          # a block's BatchNorm applied by the depthwise conv that reads it (r2: 3.67 -> 3.58 ms/step)
+    'FUSE_BNIN_PW': False,      # ... by the tensor-core pointwise conv that reads it (r2: 3.88 vs 3.67 ms/step, not kept)
     'FUSE_PPM': False,          # pyramid-pooling branches as grouped launches (training: 4.60 vs 4.58 ms/step, not kept)
     'FUSE_PPM_EVAL': True,      # ... in eval mode (folded BatchNorm): bs1 inference 2366 -> 2425 FPS
     'STEM_TC': True,            # stem convolution + weight gradient on tcgen05 (r2: fwd 154 -> 95 us, wgrad 246 -> 202 us; 4.58 -> 4.52 ms/step)

@@ -91,6 +91,36 @@ def _register_launchers():
 _register_launchers()
 
 
+def check_capture(where):
+    """Debugging aid (TSS_CAPTURE_CHECK=1 runs it after every library call): raise as soon as the CUDA-graph capture of the
+    current stream has been invalidated, so that the traceback names the first call after the offending one."""
+    status = _lib.backend().call('tss_capture_status', {'stream_handle': torch.cuda.current_stream().cuda_stream})
+    if status not in (0, 1):
+        raise RuntimeError('CUDA graph capture invalidated at or before %s (status %d)' % (where, status))
+    return status
+
+
+def instrument_backward(root):
+    """Debugging aid: ``check_capture`` before and after every node of the autograd graph under ``root``."""
+    seen, stack = set(), [root]
+    while stack:
+        node = stack.pop()
+        if node is None or node in seen:
+            continue
+        seen.add(node)
+        name = type(node).__name__
+
+        def pre(grads, name=name):
+            check_capture('entering ' + name)
+
+        def post(grad_inputs, grad_outputs, name=name):
+            check_capture('leaving ' + name)
+        node.register_prehook(pre)
+        node.register_hook(post)
+        stack.extend(nxt for nxt, _ in node.next_functions)
+    return len(seen)
+
+
 def dispatch(name, kwargs):
     """``_lib.call`` for a kernel launcher: positional call of the registered operator."""
     op, names = OPS[name]
@@ -107,12 +137,7 @@ def dispatch(name, kwargs):
         args.append(v)
     op(*args)
     if _CAPTURE_CHECK:
-        # debugging aid (TSS_CAPTURE_CHECK=1): a CUDA-graph capture that an operation has invalidated makes this query
-        # raise, so the traceback names the first library call after the offending one
-        try:
-            torch.cuda.is_current_stream_capturing()
-        except Exception as exc:
-            raise RuntimeError('CUDA graph capture invalidated at or before %s' % name) from exc
+        check_capture(name)
     return 0
 
 

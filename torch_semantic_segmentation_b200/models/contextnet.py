@@ -12,7 +12,8 @@ from torch import nn
 
 from .. import ops
 from .. import functional as Fn
-from ..nn.blocks import ConvBNBlock, BottleneckBlock, ClassScores, Dropout, hands_over_to_pointwise, set_compute_dtype
+from ..nn.blocks import (ConvBNBlock, BottleneckBlock, ClassScores, Dropout, hands_over_to_pointwise, observed,
+                         set_compute_dtype)
 
 __all__ = ['ContextNet', 'contextnet12', 'contextnet14', 'contextnet18']
 
@@ -48,7 +49,7 @@ class _Chain(nn.Sequential):
         """``blk`` (any conv+BN block) may leave its BatchNorm + ReLU to the depthwise block ``dw`` that follows:
         functional.FUSE_BNIN."""
         if not (Fn.FUSE_BNIN and isinstance(blk, ConvBNBlock) and isinstance(dw, ConvBNBlock) and blk.training
-                and torch.is_grad_enabled()):
+                and torch.is_grad_enabled() and not observed(blk)):
             return False
         c = dw[0]
         return bool(c.groups == c.in_channels and c.groups > 1 and c.kernel_size == (3, 3) and c.dilation[0] == 1

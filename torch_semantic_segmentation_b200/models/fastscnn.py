@@ -14,7 +14,7 @@ from torch import nn
 from .. import ops
 from .. import functional as Fn
 from ..nn.blocks import (Conv2dBlock, DWConv2dBlock, DSConv2dBlock, DSConvBNBlock, BottleneckBlock, ClassScores, Dropout,
-                         hands_over_to_pointwise, set_compute_dtype)
+                         hands_over_to_pointwise, observed, set_compute_dtype)
 
 __all__ = ['FastSCNN', 'fastscnn', 'Classifier']
 
@@ -82,7 +82,8 @@ class _DownsampleChain(nn.Sequential):
             nxt = modules[i + 1] if i + 1 < len(modules) else None
             last_bn = module[3] if isinstance(module, DSConvBNBlock) else module[1]      # the BatchNorm that would be deferred
             defer = bool(Fn.FUSE_BNIN and isinstance(nxt, DSConvBNBlock) and nxt.takes_pending_input()
-                         and last_bn.track_running_stats and getattr(last_bn, '_tss_sync', None) is None)
+                         and last_bn.track_running_stats and getattr(last_bn, '_tss_sync', None) is None
+                         and not observed(module) and Fn.bnin_rows_ok('dw', x))
             if isinstance(module, DSConvBNBlock):
                 x = module(x, defer_out=defer)
             else:

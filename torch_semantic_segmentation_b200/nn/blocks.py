@@ -237,11 +237,18 @@ class DSConvBNBlock(nn.Sequential, _FusedConvBN):
         return self._conv_bn(2, x, self.use_activation, sole_consumer=True, defer_apply=defer_out)
 
 
+def observed(module):
+    """Somebody looks at this module's output through a forward hook (deep-supervision taps, feature extraction): its
+    BatchNorm apply pass must then not be handed over to the consumer, or the hook would see the raw convolution."""
+    from torch.nn.modules import module as _m
+    return bool(module._forward_hooks or _m._global_forward_hooks)
+
+
 def hands_over_to_pointwise(dw, pw):
     """The depthwise block ``dw`` may leave its BatchNorm (+ReLU) to the tensor-core pointwise block ``pw`` that is its
     only reader (functional.FUSE_BNIN_PW)."""
     if not (Fn.FUSE_BNIN_PW and isinstance(dw, ConvBNBlock) and isinstance(pw, ConvBNBlock) and dw.training
-            and torch.is_grad_enabled()):
+            and torch.is_grad_enabled() and not observed(dw)):
         return False
     c_dw, c_pw = dw[0], pw[0]
     return bool(c_dw.groups == c_dw.in_channels and c_dw.groups > 1 and c_pw.kernel_size == (1, 1) and c_pw.groups == 1
@@ -298,12 +305,13 @@ class BottleneckBlock(nn.Module):
                     and getattr(c3[1], '_tss_sync', None) is None)
 
     def forward(self, input):
-        x = self.conv1(input, defer_apply=self._defer_conv1_apply())
+        x = self.conv1(input, defer_apply=self._defer_conv1_apply() and not observed(self.conv1) and Fn.bnin_rows_ok('dw', input))
         res = input if self.has_residual else None
         y = fused_dw_pw(self.conv2, 0, self.conv3, 0, x, self.conv2.use_activation, True, residual=res)
         if y is not None:
             return y
-        x = self.conv2(x, sole_consumer=True, defer_apply=self._defer_conv2_apply())
+        x = self.conv2(x, sole_consumer=True,
+                       defer_apply=self._defer_conv2_apply() and not observed(self.conv2) and Fn.bnin_rows_ok('pw', input))
         return self.conv3(x, residual=res, relu=True, sole_consumer=True)
 
 
