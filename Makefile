@@ -9,7 +9,9 @@ LIB := torch_semantic_segmentation_b200/libtss_b200.so
 
 all: $(LIB)
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/tma.cuh $(CSRC)/augment_math.h $(CSRC)/tc_ptx.cuh include/tss_b200.h
+HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/tss_b200.h
+
+build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
@@ -19,7 +21,7 @@ $(LIB): $(OBJS)
 # Instrumented copy for tools/trace_kernels.py (TSS_MARK timestamps inside the kernels); never loaded by the product.
 TRACE_LIB := torch_semantic_segmentation_b200/libtss_b200_trace.so
 TRACE_OBJS := $(patsubst $(CSRC)/%.cu,build_trace/%.o,$(SRCS))
-build_trace/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/tma.cuh $(CSRC)/augment_math.h $(CSRC)/tc_ptx.cuh include/tss_b200.h
+build_trace/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build_trace
 	$(NVCC) $(NVCCFLAGS) -DTSS_TRACE -c $< -o $@
 $(TRACE_LIB): $(TRACE_OBJS)

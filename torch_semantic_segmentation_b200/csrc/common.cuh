@@ -100,13 +100,22 @@ __device__ __forceinline__ void tss_trace_mark(int slot) {
 #define TSS_MARK_IF(cond, slot) ((void)0)
 #endif
 
+// The same wait without releasing the dependents early, for the kernels that WRITE PARAMETERS (the optimizer): kernels may
+// read parameters in front of their own wait (dw_stage_taps in tma.cuh), which is only sound if a kernel that is still
+// writing them never has a dependent grid running beside it.
+__device__ __forceinline__ void pdl_wait_hold() {
+#ifndef TSS_HOST_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 // Dynamic shared memory of the CTA.  (tests/simt_emu/ redefines this for host builds of the plain SIMT kernels.)
 #ifndef TSS_DYN_SMEM
 #define TSS_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #endif
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t tss_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+static inline cudaError_t tss_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {
 #ifdef TSS_TRACE
     {   // bind this translation unit's trace pointer (synchronous copy: set the buffer and warm up outside graph capture)

@@ -7,6 +7,7 @@
 // read of the input tile.  TMA zero-fill cannot provide the padding any more (BN(0) != 0): positions outside the
 // image are forced to zero from their coordinates.
 #include "tma.cuh"
+#include "dw_fwd_persistent.cuh"
 
 namespace {
 
@@ -288,7 +289,8 @@ template <> struct TmaTypeI<float> { static constexpr CUtensorMapDataType v = CU
 template <> struct TmaTypeI<bf16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
 
 template <typename T>
-int make_map4i(CUtensorMap* map, const void* base, int C, int W, int H, int N, int bc, int bw, int bh, const char* name) {
+int make_map4i(CUtensorMap* map, const void* base, int C, int W, int H, int N, int bc, int bw, int bh, const char* name,
+               bool nan_fill = false) {
     TssEncodeTiledFn enc = tss_encode_tiled();
     TSS_REQUIRE(enc != nullptr, "%s: cuTensorMapEncodeTiled is not available from the driver", name);
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -296,7 +298,8 @@ int make_map4i(CUtensorMap* map, const void* base, int C, int W, int H, int N, i
     cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, TmaTypeI<T>::v, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TSS_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed (%d)", name, (int)r);
     return TSS_OK;
 }
@@ -307,7 +310,25 @@ int launch_fwd(const void* x, const float* w, void* y, int N, int Hi, int Wi, in
     constexpr int IH = Geo<S, 1, TH>::IH;
     const int IW = (TW - 1) * S + 3;
     CUtensorMap map;
+    if (in_relu) {
+        // out-of-image elements arrive as NaN; the ReLU behind the BatchNorm turns them into the convolution's zero padding
+        static const int nan_pad = [] { const char* e = getenv("TSS_DW_NAN_PAD"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+        CUtensorMap map_nan;
+        if (int e = make_map4i<T>(&map_nan, x, C, Wi, Hi, N, CB, IW, IH, "dwconv3x3_fwd_bnin", nan_pad != 0)) return e;
+        bool launched = false;
+        if (int e = dw_launch_persistent<T, S, 1, TH, false, true>(map_nan, w, y, N, Hi, Wi, Ho, Wo, C, CB, TW, nullptr, nullptr, 0, stats,
+                                                                  in_scale, in_shift, in_relu, nan_pad, st, &launched))
+            return e;
+        if (launched) return TSS_OK;
+    }
     if (int e = make_map4i<T>(&map, x, C, Wi, Hi, N, CB, IW, IH, "dwconv3x3_fwd_bnin")) return e;
+    if (!in_relu) {
+        bool launched = false;
+        if (int e = dw_launch_persistent<T, S, 1, TH, false, true>(map, w, y, N, Hi, Wi, Ho, Wo, C, CB, TW, nullptr, nullptr, 0, stats,
+                                                                  in_scale, in_shift, in_relu, 0, st, &launched))
+            return e;
+        if (launched) return TSS_OK;
+    }
     const int tiles_w = (Wo + TW - 1) / TW, tiles_h = (Ho + TH - 1) / TH;
     const int threads = (CB / 8) * TW;
     const size_t tile_bytes = (size_t)IH * IW * CB * sizeof(T);
@@ -347,7 +368,7 @@ int launch_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi
     const int tiles_w = (Wo + TW - 1) / TW, tiles_h = (Ho + TH - 1) / TH;
     const int ntiles = N * tiles_h * tiles_w;
     const int cblocks = C / CB;
-    int gx = (2 * tss_num_sms() + cblocks - 1) / cblocks;
+    int gx = (2 * tss_num_sms()) / cblocks;       // rounded down: a CTA beyond the resident set would run alone, after the others
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     const int threads = (CB / 8) * TW;

@@ -131,6 +131,148 @@ dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent variant (bf16, 128-thread CTAs): a CTA keeps its taps and the producer's BatchNorm constants in registers and
+// walks the spatial tiles blockIdx.x, blockIdx.x + gridDim.x, ... of its channel block with a 2-stage TMA ring (gradient
+// halo tile + producer tile of tile i+1 in flight while tile i is computed); the two sums live in per-thread shared-memory
+// slots across all tiles and leave the CTA as one atomic per channel.  Two CTAs per SM by construction (2 x ~90 KB of
+// shared memory): the one-tile kernel above re-loads 72 taps and 32 constants per tile with scalar loads (~2 us per CTA,
+// tools/trace_kernels.py) and its 648 CTAs at 1/32 resolution land unevenly on the SMs under programmatic dependent launch.
+template <typename T>
+__global__ void __launch_bounds__(128, 2)
+dw_dgrad_bnred_persistent_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmY,
+                                 const float* __restrict__ w, T* __restrict__ g_out,
+                                 int H, int W, int C, int CB, int TW, int tiles_w, int tiles_h, int ntiles,
+                                 uint32_t stage_bytes, uint32_t ytile_off,
+                                 const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int relu, float* __restrict__ sums) {
+    TSS_DYN_SMEM(uint8_t, smem_raw);
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    const int IW = TW + 2;
+    const uint32_t tile_bytes = (uint32_t)IH * IW * CB * sizeof(T);
+    const uint32_t ytile_bytes = (uint32_t)TH * TW * CB * sizeof(T);
+    uint64_t* bars = (uint64_t*)(smem + 2 * (size_t)stage_bytes);
+    float* part = (float*)(bars + 2);          // [2][TW][CB]: every thread's running sums (its private 16 slots)
+    float* s_w = part + (size_t)2 * TW * CB;   // [9][CB] flipped taps
+    const int cb0 = blockIdx.y * CB;
+    TSS_MARK(0);
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(bars), 1);
+        mbar_init(smem_u32(bars + 1), 1);
+        mbar_fence_init();
+    }
+    dw_stage_taps<true>(w, cb0, CB, s_w);
+    const int CGB = CB >> 3;
+    const int cg = threadIdx.x % CGB, col = threadIdx.x / CGB;
+    const int c0 = cb0 + cg * 8;
+    float* my1 = part + (size_t)col * CB + cg * 8;
+    float* my2 = part + (size_t)(TW + col) * CB + cg * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { my1[e] = 0.f; my2[e] = 0.f; }
+    __syncthreads();
+    float2 wr[9][4];
+    dw_take_taps(s_w, CB, cg, wr);
+    TSS_MARK(1);
+    pdl_wait();
+    TSS_MARK(2);
+
+    auto issue = [&](int tile, int stage) {
+        int t = tile;
+        const int tw = t % tiles_w; t /= tiles_w;
+        const int th = t % tiles_h;
+        const int n = t / tiles_h;
+        const uint32_t bar = smem_u32(bars + stage);
+        uint8_t* base = smem + (size_t)stage * stage_bytes;
+        mbar_expect_tx(bar, tile_bytes + ytile_bytes);
+        tma_load_4d(smem_u32(base), &tmG, bar, cb0, tw * TW - 1, th * TH - 1, n);
+        tma_load_4d(smem_u32(base + ytile_off), &tmY, bar, cb0, tw * TW, th * TH, n);
+    };
+    int tile = blockIdx.x;
+    if (threadIdx.x == 0 && tile < ntiles) issue(tile, 0);
+
+    float mu[8], rs[8], sc[8], sh[8];
+    load8(mean + c0, mu);
+    load8(rstd + c0, rs);
+    if (gamma != nullptr) load8(gamma + c0, sc);
+    if (beta != nullptr) load8(beta + c0, sh);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        sc[e] = (gamma != nullptr ? sc[e] : 1.f) * rs[e];
+        sh[e] = (beta != nullptr ? sh[e] : 0.f) - mu[e] * sc[e];
+    }
+    TSS_MARK(3);
+
+    for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+        const int stage = it & 1;
+        const int next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < ntiles) issue(next, stage ^ 1);    // released by the __syncthreads of iteration it-1
+        int t = tile;
+        const int tw = t % tiles_w; t /= tiles_w;
+        const int th = t % tiles_h;
+        const int n = t / tiles_h;
+        const int h0 = th * TH, w0 = tw * TW;
+        mbar_wait(smem_u32(bars + stage), (uint32_t)(it >> 1) & 1);
+        TSS_MARK_IF(threadIdx.x == 0 && it < 3, 4 + 3 * it);
+        const T* halo = (const T*)(smem + (size_t)stage * stage_bytes);
+        const T* ytile = (const T*)(smem + (size_t)stage * stage_bytes + ytile_off);
+        float2 acc[TH][4];
+#pragma unroll
+        for (int r = 0; r < TH; ++r) zero8p(acc[r]);
+        const T* tp = halo + (size_t)col * CB + cg * 8;
+#pragma unroll
+        for (int j = 0; j < IH; ++j) {
+            float2 v[3][4];
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) load8p_smem(tp + ((size_t)j * IW + kx) * CB, v[kx]);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int r = j - ky;
+                if (r >= 0 && r < TH) {
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[r][e] = ffma2(v[kx][e], wr[ky * 3 + kx][e], acc[r][e]);
+                }
+            }
+        }
+        TSS_MARK_IF(threadIdx.x == 0 && it < 3, 5 + 3 * it);
+        const int wo = w0 + col;
+        if (wo < W) {
+            float s1[8], s2[8];
+            zero8(s1); zero8(s2);
+            const int64_t base = (((int64_t)n * H + h0) * W + wo) * C + c0;
+#pragma unroll
+            for (int r = 0; r < TH; ++r) {
+                if (h0 + r < H) {
+                    float yy[8], g[8];
+                    load8_smem(ytile + ((size_t)r * TW + col) * CB + cg * 8, yy);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float dz = (e & 1) ? acc[r][e >> 1].y : acc[r][e >> 1].x;
+                        const bool on = !relu || fmaf(yy[e], sc[e], sh[e]) > 0.f;
+                        g[e] = on ? dz : 0.f;
+                        s1[e] += g[e];
+                        s2[e] = fmaf(g[e], (yy[e] - mu[e]) * rs[e], s2[e]);
+                    }
+                    store8(g_out + base + (int64_t)r * W * C, g);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { my1[e] += s1[e]; my2[e] += s2[e]; }
+        }
+        __syncthreads();                       // everyone is done with this stage: it may be refilled
+        TSS_MARK_IF(threadIdx.x == 0 && it < 3, 6 + 3 * it);
+    }
+    TSS_MARK(13);
+    for (int i = threadIdx.x; i < 2 * CB; i += blockDim.x) {      // (the loop's last __syncthreads published every thread's slots)
+        const int which = i / CB, ch = i - which * CB;
+        float s = 0.f;
+        for (int cidx = 0; cidx < TW; ++cidx) s += part[(size_t)(which * TW + cidx) * CB + ch];
+        atomicAdd(sums + which * C + cb0 + ch, s);
+    }
+    TSS_MARK(14);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stride 2: the quad kernel of dwconv.cu (2x2 input pixels per 2x2 gradient neighbourhood, vertical
 // strips of R quads, persistent grid with a loop-invariant channel group per thread) with the same fused
 // reduction.  These are the largest BatchNorm-backward instances of the network (the producers are the
@@ -143,9 +285,11 @@ dw_dgrad_s2_bnred_kernel(const T* __restrict__ dy, const float* __restrict__ w, 
                          int N, int Hi, int Wi, int Ho, int Wo, int C, const T* __restrict__ yp,
                          const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                          const float* __restrict__ beta, int relu, float* __restrict__ sums) {
-    pdl_wait();
-    TSS_DYN_SMEM(float, s_sum);        // [2*C]
+    TSS_DYN_SMEM(float, s_sum);        // [2*C] sums, [9][C] taps
+    float* s_w = s_sum + 2 * C;
     for (int i = threadIdx.x; i < 2 * C; i += kQuadThreads) s_sum[i] = 0.f;
+    // taps through shared memory with coalesced loads, before the wait (parameters: see dw_stage_taps in tma.cuh)
+    dw_stage_taps<false>(w, 0, C, s_w);
     __syncthreads();
     const int CG = C >> 3;
     const int nstrips = (Ho + R - 1) / R;
@@ -155,9 +299,8 @@ dw_dgrad_s2_bnred_kernel(const T* __restrict__ dy, const float* __restrict__ w, 
     const int c0 = (int)(item % CG) * 8;          // loop-invariant: gstride % CG == 0
     float wr[9][8];
 #pragma unroll
-    for (int k = 0; k < 9; ++k)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) wr[k][e] = __ldg(w + (c0 + e) * 9 + k);
+    for (int k = 0; k < 9; ++k) load8_smem(s_w + k * C + c0, wr[k]);
+    pdl_wait();
     // the loop accumulates sum g and sum g*y; x-hat comes in at the end: sum g*xhat = rstd*(sum g*y - mean*sum g)
     float sc[8], sh[8], s1[8], s2[8];
     zero8(s1); zero8(s2);
@@ -286,7 +429,14 @@ extern "C" int tss_dwconv3x3_dgrad_s2_bnred(const void* dy, const float* w, void
     grid = (grid + qd - 1) / qd * qd;
     TSS_DISPATCH_DTYPE(dtype, "dwconv3x3_dgrad_s2_bnred", {
         auto kern = occ == 2 ? dw_dgrad_s2_bnred_kernel<T, R, 2> : dw_dgrad_s2_bnred_kernel<T, R, 3>;
-        tss_launch(kern, (unsigned)grid, kQuadThreads, (size_t)2 * C * sizeof(float), (cudaStream_t)stream,
+        if ((size_t)11 * C * sizeof(float) > 48 * 1024) {
+            static bool attr_set[2] = {false, false};
+            if (!attr_set[occ == 2]) {
+                TSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * 2048 * (int)sizeof(float)));
+                attr_set[occ == 2] = true;
+            }
+        }
+        tss_launch(kern, (unsigned)grid, kQuadThreads, (size_t)11 * C * sizeof(float), (cudaStream_t)stream,
                    (const T*)dy, w, (T*)g, N, Hi, Wi, Ho, Wo, C, (const T*)yp, mean, rstd, gamma, beta, flags & TSS_EPI_RELU, sums);
         TSS_LAUNCH_CHECK("dwconv3x3_dgrad_s2_bnred");
         return TSS_OK;
@@ -323,6 +473,33 @@ extern "C" int tss_dwconv3x3_dgrad_bnred(const void* dy, const float* w, void* g
         const int threads = (CB / 8) * TW;
         const size_t tile_bytes = (size_t)IH * IW * CB * sizeof(T);
         const size_t ytile_bytes = (size_t)TH * TW * CB * sizeof(T);
+        {
+            // persistent CTAs with a 2-stage TMA ring, two per SM (TSS_DW_PERSIST=0: the one-tile kernel below)
+            static const int persist = [] { const char* e = getenv("TSS_DW_PERSIST"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+            const size_t ytile_off = (tile_bytes + 127) & ~(size_t)127;
+            const size_t stage = ytile_off + ((ytile_bytes + 127) & ~(size_t)127);
+            const int64_t ntiles = (int64_t)N * tiles_h * tiles_w;
+            size_t smem_p = 128 + 2 * stage + 16 + (size_t)2 * TW * CB * sizeof(float) + (size_t)9 * CB * sizeof(float);
+            if (persist && sizeof(T) == 2 && threads <= 128 && smem_p <= 112 * 1024 && ntiles < (1ll << 30)) {
+                const size_t cap = (size_t)(228 * 1024) / 3 - 1024 + 256;        // a third CTA must not fit on the SM
+                if (smem_p < cap) smem_p = cap;
+                auto kp = dw_dgrad_bnred_persistent_kernel<T>;
+                static bool attr_set_p = false;
+                if (!attr_set_p) {
+                    TSS_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+                    attr_set_p = true;
+                }
+                const int cblocks = C / CB;
+                int64_t gx = ((int64_t)tss_num_sms() * 2) / cblocks;     // rounded DOWN: a CTA beyond the resident set would run alone
+                if (gx > ntiles) gx = ntiles;
+                if (gx < 1) gx = 1;
+                tss_launch(kp, dim3((unsigned)gx, (unsigned)cblocks), threads, smem_p, (cudaStream_t)stream, map, mapy, w, (T*)g, H, W, C, CB, TW,
+                           tiles_w, tiles_h, (int)ntiles, (uint32_t)stage, (uint32_t)ytile_off, mean, rstd, gamma, beta,
+                           flags & TSS_EPI_RELU, sums);
+                TSS_LAUNCH_CHECK("dwconv3x3_dgrad_bnred(persistent)");
+                return TSS_OK;
+            }
+        }
         size_t smem = 128 + ((tile_bytes + 127) & ~(size_t)127) + ((ytile_bytes + 15) & ~(size_t)15) + 16;
         const size_t part = (size_t)2 * TW * CB * sizeof(float) + 128;
         if (smem < part) smem = part;

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #include "tma.cuh"
+#include "dw_fwd_persistent.cuh"
 
 namespace {
 
@@ -155,160 +156,6 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
 
 
 // ---------------------------------------------------------------------------------------------
-// Persistent variant of dw_tma_kernel: a CTA keeps its 72 weights in registers and walks the spatial tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ... of its channel block with a 2-stage TMA ring (the halo tile of tile i+1 is in
-// flight while tile i is computed, as in the weight-gradient kernel below); the BatchNorm statistics stay in registers
-// across ALL tiles and are reduced once per CTA.  The one-tile kernel pays barrier init, weight loads, the TMA round
-// trip, a shared-memory reduction and 2*CB fp64 atomics PER TILE (r2 ncu: 2.8 TB/s on 32ch@1/2, 0.4-1.4 TB/s on the
-// small maps at 16 % occupancy).
-template <typename T, int S, int D, int TH, bool FLIP>
-__global__ void __launch_bounds__(192, 2)
-dw_tma_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w, T* __restrict__ y,
-                         int Ho, int Wo, int C, int CB, int TW, int tiles_w, int tiles_h, int ntiles, uint32_t stage_bytes,
-                         const float* __restrict__ scale, const float* __restrict__ shift, int flags,
-                         double* __restrict__ stats) {
-    constexpr int IH = Geo<S, D, TH>::IH;
-    TSS_DYN_SMEM(uint8_t, smem_raw);
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    const int IW = (TW - 1) * S + 2 * D + 1;
-    const uint32_t tile_bytes = (uint32_t)IH * IW * CB * sizeof(T);
-    uint64_t* bars = (uint64_t*)(smem + 2 * (size_t)stage_bytes);
-    float* part = (float*)(bars + 2);          // [2][TW][CB]: every thread's running statistics (its private 16 slots)
-    const int cb0 = blockIdx.y * CB;
-    TSS_MARK(0);
-    if (threadIdx.x == 0) {
-        mbar_init(smem_u32(bars), 1);
-        mbar_init(smem_u32(bars + 1), 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    TSS_MARK(1);
-    pdl_wait();
-    TSS_MARK(2);
-
-    auto issue = [&](int tile, int stage) {
-        int t = tile;
-        const int tw = t % tiles_w; t /= tiles_w;
-        const int th = t % tiles_h;
-        const int n = t / tiles_h;
-        const uint32_t bar = smem_u32(bars + stage);
-        mbar_expect_tx(bar, tile_bytes);
-        tma_load_4d(smem_u32(smem + (size_t)stage * stage_bytes), &tmX, bar, cb0, tw * TW * S - D, th * TH * S - D, n);
-    };
-    int tile = blockIdx.x;
-    if (threadIdx.x == 0 && tile < ntiles) issue(tile, 0);
-
-    const int CGB = CB >> 3;
-    const int cg = threadIdx.x % CGB, col = threadIdx.x / CGB;     // col < TW by construction
-    const int c0 = cb0 + cg * 8;
-    float2 wr[9][4];
-#pragma unroll
-    for (int k = 0; k < 9; ++k)
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            wr[k][e] = make_float2(__ldg(w + (c0 + 2 * e) * 9 + (FLIP ? 8 - k : k)), __ldg(w + (c0 + 2 * e + 1) * 9 + (FLIP ? 8 - k : k)));
-    const bool relu = (flags & TSS_EPI_RELU) != 0;
-    float* my1 = part + (size_t)col * CB + cg * 8;           // the statistics live in shared memory between tiles: registers
-    float* my2 = part + (size_t)(TW + col) * CB + cg * 8;    // hold 72 weights + 64 accumulators already
-    if (stats != nullptr) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { my1[e] = 0.f; my2[e] = 0.f; }
-    }
-
-    TSS_MARK(3);                                   // weights requested, statistics slots zeroed
-    for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
-        const int stage = it & 1;
-        const int next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < ntiles) issue(next, stage ^ 1);    // released by the __syncthreads of iteration it-1
-        int t = tile;
-        const int tw = t % tiles_w; t /= tiles_w;
-        const int th = t % tiles_h;
-        const int n = t / tiles_h;
-        const int ho0 = th * TH, wo0 = tw * TW;
-        mbar_wait(smem_u32(bars + stage), (uint32_t)(it >> 1) & 1);
-        TSS_MARK_IF(threadIdx.x == 0 && it < 3, 4 + 3 * it);           // tile `it` has landed
-        float2 acc[TH][4];
-#pragma unroll
-        for (int r = 0; r < TH; ++r) zero8p(acc[r]);
-        const T* tp = (const T*)(smem + (size_t)stage * stage_bytes) + ((size_t)col * S) * CB + cg * 8;
-#pragma unroll
-        for (int j = 0; j < IH; ++j) {
-            bool used = false;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int tt = j - ky * D;
-                if (tt >= 0 && tt % S == 0 && tt / S < TH) used = true;
-            }
-            if (!used) continue;
-            float2 v[3][4];
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) load8p_smem(tp + ((size_t)j * IW + kx * D) * CB, v[kx]);
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int tt = j - ky * D;
-                if (tt >= 0 && tt % S == 0 && tt / S < TH) {
-                    const int r = tt / S;
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) acc[r][e] = ffma2(v[kx][e], wr[ky * 3 + kx][e], acc[r][e]);
-                }
-            }
-        }
-        TSS_MARK_IF(threadIdx.x == 0 && it < 3, 5 + 3 * it);           // ... computed
-        const int wo = wo0 + col;
-        if (wo < Wo) {
-            T* yp = y + (((int64_t)n * Ho + ho0) * Wo + wo) * C + c0;
-            float2 s1[4], s2[4];
-            zero8p(s1); zero8p(s2);
-#pragma unroll
-            for (int r = 0; r < TH; ++r) {
-                if (ho0 + r < Ho) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        s1[e].x += acc[r][e].x; s1[e].y += acc[r][e].y;
-                        s2[e] = ffma2(acc[r][e], acc[r][e], s2[e]);
-                    }
-                    if (shift != nullptr) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 sc = scale != nullptr ? make_float2(__ldg(scale + c0 + 2 * e), __ldg(scale + c0 + 2 * e + 1)) : make_float2(1.f, 1.f);
-                            const float2 sh = make_float2(__ldg(shift + c0 + 2 * e), __ldg(shift + c0 + 2 * e + 1));
-                            acc[r][e] = ffma2(acc[r][e], sc, sh);
-                        }
-                    }
-                    if (relu) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) acc[r][e] = make_float2(fmaxf(acc[r][e].x, 0.f), fmaxf(acc[r][e].y, 0.f));
-                    }
-                    store8p(yp + (int64_t)r * Wo * C, acc[r]);
-                }
-            }
-            if (stats != nullptr) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    my1[2 * e] += s1[e].x; my1[2 * e + 1] += s1[e].y;
-                    my2[2 * e] += s2[e].x; my2[2 * e + 1] += s2[e].y;
-                }
-            }
-        }
-        __syncthreads();                       // everyone is done with this stage: it may be refilled
-        TSS_MARK_IF(threadIdx.x == 0 && it < 3, 6 + 3 * it);           // ... stored
-    }
-    TSS_MARK(13);
-    if (stats != nullptr) {                    // (the loop's last __syncthreads published every thread's slots)
-        for (int i = threadIdx.x; i < 2 * CB; i += blockDim.x) {
-            const int which = i / CB, ch = i - which * CB;
-            float s = 0.f;
-            for (int cidx = 0; cidx < TW; ++cidx) s += part[(size_t)(which * TW + cidx) * CB + ch];
-            atomicAdd(stats + which * C + cb0 + ch, (double)s);
-        }
-    }
-    TSS_MARK(14);
-}
-
-
-// ---------------------------------------------------------------------------------------------
 // wgrad: dw[c][ky][kx] += sum_{n,ho,wo} x[n][ho*S-D+ky*D][wo*S-D+kx*D][c] * dy[n][ho][wo][c]
 //
 // Persistent CTAs (grid.y = channel block, grid.x strides over the spatial tiles) with a 2-stage
@@ -442,28 +289,11 @@ int launch(const void* x, const float* w, void* y, int N, int Hi, int Wi, int Ho
     const size_t tile_bytes = (size_t)IH * IW * CB * sizeof(T);
     {
         // persistent CTAs with a 2-stage TMA ring (TSS_DW_PERSIST=0: the one-tile kernel below)
-        static const int persist = [] { const char* e = getenv("TSS_DW_PERSIST"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
-        const size_t stage = (tile_bytes + 127) & ~(size_t)127;
-        const int64_t ntiles = (int64_t)N * tiles_h * tiles_w;
-        const size_t part = (size_t)2 * TW * CB * sizeof(float);
-        size_t smem_p = 128 + 2 * stage + 16 + part;
-        if (persist && smem_p <= 100 * 1024 && ntiles < (1ll << 30)) {
-            auto kp = dw_tma_persistent_kernel<T, S, D, TH, FLIP>;
-            static bool attr_set_p = false;
-            if (!attr_set_p) {
-                TSS_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                attr_set_p = true;
-            }
-            const int cblocks = C / CB;
-            int64_t gx = ((int64_t)tss_num_sms() * 2 + cblocks - 1) / cblocks;        // 2 resident CTAs per SM in total
-            if (gx > ntiles) gx = ntiles;
-            if (gx < 1) gx = 1;
-            dim3 grid((unsigned)gx, (unsigned)cblocks);
-            tss_launch(kp, grid, threads, smem_p, st, map, w, (T*)y, Ho, Wo, C, CB, TW, tiles_w, tiles_h, (int)ntiles, (uint32_t)stage,
-                       scale, shift, flags, stats);
-            TSS_LAUNCH_CHECK("dwconv3x3(tma, persistent)");
-            return TSS_OK;
-        }
+        bool launched = false;
+        if (int e = dw_launch_persistent<T, S, D, TH, FLIP, false>(map, w, y, N, Hi, Wi, Ho, Wo, C, CB, TW, scale, shift, flags, stats,
+                                                                  nullptr, nullptr, 0, 0, st, &launched))
+            return e;
+        if (launched) return TSS_OK;
     }
     const size_t smem = 128 + ((tile_bytes + 15) & ~(size_t)15) + 8 + 2 * CB * sizeof(float);
     auto kern = dw_tma_kernel<T, S, D, TH, FLIP>;
@@ -517,7 +347,7 @@ int launch_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi
     const int tiles_w = (Wo + TW - 1) / TW, tiles_h = (Ho + TH - 1) / TH;
     const int ntiles = N * tiles_h * tiles_w;
     const int cblocks = C / CB;
-    int gx = (2 * tss_num_sms() + cblocks - 1) / cblocks;
+    int gx = (2 * tss_num_sms()) / cblocks;       // rounded down: a CTA beyond the resident set would run alone, after the others
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     const int threads = (CB / 8) * TW;

@@ -19,7 +19,7 @@ __global__ void adamw_prepare_kernel(float* __restrict__ hyper) {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              int64_t n4, int64_t n, const float* __restrict__ hyper, float grad_scale) {
-    pdl_wait();
+    pdl_wait_hold();        // writes parameters: no dependent grid beside it
     const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
     const float step_size = lr * hyper[6], bc2s = hyper[7];
     const float decay = 1.f - lr * wd;

@@ -63,4 +63,45 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+
+// ---------------------------------------------------------------- depthwise taps --------
+// The CB x 9 taps of one channel block, for the TMA-staged depthwise kernels.  Every thread used to fetch its 72 taps
+// with scalar loads 36 bytes apart (8 sectors per request, ~2 us of L1 traffic per CTA: tools/trace_kernels.py); now the
+// CTA copies the block with coalesced loads into shared memory as [9][CB] (tap-major, flipped for a dgrad) and each
+// thread takes 8 channels x 9 taps with 128-bit reads.  Parameters are written by the optimizer's kernels only, which
+// do not release their dependents early (optim.cu), so the copy may run BEFORE griddepcontrol.wait.
+template <bool FLIP>
+__device__ __forceinline__ void dw_stage_taps(const float* __restrict__ w, int cb0, int CB, float* s_w) {
+    const float* src = w + (size_t)cb0 * 9;
+    const int n = CB * 9;
+    // eight independent loads in flight per thread and round (a plain load -> store loop pays one global round trip per
+    // iteration: 2 us for 5 iterations in the trace)
+    for (int base = 0; base < n; base += 8 * (int)blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
+            v[u] = i < n ? __ldg(src + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
+            if (i < n) {
+                const int c = i / 9, k = i - c * 9;
+                s_w[(FLIP ? 8 - k : k) * CB + c] = v[u];
+            }
+        }
+    }
+}
+__device__ __forceinline__ void dw_take_taps(const float* s_w, int CB, int cg, float2 (&wr)[9][4]) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(s_w + k * CB + cg * 8);
+        const float4 b = *reinterpret_cast<const float4*>(s_w + k * CB + cg * 8 + 4);
+        wr[k][0] = make_float2(a.x, a.y);
+        wr[k][1] = make_float2(a.z, a.w);
+        wr[k][2] = make_float2(b.x, b.y);
+        wr[k][3] = make_float2(b.z, b.w);
+    }
+}
 #endif  // !TSS_HOST_EMU
