@@ -25,17 +25,17 @@ enum CUtensorMapDataType { CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 = 9, CU_TENSOR_MAP_D
 enum CUtensorMapInterleave { CU_TENSOR_MAP_INTERLEAVE_NONE = 0 };
 enum CUtensorMapSwizzle { CU_TENSOR_MAP_SWIZZLE_NONE = 0, CU_TENSOR_MAP_SWIZZLE_128B = 3 };
 enum CUtensorMapL2promotion { CU_TENSOR_MAP_L2_PROMOTION_L2_128B = 2 };
-enum CUtensorMapFloatOOBfill { CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = 0 };
+enum CUtensorMapFloatOOBfill { CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = 0, CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA = 1 };
 struct CUtensorMap {
     const unsigned char* base;
     uint32_t rank;
     uint64_t dim[4], stride[4];      // dim[0] = innermost extent (elements); stride[i] = byte pitch of dimension i (stride[0] = element)
     uint32_t box[4];
-    int elem_bytes, swizzle;
+    int elem_bytes, swizzle, nan_fill;
 };
 inline CUresult tss_emu_encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* gdim,
                                      const cuuint64_t* gstr, const cuuint32_t* box, const cuuint32_t*, CUtensorMapInterleave,
-                                     CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+                                     CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill fill) {
     if (rank < 2 || rank > 4) return 1;
     m->elem_bytes = dt == CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 ? 2 : 4;
     if (sw == CU_TENSOR_MAP_SWIZZLE_128B && (rank != 2 || box[0] * (uint32_t)m->elem_bytes != 128)) return 1;
@@ -51,6 +51,7 @@ inline CUresult tss_emu_encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuu
         if (i >= 1 && i < rank && gstr[i - 1] % 16 != 0) return 1;
     }
     m->swizzle = sw == CU_TENSOR_MAP_SWIZZLE_128B;
+    m->nan_fill = fill == CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA;
     return CUDA_SUCCESS;
 }
 enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0 };
@@ -124,6 +125,7 @@ inline void tma_load_nd(uint32_t dst, const CUtensorMap* map, uint32_t bar, cons
                         src += (uint64_t)x[d] * map->stride[d];
                     }
                     if (in) memcpy(v, map->base + src, eb);
+                    else if (map->nan_fill) { const uint32_t q = eb == 2 ? 0x7fffu : 0x7fffffffu; memcpy(v, &q, eb); }   // quiet NaN
                     memcpy(tss_emu::dyn_smem + (map->swizzle ? tss_emu::swz128(dst + off) : dst + off), v, eb);
                 }
     std::lock_guard<std::mutex> l(tss_emu::mbar_mutex);

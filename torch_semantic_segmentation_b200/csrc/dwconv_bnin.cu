@@ -177,7 +177,8 @@ template <typename T, int S, int D, int TH>
 __global__ void __launch_bounds__(192, 2)
 dw_wgrad_tma_bnin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                          float* __restrict__ dw, int CB, int TW, int tiles_w, int tiles_h, int ntiles, uint32_t stage_bytes,
-                         const float* __restrict__ in_scale, const float* __restrict__ in_shift, int in_relu, int Hi, int Wi) {
+                         const float* __restrict__ in_scale, const float* __restrict__ in_shift, int in_relu, int Hi, int Wi,
+                         int pad_nan) {
     constexpr int IH = Geo<S, D, TH>::IH;
     TSS_DYN_SMEM(uint8_t, smem_raw);
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -235,34 +236,48 @@ dw_wgrad_tma_bnin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         float2 g[TH][4];
 #pragma unroll
         for (int r = 0; r < TH; ++r) load8p_smem(sg + (size_t)r * TW * CB, g[r]);
+        // kPadNan: out-of-image elements arrive as NaN (tensor-map fill) and the ReLU behind the BatchNorm makes them the
+        // zero padding -- no coordinate test and no select behind the loads (see dw_fwd_persistent.cuh)
+        auto correlate = [&](auto pad_nan_tag) {
+            constexpr bool kPadNan = decltype(pad_nan_tag)::value;
 #pragma unroll
-        for (int j = 0; j < IH; ++j) {
-            bool used = false;
+            for (int j = 0; j < IH; ++j) {
+                bool used = false;
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int tt = j - ky * D;
-                if (tt >= 0 && tt % S == 0 && tt / S < TH) used = true;
-            }
-            if (!used) continue;
-            float2 v[3][4];
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int tt = j - ky * D;
+                    if (tt >= 0 && tt % S == 0 && tt / S < TH) used = true;
+                }
+                if (!used) continue;
+                float2 v[3][4];
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                load8p_smem(sx + ((size_t)j * IW + kx * D) * CB, v[kx]);
-                const int hq = th_ * TH * S - D + j, wq = tw_ * TW * S - D + col * S + kx * D;
-                in_affine(v[kx], isc, ish, in_relu, hq >= 0 && hq < Hi && wq >= 0 && wq < Wi);
-            }
+                for (int kx = 0; kx < 3; ++kx) {
+                    load8p_smem(sx + ((size_t)j * IW + kx * D) * CB, v[kx]);
+                    if (kPadNan) {
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int tt = j - ky * D;
-                if (tt >= 0 && tt % S == 0 && tt / S < TH) {
-                    const int r = tt / S;
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 a = ffma2(v[kx][e], isc[e], ish[e]);
+                            v[kx][e] = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
+                        }
+                    } else {
+                        const int hq = th_ * TH * S - D + j, wq = tw_ * TW * S - D + col * S + kx * D;
+                        in_affine(v[kx], isc, ish, in_relu, hq >= 0 && hq < Hi && wq >= 0 && wq < Wi);
+                    }
+                }
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx)
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int tt = j - ky * D;
+                    if (tt >= 0 && tt % S == 0 && tt / S < TH) {
+                        const int r = tt / S;
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) acc[ky * 3 + kx][e] = ffma2(v[kx][e], g[r][e], acc[ky * 3 + kx][e]);
+                        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) acc[ky * 3 + kx][e] = ffma2(v[kx][e], g[r][e], acc[ky * 3 + kx][e]);
+                    }
                 }
             }
-        }
+        };
+        if (pad_nan) correlate(DwTrue{}); else correlate(DwFalse{});
         __syncthreads();                       // everyone is done with this stage: it may be refilled
     }
 
@@ -363,7 +378,9 @@ int launch_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi
     const size_t part = (size_t)TW * 9 * CB * sizeof(float);
     if (2 * stage < part) stage = (part / 2 + 127) & ~(size_t)127;
     CUtensorMap mx, mg;
-    if (int e = make_map4i<T>(&mx, x, C, Wi, Hi, N, CB, IW, IH, "dwconv3x3_wgrad_bnin")) return e;
+    static const int nan_env = [] { const char* e = getenv("TSS_DW_NAN_PAD"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+    const int pad_nan = (in_relu && nan_env) ? 1 : 0;
+    if (int e = make_map4i<T>(&mx, x, C, Wi, Hi, N, CB, IW, IH, "dwconv3x3_wgrad_bnin", pad_nan != 0)) return e;
     if (int e = make_map4i<T>(&mg, dy, C, Wo, Ho, N, CB, TW, TH, "dwconv3x3_wgrad_bnin")) return e;
     const int tiles_w = (Wo + TW - 1) / TW, tiles_h = (Ho + TH - 1) / TH;
     const int ntiles = N * tiles_h * tiles_w;
@@ -380,7 +397,7 @@ int launch_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi
         attr_set = true;
     }
     tss_launch(kern, dim3((unsigned)gx, (unsigned)cblocks), threads, smem, st, mx, mg, dw, CB, TW, tiles_w, tiles_h, ntiles,
-               (uint32_t)stage, in_scale, in_shift, in_relu, Hi, Wi);
+               (uint32_t)stage, in_scale, in_shift, in_relu, Hi, Wi, pad_nan);
     TSS_LAUNCH_CHECK("dwconv3x3_wgrad_bnin");
     return TSS_OK;
 }

@@ -64,6 +64,8 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+#endif  // !TSS_HOST_EMU
+
 // ---------------------------------------------------------------- depthwise taps --------
 // The CB x 9 taps of one channel block, for the TMA-staged depthwise kernels.  Every thread used to fetch its 72 taps
 // with scalar loads 36 bytes apart (8 sectors per request, ~2 us of L1 traffic per CTA: tools/trace_kernels.py); now the
@@ -104,4 +106,4 @@ __device__ __forceinline__ void dw_take_taps(const float* s_w, int CB, int cg, f
         wr[k][3] = make_float2(b.z, b.w);
     }
 }
-#endif  // !TSS_HOST_EMU
+
