@@ -16,6 +16,7 @@ import json
 import os
 import subprocess
 import sys
+import types
 import threading
 import time
 
@@ -191,6 +192,12 @@ def kernel_family(op):
     """The CUDA kernel function an op of the table runs (ops that launch the same kernel share a family)."""
     if op.startswith('pwconv_wgrad'):
         return 'wgrad_tc_kernel (pointwise wgrad, tcgen05)'
+    if op.startswith('pwconv_dgrad_bnred'):
+        return 'pw_tc_bnred_kernel (pointwise dgrad + BatchNorm-backward reduction, tcgen05)'
+    if op.startswith('dwconv_dgrad_bnred') and ' s2 ' in op:
+        return 'dw_dgrad_s2_bnred_kernel (depthwise stride-2 dgrad + BatchNorm-backward reduction)'
+    if op.startswith('dwconv_dgrad_bnred'):
+        return 'dw_dgrad_bnred_persistent_kernel (depthwise stride-1 dgrad + BatchNorm-backward reduction)'
     if op.startswith('pwconv_'):
         return 'pw_tc_kernel (pointwise fwd + dgrad, tcgen05)'
     if op.startswith('dwconv_wgrad'):
@@ -231,6 +238,12 @@ def kernel_table(device, runner=None):
                      'gbs': nbytes / ms / 1e6, 'share_ms': ms * count})
 
     px = lambda div: N * (CROP // div) ** 2
+
+    def link(y, C):
+        """The BatchNorm in front of a fused dgrad: its raw input, batch statistics, affine, ReLU, reduction target."""
+        a = torch.rand(4, C, device=device) + 0.5
+        return types.SimpleNamespace(y=y, mean=a[0] - 1.0, rstd=a[1], gamma=a[2], beta=a[3] - 1.0, relu=True,
+                                     sums=torch.zeros(2 * C, dtype=torch.float32, device=device))
     # final x8 up-sampling of the class scores + fused CE + its backward (the 269 MB logits tensor)
     small = ops.empty_nhwc(N, CLASSES, CROP // 8, CROP // 8, bf, device, pitch=32).normal_()
     target = torch.randint(0, CLASSES, (N, CROP, CROP), device=device)
@@ -272,7 +285,14 @@ def kernel_table(device, runner=None):
         yo = act(C, div * s)             # a gradient of the output's shape
         io = 2 * C * (px(div) + px(div * s))
         add('dwconv_fwd C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_fwd(xi, wd, s, d, stats=sd))
-        add('dwconv_dgrad C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_dgrad(yo, wd, xi.shape[2], xi.shape[3], s, d))
+        if d == 1:
+            # what the step launches for these layers: the dgrad with the BatchNorm-backward reduction of the layer in front
+            # fused in (reads the gradient and that layer's raw output, writes the masked gradient)
+            lk = link(xi, C)
+            fused = ops.dwconv_dgrad_s2_bnred if s == 2 else ops.dwconv_dgrad_bnred
+            add('dwconv_dgrad_bnred C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io + 2 * C * px(div), lambda: fused(yo, wd, lk))
+        else:
+            add('dwconv_dgrad C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_dgrad(yo, wd, xi.shape[2], xi.shape[3], s, d))
         add('dwconv_wgrad C%d s%d d%d @1/%d' % (C, s, d, div), cnt, io, lambda: ops.dwconv_wgrad(xi, yo, torch.zeros_like(wd), s, d))
     # pointwise GEMMs: the tcgen05/TMEM/TMA kernels the bf16 model runs (impl 1), every shape of the network
     # (K -> N, level, layers of that shape)
@@ -287,10 +307,20 @@ def kernel_table(device, runner=None):
         dwp = torch.zeros_like(wp)
         io = 2 * px(div) * (K + Nc)
         add('pwconv_fwd %d->%d @1/%d' % (K, Nc, div), cnt, io + 2 * K * Nc, lambda: ops.pwconv_fwd(xi, wp, stats=sp, wp=pk[0], impl=1))
-        add('pwconv_dgrad %d->%d @1/%d' % (K, Nc, div), cnt, io + 2 * K * Nc, lambda: ops.pwconv_dgrad(yo, wp, wpT=pk[1], impl=1))
+        if (K, Nc, div) in FUSED_PW_DGRAD:
+            # the conv reads a depthwise conv's BatchNorm+ReLU output: its dgrad carries that BatchNorm's backward reduction
+            lk = link(xi, K)
+            add('pwconv_dgrad_bnred %d->%d @1/%d' % (K, Nc, div), cnt, io + 2 * px(div) * K + 2 * K * Nc, lambda: ops.pwconv_dgrad_bnred(yo, pk[1], lk))
+        else:
+            add('pwconv_dgrad %d->%d @1/%d' % (K, Nc, div), cnt, io + 2 * K * Nc, lambda: ops.pwconv_dgrad(yo, wp, wpT=pk[1], impl=1))
         add('pwconv_wgrad %d->%d @1/%d' % (K, Nc, div), cnt, io + 4 * K * Nc, lambda: ops.pwconv_wgrad(xi, yo, dwp, impl=1))
     rows.sort(key=lambda r: -r['share_ms'])
     return rows
+
+
+# pointwise convs (K -> Nc @ level) whose dgrad runs pw_tc_bnred_kernel in the step (14 launches: the project convs of the
+# bottlenecks, the pointwise halves of the separable convs)
+FUSED_PW_DGRAD = {(32, 48, 4), (48, 64, 8), (384, 64, 16), (384, 96, 32), (576, 96, 32), (576, 128, 32), (768, 128, 32), (128, 128, 8)}
 
 
 # ------------------------------------------------------------------ the metric's other legs --

@@ -70,6 +70,15 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
+// The first TMA instruction that names a tensor map fetches its 128-byte descriptor (a kernel parameter, independent of the
+// preceding grid): ~0.5 us in front of the first load of every CTA (tools/trace_kernels.py: "predecessor complete" ->
+// "last TMA issued").  One thread requests it before griddepcontrol.wait so that the fetch overlaps the predecessor's tail.
+__device__ __forceinline__ void tma_prefetch_desc(const void* map) {
+#ifndef TSS_HOST_EMU
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(map)) : "memory");
+#endif
+}
+
 // ---------------------------------------------------------------- in-kernel timeline ----
 // `make trace` builds libtss_b200_trace.so with -DTSS_TRACE: TSS_MARK(slot) then stores %globaltimer (ns) of the calling
 // thread into trace[cta * 16 + slot] (tools/trace_kernels.py reads the buffer and prints where a CTA's time goes).

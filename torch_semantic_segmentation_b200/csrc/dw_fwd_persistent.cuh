@@ -60,6 +60,7 @@ dw_tma_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const float* _
     float2 wr[9][4];
     dw_take_taps(s_w, CB, cg, wr);
     TSS_MARK(1);
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmX); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();
     TSS_MARK(2);
 

@@ -56,6 +56,7 @@ dw_tma_bnin_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
     if (stats != nullptr)
         for (int i = threadIdx.x; i < 2 * CB; i += blockDim.x) s_stat[i] = 0.f;
     __syncthreads();
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmX); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();              // barrier init / smem zeroing above overlap the previous kernel's tail
     if (threadIdx.x == 0) {
         mbar_expect_tx(smem_u32(bar), tile_bytes);
@@ -195,6 +196,7 @@ dw_wgrad_tma_bnin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         mbar_fence_init();
     }
     __syncthreads();
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmG); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();
 
     auto issue = [&](int tile, int stage) {

@@ -43,6 +43,7 @@ dw_dgrad_bnred_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
         mbar_fence_init();
     }
     __syncthreads();
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmY); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();
     if (threadIdx.x == 0) {
         mbar_expect_tx(smem_u32(bar), tile_bytes + ytile_bytes);
@@ -172,6 +173,7 @@ dw_dgrad_bnred_persistent_kernel(const __grid_constant__ CUtensorMap tmG, const 
     float2 wr[9][4];
     dw_take_taps(s_w, CB, cg, wr);
     TSS_MARK(1);
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmY); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();
     TSS_MARK(2);
 
@@ -397,6 +399,168 @@ dw_dgrad_s2_bnred_kernel(const T* __restrict__ dy, const float* __restrict__ w, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stride 2 through TMA (bf16): the quad arithmetic above on the structure of the persistent stride-1 kernel.  A CTA owns a
+// channel block and walks tiles of TQH x TQ quads (2 TQH x 2 TQ producer pixels) with a 2-stage ring: the gradient tile
+// (TQH+1 x TQ+1, the +1 row / column are the lower / right neighbours of the last quads; beyond the map the TMA unit
+// fills zeros) and the producer's raw-output tile of tile i+1 are in flight while tile i is computed, so the memory
+// system sees two bulk requests of ~40 KB per CTA instead of six 16-byte loads per thread (the quad kernel ran at 0.40
+// of the HBM peak on the 254 MB instance behind the stem: tools/time_ops.py).  Taps, BatchNorm constants and the two
+// running sums stay in registers across tiles (a thread's channel group is fixed).
+template <typename T, int TQH, int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
+dw_dgrad_s2_bnred_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmY,
+                             const float* __restrict__ w, T* __restrict__ g_out,
+                             int Hi, int Wi, int Ho, int Wo, int C, int CB, int TQ, int tiles_w, int tiles_h, int ntiles,
+                             uint32_t stage_bytes, uint32_t ytile_off,
+                             const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, int relu, float* __restrict__ sums) {
+    TSS_DYN_SMEM(uint8_t, smem_raw);
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    const int GW = TQ + 1;                                   // gradient tile width
+    const uint32_t gtile_bytes = (uint32_t)(TQH + 1) * GW * CB * sizeof(T);
+    const uint32_t ytile_bytes = (uint32_t)(2 * TQH) * (2 * TQ) * CB * sizeof(T);
+    uint64_t* bars = (uint64_t*)(smem + 2 * (size_t)stage_bytes);
+    float* s_sum = (float*)(bars + 2);                       // [2][CB]
+    float* s_w = s_sum + 2 * CB;                             // [9][CB] taps (not flipped: the quad formulas index them directly)
+    const int cb0 = blockIdx.y * CB;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(bars), 1);
+        mbar_init(smem_u32(bars + 1), 1);
+        mbar_fence_init();
+    }
+    dw_stage_taps<false>(w, cb0, CB, s_w);
+    for (int i = threadIdx.x; i < 2 * CB; i += blockDim.x) s_sum[i] = 0.f;
+    const int CGB = CB >> 3;
+    const int cg = threadIdx.x % CGB, col = threadIdx.x / CGB;
+    const int c0 = cb0 + cg * 8;
+    __syncthreads();
+    float2 wr[9][4];
+    dw_take_taps(s_w, CB, cg, wr);
+    if (threadIdx.x == 0) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmY); }
+    pdl_wait();
+
+    auto issue = [&](int tile, int stage) {
+        int t = tile;
+        const int tw = t % tiles_w; t /= tiles_w;
+        const int th = t % tiles_h;
+        const int n = t / tiles_h;
+        const uint32_t bar = smem_u32(bars + stage);
+        uint8_t* base = smem + (size_t)stage * stage_bytes;
+        mbar_expect_tx(bar, gtile_bytes + ytile_bytes);
+        tma_load_4d(smem_u32(base), &tmG, bar, cb0, tw * TQ, th * TQH, n);
+        tma_load_4d(smem_u32(base + ytile_off), &tmY, bar, cb0, 2 * tw * TQ, 2 * th * TQH, n);
+    };
+    int tile = blockIdx.x;
+    if (threadIdx.x == 0 && tile < ntiles) issue(tile, 0);
+
+    float2 sc[4], sh[4], s1[4], s2[4];
+    zero8p(s1); zero8p(s2);
+    {
+        float mu[8], rs[8], ga[8], be[8];
+        load8(mean + c0, mu);
+        load8(rstd + c0, rs);
+        if (gamma != nullptr) load8(gamma + c0, ga);
+        if (beta != nullptr) load8(beta + c0, be);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float a = (gamma != nullptr ? ga[e] : 1.f) * rs[e];
+            const float b = (beta != nullptr ? be[e] : 0.f) - mu[e] * a;
+            if (e & 1) { sc[e >> 1].y = a; sh[e >> 1].y = b; } else { sc[e >> 1].x = a; sh[e >> 1].x = b; }
+        }
+    }
+    const float2 zero2 = make_float2(0.f, 0.f);
+    // mask, accumulate (sum g and sum g*y; x-hat comes in at the end: sum g*xhat = rstd*(sum g*y - mean*sum g)) and store
+    // one producer pixel's 8 channels
+    auto emit = [&](float2 (&o)[4], const T* yptr, T* gptr) {
+        float2 yy[4];
+        load8p_smem(yptr, yy);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 z = ffma2(yy[e], sc[e], sh[e]);
+            if (relu && !(z.x > 0.f)) o[e].x = 0.f;
+            if (relu && !(z.y > 0.f)) o[e].y = 0.f;
+            s1[e].x += o[e].x;
+            s1[e].y += o[e].y;
+            s2[e] = ffma2(o[e], yy[e], s2[e]);
+        }
+        store8p(gptr, o);
+    };
+
+    for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+        const int stage = it & 1;
+        const int next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < ntiles) issue(next, stage ^ 1);    // released by the __syncthreads of iteration it-1
+        int t = tile;
+        const int tw = t % tiles_w; t /= tiles_w;
+        const int th = t % tiles_h;
+        const int n = t / tiles_h;
+        mbar_wait(smem_u32(bars + stage), (uint32_t)(it >> 1) & 1);
+        const T* gt = (const T*)(smem + (size_t)stage * stage_bytes) + (size_t)col * CB + cg * 8;
+        const T* yt = (const T*)(smem + (size_t)stage * stage_bytes + ytile_off) + (size_t)(2 * col) * CB + cg * 8;
+        const int q = tw * TQ + col;
+        if (q < Wo) {
+            const bool col1 = 2 * q + 1 < Wi;
+            float2 g0[2][4], g1[2][4];
+            load8p_smem(gt, g0[0]);
+            load8p_smem(gt + CB, g0[1]);
+#pragma unroll 1
+            for (int pl = 0; pl < TQH; ++pl) {
+                const int p = th * TQH + pl;
+                if (p >= Ho) break;
+                load8p_smem(gt + (size_t)(pl + 1) * GW * CB, g1[0]);
+                load8p_smem(gt + (size_t)(pl + 1) * GW * CB + CB, g1[1]);
+                const bool row1 = 2 * p + 1 < Hi;
+                const T* y0 = yt + (size_t)(2 * pl) * (2 * TQ) * CB;
+                const T* y1 = y0 + (size_t)(2 * TQ) * CB;
+                T* o0 = g_out + (((int64_t)n * Hi + 2 * p) * Wi + 2 * q) * C + c0;
+                T* o1 = o0 + (int64_t)Wi * C;
+                float2 o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = ffma2(g0[0][e], wr[4][e], zero2);
+                emit(o, y0, o0);
+                if (col1) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = ffma2(g0[1][e], wr[3][e], ffma2(g0[0][e], wr[5][e], zero2));
+                    emit(o, y0 + CB, o0 + C);
+                }
+                if (row1) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = ffma2(g1[0][e], wr[1][e], ffma2(g0[0][e], wr[7][e], zero2));
+                    emit(o, y1, o1);
+                    if (col1) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            o[e] = ffma2(g1[1][e], wr[0][e], ffma2(g1[0][e], wr[2][e], ffma2(g0[1][e], wr[6][e], ffma2(g0[0][e], wr[8][e], zero2))));
+                        emit(o, y1 + CB, o1 + C);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { g0[0][e] = g1[0][e]; g0[1][e] = g1[1][e]; }
+            }
+        }
+        __syncthreads();                       // everyone is done with this stage: it may be refilled
+    }
+    {
+        float mu[8], rs[8];
+        load8(mean + c0, mu);
+        load8(rstd + c0, rs);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float a = (e & 1) ? s1[e >> 1].y : s1[e >> 1].x;
+            const float b = (e & 1) ? s2[e >> 1].y : s2[e >> 1].x;
+            atomicAdd(&s_sum[cg * 8 + e], a);
+            atomicAdd(&s_sum[CB + cg * 8 + e], rs[e] * (b - mu[e] * a));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * CB; i += blockDim.x) {
+        const int which = i / CB, ch = i - which * CB;
+        const float v = s_sum[i];
+        if (v != 0.f) atomicAdd(sums + which * C + cb0 + ch, v);
+    }
+}
+
 int gcd_int2(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
 template <typename T> struct TmaTypeB;
@@ -415,6 +579,64 @@ extern "C" int tss_dwconv3x3_dgrad_s2_bnred(const void* dy, const float* w, void
     TSS_REQUIRE(yp != nullptr && mean != nullptr && rstd != nullptr && sums != nullptr, "dwconv3x3_dgrad_s2_bnred: missing BatchNorm operands");
     TSS_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)yp & 15) == 0, "dwconv3x3_dgrad_s2_bnred: buffers must be 16-byte aligned");
     const int Ho = (Hi - 1) / 2 + 1, Wo = (Wi - 1) / 2 + 1;
+    {
+        // bf16 with a TMA channel block: the persistent 2-stage TMA kernel (TSS_S2_TMA=0: the quad kernel below)
+        static const int tma_env = [] { const char* e = getenv("TSS_S2_TMA"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+        int CB, TQ;
+        TssEncodeTiledFn enc = tss_encode_tiled();
+        if (tma_env && dtype == TSS_BF16 && enc != nullptr && tss_dw_tma_config(C, &CB, &TQ) && (int64_t)N * Ho * Wo < (1ll << 30)) {
+            typedef bf16 T;
+            const int threads = (CB / 8) * TQ;
+            auto stage_of = [&](int tqh, size_t* yoff) {
+                const size_t gt = (size_t)(tqh + 1) * (TQ + 1) * CB * sizeof(T), yt = (size_t)(2 * tqh) * (2 * TQ) * CB * sizeof(T);
+                *yoff = (gt + 127) & ~(size_t)127;
+                return *yoff + ((yt + 127) & ~(size_t)127);
+            };
+            static const int tqh_env = [] { const char* e = getenv("TSS_S2_TQH"); return e ? atoi(e) : 0; }();
+            size_t yoff;
+            int tqh = 4;
+            if (tqh_env == 2 || 2 * stage_of(4, &yoff) > 100 * 1024) tqh = 2;      // two CTAs per SM
+            const size_t stage = stage_of(tqh, &yoff);
+            const size_t smem = 128 + 2 * stage + 16 + (size_t)11 * CB * sizeof(float);
+            CUtensorMap mg, my;
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            {
+                cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+                cuuint64_t gstr[3] = {(cuuint64_t)C * sizeof(T), (cuuint64_t)Wo * C * sizeof(T), (cuuint64_t)Ho * Wo * C * sizeof(T)};
+                cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(TQ + 1), (cuuint32_t)(tqh + 1), 1};
+                CUresult r = enc(&mg, TmaTypeB<T>::v, 4, const_cast<void*>(dy), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                TSS_REQUIRE(r == CUDA_SUCCESS, "dwconv3x3_dgrad_s2_bnred: cuTensorMapEncodeTiled (dy) failed (%d)", (int)r);
+            }
+            {
+                cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)N};
+                cuuint64_t gstr[3] = {(cuuint64_t)C * sizeof(T), (cuuint64_t)Wi * C * sizeof(T), (cuuint64_t)Hi * Wi * C * sizeof(T)};
+                cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(2 * TQ), (cuuint32_t)(2 * tqh), 1};
+                CUresult r = enc(&my, TmaTypeB<T>::v, 4, const_cast<void*>(yp), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                TSS_REQUIRE(r == CUDA_SUCCESS, "dwconv3x3_dgrad_s2_bnred: cuTensorMapEncodeTiled (yp) failed (%d)", (int)r);
+            }
+            const int tiles_w = (Wo + TQ - 1) / TQ, tiles_h = (Ho + tqh - 1) / tqh;
+            const int64_t ntiles = (int64_t)N * tiles_h * tiles_w;
+            const int cblocks = C / CB;
+            int64_t gx = ((int64_t)tss_num_sms() * 2) / cblocks;
+            if (gx > ntiles) gx = ntiles;
+            if (gx < 1) gx = 1;
+            // 128-thread blocks (C % 64 == 0, C % 32 == 0) may use 255 registers at two CTAs per SM, 192-thread ones 168
+            auto kern = threads <= 128 ? (tqh == 4 ? dw_dgrad_s2_bnred_tma_kernel<T, 4, 128> : dw_dgrad_s2_bnred_tma_kernel<T, 2, 128>)
+                                       : (tqh == 4 ? dw_dgrad_s2_bnred_tma_kernel<T, 4, 192> : dw_dgrad_s2_bnred_tma_kernel<T, 2, 192>);
+            static bool attr_set_t[4] = {false, false, false, false};
+            const int ki = (threads <= 128 ? 0 : 2) + (tqh == 4 ? 1 : 0);
+            if (!attr_set_t[ki]) {
+                TSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+                attr_set_t[ki] = true;
+            }
+            tss_launch(kern, dim3((unsigned)gx, (unsigned)cblocks), threads, smem, (cudaStream_t)stream, mg, my, w, (T*)g, Hi, Wi, Ho, Wo, C, CB, TQ,
+                       tiles_w, tiles_h, (int)ntiles, (uint32_t)stage, (uint32_t)yoff, mean, rstd, gamma, beta, flags & TSS_EPI_RELU, sums);
+            TSS_LAUNCH_CHECK("dwconv3x3_dgrad_s2_bnred(tma)");
+            return TSS_OK;
+        }
+    }
     constexpr int R = 4;
     const int CG = C / 8;
     const int64_t total = (int64_t)N * ((Ho + R - 1) / R) * Wo * CG;

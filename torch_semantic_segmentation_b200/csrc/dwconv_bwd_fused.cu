@@ -46,6 +46,7 @@ dw_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
         mbar_fence_init();
     }
     __syncthreads();
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmY); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();
     if (threadIdx.x == 0) {
         mbar_expect_tx(smem_u32(bar), 2 * tile_bytes);

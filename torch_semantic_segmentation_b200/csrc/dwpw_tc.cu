@@ -113,6 +113,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmB); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();
 
     if (warp == 0) {

@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "colsum.cuh"
 
 namespace {
 
@@ -147,6 +148,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     TSS_MARK(1);
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();          // everything above is on-chip setup; global memory is touched from here on
     TSS_MARK(2);
 
@@ -196,15 +198,18 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
             if (stats != nullptr) {                        // rows >= M are exact zeros (TMA zero fill)
-                float sq[16], sm[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { sm[i] = v[i]; sq[i] = v[i] * v[i]; }
-                const float s1 = warp_transpose_sum16(sm, lane);
-                const float s2 = warp_transpose_sum16(sq, lane);
-                if ((lane & 1) == 0) {                     // this warp's private slice: plain read-modify-write, one lane per column
+                // column sums through this warp's scratch (colsum.cuh), double-buffered: one __syncwarp per block.  The
+                // scratch aliases the pipeline stages, which are dead once the accumulator is complete (the launcher
+                // keeps the ring at >= 4 x 2 x kCsArray floats).
+                float* buf = reinterpret_cast<float*>(smem) + (q * 2 + ((c >> 4) & 1)) * kCsArray;
+                cs_store16(buf, lane, v);
+                __syncwarp();
+                float s1, s2;
+                cs_sum_sq(buf, lane, s1, s2);
+                if (lane < 16) {                           // this warp's private slice: plain read-modify-write, one lane per column
                     float* mine = s_stat + q * 2 * block_n;   // (a shared-memory float atomicAdd is a CAS spin loop in SASS)
-                    mine[c + (lane >> 1)] += s1;
-                    mine[block_n + c + (lane >> 1)] += s2;
+                    mine[c + lane] += s1;
+                    mine[block_n + c + lane] += s2;
                 }
             }
             if (row_ok) {
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(kThreads)
 pw_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         bf16* __restrict__ Y, int64_t M, int K, int64_t ldy, int block_n, int stages, uint32_t tmem_cols,
                         const float* __restrict__ scale, const float* __restrict__ shift, const bf16* __restrict__ res,
-                        int64_t ldr, int relu, double* __restrict__ stats, int stats_stride, int m_tiles) {
+                        int64_t ldr, int relu, double* __restrict__ stats, int stats_stride, int m_tiles, int cs_smem) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t b_bytes = (uint32_t)block_n * BK * 2;
@@ -283,7 +288,8 @@ pw_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     uint64_t* tmem_full = bars + 2 * stages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
-    float* s_stat = (float*)(tmem_slot + 2);                          // [4 epilogue warps][2][block_n]
+    float* s_stat = (float*)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);   // [4 epilogue warps][2][block_n]
+    float* cs_scratch = cs_smem ? s_stat + 8 * block_n : nullptr;     // [4 epilogue warps][kCsArray] (colsum.cuh)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * block_n;
@@ -311,6 +317,7 @@ pw_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();
 
     if (warp == 0) {
@@ -368,7 +375,20 @@ pw_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             for (int c = 0; c < block_n; c += 16) {
                 float v[16];
                 tmem_ld16(acc + (uint32_t)c, v);
-                if (stats != nullptr) {                    // rows >= M are exact zeros (TMA zero fill)
+                if (stats != nullptr && cs_scratch != nullptr) {     // rows >= M are exact zeros (TMA zero fill)
+                    // column sums through this warp's dedicated scratch (colsum.cuh; the ring is live here), single-buffered
+                    float* buf = cs_scratch + q * kCsArray;
+                    cs_store16(buf, lane, v);
+                    __syncwarp();
+                    float s1, s2;
+                    cs_sum_sq(buf, lane, s1, s2);
+                    __syncwarp();                          // the scratch may be rewritten
+                    if (lane < 16) {                       // this warp's private slice: plain read-modify-write
+                        float* mine = s_stat + q * 2 * block_n;
+                        mine[c + lane] += s1;
+                        mine[block_n + c + lane] += s2;
+                    }
+                } else if (stats != nullptr) {
                     float sq[16], sm[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { sm[i] = v[i]; sq[i] = v[i] * v[i]; }
@@ -493,6 +513,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmX); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();          // everything above is on-chip setup; global memory is touched from here on
 
     if (warp == 0) {
@@ -686,25 +707,31 @@ int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, 
         const int stages = stages_env > 0 ? stages_env : (num_kb == 1 ? 2 : 4);
         uint32_t tmem_cols = 32;
         while ((int)tmem_cols < 2 * bn) tmem_cols <<= 1;
-        const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 4) * 8 + 8 + 8 * bn * sizeof(float);
+        // statistics: column sums through a dedicated shared-memory scratch (TSS_PW_CS=0: the shuffle transposes)
+        static const int cs_env = [] { const char* e = getenv("TSS_PW_CS"); return e ? atoi(e) : 1; }();
+        const int cs_smem = (stats != nullptr && cs_env != 0) ? 1 : 0;
+        const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 4) * 8 + 8 + 16 + 8 * bn * sizeof(float) +
+                            (cs_smem ? (size_t)4 * kCsArray * sizeof(float) : 0);
         static bool attr_set_p = false;
         if (!attr_set_p) {
             TSS_CUDA(cudaFuncSetAttribute(pw_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr_set_p = true;
         }
         static const int per_sm_env = [] { const char* e = getenv("TSS_PW_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-        const int per_sm = per_sm_env > 0 ? per_sm_env : (stages <= 2 ? 4 : 2);
+        const int per_sm = per_sm_env > 0 ? per_sm_env : (stages <= 2 ? (cs_smem ? 3 : 4) : 2);      // (the scratch leaves room for 3)
         const int n_tiles = Nc / bn;
         int64_t gx = ((int64_t)tss_num_sms() * per_sm + n_tiles - 1) / n_tiles;     // resident CTAs shared by the column tiles
         if (gx > m_tiles) gx = m_tiles;
         if (gx < 1) gx = 1;
         dim3 grid((unsigned)gx, (unsigned)n_tiles);
         tss_launch(pw_tc_persistent_kernel, grid, kThreads, smem, st, tmA, tmB, (bf16*)y, M, K, ldy, bn, stages, tmem_cols, scale, shift,
-                   (const bf16*)res, ldr, flags & TSS_EPI_RELU, stats, Nc, (int)m_tiles);
+                   (const bf16*)res, ldr, flags & TSS_EPI_RELU, stats, Nc, (int)m_tiles, cs_smem);
         TSS_LAUNCH_CHECK("pwconv_fwd_tc(persistent)");
         return TSS_OK;
     }
-    const int stages = num_kb < 4 ? num_kb : 4;
+    int stages = num_kb < 4 ? num_kb : 4;
+    // the statistics epilogue's column-sum scratch (4 warps x 2 x kCsArray floats = 20 KB) aliases the ring
+    while (stats != nullptr && (size_t)stages * (kABytes + (size_t)bn * BK * 2) < (size_t)8 * kCsArray * sizeof(float)) ++stages;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < bn) tmem_cols <<= 1;
     const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 1) * 8 + 8 + 8 * bn * sizeof(float);

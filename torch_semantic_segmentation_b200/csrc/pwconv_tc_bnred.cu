@@ -7,12 +7,13 @@
 //   sums[C+c] += sum_m g * xhat,  xhat = (yp - mean) * rstd      (bn.cu: bn_bwd_reduce_kernel).
 // The dgrad epilogue already holds the dz tile in registers: it reads the matching yp tile (the ReLU
 // mask is recomputed from yp with the forward's arithmetic), stores g instead of dz and accumulates
-// the two sums with the same warp-transposed shuffle reduction the forward uses for its statistics.
+// the two sums through a warp-private shared-memory transposition (colsum.cuh).
 // The producer's BatchNorm backward then runs its apply pass only (no mask, no reduction): one full
 // read of dz and yp and one launch less per layer.  Main loop identical to pwconv_tc.cu.
 #include <stdlib.h>
 
 #include "tc_ptx.cuh"
+#include "colsum.cuh"
 
 namespace {
 
@@ -21,23 +22,7 @@ constexpr int BK = 64;           // bf16 elements per k-block = 128 bytes = one 
 constexpr int kThreads = 192;
 constexpr uint32_t kABytes = BM * BK * 2;
 
-// lanes 2j / 2j+1 end with the sum over the 32 lanes of v[j], j = lane >> 1
-__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
-#pragma unroll
-    for (int step = 16, n = 16; step >= 2; step >>= 1, n >>= 1) {
-        const bool upper = (lane & step) != 0;
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) {
-            const float send = upper ? v[i] : v[i + n / 2];
-            const float keep = upper ? v[i + n / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
-        }
-    }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
-
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)     // 4 x 192 threads x 85 registers: a whole 1/32-resolution layer (486 tiles) in one wave
 pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    bf16* __restrict__ G, int64_t M, int K, int64_t ldg, int block_n, int stages, uint32_t tmem_cols,
                    const bf16* __restrict__ yp, int64_t ldyp, const float* __restrict__ mean,
@@ -50,7 +35,7 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint8_t* sB = smem + (size_t)stages * kABytes;
     uint64_t* bars = (uint64_t*)(sB + (size_t)stages * b_bytes);     // full[stages], empty[stages], tmem_full
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * stages + 1);
-    float* s_stat = (float*)(tmem_slot + 2);                          // [4 epilogue warps][2][block_n]
+    float* s_stat = (float*)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);   // [4 epilogue warps][2][block_n]
     float* s_const = s_stat + 8 * block_n;                            // [4][block_n]: mean, rstd, scale, shift
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,8 +57,20 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int i = threadIdx.x; i < 8 * block_n; i += kThreads) s_stat[i] = 0.f;
     TSS_MARK(1);
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();
     TSS_MARK(2);
+    // the first pass over the ring needs no empty-slot wait: thread 0 (which initialised the barriers) issues those loads
+    // NOW, so that they fly while the CTA fetches the BatchNorm constants and meets at the barrier below (~1.5 us)
+    const int pre_kb = num_kb < stages ? num_kb : stages;
+    if (threadIdx.x == 0) {
+        for (int kb = 0; kb < pre_kb; ++kb) {
+            const uint32_t full = smem_u32(bars + kb);
+            mbar_expect_tx(full, kABytes + b_bytes);
+            tma_load_2d(smem_u32(sA + (size_t)kb * kABytes), &tmA, full, kb * BK, (int)m0);
+            tma_load_2d(smem_u32(sB + (size_t)kb * b_bytes), &tmB, full, kb * BK, n0);
+        }
+    }
     for (int i = threadIdx.x; i < block_n; i += kThreads) {           // per-column constants of the producer's BatchNorm
         const float mu = __ldg(mean + n0 + i), rs = __ldg(rstd + n0 + i);
         const float sc = (gamma != nullptr ? __ldg(gamma + n0 + i) : 1.f) * rs;
@@ -89,7 +86,7 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {                                   // ---------------- TMA producer
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = pre_kb; kb < num_kb; ++kb) {
                 const int s = kb % stages;
                 const uint32_t phase = (kb / stages) & 1;
                 mbar_wait(smem_u32(bars + stages + s), phase ^ 1);
@@ -137,6 +134,11 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(smem_u32(bars + 2 * stages), 0);
         TSS_MARK_IF(threadIdx.x == 64, 6);
         tc_fence_after();
+        // column sums through this warp's scratch: the pipeline stages are dead once the accumulator is complete (every
+        // TMA write has landed and every MMA has read its operands), so the scratch aliases them (the launcher keeps
+        // the ring at >= 4 x kCsPair floats)
+        float* scratch = reinterpret_cast<float*>(smem) + q * kCsPair;
+        float* mine = s_stat + q * 2 * block_n;            // this warp's private slice: plain read-modify-write
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
             const int c = cc * 16;
@@ -147,26 +149,26 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             float y0[8], y1[8];
             unpack8(ypre[2 * cc], y0);
             unpack8(ypre[2 * cc + 1], y1);
-            float gx[16];
+            float gx[16];                                  // g * (yp - mean); rstd comes in once per column at the end
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float yy = i < 8 ? y0[i] : y1[i - 8];
-                const float mu = s_const[c + i], rs = s_const[block_n + c + i];
-                if (relu && !(fmaf(yy, s_const[2 * block_n + c + i], s_const[3 * block_n + c + i]) > 0.f)) v[i] = 0.f;
-                gx[i] = v[i] * ((yy - mu) * rs);
-            }
-            {
-                float sm[16];
+            for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 mu4 = *reinterpret_cast<const float4*>(s_const + c + 4 * i4);
+                const float4 sc4 = *reinterpret_cast<const float4*>(s_const + 2 * block_n + c + 4 * i4);
+                const float4 sh4 = *reinterpret_cast<const float4*>(s_const + 3 * block_n + c + 4 * i4);
+                const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
 #pragma unroll
-                for (int i = 0; i < 16; ++i) sm[i] = v[i];
-                const float s1 = warp_transpose_sum16(sm, lane);
-                const float s2 = warp_transpose_sum16(gx, lane);
-                if ((lane & 1) == 0) {                     // this warp's private slice: plain read-modify-write, one lane per column
-                    float* mine = s_stat + q * 2 * block_n;   // (a shared-memory float atomicAdd is a CAS spin loop in SASS)
-                    mine[c + (lane >> 1)] += s1;
-                    mine[block_n + c + (lane >> 1)] += s2;
+                for (int e = 0; e < 4; ++e) {
+                    const int i = 4 * i4 + e;
+                    const float yy = i < 8 ? y0[i] : y1[i - 8];
+                    if (relu && !(fmaf(yy, sc[e], sh[e]) > 0.f)) v[i] = 0.f;
+                    gx[i] = v[i] * (yy - mu[e]);
                 }
             }
+            cs_store16(scratch, lane, v);
+            cs_store16(scratch + kCsArray + 16, lane, gx);
+            __syncwarp();
+            mine[(lane >> 4) * block_n + c + (lane & 15)] += cs_sum_pair(scratch, lane);   // lanes 0..15: sum g, 16..31: sum g (yp - mean)
+            __syncwarp();                                  // the scratch may be rewritten
             if (row_ok) {
                 uint32_t o[8];
 #pragma unroll
@@ -183,8 +185,8 @@ pw_tc_bnred_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     TSS_MARK(8);
     for (int i = threadIdx.x; i < block_n; i += kThreads) {
         atomicAdd(sums + n0 + i, (s_stat[i] + s_stat[2 * block_n + i]) + (s_stat[4 * block_n + i] + s_stat[6 * block_n + i]));
-        atomicAdd(sums + sums_stride + n0 + i,
-                  (s_stat[block_n + i] + s_stat[3 * block_n + i]) + (s_stat[5 * block_n + i] + s_stat[7 * block_n + i]));
+        atomicAdd(sums + sums_stride + n0 + i, s_const[block_n + i] *
+                  ((s_stat[block_n + i] + s_stat[3 * block_n + i]) + (s_stat[5 * block_n + i] + s_stat[7 * block_n + i])));
     }
     TSS_MARK(9);
     if (warp == 1) {
@@ -238,10 +240,11 @@ extern "C" int tss_pwconv_dgrad_bnred(const void* dy, const void* wpT, void* g, 
     if (int e = make_map_bnred(&tmA, dy, M, Nc, lddy, BM)) return e;
     if (int e = make_map_bnred(&tmB, wpT, K, Nc, Nc, bn)) return e;
     const int num_kb = (Nc + BK - 1) / BK;
-    const int stages = num_kb < 4 ? num_kb : 4;
+    int stages = num_kb < 4 ? num_kb : 4;
+    if (stages < 2) stages = 2;        // the epilogue's column-sum scratch (4 x kCsPair floats = 20.3 KB) aliases the ring
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < bn) tmem_cols <<= 1;
-    const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 1) * 8 + 8 + 12 * bn * sizeof(float);
+    const size_t smem = 1024 + (size_t)stages * (kABytes + (size_t)bn * BK * 2) + (2 * stages + 1) * 8 + 8 + 16 + 12 * bn * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         TSS_CUDA(cudaFuncSetAttribute(pw_tc_bnred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -86,6 +86,7 @@ pw_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmB, const bf16* __restrict
         tc_alloc(smem_u32(tmem_slot), tmem_cols);
     }
     for (int i = threadIdx.x; i < 2 * block_n; i += kThreads) s_stat[i] = 0.f;
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmB); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();
     // this layer's BatchNorm backward as dy = A*g + B*y + D per channel (A = gamma*rstd, B = -rstd*k2,
     // D = mean*rstd*k2 - k1 with k1 = A*sum(g)/m, k2 = A*sum(g*xhat)/m), and SH for the ReLU mask fma(y, A, SH) > 0

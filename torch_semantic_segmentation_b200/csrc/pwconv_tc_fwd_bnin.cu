@@ -75,6 +75,7 @@ pw_tc_fwd_bnin_kernel(const __grid_constant__ CUtensorMap tmB, const bf16* __res
     }
     if (warp == 1) tc_alloc(smem_u32(tmem_slot), tmem_cols);
     for (int i = threadIdx.x; i < 2 * block_n; i += kThreads) s_stat[i] = 0.f;
+    if (threadIdx.x == 0) {tma_prefetch_desc(&tmB); }      // descriptor fetch (~0.5 us) under the predecessor's tail
     pdl_wait();
     for (int c = threadIdx.x; c < KP; c += kThreads) {
         s_c[c] = c < K ? __ldg(in_scale + c) : 0.f;
