@@ -24,7 +24,8 @@ SLOTS, MAX_CTAS = 16, 65536
 MARKS = {
     'pw': {0: 'entry', 1: 'setup done (before griddepcontrol.wait)', 2: 'predecessor complete', 3: 'producer: last TMA issued',
            4: 'MMA: first stage landed', 5: 'MMA: accumulator committed', 10: 'epilogue: row of yp requested', 6: 'epilogue: accumulator ready',
-           7: 'epilogue: tile stored', 8: 'CTA joined', 9: 'statistics atomics issued'},
+           7: 'epilogue: tile stored', 8: 'CTA joined', 9: 'statistics atomics issued', 11: 'epilogue: first tcgen05.ld complete',
+           12: 'epilogue: first 16 columns reduced', 13: 'epilogue: first 16 columns stored'},
     'dw': {0: 'entry', 1: 'setup done (before griddepcontrol.wait)', 2: 'predecessor complete', 3: 'weights requested', 4: 'tile 0 landed',
            5: 'tile 0 computed', 6: 'tile 0 stored', 7: 'tile 1 landed', 8: 'tile 1 computed', 9: 'tile 1 stored', 10: 'tile 2 landed',
            11: 'tile 2 computed', 12: 'tile 2 stored', 13: 'all tiles done', 14: 'statistics atomics issued'},

@@ -269,6 +269,28 @@ template <> struct Raw8<float> {
     }
 };
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one full 32-byte sector per thread and request.  A tensor-core
+// epilogue thread owns a ROW of the tile, so a warp-wide access touches 32 different lines whatever its width; the
+// 256-bit form halves the number of requests the SM sends to L2 for the same bytes.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+#ifndef TSS_HOST_EMU
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+#else
+    a = reinterpret_cast<const uint4*>(p)[0];
+    b = reinterpret_cast<const uint4*>(p)[1];
+#endif
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+#ifndef TSS_HOST_EMU
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+#else
+    reinterpret_cast<uint4*>(p)[0] = a;
+    reinterpret_cast<uint4*>(p)[1] = b;
+#endif
+}
+
 __device__ __forceinline__ void zero8(float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;

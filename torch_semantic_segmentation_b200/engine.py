@@ -260,7 +260,11 @@ def _capture_stream(dev):
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     st = _capture_streams.get(key)
     if st is None:
-        st = _capture_streams[key] = torch.cuda.Stream(dev)
+        # TSS_MAIN_PRIORITY=1 gives the stream of the step's critical chain a high priority (captured kernel nodes inherit it)
+        # over the weight-gradient lane and the all-reduce stream.  Measured on B200: 3.51 against 3.43 ms/step -- the side
+        # kernels are pushed behind the chain and leave a longer tail than the dispatch stalls they cause; off by default.
+        prio = -1 if os.environ.get('TSS_MAIN_PRIORITY', '0') == '1' else 0
+        st = _capture_streams[key] = torch.cuda.Stream(dev, priority=prio)
     return st
 
 
