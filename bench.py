@@ -43,6 +43,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of a CUDA graph')
     ap.add_argument('--kernels', action='store_true', help='also dump the per-kernel table to stderr')
+    ap.add_argument('--step-only', action='store_true',
+                    help='A/B aid: print the device-timed step alone (no end-to-end leg, no kernel table) and leave')
     ap.add_argument('--headline-only', action='store_true',
                     help='skip the 1024x2048 training leg, the 500-map mIoU leg and the bs1 inference leg (A/B runs)')
     ap.add_argument('--e2e-fp32', action='store_true',
@@ -208,6 +210,8 @@ def kernel_family(op):
         return 'dw_tma_kernel (depthwise fwd + stride-1 dgrad)'
     if op.startswith('bn_bwd_reduce'):
         return 'bn_bwd_reduce_kernel (BatchNorm backward, stand-alone reduction)'
+    if op.startswith('bn_bwd_onepass'):
+        return 'bn_bwd_onepass_kernel (BatchNorm backward, both passes in one launch)'
     if op.startswith('bn_bwd_apply'):
         return 'bn_bwd_apply_kernel (BatchNorm backward apply)'
     if op.startswith('bn_apply'):
@@ -271,10 +275,22 @@ def kernel_table(device, runner=None):
         scb = torch.ones(C, device=device)
         sums = torch.zeros(2 * C, device=device)
         add('bn_apply %dch@1/%d' % (C, div), cnt, 2 * 2 * C * px(div), lambda: ops.bn_apply(yb, scb, scb, relu=True))
+        # layers that run their own reduction: one launch for both passes where dz + y stay in L2 (gate BN_BWD_ONEPASS);
+        # the row is timed either way (0 launches per step when the gate is off: tools/time_ops.py A/B)
+        onepass = bool(cnt_red) and ops.BN_BWD_ONEPASS and 2 * 2 * C * px(div) <= ops._ONEPASS_MAX_BYTES
         if cnt_red:
-            add('bn_bwd_reduce %dch@1/%d' % (C, div), cnt_red, 2 * 2 * C * px(div),
+            add('bn_bwd_reduce %dch@1/%d' % (C, div), 0 if onepass else cnt_red, 2 * 2 * C * px(div),
                 lambda: ops.bn_backward_reduce(gb, yb, scb, scb, scb, scb, True, sums))
-        add('bn_bwd_apply %dch@1/%d' % (C, div), cnt, 2 * 3 * C * px(div),
+
+            def both_passes():
+                keep, ops.BN_BWD_ONEPASS = ops.BN_BWD_ONEPASS, True
+                try:
+                    ops.bn_backward(gb, None, yb, scb, scb, scb, True, beta=scb, sums=sums)
+                finally:
+                    ops.BN_BWD_ONEPASS = keep
+            if 2 * 2 * C * px(div) <= ops._ONEPASS_MAX_BYTES:
+                add('bn_bwd_onepass %dch@1/%d' % (C, div), cnt_red if onepass else 0, 2 * 3 * C * px(div), both_passes)
+        add('bn_bwd_apply %dch@1/%d' % (C, div), cnt - (cnt_red if onepass else 0), 2 * 3 * C * px(div),
             lambda: ops.bn_backward(gb, None, yb, scb, scb, scb, False, beta=scb, sums=sums, prereduced=True))
     # depthwise: every shape of the network (channels, input level, stride, dilation, layers of that shape)
     for C, div, s, d, cnt in [(32, 2, 2, 1, 1), (48, 4, 2, 1, 1), (384, 8, 2, 1, 1), (384, 16, 1, 1, 2), (384, 16, 2, 1, 1),
@@ -561,6 +577,17 @@ def main():
         launches = graphed.kernels_per_step * args.steps
     ms_total = float(ms)
     value = world * BATCH * args.steps / (ms_total / 1e3)
+
+    if args.step_only:
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                              'ms_per_step': ms_total / args.steps, 'gpu_launches': launches, 'step_only': True,
+                              'gates': sorted('%s=%s' % (k, v) for k, v in os.environ.items() if k.startswith('TSS_'))}))
+        sampler.stop() if rank == 0 else None
+        sys.stdout.flush()
+        if world > 1:
+            os._exit(0)
+        return
 
     # ---- end to end: the public engine API, batch in pinned host memory -------------------
     e2e_input = 'fp32 crops + int64 labels (what the reference DataLoader yields)'

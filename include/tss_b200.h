@@ -272,6 +272,17 @@ int tss_bn_bwd_apply(const void* dz, const void* z, const void* y, const float* 
                      const float* rstd, const float* gamma, const float* beta, const float* sums, void* dy, void* dres,
                      float* dgamma, float* dbeta, int64_t M, int64_t count, int C, int64_t lddz, int64_t ldz,
                      int64_t ldy, int64_t lddy, int64_t lddres, int flags, int dtype, void* stream);
+/* backward, both passes in ONE launch (replaces the reduce + apply pair behind nn.BatchNorm2d's autograd,
+ * fastscnn.py:169, for tensors small enough to stay in L2 between the passes): pass 1 accumulates sums[2*C] (zeroed by
+ * the caller) exactly like tss_bn_bwd_reduce (z == NULL under TSS_EPI_RELU: mask recomputed from y), a grid-wide
+ * barrier, pass 2 writes dy (and dres = g when given) like tss_bn_bwd_apply with count = M, dgamma / dbeta accumulated
+ * by block 0.  sync: DEVICE int32 [4], zeroed once by the caller and owned by ONE stream: {arrivals, generation, sticky
+ * time-out flag, unused}; launches that share it must be stream-ordered.  All CTAs are resident at once (the grid is
+ * capped at two per SM); a CTA that waits for more than about a second sets sync[2] and nobody waits any more. */
+int tss_bn_bwd_onepass(const void* dz, const void* z, const void* y, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, float* sums, void* dy, void* dres, float* dgamma,
+                       float* dbeta, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy, int64_t lddy,
+                       int64_t lddres, int flags, int* sync, int dtype, void* stream);
 /* g = dz * (z > 0): ReLU backward alone (fusion add, eval-free paths) */
 int tss_relu_bwd(const void* dz, const void* z, void* g, int64_t M, int C, int64_t lddz, int64_t ldz,
                  int64_t ldg, int dtype, void* stream);

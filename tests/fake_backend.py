@@ -456,6 +456,13 @@ class FakeBackend:
             dgamma += sums[C:]
         return 0
 
+    def tss_bn_bwd_onepass(self, dz, z, y, mean, rstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C, lddz, ldz, ldy, lddy,
+                           lddres, flags, sync, dtype):
+        assert sync.dtype == torch.int32 and sync.numel() >= 4 and int(sync[2]) == 0
+        self.tss_bn_bwd_reduce(dz, z, y, mean, rstd, gamma, beta, sums, M, C, lddz, ldz, ldy, flags, dtype)
+        return self.tss_bn_bwd_apply(dz, z, y, mean, rstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, 0, C, lddz, ldz,
+                                     ldy, lddy, lddres, flags, dtype)
+
     def tss_relu_bwd(self, dz, z, g, M, C, lddz, ldz, ldg, dtype):
         g.copy_(dz.float() * (z.float() > 0))
         return 0

@@ -23,6 +23,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 #define __grid_constant__
@@ -136,6 +137,7 @@ inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsi
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return std::atomic_ref<unsigned long long>(*p).fetch_add(v); }
 
 template <typename V> inline V __ldg(const V* p) { return *p; }
+template <typename V> inline V __ldcg(const V* p) { return *p; }
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return {fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }

@@ -271,6 +271,45 @@ def test_training_step_with_grouped_pyramid_pooling_matches_default():
     assert rel(out[True][1], out[False][1]) < 1e-4 and rel(out[True][2], out[False][2]) < 1e-3
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_training_step_with_one_launch_batchnorm_backward_matches_default(dtype):
+    """BN_BWD_ONEPASS: every stand-alone reduce + apply pair of the step becomes one launch with a grid barrier; same loss
+    and gradients (fp32: to rounding of the atomics' order), fewer launches, and no barrier ever timed out."""
+    from oracle.golden_inputs import train_batch
+    from torch_semantic_segmentation_b200 import ops
+    from torch_semantic_segmentation_b200.losses import CrossEntropyLoss
+    from torch_semantic_segmentation_b200.models import fastscnn
+    x, y = train_batch('fastscnn')
+    out = {}
+    keep = ops.BN_BWD_ONEPASS
+    for flag in (False, True):
+        ops.BN_BWD_ONEPASS = flag
+        try:
+            torch.manual_seed(0)
+            model = fastscnn(3, 19).cuda().set_compute_dtype(dtype).train()
+            for m in model.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+            before = _lib.launch_count()
+            for _ in range(2):
+                model.zero_grad()
+                logits = model(x.cuda())
+                loss = CrossEntropyLoss(ignore_index=255)(logits, y.cuda())
+                loss.backward()
+            torch.cuda.synchronize()
+            out[flag] = (float(loss), logits.detach().float(), model.classifier[3].weight.grad.clone(),
+                         model.downsample[0][0].weight.grad.clone(), _lib.launch_count() - before)
+        finally:
+            ops.BN_BWD_ONEPASS = keep
+    assert not ops.grid_sync_timed_out()
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert abs(out[True][0] - out[False][0]) <= tol * abs(out[False][0])
+    assert rel(out[True][1], out[False][1]) < tol and rel(out[True][2], out[False][2]) < 10 * tol
+    if dtype == torch.float32:
+        assert rel(out[True][3], out[False][3]) < 5e-2          # the stem's gradient: 45 layers of amplified atomics noise
+    assert out[True][4] <= out[False][4] - 2 * 10, (out[True][4], out[False][4])
+
+
 def test_training_step_with_finalize_folded_into_apply_matches_default():
     from oracle.golden_inputs import train_batch
     from torch_semantic_segmentation_b200 import functional as Fn

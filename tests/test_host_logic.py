@@ -394,6 +394,44 @@ def test_all_gates_together_train_and_eval(fake_backend, arch):
     assert runs[True][2] < runs[False][2] - 100
 
 
+@pytest.mark.parametrize('arch', ['fastscnn', 'contextnet14'])
+def test_one_launch_batchnorm_backward_replaces_reduce_apply_pairs(fake_backend, arch):
+    """ops.BN_BWD_ONEPASS: wherever the BatchNorm backward would run its own reduction (no fused reduction in a consumer,
+    no activated tensor, no residual output, no SyncBN) and the tensors are small enough, ONE tss_bn_bwd_onepass call
+    replaces the tss_bn_bwd_reduce + tss_bn_bwd_apply pair: identical gradients on the emulated ABI."""
+    from torch_semantic_segmentation_b200 import ops
+    from torch_semantic_segmentation_b200.models.contextnet import contextnet14
+    factory = {'fastscnn': fastscnn, 'contextnet14': contextnet14}[arch]
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(2, 3, 64, 96, generator=g), torch.randint(0, 19, (2, 64, 96), generator=g)
+    inner, keep, runs = fake_backend.call, ops.BN_BWD_ONEPASS, {}
+    try:
+        for on in (False, True):
+            ops.BN_BWD_ONEPASS = on
+            calls = {}
+
+            def counting(name, kwargs, calls=calls):
+                calls[name] = calls.get(name, 0) + 1
+                return inner(name, kwargs)
+            fake_backend.call = counting
+            torch.manual_seed(0)
+            model = _no_dropout(factory(3, 19)).train()
+            loss = CrossEntropyLoss(ignore_index=255)(model(x), y)
+            loss.backward()
+            runs[on] = (float(loss), [p.grad.clone() for p in model.parameters()], calls)
+    finally:
+        ops.BN_BWD_ONEPASS = keep
+        fake_backend.call = inner
+    off, on = runs[False][2], runs[True][2]
+    n = on.get('tss_bn_bwd_onepass', 0)
+    assert n >= 10 and 'tss_bn_bwd_onepass' not in off
+    assert on.get('tss_bn_bwd_reduce', 0) == off['tss_bn_bwd_reduce'] - n
+    assert on['tss_bn_bwd_apply'] == off['tss_bn_bwd_apply'] - n
+    assert runs[True][0] == runs[False][0]
+    for a, b in zip(runs[True][1], runs[False][1]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize('loss_name', ['ce', 'ohem'])
 def test_deferred_logits_give_the_same_step_without_the_upsampling(fake_backend, loss_name):
     """functional.DEFER_LOGITS (off by default): in training the model hands the fused head its 1/8 scores directly;

@@ -256,6 +256,74 @@ def test_batchnorm_family(C, N, H, W, dtype):
 
 
 @pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('C,N,H,W,mask,pitch', [(128, 12, 96, 96, 'y', None), (64, 12, 48, 48, 'z', None), (96, 12, 24, 24, 'z', 104),
+                                                (128, 12, 24, 24, 'y', None), (48, 3, 9, 5, 'y', 56), (768, 2, 3, 4, 'none', None),
+                                                (8, 1, 1, 1, 'z', None), (384, 2, 40, 40, 'y', None), (64, 12, 96, 96, 'none', None)])
+def test_batchnorm_backward_in_one_launch(C, N, H, W, mask, pitch, dtype):
+    """tss_bn_bwd_onepass (pass 1 -> grid barrier -> pass 2, up to 296 resident CTAs) against the reduce + apply pair of
+    the torch emulation AND against this library's own two launches; launched several times back to back (the barrier
+    re-arms itself) and replayed from a CUDA graph with a dependent launch behind it; the time-out flag must stay clear."""
+    g = gen(C + H)
+    code = _lib.dtype_code(dtype)
+    M, ld = N * H * W, C if pitch is None else pitch
+    relu, use_z = int(mask != 'none'), mask == 'z'
+    dzc, dzg = pair(N, C, H, W, dtype, g, pitch)
+    yc, yg = pair(N, C, H, W, dtype, g, pitch)
+    zc, zg = pair(N, C, H, W, dtype, g, pitch)
+    if not use_z:
+        zc = zg = None
+    mean, rstd = torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    par_g = dict(mean=mean.cuda(), rstd=rstd.cuda(), gamma=gamma.cuda(), beta=beta.cuda())
+    new = lambda: torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2)
+    sums_c, dgc, dbc, dyc, drc = torch.zeros(2 * C), torch.ones(C), torch.ones(C), new(), new() if use_z else None
+    geo = dict(M=M, C=C, lddz=ld, ldz=ld if use_z else 0, ldy=ld, flags=relu, dtype=code)
+    FakeBackend().call('tss_bn_bwd_onepass', dict(dz=dzc, z=zc, y=yc, mean=mean, rstd=rstd, gamma=gamma, beta=beta, sums=sums_c,
+                                                  dy=dyc, dres=drc, dgamma=dgc, dbeta=dbc, lddy=C, lddres=C,
+                                                  sync=torch.zeros(4, dtype=torch.int32), **geo))
+    # this library's two launches
+    sums_2, dy2 = torch.zeros(2 * C).cuda(), new().cuda()
+    _lib.backend().call('tss_bn_bwd_reduce', dict(dz=dzg, z=zg, y=yg, sums=sums_2, **par_g, **geo))
+    _lib.backend().call('tss_bn_bwd_apply', dict(dz=dzg, z=zg, y=yg, sums=sums_2, dy=dy2, dres=None, dgamma=None, dbeta=None,
+                                                 lddy=C, lddres=C, count=0, **par_g, **geo))
+    sync = torch.zeros(4, dtype=torch.int32).cuda()
+    sums_g, dgg, dbg, dyg, drg = torch.zeros(2 * C).cuda(), torch.ones(C).cuda(), torch.ones(C).cuda(), new().cuda(), new().cuda() if use_z else None
+    args = dict(dz=dzg, z=zg, y=yg, sums=sums_g, dy=dyg, dres=drg, dgamma=dgg, dbeta=dbg, lddy=C, lddres=C, sync=sync, **geo, **par_g)
+
+    def check(tag):
+        torch.cuda.synchronize()
+        state = sync.cpu().tolist()
+        assert state[2] == 0 and state[0] == 0, (tag, state)
+        assert rel(sums_g, sums_c) < 1e-4, (tag, rel(sums_g, sums_c))
+        assert rel(dyg, dyc) < TOL[dtype], (tag, rel(dyg, dyc))
+        assert rel(dyg, dy2) < (1e-5 if dtype == torch.float32 else 1e-2), (tag, rel(dyg, dy2))
+        assert rel(dgg, dgc) < 1e-4 and rel(dbg, dbc) < 1e-4, tag
+        if use_z:
+            assert torch.equal(drg.cpu(), drc), tag
+
+    def reset():
+        sums_g.zero_(); dgg.fill_(1.0); dbg.fill_(1.0); dyg.zero_()
+
+    for i in range(3):
+        reset()
+        _lib.backend().call('tss_bn_bwd_onepass', args)
+        check('launch %d' % i)
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=st):
+            reset()
+            _lib.backend().call('tss_bn_bwd_onepass', args)
+            _lib.backend().call('tss_add', dict(a=dyg, b=None, out=dy2, M=M, C=C, lda=C, ldb=0, ldo=C, dtype=code))   # a dependent launch
+    torch.cuda.current_stream().wait_stream(st)
+    for i in range(3):
+        graph.replay()
+        check('replay %d' % i)
+    assert torch.equal(dy2, dyg)
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
 def test_elementwise_helpers(dtype):
     g = gen(2)
     code = _lib.dtype_code(dtype)

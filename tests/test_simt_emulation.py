@@ -22,7 +22,7 @@ EMU = os.path.join(ROOT, 'tests', 'simt_emu')
 FULL_EXCLUDE = ('pwconv_tc.cu', 'dwpw_tc.cu', 'api.cu')       # raw-asm tcgen05 GEMMs not converted yet; api.cu's role is emu_runtime.cpp
 SOURCES = ['ppm.cu', 'augment.cu', 'dwconv_bnred.cu',        # dwconv_bnred.cu: the stride-2 (plain SIMT) kernel only
            'bn_fused.cu', 'pwconv_tc_bwd.cu', 'stem_tc.cu', 'dwconv_bwd_fused.cu', 'metrics.cu', 'dropout.cu', 'dwconv_bnin.cu', 'pwconv_tc_fwd_bnin.cu',
-           'pwconv_tc_bnred.cu', 'dwconv.cu', 'dwconv_tma.cu']       # validated on the B200: calibrate the emulation itself                               # on the functional tcgen05/TMA/mbarrier emulation
+           'pwconv_tc_bnred.cu', 'dwconv.cu', 'dwconv_tma.cu', 'bn.cu']       # validated on the B200: calibrate the emulation itself                               # on the functional tcgen05/TMA/mbarrier emulation
 
 
 def rel(a, b):
@@ -567,6 +567,65 @@ def test_stem_weight_gradient_with_bn_apply_on_the_tcgen05_emulation(emulated, N
         outs[name] = (dw - 0.25, dga, dbe)
     assert rel(outs['emu'][0], outs['ref'][0]) < 5e-3
     assert rel(outs['emu'][1], outs['ref'][1]) < 1e-6 and rel(outs['emu'][2], outs['ref'][2]) < 1e-6
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('C,N,H,W,mask', [(128, 2, 12, 20, 'y'), (96, 1, 9, 40, 'none'), (64, 3, 7, 5, 'z'), (8, 1, 1, 1, 'y'),
+                                          (384, 1, 5, 7, 'y'), (48, 2, 33, 17, 'z'), (576, 1, 3, 4, 'none')])
+def test_batchnorm_backward_reduction_on_the_simt_emulation(emulated, C, N, H, W, mask, dtype):
+    """csrc/bn.cu, the reduction pass: (channel group, row lane) threads, U rows in flight, the three mask modes, lanes
+    summed through the [PL][C] shared-memory array, pitched operands."""
+    g = torch.Generator().manual_seed(C + H + W)
+    pitch = C + 16
+    wide = lambda: torch.randn(N, H, W, pitch, generator=g).to(dtype)
+    dzb, yb, zb = wide(), wide(), wide()
+    dz, y, z = (t[..., 8:8 + C].permute(0, 3, 1, 2) for t in (dzb, yb, zb))
+    mean, rstd = torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    M, code = N * H * W, _lib.dtype_code(dtype)
+    out = {}
+    for name, be in (('ref', FakeBackend()), ('emu', emulated)):
+        sums = torch.full((2 * C,), 0.25)
+        be.call('tss_bn_bwd_reduce', dict(dz=dz, z=z if mask == 'z' else None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta,
+                                          sums=sums, M=M, C=C, lddz=pitch, ldz=pitch if mask == 'z' else 0, ldy=pitch,
+                                          flags=0 if mask == 'none' else 1, dtype=code))
+        out[name] = sums
+    assert rel(out['emu'], out['ref']) < 2e-5, rel(out['emu'], out['ref'])
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('C,N,H,W,mask', [(128, 2, 12, 20, 'y'), (96, 1, 9, 40, 'none'), (64, 3, 7, 5, 'z'), (8, 1, 1, 1, 'y'),
+                                          (384, 1, 5, 7, 'y'), (576, 1, 3, 4, 'none'), (48, 2, 33, 17, 'z'), (96, 2, 7, 9, 'z')])
+def test_batchnorm_backward_in_one_launch_on_the_simt_emulation(emulated, C, N, H, W, mask, dtype):
+    """csrc/bn.cu, tss_bn_bwd_onepass: pass 1 -> (grid barrier: the emulation runs its single CTA) -> pass 2 walking the
+    thread's rows backwards, all three mask modes, dres for the residual layers; against the reduce + apply pair of the
+    torch emulation."""
+    g = torch.Generator().manual_seed(C + H + W)
+    pitch = C + 8
+    wide = lambda: torch.randn(N, H, W, pitch, generator=g).to(dtype)
+    dzb, yb, zb = wide(), wide(), wide()
+    dz, y, z = (t[..., :C].permute(0, 3, 1, 2) for t in (dzb, yb, zb))
+    mean, rstd = torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    M, code = N * H * W, _lib.dtype_code(dtype)
+    out = {}
+    for name, be in (('ref', FakeBackend()), ('emu', emulated)):
+        sums, dgamma, dbeta = torch.zeros(2 * C), torch.ones(C), torch.ones(C)
+        dy = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2)
+        dres = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2) if mask == 'z' else None
+        sync = torch.zeros(4, dtype=torch.int32)
+        be.call('tss_bn_bwd_onepass', dict(dz=dz, z=z if mask == 'z' else None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta,
+                                           sums=sums, dy=dy, dres=dres, dgamma=dgamma, dbeta=dbeta, M=M, C=C, lddz=pitch,
+                                           ldz=pitch if mask == 'z' else 0, ldy=pitch, lddy=C, lddres=C,
+                                           flags=0 if mask == 'none' else 1, sync=sync, dtype=code))
+        assert int(sync[2]) == 0 and int(sync[0]) == 0
+        out[name] = (dy.float(), sums, dgamma, dbeta, None if dres is None else dres.float())
+    r, e = out['ref'], out['emu']
+    tol = 2e-5 if dtype == torch.float32 else 6e-3
+    assert rel(e[0], r[0]) < tol, ('dy', rel(e[0], r[0]))
+    assert rel(e[1], r[1]) < 2e-5 and rel(e[2], r[2]) < 2e-5 and rel(e[3], r[3]) < 2e-5
+    if mask == 'z':
+        assert torch.equal(e[4], r[4])
 
 
 @pytest.mark.skipif(os.environ.get('TSS_EMU_FULL') != '1', reason='~2 min: set TSS_EMU_FULL=1')

@@ -148,85 +148,105 @@ bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const 
 }
 
 // ------------------------------------------------------------------ backward ----------
-// pass 1: per-channel sums of g and g*xhat.  Block = CG channel groups x PL row lanes.
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 2)
+// pass 1: per-channel sums of g and g*xhat.  Block = CG channel groups x PL row lanes, same thread mapping as the apply
+// kernels.  (The round-1 kernel needed 121 registers -- 2 CTAs per SM -- and reduced inside the CTA with shared-memory
+// float atomics, CAS loops on sm_100: 2.3-2.5 TB/s on the large maps, 8-12 us floors on the small ones.  Here rstd
+// is applied once at the end, the mask mode is a template parameter, three CTAs per SM are resident and the lanes
+// of a CTA are summed through a [PL][C] shared-memory array: no atomics in front of the one global RED per channel.)
+constexpr int kMaskNone = 0, kMaskZ = 1, kMaskY = 2;    // no ReLU / mask from the activated tensor z / recomputed from y
+
+template <typename T, int U, int kMask>
+__device__ __forceinline__ void bwd_reduce_rows(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y,
+                                                int64_t M, int64_t lddz, int64_t ldz, int64_t ldy, int c0,
+                                                int64_t first, int64_t step, const float (&mu)[8], const float (&sc)[8],
+                                                const float (&sh)[8], float (&s1)[8], float (&s2)[8]) {
+    for (int64_t m0 = first; m0 < M; m0 += U * step) {
+        Raw8<T> rg[U], ry[U], rz[kMask == kMaskZ ? U : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t m = m0 + u * step;
+            if (m < M) {
+                rg[u].ld(dz + m * lddz + c0);
+                ry[u].ld(y + m * ldy + c0);
+                if (kMask == kMaskZ) rz[u].ld(z + m * ldz + c0);
+            } else {
+                rg[u].zero(); ry[u].zero();
+                if (kMask == kMaskZ) rz[u].zero();
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float g[8], yy[8];
+            rg[u].get(g);
+            ry[u].get(yy);
+            if (kMask == kMaskZ) {
+                float zz[8];
+                rz[u].get(zz);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
+            } else if (kMask == kMaskY) {
+                // the forward's own arithmetic (scale = gamma*rstd, shift = beta - mean*scale, fma): the identical mask
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g[e] = fmaf(yy[e], sc[e], sh[e]) > 0.f ? g[e] : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                s1[e] += g[e];
+                s2[e] = fmaf(g[e], yy[e] - mu[e], s2[e]);        // rstd is applied to the finished sum
+            }
+        }
+    }
+}
+
+// the CTA's lanes summed per channel through s_part[PL][C] (<= kThreads * 8 floats), then ONE global RED per channel
+__device__ __forceinline__ void cta_channel_sums(const float (&v)[8], float* s_part, float* __restrict__ out, int C, int c0,
+                                                 int pl, int PL) {
+    float* mine = s_part + (size_t)pl * C + c0;
+    *reinterpret_cast<float4*>(mine) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(mine + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        float a = 0.f;
+        for (int p = 0; p < PL; ++p) a += s_part[(size_t)p * C + i];
+        atomicAdd(out + i, a);
+    }
+    __syncthreads();                                             // s_part may be rewritten
+}
+
+template <int kMask>
+__device__ __forceinline__ void bwd_constants(const float* __restrict__ mean, const float* __restrict__ rstd,
+                                              const float* __restrict__ gamma, const float* __restrict__ beta, int c0,
+                                              float (&mu)[8], float (&rs)[8], float (&sc)[8], float (&sh)[8]) {
+    ldg8f(mean + c0, mu);
+    ldg8f(rstd + c0, rs);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        sc[e] = (gamma != nullptr ? __ldg(gamma + c0 + e) : 1.f) * rs[e];
+        sh[e] = (kMask == kMaskY && beta != nullptr ? __ldg(beta + c0 + e) : 0.f) - mu[e] * sc[e];
+    }
+}
+
+template <typename T, int U, int kMask>
+__global__ void __launch_bounds__(kThreads, 3)
 bn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                     float* __restrict__ sums, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy,
-                     int relu, int PL) {
-    pdl_wait();
-    TSS_DYN_SMEM(float, s_sum);   // [2*C]
+                     float* __restrict__ sums, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy, int PL) {
+    __shared__ __align__(16) float s_part[kThreads * 8];
     const int CG = C >> 3;
     const int cg = threadIdx.x % CG;
     const int pl = threadIdx.x / CG;
     const int c0 = cg * 8;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_sum[i] = 0.f;
-    __syncthreads();
-    float s1[8], s2[8], mu[8], rs[8];
+    pdl_wait();
+    float s1[8], s2[8], mu[8], rs[8], sc[8], sh[8];
     zero8(s1); zero8(s2);
-    ldg8f(mean + c0, mu);
-    ldg8f(rstd + c0, rs);
-    // z == nullptr with ReLU: the mask is recomputed from y with the forward's own arithmetic
-    // (scale = gamma*rstd, shift = beta - mean*scale, fma) -- one tensor less to read
-    float sc[8], sh[8];
-    if (relu && z == nullptr) {
+    bwd_constants<kMask>(mean, rstd, gamma, beta, c0, mu, rs, sc, sh);
+    bwd_reduce_rows<T, U, kMask>(dz, z, y, M, lddz, ldz, ldy, c0, (int64_t)blockIdx.x * PL + pl, (int64_t)gridDim.x * PL,
+                                 mu, sc, sh, s1, s2);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            sc[e] = (gamma != nullptr ? __ldg(gamma + c0 + e) : 1.f) * rs[e];
-            sh[e] = (beta != nullptr ? __ldg(beta + c0 + e) : 0.f) - mu[e] * sc[e];
-        }
-    }
-    if (pl < PL) {
-        // U rows per iteration, loaded raw and unpacked late: 2U-3U independent 128-bit loads in
-        // flight per thread at a register cost of 4 per load
-        constexpr int U = 3;
-        const int64_t step = (int64_t)gridDim.x * PL;
-        for (int64_t m0 = (int64_t)blockIdx.x * PL + pl; m0 < M; m0 += U * step) {
-            Raw8<T> rg[U], ry[U], rz[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t m = m0 + u * step;
-                if (m < M) {
-                    rg[u].ld(dz + m * lddz + c0);
-                    ry[u].ld(y + m * ldy + c0);
-                    if (relu && z != nullptr) rz[u].ld(z + m * ldz + c0);
-                } else {
-                    rg[u].zero(); ry[u].zero(); rz[u].zero();
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                float g[8], yy[8];
-                rg[u].get(g);
-                ry[u].get(yy);
-                if (relu) {
-                    if (z != nullptr) {
-                        float zz[8];
-                        rz[u].get(zz);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) g[e] = fmaf(yy[e], sc[e], sh[e]) > 0.f ? g[e] : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    s1[e] += g[e];
-                    s2[e] = fmaf(g[e], (yy[e] - mu[e]) * rs[e], s2[e]);
-                }
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            atomicAdd(&s_sum[c0 + e], s1[e]);
-            atomicAdd(&s_sum[C + c0 + e], s2[e]);
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, s_sum[i]);
+    for (int e = 0; e < 8; ++e) s2[e] *= rs[e];
+    cta_channel_sums(s1, s_part, sums, C, c0, pl, PL);
+    cta_channel_sums(s2, s_part, sums + C, C, c0, pl, PL);
 }
 
 // pass 2: dy = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)); optional dres = g.  Same thread mapping as bn_apply_kernel:
@@ -308,6 +328,131 @@ bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* 
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = a[e] * (g[e] - k1[e] - (yy[e] - mu[e]) * k2[e]);
+            store8(dy + m * lddy + c0, o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ backward in ONE launch ------
+// Both passes of the BatchNorm backward in one kernel, for tensors that stay in L2 between them (dz and y together
+// up to a few tens of MB: every layer at 1/16 and 1/32 resolution and the 64 / 128-channel maps at 1/8): pass 1 as
+// above, a grid-wide barrier, pass 2 re-reads dz and y from L2 instead of HBM and the second launch (with its
+// dependent-launch edge and its constant loads) disappears.  All CTAs must be resident at once: the launcher caps the
+// grid at two CTAs per SM (<= 104 registers: room is left for a weight-gradient CTA beside them).  Whatever runs beside this kernel (weight gradients on the
+// side stream) cannot depend on it, so it drains and every CTA gets its slot; the next kernel of this stream only
+// becomes resident once every CTA here has passed griddepcontrol.launch_dependents, i.e. is resident itself.
+//
+// sync[0] = arrival counter (left at 0), sync[1] = generation (bumped by the last arrival), sync[2] = sticky error flag:
+// a CTA that waits longer than ~1 s gives up, sets it, and from then on nobody waits (wrong sums instead of a hung GPU;
+// ops.bn_backward checks the flag in debug mode, tests/test_fused_paths_gpu.py always).
+__device__ __forceinline__ void grid_barrier(int* sync) {
+    __syncthreads();
+#ifndef TSS_HOST_EMU                                             // (the emulation runs one CTA: nothing to wait for)
+    if (threadIdx.x == 0) {
+        volatile int* vs = sync;
+        const int gen = vs[1];                                   // read before arriving: it cannot change until this CTA has arrived too
+        __threadfence();                                         // this CTA's REDs on the sums before its arrival
+        if (atomicAdd(sync, 1) == (int)gridDim.x - 1) {
+            vs[0] = 0;                                           // re-armed for the next launch
+            __threadfence();
+            atomicAdd(sync + 1, 1);
+        } else {
+            unsigned spins = 0;
+            while (vs[1] == gen && vs[2] == 0) {
+                __nanosleep(64);
+                if (++spins > (1u << 21)) { atomicExch(sync + 2, 1); break; }
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+#endif
+}
+
+__device__ __forceinline__ void ldcg8f(const float* p, float (&v)[8]) {      // L2 (written by other SMs in this launch)
+    float4 a = __ldcg(reinterpret_cast<const float4*>(p));
+    float4 b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+template <typename T, int U, int kMask>         // kMaskZ: residual layers (mask from the activated tensor z, dres = g stored)
+__global__ void __maxnreg__(96)         // launched with <= kThreads threads; two CTAs fit beside two weight-gradient CTAs (192 x 40 registers)
+bn_bwd_onepass_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y,
+                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float* sums, T* __restrict__ dy, T* __restrict__ dres, float* __restrict__ dgamma,
+                      float* __restrict__ dbeta, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy, int64_t lddy,
+                      int64_t lddres, float inv_m, int PL, int* sync) {
+    __shared__ __align__(16) float s_part[kThreads * 8];
+    const int CG = C >> 3;
+    const int cg = threadIdx.x % CG;
+    const int pl = threadIdx.x / CG;
+    const int c0 = cg * 8;
+    pdl_wait();
+    // live across pass 1: mu, a, sh, s1, s2; across pass 2: a, sh, c1, k2 (dy = a * (g - c1 - y * k2), c1 = k1 - mean * k2)
+    float a[8], sh[8], c1[8], k2[8];
+    const int64_t first = (int64_t)blockIdx.x * PL + pl, step = (int64_t)gridDim.x * PL;
+    {
+        float s1[8], s2[8], mu[8], rs[8];
+        zero8(s1); zero8(s2);
+        bwd_constants<kMask>(mean, rstd, gamma, beta, c0, mu, rs, a, sh);         // a = the forward's scale
+        bwd_reduce_rows<T, U, kMask>(dz, z, y, M, lddz, ldz, ldy, c0, first, step, mu, a, sh, s1, s2);
+        ldg8f(rstd + c0, rs);                                                      // (re-read: not kept across the loop)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s2[e] *= rs[e];
+        cta_channel_sums(s1, s_part, sums, C, c0, pl, PL);
+        cta_channel_sums(s2, s_part, sums + C, C, c0, pl, PL);
+        grid_barrier(sync);
+        ldcg8f(sums + c0, s1);
+        ldcg8f(sums + C + c0, s2);
+        ldg8f(mean + c0, mu);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            k2[e] = rs[e] * (s2[e] * inv_m);
+            c1[e] = fmaf(-mu[e], k2[e], s1[e] * inv_m);
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            if (dbeta != nullptr) dbeta[c] += __ldcg(sums + c);
+            if (dgamma != nullptr) dgamma[c] += __ldcg(sums + C + c);
+        }
+    }
+    // pass 2 walks this thread's rows backwards: what pass 1 touched last is what L2 still holds for certain
+    if (first >= M) return;
+    const int64_t batches = (M - first + U * step - 1) / (U * step);
+    for (int64_t b = batches - 1; b >= 0; --b) {
+        const int64_t m0 = first + b * U * step;
+        Raw8<T> rg[U], ry[U], rz[kMask == kMaskZ ? U : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t m = m0 + u * step;
+            if (m < M) {
+                rg[u].ld(dz + m * lddz + c0);
+                ry[u].ld(y + m * ldy + c0);
+                if (kMask == kMaskZ) rz[u].ld(z + m * ldz + c0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t m = m0 + u * step;
+            if (m >= M) break;
+            float g[8], yy[8];
+            rg[u].get(g);
+            ry[u].get(yy);
+            if (kMask == kMaskZ) {
+                float zz[8];
+                rz[u].get(zz);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
+            } else if (kMask == kMaskY) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g[e] = fmaf(yy[e], a[e], sh[e]) > 0.f ? g[e] : 0.f;
+            }
+            if (dres != nullptr) store8(dres + m * lddres + c0, g);
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = a[e] * fmaf(-yy[e], k2[e], g[e] - c1[e]);
             store8(dy + m * lddy + c0, o);
         }
     }
@@ -443,17 +588,51 @@ extern "C" int tss_bn_bwd_reduce(const void* dz, const void* z, const void* y, c
                                  int64_t ldy, int flags, int dtype, void* stream) {
     if (int e = check_rows("bn_bwd_reduce", M, C)) return e;
     const int relu = flags & TSS_EPI_RELU;
-    const int CG = C / 8;
-    TSS_REQUIRE(CG <= kThreads, "bn_bwd_reduce: C=%d too large", C);
-    const int PL = kThreads / CG;
-    const int threads = PL * CG;
-    int64_t want = ceil_div64(M, (int64_t)PL * 6);           // >= 2 iterations of 3 rows per pixel lane
-    int64_t cap = (int64_t)tss_num_sms() * 2;                 // 2 resident CTAs per SM (121 registers)
-    const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+    const RowsLaunch rl = rows_launch(M, C);
+    TSS_REQUIRE(rl.threads > 0, "bn_bwd_reduce: C=%d too large", C);
+    const int mask = !relu ? kMaskNone : (z != nullptr ? kMaskZ : kMaskY);
     TSS_DISPATCH_DTYPE(dtype, "bn_bwd_reduce", {
-        tss_launch(bn_bwd_reduce_kernel<T>, grid, threads, (size_t)2 * C * sizeof(float), (cudaStream_t)stream, 
-            (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, beta, sums, M, C, lddz, ldz, ldy, relu, PL);
+        constexpr int U = sizeof(T) == 2 ? 4 : 2;
+        int64_t want = ceil_div64(M, (int64_t)rl.PL * U * 2);    // >= 2 batches of U rows per row lane
+        const int64_t cap = (int64_t)tss_num_sms() * 3;           // the resident CTAs (<= 85 registers)
+        const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+        auto kern = mask == kMaskNone ? bn_bwd_reduce_kernel<T, U, kMaskNone>
+                  : mask == kMaskZ    ? bn_bwd_reduce_kernel<T, U, kMaskZ> : bn_bwd_reduce_kernel<T, U, kMaskY>;
+        tss_launch(kern, grid, rl.threads, 0, (cudaStream_t)stream,
+            (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, beta, sums, M, C, lddz, ldz, ldy, rl.PL);
         TSS_LAUNCH_CHECK("bn_bwd_reduce");
+        return TSS_OK;
+    });
+}
+
+extern "C" int tss_bn_bwd_onepass(const void* dz, const void* z, const void* y, const float* mean, const float* rstd,
+                                  const float* gamma, const float* beta, float* sums, void* dy, void* dres, float* dgamma,
+                                  float* dbeta, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy, int64_t lddy,
+                                  int64_t lddres, int flags, int* sync, int dtype, void* stream) {
+    if (int e = check_rows("bn_bwd_onepass", M, C)) return e;
+    TSS_REQUIRE(sync != nullptr && sums != nullptr, "bn_bwd_onepass: sums and sync are required");
+    const int relu = flags & TSS_EPI_RELU;
+    const RowsLaunch rl = rows_launch(M, C);
+    TSS_REQUIRE(rl.threads > 0, "bn_bwd_onepass: C=%d too large", C);
+    const int mask = !relu ? kMaskNone : (z != nullptr ? kMaskZ : kMaskY);
+    TSS_DISPATCH_DTYPE(dtype, "bn_bwd_onepass", {
+        constexpr int U = sizeof(T) == 2 ? 4 : 2;
+        constexpr int UZ = sizeof(T) == 2 ? 2 : 1;               // three operands per row: fewer rows in flight
+        const int u = mask == kMaskZ ? UZ : U;
+        int64_t want = ceil_div64(M, (int64_t)rl.PL * u);
+#ifdef TSS_HOST_EMU
+        const int64_t cap = 1;                                    // blocks run one after the other on the emulation
+#else
+        // ALL CTAs resident at once: two per SM, minus slack for SMs that a kernel of another stream (NCCL) fills up
+        const int64_t cap = (int64_t)tss_num_sms() * 2 - 40;
+#endif
+        const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+        auto kern = mask == kMaskNone ? bn_bwd_onepass_kernel<T, U, kMaskNone>
+                  : mask == kMaskZ    ? bn_bwd_onepass_kernel<T, UZ, kMaskZ> : bn_bwd_onepass_kernel<T, U, kMaskY>;
+        tss_launch(kern, grid, rl.threads, 0, (cudaStream_t)stream,
+            (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, beta, sums, (T*)dy, (T*)dres, dgamma, dbeta, M, C,
+            lddz, ldz, ldy, lddy, lddres, (float)(1.0 / (double)M), rl.PL, sync);
+        TSS_LAUNCH_CHECK("bn_bwd_onepass");
         return TSS_OK;
     });
 }

@@ -24,6 +24,7 @@ DEFAULTS = {
     'OWN_DROPOUT': True,        # mask-free dropout kernel instead of ATen's (r2: 28.8 -> 14.1 us per pass)
     'STEM_WGRAD_PATCHES': True,  # stem weight gradient = coalesced patch matrix + the TMA-fed pointwise wgrad GEMM (r2: 4.03 -> 3.93 ms/step)
     'CLASS_TC': True,           # class-score conv (19 classes + bias) on the tcgen05 GEMMs with zero-padded operands (r2: 4.12 -> 4.04 ms/step)
+    'BN_BWD_ONEPASS': False,    # BatchNorm backward (reduce + apply) as ONE launch with a grid barrier where dz + y stay in L2
     'SLOT_GRAPHS': True,        # one captured training graph per staging slot of the trainer (no device-to-device batch copy)
 }
 

@@ -6,6 +6,8 @@ slice of a wider NHWC buffer).  Wrappers allocate outputs through PyTorch's cach
 allocator, derive sizes/pitches from the tensors and call the library on the current
 stream.  Nothing here computes on the host and nothing falls back to torch ops.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -493,6 +495,37 @@ def bn_apply(y, scale, shift, y2=None, scale2=None, shift2=None, res=None, relu=
     return out
 
 
+_GRID_SYNC = {}
+BN_BWD_ONEPASS = gate('BN_BWD_ONEPASS')      # module attribute: tests toggle it
+_ONEPASS_MAX_BYTES = int(float(os.environ.get('TSS_BN_ONEPASS_MB', '64')) * (1 << 20))
+
+
+def _grid_sync(device):
+    """The barrier words of ``tss_bn_bwd_onepass`` ({arrivals, generation, sticky time-out flag, unused}): one buffer per
+    device, so the BatchNorm backward passes of a device must be stream-ordered (they are: autograd runs a device's
+    backward on one stream; a caller with several concurrent streams passes its own buffers through the C ABI).  It is
+    allocated on first use, which must not happen inside a CUDA-graph capture (the buffer would live in that graph's
+    private pool and die with it): every graphed step of this package warms up eagerly first."""
+    key = device.index if device.type == 'cuda' else 'cpu'
+    buf = _GRID_SYNC.get(key)
+    if buf is None:
+        if device.type == 'cuda' and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError('tss_b200: the first BatchNorm backward of a process ran inside a CUDA-graph capture; '
+                               'run one eager step before capturing (or set TSS_BN_BWD_ONEPASS=0)')
+        buf = _GRID_SYNC[key] = torch.zeros(4, dtype=torch.int32, device=device)
+    return buf
+
+
+def grid_sync_timed_out():
+    """True if a grid barrier of ``tss_bn_bwd_onepass`` ever gave up waiting (its results are then wrong)."""
+    return any(int(buf[2]) != 0 for buf in _GRID_SYNC.values())
+
+
+def _onepass_fits(dz, y, z):
+    """``tss_bn_bwd_onepass`` pays off while its operands stay in L2 between its two passes."""
+    return BN_BWD_ONEPASS and sum(t.numel() * t.element_size() for t in (dz, y, z) if t is not None) <= _ONEPASS_MAX_BYTES
+
+
 def bn_backward(dz, z, y, mean, rstd, gamma, relu, want_dres=False, dgamma=None, dbeta=None, beta=None,
                 sums=None, sync=None, prereduced=False):
     """-> dy, dres (or None).  dgamma/dbeta (fp32 (C,)) are accumulated into.  ``z=None`` with
@@ -508,6 +541,14 @@ def bn_backward(dz, z, y, mean, rstd, gamma, relu, want_dres=False, dgamma=None,
     if prereduced:      # dz already is g = dz * mask and `sums` already holds the two sums (fused into the
         fl = 0          # dgrad epilogue of the consumer): the apply pass alone, without a mask
         relu = False
+    elif (sync is None or sync[0] <= 1) and _onepass_fits(dz, y, z if relu else None):
+        # both passes in one launch: dz and y (and z) stay in L2 between them
+        dy = empty_nhwc(N, C, H, W, dz.dtype, dz.device)
+        dres = empty_nhwc(N, C, H, W, dz.dtype, dz.device) if want_dres else None
+        _lib.call('tss_bn_bwd_onepass', dz=dz, z=z if relu else None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta,
+                  sums=sums, dy=dy, dres=dres, dgamma=dgamma, dbeta=dbeta, M=M, C=C, lddz=lddz, ldz=ldz, ldy=ldy, lddy=C,
+                  lddres=C, flags=fl, sync=_grid_sync(dz.device), dtype=code)
+        return dy, dres
     else:
         _lib.call('tss_bn_bwd_reduce', dz=dz, z=z if relu else None, y=y, mean=mean, rstd=rstd, gamma=gamma,
               beta=beta, sums=sums,
