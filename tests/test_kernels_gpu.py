@@ -657,6 +657,7 @@ TC_CASES = [  # K, Nc, M (rows = N*H*W with N=1, H=1)
     (96, 576, 576), (576, 96, 576), (576, 128, 576), (128, 768, 576), (768, 128, 576), (256, 128, 576), (128, 128, 9216),
     (64, 128, 9216), (128, 32, 12), (192, 32, 300), (288, 48, 300), (48, 288, 300), (32, 32, 129), (128, 128, 1),
     (32, 192, 500), (192, 48, 500), (288, 64, 300), (1152, 128, 2048), (32, 64, 700),
+    (64, 384, 27648), (64, 384, 25601), (48, 288, 30000), (64, 128, 77000),      # persistent kernel with up to 6 column tiles (K <= 64)
 ]
 
 

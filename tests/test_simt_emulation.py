@@ -37,6 +37,7 @@ class EmulatedBackend:
         self.protos = _lib.parse_header()
         self.fake = FakeBackend()
         self.emulated_calls = 0
+        self.emulated_names = {}
 
     def call(self, name, kwargs):
         fn = getattr(self.lib, name, None)
@@ -65,6 +66,7 @@ class EmulatedBackend:
         fn.restype = ctypes.c_int
         rc = fn(*args)
         self.emulated_calls += 1
+        self.emulated_names[name] = self.emulated_names.get(name, 0) + 1
         if rc != 0:
             self.lib.tss_last_error.restype = ctypes.c_char_p
             raise RuntimeError('%s failed (%d): %s' % (name, rc, self.lib.tss_last_error().decode()))
@@ -112,9 +114,10 @@ def _ppm_run(backend, flag, N, H, W, dtype):
 @pytest.mark.parametrize('shape,dtype', [((3, 6, 9), torch.float32), ((2, 8, 8), torch.bfloat16), ((20, 1, 2), torch.float32)])
 def test_grouped_pyramid_kernels_on_the_simt_emulation(emulated, shape, dtype):
     N, H, W = shape
-    before = emulated.emulated_calls
+    grouped = lambda: sum(v for k, v in emulated.emulated_names.items() if k.startswith('tss_ppm'))
+    before = grouped()
     got = _ppm_run(emulated, True, N, H, W, dtype)
-    assert emulated.emulated_calls - before == 4          # branches fwd, concat fwd, concat bwd, branches bwd
+    assert grouped() - before == 4          # branches fwd, concat fwd, concat bwd, branches bwd
     want = _ppm_run(FakeBackend(), False, N, H, W, dtype)
     tol = 2e-5 if dtype == torch.float32 else 2e-2
     assert rel(got[0], want[0]) < tol, ('out', rel(got[0], want[0]))
@@ -337,11 +340,12 @@ def test_grouped_pyramid_eval_on_the_simt_emulation(emulated, dtype):
             m.eval()
             g = torch.Generator().manual_seed(1)
             x = ops.as_nhwc(torch.randn(1, 128, 8, 16, generator=g).to(dtype))
-            before = getattr(be, 'emulated_calls', 0)
+            grouped = lambda: sum(v for k, v in getattr(be, 'emulated_names', {}).items() if k.startswith('tss_ppm'))
+            before = grouped()
             with torch.no_grad():
                 outs[name] = m(x).float()
             if flag:
-                assert be.emulated_calls - before == 2          # branches + concat
+                assert grouped() - before == 2          # branches + concat
     finally:
         Fn.FUSE_PPM = keep
     assert rel(outs['emu'], outs['ref']) < (1e-5 if dtype == torch.float32 else 2e-2)
@@ -626,6 +630,39 @@ def test_batchnorm_backward_in_one_launch_on_the_simt_emulation(emulated, C, N, 
     assert rel(e[1], r[1]) < 2e-5 and rel(e[2], r[2]) < 2e-5 and rel(e[3], r[3]) < 2e-5
     if mask == 'z':
         assert torch.equal(e[4], r[4])
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('C,N,H,W,mask,want_dres', [(128, 2, 12, 20, 'y', 0), (96, 1, 9, 40, 'none', 1), (64, 3, 7, 5, 'z', 1), (8, 1, 1, 1, 'y', 1),
+                                                    (384, 1, 5, 7, 'y', 0), (576, 1, 3, 4, 'none', 0), (48, 2, 33, 17, 'z', 1)])
+def test_batchnorm_backward_apply_on_the_simt_emulation(emulated, C, N, H, W, mask, want_dres, dtype):
+    """csrc/bn.cu, the apply pass: dy = a * (g - c1 - y * k2) with the folded per-channel constants, the three mask modes,
+    the optional residual-branch gradient, pitched operands; SyncBN's larger count."""
+    g = torch.Generator().manual_seed(C + H + W)
+    pitch = C + 8
+    wide = lambda: torch.randn(N, H, W, pitch, generator=g).to(dtype)
+    dzb, yb, zb = wide(), wide(), wide()
+    dz, y, z = (t[..., :C].permute(0, 3, 1, 2) for t in (dzb, yb, zb))
+    mean, rstd = torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    sums = torch.randn(2 * C, generator=g) * 3
+    M, code = N * H * W, _lib.dtype_code(dtype)
+    for count in (0, 2 * M):
+        out = {}
+        for name, be in (('ref', FakeBackend()), ('emu', emulated)):
+            dgamma, dbeta = torch.ones(C), torch.ones(C)
+            dy = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2)
+            dres = torch.zeros(N, H, W, C, dtype=dtype).permute(0, 3, 1, 2) if want_dres else None
+            be.call('tss_bn_bwd_apply', dict(dz=dz, z=z if mask == 'z' else None, y=y, mean=mean, rstd=rstd, gamma=gamma, beta=beta,
+                                             sums=sums, dy=dy, dres=dres, dgamma=dgamma, dbeta=dbeta, M=M, count=count, C=C,
+                                             lddz=pitch, ldz=pitch if mask == 'z' else 0, ldy=pitch, lddy=C, lddres=C,
+                                             flags=0 if mask == 'none' else 1, dtype=code))
+            out[name] = (dy.float(), dgamma, dbeta, None if dres is None else dres.float())
+        r, e = out['ref'], out['emu']
+        assert rel(e[0], r[0]) < (2e-5 if dtype == torch.float32 else 6e-3), ('dy', rel(e[0], r[0]))
+        assert rel(e[1], r[1]) < 1e-6 and rel(e[2], r[2]) < 1e-6
+        if want_dres:
+            assert torch.equal(e[3], r[3])
 
 
 @pytest.mark.skipif(os.environ.get('TSS_EMU_FULL') != '1', reason='~2 min: set TSS_EMU_FULL=1')

@@ -19,9 +19,9 @@ inline int stream_grid(int64_t items, int per_sm = 8) {
 struct RowsLaunch {
     int threads, PL;
     int64_t M;
-    int grid(int U) const {
+    int grid(int U, int per_sm = 8) const {
         int64_t want = ceil_div64(M, (int64_t)PL * U);          // >= 1 batch of U rows per row lane
-        const int64_t cap = (int64_t)tss_num_sms() * 8;
+        const int64_t cap = (int64_t)tss_num_sms() * per_sm;
         if (want < 1) want = 1;
         return (int)(want < cap ? want : cap);
     }
@@ -249,18 +249,19 @@ bn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T*
     cta_channel_sums(s2, s_part, sums + C, C, c0, pl, PL);
 }
 
-// pass 2: dy = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)); optional dres = g.  Same thread mapping as bn_apply_kernel:
-// per-channel constants a = gamma*rstd, k1 = sum(g)/n, k2 = rstd*sum(g*xhat)/n, mu (and the forward's scale / shift for
-// the recomputed ReLU mask) live in registers; dy = a*(g - k1 - (y - mu)*k2).
-template <typename T, int U, bool kRes>         // kRes: residual layers (mask from the activated tensor z, dres = g stored)
-__global__ void __launch_bounds__(kThreads)
+// pass 2: dy = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)); optional dres = g.  Same thread mapping as bn_apply_kernel.
+// Per-channel constants in registers: a = gamma*rstd (the forward's scale), k2 = rstd*sum(g*xhat)/n, c1 = sum(g)/n - mean*k2
+// (and the forward's shift for the recomputed ReLU mask): dy = a * (g - c1 - y*k2).  Three CTAs per SM (<= 80 registers;
+// the first version kept mean, k1, k2 and the shift apart: 112 registers, two CTAs, 3.4-4.1 TB/s on the 30-60 MB tensors).
+template <typename T, int U, int kMask>         // kMaskZ: residual layers (mask from the activated tensor z, dres = g stored)
+__global__ void __launch_bounds__(kThreads, 3)
 bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y,
                     const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ sums,
                     T* __restrict__ dy, T* __restrict__ dres, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, int64_t M, int C, int64_t lddz, int64_t ldz, int64_t ldy,
-                    int64_t lddy, int64_t lddres, int relu, float inv_m, int PL) {
+                    int64_t lddy, int64_t lddres, float inv_m, int PL) {
     const int CG = C >> 3;
     const int cg = threadIdx.x % CG;
     const int pl = threadIdx.x / CG;
@@ -273,9 +274,10 @@ bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* 
         }
     }
     if (pl >= PL) return;
-    float a[8], k1[8], k2[8], mu[8], sh[8];
+    constexpr bool mask_z = kMask == kMaskZ, mask_y = kMask == kMaskY;
+    float a[8], c1[8], k2[8], sh[8];
     {
-        float rs[8], s1[8], s2[8];
+        float mu[8], rs[8], s1[8], s2[8];
         ldg8f(mean + c0, mu);
         ldg8f(rstd + c0, rs);
         ldg8f(sums + c0, s1);
@@ -288,15 +290,14 @@ bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* 
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             a[e] *= rs[e];                                   // = the forward's scale
-            k1[e] = s1[e] * inv_m;
             k2[e] = rs[e] * (s2[e] * inv_m);
-            sh[e] = (beta != nullptr ? __ldg(beta + c0 + e) : 0.f) - mu[e] * a[e];
+            c1[e] = fmaf(-mu[e], k2[e], s1[e] * inv_m);
+            sh[e] = mask_y ? (beta != nullptr ? __ldg(beta + c0 + e) : 0.f) - mu[e] * a[e] : 0.f;
         }
     }
-    const bool mask_z = kRes && relu && z != nullptr;
     const int64_t step = (int64_t)gridDim.x * PL;
     for (int64_t m0 = (int64_t)blockIdx.x * PL + pl; m0 < M; m0 += U * step) {
-        Raw8<T> rg[U], ry[U], rz[kRes ? U : 1];
+        Raw8<T> rg[U], ry[U], rz[mask_z ? U : 1];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t m = m0 + u * step;
@@ -313,21 +314,19 @@ bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* 
             float g[8], yy[8];
             rg[u].get(g);
             ry[u].get(yy);
-            if (relu) {
-                if (mask_z) {
-                    float zz[8];
-                    rz[u].get(zz);
+            if (mask_z) {
+                float zz[8];
+                rz[u].get(zz);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
-                } else {
+                for (int e = 0; e < 8; ++e) g[e] = zz[e] > 0.f ? g[e] : 0.f;
+            } else if (mask_y) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) g[e] = fmaf(yy[e], a[e], sh[e]) > 0.f ? g[e] : 0.f;
-                }
+                for (int e = 0; e < 8; ++e) g[e] = fmaf(yy[e], a[e], sh[e]) > 0.f ? g[e] : 0.f;
             }
-            if (kRes && dres != nullptr) store8(dres + m * lddres + c0, g);
+            if (dres != nullptr) store8(dres + m * lddres + c0, g);
             float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = a[e] * (g[e] - k1[e] - (yy[e] - mu[e]) * k2[e]);
+            for (int e = 0; e < 8; ++e) o[e] = a[e] * fmaf(-yy[e], k2[e], g[e] - c1[e]);
             store8(dy + m * lddy + c0, o);
         }
     }
@@ -593,11 +592,16 @@ extern "C" int tss_bn_bwd_reduce(const void* dz, const void* z, const void* y, c
     const int mask = !relu ? kMaskNone : (z != nullptr ? kMaskZ : kMaskY);
     TSS_DISPATCH_DTYPE(dtype, "bn_bwd_reduce", {
         constexpr int U = sizeof(T) == 2 ? 4 : 2;
-        int64_t want = ceil_div64(M, (int64_t)rl.PL * U * 2);    // >= 2 batches of U rows per row lane
+        constexpr int U3 = sizeof(T) == 2 ? 3 : 2;
+        // (bf16: 3 rows in flight, as in the apply pass: 3.206 -> 3.189 ms/step on B200; TSS_BN_RED_U=4 for the A/B)
+        static const int u_env = [] { const char* e = getenv("TSS_BN_RED_U"); return e ? atoi(e) : 3; }();
+        const bool u3 = u_env != 4;
+        int64_t want = ceil_div64(M, (int64_t)rl.PL * (u3 ? U3 : U) * 2);    // >= 2 batches of U rows per row lane
         const int64_t cap = (int64_t)tss_num_sms() * 3;           // the resident CTAs (<= 85 registers)
         const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
-        auto kern = mask == kMaskNone ? bn_bwd_reduce_kernel<T, U, kMaskNone>
-                  : mask == kMaskZ    ? bn_bwd_reduce_kernel<T, U, kMaskZ> : bn_bwd_reduce_kernel<T, U, kMaskY>;
+        auto kern = mask == kMaskNone ? (u3 ? bn_bwd_reduce_kernel<T, U3, kMaskNone> : bn_bwd_reduce_kernel<T, U, kMaskNone>)
+                  : mask == kMaskZ    ? (u3 ? bn_bwd_reduce_kernel<T, U3, kMaskZ> : bn_bwd_reduce_kernel<T, U, kMaskZ>)
+                                      : (u3 ? bn_bwd_reduce_kernel<T, U3, kMaskY> : bn_bwd_reduce_kernel<T, U, kMaskY>);
         tss_launch(kern, grid, rl.threads, 0, (cudaStream_t)stream,
             (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, beta, sums, M, C, lddz, ldz, ldy, rl.PL);
         TSS_LAUNCH_CHECK("bn_bwd_reduce");
@@ -649,10 +653,20 @@ extern "C" int tss_bn_bwd_apply(const void* dz, const void* z, const void* y, co
     TSS_REQUIRE(rl.threads > 0, "bn_bwd_apply: C=%d too large", C);
     TSS_DISPATCH_DTYPE(dtype, "bn_bwd_apply", {
         constexpr int U = sizeof(T) == 2 ? 4 : 2;
-        auto kern = (z != nullptr || dres != nullptr) ? bn_bwd_apply_kernel<T, U, true> : bn_bwd_apply_kernel<T, U, false>;
-        tss_launch(kern, rl.grid(U), rl.threads, 0, (cudaStream_t)stream,
+        constexpr int UZ = sizeof(T) == 2 ? 2 : 1;               // three operands per row (+ a second output): fewer rows in flight
+        const int mask = !relu ? kMaskNone : (z != nullptr ? kMaskZ : kMaskY);
+        // bf16: 3 rows in flight per operand fit the 80 registers of three resident CTAs; with 4 the compiler spills into the
+        // loop (measured on B200 for the whole step: 3.286 ms with 4, 3.193 ms with 3; TSS_BN_BWD_U=4 for the A/B)
+        constexpr int U3 = sizeof(T) == 2 ? 3 : 2;
+        static const int u_env = [] { const char* e = getenv("TSS_BN_BWD_U"); return e ? atoi(e) : 3; }();
+        const bool u3 = u_env != 4;
+        auto kern = mask == kMaskNone ? (u3 ? bn_bwd_apply_kernel<T, U3, kMaskNone> : bn_bwd_apply_kernel<T, U, kMaskNone>)
+                  : mask == kMaskZ    ? bn_bwd_apply_kernel<T, UZ, kMaskZ>
+                                      : (u3 ? bn_bwd_apply_kernel<T, U3, kMaskY> : bn_bwd_apply_kernel<T, U, kMaskY>);
+        static const int cap_env = [] { const char* e = getenv("TSS_BN_BWD_CAP"); return e ? atoi(e) : 8; }();   // CTAs per SM in the grid (A/B; 3 are resident)
+        tss_launch(kern, rl.grid(mask == kMaskZ ? UZ : (u3 ? U3 : U), cap_env), rl.threads, 0, (cudaStream_t)stream,
             (const T*)dz, (const T*)z, (const T*)y, mean, rstd, gamma, beta, sums, (T*)dy, (T*)dres, dgamma, dbeta,
-            M, C, lddz, ldz, ldy, lddy, lddres, relu, (float)(1.0 / (double)count), rl.PL);
+            M, C, lddz, ldz, ldy, lddy, lddres, (float)(1.0 / (double)count), rl.PL);
         TSS_LAUNCH_CHECK("bn_bwd_apply");
         return TSS_OK;
     });

@@ -370,7 +370,9 @@ int launch_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi
 
 // Channel block / tile width for the TMA path, or false if C has no suitable block.
 bool tss_dw_tma_config(int C, int* CB, int* TW) {
-    if (C % 64 == 0) { *CB = 64; *TW = 16; return true; }
+    // (A/B: TSS_DW_TW64=24 gives the 64-channel block 192 threads per CTA -- 12 warps per SM in the two-CTA persistent kernels)
+    static const int tw64 = [] { const char* e = getenv("TSS_DW_TW64"); const int v = e ? atoi(e) : 16; return (v == 8 || v == 16 || v == 24) ? v : 16; }();
+    if (C % 64 == 0) { *CB = 64; *TW = tw64; return true; }
     if (C % 96 == 0) { *CB = 96; *TW = 16; return true; }
     if (C % 48 == 0) { *CB = 48; *TW = 32; return true; }
     if (C % 32 == 0) { *CB = 32; *TW = 32; return true; }

@@ -644,13 +644,16 @@ int tss_pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int
     if (int e = make_map(&tmX, x, M, K, ldx, WM)) return e;
     const int gx = (Nc + 127) / 128, gy = K / bk;
     const int n_groups = 2, k_groups = (bk + 63) / 64;
-    int64_t nsplit = ((int64_t)tss_num_sms() * 2) / ((int64_t)gx * gy);
+    static const int split_env = [] { const char* e = getenv("TSS_WGRAD_SPLIT"); return e ? atoi(e) : 2; }();       // CTAs per SM (A/B)
+    int64_t nsplit = ((int64_t)tss_num_sms() * split_env) / ((int64_t)gx * gy);
     const int64_t max_split = ceil_div64(M, 512);
     if (nsplit > max_split) nsplit = max_split;
     if (nsplit < 1) nsplit = 1;
     const int64_t rows_per = ceil_div64(ceil_div64(M, nsplit), WM) * WM;
     nsplit = ceil_div64(M, rows_per);
-    const int stages = 4;
+    static const int stages_env = [] { const char* e = getenv("TSS_WGRAD_STAGES"); return e ? atoi(e) : 4; }();    // (A/B)
+    int stages = stages_env;
+    while (stages > 2 && 1024 + (size_t)stages * (n_groups + k_groups) * kBoxBytes + (2 * stages + 1) * 8 + 16 > 200 * 1024) --stages;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < bk) tmem_cols <<= 1;
     const size_t smem = 1024 + (size_t)stages * (n_groups + k_groups) * kBoxBytes + (2 * stages + 1) * 8 + 16;
@@ -698,7 +701,11 @@ int tss_pwconv_fwd_tc(const void* x, const void* wp, void* y, int64_t M, int K, 
     // one-tile CTAs.  So: at most two column tiles and at least two waves of row tiles.
     static const int persist = [] { const char* e = getenv("TSS_PW_PERSIST"); return e != nullptr ? atoi(e) : 1; }();
     const int64_t m_tiles = ceil_div64(M, BM);
-    const bool persist_wins = Nc / bn <= 2 && m_tiles >= 4 * (int64_t)tss_num_sms();
+    // ... and, since the 2-stage ring (three or four resident CTAs when a tile is ONE k-block), K <= 64 with any number of column
+    // tiles: forward 64->384 @1/8 47.7 -> 43.7, @1/16 14.5 -> 12.9 (TSS_PW_PERSIST_K64=0 for the A/B)
+    static const int persist_k64 = [] { const char* e = getenv("TSS_PW_PERSIST_K64"); return e != nullptr ? atoi(e) : 1; }();
+    const bool persist_wins = (Nc / bn <= 2 && m_tiles >= 4 * (int64_t)tss_num_sms()) ||
+                              (persist_k64 && num_kb == 1 && m_tiles >= 200);
     if ((persist == 2 || (persist == 1 && persist_wins)) && m_tiles < (1ll << 30)) {
         // persistent CTAs, double-buffered TMEM accumulator, statistics flushed once per CTA
         static const int stages_env = [] { const char* e = getenv("TSS_PW_STAGES"); return e ? atoi(e) : 0; }();
