@@ -17,11 +17,13 @@ timeout 500 python bench.py --kernels > gpurun_out/bench_${TAG}.json 2> gpurun_o
 timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2> gpurun_out/bench_ref_${TAG}.err; echo "ref rc=$?"
 timeout 200 python tools/time_ops.py > gpurun_out/time_ops_${TAG}.txt 2>&1; echo "time_ops rc=$?"
 timeout 200 python tools/step_timeline.py --out gpurun_out/timeline_${TAG}.json > gpurun_out/timeline_${TAG}.txt 2>&1; echo "timeline rc=$?"
-timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph --headline-only > gpurun_out/plain_${TAG}.log 2>&1 && \
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_${TAG}.csv \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph --headline-only > gpurun_out/ncu_${TAG}.log 2>&1; echo "launch list rc=$?"
-timeout 120 python tools/run_kernels.py > gpurun_out/run_kernels_${TAG}.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'dw_|pw_tc|wgrad_tc|bn_|upsample|stem' -o /tmp/prof_${TAG} \
-    python tools/run_kernels.py --once > gpurun_out/ncu_full_${TAG}.log 2>&1; echo "ncu full rc=$?"
+timeout 200 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --step-only > gpurun_out/plain_${TAG}.log 2>&1 && \
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 1700 --csv --log-file gpurun_out/launches_${TAG}.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --step-only > gpurun_out/ncu_${TAG}.log 2>&1; echo "launch list rc=$?"
+# one ncu --set full capture of the kernels changed last (regex in $3; the whole table takes > 10 minutes of box time)
+KREGEX=${3:-bn_bwd|pw_tc}
+timeout 120 python tools/run_kernels.py --only bn_bwd,pwconv_fwd,pwconv_dgrad > gpurun_out/run_kernels_${TAG}.log 2>&1 && \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"$KREGEX" -o /tmp/prof_${TAG} \
+    python tools/run_kernels.py --once --only bn_bwd,pwconv_fwd,pwconv_dgrad > gpurun_out/ncu_full_${TAG}.log 2>&1; echo "ncu full rc=$?"
 ncu -i /tmp/prof_${TAG}.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
 cp gpurun_out/run_kernels_ops.json gpurun_out/run_kernels_ops_${TAG}.json

@@ -29,7 +29,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ops_log = []
 
-    only = sys.argv[sys.argv.index('--only') + 1] if '--only' in sys.argv else None   # op-name prefix filter
+    only = tuple(sys.argv[sys.argv.index('--only') + 1].split(',')) if '--only' in sys.argv else None   # op-name prefix filter(s)
 
     def runner(name, count, nbytes, fn):
         if only is not None and not name.startswith(only):

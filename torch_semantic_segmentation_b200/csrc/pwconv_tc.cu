@@ -651,7 +651,9 @@ int tss_pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int
     if (nsplit < 1) nsplit = 1;
     const int64_t rows_per = ceil_div64(ceil_div64(M, nsplit), WM) * WM;
     nsplit = ceil_div64(M, rows_per);
-    static const int stages_env = [] { const char* e = getenv("TSS_WGRAD_STAGES"); return e ? atoi(e) : 4; }();    // (A/B)
+    // 3 stages: two CTAs of the K = 128 layers (32 KB per stage) fit one SM, so the epilogue (REDs) of one overlaps the stream of the
+    // other; whole step on B200 3.176 ms (4 stages) / 3.167 (3) / 3.179 (2) / 3.232 (6).  TSS_WGRAD_SPLIT (CTAs per SM): 1 and 2 equal, 3 slower.
+    static const int stages_env = [] { const char* e = getenv("TSS_WGRAD_STAGES"); return e ? atoi(e) : 3; }();
     int stages = stages_env;
     while (stages > 2 && 1024 + (size_t)stages * (n_groups + k_groups) * kBoxBytes + (2 * stages + 1) * 8 + 16 > 200 * 1024) --stages;
     uint32_t tmem_cols = 32;
