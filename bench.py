@@ -669,6 +669,8 @@ def main():
     # = the same table summed per kernel function (what the ncu launch lists under profiles/ rank).
     fams = {}
     for r in rows:
+        if r['launches_per_step'] == 0:      # timed for the A/B table only (a gated-off alternative): not part of the step
+            continue
         f = fams.setdefault(kernel_family(r['kernel']), {'launches': 0, 'ms': 0.0, 'bytes': 0.0})
         f['launches'] += r['launches_per_step']
         f['ms'] += r['ms'] * r['launches_per_step']

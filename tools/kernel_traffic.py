@@ -59,6 +59,8 @@ def main():
         k += o['launches']
         dur = sum(val(r, 'gpu__time_duration.sum') for r in ks)
         dram = sum(val(r, 'dram__bytes_read.sum') + val(r, 'dram__bytes_write.sum') for r in ks)
+        if not ks:          # beyond the end of a capture that was cut short: leave the existing entry alone
+            continue
         names = [re.sub(r'\(.*', '', re.sub(r'void |<unnamed>::', '', r[col['Kernel Name']])) for r in ks]
         if not plausible(o['op'], names):
             print('dropped %s: profiled kernels %s do not match the op (slipped join)' % (o['op'], names), file=sys.stderr)

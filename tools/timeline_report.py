@@ -25,10 +25,13 @@ def main(path, top=40):
         agg[k][1] += a
         agg[k][2] += r['dur_us']
     tot = sum(v[1] for v in agg.values())
-    print('# %s: clean %.3f ms/step, %d kernels, attributed %.1f us' % (path, d['summary']['clean_ms_per_step'], len(rows), tot))
-    print('%-58s %5s %10s %6s %10s' % ('kernel', 'n', 'attrib_us', 'share', 'sum_dur_us'))
+    # the profiler window may hold more than one replay of the step: report PER STEP (optimizer launches = replays)
+    steps = max(1, sum(1 for r in rows if 'adamw_kernel' in r['name']))
+    print('# %s: clean %.3f ms/step, %d kernels in %d replay(s), attributed %.1f us per step' % (
+        path, d['summary']['clean_ms_per_step'], len(rows), steps, tot / steps))
+    print('%-58s %5s %10s %6s %10s   (per step)' % ('kernel', 'n', 'attrib_us', 'share', 'sum_dur_us'))
     for k, (n, a, dsum) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
-        print('%-58s %5d %10.1f %5.1f%% %10.1f' % (k, n, a, 100 * a / tot, dsum))
+        print('%-58s %5.0f %10.1f %5.1f%% %10.1f' % (k, n / steps, a / steps, 100 * a / tot, dsum / steps))
 
 
 if __name__ == '__main__':
