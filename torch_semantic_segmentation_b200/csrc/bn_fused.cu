@@ -9,11 +9,13 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// Thread = (8-channel group, row lane) like bn.cu's apply kernel: each thread derives scale / shift of ITS eight channels
-// from the fp64 statistics (B200 has a real FP64 pipe: ~100 flops per thread, once), keeps them in registers and walks
-// rows with U loads in flight.  The row-lane-0 threads of CTA 0 publish mean / rstd / running statistics.  The ticket is
-// taken at the END of the CTA: by then every CTA has long read the statistics, and the last one clears the scratch.
-template <typename T, int U>
+// Thread = (8-channel group, row lane) like bn.cu's apply kernel.  Prologue, ONCE PER CTA: thread c derives scale / shift of
+// channel c from the fp64 statistics with bn_finalize_kernel's own arithmetic (bit-identical constants) into shared memory --
+// ~100 instructions per channel including the fp64 sqrt and division.  (The first version let every thread derive the
+// constants of its eight channels: 8 x that chain in each of up to 300 k threads, 9 us per launch slower than the separate
+// finalize kernel.)  CTA 0 also publishes mean / rstd / running statistics.  The ticket is taken at the END of the CTA:
+// by then every CTA has long read the statistics, and the last one clears the scratch.
+template <typename T, int U, bool kRes>
 __global__ void __launch_bounds__(kThreads)
 bn_finalize_apply_kernel(double* stats, double inv_count, double unbias, const float* __restrict__ gamma,
                          const float* __restrict__ beta, float* __restrict__ running_mean,
@@ -22,42 +24,45 @@ bn_finalize_apply_kernel(double* stats, double inv_count, double unbias, const f
                          const T* __restrict__ y, const T* __restrict__ res, T* __restrict__ z, int64_t M, int C,
                          int64_t ldy, int64_t ldr, int64_t ldz, int relu, int PL) {
     __shared__ int s_last;
+    TSS_DYN_SMEM(float, s_const);                      // [2][C]: scale | shift
     const int CG = C >> 3;
     const int cg = threadIdx.x % CG;
     const int pl = threadIdx.x / CG;
     const int c0 = cg * 8;
     pdl_wait();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double st1 = stats[c], st2 = stats[C + c];
+        const double mean = st1 * inv_count;
+        double var = st2 * inv_count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float sc = (gamma != nullptr ? __ldg(gamma + c) : 1.f) * rstd;
+        s_const[c] = sc;
+        s_const[C + c] = (beta != nullptr ? __ldg(beta + c) : 0.f) - (float)mean * sc;
+        if (blockIdx.x == 0) {
+            mean_out[c] = (float)mean;
+            rstd_out[c] = rstd;
+            if (running_mean != nullptr) {
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * unbias);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
+    __syncthreads();
     if (pl < PL) {
         float sc[8], sh[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int c = c0 + e;
-            const double st1 = stats[c], st2 = stats[C + c];
-            const double mean = st1 * inv_count;
-            double var = st2 * inv_count - mean * mean;
-            if (var < 0.0) var = 0.0;
-            const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-            sc[e] = (gamma != nullptr ? __ldg(gamma + c) : 1.f) * rstd;
-            sh[e] = (beta != nullptr ? __ldg(beta + c) : 0.f) - (float)mean * sc[e];
-            if (blockIdx.x == 0 && pl == 0) {
-                mean_out[c] = (float)mean;
-                rstd_out[c] = rstd;
-                if (running_mean != nullptr) {
-                    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-                    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * unbias);
-                }
-            }
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
+        for (int e = 0; e < 8; ++e) { sc[e] = s_const[c0 + e]; sh[e] = s_const[C + c0 + e]; }
         const int64_t step = (int64_t)gridDim.x * PL;
         for (int64_t m0 = (int64_t)blockIdx.x * PL + pl; m0 < M; m0 += U * step) {
-            Raw8<T> ry[U], rr[U];
+            Raw8<T> ry[U], rr[kRes ? U : 1];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t m = m0 + u * step;
                 if (m < M) {
                     ry[u].ld(y + m * ldy + c0);
-                    if (res != nullptr) rr[u].ld(res + m * ldr + c0);
+                    if (kRes) rr[u].ld(res + m * ldr + c0);
                 }
             }
 #pragma unroll
@@ -68,7 +73,7 @@ bn_finalize_apply_kernel(double* stats, double inv_count, double unbias, const f
                 ry[u].get(v);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
-                if (res != nullptr) {
+                if (kRes) {
                     float w[8];
                     rr[u].get(w);
 #pragma unroll
@@ -115,10 +120,11 @@ extern "C" int tss_bn_finalize_apply(double* stats, int64_t count, const float* 
     TSS_DISPATCH_DTYPE(dtype, "bn_finalize_apply", {
         constexpr int U = sizeof(T) == 2 ? 4 : 2;
         int64_t grid = ceil_div64(M, (int64_t)PL * U);
-        const int64_t cap = (int64_t)tss_num_sms() * 8;
+        const int64_t cap = (int64_t)tss_num_sms() * 4;          // the resident CTAs (64 registers): the prologue runs once per CTA
         if (grid > cap) grid = cap;
         if (grid < 1) grid = 1;
-        tss_launch(bn_finalize_apply_kernel<T, U>, (unsigned)grid, threads, 0, (cudaStream_t)stream, stats,
+        auto kern = res != nullptr ? bn_finalize_apply_kernel<T, U, true> : bn_finalize_apply_kernel<T, U, false>;
+        tss_launch(kern, (unsigned)grid, threads, (size_t)2 * C * sizeof(float), (cudaStream_t)stream, stats,
                    1.0 / (double)count, unbias, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, mean,
                    rstd, ticket, (int)clear_n, (const T*)y, (const T*)res, (T*)z, M, C, ldy, ldr, ldz, flags & TSS_EPI_RELU, PL);
         TSS_LAUNCH_CHECK("bn_finalize_apply");

@@ -189,8 +189,8 @@ FUSE_PPM = gate('FUSE_PPM')
 # ... in eval mode only (folded BatchNorm): 7 launches less per inference forward (bs1 1024x2048: 2366 -> 2425 FPS on B200)
 FUSE_PPM_EVAL = gate('FUSE_PPM_EVAL')
 # BatchNorm finalize folded into the apply kernel (csrc/bn_fused.cu): one launch less per layer on the forward
-# chain (44 per step).  Validated on the B200, slower in the step (the fp64 statistics arithmetic in every CTA costs more
-# than the 44 tiny launches): off unless TSS_FUSE_BNFIN=1.
+# chain (44 per step).  Validated on the B200 (the whole GPU suite passes with the gate on), still slower in the step with
+# the constants derived once per CTA (3.204 vs 3.185 ms; per thread: 4.19 vs 3.80): off unless TSS_FUSE_BNFIN=1.
 FUSE_BNFIN = gate('FUSE_BNFIN')
 # Inside a bottleneck, conv1's BatchNorm + ReLU applied by conv2 (depthwise) while it reads its input tile
 # (csrc/dwconv_bnin.cu): the expanded activation is never materialised, conv1's apply pass disappears.

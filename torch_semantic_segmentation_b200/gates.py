@@ -13,7 +13,7 @@ DEFAULTS = {
     'FUSE_BNRED_EXT': True,     # ... also stride-2 depthwise dgrad and more single-consumer pairs (r2: 4.58 -> 4.48 ms/step)
     'FUSE_BNAPPLY': False,      # BatchNorm-backward apply in the operand producer of the pointwise dgrad
     'FUSE_BNAPPLY_DW': False,   # ... and in the stride-1 depthwise dgrad
-    'FUSE_BNFIN': False,        # BatchNorm finalize inside the apply kernel
+    'FUSE_BNFIN': False,        # BatchNorm finalize inside the apply kernel (third version, constants once per CTA through shared memory: 3.204 vs 3.185 ms/step)
     'FUSE_BNIN': True,          # a block's BatchNorm applied by the depthwise conv that reads it (r2: 3.67 -> 3.58 ms/step)
     'FUSE_BNIN_PW': False,      # ... by the tensor-core pointwise conv that reads it (r2: 3.88 vs 3.67 ms/step, not kept)
     'FUSE_PPM': False,          # pyramid-pooling branches as grouped launches (training: 4.60 vs 4.58 ms/step, not kept)
