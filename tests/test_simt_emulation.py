@@ -698,6 +698,12 @@ def test_whole_training_step_and_evaluation_on_the_emulation(tmp_path):
         seen.add(name)
         for k, v in kw.items():
             if isinstance(v, torch.Tensor) and v.numel() > 0:
+                if v.dim() == 1 and v.is_floating_point() and isinstance(kw.get('dz'), torch.Tensor):
+                    # per-channel sums of a gradient that is mean-free in exact arithmetic are rounding noise on both sides:
+                    # differences are measured against what was summed, not against the (vanishing) result
+                    floor = 1e-5 * float(kw['dz'].float().abs().sum()) / max(v.numel(), 1)
+                    if float((v.double() - clones[k].double()).abs().max()) < floor:
+                        continue
                 e = rel(v, clones[k])
                 if e > (2e-3 if (v.dtype == torch.float32 and v.dim() == 1) else 2e-4):
                     bad.append((name, k, e, tuple(v.shape)))
