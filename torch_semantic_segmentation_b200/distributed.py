@@ -59,7 +59,7 @@ def shard_range(n_items, world_size, rank):
 class GradientAllReducer:
     """Bucketed, overlapped SUM all-reduce of a ``FlatAdamW`` gradient arena."""
 
-    def __init__(self, optimizer, num_buckets=4, process_group=None):
+    def __init__(self, optimizer, num_buckets=4, process_group=None, tail_elems=None):
         self.opt = optimizer
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -72,8 +72,17 @@ class GradientAllReducer:
         target = (total + num_buckets - 1) // num_buckets
         self.buckets = []          # [lo, hi, n_params, n_ready, launched]
         self.bucket_of = {}
-        hi, lo, count = total, total, 0
+        # ... and the parameters of the first layers (the last `tail_elems` elements to become ready: the stem and the
+        # learning-to-downsample convs, ~7 k values) get a bucket of their own.  Whatever bucket holds them can only be
+        # reduced after the very last weight-gradient kernel, so its all-reduce is the one that is never hidden: it should
+        # be a latency-only message, not a quarter of the arena.
+        if tail_elems is None:
+            tail_elems = int(os.environ.get('TSS_DDP_TAIL', '16384'))       # 0: no separate tail bucket (A/B)
+        hi, lo, count, tail_cut = total, total, 0, False
         for p, off, n in reversed(optimizer.slots):
+            if not tail_cut and count > 0 and off + n <= tail_elems:
+                self.buckets.append([lo, hi, count, 0, False])
+                hi, count, tail_cut = lo, 0, True
             lo = off
             count += 1
             self.bucket_of[id(p)] = len(self.buckets)
