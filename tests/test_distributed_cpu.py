@@ -71,7 +71,7 @@ def _train_worker(rank, world, port, out):
     model = make(rank)                      # different init per rank: the broadcast must fix that
     broadcast_parameters(model)
     opt = FlatAdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
-    reducer = GradientAllReducer(opt, num_buckets=4).install()
+    reducer = GradientAllReducer(opt, num_buckets=4, tail_elems=int(os.environ.get('TSS_TEST_DDP_TAIL', '0'))).install()
     assert reducer.enabled and len(reducer.buckets) >= 2
     covered = sorted((b[0], b[1]) for b in reducer.buckets)
     assert covered[0][0] == 0 and covered[-1][1] == opt.numel
@@ -173,11 +173,15 @@ def _run(worker, tmp_path):
 
 
 @pytest.mark.timeout(600)
-def test_bucketed_gradient_allreduce_world2(tmp_path):
+@pytest.mark.parametrize('tail', [0, 16384])
+def test_bucketed_gradient_allreduce_world2(tmp_path, monkeypatch, tail):
+    monkeypatch.setenv('TSS_TEST_DDP_TAIL', str(tail))       # (spawned workers inherit the environment)
     r = _run(_train_worker, tmp_path)
     assert r['err'] < 1e-5, r
     assert r['same'], 'ranks diverged after one optimizer step'
     assert r['buckets'] >= 2 and r['launched_in_backward'] >= 1      # overlap: buckets leave during backward
+    if tail:
+        assert r['buckets'] >= 3      # the first layers' parameters in a bucket of their own
 
 
 @pytest.mark.timeout(600)

@@ -72,12 +72,14 @@ class GradientAllReducer:
         target = (total + num_buckets - 1) // num_buckets
         self.buckets = []          # [lo, hi, n_params, n_ready, launched]
         self.bucket_of = {}
-        # ... and the parameters of the first layers (the last `tail_elems` elements to become ready: the stem and the
-        # learning-to-downsample convs, ~7 k values) get a bucket of their own.  Whatever bucket holds them can only be
+        # ... and, optionally, the parameters of the first layers (the last `tail_elems` elements to become ready: the stem and
+        # the learning-to-downsample convs, ~7 k values) get a bucket of their own.  Whatever bucket holds them can only be
         # reduced after the very last weight-gradient kernel, so its all-reduce is the one that is never hidden: it should
         # be a latency-only message, not a quarter of the arena.
         if tail_elems is None:
-            tail_elems = int(os.environ.get('TSS_DDP_TAIL', '16384'))       # 0: no separate tail bucket (A/B)
+            # off by default: built after the round's last multi-GPU visit and never measured on NVLink -- and every bucket
+            # launch joins the weight-gradient lane into the main stream, so an extra bucket is not free
+            tail_elems = int(os.environ.get('TSS_DDP_TAIL', '0'))           # e.g. 16384: the first layers get their own bucket
         hi, lo, count, tail_cut = total, total, 0, False
         for p, off, n in reversed(optimizer.slots):
             if not tail_cut and count > 0 and off + n <= tail_elems:
